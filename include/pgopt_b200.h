@@ -1,0 +1,151 @@
+/* pgopt_b200.h — C ABI of libpgopt_b200.so: the B200-native (sm_100a) replacement for the
+ * data-parallel hot path of TUM-ITR/PGopt.
+ *
+ * The reference has no FFI/plugin boundary: its boundary is the Julia function signatures
+ *   particle_Gibbs(u, y, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist, g, R; x_prim)
+ *                                                   Julia/src/particle_Gibbs.jl:114
+ *   systematic_resampling(W, N)                     Julia/src/particle_Gibbs.jl:17
+ *   MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T)   Julia/src/particle_Gibbs.jl:56
+ *   solve_PG_OCP_Ipopt(...; x_vec_0, v_vec, e_vec, u_init)  Julia/src/optimal_control_Ipopt.jl:37
+ * A thin `ccall` shim (julia/PGoptB200.jl) keeps those signatures and calls the
+ * entry points below.  Plain pointers and sizes only; all matrices are column-major FP64 exactly as
+ * Julia passes them; indices returned to the caller are 1-based Int64 like the reference's.
+ * Every function returns 0 on success or a PGB_ERR_* code; pgb_last_error() gives the message.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * PGB_ERR_CUDA.
+ *
+ * Ownership: the library owns all device memory behind a handle; host buffers are borrowed for
+ * the duration of a call.  A handle is bound to one device and one stream and is not re-entrant;
+ * distinct handles may be driven from distinct host threads.
+ */
+#ifndef PGOPT_B200_H
+#define PGOPT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGB_MAX_Z 8 /* max augmented dimension n_u + n_x of the Hilbert-space basis */
+
+enum {
+  PGB_OK = 0,
+  PGB_ERR_INVALID = 1,     /* bad argument / unsupported configuration */
+  PGB_ERR_CUDA = 2,        /* CUDA runtime error (no device, OOM, launch failure) */
+  PGB_ERR_NOT_POSDEF = 3,  /* Cholesky failed (Julia: PosDefException) */
+  PGB_ERR_STATE = 4        /* call sequence error (data/prior/state not set) */
+};
+
+/* basis-function families: the C ABI cannot take Julia closures, so phi is a descriptor */
+enum {
+  PGB_BASIS_KNOWN_VB = 0,  /* examples/PG_OCP_known_basis_functions_Altro.jl:34  (n_x=2,n_u=1,n_phi=5) */
+  PGB_BASIS_HILBERT_GP = 1 /* examples/PG_OCP_generic_basis_functions_Altro.jl:52-99 (phi_sampling) */
+};
+
+/* status bits reported by pgb_get_status (sticky per handle until cleared) */
+enum {
+  PGB_STATUS_RESAMPLE_OVERRUN = 1, /* q_N < u_i: the reference raises BoundsError at :28 */
+  PGB_STATUS_INDEX_ZERO = 2,       /* u_1 <= 0: the reference returns index 0 */
+  PGB_STATUS_NONFINITE = 4,        /* NaN/Inf weight or weight sum */
+  PGB_STATUS_NOT_POSDEF = 16
+};
+
+typedef struct {
+  int32_t device;     /* CUDA device ordinal */
+  int32_t n_x, n_u, n_y, n_phi;
+  int32_t basis;      /* PGB_BASIS_* */
+  /* Hilbert-space basis over z = [u; x]: for augmented dimension k, basis row i (0-based) uses the
+   * 1-based frequency j = (i / hg_stride[k]) % hg_count[k] + 1; strides must be the row-major
+   * mixed radix of hg_count (dimension 0 slowest), which is what the reference constructs
+   * (examples/PG_OCP_generic_basis_functions_Altro.jl:59-82). */
+  int32_t hg_count[PGB_MAX_Z];
+  int32_t hg_stride[PGB_MAX_Z];
+  double hg_L[PGB_MAX_Z];
+  int64_t N;          /* particles (slot N is the conditioned trajectory)  particle_Gibbs.jl:160 */
+  int64_t T;          /* training length */
+  int32_t n_chains;   /* independent PG chains batched on this handle (>= 1) */
+  int32_t keep_w_history; /* 1: keep w[t,:] for every t (tests; costs T*N*8 bytes per chain) */
+} pgb_config;
+
+typedef struct pgb_handle pgb_handle;
+
+const char* pgb_version(void);
+const char* pgb_last_error(const pgb_handle* h); /* h may be NULL: last create/standalone error */
+
+int pgb_create(pgb_handle** out, const pgb_config* cfg);
+void pgb_destroy(pgb_handle* h);
+
+/* u: n_u x T, y: n_y x T (shared by all chains)                      particle_Gibbs.jl:114 args 1,2 */
+int pgb_set_data(pgb_handle* h, const double* u, const double* y);
+/* g(x,u) = C*x with C n_y x n_x; R n_y x n_y measurement-noise covariance   :193-197 */
+int pgb_set_measurement(pgb_handle* h, const double* C, const double* R);
+/* x_init_dist = MvNormal(mean, cov): pass mean and the lower Cholesky factor of cov   :163-165 */
+int pgb_set_init_dist(pgb_handle* h, const double* mean, const double* chol_lower);
+/* MNIW prior: V diagonal (n_phi), Lambda_Q n_x x n_x, ell_Q              :56, :226 */
+int pgb_set_prior(pgb_handle* h, const double* V_diag, const double* Lambda_Q, double ell_Q);
+/* chain state: A n_x x n_phi, Q n_x x n_x, x_prim n_x x T (NULL = zeros, :126-128);
+ * sweep_index = k of the next sweep (1 selects the plain bootstrap filter branch, :183-189). */
+int pgb_set_state(pgb_handle* h, int32_t chain, const double* A, const double* Q, const double* x_prim,
+                  int64_t sweep_index);
+int pgb_get_state(pgb_handle* h, int32_t chain, double* A, double* Q, double* x_prim, int64_t* sweep_index);
+
+/* random streams: counter-based Philox4x32-10 (chain c uses stream id chain_base + c) ... */
+int pgb_set_rng_philox(pgb_handle* h, uint64_t seed, uint32_t chain_base);
+/* ... or pre-drawn streams for the NEXT sweep of chain `chain` (parity testing; layout = order of
+ * consumption in the reference): Z0[n_x*(N-1)], Ures[T], Z[T][n_x*N], Uanc[T], Ustar,
+ * bartlett[n_x*n_x] (lower, column-major), Xmn[n_x*n_phi].  Host pointers, copied. */
+int pgb_set_rng_injected(pgb_handle* h, int32_t chain, const double* Z0, const double* Ures, const double* Z,
+                         const double* Uanc, double Ustar, const double* bartlett, const double* Xmn);
+
+/* Run n_sweeps full PG sweeps (CPF-AS filter, trace, statistics, MNIW draw) on all chains,
+ * entirely on the device.  With injected streams n_sweeps must be 1.      particle_Gibbs.jl:154-227 */
+int pgb_sweep(pgb_handle* h, int64_t n_sweeps);
+/* Split form for tests / benchmarks: filter (+ trace + statistics) only, and the MNIW draw only. */
+int pgb_sweep_filter(pgb_handle* h);
+int pgb_sweep_mniw(pgb_handle* h);
+
+/* The whole sampler (particle_Gibbs.jl:114-237) for chain-batched handles: runs
+ * K_total = K_b + 1 + (K-1)(k_d+1) sweeps and stores K samples per chain.  Outputs (host, may be
+ * NULL): A_s[chain][k][n_x*n_phi], Q_s[chain][k][n_x*n_x], w_s[chain][k][N], x_s[chain][k][n_x*N]
+ * (x_m1 column-major n_x x N), u_m1[n_u]. */
+int pgb_particle_gibbs(pgb_handle* h, int64_t K, int64_t K_b, int64_t k_d, double* A_s, double* Q_s, double* w_s,
+                       double* x_s, double* u_m1);
+
+/* current PG_sample fields of a chain (PGopt.jl:23-29; particle_Gibbs.jl:204-208): the (A, Q) the
+ * last filter ran with, w[T,:], x_pf[:,:,T], u[:,T] */
+int pgb_get_sample(pgb_handle* h, int32_t chain, double* A, double* Q, double* w_m1, double* x_m1, double* u_m1);
+/* test-only: a[T x N] (row t = step t, 1-based ancestors, row 0 zero), x[T][N][n_x] (= x_pf[:,n,t]),
+ * w[T][N] (needs keep_w_history).  Any pointer may be NULL. */
+int pgb_get_history(pgb_handle* h, int32_t chain, int64_t* a, double* x, double* w);
+int pgb_get_stats(pgb_handle* h, int32_t chain, double* Phi, double* Psi, double* Sigma, int64_t* star);
+/* status bits (PGB_STATUS_*), number of resampling steps that needed the exact serial fallback,
+ * and number of exact scans performed.  clear != 0 resets them. */
+int pgb_get_status(pgb_handle* h, int32_t chain, int32_t* status_bits, int64_t* n_fallback, int64_t* n_scans,
+                   int32_t clear);
+int pgb_synchronize(pgb_handle* h);
+
+/* Stand-alone helpers matching the exported Julia functions; host buffers in and out. */
+/* systematic_resampling(W, N) with rnd = the rand() of :21; idx is 1-based.  *status gets PGB_STATUS_* bits. */
+int pgb_systematic_resampling(int32_t device, const double* W, int64_t n_w, int64_t n_draw, double rnd,
+                              int64_t* idx, int32_t* status);
+/* MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T) with the Bartlett factor and the matrix-normal
+ * normals injected (bartlett/Xmn non-NULL) or drawn from Philox (seed, sweep_index). */
+int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Phi, const double* Psi,
+                    const double* Sigma, const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t T,
+                    const double* bartlett, const double* Xmn, uint64_t seed, uint32_t chain, uint32_t sweep_index,
+                    double* A_out, double* Q_out);
+
+/* Scenario sampling + forward rollout (optimal_control_Ipopt.jl:47-83,114-125) for K posterior
+ * samples.  cfg supplies the model (N = particles per sample, T ignored).  Inputs (host):
+ * A[K][n_x*n_phi], Q[K][n_x*n_x], w_m1[K][N], x_m1[K][n_x*N], u_m1[K][n_u], C, Le (lower factor the
+ * measurement noise is unwhitened with: [R] for the reference's scalar-R call, chol(R) otherwise),
+ * u_init[n_u*H].  Outputs (host, may be NULL): x0[K][n_x], v[K][H][n_x], e[K][H][n_y],
+ * X[K][H+1][n_x], Y[K][H][n_y].  Scenario k uses Philox stream (seed, chain = k_offset + k). */
+int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q, const double* w_m1,
+                const double* x_m1, const double* u_m1, const double* C, const double* Le, const double* u_init,
+                uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e, double* X, double* Y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGOPT_B200_H */

@@ -1,0 +1,116 @@
+/* pg_oracle.h — CPU restatement of PGopt's particle-Gibbs hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * This is the parity oracle: a plain, single-threaded C restatement of
+ *   Julia/src/particle_Gibbs.jl:17-34    systematic_resampling
+ *   Julia/src/particle_Gibbs.jl:56-81    MNIW_sample
+ *   Julia/src/particle_Gibbs.jl:114-237  particle_Gibbs (CPF-AS sweep, trace, statistics)
+ *   Julia/src/optimal_control_Ipopt.jl:47-83,114-125   scenario sampling + forward rollout
+ * and of the two basis definitions in
+ *   Julia/examples/PG_OCP_known_basis_functions_Altro.jl:34
+ *   Julia/examples/PG_OCP_generic_basis_functions_Altro.jl:52-99
+ * (paths relative to /root/reference).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it; the product never does.
+ *
+ * PARITY UNPINNED: the reference has no tests, golden vectors or fixtures, and neither Julia nor
+ * MATLAB exists in the build image or on the GPU box, so this restatement cannot be checked
+ * against outputs of the reference itself.  It is pinned only by hand-traced known-answer cases
+ * derived from the reference source (tests/test_oracle_kat.py) and by libm cross-checks.  The
+ * arithmetic the reference delegates to Distributions.jl / OpenBLAS / Julia Base (summation order
+ * of sum(), gemm order, exp/sin/cos last bits, LU vs Cholesky) is not pinned by anything upstream;
+ * every such order is fixed HERE and documented next to the code.
+ */
+#ifndef PG_ORACLE_H
+#define PG_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORC_BASIS_KNOWN_VB = 0, ORC_BASIS_HILBERT_GP = 1 };
+#define ORC_MAX_Z 8
+
+typedef struct {
+  int32_t basis;
+  int32_t n_x, n_u, n_y, n_phi;
+  /* Hilbert-space GP basis over z = [u; x] (n_z = n_u + n_x dims).  For augmented dimension k,
+   * basis row i (0-based) uses the 1-based frequency index j = (i / stride[k]) % count[k] + 1. */
+  int32_t count[ORC_MAX_Z];
+  int32_t stride[ORC_MAX_Z];
+  double L[ORC_MAX_Z];
+} orc_model;
+
+typedef struct {
+  int32_t philox;      /* 1: counter-based streams (seed, chain); 0: injected arrays below */
+  uint64_t seed;
+  uint32_t chain;
+  /* injected streams for ONE sweep (layout = order of consumption in the reference) */
+  const double* Z0;    /* [n_x*(N-1)]  initial-state normals, particle-major           :163-165 */
+  const double* Ures;  /* [T]  index t (0-based step t>=1 used)                         :172|185 */
+  const double* Z;     /* [T][n_x*N]  step t (>=1) normals, particle-major (N-1 or N)   :175|188 */
+  const double* Uanc;  /* [T]                                                          :181 */
+  double Ustar;        /*                                                              :213 */
+  const double* bartlett; /* [n_x*n_x] lower-triangular Bartlett factor, column-major   :73 */
+  const double* Xmn;      /* [n_x*n_phi] matrix-normal normals, column-major            :77 */
+} orc_streams;
+
+/* math helpers (vectorised wrappers over pgb_math.h, for tests) */
+void orc_vexp(const double* x, double* y, int64_t n);
+void orc_vlog(const double* x, double* y, int64_t n);
+void orc_vsin(const double* x, double* y, int64_t n);
+void orc_vcos(const double* x, double* y, int64_t n);
+void orc_vnormal_pairs(uint64_t seed, uint32_t purpose, uint32_t chain, uint32_t sweep, uint32_t t,
+                       int64_t npairs, double* z);
+int orc_selftest(void);
+
+double orc_pairwise_sum(const double* v, int64_t n);
+
+/* returns 0, or 1 when the reference would raise BoundsError (q_N < u_i), or 2 for idx 0 */
+int orc_systematic_resampling(const double* W, int64_t n_w, int64_t n_draw, double rnd,
+                              int64_t* idx /* 1-based */);
+
+void orc_phi(const orc_model* m, const double* x, const double* u, double* phi);
+
+int orc_cholesky_lower(double* A, int n); /* in place, column-major, upper part zeroed */
+
+/* One PG sweep (particle_Gibbs.jl:155-226 for a single k).  `first` selects the k==1 branch.
+ * Histories are caller-allocated (may be NULL): a[T*N] (1-based, row t; row 0 unused),
+ * x_pf[T][n_x][N]... see pg_oracle.c for layouts.  x_prim is updated in place. */
+int orc_sweep(const orc_model* m, int64_t N, int64_t T, const double* u /*n_u x T*/,
+              const double* y /*n_y x T*/, const double* C /*n_y x n_x*/, const double* R /*n_y x n_y*/,
+              const double* x0_mean, const double* x0_chol /*lower n_x x n_x*/,
+              const double* A, const double* Q, double* x_prim /*n_x x T*/, int first,
+              const orc_streams* s, uint32_t sweep_index,
+              int64_t* a_hist /*T x N or NULL*/, double* x_hist /*T x n_x x N or NULL*/,
+              double* w_hist /*T x N or NULL*/, double* w_last /*N*/, double* x_last /*n_x x N*/,
+              double* Phi, double* Psi, double* Sigma, int64_t* star_out);
+
+int orc_mniw_sample(int n_x, int n_phi, const double* Phi, const double* Psi, const double* Sigma,
+                    const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t Tm1,
+                    const orc_streams* s, uint32_t sweep_index, double* A_out, double* Q_out);
+
+/* Full sampler (particle_Gibbs.jl:114-237) with Philox streams. Outputs K samples. */
+int orc_particle_gibbs(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y,
+                       const double* C, const double* R, const double* x0_mean, const double* x0_chol,
+                       const double* A_init, const double* Q_init, const double* V_diag,
+                       const double* Lambda_Q, double ell_Q, int64_t K, int64_t K_b, int64_t k_d,
+                       uint64_t seed, uint32_t chain, double* x_prim /* n_x x T in/out */,
+                       double* A_s /*K x n_x x n_phi*/, double* Q_s, double* w_s /*K x N*/,
+                       double* x_s /*K x n_x x N*/);
+
+/* Scenario sampling + rollout (optimal_control_Ipopt.jl:47-83,114-125).
+ * Le = lower factor L with e = L*z.  NOTE (reference quirk, kept): the reference builds
+ * MvNormal(zeros(n_y), R) (:79); with the examples' *scalar* R = 0.1 Distributions.jl 0.25 reads a
+ * scalar second argument as a standard deviation, so e = R*z (Le = [R]); with a matrix R it is a
+ * covariance (Le = chol(R).L).  The caller (shim) makes that choice and passes Le. */
+int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const double* A /*K x n_x x n_phi*/,
+                const double* Q /*K x n_x x n_x*/, const double* w_m1 /*K x N*/,
+                const double* x_m1 /*K x n_x x N*/, const double* u_m1 /*K x n_u*/,
+                const double* C, const double* Le, const double* u_init /*n_u x H*/,
+                uint64_t seed, double* x0 /*K x n_x*/, double* v /*K x H x n_x*/,
+                double* e /*K x H x n_y*/, double* X /*K x (H+1) x n_x*/, double* Y /*K x H x n_y*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

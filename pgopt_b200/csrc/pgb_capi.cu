@@ -1,0 +1,814 @@
+// pgb_capi.cu — host side of libpgopt_b200.so: the C ABI of include/pgopt_b200.h, device memory
+// management and the launch sequences.  No torch types, no CPU compute path: every entry point that
+// computes needs a CUDA device and fails with PGB_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pgopt_b200.h"
+#include "pgb_mniw.cuh"
+#include "pgb_rollout.cuh"
+
+using namespace pgb;
+
+static thread_local std::string g_last_error;
+
+struct pgb_handle {
+  pgb_config cfg;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  std::string err;
+  FilterDev fd;
+  MniwDev md;
+  bool have_data = false, have_meas = false, have_init = false, have_prior = false, have_rng = false;
+  std::vector<char> have_state;
+  int64_t sweep_index = 1;
+  // device
+  double *d_u = nullptr, *d_y = nullptr, *d_Q = nullptr, *d_Vdiag = nullptr, *d_LambdaQ = nullptr;
+  double *d_Z0 = nullptr, *d_Z = nullptr, *d_Ures = nullptr, *d_Uanc = nullptr, *d_Ustar = nullptr;
+  double *d_bart = nullptr, *d_Xmn = nullptr;
+  int32_t* d_star_idx = nullptr;
+  int64_t* d_star_out = nullptr;
+  long long* d_counters_main = nullptr;
+  long long* d_counters_side = nullptr;
+  std::vector<double> h_u;  // host copy of u (for u_m1)
+  // the (A, Q) the last filter pass ran with (sample fields, particle_Gibbs.jl:204-205)
+  double *d_A_used = nullptr, *d_Q_used = nullptr;
+  bool injected_ready = false;
+};
+
+static int set_err(pgb_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CK(h, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return set_err(h, PGB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+static cudaError_t dalloc(pgb_handle* h, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+  if (e != cudaSuccess) return e;
+  if (h) h->allocs.push_back(q);
+  if (zero) {
+    e = cudaMemset(q, 0, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+  }
+  *p = (T*)q;
+  return cudaSuccess;
+}
+
+extern "C" const char* pgb_version(void) { return "pgopt_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* pgb_last_error(const pgb_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+static cudaError_t alloc_scanws(pgb_handle* h, ScanWS* ws, int64_t N, int nc, long long** counters) {
+  cudaError_t e;
+  memset(ws, 0, sizeof(*ws));
+  ws->N = N;
+  ws->nt = (int)((N + TILE - 1) / TILE);
+  const int64_t nt = ws->nt;
+#define A_(field, count) if ((e = dalloc(h, &ws->field, (size_t)(count))) != cudaSuccess) return e;
+  A_(S, nc) A_(tsum, nc * nt) A_(tile_prefix, nc * (nt + 1)) A_(thr_ex, nc * nt * TPB) A_(tile_agg, nc * nt)
+  A_(tile_ex, nc * (nt + 1)) A_(recs, nc * nt * RMAX) A_(crec, (int64_t)nc * CMAX) A_(seeds, (int64_t)nc * (CMAX + 1))
+  A_(qin_fb, nc * nt * TPB) A_(ticket, nc) A_(flag, nc) A_(pend, nc) A_(counters, 2 * nc)
+#undef A_
+  if (counters) *counters = ws->counters;
+  return cudaSuccess;
+}
+
+static int validate_cfg(const pgb_config* c) {
+  if (!c) return set_err(nullptr, PGB_ERR_INVALID, "config is NULL");
+  if (c->n_x < 1 || c->n_x > 4) return set_err(nullptr, PGB_ERR_INVALID, "n_x must be 1..4 (got %d)", c->n_x);
+  if (c->n_u < 1 || c->n_u > 4) return set_err(nullptr, PGB_ERR_INVALID, "n_u must be 1..4 (got %d)", c->n_u);
+  if (c->n_y < 1 || c->n_y > 4) return set_err(nullptr, PGB_ERR_INVALID, "n_y must be 1..4 (got %d)", c->n_y);
+  if (c->basis == PGB_BASIS_KNOWN_VB) {
+    if (c->n_x != 2 || c->n_u != 1 || c->n_phi != 5)
+      return set_err(nullptr, PGB_ERR_INVALID, "KNOWN_VB basis needs n_x=2, n_u=1, n_phi=5");
+  } else if (c->basis == PGB_BASIS_HILBERT_GP) {
+    int nz = c->n_x + c->n_u;
+    if (nz > PGB_MAX_Z) return set_err(nullptr, PGB_ERR_INVALID, "n_x + n_u > %d", PGB_MAX_Z);
+    int64_t stride = 1;
+    for (int k = nz - 1; k >= 0; --k) {
+      if (c->hg_count[k] < 1 || c->hg_count[k] > MAXC)
+        return set_err(nullptr, PGB_ERR_INVALID, "hg_count[%d] must be 1..%d", k, MAXC);
+      if (c->hg_stride[k] != stride)
+        return set_err(nullptr, PGB_ERR_INVALID, "hg_stride must be the row-major mixed radix of hg_count (dim %d)", k);
+      if (!(c->hg_L[k] > 0.0)) return set_err(nullptr, PGB_ERR_INVALID, "hg_L[%d] must be > 0", k);
+      stride *= c->hg_count[k];
+    }
+    if (stride != c->n_phi) return set_err(nullptr, PGB_ERR_INVALID, "n_phi != prod(hg_count)");
+  } else {
+    return set_err(nullptr, PGB_ERR_INVALID, "unknown basis id %d (arbitrary closures are not supported)", c->basis);
+  }
+  return PGB_OK;
+}
+
+static void fill_model(FilterDev& fd, const pgb_config* c) {
+  fd.n_x = c->n_x; fd.n_u = c->n_u; fd.n_y = c->n_y; fd.n_phi = c->n_phi; fd.basis = c->basis;
+  fd.n_z = c->n_x + c->n_u;
+  if (c->basis == PGB_BASIS_HILBERT_GP) {
+    const double PI = 3.141592653589793;
+    for (int k = 0; k < fd.n_z; ++k) {
+      fd.hg_count[k] = c->hg_count[k];
+      fd.hg_L[k] = c->hg_L[k];
+      volatile double sq = std::sqrt(c->hg_L[k]);
+      fd.hg_lsi[k] = 1.0 / sq;  // L_sqrt_inv = 1 ./ sqrt.(L)   (generic example :85)
+      for (int j = 0; j < c->hg_count[k]; ++j) {
+        volatile double num = PI * (double)(j + 1);  // pi .* j_vec ./ (2 .* L)   (:86)
+        volatile double den = 2.0 * c->hg_L[k];
+        fd.hg_pij2l[k][j] = num / den;
+      }
+    }
+  }
+}
+
+extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
+  if (!out) return set_err(nullptr, PGB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = validate_cfg(cfg);
+  if (rc) return rc;
+  if (cfg->N < 2 || cfg->T < 2 || cfg->n_chains < 1)
+    return set_err(nullptr, PGB_ERR_INVALID, "need N >= 2, T >= 2, n_chains >= 1");
+  if (cfg->N >= (1ll << 31) - TILE) return set_err(nullptr, PGB_ERR_INVALID, "N too large for Int32 ancestors");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s); pgopt_b200 has no CPU fallback",
+                   cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return set_err(nullptr, PGB_ERR_INVALID, "bad device ordinal %d", cfg->device);
+  pgb_handle* h = new pgb_handle();
+  h->cfg = *cfg;
+#define CKC(call)                                                                       \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      int rc_ = set_err(nullptr, PGB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+      pgb_destroy(h);                                                                   \
+      return rc_;                                                                       \
+    }                                                                                   \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const int64_t N = cfg->N, T = cfg->T;
+  const int nc = cfg->n_chains, nx = cfg->n_x, np = cfg->n_phi, nu = cfg->n_u, ny = cfg->n_y;
+  FilterDev& fd = h->fd;
+  memset(&fd, 0, sizeof(fd));
+  fill_model(fd, cfg);
+  fd.N = N; fd.T = T; fd.nc = nc;
+  fd.nt = (int)((N + TILE - 1) / TILE);
+  const int64_t nt = fd.nt;
+  CKC(dalloc(h, &h->d_u, (size_t)nu * T));
+  CKC(dalloc(h, &h->d_y, (size_t)ny * T));
+  fd.u = h->d_u; fd.y = h->d_y;
+  CKC(dalloc(h, &fd.A, (size_t)nc * nx * np));
+  CKC(dalloc(h, &h->d_Q, (size_t)nc * nx * nx));
+  CKC(dalloc(h, &h->d_A_used, (size_t)nc * nx * np));
+  CKC(dalloc(h, &h->d_Q_used, (size_t)nc * nx * nx));
+  CKC(dalloc(h, &fd.Lq, (size_t)nc * 16));
+  CKC(dalloc(h, &fd.c0, (size_t)nc));
+  CKC(dalloc(h, &fd.xprim, (size_t)nc * nx * T));
+  CKC(dalloc(h, &fd.xh, (size_t)nc * T * nx * N, false));
+  CKC(dalloc(h, &fd.ah, (size_t)nc * T * N, false));
+  CKC(cudaMemset(fd.ah, 0xff, (size_t)nc * T * N * sizeof(int32_t)));
+  CKC(dalloc(h, &fd.wbuf, (size_t)nc * N));
+  CKC(dalloc(h, &fd.ebuf, (size_t)nc * N));
+  CKC(dalloc(h, &fd.lwbuf, (size_t)nc * N));
+  CKC(dalloc(h, &fd.Fbuf, (size_t)nc * nx * N));
+  CKC(dalloc(h, &fd.waN, (size_t)nc * N));
+  if (cfg->keep_w_history) CKC(dalloc(h, &fd.whist, (size_t)nc * T * N));
+  CKC(dalloc(h, &fd.maxkey, (size_t)nc));
+  CKC(dalloc(h, &fd.status, (size_t)nc));
+  CKC(dalloc(h, &fd.S1, (size_t)nc));
+  CKC(dalloc(h, &fd.S3, (size_t)nc));
+  CKC(dalloc(h, &fd.tsum_e, (size_t)nc * nt));
+  CKC(dalloc(h, &fd.tsum_a, (size_t)nc * nt));
+  CKC(dalloc(h, &fd.ticket_e, (size_t)nc));
+  CKC(dalloc(h, &fd.ticket_a, (size_t)nc));
+  CKC(dalloc(h, &fd.utab_res, (size_t)nc * T, false));
+  CKC(dalloc(h, &fd.utab_anc, (size_t)nc * T, false));
+  CKC(dalloc(h, &fd.utab_star, (size_t)nc, false));
+  CKC(alloc_scanws(h, &fd.main, N, nc, &h->d_counters_main));
+  CKC(alloc_scanws(h, &fd.side, N, nc, &h->d_counters_side));
+  CKC(dalloc(h, &h->d_star_idx, (size_t)nc));
+  CKC(dalloc(h, &h->d_star_out, (size_t)nc));
+  // MNIW
+  MniwDev& md = h->md;
+  memset(&md, 0, sizeof(md));
+  md.nc = nc; md.n_x = nx; md.n_phi = np; md.Tm1 = T - 1;
+  CKC(dalloc(h, &h->d_Vdiag, (size_t)np));
+  CKC(dalloc(h, &h->d_LambdaQ, (size_t)nx * nx));
+  md.V_diag = h->d_Vdiag; md.Lambda_Q = h->d_LambdaQ;
+  CKC(dalloc(h, &md.zeta, (size_t)nc * nx * (T - 1)));
+  CKC(dalloc(h, &md.zb, (size_t)nc * np * (T - 1)));
+  CKC(dalloc(h, &md.Phi, (size_t)nc * nx * nx));
+  CKC(dalloc(h, &md.Psi, (size_t)nc * nx * np));
+  CKC(dalloc(h, &md.Sigma, (size_t)nc * np * np));
+  CKC(dalloc(h, &md.Ls, (size_t)nc * np * np));
+  CKC(dalloc(h, &md.Sinv, (size_t)nc * np * np));
+  CKC(dalloc(h, &md.Lv, (size_t)nc * np * np));
+  CKC(dalloc(h, &md.Mpost, (size_t)nc * nx * np));
+  CKC(dalloc(h, &md.Xn, (size_t)nc * nx * np));
+  CKC(dalloc(h, &md.LX, (size_t)nc * nx * np));
+  md.A = fd.A; md.Q = h->d_Q; md.Lq = fd.Lq; md.c0 = fd.c0; md.status = fd.status;
+  h->have_state.assign(nc, 0);
+  h->h_u.assign((size_t)nu * T, 0.0);
+#undef CKC
+  *out = h;
+  return PGB_OK;
+}
+
+extern "C" void pgb_destroy(pgb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+#define NEED(h) \
+  if (!h) return set_err(nullptr, PGB_ERR_INVALID, "handle is NULL"); \
+  CK(h, cudaSetDevice(h->cfg.device))
+
+extern "C" int pgb_set_data(pgb_handle* h, const double* u, const double* y) {
+  NEED(h);
+  if (!u || !y) return set_err(h, PGB_ERR_INVALID, "u/y NULL");
+  const size_t nu = (size_t)h->cfg.n_u * h->cfg.T, ny = (size_t)h->cfg.n_y * h->cfg.T;
+  CK(h, cudaMemcpyAsync(h->d_u, u, nu * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_y, y, ny * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  memcpy(h->h_u.data(), u, nu * 8);
+  h->have_data = true;
+  return PGB_OK;
+}
+
+static int host_chol(double* A, int n) {
+  for (int k = 0; k < n; ++k) {
+    double d = A[k + n * k];
+    if (!(d > 0.0)) return 1;
+    d = std::sqrt(d);
+    A[k + n * k] = d;
+    for (int i = k + 1; i < n; ++i) A[i + n * k] = A[i + n * k] / d;
+    for (int j = k + 1; j < n; ++j)
+      for (int i = j; i < n; ++i) A[i + n * j] = std::fma(-A[i + n * k], A[j + n * k], A[i + n * j]);
+  }
+  for (int j = 1; j < n; ++j)
+    for (int i = 0; i < j; ++i) A[i + n * j] = 0.0;
+  return 0;
+}
+
+extern "C" int pgb_set_measurement(pgb_handle* h, const double* C, const double* R) {
+  NEED(h);
+  if (!C || !R) return set_err(h, PGB_ERR_INVALID, "C/R NULL");
+  const int nx = h->cfg.n_x, ny = h->cfg.n_y;
+  memset(h->fd.C, 0, sizeof(h->fd.C));
+  memset(h->fd.R, 0, sizeof(h->fd.R));
+  memset(h->fd.Rchol, 0, sizeof(h->fd.Rchol));
+  for (int i = 0; i < ny * nx; ++i) h->fd.C[i] = C[i];
+  for (int i = 0; i < ny * ny; ++i) h->fd.R[i] = h->fd.Rchol[i] = R[i];
+  if (host_chol(h->fd.Rchol, ny)) return set_err(h, PGB_ERR_NOT_POSDEF, "R is not positive definite");
+  h->have_meas = true;
+  return PGB_OK;
+}
+
+extern "C" int pgb_set_init_dist(pgb_handle* h, const double* mean, const double* chol_lower) {
+  NEED(h);
+  if (!mean || !chol_lower) return set_err(h, PGB_ERR_INVALID, "mean/chol NULL");
+  const int nx = h->cfg.n_x;
+  memset(h->fd.x0_mean, 0, sizeof(h->fd.x0_mean));
+  memset(h->fd.x0_chol, 0, sizeof(h->fd.x0_chol));
+  for (int i = 0; i < nx; ++i) h->fd.x0_mean[i] = mean[i];
+  for (int i = 0; i < nx * nx; ++i) h->fd.x0_chol[i] = chol_lower[i];
+  h->have_init = true;
+  return PGB_OK;
+}
+
+extern "C" int pgb_set_prior(pgb_handle* h, const double* V_diag, const double* Lambda_Q, double ell_Q) {
+  NEED(h);
+  if (!V_diag || !Lambda_Q) return set_err(h, PGB_ERR_INVALID, "V_diag/Lambda_Q NULL");
+  CK(h, cudaMemcpyAsync(h->d_Vdiag, V_diag, (size_t)h->cfg.n_phi * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_LambdaQ, Lambda_Q, (size_t)h->cfg.n_x * h->cfg.n_x * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->md.ell_Q = ell_Q;
+  h->have_prior = true;
+  return PGB_OK;
+}
+
+extern "C" int pgb_set_state(pgb_handle* h, int32_t chain, const double* A, const double* Q, const double* x_prim,
+                             int64_t sweep_index) {
+  NEED(h);
+  const int nc = h->cfg.n_chains, nx = h->cfg.n_x, np = h->cfg.n_phi;
+  const int64_t T = h->cfg.T;
+  if (chain < 0 || chain >= nc) return set_err(h, PGB_ERR_INVALID, "bad chain %d", chain);
+  if (!A || !Q) return set_err(h, PGB_ERR_INVALID, "A/Q NULL");
+  if (sweep_index < 1) return set_err(h, PGB_ERR_INVALID, "sweep_index must be >= 1");
+  CK(h, cudaMemcpyAsync(h->fd.A + (size_t)chain * nx * np, A, (size_t)nx * np * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_Q + (size_t)chain * nx * nx, Q, (size_t)nx * nx * 8, cudaMemcpyHostToDevice, h->stream));
+  if (x_prim)
+    CK(h, cudaMemcpyAsync(h->fd.xprim + (size_t)chain * nx * T, x_prim, (size_t)nx * T * 8, cudaMemcpyHostToDevice, h->stream));
+  else
+    CK(h, cudaMemsetAsync(h->fd.xprim + (size_t)chain * nx * T, 0, (size_t)nx * T * 8, h->stream));
+  k_chain_params<<<(nc + 31) / 32, 32, 0, h->stream>>>(nc, nx, h->d_Q, h->fd.Lq, h->fd.c0, h->fd.status);
+  CK(h, cudaGetLastError());
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->sweep_index = sweep_index;
+  h->have_state[chain] = 1;
+  return PGB_OK;
+}
+
+extern "C" int pgb_get_state(pgb_handle* h, int32_t chain, double* A, double* Q, double* x_prim, int64_t* sweep_index) {
+  NEED(h);
+  const int nc = h->cfg.n_chains, nx = h->cfg.n_x, np = h->cfg.n_phi;
+  const int64_t T = h->cfg.T;
+  if (chain < 0 || chain >= nc) return set_err(h, PGB_ERR_INVALID, "bad chain %d", chain);
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (A) CK(h, cudaMemcpy(A, h->fd.A + (size_t)chain * nx * np, (size_t)nx * np * 8, cudaMemcpyDeviceToHost));
+  if (Q) CK(h, cudaMemcpy(Q, h->d_Q + (size_t)chain * nx * nx, (size_t)nx * nx * 8, cudaMemcpyDeviceToHost));
+  if (x_prim) CK(h, cudaMemcpy(x_prim, h->fd.xprim + (size_t)chain * nx * T, (size_t)nx * T * 8, cudaMemcpyDeviceToHost));
+  if (sweep_index) *sweep_index = h->sweep_index;
+  return PGB_OK;
+}
+
+extern "C" int pgb_set_rng_philox(pgb_handle* h, uint64_t seed, uint32_t chain_base) {
+  NEED(h);
+  h->fd.philox = 1; h->fd.seed = seed; h->fd.chain_base = chain_base;
+  h->md.philox = 1; h->md.seed = seed; h->md.chain_base = chain_base;
+  h->have_rng = true;
+  return PGB_OK;
+}
+
+extern "C" int pgb_set_rng_injected(pgb_handle* h, int32_t chain, const double* Z0, const double* Ures, const double* Z,
+                                    const double* Uanc, double Ustar, const double* bartlett, const double* Xmn) {
+  NEED(h);
+  const int nc = h->cfg.n_chains, nx = h->cfg.n_x, np = h->cfg.n_phi;
+  const int64_t N = h->cfg.N, T = h->cfg.T;
+  if (chain < 0 || chain >= nc) return set_err(h, PGB_ERR_INVALID, "bad chain %d", chain);
+  if (!Z0 || !Ures || !Z || !Uanc) return set_err(h, PGB_ERR_INVALID, "injected stream pointer NULL");
+  if (!h->d_Z0) {
+    CK(h, dalloc(h, &h->d_Z0, (size_t)nc * nx * (N - 1)));
+    CK(h, dalloc(h, &h->d_Z, (size_t)nc * T * nx * N));
+    CK(h, dalloc(h, &h->d_Ures, (size_t)nc * T));
+    CK(h, dalloc(h, &h->d_Uanc, (size_t)nc * T));
+    CK(h, dalloc(h, &h->d_Ustar, (size_t)nc));
+    CK(h, dalloc(h, &h->d_bart, (size_t)nc * nx * nx));
+    CK(h, dalloc(h, &h->d_Xmn, (size_t)nc * nx * np));
+  }
+  CK(h, cudaMemcpy(h->d_Z0 + (size_t)chain * nx * (N - 1), Z0, (size_t)nx * (N - 1) * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(h->d_Z + (size_t)chain * T * nx * N, Z, (size_t)T * nx * N * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(h->d_Ures + (size_t)chain * T, Ures, (size_t)T * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(h->d_Uanc + (size_t)chain * T, Uanc, (size_t)T * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(h->d_Ustar + chain, &Ustar, 8, cudaMemcpyHostToDevice));
+  if (bartlett) CK(h, cudaMemcpy(h->d_bart + (size_t)chain * nx * nx, bartlett, (size_t)nx * nx * 8, cudaMemcpyHostToDevice));
+  if (Xmn) CK(h, cudaMemcpy(h->d_Xmn + (size_t)chain * nx * np, Xmn, (size_t)nx * np * 8, cudaMemcpyHostToDevice));
+  h->fd.philox = 0;
+  h->fd.Z0 = h->d_Z0; h->fd.Z = h->d_Z; h->fd.Ures = h->d_Ures; h->fd.Uanc = h->d_Uanc; h->fd.Ustar = h->d_Ustar;
+  h->md.philox = 0; h->md.bartlett = h->d_bart; h->md.Xmn = h->d_Xmn;
+  h->have_rng = true;
+  h->injected_ready = true;
+  return PGB_OK;
+}
+
+static int check_ready(pgb_handle* h) {
+  if (!h->have_data || !h->have_meas || !h->have_init || !h->have_rng)
+    return set_err(h, PGB_ERR_STATE, "set_data / set_measurement / set_init_dist / set_rng_* must be called first");
+  for (char c : h->have_state)
+    if (!c) return set_err(h, PGB_ERR_STATE, "pgb_set_state missing for a chain");
+  return PGB_OK;
+}
+
+// Launch sequence of one exact scan + consumer on stream s.
+template <int NX, int MODE>
+static void launch_scan(pgb_handle* h, const ScanWS& ws, const double* v, const pgb_utable* utab, int64_t utab_stride,
+                        int64_t utab_index, int32_t* out_idx, int64_t out_stride, int64_t t, int first,
+                        unsigned long long* maxkey_reset) {
+  const FilterDev& fd = h->fd;
+  cudaStream_t s = h->stream;
+  dim3 gt(ws.nt, fd.nc), g1(1, fd.nc);
+  k_scan_local<<<gt, TPB, 0, s>>>(ws, v, fd.status);
+  k_resolve<<<g1, TPB, 0, s>>>(ws);
+  k_expand<NX, MODE><<<gt, TPB, 0, s>>>(fd, ws, v, utab, utab_stride, utab_index, out_idx, out_stride, t, first, 0);
+  k_seq_exact<<<g1, 32, 0, s>>>(ws, v, fd.status, maxkey_reset);
+  k_expand<NX, MODE><<<gt, TPB, 0, s>>>(fd, ws, v, utab, utab_stride, utab_index, out_idx, out_stride, t, first, 1);
+}
+
+template <int NX>
+static int run_filter_nx(pgb_handle* h) {
+  FilterDev& fd = h->fd;
+  MniwDev& md = h->md;
+  cudaStream_t s = h->stream;
+  const int64_t N = fd.N, T = fd.T;
+  const int nc = fd.nc;
+  const int first = (h->sweep_index == 1);
+  fd.sweep = (uint32_t)h->sweep_index;
+  md.sweep = fd.sweep;
+  const size_t nA = (size_t)nc * NX * fd.n_phi * 8, nQ = (size_t)nc * NX * NX * 8;
+  CK(h, cudaMemcpyAsync(h->d_A_used, fd.A, nA, cudaMemcpyDeviceToDevice, s));
+  CK(h, cudaMemcpyAsync(h->d_Q_used, h->d_Q, nQ, cudaMemcpyDeviceToDevice, s));
+  CK(h, cudaMemsetAsync(fd.maxkey, 0, (size_t)nc * 8, s));
+  dim3 gt(fd.nt, nc);
+  const size_t smA = (size_t)NX * fd.n_phi * 8;
+  k_build_utabs<<<dim3((unsigned)((T + 127) / 128), nc), 128, 0, s>>>(fd, first);
+  k_init<NX><<<dim3((unsigned)((N + TPB - 1) / TPB), nc), TPB, 0, s>>>(fd, first);
+  k_weights<<<gt, TPB, 0, s>>>(fd);
+  for (int64_t t = 1; t < T; ++t) {
+    k_prep<NX><<<gt, TPB, smA, s>>>(fd, t, first);
+    launch_scan<NX, MODE_PROPAGATE>(h, fd.main, fd.wbuf, fd.utab_res, T, t, nullptr, 0, t, first, fd.maxkey);
+    if (!first) {
+      k_norm<<<gt, TPB, 0, s>>>(fd);
+      launch_scan<NX, MODE_INDEX>(h, fd.side, fd.waN, fd.utab_anc, T, t, fd.ah + t * N + (N - 1), T * N, t, first, nullptr);
+    }
+    k_weights<<<gt, TPB, 0, s>>>(fd);
+  }
+  // w_T, then star = systematic_resampling(w[end,:], 1)   (:213)
+  k_prep<NX><<<gt, TPB, smA, s>>>(fd, T, first);
+  launch_scan<NX, MODE_INDEX>(h, fd.main, fd.wbuf, fd.utab_star, 1, 0, h->d_star_idx, 1, 0, first, nullptr);
+  k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out);
+  // statistics (:221-225)
+  k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md);
+  const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
+  k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md);
+  CK(h, cudaGetLastError());
+  return PGB_OK;
+}
+
+static int run_filter(pgb_handle* h) {
+  switch (h->cfg.n_x) {
+    case 1: return run_filter_nx<1>(h);
+    case 2: return run_filter_nx<2>(h);
+    case 3: return run_filter_nx<3>(h);
+    default: return run_filter_nx<4>(h);
+  }
+}
+
+static int run_mniw(pgb_handle* h) {
+  if (!h->have_prior) return set_err(h, PGB_ERR_STATE, "pgb_set_prior must be called before the MNIW draw");
+  k_mniw<<<h->fd.nc, MNIW_TPB, 0, h->stream>>>(h->md);
+  CK(h, cudaGetLastError());
+  h->sweep_index += 1;
+  return PGB_OK;
+}
+
+static int check_posdef(pgb_handle* h) {
+  std::vector<int> st(h->fd.nc);
+  CK(h, cudaMemcpyAsync(st.data(), h->fd.status, (size_t)h->fd.nc * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  for (int v : st)
+    if (v & PGB_STATUS_NOT_POSDEF)
+      return set_err(h, PGB_ERR_NOT_POSDEF, "Cholesky failed on device (matrix not positive definite)");
+  return PGB_OK;
+}
+
+extern "C" int pgb_sweep_filter(pgb_handle* h) {
+  NEED(h);
+  int rc = check_ready(h);
+  if (rc) return rc;
+  return run_filter(h);
+}
+extern "C" int pgb_sweep_mniw(pgb_handle* h) {
+  NEED(h);
+  return run_mniw(h);
+}
+extern "C" int pgb_sweep(pgb_handle* h, int64_t n_sweeps) {
+  NEED(h);
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!h->fd.philox && n_sweeps != 1) return set_err(h, PGB_ERR_INVALID, "injected streams cover exactly one sweep");
+  for (int64_t i = 0; i < n_sweeps; ++i) {
+    if ((rc = run_filter(h))) return rc;
+    if ((rc = run_mniw(h))) return rc;
+  }
+  return check_posdef(h);
+}
+extern "C" int pgb_synchronize(pgb_handle* h) {
+  NEED(h);
+  CK(h, cudaStreamSynchronize(h->stream));
+  return PGB_OK;
+}
+
+static int fetch_sample(pgb_handle* h, int chain, double* A, double* Q, double* w_m1, double* x_m1, double* u_m1,
+                        std::vector<double>& tmp) {
+  const int nx = h->cfg.n_x, np = h->cfg.n_phi, nu = h->cfg.n_u;
+  const int64_t N = h->cfg.N, T = h->cfg.T;
+  cudaStream_t s = h->stream;
+  if (A) CK(h, cudaMemcpyAsync(A, h->d_A_used + (size_t)chain * nx * np, (size_t)nx * np * 8, cudaMemcpyDeviceToHost, s));
+  if (Q) CK(h, cudaMemcpyAsync(Q, h->d_Q_used + (size_t)chain * nx * nx, (size_t)nx * nx * 8, cudaMemcpyDeviceToHost, s));
+  if (w_m1) CK(h, cudaMemcpyAsync(w_m1, h->fd.wbuf + (size_t)chain * N, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
+  if (x_m1) {
+    tmp.resize((size_t)nx * N);
+    CK(h, cudaMemcpyAsync(tmp.data(), h->fd.xh + ((size_t)chain * T + (T - 1)) * nx * N, (size_t)nx * N * 8,
+                          cudaMemcpyDeviceToHost, s));
+  }
+  CK(h, cudaStreamSynchronize(s));
+  if (x_m1)
+    for (int64_t n = 0; n < N; ++n)
+      for (int d = 0; d < nx; ++d) x_m1[d + nx * n] = tmp[(size_t)d * N + n];
+  if (u_m1)
+    for (int c = 0; c < nu; ++c) u_m1[c] = h->h_u[(size_t)nu * (T - 1) + c];
+  return PGB_OK;
+}
+
+extern "C" int pgb_get_sample(pgb_handle* h, int32_t chain, double* A, double* Q, double* w_m1, double* x_m1,
+                              double* u_m1) {
+  NEED(h);
+  if (chain < 0 || chain >= h->cfg.n_chains) return set_err(h, PGB_ERR_INVALID, "bad chain %d", chain);
+  std::vector<double> tmp;
+  return fetch_sample(h, chain, A, Q, w_m1, x_m1, u_m1, tmp);
+}
+
+extern "C" int pgb_particle_gibbs(pgb_handle* h, int64_t K, int64_t K_b, int64_t k_d, double* A_s, double* Q_s,
+                                  double* w_s, double* x_s, double* u_m1) {
+  NEED(h);
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!h->fd.philox) return set_err(h, PGB_ERR_INVALID, "pgb_particle_gibbs needs Philox streams");
+  if (!h->have_prior) return set_err(h, PGB_ERR_STATE, "pgb_set_prior missing");
+  if (K < 1 || K_b < 0 || k_d < 0) return set_err(h, PGB_ERR_INVALID, "bad K/K_b/k_d");
+  const int nc = h->cfg.n_chains, nx = h->cfg.n_x, np = h->cfg.n_phi;
+  const int64_t N = h->cfg.N;
+  const int64_t K_total = K_b + 1 + (K - 1) * (k_d + 1);  // particle_Gibbs.jl:116
+  std::vector<double> tmp;
+  int64_t cur = 0;
+  for (int64_t k = h->sweep_index; k <= K_total; ++k) {
+    if ((rc = run_filter(h))) return rc;
+    if (K_b < k && ((k - (K_b + 1)) % (k_d + 1) == 0) && cur < K) {  // :203
+      for (int c = 0; c < nc; ++c) {
+        size_t o = (size_t)c * K + cur;
+        rc = fetch_sample(h, c, A_s ? A_s + o * nx * np : nullptr, Q_s ? Q_s + o * nx * nx : nullptr,
+                          w_s ? w_s + o * N : nullptr, x_s ? x_s + o * nx * N : nullptr, u_m1, tmp);
+        if (rc) return rc;
+      }
+      ++cur;
+    }
+    if ((rc = run_mniw(h))) return rc;
+    if ((k & 15) == 0 && (rc = check_posdef(h))) return rc;
+  }
+  return check_posdef(h);
+}
+
+extern "C" int pgb_get_history(pgb_handle* h, int32_t chain, int64_t* a, double* x, double* w) {
+  NEED(h);
+  const int nx = h->cfg.n_x;
+  const int64_t N = h->cfg.N, T = h->cfg.T;
+  if (chain < 0 || chain >= h->cfg.n_chains) return set_err(h, PGB_ERR_INVALID, "bad chain %d", chain);
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (a) {
+    std::vector<int32_t> t32((size_t)T * N);
+    CK(h, cudaMemcpy(t32.data(), h->fd.ah + (size_t)chain * T * N, (size_t)T * N * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < t32.size(); ++i) a[i] = (int64_t)t32[i] + 1;
+    for (int64_t n = 0; n < N; ++n) a[n] = 0;  // a[1,:] is never written by the reference
+  }
+  if (x) {
+    std::vector<double> tx((size_t)T * nx * N);
+    CK(h, cudaMemcpy(tx.data(), h->fd.xh + (size_t)chain * T * nx * N, tx.size() * 8, cudaMemcpyDeviceToHost));
+    for (int64_t t = 0; t < T; ++t)
+      for (int64_t n = 0; n < N; ++n)
+        for (int d = 0; d < nx; ++d) x[(t * N + n) * nx + d] = tx[((size_t)t * nx + d) * N + n];
+  }
+  if (w) {
+    if (!h->fd.whist) return set_err(h, PGB_ERR_STATE, "w history was not kept (keep_w_history = 0)");
+    CK(h, cudaMemcpy(w, h->fd.whist + (size_t)chain * T * N, (size_t)T * N * 8, cudaMemcpyDeviceToHost));
+  }
+  return PGB_OK;
+}
+
+extern "C" int pgb_get_stats(pgb_handle* h, int32_t chain, double* Phi, double* Psi, double* Sigma, int64_t* star) {
+  NEED(h);
+  const int nx = h->cfg.n_x, np = h->cfg.n_phi;
+  if (chain < 0 || chain >= h->cfg.n_chains) return set_err(h, PGB_ERR_INVALID, "bad chain %d", chain);
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (Phi) CK(h, cudaMemcpy(Phi, h->md.Phi + (size_t)chain * nx * nx, (size_t)nx * nx * 8, cudaMemcpyDeviceToHost));
+  if (Psi) CK(h, cudaMemcpy(Psi, h->md.Psi + (size_t)chain * nx * np, (size_t)nx * np * 8, cudaMemcpyDeviceToHost));
+  if (Sigma) CK(h, cudaMemcpy(Sigma, h->md.Sigma + (size_t)chain * np * np, (size_t)np * np * 8, cudaMemcpyDeviceToHost));
+  if (star) CK(h, cudaMemcpy(star, h->d_star_out + chain, 8, cudaMemcpyDeviceToHost));
+  return PGB_OK;
+}
+
+extern "C" int pgb_get_status(pgb_handle* h, int32_t chain, int32_t* status_bits, int64_t* n_fallback, int64_t* n_scans,
+                              int32_t clear) {
+  NEED(h);
+  if (chain < 0 || chain >= h->cfg.n_chains) return set_err(h, PGB_ERR_INVALID, "bad chain %d", chain);
+  CK(h, cudaStreamSynchronize(h->stream));
+  int st = 0;
+  long long cm[2], cs[2];
+  CK(h, cudaMemcpy(&st, h->fd.status + chain, 4, cudaMemcpyDeviceToHost));
+  CK(h, cudaMemcpy(cm, h->d_counters_main + 2 * chain, 16, cudaMemcpyDeviceToHost));
+  CK(h, cudaMemcpy(cs, h->d_counters_side + 2 * chain, 16, cudaMemcpyDeviceToHost));
+  if (status_bits) *status_bits = st;
+  if (n_fallback) *n_fallback = cm[0] + cs[0];
+  if (n_scans) *n_scans = cm[1] + cs[1];
+  if (clear) {
+    CK(h, cudaMemset(h->fd.status + chain, 0, 4));
+    CK(h, cudaMemset(h->d_counters_main + 2 * chain, 0, 16));
+    CK(h, cudaMemset(h->d_counters_side + 2 * chain, 0, 16));
+  }
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void k_build_one_utab(pgb_utable* ut, int64_t M, double rnd) { pgb_utable_build(ut, M, rnd); }
+
+extern "C" int pgb_systematic_resampling(int32_t device, const double* W, int64_t n_w, int64_t n_draw, double rnd,
+                                         int64_t* idx, int32_t* status) {
+  if (!W || !idx || n_w < 1 || n_draw < 1) return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
+  if (n_w >= (1ll << 31) - TILE) return set_err(nullptr, PGB_ERR_INVALID, "n_w too large");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s); pgopt_b200 has no CPU fallback",
+                   cudaGetErrorString(e));
+  pgb_handle tmp;  // only used as an allocation list / error sink
+  pgb_handle* h = &tmp;
+  h->cfg.device = device;
+  struct Cleanup {
+    pgb_handle* h;
+    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
+  } cleanup{h};
+  CK(h, cudaSetDevice(device));
+  FilterDev fd;
+  memset(&fd, 0, sizeof(fd));
+  fd.nc = 1; fd.N = n_w; fd.T = 1; fd.n_x = 1; fd.n_y = 1; fd.n_u = 1;
+  ScanWS ws;
+  CK(h, alloc_scanws(h, &ws, n_w, 1, nullptr));
+  fd.nt = ws.nt;
+  double* d_W = nullptr;
+  int32_t* d_idx = nullptr;
+  pgb_utable* d_ut = nullptr;
+  CK(h, dalloc(h, &d_W, (size_t)n_w));
+  CK(h, dalloc(h, &d_idx, (size_t)n_draw));
+  CK(h, dalloc(h, &d_ut, 1));
+  CK(h, dalloc(h, &fd.status, 1));
+  CK(h, cudaMemcpy(d_W, W, (size_t)n_w * 8, cudaMemcpyHostToDevice));
+  cudaStream_t s = 0;
+  h->stream = s;
+  h->fd = fd;
+  k_build_one_utab<<<1, 1, 0, s>>>(d_ut, n_draw, rnd);
+  k_tile_sums<<<dim3(ws.nt, 1), TPB, 0, s>>>(ws, d_W);
+  launch_scan<1, MODE_INDEX>(h, ws, d_W, d_ut, 1, 0, d_idx, n_draw, 0, 0, nullptr);
+  CK(h, cudaGetLastError());
+  CK(h, cudaDeviceSynchronize());
+  std::vector<int32_t> t32((size_t)n_draw);
+  int st = 0;
+  CK(h, cudaMemcpy(t32.data(), d_idx, (size_t)n_draw * 4, cudaMemcpyDeviceToHost));
+  CK(h, cudaMemcpy(&st, fd.status, 4, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n_draw; ++i) idx[i] = (int64_t)t32[i] + 1;
+  if (status) {
+    long long c[2];
+    CK(h, cudaMemcpy(c, ws.counters, 16, cudaMemcpyDeviceToHost));
+    *status = st | (c[0] ? 0x100 : 0);  // bit 8: the serial exact fallback ran
+  }
+  h->stream = nullptr;
+  return PGB_OK;
+}
+
+extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Phi, const double* Psi,
+                               const double* Sigma, const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t T,
+                               const double* bartlett, const double* Xmn, uint64_t seed, uint32_t chain,
+                               uint32_t sweep_index, double* A_out, double* Q_out) {
+  if (!Phi || !Psi || !Sigma || !V_diag || !Lambda_Q || !A_out || !Q_out || n_x < 1 || n_x > 4 || n_phi < 1)
+    return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s); pgopt_b200 has no CPU fallback",
+                   cudaGetErrorString(e));
+  pgb_handle tmp;
+  pgb_handle* h = &tmp;
+  struct Cleanup {
+    pgb_handle* h;
+    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
+  } cleanup{h};
+  CK(h, cudaSetDevice(device));
+  MniwDev md;
+  memset(&md, 0, sizeof(md));
+  md.nc = 1; md.n_x = n_x; md.n_phi = n_phi; md.Tm1 = T; md.ell_Q = ell_Q;
+  const size_t pp = (size_t)n_phi * n_phi, xp = (size_t)n_x * n_phi, xx = (size_t)n_x * n_x;
+  double *dV, *dL, *dB = nullptr, *dX = nullptr, *dQ;
+  CK(h, dalloc(h, &dV, (size_t)n_phi));
+  CK(h, dalloc(h, &dL, xx));
+  CK(h, dalloc(h, &md.Phi, xx)); CK(h, dalloc(h, &md.Psi, xp)); CK(h, dalloc(h, &md.Sigma, pp));
+  CK(h, dalloc(h, &md.Ls, pp)); CK(h, dalloc(h, &md.Sinv, pp)); CK(h, dalloc(h, &md.Lv, pp));
+  CK(h, dalloc(h, &md.Mpost, xp)); CK(h, dalloc(h, &md.Xn, xp)); CK(h, dalloc(h, &md.LX, xp));
+  CK(h, dalloc(h, &md.A, xp)); CK(h, dalloc(h, &dQ, xx)); CK(h, dalloc(h, &md.Lq, 16)); CK(h, dalloc(h, &md.c0, 1));
+  CK(h, dalloc(h, &md.status, 1));
+  md.Q = dQ; md.V_diag = dV; md.Lambda_Q = dL;
+  CK(h, cudaMemcpy(dV, V_diag, (size_t)n_phi * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dL, Lambda_Q, xx * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(md.Phi, Phi, xx * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(md.Psi, Psi, xp * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(md.Sigma, Sigma, pp * 8, cudaMemcpyHostToDevice));
+  if (bartlett && Xmn) {
+    CK(h, dalloc(h, &dB, xx)); CK(h, dalloc(h, &dX, xp));
+    CK(h, cudaMemcpy(dB, bartlett, xx * 8, cudaMemcpyHostToDevice));
+    CK(h, cudaMemcpy(dX, Xmn, xp * 8, cudaMemcpyHostToDevice));
+    md.philox = 0; md.bartlett = dB; md.Xmn = dX;
+  } else {
+    md.philox = 1; md.seed = seed; md.chain_base = chain; md.sweep = sweep_index;
+  }
+  k_mniw<<<1, MNIW_TPB>>>(md);
+  CK(h, cudaGetLastError());
+  CK(h, cudaDeviceSynchronize());
+  int st = 0;
+  CK(h, cudaMemcpy(&st, md.status, 4, cudaMemcpyDeviceToHost));
+  if (st & PGB_STATUS_NOT_POSDEF) return set_err(nullptr, PGB_ERR_NOT_POSDEF, "matrix not positive definite");
+  CK(h, cudaMemcpy(A_out, md.A, xp * 8, cudaMemcpyDeviceToHost));
+  CK(h, cudaMemcpy(Q_out, dQ, xx * 8, cudaMemcpyDeviceToHost));
+  return PGB_OK;
+}
+
+template <int NX>
+static void launch_rollout(const FilterDev& fd, const RolloutDev& rd) {
+  k_rollout<NX><<<(unsigned)((rd.K + 127) / 128), 128>>>(fd, rd);
+}
+
+extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q,
+                           const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
+                           const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e,
+                           double* X, double* Y) {
+  int rc = validate_cfg(cfg);
+  if (rc) return rc;
+  if (!A || !Q || !w_m1 || !x_m1 || !u_m1 || !C || !Le || !u_init || K < 1 || H < 1 || cfg->N < 1)
+    return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0)
+    return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s); pgopt_b200 has no CPU fallback",
+                   cudaGetErrorString(ce));
+  pgb_handle tmp;
+  pgb_handle* h = &tmp;
+  struct Cleanup {
+    pgb_handle* h;
+    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
+  } cleanup{h};
+  CK(h, cudaSetDevice(cfg->device));
+  const int nx = cfg->n_x, np = cfg->n_phi, nu = cfg->n_u, ny = cfg->n_y;
+  const int64_t N = cfg->N;
+  FilterDev fd;
+  memset(&fd, 0, sizeof(fd));
+  fill_model(fd, cfg);
+  for (int i = 0; i < ny * nx; ++i) fd.C[i] = C[i];
+  RolloutDev rd;
+  memset(&rd, 0, sizeof(rd));
+  rd.K = K; rd.H = H; rd.N = N; rd.seed = seed; rd.k_offset = k_offset;
+  for (int i = 0; i < ny * ny; ++i) rd.Le[i] = Le[i];
+  const int m = nx * np;
+  double *dA, *dAt, *dQ, *dw, *dx, *dum, *dui;
+  CK(h, dalloc(h, &dA, (size_t)K * m, false));
+  CK(h, dalloc(h, &dAt, (size_t)K * m, false));
+  CK(h, dalloc(h, &dQ, (size_t)K * nx * nx, false));
+  CK(h, dalloc(h, &dw, (size_t)K * N, false));
+  CK(h, dalloc(h, &dx, (size_t)K * nx * N, false));
+  CK(h, dalloc(h, &dum, (size_t)K * nu, false));
+  CK(h, dalloc(h, &dui, (size_t)nu * H, false));
+  CK(h, dalloc(h, &rd.status, 1));
+  CK(h, cudaMemcpy(dA, A, (size_t)K * m * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dQ, Q, (size_t)K * nx * nx * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dw, w_m1, (size_t)K * N * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dx, x_m1, (size_t)K * nx * N * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dum, u_m1, (size_t)K * nu * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dui, u_init, (size_t)nu * H * 8, cudaMemcpyHostToDevice));
+  if (x0) CK(h, dalloc(h, &rd.x0, (size_t)K * nx, false));
+  if (v) CK(h, dalloc(h, &rd.v, (size_t)K * H * nx, false));
+  if (e) CK(h, dalloc(h, &rd.e, (size_t)K * H * ny, false));
+  if (X) CK(h, dalloc(h, &rd.X, (size_t)K * (H + 1) * nx, false));
+  if (Y) CK(h, dalloc(h, &rd.Y, (size_t)K * H * ny, false));
+  k_transpose_A<<<dim3((unsigned)((K + 31) / 32), (unsigned)((m + 31) / 32)), dim3(32, 8)>>>(dA, dAt, K, m);
+  rd.At = dAt; rd.Q = dQ; rd.w_m1 = dw; rd.x_m1 = dx; rd.u_m1 = dum; rd.u_init = dui;
+  switch (nx) {
+    case 1: launch_rollout<1>(fd, rd); break;
+    case 2: launch_rollout<2>(fd, rd); break;
+    case 3: launch_rollout<3>(fd, rd); break;
+    default: launch_rollout<4>(fd, rd); break;
+  }
+  CK(h, cudaGetLastError());
+  CK(h, cudaDeviceSynchronize());
+  int st = 0;
+  CK(h, cudaMemcpy(&st, rd.status, 4, cudaMemcpyDeviceToHost));
+  if (st & PGB_STATUS_NOT_POSDEF) return set_err(nullptr, PGB_ERR_NOT_POSDEF, "a scenario's Q is not positive definite");
+  if (x0) CK(h, cudaMemcpy(x0, rd.x0, (size_t)K * nx * 8, cudaMemcpyDeviceToHost));
+  if (v) CK(h, cudaMemcpy(v, rd.v, (size_t)K * H * nx * 8, cudaMemcpyDeviceToHost));
+  if (e) CK(h, cudaMemcpy(e, rd.e, (size_t)K * H * ny * 8, cudaMemcpyDeviceToHost));
+  if (X) CK(h, cudaMemcpy(X, rd.X, (size_t)K * (H + 1) * nx * 8, cudaMemcpyDeviceToHost));
+  if (Y) CK(h, cudaMemcpy(Y, rd.Y, (size_t)K * H * ny * 8, cudaMemcpyDeviceToHost));
+  return PGB_OK;
+}

@@ -1,0 +1,425 @@
+// pgb_mniw.cuh — sufficient statistics (Julia/src/particle_Gibbs.jl:221-225) and the MNIW parameter
+// draw (particle_Gibbs.jl:56-81) on the device.
+//
+// Bit-exactness vs the oracle: every dense-algebra step is done in "right-looking" form, where each
+// matrix entry receives its fma updates in the same (increasing / decreasing pivot) order as the
+// oracle's sequential loops, so the parallel factorisations and triangular solves produce the same
+// bits as oracle/pg_oracle.c.  Sums over time use the balanced-tree order of pgb_device.cuh.
+#pragma once
+#include "pgb_filter.cuh"
+
+namespace pgb {
+
+constexpr int MNIW_TPB = 512;
+
+struct MniwDev {
+  int nc, n_x, n_phi;
+  int64_t Tm1;
+  double ell_Q;
+  const double* V_diag;    // [n_phi]
+  const double* Lambda_Q;  // [n_x*n_x]
+  double* zeta;   // [nc][n_x][Tm1]
+  double* zb;     // [nc][n_phi][Tm1]
+  double* Phi;    // [nc][n_x*n_x]
+  double* Psi;    // [nc][n_x*n_phi]
+  double* Sigma;  // [nc][n_phi*n_phi]
+  double* Ls;     // [nc][n_phi*n_phi] workspaces
+  double* Sinv;   // [nc][n_phi*n_phi]
+  double* Lv;     // [nc][n_phi*n_phi]
+  double* Mpost;  // [nc][n_x*n_phi]
+  double* Xn;     // [nc][n_x*n_phi]
+  double* LX;     // [nc][n_x*n_phi]
+  double* A;      // [nc][n_x*n_phi]  chain state (in/out)
+  double* Q;      // [nc][n_x*n_x]
+  double* Lq;     // [nc][16]
+  double* c0;     // [nc]
+  int* status;    // [nc]
+  int philox;
+  uint64_t seed;
+  uint32_t chain_base, sweep;
+  const double* bartlett;  // injected [nc][n_x*n_x]
+  const double* Xmn;       // injected [nc][n_x*n_phi]
+};
+
+// phi(x', u) for every t < T-1 and zeta = x'[:, 2:T]
+template <int NX>
+__global__ void __launch_bounds__(128) k_stats_z(FilterDev fd, MniwDev md) {
+  const int chain = blockIdx.y;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t Tm1 = md.Tm1;
+  if (t >= Tm1) return;
+  const double* xp = fd.xprim + (int64_t)chain * NX * fd.T;
+  const double* u = fd.u + (int64_t)fd.n_u * t;
+  double* zeta = md.zeta + (int64_t)chain * NX * Tm1;
+  double* zb = md.zb + (int64_t)chain * fd.n_phi * Tm1;
+  double x[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) {
+    x[d] = xp[d + NX * t];
+    zeta[(int64_t)d * Tm1 + t] = xp[d + NX * (t + 1)];
+  }
+  if (fd.basis == 0) {
+    zb[0 * Tm1 + t] = __dmul_rn(0.1, x[0]);
+    zb[1 * Tm1 + t] = __dmul_rn(0.1, x[NX > 1 ? 1 : 0]);
+    zb[2 * Tm1 + t] = u[0];
+    zb[3 * Tm1 + t] = __dmul_rn(__dmul_rn(0.01, pgb_cos(__dmul_rn(3.0, x[0]))), x[NX > 1 ? 1 : 0]);
+    zb[4 * Tm1 + t] = __dmul_rn(__dmul_rn(0.1, pgb_sin(__dmul_rn(2.0, x[NX > 1 ? 1 : 0]))), u[0]);
+    return;
+  }
+  const int nz = fd.n_z;
+  double tk[PGB_MAX_Z_][MAXC];
+  for (int k = 0; k < nz; ++k) {
+    double zk = (k < fd.n_u) ? u[k] : x[k - fd.n_u];
+    double zl = __dadd_rn(zk, fd.hg_L[k]);
+    for (int j = 0; j < fd.hg_count[k]; ++j)
+      tk[k][j] = __dmul_rn(fd.hg_lsi[k], pgb_sin(__dmul_rn(fd.hg_pij2l[k][j], zl)));
+  }
+  int dig[PGB_MAX_Z_];
+  for (int k = 0; k < nz; ++k) dig[k] = 0;
+  for (int i = 0; i < fd.n_phi; ++i) {
+    double p = 1.0;
+    for (int k = 0; k < nz; ++k) p = __dmul_rn(p, tk[k][dig[k]]);
+    zb[(int64_t)i * Tm1 + t] = p;
+    int k = nz - 1;
+    while (k >= 0 && ++dig[k] == fd.hg_count[k]) dig[k--] = 0;
+  }
+}
+
+// One CTA per output entry: Phi = zeta zeta', Psi = zeta z', Sigma = z z' as tree sums over t.
+__global__ void __launch_bounds__(TPB) k_stats(MniwDev md) {
+  __shared__ double sm[NWARP];
+  const int chain = blockIdx.y;
+  const int nx = md.n_x, np = md.n_phi;
+  const int64_t Tm1 = md.Tm1;
+  const double* zeta = md.zeta + (int64_t)chain * nx * Tm1;
+  const double* zb = md.zb + (int64_t)chain * np * Tm1;
+  int64_t e = blockIdx.x;
+  const double *pa, *pb;
+  double* out;
+  if (e < nx * nx) {
+    int a = (int)(e % nx), b = (int)(e / nx);
+    pa = zeta + (int64_t)a * Tm1; pb = zeta + (int64_t)b * Tm1;
+    out = md.Phi + (int64_t)chain * nx * nx + e;
+  } else if (e < nx * nx + (int64_t)nx * np) {
+    e -= nx * nx;
+    int a = (int)(e % nx), i = (int)(e / nx);
+    pa = zeta + (int64_t)a * Tm1; pb = zb + (int64_t)i * Tm1;
+    out = md.Psi + (int64_t)chain * nx * np + e;
+  } else {
+    e -= nx * nx + (int64_t)nx * np;
+    int i = (int)(e % np), j = (int)(e / np);
+    pa = zb + (int64_t)i * Tm1; pb = zb + (int64_t)j * Tm1;
+    out = md.Sigma + (int64_t)chain * np * np + e;
+  }
+  int64_t P = TPB;
+  while (P < Tm1) P <<= 1;
+  const int per = (int)(P / TPB);
+  const int64_t base = (int64_t)threadIdx.x * per;
+  double st[16];
+  int sp = 0;
+  for (int i = 0; i < per; ++i) {
+    double x = (base + i < Tm1) ? __dmul_rn(pa[base + i], pb[base + i]) : 0.0;
+    int merges = __ffs(i + 1) - 1;
+    for (int m = 0; m < merges; ++m) x = __dadd_rn(st[--sp], x);
+    st[sp++] = x;
+  }
+  double s = block_tree_sum(st[0], sm);
+  if (threadIdx.x == 0) *out = s;
+}
+
+// ---- small serial helpers (n <= 4), executed by one thread; same loops as the oracle's ----
+__device__ inline int small_chol(double* A, int n) {
+  for (int k = 0; k < n; ++k) {
+    double d = A[k + n * k];
+    if (!(d > 0.0)) return 1;
+    d = __dsqrt_rn(d);
+    A[k + n * k] = d;
+    for (int i = k + 1; i < n; ++i) A[i + n * k] = __ddiv_rn(A[i + n * k], d);
+    for (int j = k + 1; j < n; ++j)
+      for (int i = j; i < n; ++i) A[i + n * j] = __fma_rn(-A[i + n * k], A[j + n * k], A[i + n * j]);
+  }
+  for (int j = 1; j < n; ++j)
+    for (int i = 0; i < j; ++i) A[i + n * j] = 0.0;
+  return 0;
+}
+__device__ inline void small_inverse_from_chol(const double* L, int n, double* inv) {
+  double col[4];
+  for (int j = 0; j < n; ++j) {
+    for (int i = 0; i < n; ++i) col[i] = (i == j) ? 1.0 : 0.0;
+    for (int d = 0; d < n; ++d) {
+      double acc = col[d];
+      for (int e = 0; e < d; ++e) acc = __fma_rn(-L[d + n * e], col[e], acc);
+      col[d] = __ddiv_rn(acc, L[d + n * d]);
+    }
+    for (int d = n - 1; d >= 0; --d) {
+      double acc = col[d];
+      for (int e = n - 1; e > d; --e) acc = __fma_rn(-L[e + n * d], col[e], acc);
+      col[d] = __ddiv_rn(acc, L[d + n * d]);
+    }
+    for (int i = 0; i < n; ++i) inv[i + n * j] = col[i];
+  }
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < j; ++i) inv[i + n * j] = inv[j + n * i];
+}
+// Lq = chol(Q), c0 = -(n log 2pi + logdet Q)/2   (MvNormal(zeros, Q), particle_Gibbs.jl:157,178)
+__device__ inline int chain_params_from_Q(const double* Q, int n, double* Lq16, double* c0) {
+  double L[16];
+  for (int i = 0; i < n * n; ++i) L[i] = Q[i];
+  if (small_chol(L, n)) return 1;
+  double logdet = 0.0;
+  for (int d = 0; d < n; ++d) logdet = __dadd_rn(logdet, pgb_log(L[d + n * d]));
+  logdet = __dmul_rn(2.0, logdet);
+  *c0 = __ddiv_rn(-__dadd_rn(__dmul_rn((double)n, 1.8378770664093453), logdet), 2.0);
+  for (int i = 0; i < 16; ++i) Lq16[i] = (i < n * n) ? L[i] : 0.0;
+  return 0;
+}
+__global__ void k_chain_params(int nc, int n_x, const double* Q, double* Lq, double* c0, int* status) {
+  int chain = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= nc) return;
+  if (chain_params_from_Q(Q + (int64_t)chain * n_x * n_x, n_x, Lq + chain * 16, c0 + chain))
+    atomicOr(&status[chain], 16);
+}
+
+// Marsaglia-Tsang chi-square from the MNIW Philox stream (same consumption as the oracle's mt_chi2)
+__device__ inline double mt_chi2_dev(uint64_t seed, uint32_t cid, uint32_t sweep, uint32_t which, double df) {
+  double a = __ddiv_rn(df, 2.0);
+  double d = __dsub_rn(a, __ddiv_rn(1.0, 3.0));
+  double c = __ddiv_rn(1.0, __dsqrt_rn(__dmul_rn(9.0, d)));
+  for (uint32_t attempt = 0;; ++attempt) {
+    double x, unused;
+    pgb_normal_pair(pgb_stream_block(seed, PGB_STREAM_MNIW, cid, sweep, which, 2 * attempt), &x, &unused);
+    pgb_u32x4 b = pgb_stream_block(seed, PGB_STREAM_MNIW, cid, sweep, which, 2 * attempt + 1);
+    double uu = pgb_u53(b.v[0], b.v[1]);
+    double v = __dadd_rn(1.0, __dmul_rn(c, x));
+    if (v <= 0.0) continue;
+    v = __dmul_rn(__dmul_rn(v, v), v);
+    // log(u) < 0.5*x*x + d - d*v + d*log(v)   (left-assoc, as written in the oracle)
+    double rhs = __dadd_rn(__dsub_rn(__dadd_rn(__dmul_rn(__dmul_rn(0.5, x), x), d), __dmul_rn(d, v)),
+                           __dmul_rn(d, pgb_log(v)));
+    if (pgb_log(uu) < rhs) return __dmul_rn(2.0, __dmul_rn(d, v));
+  }
+}
+
+// right-looking Cholesky of an n x n column-major matrix in global memory by one CTA
+__device__ inline int cta_cholesky(double* A, int n, int* s_fail) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int k = 0; k < n; ++k) {
+    __syncthreads();
+    if (tid == 0) {
+      double d = A[k + (int64_t)n * k];
+      if (!(d > 0.0)) *s_fail = 1;
+      else A[k + (int64_t)n * k] = __dsqrt_rn(d);
+    }
+    __syncthreads();
+    if (*s_fail) return 1;
+    const double d = A[k + (int64_t)n * k];
+    for (int i = k + 1 + tid; i < n; i += nth) A[i + (int64_t)n * k] = __ddiv_rn(A[i + (int64_t)n * k], d);
+    __syncthreads();
+    const int m = n - k - 1;  // trailing size
+    for (int64_t e = tid; e < (int64_t)m * m; e += nth) {
+      int i = k + 1 + (int)(e % m), j = k + 1 + (int)(e / m);
+      if (i >= j) A[i + (int64_t)n * j] = __fma_rn(-A[i + (int64_t)n * k], A[j + (int64_t)n * k], A[i + (int64_t)n * j]);
+    }
+  }
+  __syncthreads();
+  for (int64_t e = tid; e < (int64_t)n * n; e += nth) {
+    int i = (int)(e % n), j = (int)(e / n);
+    if (i < j) A[e] = 0.0;
+  }
+  __syncthreads();
+  return 0;
+}
+// Solve (L L') X = B for nrhs right-hand sides stored as columns of B (ld = n), in place.
+// Column sweeps keep every entry's update order identical to the oracle's substitutions.
+__device__ inline void cta_chol_solve(const double* L, int n, double* B, int nrhs) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int e = 0; e < n; ++e) {  // forward: L y = b
+    __syncthreads();
+    const double piv = L[e + (int64_t)n * e];
+    for (int r = tid; r < nrhs; r += nth) B[e + (int64_t)n * r] = __ddiv_rn(B[e + (int64_t)n * r], piv);
+    __syncthreads();
+    const int m = n - e - 1;
+    for (int64_t w = tid; w < (int64_t)m * nrhs; w += nth) {
+      int d = e + 1 + (int)(w % m), r = (int)(w / m);
+      B[d + (int64_t)n * r] = __fma_rn(-L[d + (int64_t)n * e], B[e + (int64_t)n * r], B[d + (int64_t)n * r]);
+    }
+  }
+  for (int e = n - 1; e >= 0; --e) {  // backward: L' x = y
+    __syncthreads();
+    const double piv = L[e + (int64_t)n * e];
+    for (int r = tid; r < nrhs; r += nth) B[e + (int64_t)n * r] = __ddiv_rn(B[e + (int64_t)n * r], piv);
+    __syncthreads();
+    for (int64_t w = tid; w < (int64_t)e * nrhs; w += nth) {
+      int d = (int)(w % e), r = (int)(w / e);
+      B[d + (int64_t)n * r] = __fma_rn(-L[e + (int64_t)n * d], B[e + (int64_t)n * r], B[d + (int64_t)n * r]);
+    }
+  }
+  __syncthreads();
+}
+
+// MNIW_sample + refresh of the chain parameters used by the next sweep.  One CTA per chain.
+__global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md) {
+  __shared__ int s_fail;
+  __shared__ double s_small[8][16];  // covM, Lc, S, B, LB, Wm, Qn, Lq
+  const int chain = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int nx = md.n_x, np = md.n_phi;
+  const int64_t pp = (int64_t)np * np;
+  double* Ls = md.Ls + chain * pp;
+  double* Sinv = md.Sinv + chain * pp;
+  double* Lv = md.Lv + chain * pp;
+  double* Mp = md.Mpost + (int64_t)chain * nx * np;
+  double* Xn = md.Xn + (int64_t)chain * nx * np;
+  double* LX = md.LX + (int64_t)chain * nx * np;
+  const double* Phi = md.Phi + (int64_t)chain * nx * nx;
+  const double* Psi = md.Psi + (int64_t)chain * nx * np;
+  const double* Sigma = md.Sigma + chain * pp;
+  double* Aout = md.A + (int64_t)chain * nx * np;
+  double* Qout = md.Q + (int64_t)chain * nx * nx;
+  const uint32_t cid = md.chain_base + chain;
+  if (tid == 0) s_fail = 0;
+  // Sigbar = Sigma + I/V (:64)
+  for (int64_t e = tid; e < pp; e += nth) {
+    int i = (int)(e % np), j = (int)(e / np);
+    double v = Sigma[e];
+    if (i == j) v = __dadd_rn(v, __ddiv_rn(1.0, md.V_diag[i]));
+    Ls[e] = v;
+  }
+  if (cta_cholesky(Ls, np, &s_fail)) {
+    if (tid == 0) atomicOr(&md.status[chain], 16);
+    return;
+  }
+  // post_mean = Psibar / Sigbar (:67): RHS r = row r of Psi, stored as column r of a np x nx buffer.
+  // Mp is used as that buffer (column-major np x nx), transposed afterwards into LX as scratch.
+  for (int64_t e = tid; e < (int64_t)np * nx; e += nth) {
+    int i = (int)(e % np), d = (int)(e / np);
+    LX[e] = Psi[d + nx * i];
+  }
+  cta_chol_solve(Ls, np, LX, nx);
+  for (int64_t e = tid; e < (int64_t)np * nx; e += nth) {
+    int i = (int)(e % np), d = (int)(e / np);
+    Mp[d + nx * i] = LX[e];
+  }
+  __syncthreads();
+  // cov_M = (Lambda_Q + Phibar) - M Psi' (:65), symmetrised (:66) -> s_small[1]
+  if (tid < nx * nx) {
+    int a = tid % nx, b = tid / nx;
+    double acc = 0.0;
+    for (int i = 0; i < np; ++i) acc = __fma_rn(Mp[a + nx * i], Psi[b + nx * i], acc);
+    s_small[0][a + nx * b] = __dsub_rn(__dadd_rn(md.Lambda_Q[a + nx * b], Phi[a + nx * b]), acc);
+  }
+  __syncthreads();
+  if (tid < nx * nx) {
+    int a = tid % nx, b = tid / nx;
+    s_small[1][a + nx * b] = __dmul_rn(0.5, __dadd_rn(s_small[0][a + nx * b], s_small[0][b + nx * a]));
+  }
+  // left_cov = I / Sigbar (:68): inverse via np right-hand sides, lower triangle mirrored
+  for (int64_t e = tid; e < pp; e += nth) Sinv[e] = ((e % np) == (e / np)) ? 1.0 : 0.0;
+  cta_chol_solve(Ls, np, Sinv, np);
+  for (int64_t e = tid; e < pp; e += nth) {
+    int i = (int)(e % np), j = (int)(e / np);
+    if (i < j) Sinv[e] = Sinv[j + (int64_t)np * i];
+  }
+  __syncthreads();
+  // symmetrise (:69) and factor: chol(left_cov_sym)
+  for (int64_t e = tid; e < pp; e += nth) {
+    int i = (int)(e % np), j = (int)(e / np);
+    Lv[e] = __dmul_rn(0.5, __dadd_rn(Sinv[i + (int64_t)np * j], Sinv[j + (int64_t)np * i]));
+  }
+  if (cta_cholesky(Lv, np, &s_fail)) {
+    if (tid == 0) atomicOr(&md.status[chain], 16);
+    return;
+  }
+  // Q ~ InverseWishart(ell_Q + T n_x, cov_M_sym) (:72-73) — n_x x n_x, one thread
+  if (tid == 0) {
+    double* Lc = s_small[1];
+    double* S = s_small[2];
+    double* B = s_small[3];
+    double* LB = s_small[4];
+    double* Wm = s_small[5];
+    double* Qn = s_small[6];
+    double* Lq = s_small[7];
+    int fail = 0;
+    double df = __dadd_rn(md.ell_Q, __dmul_rn((double)md.Tm1, (double)nx));
+    fail |= small_chol(Lc, nx);
+    if (!fail) {
+      small_inverse_from_chol(Lc, nx, S);
+      fail |= small_chol(S, nx);
+    }
+    if (!fail) {
+      for (int i = 0; i < nx * nx; ++i) B[i] = 0.0;
+      if (md.philox) {
+        for (int i = 0; i < nx; ++i)
+          B[i + nx * i] = __dsqrt_rn(mt_chi2_dev(md.seed, cid, md.sweep, (uint32_t)i, __dsub_rn(df, (double)i)));
+        int e = 0;
+        for (int c = 0; c < nx; ++c)
+          for (int r = c + 1; r < nx; ++r, ++e) {
+            double z0, z1;
+            pgb_normal_pair(pgb_stream_block(md.seed, PGB_STREAM_MNIW, cid, md.sweep, 200, (uint32_t)e), &z0, &z1);
+            B[r + nx * c] = z0;
+          }
+      } else {
+        const double* bi = md.bartlett + (int64_t)chain * nx * nx;
+        for (int c = 0; c < nx; ++c)
+          for (int r = c; r < nx; ++r) B[r + nx * c] = bi[r + nx * c];
+      }
+      for (int r = 0; r < nx; ++r)
+        for (int c = 0; c < nx; ++c) {
+          double acc = 0.0;
+          for (int k = 0; k < nx; ++k) acc = __fma_rn(S[r + nx * k], B[k + nx * c], acc);
+          LB[r + nx * c] = acc;
+        }
+      for (int r = 0; r < nx; ++r)
+        for (int c = 0; c < nx; ++c) {
+          double acc = 0.0;
+          for (int k = 0; k < nx; ++k) acc = __fma_rn(LB[r + nx * k], LB[c + nx * k], acc);
+          Wm[r + nx * c] = acc;
+        }
+      fail |= small_chol(Wm, nx);
+    }
+    if (!fail) {
+      small_inverse_from_chol(Wm, nx, Qn);
+      for (int i = 0; i < nx * nx; ++i) Lq[i] = Qn[i];
+      fail |= small_chol(Lq, nx);
+    }
+    if (fail) s_fail = 1;
+  }
+  // matrix-normal normals X (n_x x n_phi, column-major) (:77)
+  if (md.philox) {
+    const int tot = nx * np;
+    for (int p = tid; p < (tot + 1) / 2; p += nth) {
+      double z0, z1;
+      pgb_normal_pair(pgb_stream_block(md.seed, PGB_STREAM_MNIW, cid, md.sweep, 300, (uint32_t)p), &z0, &z1);
+      Xn[2 * p] = z0;
+      if (2 * p + 1 < tot) Xn[2 * p + 1] = z1;
+    }
+  } else {
+    const double* xi = md.Xmn + (int64_t)chain * nx * np;
+    for (int e = tid; e < nx * np; e += nth) Xn[e] = xi[e];
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) atomicOr(&md.status[chain], 16);
+    return;
+  }
+  // A = M + chol(Q).L * X * chol(left_cov_sym).U (:76-77)
+  const double* Lq = s_small[7];
+  for (int e = tid; e < nx * np; e += nth) {
+    int r = e % nx, i = e / nx;
+    double acc = 0.0;
+    for (int k = 0; k <= r; ++k) acc = __fma_rn(Lq[r + nx * k], Xn[k + nx * i], acc);
+    LX[e] = acc;
+  }
+  __syncthreads();
+  for (int e = tid; e < nx * np; e += nth) {
+    int r = e % nx, i = e / nx;
+    double acc = 0.0;
+    for (int k = 0; k <= i; ++k) acc = __fma_rn(LX[r + nx * k], Lv[i + (int64_t)np * k], acc);
+    Aout[e] = __dadd_rn(Mp[e], acc);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < nx * nx; ++i) Qout[i] = s_small[6][i];
+    if (chain_params_from_Q(s_small[6], nx, md.Lq + chain * 16, md.c0 + chain)) atomicOr(&md.status[chain], 16);
+  }
+}
+
+}  // namespace pgb
