@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — CPF-AS particle-steps/s (N = 2^20, T = 2000) and PG sweeps/s on B200.
+
+A "step" is one conditional particle-Gibbs sweep (k > 1 branch of Julia/src/particle_Gibbs.jl:168-200:
+T-1 resample / propagate / ancestor-sample / weight steps over N particles, then trace + statistics)
+on synthetic data shaped like BASELINE.json configs[2]: the reduced-rank-GP ("generic") basis model,
+n_x = 2, n_phi = 125, single GPU, counter-based (Philox) random streams.  With --gpus N > 1 every rank
+runs its own independent chain of the same size (weak scaling, no collective on the data path); the
+end-to-end leg gathers the packed (A, Q, x_T) samples over NCCL.
+
+  value : particle-steps/s of the filter phase, inputs resident in HBM, CUDA-event timed
+  e2e   : the same metric through the public API with HOST buffers (pinned) — u, y, A, Q, x_prim go
+          H2D and the PG_sample (A, Q, w_m1, x_m1) comes back D2H inside the timed region, and the
+          sweep includes the MNIW draw
+  --impl reference : the CPU oracle (restatement of the reference; Julia is not installable here) on
+          a bounded sample of the same workload, one host thread like the reference's sampler.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_PARTICLE_STEP = lambda n_x: 16 * n_x + 20      # x r+w, w r+w, Int32 ancestor
+FLOPS_PER_PARTICLE_STEP = {"generic": 1250.0, "known": 100.0}
+
+
+# ------------------------------------------------------------------------------------------- workload
+def f_true(x, u):
+    return np.array([0.8 * x[0] - 0.5 * x[1] + 0.1 * np.cos(3 * x[0]) * x[1],
+                     0.4 * x[0] + 0.5 * x[1] + (1 + 0.3 * np.sin(2 * x[1])) * u])
+
+
+def make_data(T, seed):
+    rng = np.random.default_rng(seed)
+    Lq = np.linalg.cholesky(np.array([[0.03, -0.004], [-0.004, 0.01]]))
+    u = rng.normal(0, 3, (1, T))
+    x = np.zeros((2, T + 1))
+    x[:, 0] = rng.normal(2, 1, 2)
+    y = np.zeros((1, T))
+    for t in range(T):
+        x[:, t + 1] = f_true(x[:, t], u[0, t]) + Lq @ rng.normal(size=2)
+        y[0, t] = x[0, t] + 0.1 * rng.normal()
+    return u, y, x
+
+
+def hilbert_phi_np(count, L, x, u):
+    """vectorised NumPy statement of the reduced-rank GP basis (only used to build a plausible A)"""
+    z = np.vstack([u, x])
+    nz = len(L)
+    phi = np.ones((1, z.shape[1]))
+    for k in range(nz):
+        j = np.arange(1, count[k] + 1)[:, None]
+        tk = (1 / np.sqrt(L[k])) * np.sin((np.pi * j / (2 * L[k])) * (z[k][None, :] + L[k]))
+        phi = (phi[:, None, :] * tk[None, :, :]).reshape(-1, z.shape[1])
+    return phi
+
+
+def build_problem(model, T, seed=0):
+    import pgopt_b200 as pg
+    u, y, x = make_data(T, seed)
+    if model == "known":
+        basis = pg.KnownBasisVB()
+        A = np.array([[8.0, -5.0, 0.0, 10.0, 0.0], [4.0, 5.0, 1.0, 0.0, 3.0]])
+        V = 10 * np.ones(5)
+    else:
+        basis = pg.HilbertGPBasis([5, 5, 5], [10.0, 20.0, 20.0])
+        Phi = hilbert_phi_np(basis.count, basis.L, x[:, :T], u)
+        A = np.linalg.solve(Phi @ Phi.T + 1e-3 * np.eye(125), Phi @ x[:, 1:T + 1].T).T  # ridge fit on the true states
+        V = pg.hilbert_gp_prior_V([5, 5, 5], [10, 20, 20], 2 * np.pi * np.ones(3), 100 ** 2 / (8 * np.pi ** 4))
+    Q = np.array([[0.05, 0.0], [0.0, 0.03]])
+    return dict(basis=basis, u=u, y=y, A=A, Q=Q, V=V, x_prim=x[:, :T].copy(), n_phi=basis.n_phi)
+
+
+# ------------------------------------------------------------------------------------------- helpers
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+PROF_NAMES = ["k_prep", "k_norm", "k_scan_local", "k_resolve", "k_expand", "k_seq_exact", "k_expand_fallback",
+              "k_weights", "k_init", "tail(trace+stats)", "k_mniw"]
+
+
+def dist_setup(n_gpus):
+    if n_gpus <= 1 or "RANK" not in os.environ:
+        return None, 0, 1, 0
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist, rank, world, local
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def time_filter(eng, prob, steps, warmup, sweep_index=2):
+    """device-resident timing of pgb_sweep_filter; returns list of ms"""
+    from pgopt_b200._lib import lib, check
+    ms = []
+    for i in range(warmup + steps):
+        eng.set_state(prob["A"], prob["Q"], prob["x_prim"], sweep_index)   # untimed: same state every step
+        check(lib().pgb_timer_start(eng._h), eng._h)
+        eng.sweep_filter()
+        t = C.c_double(0)
+        check(lib().pgb_timer_stop(eng._h, C.byref(t)), eng._h)
+        if i >= warmup:
+            ms.append(t.value)
+    return ms
+
+
+def run_gpu(args):
+    import torch
+    import pgopt_b200 as pg
+    from pgopt_b200._lib import lib, check
+    dist, rank, world, local = dist_setup(args.gpus)
+    N, T = args.particles, args.T
+    prob = build_problem(args.model, T, seed=0)
+    n_x, n_u, n_y, n_phi = 2, 1, 1, prob["n_phi"]
+    eng = pg.ParticleGibbsEngine(prob["basis"], 1, N, T, n_chains=1, device=local)
+    eng.set_data(prob["u"], prob["y"])
+    eng.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+    eng.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+    eng.set_prior(prob["V"], 100 * np.eye(2), 10.0)
+    eng.set_rng_philox(1234, rank)
+
+    def barrier():
+        eng.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-resident timing (value)
+    n0 = C.c_int64(0)
+    for _ in range(args.warmup):
+        eng.set_state(prob["A"], prob["Q"], prob["x_prim"], 2)
+        eng.sweep_filter()
+    barrier()
+    check(lib().pgb_get_launch_count(eng._h, C.byref(n0)), eng._h)
+    clk = ClockSampler(local)
+    clk.start()
+    ms = time_filter(eng, prob, args.steps, 0)
+    barrier()
+    clocks = clk.stop()
+    n1 = C.c_int64(0)
+    check(lib().pgb_get_launch_count(eng._h, C.byref(n1)), eng._h)
+    t_total = sum(ms) / 1e3
+    if dist:
+        tt = torch.tensor([t_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_total = float(tt.item())
+    psteps = N * (T - 1) * args.steps
+    value = world * psteps / t_total
+    st, nfb, nscan = eng.status(0, clear=True)
+
+    # ---- per-kernel profile (separate pass: event pairs around every launch perturb the step time)
+    check(lib().pgb_profile(eng._h, 1), eng._h)
+    eng.set_state(prob["A"], prob["Q"], prob["x_prim"], 2)
+    eng.sweep_filter()
+    launches = (C.c_int64 * len(PROF_NAMES))()
+    pms = (C.c_double * len(PROF_NAMES))()
+    check(lib().pgb_get_profile(eng._h, launches, pms), eng._h)
+    check(lib().pgb_profile(eng._h, 0), eng._h)
+    prof = {PROF_NAMES[i]: {"launches": int(launches[i]), "ms": float(pms[i])} for i in range(len(PROF_NAMES))
+            if launches[i]}
+    tot_prof = sum(v["ms"] for v in prof.values()) or 1.0
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+
+    # ---- end to end through the public API with pinned host buffers
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+        return t, t.numpy()
+    keep = [pinned(prob["u"]), pinned(prob["y"]), pinned(np.asfortranarray(prob["A"]).ravel(order="F")),
+            pinned(np.asfortranarray(prob["Q"]).ravel(order="F")), pinned(np.asfortranarray(prob["x_prim"]).ravel(order="F"))]
+    hu, hy, hA, hQ, hxp = [k[1] for k in keep]
+    outA, outQ = pinned(np.zeros(n_x * n_phi)), pinned(np.zeros(n_x * n_x))
+    outw, outx = pinned(np.zeros(N)), pinned(np.zeros(n_x * N))
+    outu = np.zeros(n_u)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    h2d = (hu.nbytes + hy.nbytes + hA.nbytes + hQ.nbytes + hxp.nbytes)
+    d2h = outA[1].nbytes + outQ[1].nbytes + outw[1].nbytes + outx[1].nbytes
+
+    def e2e_step():
+        check(lib().pgb_set_data(eng._h, p(hu), p(hy)), eng._h)
+        check(lib().pgb_set_state(eng._h, 0, p(hA), p(hQ), p(hxp), C.c_int64(2)), eng._h)
+        check(lib().pgb_sweep(eng._h, C.c_int64(1)), eng._h)
+        check(lib().pgb_get_sample(eng._h, 0, p(outA[1]), p(outQ[1]), p(outw[1]), p(outx[1]), p(outu)), eng._h)
+        if dist:  # gather of the packed (A, Q, x_T) sample of every chain
+            pack = torch.from_numpy(np.concatenate([outA[1], outQ[1], outx[1][:n_x]])).cuda()
+            allp = [torch.empty_like(pack) for _ in range(world)]
+            dist.all_gather(allp, pack)
+            _ = allp[0].cpu()
+
+    for _ in range(max(1, args.warmup - 1)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    te = time.perf_counter() - t0
+    if dist:
+        tt = torch.tensor([te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+    e2e_value = world * psteps / te
+    sweeps_per_s = world * args.steps / te
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_sample(args.model, args.cpu_particles, args.cpu_T)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        bps = BYTES_PER_PARTICLE_STEP(n_x)
+        t_per_sweep = t_total / args.steps
+        achieved = bps * N * (T - 1) / t_per_sweep / 1e9
+        out = {
+            "metric": "CPF-AS particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_per_sweep, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "CPF-AS conditional sweep (k>1), %s-basis model n_x=2 n_phi=%d, N=%d particles, T=%d, "
+                                   "Philox streams, x/a history stored in HBM; BASELINE.json configs[2]"
+                                   % (args.model, n_phi, N, T),
+                       "N": N, "T": T, "n_phi": n_phi, "chains_per_gpu": 1,
+                       "l2": "per-step working set re-streamed; history (x: %d GB, a: %d GB) written once, larger than L2"
+                             % (N * T * n_x * 8 >> 30, N * T * 4 >> 30)},
+            "pg_sweeps_per_s": sweeps_per_s,
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "includes": "set_data+set_state H2D, filter+trace+stats+MNIW, get_sample D2H"},
+            "gpu_launches": int(n1.value - n0.value),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "one CPF-AS time step = k_prep + scan pipeline + k_expand + k_weights (%d launches/step)"
+                                   % ((n1.value - n0.value) // max(1, args.steps * (T - 1))),
+                         "algorithmic_bytes_per_particle_step": bps,
+                         "dominant_kernel": dom, "dominant_share": prof[dom]["ms"] / tot_prof,
+                         "fp64_tflops_achieved": FLOPS_PER_PARTICLE_STEP[args.model] * N * (T - 1) / t_per_sweep / 1e12,
+                         "note": "generic basis is FP64-pipe bound (SURVEY.md §8d); the HBM fraction is reported for the "
+                                 "contract, the FP64 rate is the binding one" if args.model == "generic" else ""},
+            "kernel_profile_ms_per_sweep": prof,
+            "resampling": {"status_bits": st, "exact_scans": nscan, "serial_fallbacks": nfb},
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    eng.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(model, Ns, Ts, repeats=1):
+    """Oracle (C restatement of particle_Gibbs.jl) timed on a bounded sample of the workload, 1 thread."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as O
+    prob = build_problem(model, Ts, seed=0)
+    b = prob["basis"]
+    om = O.known_model() if model == "known" else O.hilbert_model(2, 1, b.count, b.stride, b.L)
+    st = O.make_streams(philox=True, seed=1234, chain=0)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.sweep(om, Ns, Ts, prob["u"], prob["y"], [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), prob["A"], prob["Q"],
+                prob["x_prim"], False, st, 2, hist=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": Ns * (Ts - 1) / best, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": "one conditional sweep of the same model at N=%d, T=%d (%.1f s); the reference sampler is "
+                      "single-threaded (particle_Gibbs.jl:154-230), so is the port" % (Ns, Ts, best)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_sample(args.model, args.cpu_particles, args.cpu_T)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    sec = args.cpu_particles * (args.cpu_T - 1) / v
+    print(json.dumps({
+        "impl": "reference", "metric": "CPF-AS particle-steps/sec", "value": v, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "CPF-AS conditional sweep (k>1), %s-basis model, bounded sample N=%d, T=%d of the "
+                               "N=%d, T=%d workload" % (args.model, args.cpu_particles, args.cpu_T, args.particles, args.T)},
+        "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": 1, "kind": "port", "sample": vals[-1]["sample"]},
+        "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Julia/MATLAB are not installable in this image: the reference arm is the C oracle restating "
+                "Julia/src/particle_Gibbs.jl (oracle/pg_oracle.c)"}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="generic", choices=["generic", "known"])
+    ap.add_argument("--particles", type=int, default=2 ** 20)
+    ap.add_argument("--T", type=int, default=2000)
+    ap.add_argument("--cpu-particles", type=int, default=2 ** 13)
+    ap.add_argument("--cpu-T", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

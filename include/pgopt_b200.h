@@ -124,6 +124,19 @@ int pgb_get_status(pgb_handle* h, int32_t chain, int32_t* status_bits, int64_t* 
                    int32_t clear);
 int pgb_synchronize(pgb_handle* h);
 
+/* Measurement support (bench.py).  pgb_timer_start/stop bracket work on the handle's stream with
+ * CUDA events and return the elapsed device time.  pgb_profile(h, 1) additionally brackets every
+ * kernel launch of the filter with an event pair; pgb_get_profile returns, per kernel class
+ * (PGB_PROF_*), the number of launches and the summed device time since profiling was switched on.
+ * pgb_get_launch_count returns the number of kernels this handle has launched so far. */
+enum { PGB_PROF_PREP = 0, PGB_PROF_NORM, PGB_PROF_SCAN_LOCAL, PGB_PROF_RESOLVE, PGB_PROF_EXPAND, PGB_PROF_SEQ,
+       PGB_PROF_EXPAND_FB, PGB_PROF_WEIGHTS, PGB_PROF_INIT, PGB_PROF_TAIL, PGB_PROF_MNIW, PGB_PROF_NCLASS };
+int pgb_timer_start(pgb_handle* h);
+int pgb_timer_stop(pgb_handle* h, double* elapsed_ms);
+int pgb_profile(pgb_handle* h, int32_t on);
+int pgb_get_profile(pgb_handle* h, int64_t* launches /*[PGB_PROF_NCLASS]*/, double* ms /*[PGB_PROF_NCLASS]*/);
+int pgb_get_launch_count(pgb_handle* h, int64_t* n);
+
 /* Stand-alone helpers matching the exported Julia functions; host buffers in and out. */
 /* systematic_resampling(W, N) with rnd = the rand() of :21; idx is 1-based.  *status gets PGB_STATUS_* bits. */
 int pgb_systematic_resampling(int32_t device, const double* W, int64_t n_w, int64_t n_draw, double rnd,
@@ -144,6 +157,13 @@ int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Ph
 int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q, const double* w_m1,
                 const double* x_m1, const double* u_m1, const double* C, const double* Le, const double* u_init,
                 uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e, double* X, double* Y);
+
+/* ---- test hooks (not part of the drop-in surface) ---------------------------------------------
+ * pgb_test_force_fallback(1) makes every exact scan take the serial-walk fallback path (results must
+ * not change); pgb_test_math evaluates the device build of pgb_math.h: fn 0 exp, 1 log, 2 sin, 3 cos,
+ * 4 Box-Muller pairs from Philox (x[0] = seed, y gets 2n normals of purpose Z, sweep 1, t 5). */
+void pgb_test_force_fallback(int32_t on);
+int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_t n);
 
 #ifdef __cplusplus
 }

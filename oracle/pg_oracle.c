@@ -51,7 +51,10 @@ int orc_systematic_resampling(const double* W_in, int64_t n_w, int64_t n_draw, d
   int status = 0;
   double* W = (double*)malloc(sizeof(double) * (size_t)(n_w > 0 ? n_w : 1));
   double s = orc_pairwise_sum(W_in, n_w); /* :19 */
-  for (int64_t i = 0; i < n_w; ++i) W[i] = W_in[i] / s;
+  for (int64_t i = 0; i < n_w; ++i) {
+    W[i] = W_in[i] / s;
+    if (!(W[i] >= 0.0 && W[i] <= 1.7976931348623157e308)) status |= 4; /* NaN/Inf weights: the reference carries on silently */
+  }
   double inc = 1.0 / (double)n_draw;
   double u = inc * rnd; /* :21  u = 1 / N * rand() */
   double q = 0.0;       /* :23 */

@@ -65,7 +65,8 @@ int orc_selftest(void);
 
 double orc_pairwise_sum(const double* v, int64_t n);
 
-/* returns 0, or 1 when the reference would raise BoundsError (q_N < u_i), or 2 for idx 0 */
+/* returns status bits: 1 the reference would raise BoundsError (q_N < u_i), 2 an index 0 was returned,
+ * 4 a normalised weight is NaN/Inf/negative (the reference carries on silently) */
 int orc_systematic_resampling(const double* W, int64_t n_w, int64_t n_draw, double rnd,
                               int64_t* idx /* 1-based */);
 

@@ -1,0 +1,56 @@
+"""ctypes binding of libpgopt_b200.so (include/pgopt_b200.h).  Fails loudly when the CUDA library is
+missing: there is no CPU path in this package."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpgopt_b200.so")
+PGB_MAX_Z = 8
+
+PGB_OK, PGB_ERR_INVALID, PGB_ERR_CUDA, PGB_ERR_NOT_POSDEF, PGB_ERR_STATE = 0, 1, 2, 3, 4
+BASIS_KNOWN_VB, BASIS_HILBERT_GP = 0, 1
+STATUS_RESAMPLE_OVERRUN, STATUS_INDEX_ZERO, STATUS_NONFINITE, STATUS_NOT_POSDEF = 1, 2, 4, 16
+
+
+class PgbConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("n_x", C.c_int32), ("n_u", C.c_int32), ("n_y", C.c_int32),
+                ("n_phi", C.c_int32), ("basis", C.c_int32), ("hg_count", C.c_int32 * PGB_MAX_Z),
+                ("hg_stride", C.c_int32 * PGB_MAX_Z), ("hg_L", C.c_double * PGB_MAX_Z), ("N", C.c_int64),
+                ("T", C.c_int64), ("n_chains", C.c_int32), ("keep_w_history", C.c_int32)]
+
+
+class PgoptError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pgopt_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+EXPORTS = ["pgb_version", "pgb_last_error", "pgb_create", "pgb_destroy", "pgb_set_data", "pgb_set_measurement",
+           "pgb_set_init_dist", "pgb_set_prior", "pgb_set_state", "pgb_get_state", "pgb_set_rng_philox",
+           "pgb_set_rng_injected", "pgb_sweep", "pgb_sweep_filter", "pgb_sweep_mniw", "pgb_particle_gibbs",
+           "pgb_get_sample", "pgb_get_history", "pgb_get_stats", "pgb_get_status", "pgb_synchronize",
+           "pgb_systematic_resampling", "pgb_mniw_sample", "pgb_rollout", "pgb_test_force_fallback", "pgb_test_math",
+           "pgb_timer_start", "pgb_timer_stop", "pgb_profile", "pgb_get_profile", "pgb_get_launch_count"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libpgopt_b200.so is not built (%s); run `python -c 'import __graft_entry__ as g; "
+                              "g.build()'` or `python pgopt_b200/build.py`. There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.pgb_version.restype = C.c_char_p
+        L.pgb_last_error.restype = C.c_char_p
+        L.pgb_last_error.argtypes = [C.c_void_p]
+        L.pgb_destroy.restype = None
+        L.pgb_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        msg = lib().pgb_last_error(handle)
+        raise PgoptError(rc, msg.decode() if msg else "unknown")

@@ -1,0 +1,375 @@
+"""Host-side mirror of the reference's Julia API for the hot path, over libpgopt_b200.so.
+
+Same names, argument order and meaning as Julia/src/particle_Gibbs.jl and
+Julia/src/optimal_control_Ipopt.jl; arrays are NumPy, column-major ("F") where the reference passes
+matrices, indices 1-based like Julia's.  Julia closures cannot cross a C ABI, so `phi` and `g` are
+descriptor objects (KnownBasisVB / HilbertGPBasis, LinearMeasurement); passing an arbitrary callable
+raises TypeError — there is no CPU fallback path.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import PgbConfig, PgoptError, check, lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a):
+    """contiguous float64 vector holding `a` in column-major order"""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F"))
+
+
+# ----------------------------------------------------------------------------------------------
+# descriptors
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class PG_sample:
+    """Julia/src/PGopt.jl:23-29"""
+    A: np.ndarray      # (n_x, n_phi)
+    Q: np.ndarray      # (n_x, n_x)
+    w_m1: np.ndarray   # (N,)
+    x_m1: np.ndarray   # (n_x, N)
+    u_m1: np.ndarray   # (n_u,)
+
+
+class KnownBasisVB:
+    """phi of Julia/examples/PG_OCP_known_basis_functions_Altro.jl:34 (n_x = 2, n_u = 1, n_phi = 5)."""
+    n_x, n_u, n_phi = 2, 1, 5
+
+    def fill(self, cfg):
+        cfg.basis = _lib.BASIS_KNOWN_VB
+
+
+class HilbertGPBasis:
+    """phi_sampling of Julia/examples/PG_OCP_generic_basis_functions_Altro.jl:52-99.
+
+    n_phi_dims = [n_phi_u..., n_phi_x...] and L = [L_u..., L_x...] exactly as in the example.  The
+    reference enumerates the index vectors with slot 1 fastest (:59-72) and then reverses them
+    (:82), so augmented dimension k (z = [u; x]) uses slot n_z+1-k: its count is
+    n_phi_dims[n_z+1-k] and its stride prod(n_phi_dims[1:n_z-k]) — the last state varies fastest.
+    """
+
+    def __init__(self, n_phi_dims, L, n_u=1):
+        self.n_phi_dims = [int(v) for v in np.ravel(n_phi_dims)]
+        self.L = [float(v) for v in np.ravel(L)]
+        if len(self.n_phi_dims) != len(self.L):
+            raise ValueError("n_phi_dims and L must have one entry per augmented dimension")
+        self.n_z = len(self.L)
+        self.n_u = int(n_u)
+        self.n_x = self.n_z - self.n_u
+        self.n_phi = int(np.prod(self.n_phi_dims))
+        nz = self.n_z
+        self.count = [self.n_phi_dims[nz - 1 - k] for k in range(nz)]
+        self.stride = [int(np.prod(self.n_phi_dims[:nz - 1 - k])) for k in range(nz)]
+
+    def fill(self, cfg):
+        cfg.basis = _lib.BASIS_HILBERT_GP
+        for k in range(self.n_z):
+            cfg.hg_count[k], cfg.hg_stride[k], cfg.hg_L[k] = self.count[k], self.stride[k], self.L[k]
+
+
+def hilbert_gp_prior_V(n_phi_dims, L, l, sf):
+    """Diagonal of the prior V from the SE spectral density, generic example :59-80,:111-115.
+    Replicates the reference: lambda is computed *before* the index reversal (:78 vs :82)."""
+    n_phi_dims = [int(v) for v in np.ravel(n_phi_dims)]
+    L = np.asarray(L, dtype=np.float64).ravel()
+    l = np.asarray(l, dtype=np.float64).ravel()
+    nz = len(L)
+    n_phi = int(np.prod(n_phi_dims))
+    variants = np.concatenate([[1], np.cumprod(n_phi_dims[:-1])]).astype(np.int64)
+    V = np.empty(n_phi)
+    for i in range(n_phi):
+        rem = i
+        sub = np.zeros(nz)
+        for j in range(nz - 1, -1, -1):
+            sub[j] = rem // variants[j] + 1
+            rem = rem % variants[j]
+        lam = (np.pi * sub / (2 * L)) ** 2
+        V[i] = sf * ((2 * np.pi) ** (nz / 2)) * np.prod(l) * np.exp(-0.5 * np.sum((l ** 2) * lam))
+    return V
+
+
+class LinearMeasurement:
+    """g(x, u) = C*x (both reference examples use [1 0]*x, known example :54)."""
+
+    def __init__(self, C_):
+        self.C = np.atleast_2d(np.asarray(C_, dtype=np.float64))
+
+
+class MvNormal:
+    """x_init_dist = MvNormal(mean, cov) (known example :48-50); cov scalar, vector (diag) or matrix."""
+
+    def __init__(self, mean, cov):
+        self.mean = np.asarray(mean, dtype=np.float64).ravel()
+        n = self.mean.size
+        cov = np.asarray(cov, dtype=np.float64)
+        if cov.ndim == 0:
+            cov = float(cov) * np.eye(n)
+        elif cov.ndim == 1:
+            cov = np.diag(cov)
+        self.cov = cov
+        self.chol = np.linalg.cholesky(cov)
+
+
+def _basis(phi):
+    if isinstance(phi, (KnownBasisVB, HilbertGPBasis)):
+        return phi
+    raise TypeError("phi must be a KnownBasisVB or HilbertGPBasis descriptor: arbitrary closures cannot cross the "
+                    "C ABI and pgopt_b200 has no CPU fallback")
+
+
+def _meas(g):
+    if isinstance(g, LinearMeasurement):
+        return g
+    if isinstance(g, np.ndarray):
+        return LinearMeasurement(g)
+    raise TypeError("g must be a LinearMeasurement (g(x,u) = C*x) or the matrix C")
+
+
+def _make_cfg(phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False):
+    b = _basis(phi)
+    cfg = PgbConfig()
+    cfg.device, cfg.n_x, cfg.n_u, cfg.n_y, cfg.n_phi = device, b.n_x, b.n_u, n_y, b.n_phi
+    b.fill(cfg)
+    cfg.N, cfg.T, cfg.n_chains, cfg.keep_w_history = int(N), int(T), int(n_chains), int(keep_w_history)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------
+# engine (one handle = one device, one stream, n_chains batched chains)
+# ----------------------------------------------------------------------------------------------
+class ParticleGibbsEngine:
+    def __init__(self, phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False):
+        self.cfg = _make_cfg(phi, n_y, N, T, n_chains, device, keep_w_history)
+        self.n_x, self.n_u, self.n_y, self.n_phi = self.cfg.n_x, self.cfg.n_u, n_y, self.cfg.n_phi
+        self.N, self.T, self.n_chains = int(N), int(T), int(n_chains)
+        self._h = C.c_void_p()
+        check(lib().pgb_create(C.byref(self._h), C.byref(self.cfg)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().pgb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        check(rc, self._h)
+
+    def set_data(self, u, y):
+        u, y = _f(np.atleast_2d(u)), _f(np.atleast_2d(y))
+        assert u.size == self.n_u * self.T and y.size == self.n_y * self.T
+        self._ck(lib().pgb_set_data(self._h, _p(u), _p(y)))
+
+    def set_measurement(self, g, R):
+        g = _meas(g)
+        Cm, Rm = _f(g.C), _f(np.atleast_2d(np.asarray(R, dtype=np.float64)))
+        assert Cm.size == self.n_y * self.n_x and Rm.size == self.n_y * self.n_y
+        self._ck(lib().pgb_set_measurement(self._h, _p(Cm), _p(Rm)))
+
+    def set_init_dist(self, dist):
+        self._ck(lib().pgb_set_init_dist(self._h, _p(_f(dist.mean)), _p(_f(dist.chol))))
+
+    def set_prior(self, V, Lambda_Q, ell_Q):
+        V = np.asarray(V, dtype=np.float64)
+        if V.ndim == 2:
+            if np.count_nonzero(V - np.diag(np.diag(V))):
+                raise ValueError("only a diagonal prior covariance V is supported (both reference examples)")
+            V = np.diag(V)
+        LQ = np.asarray(Lambda_Q, dtype=np.float64)
+        self._ck(lib().pgb_set_prior(self._h, _p(_f(V)), _p(_f(LQ)), C.c_double(float(ell_Q))))
+
+    def set_state(self, A, Q, x_prim=None, sweep_index=1, chain=0):
+        xp = None if x_prim is None else _f(x_prim)
+        self._ck(lib().pgb_set_state(self._h, C.c_int32(chain), _p(_f(A)), _p(_f(Q)), _p(xp), C.c_int64(sweep_index)))
+
+    def get_state(self, chain=0):
+        A, Q, xp = np.empty(self.n_x * self.n_phi), np.empty(self.n_x * self.n_x), np.empty(self.n_x * self.T)
+        k = C.c_int64(0)
+        self._ck(lib().pgb_get_state(self._h, C.c_int32(chain), _p(A), _p(Q), _p(xp), C.byref(k)))
+        return (A.reshape((self.n_x, self.n_phi), order="F"), Q.reshape((self.n_x, self.n_x), order="F"),
+                xp.reshape((self.n_x, self.T), order="F"), k.value)
+
+    def set_rng_philox(self, seed, chain_base=0):
+        self._ck(lib().pgb_set_rng_philox(self._h, C.c_uint64(seed), C.c_uint32(chain_base)))
+
+    def set_rng_injected(self, Z0, Ures, Z, Uanc, Ustar, bartlett=None, Xmn=None, chain=0):
+        """Z0 (N-1, n_x), Ures (T,), Z (T, N, n_x), Uanc (T,), Ustar, bartlett (n_x,n_x) lower, Xmn (n_x,n_phi)."""
+        Z0c = np.ascontiguousarray(Z0, dtype=np.float64)
+        Zc = np.ascontiguousarray(Z, dtype=np.float64)
+        assert Z0c.size == (self.N - 1) * self.n_x and Zc.size == self.T * self.N * self.n_x
+        b = None if bartlett is None else _f(bartlett)
+        X = None if Xmn is None else _f(Xmn)
+        self._ck(lib().pgb_set_rng_injected(self._h, C.c_int32(chain), _p(Z0c), _p(_f(Ures)), _p(Zc), _p(_f(Uanc)),
+                                            C.c_double(float(Ustar)), _p(b), _p(X)))
+
+    def sweep(self, n_sweeps=1):
+        self._ck(lib().pgb_sweep(self._h, C.c_int64(n_sweeps)))
+
+    def sweep_filter(self):
+        self._ck(lib().pgb_sweep_filter(self._h))
+
+    def sweep_mniw(self):
+        self._ck(lib().pgb_sweep_mniw(self._h))
+
+    def synchronize(self):
+        self._ck(lib().pgb_synchronize(self._h))
+
+    def get_sample(self, chain=0):
+        A, Q = np.empty(self.n_x * self.n_phi), np.empty(self.n_x * self.n_x)
+        w, x, u = np.empty(self.N), np.empty(self.n_x * self.N), np.empty(self.n_u)
+        self._ck(lib().pgb_get_sample(self._h, C.c_int32(chain), _p(A), _p(Q), _p(w), _p(x), _p(u)))
+        return PG_sample(A.reshape((self.n_x, self.n_phi), order="F"), Q.reshape((self.n_x, self.n_x), order="F"), w,
+                         x.reshape((self.n_x, self.N), order="F"), u)
+
+    def get_history(self, chain=0, want_w=True):
+        a = np.zeros((self.T, self.N), dtype=np.int64)
+        x = np.zeros((self.T, self.N, self.n_x))
+        w = np.zeros((self.T, self.N)) if want_w else None
+        self._ck(lib().pgb_get_history(self._h, C.c_int32(chain), _p(a), _p(x), _p(w)))
+        return a, x, w
+
+    def get_stats(self, chain=0):
+        Phi, Psi, Sig = np.empty(self.n_x ** 2), np.empty(self.n_x * self.n_phi), np.empty(self.n_phi ** 2)
+        star = C.c_int64(0)
+        self._ck(lib().pgb_get_stats(self._h, C.c_int32(chain), _p(Phi), _p(Psi), _p(Sig), C.byref(star)))
+        return (Phi.reshape((self.n_x, self.n_x), order="F"), Psi.reshape((self.n_x, self.n_phi), order="F"),
+                Sig.reshape((self.n_phi, self.n_phi), order="F"), star.value)
+
+    def status(self, chain=0, clear=False):
+        st, nf, ns = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+        self._ck(lib().pgb_get_status(self._h, C.c_int32(chain), C.byref(st), C.byref(nf), C.byref(ns), C.c_int32(int(clear))))
+        return st.value, nf.value, ns.value
+
+    def particle_gibbs(self, K, K_b, k_d, keep_particles=True):
+        nc, nx, np_, N = self.n_chains, self.n_x, self.n_phi, self.N
+        A_s, Q_s = np.empty((nc, K, nx * np_)), np.empty((nc, K, nx * nx))
+        w_s = np.empty((nc, K, N)) if keep_particles else None
+        x_s = np.empty((nc, K, nx * N)) if keep_particles else None
+        u_m1 = np.empty(self.n_u)
+        self._ck(lib().pgb_particle_gibbs(self._h, C.c_int64(K), C.c_int64(K_b), C.c_int64(k_d), _p(A_s), _p(Q_s),
+                                          _p(w_s), _p(x_s), _p(u_m1)))
+        return A_s, Q_s, w_s, x_s, u_m1
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's exported functions
+# ----------------------------------------------------------------------------------------------
+def systematic_resampling(W, N, rnd=None, rng=None, device=0, return_status=False):
+    """systematic_resampling(W, N) — Julia/src/particle_Gibbs.jl:17-34.  `rnd` is the rand() of :21
+    (drawn from `rng` / NumPy when omitted).  Returns 1-based Int64 indices."""
+    W = np.ascontiguousarray(W, dtype=np.float64).ravel()
+    if rnd is None:
+        rnd = (rng or np.random.default_rng()).random()
+    idx = np.empty(int(N), dtype=np.int64)
+    st = C.c_int32(0)
+    check(lib().pgb_systematic_resampling(C.c_int32(device), _p(W), C.c_int64(W.size), C.c_int64(int(N)),
+                                          C.c_double(float(rnd)), _p(idx), C.byref(st)))
+    if st.value & _lib.STATUS_RESAMPLE_OVERRUN and not return_status:
+        raise IndexError("BoundsError: attempt to access %d-element Vector at index [%d] (weights sum below the "
+                         "sampling grid, Julia/src/particle_Gibbs.jl:28)" % (W.size, W.size + 1))
+    return (idx, st.value) if return_status else idx
+
+
+def MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T, bartlett=None, Xmn=None, seed=0, chain=0, sweep_index=1,
+                device=0):
+    """MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T) — Julia/src/particle_Gibbs.jl:56-81.
+    The Bartlett factor / matrix-normal normals may be injected (parity) or come from Philox."""
+    Phi, Psi, Sigma = np.atleast_2d(Phi), np.atleast_2d(Psi), np.atleast_2d(Sigma)
+    n_x, n_phi = Psi.shape
+    V = np.asarray(V, dtype=np.float64)
+    if V.ndim == 2:
+        if np.count_nonzero(V - np.diag(np.diag(V))):
+            raise ValueError("only a diagonal V is supported")
+        V = np.diag(V)
+    A, Q = np.empty(n_x * n_phi), np.empty(n_x * n_x)
+    b = None if bartlett is None else _f(bartlett)
+    X = None if Xmn is None else _f(Xmn)
+    check(lib().pgb_mniw_sample(C.c_int32(device), C.c_int32(n_x), C.c_int32(n_phi), _p(_f(Phi)), _p(_f(Psi)),
+                                _p(_f(Sigma)), _p(_f(V)), _p(_f(np.asarray(Lambda_Q, dtype=np.float64))),
+                                C.c_double(float(ell_Q)), C.c_int64(int(T)), _p(b), _p(X), C.c_uint64(seed),
+                                C.c_uint32(chain), C.c_uint32(sweep_index), _p(A), _p(Q)))
+    return A.reshape((n_x, n_phi), order="F"), Q.reshape((n_x, n_x), order="F")
+
+
+def particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist, g, R,
+                   x_prim=None, seed=0, chain=0, device=0, verbose=False):
+    """particle_Gibbs(u, y, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist, g, R; x_prim)
+    — Julia/src/particle_Gibbs.jl:114-237.  Returns a list of K PG_sample.  `x_prim`, when given, is
+    updated in place like the reference does (:214-217)."""
+    u = np.atleast_2d(np.asarray(u_training, dtype=np.float64))
+    y = np.atleast_2d(np.asarray(y_training, dtype=np.float64))
+    A_init = np.atleast_2d(np.asarray(A_init, dtype=np.float64))
+    n_y, T = y.shape
+    eng = ParticleGibbsEngine(phi, n_y, N, T, 1, device)
+    try:
+        eng.set_data(u, y)
+        eng.set_measurement(g, R)
+        eng.set_init_dist(x_init_dist)
+        eng.set_prior(V, Lambda_Q, ell_Q)
+        eng.set_state(A_init, np.asarray(Q_init, dtype=np.float64) * np.eye(A_init.shape[0])
+                      if np.ndim(Q_init) == 0 else Q_init, x_prim, 1)
+        eng.set_rng_philox(seed, chain)
+        if verbose:
+            print("### Started learning algorithm")
+        A_s, Q_s, w_s, x_s, u_m1 = eng.particle_gibbs(K, K_b, k_d)
+        if x_prim is not None:
+            x_prim[...] = eng.get_state()[2]
+        n_x, n_phi = eng.n_x, eng.n_phi
+        out = []
+        for k in range(K):
+            out.append(PG_sample(A_s[0, k].reshape((n_x, n_phi), order="F"), Q_s[0, k].reshape((n_x, n_x), order="F"),
+                                 w_s[0, k].copy(), x_s[0, k].reshape((n_x, N), order="F"), u_m1.copy()))
+        if verbose:
+            print("### Learning complete")
+        return out
+    finally:
+        eng.close()
+
+
+def scenario_rollout(PG_samples, phi, g, R, H, u_init=None, seed=0, k_offset=0, device=0):
+    """Scenario sampling and forward rollout that solve_PG_OCP_Ipopt performs before building the NLP
+    (Julia/src/optimal_control_Ipopt.jl:47-83,114-125).  Returns the arrays in the reference's layouts so
+    they can be passed back through its `x_vec_0`, `v_vec`, `e_vec`, `u_init` keyword arguments:
+    x_vec_0 (n_x*K,), v_vec (n_x,H,K), e_vec (n_y,H,K), X_init (n_x*K,H+1), Y_init (n_y*K,H)."""
+    b = _basis(phi)
+    gm = _meas(g)
+    K = len(PG_samples)
+    n_x, n_u, n_phi = b.n_x, b.n_u, b.n_phi
+    n_y = gm.C.shape[0]
+    N = PG_samples[0].w_m1.size
+    if np.ndim(R) == 0:
+        Le = np.array([[float(R)]])  # MvNormal(zeros(n_y), R::Real) reads R as a std (reference quirk, :79)
+    else:
+        Le = np.linalg.cholesky(np.atleast_2d(np.asarray(R, dtype=np.float64)))
+    if u_init is None:
+        u_init = np.zeros((n_u, H))  # :110
+    cfg = _make_cfg(b, n_y, N, 2, 1, device)
+    A = np.ascontiguousarray(np.stack([_f(s.A) for s in PG_samples]))
+    Q = np.ascontiguousarray(np.stack([_f(s.Q) for s in PG_samples]))
+    w = np.ascontiguousarray(np.stack([np.asarray(s.w_m1, dtype=np.float64).ravel() for s in PG_samples]))
+    x = np.ascontiguousarray(np.stack([_f(s.x_m1) for s in PG_samples]))
+    um = np.ascontiguousarray(np.stack([np.asarray(s.u_m1, dtype=np.float64).ravel() for s in PG_samples]))
+    x0, v, e = np.empty((K, n_x)), np.empty((K, H, n_x)), np.empty((K, H, n_y))
+    X, Y = np.empty((K, H + 1, n_x)), np.empty((K, H, n_y))
+    check(lib().pgb_rollout(C.byref(cfg), C.c_int64(K), C.c_int64(H), _p(A), _p(Q), _p(w), _p(x), _p(um), _p(_f(gm.C)),
+                            _p(_f(Le)), _p(_f(np.atleast_2d(u_init))), C.c_uint64(seed), C.c_uint32(k_offset),
+                            _p(x0), _p(v), _p(e), _p(X), _p(Y)))
+    return dict(x_vec_0=x0.reshape(-1), v_vec=np.transpose(v, (2, 1, 0)), e_vec=np.transpose(e, (2, 1, 0)),
+                X_init=np.transpose(X, (0, 2, 1)).reshape(K * n_x, H + 1),
+                Y_init=np.transpose(Y, (0, 2, 1)).reshape(K * n_y, H), raw=dict(x0=x0, v=v, e=e, X=X, Y=Y))

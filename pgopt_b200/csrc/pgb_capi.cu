@@ -18,6 +18,7 @@
 using namespace pgb;
 
 static thread_local std::string g_last_error;
+static int g_force_fallback = 0;
 
 struct pgb_handle {
   pgb_config cfg;
@@ -41,7 +42,55 @@ struct pgb_handle {
   // the (A, Q) the last filter pass ran with (sample fields, particle_Gibbs.jl:204-205)
   double *d_A_used = nullptr, *d_Q_used = nullptr;
   bool injected_ready = false;
+  // measurement
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool profile = false;
+  int64_t n_launch = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_class;   // class of pair i (events 2i, 2i+1)
+  size_t ev_used = 0;
+  int64_t prof_launches[PGB_PROF_NCLASS] = {0};
+  double prof_ms[PGB_PROF_NCLASS] = {0};
 };
+
+// Bracket one launch: counts it and, in profiling mode, records an event pair around it.
+struct LaunchScope {
+  pgb_handle* h;
+  cudaEvent_t e1 = nullptr;
+  LaunchScope(pgb_handle* h_, int cls) : h(h_) {
+    h->n_launch += 1;
+    if (!h->profile) return;
+    if (h->ev_used + 2 > h->ev_pool.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev_pool.push_back(e);
+      }
+    }
+    cudaEvent_t e0 = h->ev_pool[h->ev_used];
+    e1 = h->ev_pool[h->ev_used + 1];
+    h->ev_used += 2;
+    h->ev_class.push_back(cls);
+    cudaEventRecord(e0, h->stream);
+  }
+  ~LaunchScope() {
+    if (e1) cudaEventRecord(e1, h->stream);
+  }
+};
+#define LAUNCH(h, cls, ...) do { LaunchScope ls_(h, cls); __VA_ARGS__; } while (0)
+
+static void profile_collect(pgb_handle* h) {
+  if (!h->ev_used) return;
+  cudaStreamSynchronize(h->stream);
+  for (size_t i = 0; i < h->ev_used / 2; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]);
+    h->prof_launches[h->ev_class[i]] += 1;
+    h->prof_ms[h->ev_class[i]] += ms;
+  }
+  h->ev_used = 0;
+  h->ev_class.clear();
+}
 
 static int set_err(pgb_handle* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -242,6 +291,9 @@ extern "C" void pgb_destroy(pgb_handle* h) {
     cudaStreamDestroy(h->stream);
   }
   for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
 }
 
@@ -327,7 +379,7 @@ extern "C" int pgb_set_state(pgb_handle* h, int32_t chain, const double* A, cons
     CK(h, cudaMemcpyAsync(h->fd.xprim + (size_t)chain * nx * T, x_prim, (size_t)nx * T * 8, cudaMemcpyHostToDevice, h->stream));
   else
     CK(h, cudaMemsetAsync(h->fd.xprim + (size_t)chain * nx * T, 0, (size_t)nx * T * 8, h->stream));
-  k_chain_params<<<(nc + 31) / 32, 32, 0, h->stream>>>(nc, nx, h->d_Q, h->fd.Lq, h->fd.c0, h->fd.status);
+  k_chain_params<<<1, 32, 0, h->stream>>>(chain, nx, h->d_Q, h->fd.Lq, h->fd.c0, h->fd.status);
   CK(h, cudaGetLastError());
   CK(h, cudaStreamSynchronize(h->stream));
   h->sweep_index = sweep_index;
@@ -403,11 +455,13 @@ static void launch_scan(pgb_handle* h, const ScanWS& ws, const double* v, const 
   const FilterDev& fd = h->fd;
   cudaStream_t s = h->stream;
   dim3 gt(ws.nt, fd.nc), g1(1, fd.nc);
-  k_scan_local<<<gt, TPB, 0, s>>>(ws, v, fd.status);
-  k_resolve<<<g1, TPB, 0, s>>>(ws);
-  k_expand<NX, MODE><<<gt, TPB, 0, s>>>(fd, ws, v, utab, utab_stride, utab_index, out_idx, out_stride, t, first, 0);
-  k_seq_exact<<<g1, 32, 0, s>>>(ws, v, fd.status, maxkey_reset);
-  k_expand<NX, MODE><<<gt, TPB, 0, s>>>(fd, ws, v, utab, utab_stride, utab_index, out_idx, out_stride, t, first, 1);
+  LAUNCH(h, PGB_PROF_SCAN_LOCAL, (k_scan_local<<<gt, TPB, 0, s>>>(ws, v, fd.status)));
+  LAUNCH(h, PGB_PROF_RESOLVE, (k_resolve<<<g1, TPB, 0, s>>>(ws, g_force_fallback)));
+  LAUNCH(h, PGB_PROF_EXPAND, (k_expand<NX, MODE><<<gt, TPB, 0, s>>>(fd, ws, v, utab, utab_stride, utab_index, out_idx,
+                                                                    out_stride, t, first, 0)));
+  LAUNCH(h, PGB_PROF_SEQ, (k_seq_exact<<<g1, 32, 0, s>>>(ws, v, fd.status, maxkey_reset)));
+  LAUNCH(h, PGB_PROF_EXPAND_FB, (k_expand<NX, MODE><<<gt, TPB, 0, s>>>(fd, ws, v, utab, utab_stride, utab_index, out_idx,
+                                                                       out_stride, t, first, 1)));
 }
 
 template <int NX>
@@ -426,26 +480,26 @@ static int run_filter_nx(pgb_handle* h) {
   CK(h, cudaMemsetAsync(fd.maxkey, 0, (size_t)nc * 8, s));
   dim3 gt(fd.nt, nc);
   const size_t smA = (size_t)NX * fd.n_phi * 8;
-  k_build_utabs<<<dim3((unsigned)((T + 127) / 128), nc), 128, 0, s>>>(fd, first);
-  k_init<NX><<<dim3((unsigned)((N + TPB - 1) / TPB), nc), TPB, 0, s>>>(fd, first);
-  k_weights<<<gt, TPB, 0, s>>>(fd);
+  LAUNCH(h, PGB_PROF_INIT, (k_build_utabs<<<dim3((unsigned)((T + 127) / 128), nc), 128, 0, s>>>(fd, first)));
+  LAUNCH(h, PGB_PROF_INIT, (k_init<NX><<<dim3((unsigned)((N + TPB - 1) / TPB), nc), TPB, 0, s>>>(fd, first)));
+  LAUNCH(h, PGB_PROF_WEIGHTS, (k_weights<<<gt, TPB, 0, s>>>(fd)));
   for (int64_t t = 1; t < T; ++t) {
-    k_prep<NX><<<gt, TPB, smA, s>>>(fd, t, first);
+    LAUNCH(h, PGB_PROF_PREP, (k_prep<NX><<<gt, TPB, smA, s>>>(fd, t, first)));
     launch_scan<NX, MODE_PROPAGATE>(h, fd.main, fd.wbuf, fd.utab_res, T, t, nullptr, 0, t, first, fd.maxkey);
     if (!first) {
-      k_norm<<<gt, TPB, 0, s>>>(fd);
+      LAUNCH(h, PGB_PROF_NORM, (k_norm<<<gt, TPB, 0, s>>>(fd)));
       launch_scan<NX, MODE_INDEX>(h, fd.side, fd.waN, fd.utab_anc, T, t, fd.ah + t * N + (N - 1), T * N, t, first, nullptr);
     }
-    k_weights<<<gt, TPB, 0, s>>>(fd);
+    LAUNCH(h, PGB_PROF_WEIGHTS, (k_weights<<<gt, TPB, 0, s>>>(fd)));
   }
   // w_T, then star = systematic_resampling(w[end,:], 1)   (:213)
-  k_prep<NX><<<gt, TPB, smA, s>>>(fd, T, first);
+  LAUNCH(h, PGB_PROF_TAIL, (k_prep<NX><<<gt, TPB, smA, s>>>(fd, T, first)));
   launch_scan<NX, MODE_INDEX>(h, fd.main, fd.wbuf, fd.utab_star, 1, 0, h->d_star_idx, 1, 0, first, nullptr);
-  k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out);
+  LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
   // statistics (:221-225)
-  k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md);
+  LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
   const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
-  k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md);
+  LAUNCH(h, PGB_PROF_TAIL, (k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md)));
   CK(h, cudaGetLastError());
   return PGB_OK;
 }
@@ -461,7 +515,7 @@ static int run_filter(pgb_handle* h) {
 
 static int run_mniw(pgb_handle* h) {
   if (!h->have_prior) return set_err(h, PGB_ERR_STATE, "pgb_set_prior must be called before the MNIW draw");
-  k_mniw<<<h->fd.nc, MNIW_TPB, 0, h->stream>>>(h->md);
+  LAUNCH(h, PGB_PROF_MNIW, (k_mniw<<<h->fd.nc, MNIW_TPB, 0, h->stream>>>(h->md)));
   CK(h, cudaGetLastError());
   h->sweep_index += 1;
   return PGB_OK;
@@ -810,5 +864,88 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   if (e) CK(h, cudaMemcpy(e, rd.e, (size_t)K * H * ny * 8, cudaMemcpyDeviceToHost));
   if (X) CK(h, cudaMemcpy(X, rd.X, (size_t)K * (H + 1) * nx * 8, cudaMemcpyDeviceToHost));
   if (Y) CK(h, cudaMemcpy(Y, rd.Y, (size_t)K * H * ny * 8, cudaMemcpyDeviceToHost));
+  return PGB_OK;
+}
+
+extern "C" int pgb_timer_start(pgb_handle* h) {
+  NEED(h);
+  if (!h->ev0) { CK(h, cudaEventCreate(&h->ev0)); CK(h, cudaEventCreate(&h->ev1)); }
+  CK(h, cudaEventRecord(h->ev0, h->stream));
+  return PGB_OK;
+}
+extern "C" int pgb_timer_stop(pgb_handle* h, double* elapsed_ms) {
+  NEED(h);
+  if (!h->ev0 || !elapsed_ms) return set_err(h, PGB_ERR_STATE, "pgb_timer_start was not called");
+  CK(h, cudaEventRecord(h->ev1, h->stream));
+  CK(h, cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CK(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *elapsed_ms = ms;
+  return PGB_OK;
+}
+extern "C" int pgb_profile(pgb_handle* h, int32_t on) {
+  NEED(h);
+  profile_collect(h);
+  h->profile = on != 0;
+  if (on) {
+    for (int i = 0; i < PGB_PROF_NCLASS; ++i) { h->prof_launches[i] = 0; h->prof_ms[i] = 0.0; }
+  }
+  return PGB_OK;
+}
+extern "C" int pgb_get_profile(pgb_handle* h, int64_t* launches, double* ms) {
+  NEED(h);
+  profile_collect(h);
+  for (int i = 0; i < PGB_PROF_NCLASS; ++i) {
+    if (launches) launches[i] = h->prof_launches[i];
+    if (ms) ms[i] = h->prof_ms[i];
+  }
+  return PGB_OK;
+}
+extern "C" int pgb_get_launch_count(pgb_handle* h, int64_t* n) {
+  NEED(h);
+  if (n) *n = h->n_launch;
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hooks
+// ------------------------------------------------------------------------------------------------
+extern "C" void pgb_test_force_fallback(int32_t on) { g_force_fallback = on ? 1 : 0; }
+
+__global__ void k_test_math(int fn, const double* __restrict__ x, double* __restrict__ y, int64_t n, uint64_t seed) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  switch (fn) {
+    case 0: y[i] = pgb_exp(x[i]); break;
+    case 1: y[i] = pgb_log(x[i]); break;
+    case 2: y[i] = pgb_sin(x[i]); break;
+    case 3: y[i] = pgb_cos(x[i]); break;
+    default: pgb_normal_pair(pgb_stream_block(seed, PGB_STREAM_Z, 0, 1, 5, (uint32_t)i), &y[2 * i], &y[2 * i + 1]);
+  }
+}
+
+extern "C" int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_t n) {
+  if (!x || !y || n < 1) return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
+  pgb_handle tmp;
+  pgb_handle* h = &tmp;
+  struct Cleanup {
+    pgb_handle* h;
+    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
+  } cleanup{h};
+  CK(h, cudaSetDevice(device));
+  const int64_t nout = (fn == 4) ? 2 * n : n;
+  const int64_t nin = (fn == 4) ? 1 : n;
+  double *dx, *dy;
+  CK(h, dalloc(h, &dx, (size_t)nin));
+  CK(h, dalloc(h, &dy, (size_t)nout));
+  CK(h, cudaMemcpy(dx, x, (size_t)nin * 8, cudaMemcpyHostToDevice));
+  uint64_t seed = (fn == 4) ? (uint64_t)x[0] : 0;
+  k_test_math<<<(unsigned)((n + 255) / 256), 256>>>(fn, dx, dy, n, seed);
+  CK(h, cudaGetLastError());
+  CK(h, cudaDeviceSynchronize());
+  CK(h, cudaMemcpy(y, dy, (size_t)nout * 8, cudaMemcpyDeviceToHost));
   return PGB_OK;
 }

@@ -173,9 +173,8 @@ __device__ inline int chain_params_from_Q(const double* Q, int n, double* Lq16, 
   for (int i = 0; i < 16; ++i) Lq16[i] = (i < n * n) ? L[i] : 0.0;
   return 0;
 }
-__global__ void k_chain_params(int nc, int n_x, const double* Q, double* Lq, double* c0, int* status) {
-  int chain = blockIdx.x * blockDim.x + threadIdx.x;
-  if (chain >= nc) return;
+__global__ void k_chain_params(int chain, int n_x, const double* Q, double* Lq, double* c0, int* status) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
   if (chain_params_from_Q(Q + (int64_t)chain * n_x * n_x, n_x, Lq + chain * 16, c0 + chain))
     atomicOr(&status[chain], 16);
 }

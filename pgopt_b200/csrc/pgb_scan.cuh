@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(TPB) k_scan_local(ScanWS ws, const double* __r
 
 constexpr int RESOLVE_SMEM_RECS = 512;
 
-__global__ void __launch_bounds__(TPB) k_resolve(ScanWS ws) {
+__global__ void __launch_bounds__(TPB) k_resolve(ScanWS ws, int force_fallback) {
   __shared__ pgb_agg smagg[NWARP];
   __shared__ pgb_map s_f[RESOLVE_SMEM_RECS];
   __shared__ double s_W[RESOLVE_SMEM_RECS][4];
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(ScanWS ws) {
     ws.counters[2 * chain + 1] += 1;
   }
   const int C = carry.cnt;
-  if (C > CMAX) {
+  if (C > CMAX || force_fallback) {
     if (tid == 0) atomicOr(&ws.flag[chain], 1);
     return;
   }

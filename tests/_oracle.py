@@ -107,7 +107,7 @@ def make_streams(philox=True, seed=0, chain=0, Z0=None, Ures=None, Z=None, Uanc=
     keep = []
     for name, arr in (("Z0", Z0), ("Ures", Ures), ("Z", Z), ("Uanc", Uanc), ("bartlett", bartlett), ("Xmn", Xmn)):
         if arr is not None:
-            arr = f64(arr)
+            arr = f64(np.asarray(arr, dtype=np.float64).ravel(order="F")) if name in ("bartlett", "Xmn") else f64(arr)
             keep.append(arr)
             setattr(s, name, arr.ctypes.data)
     s.Ustar = float(Ustar)

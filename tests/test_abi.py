@@ -1,0 +1,70 @@
+"""The C-ABI library loads, exports every symbol include/pgopt_b200.h declares, validates arguments on the
+host and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pgopt_b200
+from pgopt_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "pgopt_b200.h")).read()
+    declared = set(re.findall(r"\b(pgb_[a-z_0-9]+)\s*\(", hdr))
+    declared.discard("pgb_last_error")  # matched below as well; keep explicit
+    declared.add("pgb_last_error")
+    L = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), "libpgopt_b200.so does not export %s" % name
+    assert set(_lib.EXPORTS) == declared
+    assert b"sm_100a" in L.pgb_version()
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_closures_are_rejected():
+    with pytest.raises(TypeError):
+        pgopt_b200.api._basis(lambda x, u: x)
+    with pytest.raises(TypeError):
+        pgopt_b200.api._meas(lambda x, u: x)
+
+
+def test_config_validation_on_host():
+    cfg = _lib.PgbConfig()
+    cfg.device, cfg.n_x, cfg.n_u, cfg.n_y, cfg.n_phi, cfg.basis = 0, 2, 1, 1, 7, _lib.BASIS_KNOWN_VB
+    cfg.N, cfg.T, cfg.n_chains = 30, 100, 1
+    h = C.c_void_p()
+    assert _lib.lib().pgb_create(C.byref(h), C.byref(cfg)) == _lib.PGB_ERR_INVALID
+    assert b"KNOWN_VB" in _lib.lib().pgb_last_error(None)
+    b = pgopt_b200.HilbertGPBasis([5, 5, 5], [10, 20, 20])
+    assert b.count == [5, 5, 5] and b.stride == [25, 5, 1] and b.n_phi == 125 and b.n_x == 2
+    b = pgopt_b200.HilbertGPBasis([1, 5, 5, 5, 5], [4, 5, 6, 7, 8])
+    assert b.count == [5, 5, 5, 5, 1] and b.stride == [125, 25, 5, 1, 1] and b.n_phi == 625 and b.n_x == 4
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    with pytest.raises(pgopt_b200.PgoptError) as ei:
+        pgopt_b200.systematic_resampling(np.ones(4), 4, rnd=0.5)
+    assert ei.value.code == _lib.PGB_ERR_CUDA and "no CPU fallback" in str(ei.value)
+    with pytest.raises(pgopt_b200.PgoptError) as ei:
+        pgopt_b200.ParticleGibbsEngine(pgopt_b200.KnownBasisVB(), 1, 30, 100)
+    assert ei.value.code == _lib.PGB_ERR_CUDA

@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libpgopt_b200.so) against the CPU oracle on the
+same seeded inputs.  Bar: bit-exact for indices; floats bit-exact too wherever the same defined order
+runs on both sides (everything except the stated-tolerance cases)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import _problems as P
+import pgopt_b200 as pg
+from pgopt_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------------------------------ math
+@pytest.mark.parametrize("fn,name,lo,hi", [(0, "exp", -750, 710), (1, "log", 1e-300, 1e300), (2, "sin", -1e5, 1e5),
+                                           (3, "cos", -1e5, 1e5)])
+def test_device_math_is_bit_identical_to_host(fn, name, lo, hi):
+    rng = np.random.default_rng(fn)
+    x = rng.uniform(lo, hi, 200000) if fn != 1 else 10.0 ** rng.uniform(-300, 300, 200000)
+    x = np.concatenate([x, rng.uniform(-3, 3, 100000) if fn != 1 else rng.uniform(0, 2, 100000)])
+    y = np.empty_like(x)
+    _lib.check(_lib.lib().pgb_test_math(0, fn, _p(x), _p(y), C.c_int64(x.size)))
+    assert np.array_equal(y.view(np.uint64), O.vfun(name, x).view(np.uint64))
+
+
+def test_device_philox_normals_bit_identical():
+    n = 100000
+    y = np.empty(2 * n)
+    x = np.array([1234.0])
+    _lib.check(_lib.lib().pgb_test_math(0, 4, _p(x), _p(y), C.c_int64(n)))
+    assert np.array_equal(y.view(np.uint64), O.normal_pairs(1234, 2, 0, 1, 5, n).view(np.uint64))
+
+
+# ------------------------------------------------------------------------------------------ resampling
+def _weights(kind, N, rng):
+    if kind == 0:
+        return rng.uniform(0, 1, N)
+    if kind == 1:
+        return np.exp(-0.5 * rng.normal(0, 3, N) ** 2 / 0.1)
+    if kind == 2:
+        w = np.zeros(N)
+        w[rng.integers(0, N)] = 1.0
+        w[N - 1] += 1e-300
+        return w
+    if kind == 3:
+        return rng.uniform(0, 1, N) * (rng.uniform(0, 1, N) < 0.05) + 1e-320
+    if kind == 4:
+        return np.exp(rng.normal(0, 30, N))
+    if kind == 5:
+        return np.ones(N)
+    w = np.exp(-0.5 * (rng.normal(0, 0.2, N)) ** 2 / 0.1)
+    return w / w.sum()
+
+
+def test_resampling_hand_trace():
+    assert pg.systematic_resampling([.1, .2, .3, .4], 4, rnd=0.5).tolist() == [2, 3, 4, 4]
+    assert pg.systematic_resampling([1, 1, 1, 1], 3, rnd=0.999).tolist() == [2, 3, 4]
+    idx, st = pg.systematic_resampling([1.0, 1.0], 2, rnd=0.0, return_status=True)
+    assert idx.tolist() == [0, 1] and st & _lib.STATUS_INDEX_ZERO
+
+
+@pytest.mark.parametrize("N", [2, 3, 5, 29, 30, 31, 1000, 1024, 1025, 4097, 65536, 2 ** 18 + 3])
+def test_resampling_bit_exact(N):
+    rng = np.random.default_rng(N)
+    for kind in range(7):
+        w = _weights(kind, N, rng)
+        for nd in sorted({1, max(1, N - 1), N, min(2 * N, 1000)}):
+            rnd = rng.uniform()
+            a, st = O.systematic_resampling(w, nd, rnd)
+            b, stg = pg.systematic_resampling(w, nd, rnd=rnd, return_status=True)
+            assert np.array_equal(a, b), "N=%d kind=%d nd=%d: %d indices differ" % (N, kind, nd, np.sum(a != b))
+            assert (stg & 3) == st
+            assert not (stg & 0x100), "serial fallback ran on a sane input (N=%d kind=%d nd=%d)" % (N, kind, nd)
+
+
+@pytest.mark.parametrize("N", [2 ** 20, 2 ** 22])
+def test_resampling_bit_exact_large(N):
+    rng = np.random.default_rng(7)
+    w = np.exp(-0.5 * rng.normal(0, 1, N) ** 2 / 0.3)
+    a, st = O.systematic_resampling(w, N - 1, 0.37)
+    b, stg = pg.systematic_resampling(w, N - 1, rnd=0.37, return_status=True)
+    assert st == 0 and np.array_equal(a, b) and not (stg & 0x100)
+    # size-independent properties
+    assert np.all(np.diff(b) >= 0) and b.min() >= 1 and b.max() <= N
+    counts = np.bincount(b - 1, minlength=N)
+    assert np.all(np.abs(counts - (N - 1) * w / w.sum()) <= 1.0 + 1e-6)
+
+
+def test_resampling_forced_fallback_is_still_exact():
+    rng = np.random.default_rng(3)
+    _lib.lib().pgb_test_force_fallback(1)
+    try:
+        for N in (30, 5000, 70000):
+            w = _weights(1, N, rng)
+            rnd = rng.uniform()
+            a, _ = O.systematic_resampling(w, N - 1, rnd)
+            b, stg = pg.systematic_resampling(w, N - 1, rnd=rnd, return_status=True)
+            assert np.array_equal(a, b) and (stg & 0x100)
+    finally:
+        _lib.lib().pgb_test_force_fallback(0)
+
+
+def test_resampling_overrun_status():
+    # weights whose sequential sum stays below the last grid point: the reference raises BoundsError
+    w = np.array([0.1] * 10)
+    rnd = 1.0 - 2.0 ** -53
+    a, st = O.systematic_resampling(w, 10, rnd)
+    b, stg = pg.systematic_resampling(w, 10, rnd=rnd, return_status=True)
+    assert np.array_equal(a, b) and (stg & 1) == (st & 1)
+    if st & 1:
+        with pytest.raises(IndexError):
+            pg.systematic_resampling(w, 10, rnd=rnd)
+
+
+# ------------------------------------------------------------------------------------------ sweep
+def _models():
+    hb = pg.HilbertGPBasis([5, 5, 5], [10, 20, 20])
+    return {"known": (pg.KnownBasisVB(), O.known_model(), P.plausible_A_known()),
+            "hilbert": (hb, O.hilbert_model(2, 1, hb.count, hb.stride, hb.L),
+                        np.random.default_rng(9).normal(0, 2.0, (2, 125)))}
+
+
+def _engine(basis, N, T, u, y, keep_w=True, n_chains=1):
+    e = pg.ParticleGibbsEngine(basis, 1, N, T, n_chains=n_chains, keep_w_history=keep_w)
+    e.set_data(u, y)
+    e.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+    e.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+    return e
+
+
+def _assert_same(name, a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.dtype.kind == "f":
+        bad = a.view(np.uint64) != b.view(np.uint64)
+        bad &= ~((a == 0) & (b == 0))
+    else:
+        bad = a != b
+    assert not bad.any(), "%s: %d of %d entries differ (first at %s: %r vs %r)" % (
+        name, bad.sum(), bad.size, np.argwhere(bad)[0], a[tuple(np.argwhere(bad)[0])], b[tuple(np.argwhere(bad)[0])])
+
+
+@pytest.mark.parametrize("model", ["known", "hilbert"])
+@pytest.mark.parametrize("first", [False, True])
+@pytest.mark.parametrize("N,T", [(30, 120), (1500, 25)])
+def test_sweep_bit_exact_injected_streams(model, first, N, T):
+    basis, om, A = _models()[model]
+    u, y, _ = P.make_data(T, 11)
+    s = P.injected_streams(N, T, 2, basis.n_phi, 21)
+    st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
+    xp = np.zeros((2, T))
+    if not first:  # a plausible conditioned trajectory: the output of a first sweep
+        xp = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, True, st, 1)["x_prim"]
+    k = 1 if first else 2
+    ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, first, st, k)
+    with _engine(basis, N, T, u, y) as e:
+        e.set_state(A, P.Q_TRUE, xp, k)
+        e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+        e.sweep_filter()
+        a, x, w = e.get_history()
+        Phi, Psi, Sig, star = e.get_stats()
+        _, _, xprim, _ = e.get_state()
+        smp = e.get_sample()
+        stat, nfb, nscan = e.status()
+    _assert_same("ancestors", a[1:], ref["a"][1:])
+    _assert_same("x_pf", x, ref["x"])
+    _assert_same("w", w, ref["w"])
+    assert star == ref["star"]
+    _assert_same("x_prim", xprim, ref["x_prim"])
+    _assert_same("Phi", Phi, ref["Phi"])
+    _assert_same("Psi", Psi, ref["Psi"])
+    _assert_same("Sigma", Sig, ref["Sigma"])
+    _assert_same("w_m1", smp.w_m1, ref["w_last"])
+    _assert_same("x_m1", smp.x_m1.T, ref["x_last"])
+    assert stat == ref["status"] == 0 and nfb == 0 and nscan == (T if first else 2 * T - 1)
+
+
+def test_sweep_with_underflowing_ancestor_weights():
+    """An implausible conditioned trajectory makes every ancestor weight underflow: waN ./ sum(waN) is NaN
+    (particle_Gibbs.jl:180).  The reference carries on silently (index 1); so do we, bit for bit, and the
+    NONFINITE status bit is raised."""
+    basis, om, A = _models()["known"]
+    N, T = 30, 10
+    u, y, _ = P.make_data(T, 11)
+    s = P.injected_streams(N, T, 2, 5, 21)
+    xp = np.random.default_rng(4).normal(2, 1, (2, T))
+    st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
+    ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, False, st, 2)
+    with _engine(basis, N, T, u, y) as e:
+        e.set_state(A, P.Q_TRUE, xp, 2)
+        e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+        e.sweep_filter()
+        a, x, w = e.get_history()
+        stat, nfb, nscan = e.status()
+    assert ref["status"] & 4 and stat == ref["status"]
+    _assert_same("ancestors", a[1:], ref["a"][1:])
+    _assert_same("x_pf", x, ref["x"])
+    _assert_same("w", w, ref["w"])
+
+
+def test_sweep_forced_fallback_is_still_exact():
+    basis, om, A = _models()["known"]
+    N, T = 300, 20
+    u, y, _ = P.make_data(T, 12)
+    s = P.injected_streams(N, T, 2, 5, 22)
+    st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
+    xp = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, np.zeros((2, T)), True, st, 1)["x_prim"]
+    ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, False, st, 2)
+    _lib.lib().pgb_test_force_fallback(1)
+    try:
+        with _engine(basis, N, T, u, y) as e:
+            e.set_state(A, P.Q_TRUE, xp, 2)
+            e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+            e.sweep_filter()
+            a, x, w = e.get_history()
+            stat, nfb, nscan = e.status()
+    finally:
+        _lib.lib().pgb_test_force_fallback(0)
+    assert nfb == nscan and nfb > 0 and stat == ref["status"]
+    _assert_same("ancestors", a[1:], ref["a"][1:])
+    _assert_same("x_pf", x, ref["x"])
+    _assert_same("w", w, ref["w"])
+
+
+@pytest.mark.parametrize("model", ["known", "hilbert"])
+def test_mniw_bit_exact(model):
+    basis, om, A = _models()[model]
+    rng = np.random.default_rng(31)
+    n_x, n_phi, Tm1 = 2, basis.n_phi, 399
+    zeta, z = rng.normal(size=(n_x, Tm1)), rng.normal(size=(n_phi, Tm1))
+    Phi, Psi, Sig = zeta @ zeta.T, zeta @ z.T, z @ z.T
+    Sig = 0.5 * (Sig + Sig.T)
+    V = 10 * np.ones(n_phi) if model == "known" else pg.hilbert_gp_prior_V([5, 5, 5], [10, 20, 20], 2 * np.pi * np.ones(3),
+                                                                              100 ** 2 / (8 * np.pi ** 4))
+    Lam, ell = 100 * np.eye(n_x), 10.0
+    s = P.injected_streams(4, 4, n_x, n_phi, 3, df=ell + Tm1 * n_x)
+    st = O.make_streams(philox=False, bartlett=s["bartlett"], Xmn=s["Xmn"])
+    Ar, Qr, rc = O.mniw_sample(n_x, n_phi, Phi, Psi, Sig, V, Lam, ell, Tm1, st, 1)
+    Ag, Qg = pg.MNIW_sample(Phi, Psi, Sig, V, Lam, ell, Tm1, bartlett=s["bartlett"], Xmn=s["Xmn"])
+    assert rc == 0
+    _assert_same("Q", Qg, Qr)
+    _assert_same("A", Ag, Ar)
+    # Philox-driven draw (Marsaglia-Tsang chi-square on the device) must match too
+    stp = O.make_streams(philox=True, seed=77, chain=3)
+    Ar, Qr, rc = O.mniw_sample(n_x, n_phi, Phi, Psi, Sig, V, Lam, ell, Tm1, stp, 5)
+    Ag, Qg = pg.MNIW_sample(Phi, Psi, Sig, V, Lam, ell, Tm1, seed=77, chain=3, sweep_index=5)
+    _assert_same("Q philox", Qg, Qr)
+    _assert_same("A philox", Ag, Ar)
+
+
+@pytest.mark.parametrize("model,N,T,K,K_b,k_d", [("known", 30, 150, 4, 6, 2), ("hilbert", 30, 60, 3, 3, 1),
+                                                 ("known", 2500, 30, 3, 2, 1)])
+def test_particle_gibbs_bit_exact_philox(model, N, T, K, K_b, k_d):
+    """Whole sampler (particle_Gibbs.jl:114-237) with counter-based streams: every kept sample identical."""
+    basis, om, _ = _models()[model]
+    u, y, _ = P.make_data(T, 13)
+    n_phi = basis.n_phi
+    V = 10 * np.ones(n_phi) if model == "known" else pg.hilbert_gp_prior_V([5, 5, 5], [10, 20, 20], 2 * np.pi * np.ones(3),
+                                                                            100 ** 2 / (8 * np.pi ** 4))
+    ref = O.particle_gibbs(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), np.zeros((2, n_phi)),
+                           100 * np.eye(2), V, 100 * np.eye(2), 10.0, K, K_b, k_d, seed=99, chain=2)
+    xp = np.zeros((2, T))
+    smp = pg.particle_Gibbs(u, y, K, K_b, k_d, N, basis, 100 * np.eye(2), 10.0, 100 * np.eye(2), V, np.zeros((2, n_phi)),
+                            pg.MvNormal([2.0, 2.0], 1.0), pg.LinearMeasurement([[1.0, 0.0]]), 0.1, x_prim=xp, seed=99, chain=2)
+    assert ref["status"] == 0 and len(smp) == K
+    for k in range(K):
+        _assert_same("A[%d]" % k, smp[k].A, ref["A"][k])
+        _assert_same("Q[%d]" % k, smp[k].Q, ref["Q"][k])
+        _assert_same("w_m1[%d]" % k, smp[k].w_m1, ref["w"][k])
+        _assert_same("x_m1[%d]" % k, smp[k].x_m1.T, ref["x"][k])
+        assert smp[k].u_m1[0] == u[0, -1]
+    _assert_same("x_prim (in-place update)", xp, ref["x_prim"])
+
+
+def test_batched_chains_match_single_chains():
+    """n_chains batched on one handle == the same chains run one at a time (and == the oracle)."""
+    basis, om, _ = _models()["known"]
+    N, T, nc = 700, 25, 3
+    u, y, _ = P.make_data(T, 14)
+    V = 10 * np.ones(5)
+    with _engine(basis, N, T, u, y, keep_w=False, n_chains=nc) as e:
+        e.set_prior(V, 100 * np.eye(2), 10.0)
+        for c in range(nc):
+            e.set_state(np.zeros((2, 5)), 100 * np.eye(2), None, 1, chain=c)
+        e.set_rng_philox(5, 10)
+        A_s, Q_s, w_s, x_s, _ = e.particle_gibbs(2, 2, 0)
+    for c in range(nc):
+        ref = O.particle_gibbs(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), np.zeros((2, 5)),
+                               100 * np.eye(2), V, 100 * np.eye(2), 10.0, 2, 2, 0, seed=5, chain=10 + c)
+        for k in range(2):
+            _assert_same("A", A_s[c, k].reshape((2, 5), order="F"), ref["A"][k])
+            _assert_same("w", w_s[c, k], ref["w"][k])
+
+
+# ------------------------------------------------------------------------------------------ rollout
+@pytest.mark.parametrize("model", ["known", "hilbert4"])
+def test_rollout_bit_exact(model):
+    rng = np.random.default_rng(41)
+    if model == "known":
+        basis, om = pg.KnownBasisVB(), O.known_model()
+        n_x = 2
+    else:
+        basis = pg.HilbertGPBasis([1, 3, 3, 3, 3], [4.0, 5.0, 6.0, 7.0, 8.0])
+        om = O.hilbert_model(4, 1, basis.count, basis.stride, basis.L)
+        n_x = 4
+    K, H, N, n_phi = 37, 41, 30, basis.n_phi
+    A = rng.normal(0, 0.3, (K, n_x, n_phi))
+    Q = np.stack([(lambda B: B @ B.T + 0.05 * np.eye(n_x))(rng.normal(0, 0.2, (n_x, n_x))) for _ in range(K)])
+    w = rng.uniform(size=(K, N))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, N, n_x))
+    um = rng.normal(0, 1, (K, 1))
+    Cm = np.zeros((1, n_x))
+    Cm[0, 0] = 1.0
+    u_init = rng.normal(0, 1, (1, H))
+    ref = O.rollout(om, K, H, N, A, Q, w, x, um, Cm, [[0.1]], u_init, seed=17)
+    samples = [pg.PG_sample(A[k], Q[k], w[k], x[k].T, um[k]) for k in range(K)]
+    out = pg.scenario_rollout(samples, basis, pg.LinearMeasurement(Cm), 0.1, H, u_init=u_init, seed=17)
+    assert ref["status"] == 0
+    for name in ("x0", "v", "e", "X", "Y"):
+        _assert_same(name, out["raw"][name], ref[name])
+    # reference layouts (optimal_control_Ipopt.jl:48,68,78,115,117)
+    assert out["x_vec_0"].shape == (n_x * K,) and out["v_vec"].shape == (n_x, H, K) and out["e_vec"].shape == (1, H, K)
+    assert out["X_init"].shape == (n_x * K, H + 1) and out["Y_init"].shape == (K, H)
+    np.testing.assert_array_equal(out["X_init"][n_x * 3:n_x * 4, 5], ref["X"][3, 5])
+    np.testing.assert_array_equal(out["v_vec"][:, 7, 2], ref["v"][2, 7])
