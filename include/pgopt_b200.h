@@ -131,6 +131,9 @@ int pgb_synchronize(pgb_handle* h);
  * pgb_get_launch_count returns the number of kernels this handle has launched so far. */
 enum { PGB_PROF_PREP = 0, PGB_PROF_NORM, PGB_PROF_SCAN_LOCAL, PGB_PROF_RESOLVE, PGB_PROF_EXPAND, PGB_PROF_SEQ,
        PGB_PROF_EXPAND_FB, PGB_PROF_WEIGHTS, PGB_PROF_INIT, PGB_PROF_TAIL, PGB_PROF_MNIW, PGB_PROF_NCLASS };
+/* persistent != 0 (default): the whole T loop of a sweep is one cooperative persistent kernel; 0: one
+ * launch per phase (13 launches per time step; kept for per-kernel profiling and as a cross-check). */
+int pgb_set_mode(pgb_handle* h, int32_t persistent);
 int pgb_timer_start(pgb_handle* h);
 int pgb_timer_stop(pgb_handle* h, double* elapsed_ms);
 int pgb_profile(pgb_handle* h, int32_t on);

@@ -171,6 +171,9 @@ class ParticleGibbsEngine:
     def _ck(self, rc):
         check(rc, self._h)
 
+    def set_mode(self, persistent=True):
+        self._ck(lib().pgb_set_mode(self._h, C.c_int32(int(persistent))))
+
     def set_data(self, u, y):
         u, y = _f(np.atleast_2d(u)), _f(np.atleast_2d(y))
         assert u.size == self.n_u * self.T and y.size == self.n_y * self.T

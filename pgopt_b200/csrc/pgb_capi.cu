@@ -14,6 +14,7 @@
 #include "../../include/pgopt_b200.h"
 #include "pgb_mniw.cuh"
 #include "pgb_rollout.cuh"
+#include "pgb_persist.cuh"
 
 using namespace pgb;
 
@@ -42,6 +43,10 @@ struct pgb_handle {
   // the (A, Q) the last filter pass ran with (sample fields, particle_Gibbs.jl:204-205)
   double *d_A_used = nullptr, *d_Q_used = nullptr;
   bool injected_ready = false;
+  // persistent (single cooperative kernel) filter path
+  bool persistent = true;
+  PersistDev pd;
+  int num_sms = 0;
   // measurement
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool profile = false;
@@ -136,7 +141,7 @@ static cudaError_t alloc_scanws(pgb_handle* h, ScanWS* ws, int64_t N, int nc, lo
 #define A_(field, count) if ((e = dalloc(h, &ws->field, (size_t)(count))) != cudaSuccess) return e;
   A_(S, nc) A_(tsum, nc * nt) A_(tile_prefix, nc * (nt + 1)) A_(thr_ex, nc * nt * TPB) A_(tile_agg, nc * nt)
   A_(tile_ex, nc * (nt + 1)) A_(recs, nc * nt * RMAX) A_(crec, (int64_t)nc * CMAX) A_(seeds, (int64_t)nc * (CMAX + 1))
-  A_(qin_fb, nc * nt * TPB) A_(ticket, nc) A_(flag, nc) A_(pend, nc) A_(counters, 2 * nc)
+  A_(qin_fb, nc * nt * TPB) A_(ticket, nc) A_(flag, 2 * nc) A_(pend, nc) A_(counters, 2 * nc)
 #undef A_
   if (counters) *counters = ws->counters;
   return cudaSuccess;
@@ -276,6 +281,23 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
   CKC(dalloc(h, &md.Xn, (size_t)nc * nx * np));
   CKC(dalloc(h, &md.LX, (size_t)nc * nx * np));
   md.A = fd.A; md.Q = h->d_Q; md.Lq = fd.Lq; md.c0 = fd.c0; md.status = fd.status;
+  {
+    PersistDev& pd = h->pd;
+    memset(&pd, 0, sizeof(pd));
+    CKC(dalloc(h, &pd.bar, 4));
+    CKC(dalloc(h, &pd.pe, (size_t)nc * P_MAXNB));
+    CKC(dalloc(h, &pd.pw, (size_t)nc * P_MAXNB));
+    CKC(dalloc(h, &pd.pa, (size_t)nc * P_MAXNB));
+    CKC(dalloc(h, &pd.pa2, (size_t)nc * P_MAXNB));
+    pd.star_idx = h->d_star_idx;
+    CKC(dalloc(h, &pd.heavy, (size_t)nc * P_HEAVY_MAX));
+    CKC(dalloc(h, &pd.heavy_cnt, (size_t)nc));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, cfg->device));
+    h->num_sms = prop.multiProcessorCount;
+    const char* env = getenv("PGB_PERSISTENT");
+    if (env && env[0] == '0') h->persistent = false;
+  }
   h->have_state.assign(nc, 0);
   h->h_u.assign((size_t)nu * T, 0.0);
 #undef CKC
@@ -504,7 +526,66 @@ static int run_filter_nx(pgb_handle* h) {
   return PGB_OK;
 }
 
+// One cooperative launch for the whole time loop.  Returns -1 when the configuration does not fit
+// (too many chains / tiles for the co-resident grid); the caller then uses the multi-kernel path.
+template <int NX>
+static int run_filter_persistent_nx(pgb_handle* h) {
+  FilterDev& fd = h->fd;
+  MniwDev& md = h->md;
+  PersistDev& pd = h->pd;
+  cudaStream_t s = h->stream;
+  const int64_t T = fd.T;
+  const int nc = fd.nc;
+  const size_t smA = (size_t)NX * fd.n_phi * 8;
+  int occ = 0;
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_persistent<NX>, TPB, smA));
+  const int max_ctas = occ * h->num_sms;
+  int nbmax = max_ctas / nc;
+  if (nbmax > P_MAXNB) nbmax = P_MAXNB;
+  if (nbmax < 1) return -1;
+  int tpc = 1;
+  while ((fd.nt + tpc - 1) / tpc > nbmax) tpc *= 2;
+  if (tpc > P_MAXTPC) return -1;
+  pd.tpc = tpc;
+  pd.nb = (fd.nt + tpc - 1) / tpc;
+  pd.force_fallback = g_force_fallback;
+  int first = (h->sweep_index == 1);
+  fd.sweep = (uint32_t)h->sweep_index;
+  md.sweep = fd.sweep;
+  const size_t nA = (size_t)nc * NX * fd.n_phi * 8, nQ = (size_t)nc * NX * NX * 8;
+  CK(h, cudaMemcpyAsync(h->d_A_used, fd.A, nA, cudaMemcpyDeviceToDevice, s));
+  CK(h, cudaMemcpyAsync(h->d_Q_used, h->d_Q, nQ, cudaMemcpyDeviceToDevice, s));
+  CK(h, cudaMemsetAsync(fd.maxkey, 0, (size_t)nc * 8, s));
+  CK(h, cudaMemsetAsync(pd.bar, 0, 4, s));
+  CK(h, cudaMemsetAsync(pd.heavy_cnt, 0, (size_t)nc * 4, s));
+  CK(h, cudaMemsetAsync(fd.main.flag, 0, (size_t)2 * nc * 4, s));
+  CK(h, cudaMemsetAsync(fd.side.flag, 0, (size_t)2 * nc * 4, s));
+  LAUNCH(h, PGB_PROF_INIT, (k_build_utabs<<<dim3((unsigned)((T + 127) / 128), nc), 128, 0, s>>>(fd, first)));
+  {
+    LaunchScope ls(h, PGB_PROF_EXPAND);
+    void* args[] = {(void*)&fd, (void*)&pd, (void*)&first};
+    CK(h, cudaLaunchCooperativeKernel((const void*)k_sweep_persistent<NX>, dim3((unsigned)(nc * pd.nb)), dim3(TPB), args,
+                                      smA, s));
+  }
+  LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
+  const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
+  LAUNCH(h, PGB_PROF_TAIL, (k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md)));
+  CK(h, cudaGetLastError());
+  return PGB_OK;
+}
+
 static int run_filter(pgb_handle* h) {
+  if (h->persistent) {
+    int rc;
+    switch (h->cfg.n_x) {
+      case 1: rc = run_filter_persistent_nx<1>(h); break;
+      case 2: rc = run_filter_persistent_nx<2>(h); break;
+      case 3: rc = run_filter_persistent_nx<3>(h); break;
+      default: rc = run_filter_persistent_nx<4>(h); break;
+    }
+    if (rc >= 0) return rc;
+  }
   switch (h->cfg.n_x) {
     case 1: return run_filter_nx<1>(h);
     case 2: return run_filter_nx<2>(h);
@@ -867,6 +948,11 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   return PGB_OK;
 }
 
+extern "C" int pgb_set_mode(pgb_handle* h, int32_t persistent) {
+  NEED(h);
+  h->persistent = persistent != 0;
+  return PGB_OK;
+}
 extern "C" int pgb_timer_start(pgb_handle* h) {
   NEED(h);
   if (!h->ev0) { CK(h, cudaEventCreate(&h->ev0)); CK(h, cudaEventCreate(&h->ev1)); }

@@ -127,10 +127,11 @@ def _models():
                         np.random.default_rng(9).normal(0, 2.0, (2, 125)))}
 
 
-def _engine(basis, N, T, u, y, keep_w=True, n_chains=1):
+def _engine(basis, N, T, u, y, keep_w=True, n_chains=1, persistent=True, R=0.1):
     e = pg.ParticleGibbsEngine(basis, 1, N, T, n_chains=n_chains, keep_w_history=keep_w)
+    e.set_mode(persistent)
     e.set_data(u, y)
-    e.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+    e.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), R)
     e.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
     return e
 
@@ -146,10 +147,11 @@ def _assert_same(name, a, b):
         name, bad.sum(), bad.size, np.argwhere(bad)[0], a[tuple(np.argwhere(bad)[0])], b[tuple(np.argwhere(bad)[0])])
 
 
+@pytest.mark.parametrize("persistent", [True, False])
 @pytest.mark.parametrize("model", ["known", "hilbert"])
 @pytest.mark.parametrize("first", [False, True])
-@pytest.mark.parametrize("N,T", [(30, 120), (1500, 25)])
-def test_sweep_bit_exact_injected_streams(model, first, N, T):
+@pytest.mark.parametrize("N,T", [(30, 120), (1500, 25), (9000, 12)])
+def test_sweep_bit_exact_injected_streams(model, first, N, T, persistent):
     basis, om, A = _models()[model]
     u, y, _ = P.make_data(T, 11)
     s = P.injected_streams(N, T, 2, basis.n_phi, 21)
@@ -159,7 +161,7 @@ def test_sweep_bit_exact_injected_streams(model, first, N, T):
         xp = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, True, st, 1)["x_prim"]
     k = 1 if first else 2
     ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, first, st, k)
-    with _engine(basis, N, T, u, y) as e:
+    with _engine(basis, N, T, u, y, persistent=persistent) as e:
         e.set_state(A, P.Q_TRUE, xp, k)
         e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
         e.sweep_filter()
@@ -181,7 +183,33 @@ def test_sweep_bit_exact_injected_streams(model, first, N, T):
     assert stat == ref["status"] == 0 and nfb == 0 and nscan == (T if first else 2 * T - 1)
 
 
-def test_sweep_with_underflowing_ancestor_weights():
+@pytest.mark.parametrize("persistent", [True, False])
+def test_sweep_with_degenerate_weights(persistent):
+    """A very sharp likelihood makes a handful of particles own almost all offspring (the cooperative
+    heavy-particle expansion of the persistent kernel); results must not change."""
+    basis, om, A = _models()["known"]
+    N, T = 6000, 15
+    u, y, _ = P.make_data(T, 15)
+    s = P.injected_streams(N, T, 2, 5, 23)
+    st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
+    R = 1e-7
+    xp = O.sweep(om, N, T, u, y, [[1.0, 0.0]], R, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, np.zeros((2, T)), True, st, 1)["x_prim"]
+    ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], R, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, False, st, 2)
+    assert max(np.bincount(ref["a"][t, :N - 1]).max() for t in range(1, T)) > 1000
+    with _engine(basis, N, T, u, y, persistent=persistent, R=R) as e:
+        e.set_state(A, P.Q_TRUE, xp, 2)
+        e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+        e.sweep_filter()
+        a, x, w = e.get_history()
+        stat, nfb, nscan = e.status()
+    assert (stat & 3) == (ref["status"] & 3)
+    _assert_same("ancestors", a[1:], ref["a"][1:])
+    _assert_same("x_pf", x, ref["x"])
+    _assert_same("w", w, ref["w"])
+
+
+@pytest.mark.parametrize("persistent", [True, False])
+def test_sweep_with_underflowing_ancestor_weights(persistent):
     """An implausible conditioned trajectory makes every ancestor weight underflow: waN ./ sum(waN) is NaN
     (particle_Gibbs.jl:180).  The reference carries on silently (index 1); so do we, bit for bit, and the
     NONFINITE status bit is raised."""
@@ -192,7 +220,7 @@ def test_sweep_with_underflowing_ancestor_weights():
     xp = np.random.default_rng(4).normal(2, 1, (2, T))
     st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
     ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, False, st, 2)
-    with _engine(basis, N, T, u, y) as e:
+    with _engine(basis, N, T, u, y, persistent=persistent) as e:
         e.set_state(A, P.Q_TRUE, xp, 2)
         e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
         e.sweep_filter()
@@ -204,9 +232,11 @@ def test_sweep_with_underflowing_ancestor_weights():
     _assert_same("w", w, ref["w"])
 
 
-def test_sweep_forced_fallback_is_still_exact():
+@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("N", [300, 5000])
+def test_sweep_forced_fallback_is_still_exact(persistent, N):
     basis, om, A = _models()["known"]
-    N, T = 300, 20
+    T = 20
     u, y, _ = P.make_data(T, 12)
     s = P.injected_streams(N, T, 2, 5, 22)
     st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
@@ -214,7 +244,7 @@ def test_sweep_forced_fallback_is_still_exact():
     ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, False, st, 2)
     _lib.lib().pgb_test_force_fallback(1)
     try:
-        with _engine(basis, N, T, u, y) as e:
+        with _engine(basis, N, T, u, y, persistent=persistent) as e:
             e.set_state(A, P.Q_TRUE, xp, 2)
             e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
             e.sweep_filter()
