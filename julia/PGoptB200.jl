@@ -1,0 +1,179 @@
+# PGoptB200.jl — thin `ccall` shim that keeps PGopt's Julia signatures for the hot path and runs them on
+# libpgopt_b200.so (hand-written sm_100a CUDA behind a C ABI; include/pgopt_b200.h).
+#
+# NOT EXECUTED IN THE BUILD ENVIRONMENT: neither Julia nor a network exists there (SURVEY.md §1 fact 2), so this
+# file is the binding a PGopt maintainer would add; the same entry points are exercised by the Python ctypes
+# mirror pgopt_b200/api.py, which the test-suite runs on a B200.
+#
+# Drop-in use:   using PGoptB200   instead of   using PGopt   for
+#   particle_Gibbs, systematic_resampling, MNIW_sample, PG_sample, scenario_rollout
+# and hand scenario_rollout's outputs to PGopt.solve_PG_OCP_Ipopt(...; x_vec_0, v_vec, e_vec, u_init).
+module PGoptB200
+
+using LinearAlgebra
+using Distributions
+
+export PG_sample, KnownBasisVB, HilbertGPBasis, LinearMeasurement, particle_Gibbs, systematic_resampling,
+       MNIW_sample, scenario_rollout
+
+const LIB = get(ENV, "PGOPT_B200_LIB", "libpgopt_b200.so")
+const PGB_MAX_Z = 8
+
+# Julia/src/PGopt.jl:23-29
+mutable struct PG_sample
+    A::Matrix{Float64}
+    Q::Matrix{Float64}
+    w_m1::Array{Float64}
+    x_m1::Array{Float64}
+    u_m1::Array{Float64}
+end
+
+# Julia closures cannot cross a C ABI: phi and g are descriptors.
+struct KnownBasisVB end                      # examples/PG_OCP_known_basis_functions_Altro.jl:34
+struct HilbertGPBasis                        # examples/PG_OCP_generic_basis_functions_Altro.jl:52-99
+    n_phi_dims::Vector{Int}                  # [n_phi_u..., n_phi_x...]
+    L::Vector{Float64}                       # [L_u..., L_x...]
+    n_u::Int
+end
+struct LinearMeasurement                     # g(x,u) = C*x   (known example :54)
+    C::Matrix{Float64}
+end
+
+# mirror of pgb_config (include/pgopt_b200.h)
+struct PgbConfig
+    device::Int32; n_x::Int32; n_u::Int32; n_y::Int32; n_phi::Int32; basis::Int32
+    hg_count::NTuple{PGB_MAX_Z,Int32}; hg_stride::NTuple{PGB_MAX_Z,Int32}; hg_L::NTuple{PGB_MAX_Z,Float64}
+    N::Int64; T::Int64; n_chains::Int32; keep_w_history::Int32
+end
+
+pad8(v, T) = ntuple(i -> i <= length(v) ? T(v[i]) : zero(T), PGB_MAX_Z)
+
+function make_config(phi, n_y, N, T; device=0, n_chains=1)
+    if phi isa KnownBasisVB
+        return PgbConfig(device, 2, 1, n_y, 5, 0, pad8(Int[], Int32), pad8(Int[], Int32), pad8(Float64[], Float64),
+                         N, T, n_chains, 0), 2, 1, 5
+    elseif phi isa HilbertGPBasis
+        nz = length(phi.L)
+        # the reference reverses the index vectors (:82): dimension k uses slot nz+1-k
+        count = [phi.n_phi_dims[nz+1-k] for k in 1:nz]
+        stride = [prod(phi.n_phi_dims[1:nz-k]) for k in 1:nz]
+        n_phi = prod(phi.n_phi_dims)
+        return PgbConfig(device, nz - phi.n_u, phi.n_u, n_y, n_phi, 1, pad8(count, Int32), pad8(stride, Int32),
+                         pad8(phi.L, Float64), N, T, n_chains, 0), nz - phi.n_u, phi.n_u, n_phi
+    else
+        throw(ArgumentError("phi must be a KnownBasisVB or HilbertGPBasis descriptor: arbitrary closures cannot " *
+                            "cross the C ABI and there is no CPU fallback"))
+    end
+end
+
+function check(rc, h=C_NULL)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:pgb_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
+    rc == 3 && throw(PosDefException(0))
+    error("pgopt_b200 error $rc: $msg")
+end
+
+"""
+    systematic_resampling(W, N)          # Julia/src/particle_Gibbs.jl:17-34
+"""
+function systematic_resampling(W, N; rnd=rand(), device=0)
+    Wv = Vector{Float64}(W)
+    idx = Vector{Int64}(undef, N)
+    st = Ref{Int32}(0)
+    check(ccall((:pgb_systematic_resampling, LIB), Cint,
+                (Int32, Ptr{Float64}, Int64, Int64, Float64, Ptr{Int64}, Ref{Int32}),
+                device, Wv, length(Wv), N, rnd, idx, st))
+    (st[] & 1) != 0 && throw(BoundsError(Wv, length(Wv) + 1))   # what :28 raises
+    return idx
+end
+
+"""
+    MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T)      # Julia/src/particle_Gibbs.jl:56-81
+"""
+function MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T; seed=rand(UInt64), chain=0, sweep_index=1, device=0)
+    n_x, n_phi = size(Psi)
+    Vd = V isa Diagonal ? Vector{Float64}(V.diag) : Vector{Float64}(diag(V))
+    A = Matrix{Float64}(undef, n_x, n_phi); Q = Matrix{Float64}(undef, n_x, n_x)
+    check(ccall((:pgb_mniw_sample, LIB), Cint,
+                (Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Int64,
+                 Ptr{Float64}, Ptr{Float64}, UInt64, UInt32, UInt32, Ptr{Float64}, Ptr{Float64}),
+                device, n_x, n_phi, Matrix{Float64}(Phi), Matrix{Float64}(Psi), Matrix{Float64}(Sigma), Vd,
+                Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q), T, C_NULL, C_NULL, seed, chain, sweep_index, A, Q))
+    return A, Q
+end
+
+"""
+    particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist, g, R; x_prim=nothing)
+
+Same signature as Julia/src/particle_Gibbs.jl:114; `phi` / `g` are descriptors.
+"""
+function particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist,
+                        g::LinearMeasurement, R; x_prim=nothing, seed=rand(UInt64), chain=0, device=0)
+    n_y, T = size(y_training)
+    cfg, n_x, n_u, n_phi = make_config(phi, n_y, N, T; device=device)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:pgb_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{PgbConfig}), h, cfg))
+    try
+        u = Matrix{Float64}(u_training); y = Matrix{Float64}(y_training)
+        check(ccall((:pgb_set_data, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], u, y), h[])
+        Rm = R isa Number ? fill(Float64(R), 1, 1) : Matrix{Float64}(R)
+        check(ccall((:pgb_set_measurement, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], g.C, Rm), h[])
+        mu = Vector{Float64}(mean(x_init_dist)); Lc = Matrix{Float64}(cholesky(Matrix(cov(x_init_dist))).L)
+        check(ccall((:pgb_set_init_dist, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], mu, Lc), h[])
+        Vd = V isa Diagonal ? Vector{Float64}(V.diag) : Vector{Float64}(diag(V))
+        check(ccall((:pgb_set_prior, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
+                    h[], Vd, Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q)), h[])
+        xp = x_prim === nothing ? C_NULL : Matrix{Float64}(x_prim)
+        check(ccall((:pgb_set_state, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+                    h[], 0, Matrix{Float64}(A_init), Matrix{Float64}(Q_init * I(n_x)), xp, 1), h[])
+        check(ccall((:pgb_set_rng_philox, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt32), h[], seed, chain), h[])
+        A_s = Array{Float64}(undef, n_x, n_phi, K); Q_s = Array{Float64}(undef, n_x, n_x, K)
+        w_s = Array{Float64}(undef, N, K); x_s = Array{Float64}(undef, n_x, N, K); u_m1 = Vector{Float64}(undef, n_u)
+        println("### Started learning algorithm")
+        t0 = time()
+        check(ccall((:pgb_particle_gibbs, LIB), Cint,
+                    (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    h[], K, K_b, k_d, A_s, Q_s, w_s, x_s, u_m1), h[])
+        if x_prim !== nothing       # the reference mutates x_prim in place (:214-217)
+            xo = Matrix{Float64}(undef, n_x, T)
+            check(ccall((:pgb_get_state, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                        h[], 0, C_NULL, C_NULL, xo, C_NULL), h[])
+            x_prim .= xo
+        end
+        println("### Learning complete\nRuntime: ", round(time() - t0; digits=2), " s")
+        return [PG_sample(A_s[:, :, k], Q_s[:, :, k], w_s[:, k], x_s[:, :, k], copy(u_m1)) for k in 1:K]
+    finally
+        ccall((:pgb_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+end
+
+"""
+    scenario_rollout(PG_samples, phi, g, R, H; u_init=zeros(n_u, H))
+
+The sampling + forward rollout solve_PG_OCP_Ipopt does before building the NLP
+(Julia/src/optimal_control_Ipopt.jl:47-83,114-125); returns (x_vec_0, v_vec, e_vec, X_init, Y_init) in the
+reference's layouts — pass the first three back as keyword arguments of solve_PG_OCP_Ipopt.
+"""
+function scenario_rollout(PG_samples::Vector{PG_sample}, phi, g::LinearMeasurement, R, H; u_init=nothing,
+                          seed=rand(UInt64), k_offset=0, device=0)
+    K = length(PG_samples); N = length(PG_samples[1].w_m1); n_y = size(g.C, 1)
+    cfg, n_x, n_u, n_phi = make_config(phi, n_y, N, 2; device=device)
+    u0 = u_init === nothing ? zeros(n_u, H) : Matrix{Float64}(u_init)
+    # MvNormal(zeros(n_y), R::Real) reads a scalar as a standard deviation (reference quirk, :79)
+    Le = R isa Number ? fill(Float64(R), 1, 1) : Matrix{Float64}(cholesky(Matrix(R)).L)
+    A = cat([s.A for s in PG_samples]...; dims=3); Q = cat([s.Q for s in PG_samples]...; dims=3)
+    w = hcat([s.w_m1 for s in PG_samples]...); x = cat([s.x_m1 for s in PG_samples]...; dims=3)
+    um = hcat([s.u_m1 for s in PG_samples]...)
+    x0 = Array{Float64}(undef, n_x, K); v = Array{Float64}(undef, n_x, H, K); e = Array{Float64}(undef, n_y, H, K)
+    X = Array{Float64}(undef, n_x, H + 1, K); Y = Array{Float64}(undef, n_y, H, K)
+    check(ccall((:pgb_rollout, LIB), Cint,
+                (Ref{PgbConfig}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, UInt64, UInt32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}),
+                cfg, K, H, A, Q, w, x, um, g.C, Le, u0, seed, k_offset, x0, v, e, X, Y))
+    X_init = reshape(permutedims(X, (1, 3, 2)), n_x * K, H + 1)
+    Y_init = reshape(permutedims(Y, (1, 3, 2)), n_y * K, H)
+    return vec(x0), v, e, X_init, Y_init
+end
+
+end # module

@@ -199,6 +199,7 @@ typedef struct {
   int64_t m0[PGB_UT_MAXROWS];   // its mantissa integer
   int64_t c[PGB_UT_MAXROWS];    // ulps added per draw inside the row
   double u0[PGB_UT_MAXROWS];    // its value (= from_mant(key, m0))
+  double invc[PGB_UT_MAXROWS];  // 1/c (quotient estimate, corrected exactly with integer arithmetic)
   int32_t key[PGB_UT_MAXROWS];
   int32_t nrows;
   int64_t M;                    // number of draws
@@ -241,6 +242,7 @@ PGB_HD void pgb_utable_build(pgb_utable* T, int64_t M, double rnd) {
     T->m0[r] = m;
     T->c[r] = c;
     T->u0[r] = u;
+    T->invc[r] = (c > 0) ? PGB_DIV(1.0, (double)c) : 0.0;
     T->key[r] = key;
     ++r;
     double last = pgb_from_mant(key, m + (len - 1) * c);
@@ -258,14 +260,16 @@ PGB_HD double pgb_utable_at(const pgb_utable* T, int64_t i) {
   }
   return pgb_from_mant(T->key[lo], T->m0[lo] + (i - T->i0[lo]) * T->c[lo]);
 }
-// #{ i in [1, M] : u_i <= q }   (q finite >= 0)
-PGB_HD int64_t pgb_utable_count_le(const pgb_utable* T, double q) {
-  if (T->nrows == 0 || q < T->u0[0]) return 0;
-  int lo = 0, hi = T->nrows - 1;
-  while (lo < hi) {
-    int mid = (lo + hi + 1) >> 1;
-    if (T->u0[mid] <= q) lo = mid; else hi = mid - 1;
-  }
+// floor((mq - m0) / c) without a 64-bit integer division: double estimate, exact integer correction
+PGB_HD int64_t pgb_floor_div_est(int64_t num, int64_t c, double invc) {
+  int64_t j = (int64_t)((double)num * invc);
+  if (j < 0) j = 0;
+  while ((j + 1) * c <= num) ++j;
+  while (j > 0 && j * c > num) --j;
+  return j;
+}
+// #{ i in row `lo` of T : u_i <= q } given that row lo is the last row with u0 <= q
+PGB_HD int64_t pgb_utable_count_in_row(const pgb_utable* T, int lo, double q) {
   int64_t i0 = T->i0[lo];
   int64_t len = ((lo + 1 < T->nrows) ? T->i0[lo + 1] : T->M + 1) - i0;
   int64_t j;
@@ -274,10 +278,29 @@ PGB_HD int64_t pgb_utable_count_le(const pgb_utable* T, double q) {
   } else if (pgb_segkey(q) != T->key[lo]) {
     j = len - 1;  // q lies in a higher binade than the whole row
   } else {
-    j = (pgb_mant(q) - T->m0[lo]) / T->c[lo];
+    j = pgb_floor_div_est(pgb_mant(q) - T->m0[lo], T->c[lo], T->invc[lo]);
     if (j > len - 1) j = len - 1;
   }
   return i0 + j;
+}
+// #{ i in [1, M] : u_i <= q }   (q finite >= 0)
+PGB_HD int64_t pgb_utable_count_le(const pgb_utable* T, double q) {
+  if (T->nrows == 0 || !(q >= T->u0[0])) return 0;
+  int lo = 0, hi = T->nrows - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (T->u0[mid] <= q) lo = mid; else hi = mid - 1;
+  }
+  return pgb_utable_count_in_row(T, lo, q);
+}
+// same, for a non-decreasing sequence of queries: *row is the row found for the previous query
+PGB_HD int64_t pgb_utable_count_le_hint(const pgb_utable* T, double q, int* row) {
+  if (T->nrows == 0 || !(q >= T->u0[0])) return 0;
+  int lo = *row;
+  if (lo < 0 || lo >= T->nrows || !(T->u0[lo] <= q)) lo = 0;
+  while (lo + 1 < T->nrows && T->u0[lo + 1] <= q) ++lo;
+  *row = lo;
+  return pgb_utable_count_in_row(T, lo, q);
 }
 
 #endif  // PGB_EXACT_H
