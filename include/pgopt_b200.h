@@ -167,6 +167,8 @@ int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, co
  * 4 Box-Muller pairs from Philox (x[0] = seed, y gets 2n normals of purpose Z, sweep 1, t 5). */
 void pgb_test_force_fallback(int32_t on);
 int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_t n);
+/* DFMA micro-benchmark (8 independent chains per thread, all SMs): measured FP64 FMA rate of the device. */
+int pgb_test_fp64_peak(int32_t device, double* tflops);
 
 #ifdef __cplusplus
 }

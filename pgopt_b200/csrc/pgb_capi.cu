@@ -141,7 +141,7 @@ static cudaError_t alloc_scanws(pgb_handle* h, ScanWS* ws, int64_t N, int nc, lo
 #define A_(field, count) if ((e = dalloc(h, &ws->field, (size_t)(count))) != cudaSuccess) return e;
   A_(S, nc) A_(tsum, nc * nt) A_(tile_prefix, nc * (nt + 1)) A_(thr_ex, nc * nt * TPB) A_(tile_agg, nc * nt)
   A_(tile_ex, nc * (nt + 1)) A_(recs, nc * nt * RMAX) A_(crec, (int64_t)nc * CMAX) A_(seeds, (int64_t)nc * (CMAX + 1))
-  A_(qin_fb, nc * nt * TPB) A_(ticket, nc) A_(flag, 2 * nc) A_(pend, nc) A_(counters, 2 * nc)
+  A_(qin_fb, nc * nt * TPB) A_(Wn, nc * nt * TILE) A_(ticket, nc) A_(flag, 2 * nc) A_(pend, nc) A_(counters, 2 * nc)
 #undef A_
   if (counters) *counters = ws->counters;
   return cudaSuccess;
@@ -536,8 +536,9 @@ static int run_filter_persistent_nx(pgb_handle* h) {
   cudaStream_t s = h->stream;
   const int64_t T = fd.T;
   const int nc = fd.nc;
-  const size_t smA = (size_t)NX * fd.n_phi * 8;
+  const size_t smA = sizeof(PersistShared) + (size_t)NX * fd.n_phi * 8;
   int occ = 0;
+  CK(h, cudaFuncSetAttribute(k_sweep_persistent<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
   CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_persistent<NX>, TPB, smA));
   const int max_ctas = occ * h->num_sms;
   int nbmax = max_ctas / nc;
@@ -1033,5 +1034,53 @@ extern "C" int pgb_test_math(int32_t device, int32_t fn, const double* x, double
   CK(h, cudaGetLastError());
   CK(h, cudaDeviceSynchronize());
   CK(h, cudaMemcpy(y, dy, (size_t)nout * 8, cudaMemcpyDeviceToHost));
+  return PGB_OK;
+}
+
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+    a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int pgb_test_fp64_peak(int32_t device, double* tflops) {
+  if (!tflops) return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
+  pgb_handle tmp;
+  pgb_handle* h = &tmp;
+  struct Cleanup {
+    pgb_handle* h;
+    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
+  } cleanup{h};
+  CK(h, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(h, cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, iters = 20000;
+  double* out;
+  CK(h, dalloc(h, &out, (size_t)blocks * 256));
+  cudaEvent_t e0, e1;
+  CK(h, cudaEventCreate(&e0));
+  CK(h, cudaEventCreate(&e1));
+  k_fp64_peak<<<blocks, 256>>>(out, 1000);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    CK(h, cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, 256>>>(out, iters);
+    CK(h, cudaEventRecord(e1));
+    CK(h, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(h, cudaEventElapsedTime(&ms, e0, e1));
+    double tf = 2.0 * 8.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
   return PGB_OK;
 }

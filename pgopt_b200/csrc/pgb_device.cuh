@@ -71,7 +71,8 @@ __device__ __forceinline__ double tree4(const double v[4]) {
 }
 
 // Deterministic (but otherwise arbitrary-order) exclusive FP scan across the CTA; used only for the
-// *approximate* prefix that predicts binades.  sm: NWARP doubles.  *total = CTA sum (same order).
+// *approximate* prefix that predicts binades.  sm: NWARP + 1 doubles.  *total = CTA sum (same order).
+// The NWARP warp totals are scanned once by warp 0 (not redundantly by every thread).
 __device__ __forceinline__ double block_excl_scan_approx(double v, double* sm, double* total) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   double inc = v;
@@ -83,16 +84,24 @@ __device__ __forceinline__ double block_excl_scan_approx(double v, double* sm, d
   __syncthreads();
   if (l == 31) sm[w] = inc;
   __syncthreads();
-  double base = 0.0, tot = 0.0;
+  if (w == 0) {
+    double x = (l < NWARP) ? sm[l] : 0.0;
+    double xi = x;
 #pragma unroll
-  for (int i = 0; i < NWARP; ++i) {
-    if (i < w) base = __dadd_rn(base, sm[i]);
-    tot = __dadd_rn(tot, sm[i]);
+    for (int o = 1; o < NWARP; o <<= 1) {
+      double t = __shfl_up_sync(0xffffffffu, xi, o);
+      if (l >= o) xi = __dadd_rn(t, xi);
+    }
+    double ex = __shfl_up_sync(0xffffffffu, xi, 1);
+    if (l == 0) ex = 0.0;
+    if (l < NWARP) sm[l] = ex;
+    if (l == NWARP - 1) sm[NWARP] = xi;
   }
+  __syncthreads();
   double ex = __shfl_up_sync(0xffffffffu, inc, 1);
   if (l == 0) ex = 0.0;
-  *total = tot;
-  return __dadd_rn(base, ex);
+  *total = sm[NWARP];
+  return __dadd_rn(sm[w], ex);
 }
 
 __device__ __forceinline__ pgb_agg shfl_up_agg(pgb_agg a, int o) {
@@ -105,7 +114,7 @@ __device__ __forceinline__ pgb_agg shfl_up_agg(pgb_agg a, int o) {
 }
 
 // Exclusive segmented composition scan of one pgb_agg per thread across the CTA.
-// sm: NWARP pgb_agg.  *total = combination of all TPB elements.
+// sm: NWARP + 1 pgb_agg.  *total = combination of all TPB elements.
 __device__ __forceinline__ pgb_agg block_excl_scan_agg(pgb_agg v, pgb_agg* sm, pgb_agg* total) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   pgb_agg inc = v;
@@ -117,16 +126,23 @@ __device__ __forceinline__ pgb_agg block_excl_scan_agg(pgb_agg v, pgb_agg* sm, p
   __syncthreads();
   if (l == 31) sm[w] = inc;
   __syncthreads();
-  pgb_agg base = pgb_agg_identity(), tot = pgb_agg_identity();
+  if (w == 0) {
+    pgb_agg xi = (l < NWARP) ? sm[l] : pgb_agg_identity();
 #pragma unroll
-  for (int i = 0; i < NWARP; ++i) {
-    if (i < w) base = pgb_agg_combine(base, sm[i]);
-    tot = pgb_agg_combine(tot, sm[i]);
+    for (int o = 1; o < NWARP; o <<= 1) {
+      pgb_agg t = shfl_up_agg(xi, o);
+      if (l >= o) xi = pgb_agg_combine(t, xi);
+    }
+    pgb_agg ex = shfl_up_agg(xi, 1);
+    if (l == 0) ex = pgb_agg_identity();
+    if (l < NWARP) sm[l] = ex;
+    if (l == NWARP - 1) sm[NWARP] = xi;
   }
+  __syncthreads();
   pgb_agg ex = shfl_up_agg(inc, 1);
   if (l == 0) ex = pgb_agg_identity();
-  *total = tot;
-  return pgb_agg_combine(base, ex);
+  *total = sm[NWARP];
+  return pgb_agg_combine(sm[w], ex);
 }
 
 // order-preserving map double -> uint64 (for atomicMax over doubles)

@@ -285,6 +285,7 @@ PGB_HD int64_t pgb_utable_count_in_row(const pgb_utable* T, int lo, double q) {
 }
 // #{ i in [1, M] : u_i <= q }   (q finite >= 0)
 PGB_HD int64_t pgb_utable_count_le(const pgb_utable* T, double q) {
+  if (q != q) return T->M;  // NaN prefix: `while q < u` is false for every draw, all of them stop here
   if (T->nrows == 0 || !(q >= T->u0[0])) return 0;
   int lo = 0, hi = T->nrows - 1;
   while (lo < hi) {
@@ -295,6 +296,7 @@ PGB_HD int64_t pgb_utable_count_le(const pgb_utable* T, double q) {
 }
 // same, for a non-decreasing sequence of queries: *row is the row found for the previous query
 PGB_HD int64_t pgb_utable_count_le_hint(const pgb_utable* T, double q, int* row) {
+  if (q != q) return T->M;
   if (T->nrows == 0 || !(q >= T->u0[0])) return 0;
   int lo = *row;
   if (lo < 0 || lo >= T->nrows || !(T->u0[lo] <= q)) lo = 0;

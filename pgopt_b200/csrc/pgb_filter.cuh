@@ -176,7 +176,7 @@ __device__ __forceinline__ void block_max_to_global(double v, unsigned long long
 // ------------------------------------------------------------------------------------------
 template <int NX>
 __global__ void __launch_bounds__(TPB) k_init(FilterDev fd, int first) {
-  __shared__ double sm[NWARP];
+  __shared__ double sm[NWARP + 1];
   const int chain = blockIdx.y;
   const int64_t N = fd.N;
   double* x0 = fd.xh + (int64_t)chain * fd.T * NX * N;  // step 0
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(TPB) k_init(FilterDev fd, int first) {
 // e = exp(lw - max), tile sums; last CTA: S1
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_weights(FilterDev fd) {
-  __shared__ double sm[NWARP];
+  __shared__ double sm[NWARP + 1];
   __shared__ int sflag;
   const int chain = blockIdx.y, tile = blockIdx.x;
   const int64_t N = fd.N;
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(TPB) k_weights(FilterDev fd) {
 template <int NX>
 __global__ void __launch_bounds__(TPB) k_prep(FilterDev fd, int64_t t, int first) {
   extern __shared__ double A_sm[];
-  __shared__ double sm[NWARP];
+  __shared__ double sm[NWARP + 1];
   __shared__ int sflag;
   const int chain = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   const int64_t N = fd.N, T = fd.T;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(TPB) k_prep(FilterDev fd, int64_t t, int first
 
 // waN ./= sum(waN) (:180) in place, then tile sums for the resampler's own normalisation (:19)
 __global__ void __launch_bounds__(TPB) k_norm(FilterDev fd) {
-  __shared__ double sm[NWARP];
+  __shared__ double sm[NWARP + 1];
   __shared__ int sflag;
   const int chain = blockIdx.y, tile = blockIdx.x;
   const int64_t N = fd.N;
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(TPB) k_expand(FilterDev fd, ScanWS ws, const d
                                                 int64_t utab_index, int32_t* __restrict__ out_idx,
                                                 int64_t out_stride, int64_t t, int first, int fallback_pass) {
   __shared__ double sQ[TPB];
-  __shared__ double sm[NWARP];
+  __shared__ double sm[NWARP + 1];
   __shared__ int sI;
   const int chain = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   const int64_t N = ws.N;

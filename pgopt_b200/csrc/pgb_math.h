@@ -24,8 +24,11 @@
 
 #if defined(__CUDACC__)
 #define PGB_HD static __host__ __device__ __forceinline__
+// larger routines: one copy per kernel instead of one per call site (code size / instruction cache)
+#define PGB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define PGB_HD static inline
+#define PGB_HD_NOINLINE static inline
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -72,7 +75,7 @@ PGB_HD double pgb_pow2i(int k) { return pgb_u2d((uint64_t)(k + 1023) << 52); }
 // exp: k = rint(x*log2(e)); r = x - k*ln2 (two-constant Cody-Waite, exact first step);
 // degree-14 Taylor/Horner on |r| <= 0.3466 (remainder 4e-18), scaled by 2^k.
 // ---------------------------------------------------------------------------------
-PGB_HD double pgb_exp(double x) {
+PGB_HD_NOINLINE double pgb_exp(double x) {
   if (x != x) return x;
   if (x > 709.782712893384) return pgb_u2d(0x7ff0000000000000ull);
   if (x < -746.0) return 0.0;
@@ -106,7 +109,7 @@ PGB_HD double pgb_exp(double x) {
 // log (x > 0): x = 2^k * m, m in [sqrt(1/2), sqrt(2)); f = m-1; s = f/(2+f);
 // log(m) = f - (f^2/2 - s*(f^2/2 + R(s^2)))   (the classic 7-term even polynomial).
 // ---------------------------------------------------------------------------------
-PGB_HD double pgb_log(double x) {
+PGB_HD_NOINLINE double pgb_log(double x) {
   if (x != x || x < 0.0) return pgb_u2d(0x7ff8000000000000ull);
   if (x == 0.0) return pgb_u2d(0xfff0000000000000ull);
   uint64_t ux = pgb_d2u(x);
@@ -183,7 +186,7 @@ PGB_HD int pgb_rem_pio2(double x, double* r) {
   *r = r1;
   return (int)(((long long)kd) & 3);
 }
-PGB_HD double pgb_sin(double x) {
+PGB_HD_NOINLINE double pgb_sin(double x) {
   if (!(fabs(x) < 1e15)) return PGB_SUB(x, x);  // inf/nan/out of domain -> nan
   double r;
   int q = pgb_rem_pio2(x, &r);
@@ -194,7 +197,7 @@ PGB_HD double pgb_sin(double x) {
     default: return -pgb_kcos(r);
   }
 }
-PGB_HD double pgb_cos(double x) {
+PGB_HD_NOINLINE double pgb_cos(double x) {
   if (!(fabs(x) < 1e15)) return PGB_SUB(x, x);
   double r;
   int q = pgb_rem_pio2(x, &r);
@@ -205,7 +208,7 @@ PGB_HD double pgb_cos(double x) {
     default: return pgb_ksin(r);
   }
 }
-PGB_HD void pgb_sincos(double x, double* s, double* c) {
+PGB_HD_NOINLINE void pgb_sincos(double x, double* s, double* c) {
   if (!(fabs(x) < 1e15)) {
     *s = *c = PGB_SUB(x, x);
     return;
@@ -234,7 +237,7 @@ PGB_HD void pgb_mulhilo32(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
   *hi = (uint32_t)(p >> 32);
   *lo = (uint32_t)p;
 }
-PGB_HD pgb_u32x4 pgb_philox4x32_10(pgb_u32x4 ctr, uint32_t k0, uint32_t k1) {
+PGB_HD_NOINLINE pgb_u32x4 pgb_philox4x32_10(pgb_u32x4 ctr, uint32_t k0, uint32_t k1) {
   for (int i = 0; i < 10; ++i) {
     uint32_t hi0, lo0, hi1, lo1;
     pgb_mulhilo32(0xD2511F53u, ctr.v[0], &hi0, &lo0);

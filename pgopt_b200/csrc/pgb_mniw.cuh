@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) k_stats_z(FilterDev fd, MniwDev md) {
 
 // One CTA per output entry: Phi = zeta zeta', Psi = zeta z', Sigma = z z' as tree sums over t.
 __global__ void __launch_bounds__(TPB) k_stats(MniwDev md) {
-  __shared__ double sm[NWARP];
+  __shared__ double sm[NWARP + 1];
   const int chain = blockIdx.y;
   const int nx = md.n_x, np = md.n_phi;
   const int64_t Tm1 = md.Tm1;

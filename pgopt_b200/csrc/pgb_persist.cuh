@@ -26,6 +26,7 @@ constexpr int P_MAXTPC = 64;      // max tiles per CTA
 constexpr int P_MAXREC = 512;     // complex threads resolved per scan (more -> serial fallback)
 constexpr int P_HEAVY = 32;       // offspring count above which a particle goes to the cooperative list
 constexpr int P_HEAVY_MAX = 1 << 15;
+constexpr int P_CAP = 2048;        // output slots staged per chunk in shared memory
 
 struct HeavyEnt {
   int64_t n;          // ancestor (0-based)
@@ -79,8 +80,8 @@ struct TreeAcc {
 };
 
 struct PersistShared {
-  double sm[NWARP];
-  pgb_agg smagg[NWARP];
+  double sm[NWARP + 1];
+  pgb_agg smagg[NWARP + 1];
   double sP[TPB];
   double sQ[TPB];
   int sI;
@@ -92,6 +93,9 @@ struct PersistShared {
   double rW[P_MAXREC][4];
   double seeds[P_MAXREC + 1];
   int any_flag;
+  long long sJ[2];           // output range of the current tile
+  int s_anc[P_CAP];          // ancestor (+1; 0 = index 0; -1 = skip) of each output slot of the current chunk
+  pgb_utable ut;             // this step's sampling grid
 };
 
 // exclusive approximate scan of p[0..nb) into sh.pfx[0..nb] (every CTA computes identical values)
@@ -130,6 +134,11 @@ __device__ __forceinline__ void p_scan_local(const ScanWS& ws, const double* v, 
       if (!(W[i] >= 0.0 && W[i] <= 1.7976931348623157e308)) bad = true;
     }
     if (bad) atomicOr(&status[chain], 4);
+    {
+      double2* wn = reinterpret_cast<double2*>(ws.Wn + ((int64_t)chain * ws.nt + tile) * TILE + (int64_t)tid * IPT);
+      wn[0] = make_double2(W[0], W[1]);
+      wn[1] = make_double2(W[2], W[3]);
+    }
     double s1 = W[0], s2 = __dadd_rn(s1, W[1]), s3 = __dadd_rn(s2, W[2]), s4 = __dadd_rn(s3, W[3]);
     double tot;
     double ex = block_excl_scan_approx(s4, sh.sm, &tot);
@@ -227,10 +236,12 @@ __device__ __forceinline__ bool p_exact_prefixes(const ScanWS& ws, const double*
                                                  double q[5], int* flagp) {
   const int tid = threadIdx.x;
   const int tile = c * tpc + k;
-  const double* vc = v + (int64_t)chain * ws.N;
   int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) W[i] = (base + i < ws.N) ? __ddiv_rn(vc[base + i], S) : 0.0;
+  {
+    const double2* wn = reinterpret_cast<const double2*>(ws.Wn + ((int64_t)chain * ws.nt + tile) * TILE + (int64_t)tid * IPT);
+    double2 a = wn[0], b = wn[1];
+    W[0] = a.x; W[1] = a.y; W[2] = b.x; W[3] = b.y;
+  }
   const int64_t gthr = ((int64_t)chain * ws.nt + tile) * TPB + tid;
   double qin;
   if (fallback_pass) {
@@ -398,6 +409,107 @@ __device__ __forceinline__ void p_heavy(const FilterDev& fd, int chain, int c, i
   }
 }
 
+// By-output expansion of one tile (normal pass, MODE_PROPAGATE): the tile's elements own a contiguous range of
+// output slots; each thread first *scatters* the ancestor index of its few offspring into shared memory, then
+// every thread *propagates* one output slot at a time — no SIMT divergence in the expensive part (Philox,
+// Box-Muller, log-weight) and fully coalesced stores of a[t,:], x_t, lw.
+template <int NX>
+__device__ __forceinline__ void p_consume_by_output(const FilterDev& fd, const EmitCtx<NX>& ec, int chain, int tile,
+                                                    const double q[5], PersistShared& sh, int64_t t, int first,
+                                                    int* stat, double& lmax, HeavyEnt* heavy, int* heavy_cnt) {
+  const int tid = threadIdx.x;
+  const int64_t N = fd.N;
+  const pgb_utable* ut = &sh.ut;
+  const int64_t M = ut->M;
+  const int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
+  int64_t rr[5];
+  int64_t zero_upto = 0;
+  if (base < N) {
+    int row = -1;
+    rr[0] = pgb_utable_count_le_hint(ut, q[0], &row);
+    if (base == 0) {
+      if (rr[0] > 0) atomicOr(stat, 2);
+      zero_upto = rr[0];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int64_t n = base + i;
+      if (n < N) {
+        int64_t r = pgb_utable_count_le_hint(ut, q[i + 1], &row);
+        if (r < rr[i]) r = rr[i];
+        if (n == N - 1 && r < M) {
+          atomicOr(stat, 1);
+          r = M;
+        }
+        rr[i + 1] = r;
+      } else {
+        rr[i + 1] = rr[i];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) rr[i] = M;
+  }
+  const int64_t jfrom0 = (base == 0) ? 0 : rr[0];
+  __syncthreads();
+  if (tid == 0) sh.sJ[0] = jfrom0;
+  if (tid == TPB - 1) sh.sJ[1] = rr[4];
+  __syncthreads();
+  const int64_t J0 = sh.sJ[0], J1 = sh.sJ[1];
+  // heavy particles go to the chain-wide cooperative list (once)
+  bool is_heavy[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t lo = (i == 0) ? jfrom0 : rr[i], hi = rr[i + 1];
+    is_heavy[i] = false;
+    if (hi - lo > P_HEAVY && base + i < N) {
+      int slot = atomicAdd(heavy_cnt, 1);
+      if (slot < P_HEAVY_MAX) {
+        HeavyEnt he;
+        he.n = base + i; he.jfrom = lo; he.r = hi; he.zero_upto = (i == 0) ? zero_upto : 0;
+        heavy[slot] = he;
+        is_heavy[i] = true;
+      }
+    }
+  }
+  for (int64_t cs = J0; cs < J1; cs += P_CAP) {
+    const int64_t ce = (cs + P_CAP < J1) ? cs + P_CAP : J1;  // chunk covers draws (cs, ce]
+    for (int o = tid; o < (int)(ce - cs); o += TPB) sh.s_anc[o] = -1;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (is_heavy[i]) continue;
+      int64_t lo = (i == 0) ? jfrom0 : rr[i], hi = rr[i + 1];
+      if (lo < cs) lo = cs;
+      if (hi > ce) hi = ce;
+      const int64_t zu = (i == 0) ? zero_upto : 0;
+      for (int64_t j = lo + 1; j <= hi; ++j) sh.s_anc[j - cs - 1] = (j <= zu) ? 0 : (int)(base + i) + 1;
+    }
+    __syncthreads();
+    for (int o = tid; o < (int)(ce - cs); o += TPB) {
+      const int v = sh.s_anc[o];
+      if (v < 0) continue;
+      const int64_t n = (v == 0) ? 0 : (int64_t)v - 1;
+      double F[NX];
+#pragma unroll
+      for (int d = 0; d < NX; ++d) F[d] = ec.Fb[(int64_t)d * N + n];
+      emit_offspring<NX>(fd, ec, chain, t, cs + o, (v == 0) ? -1 : (int32_t)n, F, stat, lmax);
+    }
+    __syncthreads();
+  }
+  if (!first && tile == 0 && tid == 0) {
+    double x[NX];
+#pragma unroll
+    for (int d = 0; d < NX; ++d) {
+      x[d] = fd.xprim[(int64_t)chain * NX * fd.T + d + NX * t];
+      ec.xt[(int64_t)d * N + (N - 1)] = x[d];
+    }
+    double lw = log_weight<NX>(fd, x, ec.yt);
+    ec.lwb[N - 1] = lw;
+    lmax = fmax(lmax, lw);
+  }
+}
+
 // serial exact walk by warp 0 of the chain's first CTA (fix-up path)
 __device__ __forceinline__ void p_seq_exact(const ScanWS& ws, const double* v, double S, int chain) {
   const int lane = threadIdx.x;
@@ -422,8 +534,9 @@ __device__ __forceinline__ void p_seq_exact(const ScanWS& ws, const double* v, d
 
 template <int NX>
 __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, PersistDev pd, int first) {
-  extern __shared__ double A_sm[];
-  __shared__ PersistShared sh;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PersistShared& sh = *reinterpret_cast<PersistShared*>(smem_raw);
+  double* A_sm = reinterpret_cast<double*>(smem_raw + sizeof(PersistShared));
   const int tid = threadIdx.x;
   const int nb = pd.nb, tpc = pd.tpc;
   const int chain = blockIdx.x / nb, c = blockIdx.x % nb;
@@ -626,17 +739,25 @@ __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, Persi
       const bool skip = sh.sI != 0;
       double lmax = -INFINITY;
       const pgb_utable* ut = last_only ? &fd.utab_star[chain] : &fd.utab_res[(int64_t)chain * T + t];
+      {  // stage this step's sampling grid in shared memory (every thread searches it five times)
+        const int* src = reinterpret_cast<const int*>(ut);
+        int* dst = reinterpret_cast<int*>(&sh.ut);
+        for (int i = tid; i < (int)(sizeof(pgb_utable) / 4); i += TPB) dst[i] = src[i];
+        __syncthreads();
+      }
+      EmitCtx<NX> ec;
+      if (!last_only) emit_ctx_init<NX>(ec, fd, chain, t);
       for (int k = 0; k < tpc && !skip; ++k) {
         const int tile = c * tpc + k;
         if (tile >= nt) break;
         double W[4], q[5];
         if (!p_exact_prefixes(fd.main, fd.wbuf, S2, chain, c, k, nb, tpc, false, sh, W, q, fmain)) continue;
         if (last_only)
-          p_consume<NX, MODE_INDEX>(fd, chain, tile, q, ut, pd.star_idx + chain, t, first, &fd.main.pend[chain], lmax,
+          p_consume<NX, MODE_INDEX>(fd, chain, tile, q, &sh.ut, pd.star_idx + chain, t, first, &fd.main.pend[chain], lmax,
                                     nullptr, nullptr);
         else
-          p_consume<NX, MODE_PROPAGATE>(fd, chain, tile, q, ut, nullptr, t, first, &fd.main.pend[chain], lmax,
-                                        pd.heavy + (int64_t)chain * P_HEAVY_MAX, pd.heavy_cnt + chain);
+          p_consume_by_output<NX>(fd, ec, chain, tile, q, sh, t, first, &fd.main.pend[chain], lmax,
+                                  pd.heavy + (int64_t)chain * P_HEAVY_MAX, pd.heavy_cnt + chain);
       }
       if (!last_only) block_max_to_global(lmax, &fd.maxkey[chain], sh.sm);
       if (anc) {

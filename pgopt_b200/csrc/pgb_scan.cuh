@@ -34,6 +34,7 @@ struct ScanWS {
   ScanRec* crec;      // [nc][CMAX]      compacted records in global order
   double* seeds;      // [nc][CMAX+1]
   double* qin_fb;     // [nc][nt*TPB]    exact incoming values written by the serial fallback
+  double* Wn;         // [nc][nt*TILE]   normalised weights W = v/S kept between scan-local and consumer (persistent path)
   unsigned int* ticket; // [nc]
   int* flag;          // [nc]  bit0: redo this scan with the serial exact walk
   int* pend;          // [nc]  status bits raised by the normal consumer pass (merged or discarded)
@@ -60,7 +61,7 @@ __device__ __forceinline__ void finalize_tile_sums(const double* __restrict__ ts
 
 // Stand-alone tile-sum kernel (used by the stand-alone resampling entry point and the star draw).
 __global__ void __launch_bounds__(TPB) k_tile_sums(ScanWS ws, const double* __restrict__ v) {
-  __shared__ double sm[NWARP];
+  __shared__ double sm[NWARP + 1];
   __shared__ int sflag;
   const int chain = blockIdx.y, tile = blockIdx.x;
   const double* vc = v + (int64_t)chain * ws.N;
@@ -78,8 +79,8 @@ __global__ void __launch_bounds__(TPB) k_tile_sums(ScanWS ws, const double* __re
 }
 
 __global__ void __launch_bounds__(TPB) k_scan_local(ScanWS ws, const double* __restrict__ v, int* __restrict__ status) {
-  __shared__ double sm[NWARP];
-  __shared__ pgb_agg smagg[NWARP];
+  __shared__ double sm[NWARP + 1];
+  __shared__ pgb_agg smagg[NWARP + 1];
   __shared__ double sP[TPB];
   const int chain = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
   const double* vc = v + (int64_t)chain * ws.N;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(TPB) k_scan_local(ScanWS ws, const double* __r
 constexpr int RESOLVE_SMEM_RECS = 512;
 
 __global__ void __launch_bounds__(TPB) k_resolve(ScanWS ws, int force_fallback) {
-  __shared__ pgb_agg smagg[NWARP];
+  __shared__ pgb_agg smagg[NWARP + 1];
   __shared__ pgb_map s_f[RESOLVE_SMEM_RECS];
   __shared__ double s_W[RESOLVE_SMEM_RECS][4];
   const int chain = blockIdx.y, tid = threadIdx.x;

@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing: independent PG chains (and independent scenarios) sharded over ranks, one process per GPU.
+
+The within-chain filter does not shard, so there is no collective on the data path: every rank runs
+its own chains with their own Philox stream ids and only the kept samples — packed (A, Q, x_T) per sample, about
+2 KB — are gathered at the end with one all-gather (NCCL on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block [lo, hi) of n_items owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_samples(A_s, Q_s, x_T):
+    """A_s (n, K, n_x*n_phi), Q_s (n, K, n_x*n_x), x_T (n, K, n_x) -> (n, K, P) float64"""
+    return np.ascontiguousarray(np.concatenate([A_s, Q_s, x_T], axis=2), dtype=np.float64)
+
+
+def unpack_samples(pack, n_x, n_phi):
+    a, q = n_x * n_phi, n_x * n_x
+    return pack[..., :a], pack[..., a:a + q], pack[..., a + q:a + q + n_x]
+
+
+def gather_packed(local_pack, n_total, dist=None, device=None):
+    """All-gather the per-rank packs (uneven shards are padded to the largest) -> (n_total, K, P) on every rank."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_pack
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nmax = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    K, P = local_pack.shape[1], local_pack.shape[2]
+    buf = torch.zeros((nmax, K, P), dtype=torch.float64, device=device)
+    buf[:local_pack.shape[0]] = torch.from_numpy(local_pack).to(buf.device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        parts.append(out[r][:hi - lo].cpu().numpy())
+    return np.concatenate(parts, axis=0)
+
+
+def draw_x_T(w_s, x_s, n_x, seed, chain_ids, resample):
+    """x_T = x_m1[:, star] with star ~ systematic_resampling(w_m1, 1) (optimal_control_Ipopt.jl:58-59), drawn on the
+    rank that owns the chain so that the N-sized particle arrays never travel."""
+    n, K, N = w_s.shape
+    out = np.empty((n, K, n_x))
+    for i in range(n):
+        rng = np.random.default_rng([seed, int(chain_ids[i])])
+        for k in range(K):
+            star = int(resample(w_s[i, k], 1, rng.random())[0])
+            out[i, k] = x_s[i, k].reshape((n_x, N), order="F")[:, max(star, 1) - 1]
+    return out
+
+
+def run_chains(engine_factory, n_chains, K, K_b, k_d, seed, dist=None, device=None, resample=None):
+    """Run `n_chains` independent chains sharded over the process group and gather packed (A, Q, x_T).
+    engine_factory(n_local, chain_base) -> a configured ParticleGibbsEngine (data, prior, state set)."""
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    lo, hi = shard_range(n_chains, rank, world)
+    if resample is None:
+        from .api import systematic_resampling as resample
+    eng = engine_factory(hi - lo, lo)
+    try:
+        eng.set_rng_philox(seed, lo)
+        A_s, Q_s, w_s, x_s, _ = eng.particle_gibbs(K, K_b, k_d)
+        x_T = draw_x_T(w_s, x_s, eng.n_x, seed, range(lo, hi), resample)
+        local = pack_samples(A_s, Q_s, x_T)
+    finally:
+        eng.close()
+    return gather_packed(local, n_chains, dist, device)

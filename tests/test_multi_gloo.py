@@ -1,0 +1,83 @@
+"""N > 1 host logic on the CPU: world_size-2 gloo.  Each rank produces the samples of its own chains (here with
+the CPU oracle standing in for the GPU engine), packs (A, Q, x_T) and all-gathers; the result must equal the
+single-process run of all chains, i.e. sharding must not change any sample."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import _oracle as O
+import _problems as P
+from pgopt_b200 import multi
+
+N_CHAINS, K, N, T = 5, 2, 30, 40
+
+
+class OracleEngine:
+    """duck-typed stand-in for ParticleGibbsEngine.particle_gibbs on the CPU"""
+    n_x, n_phi = 2, 5
+
+    def __init__(self, n_local, chain_base):
+        self.n_local, self.chain_base = n_local, chain_base
+        self.u, self.y, _ = P.make_data(T, 3)
+
+    def set_rng_philox(self, seed, chain_base):
+        self.seed, self.chain_base = seed, chain_base
+
+    def particle_gibbs(self, K_, K_b, k_d):
+        A_s, Q_s = np.empty((self.n_local, K_, 10)), np.empty((self.n_local, K_, 4))
+        w_s, x_s = np.empty((self.n_local, K_, N)), np.empty((self.n_local, K_, 2 * N))
+        for i in range(self.n_local):
+            r = O.particle_gibbs(O.known_model(), N, T, self.u, self.y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2),
+                                 np.zeros((2, 5)), 100 * np.eye(2), 10 * np.ones(5), 100 * np.eye(2), 10.0, K_, K_b, k_d,
+                                 seed=self.seed, chain=self.chain_base + i)
+            A_s[i] = r["A"].transpose(0, 2, 1).reshape(K_, -1)
+            Q_s[i] = r["Q"].transpose(0, 2, 1).reshape(K_, -1)
+            w_s[i] = r["w"]
+            x_s[i] = r["x"].reshape(K_, -1)  # (N, n_x) C-order == (n_x, N) F-order
+        return A_s, Q_s, w_s, x_s, self.u[:, -1]
+
+    def close(self):
+        pass
+
+
+def _resample(w, n, rnd):
+    return O.systematic_resampling(w, n, rnd)[0]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        got = multi.run_chains(OracleEngine, N_CHAINS, K, 3, 1, seed=9, dist=dist, resample=_resample)
+        np.save(os.path.join(out_dir, "rank%d.npy" % rank), got)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_covers_everything():
+    for n in (1, 5, 8, 64, 100000):
+        for world in (1, 2, 3, 8):
+            blocks = [multi.shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b[1] - b[0] for b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_ranks_gather_equals_single_process(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ref = multi.run_chains(OracleEngine, N_CHAINS, K, 3, 1, seed=9, dist=None, resample=_resample)
+    for r in range(2):
+        got = np.load(os.path.join(str(tmp_path), "rank%d.npy" % r))
+        assert got.shape == (N_CHAINS, K, 10 + 4 + 2)
+        np.testing.assert_array_equal(got, ref)
+    A, Q, xT = multi.unpack_samples(ref, 2, 5)
+    assert A.shape == (N_CHAINS, K, 10) and Q.shape == (N_CHAINS, K, 4) and xT.shape == (N_CHAINS, K, 2)
