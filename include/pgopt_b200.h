@@ -134,6 +134,10 @@ enum { PGB_PROF_PREP = 0, PGB_PROF_NORM, PGB_PROF_SCAN_LOCAL, PGB_PROF_RESOLVE, 
 /* persistent != 0 (default): the whole T loop of a sweep is one cooperative persistent kernel; 0: one
  * launch per phase (13 launches per time step; kept for per-kernel profiling and as a cross-check). */
 int pgb_set_mode(pgb_handle* h, int32_t persistent);
+/* average over CTAs of the SM-clock cycles thread 0 spent in each section of the last persistent sweep
+ * (section ids documented in pgb_persist.cuh: 1 phase A, 2 wait B1, 3 scan-local main, 4 normalise side, 5 wait B2,
+ * 6 resolve, 7 prefixes+expansion, 8 scan-local side, 9 wait B3, 10 side resolve+index, 11 weights, 12 wait B4, 13 fix-up test) */
+int pgb_get_phase_cycles(pgb_handle* h, double* avg_cycles /*[16]*/, int32_t* n_ctas);
 int pgb_timer_start(pgb_handle* h);
 int pgb_timer_stop(pgb_handle* h, double* elapsed_ms);
 int pgb_profile(pgb_handle* h, int32_t on);

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpgopt_b200.so")
+LIB_PATH = os.environ.get("PGOPT_B200_LIB", os.path.join(HERE, "lib", "libpgopt_b200.so"))
 PGB_MAX_Z = 8
 
 PGB_OK, PGB_ERR_INVALID, PGB_ERR_CUDA, PGB_ERR_NOT_POSDEF, PGB_ERR_STATE = 0, 1, 2, 3, 4
@@ -31,7 +31,7 @@ EXPORTS = ["pgb_version", "pgb_last_error", "pgb_create", "pgb_destroy", "pgb_se
            "pgb_set_rng_injected", "pgb_sweep", "pgb_sweep_filter", "pgb_sweep_mniw", "pgb_particle_gibbs",
            "pgb_get_sample", "pgb_get_history", "pgb_get_stats", "pgb_get_status", "pgb_synchronize",
            "pgb_systematic_resampling", "pgb_mniw_sample", "pgb_rollout", "pgb_test_force_fallback", "pgb_test_math", "pgb_test_fp64_peak",
-           "pgb_set_mode", "pgb_timer_start", "pgb_timer_stop", "pgb_profile", "pgb_get_profile", "pgb_get_launch_count"]
+           "pgb_set_mode", "pgb_get_phase_cycles", "pgb_timer_start", "pgb_timer_stop", "pgb_profile", "pgb_get_profile", "pgb_get_launch_count"]
 
 
 def lib():

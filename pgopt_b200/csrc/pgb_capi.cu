@@ -292,6 +292,7 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
     pd.star_idx = h->d_star_idx;
     CKC(dalloc(h, &pd.heavy, (size_t)nc * P_HEAVY_MAX));
     CKC(dalloc(h, &pd.heavy_cnt, (size_t)nc));
+    CKC(dalloc(h, &pd.prof, (size_t)1024 * P_NPROF));
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
     h->num_sms = prop.multiProcessorCount;
@@ -949,6 +950,20 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   return PGB_OK;
 }
 
+extern "C" int pgb_get_phase_cycles(pgb_handle* h, double* avg_cycles /*[16]*/, int32_t* n_ctas) {
+  NEED(h);
+  CK(h, cudaStreamSynchronize(h->stream));
+  const int g = h->fd.nc * h->pd.nb;
+  std::vector<long long> v((size_t)1024 * P_NPROF);
+  CK(h, cudaMemcpy(v.data(), h->pd.prof, v.size() * 8, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < P_NPROF; ++i) {
+    double s = 0;
+    for (int c = 0; c < g && c < 1024; ++c) s += (double)v[(size_t)c * P_NPROF + i];
+    avg_cycles[i] = g > 0 ? s / g : 0.0;
+  }
+  if (n_ctas) *n_ctas = g;
+  return PGB_OK;
+}
 extern "C" int pgb_set_mode(pgb_handle* h, int32_t persistent) {
   NEED(h);
   h->persistent = persistent != 0;

@@ -21,11 +21,12 @@
 
 namespace pgb {
 
-constexpr int P_MAXNB = 320;      // max CTAs per chain (>= 148 * 2)
+constexpr int P_MAXNB = 640;      // max CTAs per chain (>= 148 * 4)
 constexpr int P_MAXTPC = 64;      // max tiles per CTA
-constexpr int P_MAXREC = 512;     // complex threads resolved per scan (more -> serial fallback)
+constexpr int P_MAXREC = 160;     // complex threads resolved per scan (more -> serial fallback)
 constexpr int P_HEAVY = 32;       // offspring count above which a particle goes to the cooperative list
 constexpr int P_HEAVY_MAX = 1 << 15;
+constexpr int P_NPROF = 16;
 constexpr int P_CAP = 2048;        // output slots staged per chunk in shared memory
 
 struct HeavyEnt {
@@ -43,6 +44,7 @@ struct PersistDev {
   // particles with more than P_HEAVY offspring are expanded by the whole chain's CTAs (phase D)
   struct HeavyEnt* heavy;   // [nc][P_HEAVY_MAX]
   int* heavy_cnt;           // [nc]
+  long long* prof;          // [grid][P_NPROF] per-CTA cycle counts per section (thread 0), or null
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -532,8 +534,11 @@ __device__ __forceinline__ void p_seq_exact(const ScanWS& ws, const double* v, d
   if (lane == 0) ws.counters[2 * chain + 0] += 1;
 }
 
+#ifndef PGB_PERSIST_MINBLOCKS
+#define PGB_PERSIST_MINBLOCKS 2
+#endif
 template <int NX>
-__global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, PersistDev pd, int first) {
+__global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent(FilterDev fd, PersistDev pd, int first) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PersistShared& sh = *reinterpret_cast<PersistShared*>(smem_raw);
   double* A_sm = reinterpret_cast<double*>(smem_raw + sizeof(PersistShared));
@@ -543,6 +548,12 @@ __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, Persi
   const int64_t N = fd.N, T = fd.T;
   const int nt = fd.nt;
   unsigned int bar_target = 0;
+  // section timers (thread 0 of every CTA; SM clock): see pgb_get_phase_cycles
+  long long tacc[P_NPROF];
+#pragma unroll
+  for (int i = 0; i < P_NPROF; ++i) tacc[i] = 0;
+  long long tlast = clock64();
+#define P_TICK(idx) do { if (tid == 0) { long long now_ = clock64(); tacc[idx] += now_ - tlast; tlast = now_; } } while (0)
   double* pe = pd.pe + (int64_t)chain * nb;
   double* pw = pd.pw + (int64_t)chain * nb;
   double* pa = pd.pa + (int64_t)chain * nb;
@@ -617,6 +628,7 @@ __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, Persi
   weights_phase();
   grid_barrier(pd.bar, bar_target);
 
+  P_TICK(0);
   for (int64_t t = 1; t <= T; ++t) {
     const bool last_only = (t == T);  // finalise w_T and draw the trajectory index only
     const bool anc = !first && !last_only;
@@ -697,12 +709,15 @@ __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, Persi
         if (anc) pa[c] = acca.result();
       }
     }
+    P_TICK(1);
     grid_barrier(pd.bar, bar_target);  // B1
+    P_TICK(2);
     // ================================================================ phase B: main scan-local, side normalise
     const double S2 = block_tree_sum_array(pw, nb, sh.sm);
     {
       approx_prefix(pw, nb, sh);
       p_scan_local(fd.main, fd.wbuf, S2, sh.tsum_w, chain, c, nb, tpc, sh, fd.status, fmain);
+      P_TICK(3);
       if (anc) {
         const double S3 = block_tree_sum_array(pa, nb, sh.sm);
         double* wa = fd.waN + (int64_t)chain * N;
@@ -726,11 +741,14 @@ __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, Persi
         }
         if (tid == 0) pa2[c] = acc.result();
       }
+      P_TICK(4);
     }
     grid_barrier(pd.bar, bar_target);  // B2
+    P_TICK(5);
     // ================================================================ phase C: main resolve + consume, side scan-local
     {
       p_resolve(fd.main, chain, nb, tpc, sh, pd.force_fallback, fmain);
+      P_TICK(6);
       if (tid == 0) {
         sh.sI = *fmain & 1;
         if (c == 0) fd.main.counters[2 * chain + 1] += 1;
@@ -760,13 +778,16 @@ __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, Persi
                                   pd.heavy + (int64_t)chain * P_HEAVY_MAX, pd.heavy_cnt + chain);
       }
       if (!last_only) block_max_to_global(lmax, &fd.maxkey[chain], sh.sm);
+      P_TICK(7);
       if (anc) {
         const double S4 = block_tree_sum_array(pa2, nb, sh.sm);
         approx_prefix(pa2, nb, sh);
         p_scan_local(fd.side, fd.waN, S4, sh.tsum_a2, chain, c, nb, tpc, sh, fd.status, fside);
       }
+      P_TICK(8);
     }
     grid_barrier(pd.bar, bar_target);  // B3
+    P_TICK(9);
     // ================================================================ phase D: side resolve + find, weights (optimistic)
     {
       if (anc) {
@@ -789,6 +810,7 @@ __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, Persi
           p_consume<NX, MODE_INDEX>(fd, chain, tile, q, ut, out, t, first, &fd.side.pend[chain], dummy, nullptr, nullptr);
         }
       }
+      P_TICK(10);
       // degenerate weights: a few particles own most offspring -> expand them with the whole chain, then one
       // extra (grid-uniform) barrier before the weight update can see every log-weight
       if (!last_only) {
@@ -814,7 +836,9 @@ __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, Persi
         fd.side.flag[chain + fd.nc * (int)((t + 1) & 1)] = 0;
       }
     }
+    P_TICK(11);
     grid_barrier(pd.bar, bar_target);  // B4 (all consumers done; this step's flags are final)
+    P_TICK(12);
     // ---------------------------------------------------------------- fix-up: rare, uniform across the grid
     {
       if (tid == 0) {
@@ -879,7 +903,13 @@ __global__ void __launch_bounds__(TPB, 2) k_sweep_persistent(FilterDev fd, Persi
         fd.side.pend[chain] = 0;
       }
     }
+    P_TICK(13);
   }
+  if (pd.prof && tid == 0) {
+#pragma unroll
+    for (int i = 0; i < P_NPROF; ++i) pd.prof[(int64_t)blockIdx.x * P_NPROF + i] = tacc[i];
+  }
+#undef P_TICK
 }
 
 }  // namespace pgb
