@@ -168,7 +168,8 @@ int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, co
 /* ---- test hooks (not part of the drop-in surface) ---------------------------------------------
  * pgb_test_force_fallback(1) makes every exact scan take the serial-walk fallback path (results must
  * not change); pgb_test_math evaluates the device build of pgb_math.h: fn 0 exp, 1 log, 2 sin, 3 cos,
- * 4 Box-Muller pairs from Philox (x[0] = seed, y gets 2n normals of purpose Z, sweep 1, t 5). */
+ * 4 Box-Muller pairs from Philox (x[0] = seed, y gets 2n normals of purpose Z, sweep 1, t 5);
+ * 10..14: the same through the 4-wide branch-free versions of pgb_vmath.cuh (11: positive normal arguments). */
 void pgb_test_force_fallback(int32_t on);
 int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_t n);
 /* DFMA micro-benchmark (8 independent chains per thread, all SMs): measured FP64 FMA rate of the device. */

@@ -1022,8 +1022,34 @@ __global__ void k_test_math(int fn, const double* __restrict__ x, double* __rest
     case 1: y[i] = pgb_log(x[i]); break;
     case 2: y[i] = pgb_sin(x[i]); break;
     case 3: y[i] = pgb_cos(x[i]); break;
-    default: pgb_normal_pair(pgb_stream_block(seed, PGB_STREAM_Z, 0, 1, 5, (uint32_t)i), &y[2 * i], &y[2 * i + 1]);
+    case 4: pgb_normal_pair(pgb_stream_block(seed, PGB_STREAM_Z, 0, 1, 5, (uint32_t)i), &y[2 * i], &y[2 * i + 1]); break;
+    default: break;
   }
+}
+
+// K-wide branch-free versions (pgb_vmath.cuh): thread i handles elements 4i..4i+3
+__global__ void k_test_vmath(int fn, const double* __restrict__ x, double* __restrict__ y, int64_t n, uint64_t seed) {
+  int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  double a[4], b[4], c[4];
+  for (int k = 0; k < 4; ++k) a[k] = (fn != 14 && i4 + k < n) ? x[i4 + k] : 1.0;
+  if (fn == 10) vexp<4>(a, b);
+  else if (fn == 11) vlog_pos_normal<4>(a, b);
+  else if (fn == 12) vsincos<4>(a, b, c);
+  else if (fn == 13) vsincos<4>(a, c, b);
+  else {
+    pgb_u32x4 ctr[4];
+    for (int k = 0; k < 4; ++k) {
+      ctr[k].v[0] = (uint32_t)(i4 + k); ctr[k].v[1] = 5; ctr[k].v[2] = 1; ctr[k].v[3] = ((uint32_t)PGB_STREAM_Z << 24);
+    }
+    vphilox<4>(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    vnormal_pairs<4>(ctr, b, c);
+    for (int k = 0; k < 4; ++k)
+      if (i4 + k < n) { y[2 * (i4 + k)] = b[k]; y[2 * (i4 + k) + 1] = c[k]; }
+    return;
+  }
+  for (int k = 0; k < 4; ++k)
+    if (i4 + k < n) y[i4 + k] = b[k];
 }
 
 extern "C" int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_t n) {
@@ -1038,14 +1064,16 @@ extern "C" int pgb_test_math(int32_t device, int32_t fn, const double* x, double
     ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
   } cleanup{h};
   CK(h, cudaSetDevice(device));
-  const int64_t nout = (fn == 4) ? 2 * n : n;
-  const int64_t nin = (fn == 4) ? 1 : n;
+  const bool pairs = (fn == 4 || fn == 14);
+  const int64_t nout = pairs ? 2 * n : n;
+  const int64_t nin = pairs ? 1 : n;
   double *dx, *dy;
   CK(h, dalloc(h, &dx, (size_t)nin));
   CK(h, dalloc(h, &dy, (size_t)nout));
   CK(h, cudaMemcpy(dx, x, (size_t)nin * 8, cudaMemcpyHostToDevice));
-  uint64_t seed = (fn == 4) ? (uint64_t)x[0] : 0;
-  k_test_math<<<(unsigned)((n + 255) / 256), 256>>>(fn, dx, dy, n, seed);
+  uint64_t seed = pairs ? (uint64_t)x[0] : 0;
+  if (fn >= 10) k_test_vmath<<<(unsigned)((n + 1023) / 1024), 256>>>(fn, dx, dy, n, seed);
+  else k_test_math<<<(unsigned)((n + 255) / 256), 256>>>(fn, dx, dy, n, seed);
   CK(h, cudaGetLastError());
   CK(h, cudaDeviceSynchronize());
   CK(h, cudaMemcpy(y, dy, (size_t)nout * 8, cudaMemcpyDeviceToHost));

@@ -12,6 +12,7 @@
 //   k_weights  e = exp(lw - max) (:198) and tile sums
 #pragma once
 #include "pgb_scan.cuh"
+#include "pgb_vmath.cuh"
 
 namespace pgb {
 
@@ -106,6 +107,41 @@ __device__ __forceinline__ void eval_F(const FilterDev& fd, const double* __rest
   for (int d = 0; d < NX; ++d) F[d] = acc[d];
 }
 
+// F for the thread's four particles at once (known basis: the four sin/cos chains are interleaved)
+template <int NX>
+__device__ __forceinline__ void eval_F4(const FilterDev& fd, const double* __restrict__ A_sm, const double (&x)[4][NX],
+                                        const double* __restrict__ u, double (&F)[4][NX]) {
+  if (fd.basis == 0) {
+    double a3[4], a2[4], s3[4], c3[4], s2[4], c2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      a3[k] = __dmul_rn(3.0, x[k][0]);
+      a2[k] = __dmul_rn(2.0, x[k][NX > 1 ? 1 : 0]);
+    }
+    vsincos<4>(a3, s3, c3);
+    vsincos<4>(a2, s2, c2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double phi[5];
+      phi[0] = __dmul_rn(0.1, x[k][0]);
+      phi[1] = __dmul_rn(0.1, x[k][NX > 1 ? 1 : 0]);
+      phi[2] = u[0];
+      phi[3] = __dmul_rn(__dmul_rn(0.01, c3[k]), x[k][NX > 1 ? 1 : 0]);
+      phi[4] = __dmul_rn(__dmul_rn(0.1, s2[k]), u[0]);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) acc = __fma_rn(A_sm[d + NX * i], phi[i], acc);
+        F[k][d] = acc;
+      }
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int k = 0; k < 4; ++k) eval_F<NX>(fd, A_sm, x[k], u, F[k]);
+}
+
 template <int NX>
 __device__ __forceinline__ double log_weight(const FilterDev& fd, const double x[NX], const double* __restrict__ y) {
   const int ny = fd.n_y;
@@ -114,7 +150,7 @@ __device__ __forceinline__ double log_weight(const FilterDev& fd, const double x
 #pragma unroll
     for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[d], x[d], g);
     double dd = __dsub_rn(g, y[0]);
-    return __ddiv_rn(__ddiv_rn(-__dmul_rn(dd, dd), 2.0), fd.R[0]);  // :194  -(d)^2 / 2 / R
+    return __ddiv_rn(__dmul_rn(-__dmul_rn(dd, dd), 0.5), fd.R[0]);  // :194  -(d)^2 / 2 / R  (x/2 == x*0.5 exactly)
   }
   double r[4];
   for (int o = 0; o < ny; ++o) {
@@ -130,7 +166,7 @@ __device__ __forceinline__ double log_weight(const FilterDev& fd, const double x
     r[o] = __ddiv_rn(acc, fd.Rchol[o + ny * o]);
     s = __fma_rn(r[o], r[o], s);
   }
-  return __ddiv_rn(-s, 2.0);
+  return __dmul_rn(-s, 0.5);
 }
 
 // standard normals for output slot j (all NX dims): dims (2p, 2p+1) come from Philox block j*NP + p

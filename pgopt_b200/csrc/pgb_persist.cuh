@@ -325,6 +325,64 @@ __device__ __forceinline__ void emit_offspring(const FilterDev& fd, const EmitCt
   if (!(lw == lw)) atomicOr(stat, 4);
 }
 
+// Four output slots at once (independent Philox / Box-Muller / log-weight chains interleaved).  Same values as
+// emit_offspring for every slot.
+template <int NX>
+__device__ __forceinline__ void emit_offspring4(const FilterDev& fd, const EmitCtx<NX>& ec, int chain, int64_t t,
+                                                const int64_t (&jj)[4], const int32_t (&a0)[4], const bool (&act)[4],
+                                                const double (&F)[4][NX], int* stat, double& lmax) {
+  constexpr int NP = (NX + 1) / 2;
+  const int64_t N = fd.N;
+  double z[4][2 * NP];
+  if (fd.philox) {
+    pgb_u32x4 ctr[4 * NP];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        ctr[k * NP + p].v[0] = (uint32_t)(jj[k] * NP + p);
+        ctr[k * NP + p].v[1] = (uint32_t)t;
+        ctr[k * NP + p].v[2] = fd.sweep;
+        ctr[k * NP + p].v[3] = ((uint32_t)PGB_STREAM_Z << 24) | ((fd.chain_base + chain) & 0x00ffffffu);
+      }
+    vphilox<4 * NP>(ctr, (uint32_t)fd.seed, (uint32_t)(fd.seed >> 32));
+    double z0[4 * NP], z1[4 * NP];
+    vnormal_pairs<4 * NP>(ctr, z0, z1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        z[k][2 * p] = z0[k * NP + p];
+        z[k][2 * p + 1] = z1[k * NP + p];
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int d = 0; d < NX; ++d) z[k][d] = act[k] ? ec.zin[jj[k] * NX + d] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double x[NX];
+#pragma unroll
+    for (int d = 0; d < NX; ++d) {
+      double acc = 0.0;
+#pragma unroll
+      for (int e = 0; e <= d; ++e) acc = __fma_rn(ec.Lq[d + NX * e], z[k][e], acc);
+      x[d] = __dadd_rn(F[k][d], acc);
+    }
+    double lw = log_weight<NX>(fd, x, ec.yt);
+    if (act[k]) {
+      ec.at[jj[k]] = a0[k];
+#pragma unroll
+      for (int d = 0; d < NX; ++d) ec.xt[(int64_t)d * N + jj[k]] = x[d];
+      ec.lwb[jj[k]] = lw;
+      lmax = fmax(lmax, lw);
+      if (!(lw == lw)) atomicOr(stat, 4);
+    }
+  }
+}
+
 // Consumer for one tile (same arithmetic as k_expand).  heavy != nullptr: particles with more than
 // P_HEAVY offspring are deferred to the chain-wide cooperative list instead of being expanded by one thread.
 template <int NX, int MODE>
@@ -488,14 +546,24 @@ __device__ __forceinline__ void p_consume_by_output(const FilterDev& fd, const E
       for (int64_t j = lo + 1; j <= hi; ++j) sh.s_anc[j - cs - 1] = (j <= zu) ? 0 : (int)(base + i) + 1;
     }
     __syncthreads();
-    for (int o = tid; o < (int)(ce - cs); o += TPB) {
-      const int v = sh.s_anc[o];
-      if (v < 0) continue;
-      const int64_t n = (v == 0) ? 0 : (int64_t)v - 1;
-      double F[NX];
+    const int cnt = (int)(ce - cs);
+    for (int o0 = 0; o0 < cnt; o0 += 4 * TPB) {
+      int64_t jj[4];
+      int32_t a0[4];
+      bool act[4];
+      double F[4][NX];
 #pragma unroll
-      for (int d = 0; d < NX; ++d) F[d] = ec.Fb[(int64_t)d * N + n];
-      emit_offspring<NX>(fd, ec, chain, t, cs + o, (v == 0) ? -1 : (int32_t)n, F, stat, lmax);
+      for (int k = 0; k < 4; ++k) {
+        const int o = o0 + k * TPB + tid;
+        const int v = (o < cnt) ? sh.s_anc[o] : -1;
+        act[k] = v >= 0;
+        const int64_t n = (v <= 0) ? 0 : (int64_t)v - 1;
+        a0[k] = (v == 0) ? -1 : (int32_t)n;
+        jj[k] = cs + o;
+#pragma unroll
+        for (int d = 0; d < NX; ++d) F[k][d] = act[k] ? ec.Fb[(int64_t)d * N + n] : 0.0;
+      }
+      if (act[0] | act[1] | act[2] | act[3]) emit_offspring4<NX>(fd, ec, chain, t, jj, a0, act, F, stat, lmax);
     }
     __syncthreads();
   }
@@ -612,14 +680,14 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
     for (int k = 0; k < tpc; ++k) {
       const int tile = c * tpc + k;
       int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
-      double v[4];
+      double a[4], v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = (tile < nt && base + i < N) ? __dsub_rn(lw[base + i], m) : 0.0;
+      vexp<4>(a, v);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        v[i] = 0.0;
-        if (tile < nt && base + i < N) {
-          v[i] = pgb_exp(__dsub_rn(lw[base + i], m));
-          e[base + i] = v[i];
-        }
+        if (tile < nt && base + i < N) e[base + i] = v[i];
+        else v[i] = 0.0;
       }
       acc.push(block_tree_sum(tree4(v), sh.sm));
     }
@@ -665,37 +733,51 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
         const int tile = c * tpc + k;
         int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
         double wv[4], av[4];
+        bool live[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           int64_t n = base + i;
-          wv[i] = 0.0;
+          live[i] = (tile < nt && n < N);
+          wv[i] = live[i] ? __ddiv_rn(e[n], S1) : 0.0;
           av[i] = 0.0;
-          if (tile < nt && n < N) {
-            double wi = __ddiv_rn(e[n], S1);
-            wv[i] = wi;
-            w[n] = wi;
-            if (wh) wh[n] = wi;
-            if (!last_only) {
-              double x[NX], F[NX];
+          if (live[i]) {
+            w[n] = wv[i];
+            if (wh) wh[n] = wv[i];
+          }
+        }
+        if (!last_only) {
+          double x[4][NX], F[4][NX];
 #pragma unroll
-              for (int d = 0; d < NX; ++d) x[d] = xp[(int64_t)d * N + n];
-              eval_F<NX>(fd, A_sm, x, up, F);
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-              for (int d = 0; d < NX; ++d) Fb[(int64_t)d * N + n] = F[d];
-              if (anc) {
-                double r[NX], sq = 0.0;
+            for (int d = 0; d < NX; ++d) x[i][d] = live[i] ? xp[(int64_t)d * N + base + i] : 0.0;
+          eval_F4<NX>(fd, A_sm, x, up, F);
 #pragma unroll
-                for (int d = 0; d < NX; ++d) {
-                  double acc = __dsub_rn(F[d], xref[d]);
+          for (int i = 0; i < 4; ++i)
+            if (live[i]) {
 #pragma unroll
-                  for (int e2 = 0; e2 < d; ++e2) acc = __fma_rn(-Lq[d + NX * e2], r[e2], acc);
-                  r[d] = __ddiv_rn(acc, Lq[d + NX * d]);
-                  sq = __fma_rn(r[d], r[d], sq);
-                }
-                double a = __dmul_rn(wi, pgb_exp(__dsub_rn(c0, __ddiv_rn(sq, 2.0))));
-                av[i] = a;
-                wa[n] = a;
+              for (int d = 0; d < NX; ++d) Fb[(int64_t)d * N + base + i] = F[i][d];
+            }
+          if (anc) {
+            double ea[4], pv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              double r[NX], sq = 0.0;
+#pragma unroll
+              for (int d = 0; d < NX; ++d) {
+                double acc = __dsub_rn(F[i][d], xref[d]);
+#pragma unroll
+                for (int e2 = 0; e2 < d; ++e2) acc = __fma_rn(-Lq[d + NX * e2], r[e2], acc);
+                r[d] = __ddiv_rn(acc, Lq[d + NX * d]);
+                sq = __fma_rn(r[d], r[d], sq);
               }
+              ea[i] = __dsub_rn(c0, __dmul_rn(sq, 0.5));
+            }
+            vexp<4>(ea, pv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              av[i] = live[i] ? __dmul_rn(wv[i], pv[i]) : 0.0;
+              if (live[i]) wa[base + i] = av[i];
             }
           }
         }

@@ -38,6 +38,32 @@ def test_device_philox_normals_bit_identical():
     assert np.array_equal(y.view(np.uint64), O.normal_pairs(1234, 2, 0, 1, 5, n).view(np.uint64))
 
 
+@pytest.mark.parametrize("fn,name", [(10, "exp"), (11, "log"), (12, "sin"), (13, "cos")])
+def test_vector_math_is_bit_identical_to_scalar(fn, name):
+    """pgb_vmath.cuh (4-wide, branch-free, used in the persistent kernel) == pgb_math.h on the host."""
+    rng = np.random.default_rng(fn)
+    if fn == 10:
+        x = np.concatenate([rng.uniform(-750, 712, 300001), rng.uniform(-40, 1, 200000),
+                            [0.0, -0.0, 709.78, 709.79, 710.5, -745.1, -745.2, -746.0, -746.1, -1e300, 1e300, np.nan, np.inf, -np.inf]])
+    elif fn == 11:
+        x = np.concatenate([rng.uniform(0, 1, 300000), 10.0 ** rng.uniform(-300, 300, 100003), [2.0 ** -54, 1.0, 2.0 ** -1022]])
+    else:
+        x = np.concatenate([rng.uniform(-7, 7, 300001), rng.uniform(-1e5, 1e5, 200000), [0.0, -0.0, 1e14, 2e15, np.inf, np.nan]])
+    y = np.empty_like(x)
+    _lib.check(_lib.lib().pgb_test_math(0, fn, _p(x), _p(y), C.c_int64(x.size)))
+    ref = O.vfun(name, x)
+    same = (y.view(np.uint64) == ref.view(np.uint64)) | (np.isnan(y) & np.isnan(ref))
+    assert same.all(), "%d differ, first x=%r: %r vs %r" % ((~same).sum(), x[~same][0], y[~same][0], ref[~same][0])
+
+
+def test_vector_philox_normals_bit_identical():
+    n = 100003
+    y = np.empty(2 * n)
+    x = np.array([987654321.0])
+    _lib.check(_lib.lib().pgb_test_math(0, 14, _p(x), _p(y), C.c_int64(n)))
+    assert np.array_equal(y.view(np.uint64), O.normal_pairs(987654321, 2, 0, 1, 5, n).view(np.uint64))
+
+
 # ------------------------------------------------------------------------------------------ resampling
 def _weights(kind, N, rng):
     if kind == 0:
