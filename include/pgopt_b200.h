@@ -166,8 +166,8 @@ int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, co
                 uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e, double* X, double* Y);
 
 /* ---- test hooks (not part of the drop-in surface) ---------------------------------------------
- * pgb_test_force_fallback(1) makes every exact scan take the serial-walk fallback path (results must
- * not change); pgb_test_math evaluates the device build of pgb_math.h: fn 0 exp, 1 log, 2 sin, 3 cos,
+ * pgb_test_force_fallback(1) makes every exact scan take the serial-walk fallback path, (2) makes the ancestor
+ * draw use the exact scan instead of the certified approximate shortcut (results must not change); pgb_test_math evaluates the device build of pgb_math.h: fn 0 exp, 1 log, 2 sin, 3 cos,
  * 4 Box-Muller pairs from Philox (x[0] = seed, y gets 2n normals of purpose Z, sweep 1, t 5);
  * 10..14: the same through the 4-wide branch-free versions of pgb_vmath.cuh (11: positive normal arguments). */
 void pgb_test_force_fallback(int32_t on);

@@ -293,6 +293,7 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
     CKC(dalloc(h, &pd.heavy, (size_t)nc * P_HEAVY_MAX));
     CKC(dalloc(h, &pd.heavy_cnt, (size_t)nc));
     CKC(dalloc(h, &pd.prof, (size_t)1024 * P_NPROF));
+    CKC(dalloc(h, &pd.cand, (size_t)2 * nc));
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
     h->num_sms = prop.multiProcessorCount;
@@ -479,7 +480,7 @@ static void launch_scan(pgb_handle* h, const ScanWS& ws, const double* v, const 
   cudaStream_t s = h->stream;
   dim3 gt(ws.nt, fd.nc), g1(1, fd.nc);
   LAUNCH(h, PGB_PROF_SCAN_LOCAL, (k_scan_local<<<gt, TPB, 0, s>>>(ws, v, fd.status)));
-  LAUNCH(h, PGB_PROF_RESOLVE, (k_resolve<<<g1, TPB, 0, s>>>(ws, g_force_fallback)));
+  LAUNCH(h, PGB_PROF_RESOLVE, (k_resolve<<<g1, TPB, 0, s>>>(ws, g_force_fallback & 1)));
   LAUNCH(h, PGB_PROF_EXPAND, (k_expand<NX, MODE><<<gt, TPB, 0, s>>>(fd, ws, v, utab, utab_stride, utab_index, out_idx,
                                                                     out_stride, t, first, 0)));
   LAUNCH(h, PGB_PROF_SEQ, (k_seq_exact<<<g1, 32, 0, s>>>(ws, v, fd.status, maxkey_reset)));
@@ -560,6 +561,7 @@ static int run_filter_persistent_nx(pgb_handle* h) {
   CK(h, cudaMemsetAsync(fd.maxkey, 0, (size_t)nc * 8, s));
   CK(h, cudaMemsetAsync(pd.bar, 0, 4, s));
   CK(h, cudaMemsetAsync(pd.heavy_cnt, 0, (size_t)nc * 4, s));
+  CK(h, cudaMemsetAsync(pd.cand, 0, (size_t)2 * nc * 4, s));
   CK(h, cudaMemsetAsync(fd.main.flag, 0, (size_t)2 * nc * 4, s));
   CK(h, cudaMemsetAsync(fd.side.flag, 0, (size_t)2 * nc * 4, s));
   LAUNCH(h, PGB_PROF_INIT, (k_build_utabs<<<dim3((unsigned)((T + 127) / 128), nc), 128, 0, s>>>(fd, first)));
@@ -1012,7 +1014,7 @@ extern "C" int pgb_get_launch_count(pgb_handle* h, int64_t* n) {
 // ------------------------------------------------------------------------------------------------
 // test hooks
 // ------------------------------------------------------------------------------------------------
-extern "C" void pgb_test_force_fallback(int32_t on) { g_force_fallback = on ? 1 : 0; }
+extern "C" void pgb_test_force_fallback(int32_t on) { g_force_fallback = on; }
 
 __global__ void k_test_math(int fn, const double* __restrict__ x, double* __restrict__ y, int64_t n, uint64_t seed) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -45,6 +45,7 @@ struct PersistDev {
   struct HeavyEnt* heavy;   // [nc][P_HEAVY_MAX]
   int* heavy_cnt;           // [nc]
   long long* prof;          // [grid][P_NPROF] per-CTA cycle counts per section (thread 0), or null
+  int* cand;                // [nc][2] ancestor draw: {number of certain hits, index} (approximate-scan shortcut)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -176,6 +177,42 @@ __device__ __forceinline__ void p_scan_local(const ScanWS& ws, const double* v, 
     praw = pnext_raw;
   }
   if (tid == 0) ws.tile_agg[(int64_t)chain * ws.nt + c] = carry;  // CTA aggregate (slot c of tile_agg)
+}
+
+// Ancestor index of the conditioned trajectory (particle_Gibbs.jl:181) without the exact machinery: the draw is a
+// single comparison q_{n-1} < u <= q_n, so an ordinary (approximate) scan decides it whenever u is farther than a
+// rigorous error bound `delta` from both neighbouring prefixes: |q~_n - q_n(sequential)| <= delta implies that an
+// element with q~_{n-1} + delta < u <= q~_n - delta IS the sequential answer (q is monotone, the answer unique).
+// delta bounds both the sequential rounding error (< n 2^-53 sum) and that of the blocked scan.  No certain
+// element (probability ~ 2 delta / W ~ 1e-3 per step) -> the caller runs the exact scan for this step.
+__device__ __forceinline__ void p_side_approx(const ScanWS& ws, const double* v, double S, const double* tsum_sm,
+                                              int chain, int c, int tpc, PersistShared& sh, double u, double delta,
+                                              int* cand) {
+  const int tid = threadIdx.x;
+  const int64_t N = ws.N;
+  const double* vc = v + (int64_t)chain * N;
+  double praw = sh.pfx[c];
+  for (int k = 0; k < tpc; ++k) {
+    const int tile = c * tpc + k;
+    if (tile >= ws.nt) break;
+    int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
+    double W[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) W[i] = (base + i < N) ? __ddiv_rn(vc[base + i], S) : 0.0;
+    double s1 = W[0], s2 = __dadd_rn(s1, W[1]), s3 = __dadd_rn(s2, W[2]), s4 = __dadd_rn(s3, W[3]);
+    double tot;
+    double ex = block_excl_scan_approx(s4, sh.sm, &tot);
+    double P = __dadd_rn(__ddiv_rn(praw, S), ex);
+    double qt[5] = {P, __dadd_rn(P, s1), __dadd_rn(P, s2), __dadd_rn(P, s3), __dadd_rn(P, s4)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (base + i < N && (qt[i] + delta < u) && (u <= qt[i + 1] - delta)) {
+        atomicAdd(&cand[0], 1);
+        cand[1] = (int)(base + i);
+      }
+    }
+    praw = __dadd_rn(praw, tsum_sm[k]);
+  }
 }
 
 // Resolve (every CTA redundantly): exclusive scan of CTA aggregates, gather records, serial chain.
@@ -709,6 +746,7 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
       if (c == 0 && tid == 0) {
         fd.maxkey[chain] = 0ull;  // its readers finished before the last barrier
         pd.heavy_cnt[chain] = 0;
+        pd.cand[2 * chain] = 0;
       }
       const double* e = fd.ebuf + (int64_t)chain * N;
       double* w = fd.wbuf + (int64_t)chain * N;
@@ -829,7 +867,7 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
     P_TICK(5);
     // ================================================================ phase C: main resolve + consume, side scan-local
     {
-      p_resolve(fd.main, chain, nb, tpc, sh, pd.force_fallback, fmain);
+      p_resolve(fd.main, chain, nb, tpc, sh, pd.force_fallback & 1, fmain);
       P_TICK(6);
       if (tid == 0) {
         sh.sI = *fmain & 1;
@@ -864,7 +902,9 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
       if (anc) {
         const double S4 = block_tree_sum_array(pa2, nb, sh.sm);
         approx_prefix(pa2, nb, sh);
-        p_scan_local(fd.side, fd.waN, S4, sh.tsum_a2, chain, c, nb, tpc, sh, fd.status, fside);
+        const double ua = fd.utab_anc[(int64_t)chain * T + t].u0[0];  // one draw: u = rand()
+        const double delta = 6.0 * ((double)N + 4096.0) * 0x1p-53;
+        p_side_approx(fd.side, fd.waN, S4, sh.tsum_a2, chain, c, tpc, sh, ua, delta, pd.cand + 2 * chain);
       }
       P_TICK(8);
     }
@@ -873,23 +913,41 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
     // ================================================================ phase D: side resolve + find, weights (optimistic)
     {
       if (anc) {
-        const double S4 = block_tree_sum_array(pa2, nb, sh.sm);
-        p_resolve(fd.side, chain, nb, tpc, sh, pd.force_fallback, fside);
+        // approximate shortcut decided?  (uniform over the grid: every CTA reads every chain's counter)
         if (tid == 0) {
-          sh.sI = *fside & 1;
-          if (c == 0) fd.side.counters[2 * chain + 1] += 1;
+          int amb = 0;
+          for (int ch = 0; ch < fd.nc; ++ch) amb |= (pd.cand[2 * ch] == 0) || pd.force_fallback;
+          sh.any_flag = amb;
         }
         __syncthreads();
-        const bool skip = sh.sI != 0;
-        double dummy = 0.0;
-        const pgb_utable* ut = &fd.utab_anc[(int64_t)chain * T + t];
-        int32_t* out = fd.ah + ((int64_t)chain * T + t) * N + (N - 1);
-        for (int k = 0; k < tpc && !skip; ++k) {
-          const int tile = c * tpc + k;
-          if (tile >= nt) break;
-          double W[4], q[5];
-          if (!p_exact_prefixes(fd.side, fd.waN, S4, chain, c, k, nb, tpc, false, sh, W, q, fside)) continue;
-          p_consume<NX, MODE_INDEX>(fd, chain, tile, q, ut, out, t, first, &fd.side.pend[chain], dummy, nullptr, nullptr);
+        const bool amb_any = sh.any_flag != 0;
+        const bool amb_me = (pd.cand[2 * chain] == 0) || pd.force_fallback;
+        if (!amb_me && c == 0 && tid == 0) fd.ah[((int64_t)chain * T + t) * N + (N - 1)] = pd.cand[2 * chain + 1];
+        if (amb_any) {
+          // rare: run the exact scan of the ancestor weights for the chains that need it (two extra barriers)
+          const double S4 = block_tree_sum_array(pa2, nb, sh.sm);
+          approx_prefix(pa2, nb, sh);
+          if (amb_me) p_scan_local(fd.side, fd.waN, S4, sh.tsum_a2, chain, c, nb, tpc, sh, fd.status, fside);
+          grid_barrier(pd.bar, bar_target);
+          if (amb_me) {
+            p_resolve(fd.side, chain, nb, tpc, sh, pd.force_fallback & 1, fside);
+            if (tid == 0) {
+              sh.sI = *fside & 1;
+              if (c == 0) fd.side.counters[2 * chain + 1] += 1;
+            }
+            __syncthreads();
+            const bool skip = sh.sI != 0;
+            double dummy = 0.0;
+            const pgb_utable* ut = &fd.utab_anc[(int64_t)chain * T + t];
+            int32_t* out = fd.ah + ((int64_t)chain * T + t) * N + (N - 1);
+            for (int k = 0; k < tpc && !skip; ++k) {
+              const int tile = c * tpc + k;
+              if (tile >= nt) break;
+              double W[4], q[5];
+              if (!p_exact_prefixes(fd.side, fd.waN, S4, chain, c, k, nb, tpc, false, sh, W, q, fside)) continue;
+              p_consume<NX, MODE_INDEX>(fd, chain, tile, q, ut, out, t, first, &fd.side.pend[chain], dummy, nullptr, nullptr);
+            }
+          }
         }
       }
       P_TICK(10);

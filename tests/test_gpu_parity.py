@@ -206,7 +206,10 @@ def test_sweep_bit_exact_injected_streams(model, first, N, T, persistent):
     _assert_same("Sigma", Sig, ref["Sigma"])
     _assert_same("w_m1", smp.w_m1, ref["w_last"])
     _assert_same("x_m1", smp.x_m1.T, ref["x_last"])
-    assert stat == ref["status"] == 0 and nfb == 0 and nscan == (T if first else 2 * T - 1)
+    assert stat == ref["status"] == 0 and nfb == 0
+    # T main scans (+1 star draw counted in them); the ancestor draw only needs the exact scan when the certified
+    # approximate shortcut is undecided (persistent mode), always in the multi-kernel mode
+    assert (T <= nscan <= 2 * T - 1) if (persistent and not first) else nscan == (T if first else 2 * T - 1)
 
 
 @pytest.mark.parametrize("persistent", [True, False])
@@ -256,6 +259,35 @@ def test_sweep_with_underflowing_ancestor_weights(persistent):
     _assert_same("ancestors", a[1:], ref["a"][1:])
     _assert_same("x_pf", x, ref["x"])
     _assert_same("w", w, ref["w"])
+
+
+@pytest.mark.parametrize("model", ["known", "hilbert"])
+@pytest.mark.parametrize("N,T", [(30, 100), (3000, 20)])
+def test_ancestor_draw_shortcut_equals_exact_scan(model, N, T):
+    """Persistent mode decides the ancestor index of the conditioned trajectory from an approximate scan with a
+    rigorous error bound; forcing the exact scan instead (test hook 2) must give the same history."""
+    basis, om, A = _models()[model]
+    u, y, _ = P.make_data(T, 16)
+    s = P.injected_streams(N, T, 2, basis.n_phi, 24)
+    st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
+    xp = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, np.zeros((2, T)), True, st, 1)["x_prim"]
+    ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, False, st, 2)
+    hist = []
+    for force in (0, 2):
+        _lib.lib().pgb_test_force_fallback(force)
+        try:
+            with _engine(basis, N, T, u, y, persistent=True) as e:
+                e.set_state(A, P.Q_TRUE, xp, 2)
+                e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+                e.sweep_filter()
+                a, x, w = e.get_history()
+                stat, nfb, nscan = e.status()
+        finally:
+            _lib.lib().pgb_test_force_fallback(0)
+        _assert_same("ancestors (force=%d)" % force, a[1:], ref["a"][1:])
+        assert nfb == 0 and stat == 0
+        hist.append(nscan)
+    assert hist[1] == 2 * T - 1 and hist[0] < hist[1]  # the shortcut really skipped exact scans
 
 
 @pytest.mark.parametrize("persistent", [True, False])
