@@ -131,8 +131,9 @@ int pgb_synchronize(pgb_handle* h);
  * pgb_get_launch_count returns the number of kernels this handle has launched so far. */
 enum { PGB_PROF_PREP = 0, PGB_PROF_NORM, PGB_PROF_SCAN_LOCAL, PGB_PROF_RESOLVE, PGB_PROF_EXPAND, PGB_PROF_SEQ,
        PGB_PROF_EXPAND_FB, PGB_PROF_WEIGHTS, PGB_PROF_INIT, PGB_PROF_TAIL, PGB_PROF_MNIW, PGB_PROF_NCLASS };
-/* persistent != 0 (default): the whole T loop of a sweep is one cooperative persistent kernel; 0: one
- * launch per phase (13 launches per time step; kept for per-kernel profiling and as a cross-check). */
+/* 2 (default): the whole T loop of a sweep is one cooperative persistent kernel in the warp-tile formulation;
+ * 1: the same with 1024-particle CTA tiles; 0: one launch per phase (13 launches per time step).  The two
+ * alternatives are kept for profiling and as cross-checks; all three are bit-identical. */
 int pgb_set_mode(pgb_handle* h, int32_t persistent);
 /* average over CTAs of the SM-clock cycles thread 0 spent in each section of the last persistent sweep
  * (section ids documented in pgb_persist.cuh: 1 phase A, 2 wait B1, 3 scan-local main, 4 normalise side, 5 wait B2,
@@ -174,6 +175,8 @@ void pgb_test_force_fallback(int32_t on);
 int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_t n);
 /* DFMA micro-benchmark (8 independent chains per thread, all SMs): measured FP64 FMA rate of the device. */
 int pgb_test_fp64_peak(int32_t device, double* tflops);
+/* one elementwise phase in isolation inside a persistent loop with grid barriers (0: exp + tree sums, 1: copy, 2: divide) */
+int pgb_test_microbench(int32_t device, int32_t variant, int64_t N, int32_t iters, double* us_per_iter);
 
 #ifdef __cplusplus
 }

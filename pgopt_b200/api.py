@@ -171,8 +171,10 @@ class ParticleGibbsEngine:
     def _ck(self, rc):
         check(rc, self._h)
 
-    def set_mode(self, persistent=True):
-        self._ck(lib().pgb_set_mode(self._h, C.c_int32(int(persistent))))
+    def set_mode(self, persistent=2):
+        """2 (default, also True... see below): warp-tile persistent kernel; 1: tile persistent kernel; 0/False: multi-kernel"""
+        mode = 2 if persistent is True else int(persistent)
+        self._ck(lib().pgb_set_mode(self._h, C.c_int32(mode)))
 
     def set_data(self, u, y):
         u, y = _f(np.atleast_2d(u)), _f(np.atleast_2d(y))

@@ -15,6 +15,7 @@
 #include "pgb_mniw.cuh"
 #include "pgb_rollout.cuh"
 #include "pgb_persist.cuh"
+#include "pgb_persist_w.cuh"
 
 using namespace pgb;
 
@@ -44,7 +45,7 @@ struct pgb_handle {
   double *d_A_used = nullptr, *d_Q_used = nullptr;
   bool injected_ready = false;
   // persistent (single cooperative kernel) filter path
-  bool persistent = true;
+  int persistent = 1;  // 1: tile persistent kernel (default, fastest measured), 2: warp-tile persistent kernel, 0: one launch per phase
   PersistDev pd;
   int num_sms = 0;
   // measurement
@@ -297,8 +298,10 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
     h->num_sms = prop.multiProcessorCount;
+    const char* abl = getenv("PGB_ABLATE");
+    fd.ablate = abl ? atoi(abl) : 0;
     const char* env = getenv("PGB_PERSISTENT");
-    if (env && env[0] == '0') h->persistent = false;
+    if (env && env[0] >= '0' && env[0] <= '2') h->persistent = env[0] - '0';
   }
   h->have_state.assign(nc, 0);
   h->h_u.assign((size_t)nu * T, 0.0);
@@ -531,24 +534,26 @@ static int run_filter_nx(pgb_handle* h) {
 // One cooperative launch for the whole time loop.  Returns -1 when the configuration does not fit
 // (too many chains / tiles for the co-resident grid); the caller then uses the multi-kernel path.
 template <int NX>
-static int run_filter_persistent_nx(pgb_handle* h) {
+static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
   FilterDev& fd = h->fd;
   MniwDev& md = h->md;
   PersistDev& pd = h->pd;
   cudaStream_t s = h->stream;
   const int64_t T = fd.T;
   const int nc = fd.nc;
-  const size_t smA = sizeof(PersistShared) + (size_t)NX * fd.n_phi * 8;
+  const size_t smA = (warp_tiles ? sizeof(WShared) : sizeof(PersistShared)) + (size_t)NX * fd.n_phi * 8;
+  const void* kfn = warp_tiles ? (const void*)k_sweep_w<NX> : (const void*)k_sweep_persistent<NX>;
   int occ = 0;
-  CK(h, cudaFuncSetAttribute(k_sweep_persistent<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
-  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_persistent<NX>, TPB, smA));
+  CK(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
+  if (warp_tiles) CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_w<NX>, TPB, smA));
+  else CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_persistent<NX>, TPB, smA));
   const int max_ctas = occ * h->num_sms;
   int nbmax = max_ctas / nc;
   if (nbmax > P_MAXNB) nbmax = P_MAXNB;
   if (nbmax < 1) return -1;
   int tpc = 1;
   while ((fd.nt + tpc - 1) / tpc > nbmax) tpc *= 2;
-  if (tpc > P_MAXTPC) return -1;
+  if (tpc > (warp_tiles ? W_MAXTPC : P_MAXTPC)) return -1;
   pd.tpc = tpc;
   pd.nb = (fd.nt + tpc - 1) / tpc;
   pd.force_fallback = g_force_fallback;
@@ -568,8 +573,7 @@ static int run_filter_persistent_nx(pgb_handle* h) {
   {
     LaunchScope ls(h, PGB_PROF_EXPAND);
     void* args[] = {(void*)&fd, (void*)&pd, (void*)&first};
-    CK(h, cudaLaunchCooperativeKernel((const void*)k_sweep_persistent<NX>, dim3((unsigned)(nc * pd.nb)), dim3(TPB), args,
-                                      smA, s));
+    CK(h, cudaLaunchCooperativeKernel(kfn, dim3((unsigned)(nc * pd.nb)), dim3(TPB), args, smA, s));
   }
   LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
   LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
@@ -580,13 +584,14 @@ static int run_filter_persistent_nx(pgb_handle* h) {
 }
 
 static int run_filter(pgb_handle* h) {
-  if (h->persistent) {
+  for (int mode = h->persistent; mode >= 1; --mode) {  // a configuration that does not fit falls through
     int rc;
+    const bool wt = (mode == 2);
     switch (h->cfg.n_x) {
-      case 1: rc = run_filter_persistent_nx<1>(h); break;
-      case 2: rc = run_filter_persistent_nx<2>(h); break;
-      case 3: rc = run_filter_persistent_nx<3>(h); break;
-      default: rc = run_filter_persistent_nx<4>(h); break;
+      case 1: rc = run_filter_persistent_nx<1>(h, wt); break;
+      case 2: rc = run_filter_persistent_nx<2>(h, wt); break;
+      case 3: rc = run_filter_persistent_nx<3>(h, wt); break;
+      default: rc = run_filter_persistent_nx<4>(h, wt); break;
     }
     if (rc >= 0) return rc;
   }
@@ -968,7 +973,7 @@ extern "C" int pgb_get_phase_cycles(pgb_handle* h, double* avg_cycles /*[16]*/, 
 }
 extern "C" int pgb_set_mode(pgb_handle* h, int32_t persistent) {
   NEED(h);
-  h->persistent = persistent != 0;
+  h->persistent = persistent < 0 ? 0 : (persistent > 2 ? 2 : persistent);
   return PGB_OK;
 }
 extern "C" int pgb_timer_start(pgb_handle* h) {
@@ -1025,6 +1030,40 @@ __global__ void k_test_math(int fn, const double* __restrict__ x, double* __rest
     case 2: y[i] = pgb_sin(x[i]); break;
     case 3: y[i] = pgb_cos(x[i]); break;
     case 4: pgb_normal_pair(pgb_stream_block(seed, PGB_STREAM_Z, 0, 1, 5, (uint32_t)i), &y[2 * i], &y[2 * i + 1]); break;
+    case 20: {  // x holds pairs (a, d): y[i] = 1 if div_inv(a, d) == a / d bitwise (or both NaN)
+      double a = x[2 * i], d = x[2 * i + 1];
+      InvDiv iv = make_invdiv(d);
+      double q = div_inv(a, iv), t = __ddiv_rn(a, d);
+      y[i] = (__double_as_longlong(q) == __double_as_longlong(t) || (q != q && t != t)) ? 1.0 : 0.0;
+      break;
+    }
+    case 21: {  // self-generated operands: x[i] is a seed; 4096 pairs per thread; y[i] = number of mismatches
+      uint64_t st = (uint64_t)x[i] * 0x9E3779B97F4A7C15ull + 0x1234567ull + (uint64_t)i;
+      int bad = 0;
+      for (int k = 0; k < 4096; ++k) {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        uint64_t ma = st;
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        uint64_t md = st;
+        // mantissas: random, or special patterns (all ones, few bits) ; exponents within the fast range
+        if ((k & 7) == 1) md |= 0x000fffffffffff00ull;
+        if ((k & 7) == 2) md &= 0xfff00000000000ffull;
+        if ((k & 7) == 3) ma |= 0x000ffffffffffff0ull;
+        int ea = 1023 + (int)((ma >> 52) % 600) - 300, ed = 1023 + (int)((md >> 52) % 600) - 300;
+        double a = __longlong_as_double((long long)((ma & 0x000fffffffffffffull) | ((uint64_t)ea << 52)));
+        double d = __longlong_as_double((long long)((md & 0x000fffffffffffffull) | ((uint64_t)ed << 52)));
+        if ((k & 7) == 4) {  // numerators next to exact multiples of d (rounding boundary cases)
+          double qq = __longlong_as_double((long long)((ma & 0x000fffffffffffffull) | (1023ull << 52)));
+          a = __dmul_rn(qq, d);
+          a = __longlong_as_double(__double_as_longlong(a) + (long long)(k % 3) - 1);
+        }
+        InvDiv iv = make_invdiv(d);
+        double q = div_inv(a, iv), t = __ddiv_rn(a, d);
+        if (__double_as_longlong(q) != __double_as_longlong(t)) ++bad;
+      }
+      y[i] = (double)bad;
+      break;
+    }
     default: break;
   }
 }
@@ -1035,17 +1074,17 @@ __global__ void k_test_vmath(int fn, const double* __restrict__ x, double* __res
   if (i4 >= n) return;
   double a[4], b[4], c[4];
   for (int k = 0; k < 4; ++k) a[k] = (fn != 14 && i4 + k < n) ? x[i4 + k] : 1.0;
-  if (fn == 10) vexp<4>(a, b);
-  else if (fn == 11) vlog_pos_normal<4>(a, b);
-  else if (fn == 12) vsincos<4>(a, b, c);
-  else if (fn == 13) vsincos<4>(a, c, b);
+  if (fn == 10) vexp_wide<4>(a, b);
+  else if (fn == 11) vlog_pos_normal_wide<4>(a, b);
+  else if (fn == 12) vsincos_wide<4>(a, b, c);
+  else if (fn == 13) vsincos_wide<4>(a, c, b);
   else {
     pgb_u32x4 ctr[4];
     for (int k = 0; k < 4; ++k) {
       ctr[k].v[0] = (uint32_t)(i4 + k); ctr[k].v[1] = 5; ctr[k].v[2] = 1; ctr[k].v[3] = ((uint32_t)PGB_STREAM_Z << 24);
     }
-    vphilox<4>(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
-    vnormal_pairs<4>(ctr, b, c);
+    vphilox_wide<4>(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    vnormal_pairs_wide<4>(ctr, b, c);
     for (int k = 0; k < 4; ++k)
       if (i4 + k < n) { y[2 * (i4 + k)] = b[k]; y[2 * (i4 + k) + 1] = c[k]; }
     return;
@@ -1068,13 +1107,13 @@ extern "C" int pgb_test_math(int32_t device, int32_t fn, const double* x, double
   CK(h, cudaSetDevice(device));
   const bool pairs = (fn == 4 || fn == 14);
   const int64_t nout = pairs ? 2 * n : n;
-  const int64_t nin = pairs ? 1 : n;
+  const int64_t nin = pairs ? 1 : (fn == 20 ? 2 * n : n);
   double *dx, *dy;
   CK(h, dalloc(h, &dx, (size_t)nin));
   CK(h, dalloc(h, &dy, (size_t)nout));
   CK(h, cudaMemcpy(dx, x, (size_t)nin * 8, cudaMemcpyHostToDevice));
   uint64_t seed = pairs ? (uint64_t)x[0] : 0;
-  if (fn >= 10) k_test_vmath<<<(unsigned)((n + 1023) / 1024), 256>>>(fn, dx, dy, n, seed);
+  if (fn >= 10 && fn < 20) k_test_vmath<<<(unsigned)((n + 1023) / 1024), 256>>>(fn, dx, dy, n, seed);
   else k_test_math<<<(unsigned)((n + 255) / 256), 256>>>(fn, dx, dy, n, seed);
   CK(h, cudaGetLastError());
   CK(h, cudaDeviceSynchronize());
@@ -1127,5 +1166,131 @@ extern "C" int pgb_test_fp64_peak(int32_t device, double* tflops) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *tflops = best;
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// micro-benchmark of one elementwise phase in isolation (what a persistent phase can reach):
+// variant 0: y = exp(x - m) with per-CTA tree sums (the weight phase), 1: plain copy, 2: y = x / s
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) k_micro(int variant, const double* __restrict__ x, double* __restrict__ y,
+                                                  double* part, unsigned int* bar, int64_t N, int iters, int tpc) {
+  __shared__ double wpart[8][2];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.x, nwt = 8 * tpc;
+  unsigned int target = 0;
+  for (int it = 0; it < iters; ++it) {
+    TreeAcc acc;
+    acc.init();
+    const double m = 0.25 + 1e-3 * it;
+    for (int j = 0; j < tpc; ++j) {
+      const int64_t base = ((int64_t)c * nwt + w * tpc + j) * 128 + lane * 4;
+      double a[4], v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = (base + i < N) ? x[base + i] : 0.0;
+      if (variant == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = __dsub_rn(a[i], m);
+        vexp<4>(a, v);
+      } else if (variant == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __ddiv_rn(a[i], m);
+      } else if (variant == 3) {  // Philox + Box-Muller for 4 outputs
+        pgb_u32x4 ctr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ctr[i].v[0] = (uint32_t)(base + i); ctr[i].v[1] = it; ctr[i].v[2] = 1; ctr[i].v[3] = 7;
+        }
+        vphilox<4>(ctr, 123u, 456u);
+        double z0[4], z1[4];
+        vnormal_pairs<4>(ctr, z0, z1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __dadd_rn(z0[i], __dadd_rn(z1[i], a[i]));
+      } else if (variant == 4) {  // two sincos per element (known-basis F)
+        double s1[4], c1[4], s2[4], c2[4];
+        vsincos<4>(a, s1, c1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = __dmul_rn(a[i], 2.0);
+        vsincos<4>(a, s2, c2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __dadd_rn(c1[i], s2[i]);
+      } else if (variant == 5) {  // classify + maps + warp segmented scan (scan-local without the division)
+        double s1 = a[0], s2 = __dadd_rn(s1, a[1]), s3 = __dadd_rn(s2, a[2]), s4 = __dadd_rn(s3, a[3]);
+        double inc = s4;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          double t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc = __dadd_rn(t, inc);
+        }
+        double P = __dadd_rn(0.25 + 1e-3 * j, __dsub_rn(inc, s4));
+        double Pn = __shfl_down_sync(0xffffffffu, P, 1);
+        double qt[5] = {P, __dadd_rn(P, s1), __dadd_rn(P, s2), __dadd_rn(P, s3), Pn};
+        pgb_agg agg = pgb_classify4(a, qt);
+        pgb_agg total;
+        pgb_agg ex = warp_excl_scan_agg(agg, &total);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = a[i] + (double)(ex.f.c0 + total.f.c1 + ex.cnt);
+      } else if (variant == 6) {  // sampling-grid counts (5 per thread) on a synthetic table
+        __shared__ pgb_utable ut;
+        if (it == 0 && j == 0) {
+          if (tid == 0) pgb_utable_build(&ut, N - 1, 0.37);
+          __syncthreads();
+        }
+        int row = -1;
+        long long r = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r += pgb_utable_count_le_hint(&ut, __dmul_rn(a[i], 1e-6 * (double)(base + i)), &row);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = a[i] + (double)r;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = a[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (base + i < N) y[base + i] = v[i];
+      acc.push(warp_tree_sum(tree4(v)));
+    }
+    if (lane == 0) wpart[w][0] = acc.result();
+    __syncthreads();
+    if (tid == 0) part[c] = tree8(wpart, 0);
+    grid_barrier(bar, target);
+  }
+}
+
+extern "C" int pgb_test_microbench(int32_t device, int32_t variant, int64_t N, int32_t iters, double* us_per_iter) {
+  pgb_handle tmp;
+  pgb_handle* h = &tmp;
+  struct Cleanup {
+    pgb_handle* h;
+    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
+  } cleanup{h};
+  CK(h, cudaSetDevice(device));
+  double *x, *y, *part;
+  unsigned int* bar;
+  CK(h, dalloc(h, &x, (size_t)N));
+  CK(h, dalloc(h, &y, (size_t)N));
+  CK(h, dalloc(h, &part, 1024));
+  CK(h, dalloc(h, &bar, 4));
+  int tpc = 1;
+  const int nt = (int)((N + 1023) / 1024);
+  while ((nt + tpc - 1) / tpc > 256) tpc *= 2;
+  const int grid = (nt + tpc - 1) / tpc;
+  cudaEvent_t e0, e1;
+  CK(h, cudaEventCreate(&e0));
+  CK(h, cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; ++rep) {
+    CK(h, cudaMemset(bar, 0, 4));
+    void* args[] = {(void*)&variant, (void*)&x, (void*)&y, (void*)&part, (void*)&bar, (void*)&N, (void*)&iters, (void*)&tpc};
+    CK(h, cudaEventRecord(e0));
+    CK(h, cudaLaunchCooperativeKernel((const void*)k_micro, dim3(grid), dim3(256), args, 0, 0));
+    CK(h, cudaEventRecord(e1));
+    CK(h, cudaEventSynchronize(e1));
+  }
+  float ms = 0.f;
+  CK(h, cudaEventElapsedTime(&ms, e0, e1));
+  *us_per_iter = 1e3 * ms / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return PGB_OK;
 }

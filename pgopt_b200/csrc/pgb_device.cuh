@@ -145,6 +145,42 @@ __device__ __forceinline__ pgb_agg block_excl_scan_agg(pgb_agg v, pgb_agg* sm, p
   return pgb_agg_combine(sm[w], ex);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Correctly rounded division by a divisor that is the same for many numerators (weight sums, R,
+// Cholesky diagonal): the reciprocal is computed once with a true division, each quotient then costs
+// one multiply and four fused multiply-adds instead of the ~30-instruction __ddiv_rn sequence.
+//   q0 = RN(a y), r0 = RN(a - d q0), q1 = RN(q0 + r0 y)   -> q1 is a faithful quotient
+//   r1 = a - d q1 (exact), q = RN(q1 + r1 y)              -> correctly rounded (Markstein 1990: y = RN(1/d)
+//                                                            and q1 faithful imply q = RN(a/d))
+// Operands outside a wide safe range (so that no intermediate can under/overflow), zeros, infinities and
+// NaNs take the true division.  tests/test_gpu_parity.py::test_invariant_division_is_correctly_rounded
+// compares against __ddiv_rn bit for bit on random and adversarial operands.
+// ---------------------------------------------------------------------------------------------
+struct InvDiv {
+  double d, y;
+  bool ok;
+};
+__device__ __forceinline__ InvDiv make_invdiv(double d) {
+  InvDiv iv;
+  iv.d = d;
+  iv.y = __ddiv_rn(1.0, d);
+  const double ad = fabs(d);
+  iv.ok = (ad >= 0x1p-500) && (ad <= 0x1p500);
+  return iv;
+}
+__device__ __noinline__ double ddiv_slow(double a, double d) { return __ddiv_rn(a, d); }
+__device__ __forceinline__ double div_inv(double a, const InvDiv& iv) {
+  const double aa = fabs(a);
+  if (iv.ok && aa >= 0x1p-500 && aa <= 0x1p500) {
+    double q0 = __dmul_rn(a, iv.y);
+    double r0 = __fma_rn(-iv.d, q0, a);
+    double q1 = __fma_rn(r0, iv.y, q0);
+    double r1 = __fma_rn(-iv.d, q1, a);
+    return __fma_rn(r1, iv.y, q1);
+  }
+  return ddiv_slow(a, iv.d);
+}
+
 // order-preserving map double -> uint64 (for atomicMax over doubles)
 __device__ __forceinline__ unsigned long long ordered_key(double x) {
   unsigned long long u = (unsigned long long)__double_as_longlong(x);

@@ -161,7 +161,7 @@ PGB_HD int pgb_lower_candidate_key(double q) {
 // aggregate, or the complex marker when any element changes binade / is ambiguous.
 // Elements whose addition is a no-op in every candidate binade (zero or negligible weight)
 // constrain nothing and are skipped.
-PGB_HD pgb_agg pgb_classify4(const double W[4], const double qt[5]) {
+PGB_HD_HELPER pgb_agg pgb_classify4(const double W[4], const double qt[5]) {
   pgb_agg a = pgb_agg_identity();
   for (int i = 0; i < 4; ++i) {
     if (W[i] == 0.0) continue;  // identity in every binade
@@ -284,7 +284,7 @@ PGB_HD int64_t pgb_utable_count_in_row(const pgb_utable* T, int lo, double q) {
   return i0 + j;
 }
 // #{ i in [1, M] : u_i <= q }   (q finite >= 0)
-PGB_HD int64_t pgb_utable_count_le(const pgb_utable* T, double q) {
+PGB_HD_HELPER int64_t pgb_utable_count_le(const pgb_utable* T, double q) {
   if (q != q) return T->M;  // NaN prefix: `while q < u` is false for every draw, all of them stop here
   if (T->nrows == 0 || !(q >= T->u0[0])) return 0;
   int lo = 0, hi = T->nrows - 1;
@@ -295,7 +295,7 @@ PGB_HD int64_t pgb_utable_count_le(const pgb_utable* T, double q) {
   return pgb_utable_count_in_row(T, lo, q);
 }
 // same, for a non-decreasing sequence of queries: *row is the row found for the previous query
-PGB_HD int64_t pgb_utable_count_le_hint(const pgb_utable* T, double q, int* row) {
+PGB_HD_HELPER int64_t pgb_utable_count_le_hint(const pgb_utable* T, double q, int* row) {
   if (q != q) return T->M;
   if (T->nrows == 0 || !(q >= T->u0[0])) return 0;
   int lo = *row;

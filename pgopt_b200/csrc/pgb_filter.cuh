@@ -52,6 +52,7 @@ struct FilterDev {
   const double *Z0, *Z, *Ures, *Uanc, *Ustar;  // injected: [nc][n_x*(N-1)], [nc][T][n_x*N], [nc][T], [nc][T], [nc]
   pgb_utable *utab_res, *utab_anc, *utab_star; // [nc][T], [nc][T], [nc]
   ScanWS main, side;
+  int ablate;  // timing experiments only (env PGB_ABLATE): see pgb_persist.cuh
 };
 
 // ------------------------------------------------------------------------------------------
@@ -140,6 +141,20 @@ __device__ __forceinline__ void eval_F4(const FilterDev& fd, const double* __res
   }
 #pragma unroll 1
   for (int k = 0; k < 4; ++k) eval_F<NX>(fd, A_sm, x[k], u, F[k]);
+}
+
+// same as log_weight below with the division by the scalar R done through a precomputed reciprocal (n_y == 1)
+template <int NX>
+__device__ __forceinline__ double log_weight(const FilterDev& fd, const double x[NX], const double* __restrict__ y);
+template <int NX>
+__device__ __forceinline__ double log_weight_iv(const FilterDev& fd, const double x[NX], const double* __restrict__ y,
+                                                const InvDiv& ivR) {
+  if (fd.n_y != 1) return log_weight<NX>(fd, x, y);
+  double g = 0.0;
+#pragma unroll
+  for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[d], x[d], g);
+  double dd = __dsub_rn(g, y[0]);
+  return div_inv(__dmul_rn(-__dmul_rn(dd, dd), 0.5), ivR);
 }
 
 template <int NX>

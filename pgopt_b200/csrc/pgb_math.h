@@ -26,7 +26,19 @@
 #define PGB_HD static __host__ __device__ __forceinline__
 // larger routines: one copy per kernel instead of one per call site (code size / instruction cache)
 #define PGB_HD_NOINLINE static __host__ __device__ __noinline__
+// bulky helpers of the exact-scan algebra / phase functions: inline or not is a tuning knob (code size vs calls)
+#ifndef PGB_NOINLINE_HELPERS
+#define PGB_NOINLINE_HELPERS 0
+#endif
+#if PGB_NOINLINE_HELPERS
+#define PGB_HD_HELPER static __host__ __device__ __noinline__
+#define PGB_DEV_HELPER __device__ __noinline__
 #else
+#define PGB_HD_HELPER static __host__ __device__ __forceinline__
+#define PGB_DEV_HELPER __device__ __forceinline__
+#endif
+#else
+#define PGB_HD_HELPER static inline
 #define PGB_HD static inline
 #define PGB_HD_NOINLINE static inline
 #endif

@@ -123,6 +123,7 @@ __device__ __forceinline__ void p_scan_local(const ScanWS& ws, const double* v, 
   const int tid = threadIdx.x;
   const int64_t N = ws.N;
   const double* vc = v + (int64_t)chain * N;
+  const InvDiv ivS = make_invdiv(S);
   pgb_agg carry = pgb_agg_identity();
   double praw = sh.pfx[c];
   for (int k = 0; k < tpc; ++k) {
@@ -133,7 +134,7 @@ __device__ __forceinline__ void p_scan_local(const ScanWS& ws, const double* v, 
     bool bad = false;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      W[i] = (base + i < N) ? __ddiv_rn(vc[base + i], S) : 0.0;
+      W[i] = (base + i < N) ? div_inv(vc[base + i], ivS) : 0.0;
       if (!(W[i] >= 0.0 && W[i] <= 1.7976931348623157e308)) bad = true;
     }
     if (bad) atomicOr(&status[chain], 4);
@@ -147,7 +148,7 @@ __device__ __forceinline__ void p_scan_local(const ScanWS& ws, const double* v, 
     double ex = block_excl_scan_approx(s4, sh.sm, &tot);
     const bool last_tile = (k == tpc - 1) || (tile + 1 >= ws.nt);
     double pnext_raw = last_tile ? sh.pfx[c + 1] : __dadd_rn(praw, tsum_sm[k]);
-    double Pc = __ddiv_rn(praw, S), Pn = __ddiv_rn(pnext_raw, S);
+    double Pc = __dmul_rn(praw, ivS.y), Pn = __dmul_rn(pnext_raw, ivS.y);  // approximate quantities only
     double P = __dadd_rn(Pc, ex);
     __syncthreads();
     sh.sP[tid] = P;
@@ -192,17 +193,18 @@ __device__ __forceinline__ void p_side_approx(const ScanWS& ws, const double* v,
   const int64_t N = ws.N;
   const double* vc = v + (int64_t)chain * N;
   double praw = sh.pfx[c];
+  const InvDiv ivS = make_invdiv(S);
   for (int k = 0; k < tpc; ++k) {
     const int tile = c * tpc + k;
     if (tile >= ws.nt) break;
     int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
     double W[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) W[i] = (base + i < N) ? __ddiv_rn(vc[base + i], S) : 0.0;
+    for (int i = 0; i < 4; ++i) W[i] = (base + i < N) ? div_inv(vc[base + i], ivS) : 0.0;
     double s1 = W[0], s2 = __dadd_rn(s1, W[1]), s3 = __dadd_rn(s2, W[2]), s4 = __dadd_rn(s3, W[3]);
     double tot;
     double ex = block_excl_scan_approx(s4, sh.sm, &tot);
-    double P = __dadd_rn(__ddiv_rn(praw, S), ex);
+    double P = __dadd_rn(__dmul_rn(praw, ivS.y), ex);
     double qt[5] = {P, __dadd_rn(P, s1), __dadd_rn(P, s2), __dadd_rn(P, s3), __dadd_rn(P, s4)};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -328,6 +330,7 @@ struct EmitCtx {
   double* lwb;
   const double* yt;
   const double* zin;
+  InvDiv ivR;
 };
 template <int NX>
 __device__ __forceinline__ void emit_ctx_init(EmitCtx<NX>& ec, const FilterDev& fd, int chain, int64_t t) {
@@ -340,6 +343,7 @@ __device__ __forceinline__ void emit_ctx_init(EmitCtx<NX>& ec, const FilterDev& 
   ec.lwb = fd.lwbuf + (int64_t)chain * N;
   ec.yt = fd.y + (int64_t)fd.n_y * t;
   ec.zin = fd.Z ? fd.Z + ((int64_t)chain * fd.T + t) * NX * N : nullptr;
+  ec.ivR = make_invdiv(fd.R[0]);
 }
 template <int NX>
 __device__ __forceinline__ void emit_offspring(const FilterDev& fd, const EmitCtx<NX>& ec, int chain, int64_t t,
@@ -365,13 +369,18 @@ __device__ __forceinline__ void emit_offspring(const FilterDev& fd, const EmitCt
 // Four output slots at once (independent Philox / Box-Muller / log-weight chains interleaved).  Same values as
 // emit_offspring for every slot.
 template <int NX>
-__device__ __forceinline__ void emit_offspring4(const FilterDev& fd, const EmitCtx<NX>& ec, int chain, int64_t t,
+PGB_DEV_HELPER void emit_offspring4(const FilterDev& fd, const EmitCtx<NX>& ec, int chain, int64_t t,
                                                 const int64_t (&jj)[4], const int32_t (&a0)[4], const bool (&act)[4],
                                                 const double (&F)[4][NX], int* stat, double& lmax) {
   constexpr int NP = (NX + 1) / 2;
   const int64_t N = fd.N;
   double z[4][2 * NP];
-  if (fd.philox) {
+  if (fd.ablate & 4) {  // timing experiment: no Philox / Box-Muller
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int d = 0; d < 2 * NP; ++d) z[k][d] = 0.25 * (double)(jj[k] & 7);
+  } else if (fd.philox) {
     pgb_u32x4 ctr[4 * NP];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -408,7 +417,7 @@ __device__ __forceinline__ void emit_offspring4(const FilterDev& fd, const EmitC
       for (int e = 0; e <= d; ++e) acc = __fma_rn(ec.Lq[d + NX * e], z[k][e], acc);
       x[d] = __dadd_rn(F[k][d], acc);
     }
-    double lw = log_weight<NX>(fd, x, ec.yt);
+    double lw = (fd.ablate & 8) ? -x[0] * x[0] : log_weight_iv<NX>(fd, x, ec.yt, ec.ivR);
     if (act[k]) {
       ec.at[jj[k]] = a0[k];
 #pragma unroll
@@ -521,7 +530,10 @@ __device__ __forceinline__ void p_consume_by_output(const FilterDev& fd, const E
   const int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
   int64_t rr[5];
   int64_t zero_upto = 0;
-  if (base < N) {
+  if (base < N && (fd.ablate & 16)) {  // timing experiment: one offspring per particle, no grid counts
+#pragma unroll
+    for (int i = 0; i < 5; ++i) rr[i] = (base + i < M) ? base + i : M;
+  } else if (base < N) {
     int row = -1;
     rr[0] = pgb_utable_count_le_hint(ut, q[0], &row);
     if (base == 0) {
@@ -559,7 +571,7 @@ __device__ __forceinline__ void p_consume_by_output(const FilterDev& fd, const E
   for (int i = 0; i < 4; ++i) {
     const int64_t lo = (i == 0) ? jfrom0 : rr[i], hi = rr[i + 1];
     is_heavy[i] = false;
-    if (hi - lo > P_HEAVY && base + i < N) {
+    if (heavy && hi - lo > P_HEAVY && base + i < N) {
       int slot = atomicAdd(heavy_cnt, 1);
       if (slot < P_HEAVY_MAX) {
         HeavyEnt he;
@@ -743,6 +755,7 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
     // ================================================================ phase A: w_{t-1}, F, waN
     {
       const double S1 = block_tree_sum_array(pe, nb, sh.sm);
+      const InvDiv ivS1 = make_invdiv(S1);
       if (c == 0 && tid == 0) {
         fd.maxkey[chain] = 0ull;  // its readers finished before the last barrier
         pd.heavy_cnt[chain] = 0;
@@ -756,10 +769,13 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
       double* wa = fd.waN + (int64_t)chain * N;
       const double* up = fd.u + (int64_t)fd.n_u * (t - 1);
       double Lq[NX * NX], xref[NX];
+      InvDiv ivL[NX];
       double c0 = 0.0;
       if (anc) {
 #pragma unroll
         for (int i = 0; i < NX * NX; ++i) Lq[i] = fd.Lq[chain * 16 + i];
+#pragma unroll
+        for (int d = 0; d < NX; ++d) ivL[d] = make_invdiv(Lq[d + NX * d]);
 #pragma unroll
         for (int d = 0; d < NX; ++d) xref[d] = fd.xprim[(int64_t)chain * NX * T + d + NX * t];
         c0 = fd.c0[chain];
@@ -776,7 +792,7 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
         for (int i = 0; i < 4; ++i) {
           int64_t n = base + i;
           live[i] = (tile < nt && n < N);
-          wv[i] = live[i] ? __ddiv_rn(e[n], S1) : 0.0;
+          wv[i] = live[i] ? div_inv(e[n], ivS1) : 0.0;
           av[i] = 0.0;
           if (live[i]) {
             w[n] = wv[i];
@@ -789,14 +805,21 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
           for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int d = 0; d < NX; ++d) x[i][d] = live[i] ? xp[(int64_t)d * N + base + i] : 0.0;
-          eval_F4<NX>(fd, A_sm, x, up, F);
+          if (fd.ablate & 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int d = 0; d < NX; ++d) F[i][d] = x[i][d];
+          } else {
+            eval_F4<NX>(fd, A_sm, x, up, F);
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (live[i]) {
 #pragma unroll
               for (int d = 0; d < NX; ++d) Fb[(int64_t)d * N + base + i] = F[i][d];
             }
-          if (anc) {
+          if (anc && !(fd.ablate & 2)) {
             double ea[4], pv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -806,7 +829,7 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
                 double acc = __dsub_rn(F[i][d], xref[d]);
 #pragma unroll
                 for (int e2 = 0; e2 < d; ++e2) acc = __fma_rn(-Lq[d + NX * e2], r[e2], acc);
-                r[d] = __ddiv_rn(acc, Lq[d + NX * d]);
+                r[d] = div_inv(acc, ivL[d]);
                 sq = __fma_rn(r[d], r[d], sq);
               }
               ea[i] = __dsub_rn(c0, __dmul_rn(sq, 0.5));
@@ -840,6 +863,7 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
       P_TICK(3);
       if (anc) {
         const double S3 = block_tree_sum_array(pa, nb, sh.sm);
+        const InvDiv ivS3 = make_invdiv(S3);
         double* wa = fd.waN + (int64_t)chain * N;
         TreeAcc acc;
         acc.init();
@@ -851,7 +875,7 @@ __global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent
           for (int i = 0; i < 4; ++i) {
             v[i] = 0.0;
             if (tile < nt && base + i < N) {
-              v[i] = __ddiv_rn(wa[base + i], S3);
+              v[i] = div_inv(wa[base + i], ivS3);
               wa[base + i] = v[i];
             }
           }

@@ -11,8 +11,16 @@
 
 namespace pgb {
 
+// PGB_SMALL_CODE=1 makes the K-wide entry points forward to the scalar __noinline__ routines of pgb_math.h (one
+// call per lane, compact code).  Measured on B200 (scripts/ab_variants.py, N = 2^20, known basis): interleaved +
+// fully inlined 195 us/step, compact 225 us/step, compact + non-inlined helpers 277 us/step — the kernel is bound by
+// per-warp dependency latency, not by instruction fetch, so the interleaved versions are the default.
+#ifndef PGB_SMALL_CODE
+#define PGB_SMALL_CODE 0
+#endif
+
 template <int K>
-__device__ __forceinline__ void vexp(const double (&x)[K], double (&y)[K]) {
+__device__ __forceinline__ void vexp_wide(const double (&x)[K], double (&y)[K]) {
   double xc[K], kd[K], r[K], p[K];
   int ki[K];
 #pragma unroll
@@ -51,7 +59,7 @@ __device__ __forceinline__ void vexp(const double (&x)[K], double (&y)[K]) {
 
 // log for finite, positive, NORMAL arguments (the Box-Muller uniforms are >= 2^-54)
 template <int K>
-__device__ __forceinline__ void vlog_pos_normal(const double (&x)[K], double (&y)[K]) {
+__device__ __forceinline__ void vlog_pos_normal_wide(const double (&x)[K], double (&y)[K]) {
   double f[K], s[K], dk[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -84,7 +92,7 @@ __device__ __forceinline__ void vlog_pos_normal(const double (&x)[K], double (&y
 
 // sin and cos of K arguments (|x| < 2^50 handled exactly like the scalar routine; beyond 1e15 -> NaN)
 template <int K>
-__device__ __forceinline__ void vsincos(const double (&x)[K], double (&sn)[K], double (&cs)[K]) {
+__device__ __forceinline__ void vsincos_wide(const double (&x)[K], double (&sn)[K], double (&cs)[K]) {
   double r[K];
   int q[K];
 #pragma unroll
@@ -134,7 +142,7 @@ __device__ __forceinline__ void vsincos(const double (&x)[K], double (&sn)[K], d
 
 // K Philox4x32-10 blocks with a common key
 template <int K>
-__device__ __forceinline__ void vphilox(pgb_u32x4 (&ctr)[K], uint32_t k0, uint32_t k1) {
+__device__ __forceinline__ void vphilox_wide(pgb_u32x4 (&ctr)[K], uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
 #pragma unroll
@@ -155,21 +163,69 @@ __device__ __forceinline__ void vphilox(pgb_u32x4 (&ctr)[K], uint32_t k0, uint32
 
 // K Box-Muller pairs from K Philox blocks (same as pgb_normal_pair)
 template <int K>
-__device__ __forceinline__ void vnormal_pairs(const pgb_u32x4 (&bits)[K], double (&z0)[K], double (&z1)[K]) {
+__device__ __forceinline__ void vnormal_pairs_wide(const pgb_u32x4 (&bits)[K], double (&z0)[K], double (&z1)[K]) {
   double u1[K], ang[K], lg[K], s[K], c[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     u1[k] = pgb_u53(bits[k].v[0], bits[k].v[1]);
     ang[k] = __dmul_rn(0x1.921fb54442d18p+2, pgb_u53(bits[k].v[2], bits[k].v[3]));
   }
-  vlog_pos_normal<K>(u1, lg);
-  vsincos<K>(ang, s, c);
+  vlog_pos_normal_wide<K>(u1, lg);
+  vsincos_wide<K>(ang, s, c);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     double rad = __dsqrt_rn(__dmul_rn(-2.0, lg[k]));
     z0[k] = __dmul_rn(rad, c[k]);
     z1[k] = __dmul_rn(rad, s[k]);
   }
+}
+
+
+template <int K>
+__device__ __forceinline__ void vexp(const double (&x)[K], double (&y)[K]) {
+#if PGB_SMALL_CODE
+#pragma unroll
+  for (int k = 0; k < K; ++k) y[k] = pgb_exp(x[k]);
+#else
+  vexp_wide<K>(x, y);
+#endif
+}
+template <int K>
+__device__ __forceinline__ void vsincos(const double (&x)[K], double (&sn)[K], double (&cs)[K]) {
+#if PGB_SMALL_CODE
+#pragma unroll
+  for (int k = 0; k < K; ++k) pgb_sincos(x[k], &sn[k], &cs[k]);
+#else
+  vsincos_wide<K>(x, sn, cs);
+#endif
+}
+template <int K>
+__device__ __forceinline__ void vlog_pos_normal(const double (&x)[K], double (&y)[K]) {
+#if PGB_SMALL_CODE
+#pragma unroll
+  for (int k = 0; k < K; ++k) y[k] = pgb_log(x[k]);
+#else
+  vlog_pos_normal_wide<K>(x, y);
+#endif
+}
+template <int K>
+__device__ __forceinline__ void vphilox(pgb_u32x4 (&ctr)[K], uint32_t k0, uint32_t k1) {
+#if PGB_SMALL_CODE
+#pragma unroll
+  for (int k = 0; k < K; ++k) ctr[k] = pgb_philox4x32_10(ctr[k], k0, k1);
+#else
+  vphilox_wide<K>(ctr, k0, k1);
+#endif
+}
+__device__ __noinline__ void normal_pair_noinline(pgb_u32x4 bits, double* z0, double* z1) { pgb_normal_pair(bits, z0, z1); }
+template <int K>
+__device__ __forceinline__ void vnormal_pairs(const pgb_u32x4 (&bits)[K], double (&z0)[K], double (&z1)[K]) {
+#if PGB_SMALL_CODE
+#pragma unroll
+  for (int k = 0; k < K; ++k) normal_pair_noinline(bits[k], &z0[k], &z1[k]);
+#else
+  vnormal_pairs_wide<K>(bits, z0, z1);
+#endif
 }
 
 }  // namespace pgb
