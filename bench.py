@@ -74,8 +74,12 @@ def build_problem(model, T, seed=0):
     else:
         basis = pg.HilbertGPBasis([5, 5, 5], [10.0, 20.0, 20.0])
         Phi = hilbert_phi_np(basis.count, basis.L, x[:, :T], u)
-        A = np.linalg.solve(Phi @ Phi.T + 1e-3 * np.eye(125), Phi @ x[:, 1:T + 1].T).T  # ridge fit on the true states
         V = pg.hilbert_gp_prior_V([5, 5, 5], [10, 20, 20], 2 * np.pi * np.ones(3), 100 ** 2 / (8 * np.pi ** 4))
+        # what the sampler itself would produce given the true trajectory: the MNIW posterior mean of A
+        # (particle_Gibbs.jl:64-67) and the residual covariance as Q
+        A = np.linalg.solve(Phi @ Phi.T + np.diag(1 / V), Phi @ x[:, 1:T + 1].T).T
+        return dict(basis=basis, u=u, y=y, A=A, Q=np.cov(x[:, 1:T + 1] - A @ Phi), V=V, x_prim=x[:, :T].copy(),
+                    n_phi=basis.n_phi)
     Q = np.array([[0.05, 0.0], [0.0, 0.03]])
     return dict(basis=basis, u=u, y=y, A=A, Q=Q, V=V, x_prim=x[:, :T].copy(), n_phi=basis.n_phi)
 
@@ -126,8 +130,11 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-PROF_NAMES = ["k_prep", "k_norm", "k_scan_local", "k_resolve", "k_expand", "k_seq_exact", "k_expand_fallback",
-              "k_weights", "k_init", "tail(trace+stats)", "k_mniw"]
+PROF_NAMES = ["k_prep", "k_norm", "k_scan_local", "k_resolve", "k_sweep_persistent (whole T loop)", "k_seq_exact",
+              "k_expand_fallback", "k_weights", "k_build_utabs", "tail(trace+stats)", "k_mniw"]
+PHASE_NAMES = ["init", "A prep (w, F, waN)", "wait B1", "B scan-local main", "B normalise side", "wait B2", "C resolve",
+               "C exact prefixes + expansion", "C ancestor shortcut", "wait B3", "D ancestor index", "D heavy + weights",
+               "wait B4", "fix-up test"]
 
 
 def dist_setup(n_gpus):
@@ -213,6 +220,13 @@ def run_gpu(args):
             if launches[i]}
     tot_prof = sum(v["ms"] for v in prof.values()) or 1.0
     dom = max(prof, key=lambda k: prof[k]["ms"])
+    cyc = (C.c_double * 16)()
+    ncta = C.c_int32(0)
+    check(lib().pgb_get_phase_cycles(eng._h, cyc, C.byref(ncta)), eng._h)
+    tot_cyc = sum(cyc) or 1.0
+    phases = {PHASE_NAMES[i]: round(100 * cyc[i] / tot_cyc, 1) for i in range(len(PHASE_NAMES)) if cyc[i]}
+    fp64_peak = C.c_double(0)
+    check(lib().pgb_test_fp64_peak(local, C.byref(fp64_peak)))
 
     # ---- end to end through the public API with pinned host buffers
     def pinned(a):
@@ -281,8 +295,8 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "one CPF-AS time step = k_prep + scan pipeline + k_expand + k_weights (%d launches/step)"
-                                   % ((n1.value - n0.value) // max(1, args.steps * (T - 1))),
+                         "kernel": "k_sweep_persistent: one cooperative launch = one whole conditional sweep (T-1 steps x 4 grid barriers); "
+                                   "%d launches per sweep in total" % ((n1.value - n0.value) // max(1, args.steps)),
                          "algorithmic_bytes_per_particle_step": bps,
                          "dominant_kernel": dom, "dominant_share": prof[dom]["ms"] / tot_prof,
                          "fp64_tflops_achieved": FLOPS_PER_PARTICLE_STEP[args.model] * N * (T - 1) / t_per_sweep / 1e12,

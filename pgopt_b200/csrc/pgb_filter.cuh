@@ -108,6 +108,59 @@ __device__ __forceinline__ void eval_F(const FilterDev& fd, const double* __rest
   for (int d = 0; d < NX; ++d) F[d] = acc[d];
 }
 
+// Hilbert-space basis with 5 x 5 x 5 functions over z = [u; x1; x2] (the reference's generic example), two particles
+// at once: the 15 sines of each particle are evaluated 5-wide, the 125 tensor-product terms are fully unrolled with
+// the per-dimension factors in registers, and every A entry read from shared memory feeds both particles.  Same
+// products and the same fma order as eval_F (i increasing), hence the same bits.
+template <int NX>
+__device__ __noinline__ void eval_F_hilbert355_pair(const FilterDev& fd, const double* __restrict__ A_sm,
+                                                       const double xa[NX], const double xb[NX],
+                                                       const double* __restrict__ u, double Fa[NX], double Fb2[NX]) {
+  double t[2][3][5];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double zk = (k < fd.n_u) ? u[k] : (p == 0 ? xa[(k - fd.n_u) < NX ? (k - fd.n_u) : 0] : xb[(k - fd.n_u) < NX ? (k - fd.n_u) : 0]);
+      const double zl = __dadd_rn(zk, fd.hg_L[k]);
+      double arg[5], sn[5], cs[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) arg[j] = __dmul_rn(fd.hg_pij2l[k][j], zl);
+      vsincos_wide<5>(arg, sn, cs);
+#pragma unroll
+      for (int j = 0; j < 5; ++j) t[p][k][j] = __dmul_rn(fd.hg_lsi[k], sn[j]);
+    }
+  double acc[2][NX];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int d = 0; d < NX; ++d) acc[p][d] = 0.0;
+#pragma unroll
+  for (int j0 = 0; j0 < 5; ++j0)
+#pragma unroll
+    for (int j1 = 0; j1 < 5; ++j1) {
+      const double pa = __dmul_rn(t[0][0][j0], t[0][1][j1]);
+      const double pb = __dmul_rn(t[1][0][j0], t[1][1][j1]);
+#pragma unroll
+      for (int j2 = 0; j2 < 5; ++j2) {
+        const int i = (j0 * 5 + j1) * 5 + j2;
+        const double qa = __dmul_rn(pa, t[0][2][j2]);
+        const double qb = __dmul_rn(pb, t[1][2][j2]);
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+          const double a = A_sm[d + NX * i];
+          acc[0][d] = __fma_rn(a, qa, acc[0][d]);
+          acc[1][d] = __fma_rn(a, qb, acc[1][d]);
+        }
+      }
+    }
+#pragma unroll
+  for (int d = 0; d < NX; ++d) {
+    Fa[d] = acc[0][d];
+    Fb2[d] = acc[1][d];
+  }
+}
+
 // F for the thread's four particles at once (known basis: the four sin/cos chains are interleaved)
 template <int NX>
 __device__ __forceinline__ void eval_F4(const FilterDev& fd, const double* __restrict__ A_sm, const double (&x)[4][NX],
@@ -137,6 +190,11 @@ __device__ __forceinline__ void eval_F4(const FilterDev& fd, const double* __res
         F[k][d] = acc;
       }
     }
+    return;
+  }
+  if (NX == 2 && fd.n_z == 3 && fd.hg_count[0] == 5 && fd.hg_count[1] == 5 && fd.hg_count[2] == 5) {
+#pragma unroll 1
+    for (int k = 0; k < 4; k += 2) eval_F_hilbert355_pair<NX>(fd, A_sm, x[k], x[k + 1], u, F[k], F[k + 1]);
     return;
   }
 #pragma unroll 1

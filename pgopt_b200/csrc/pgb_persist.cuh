@@ -655,7 +655,8 @@ __device__ __forceinline__ void p_seq_exact(const ScanWS& ws, const double* v, d
 #define PGB_PERSIST_MINBLOCKS 2
 #endif
 template <int NX>
-__global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS) k_sweep_persistent(FilterDev fd, PersistDev pd, int first) {
+__global__ void __launch_bounds__(TPB, PGB_PERSIST_MINBLOCKS)
+k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__ PersistDev pd, int first) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PersistShared& sh = *reinterpret_cast<PersistShared*>(smem_raw);
   double* A_sm = reinterpret_cast<double*>(smem_raw + sizeof(PersistShared));
