@@ -299,10 +299,14 @@ def run_gpu(args):
                                    "%d launches per sweep in total" % ((n1.value - n0.value) // max(1, args.steps)),
                          "algorithmic_bytes_per_particle_step": bps,
                          "dominant_kernel": dom, "dominant_share": prof[dom]["ms"] / tot_prof,
-                         "fp64_tflops_achieved": FLOPS_PER_PARTICLE_STEP[args.model] * N * (T - 1) / t_per_sweep / 1e12,
-                         "note": "generic basis is FP64-pipe bound (SURVEY.md §8d); the HBM fraction is reported for the "
-                                 "contract, the FP64 rate is the binding one" if args.model == "generic" else ""},
+                         "fp64": {"algorithmic_tflops_achieved": FLOPS_PER_PARTICLE_STEP[args.model] * N * (T - 1) / t_per_sweep / 1e12,
+                                  "dfma_peak_tflops_measured": fp64_peak.value,
+                                  "flops_per_particle_step": FLOPS_PER_PARTICLE_STEP[args.model]},
+                         "note": "measured: the path is instruction-/latency-bound in FP64 (divisions, exp/log/sin/cos, Philox, "
+                                 "exact-scan integer algebra) with DRAM ~5% busy; see DESIGN.md section 5 and profiles/"},
             "kernel_profile_ms_per_sweep": prof,
+            "persistent_kernel_phase_share_pct": phases,
+            "persistent_ctas": int(ncta.value),
             "resampling": {"status_bits": st, "exact_scans": nscan, "serial_fallbacks": nfb},
         }
         if cpu:
