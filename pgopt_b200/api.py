@@ -171,9 +171,11 @@ class ParticleGibbsEngine:
     def _ck(self, rc):
         check(rc, self._h)
 
-    def set_mode(self, persistent=2):
-        """2 (default, also True... see below): warp-tile persistent kernel; 1: tile persistent kernel; 0/False: multi-kernel"""
-        mode = 2 if persistent is True else int(persistent)
+    def set_mode(self, persistent=1):
+        """1 / True (library default): tile persistent kernel, one cooperative launch per sweep; 2: warp-tile
+        persistent kernel (alternative formulation, slower); 0 / False: multi-kernel path (13 launches per step;
+        per-kernel profiling and cross-check).  All three are bit-identical."""
+        mode = 1 if persistent is True else int(persistent)
         self._ck(lib().pgb_set_mode(self._h, C.c_int32(mode)))
 
     def set_data(self, u, y):

@@ -12,8 +12,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpgopt_b200.so")
 SOURCES = ["pgb_capi.cu"]
-HEADERS = ["pgb_math.h", "pgb_exact.h", "pgb_device.cuh", "pgb_scan.cuh", "pgb_filter.cuh", "pgb_mniw.cuh",
-           "pgb_rollout.cuh", os.path.join("..", "..", "include", "pgopt_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + \
+    [os.path.join("..", "..", "include", "pgopt_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",  # products/sums never fuse unless written as __fma_rn (bit parity with the oracle)
