@@ -295,6 +295,8 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
     CKC(dalloc(h, &pd.heavy_cnt, (size_t)nc));
     CKC(dalloc(h, &pd.prof, (size_t)1024 * P_NPROF));
     CKC(dalloc(h, &pd.cand, (size_t)2 * nc));
+    CKC(dalloc(h, &pd.sm_slots, (size_t)1024));
+    CKC(dalloc(h, &pd.cta_key, (size_t)4096));
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
     h->num_sms = prop.multiProcessorCount;
@@ -548,14 +550,24 @@ static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
   if (warp_tiles) CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_w<NX>, TPB, smA));
   else CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_persistent<NX>, TPB, smA));
   const int max_ctas = occ * h->num_sms;
+  if (max_ctas > 4096) return -1;
   int nbmax = max_ctas / nc;
-  if (nbmax > P_MAXNB) nbmax = P_MAXNB;
   if (nbmax < 1) return -1;
   int tpc = 1;
-  while ((fd.nt + tpc - 1) / tpc > nbmax) tpc *= 2;
-  if (tpc > (warp_tiles ? W_MAXTPC : P_MAXTPC)) return -1;
-  pd.tpc = tpc;
-  pd.nb = (fd.nt + tpc - 1) / tpc;
+  if (warp_tiles) {  // one block per CTA
+    if (nbmax > W_MAXNB) nbmax = W_MAXNB;
+    while ((fd.nt + tpc - 1) / tpc > nbmax) tpc *= 2;
+    if (tpc > W_MAXTPC) return -1;
+    pd.tpc = tpc;
+    pd.nb = (fd.nt + tpc - 1) / tpc;
+    pd.npc = pd.nb;
+  } else {  // finest blocks the per-chain tables allow, dealt over every co-resident CTA slot
+    while ((fd.nt + tpc - 1) / tpc > P_MAXNB) tpc *= 2;
+    pd.tpc = tpc;
+    pd.nb = (fd.nt + tpc - 1) / tpc;
+    pd.npc = pd.nb < nbmax ? pd.nb : nbmax;
+    if (((pd.nb + pd.npc - 1) / pd.npc) * tpc > P_MAXTPC) return -1;
+  }
   pd.force_fallback = g_force_fallback;
   int first = (h->sweep_index == 1);
   fd.sweep = (uint32_t)h->sweep_index;
@@ -565,6 +577,7 @@ static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
   CK(h, cudaMemcpyAsync(h->d_Q_used, h->d_Q, nQ, cudaMemcpyDeviceToDevice, s));
   CK(h, cudaMemsetAsync(fd.maxkey, 0, (size_t)nc * 8, s));
   CK(h, cudaMemsetAsync(pd.bar, 0, 4, s));
+  CK(h, cudaMemsetAsync(pd.sm_slots, 0, (size_t)1024 * 4, s));
   CK(h, cudaMemsetAsync(pd.heavy_cnt, 0, (size_t)nc * 4, s));
   CK(h, cudaMemsetAsync(pd.cand, 0, (size_t)2 * nc * 4, s));
   CK(h, cudaMemsetAsync(fd.main.flag, 0, (size_t)2 * nc * 4, s));
@@ -573,7 +586,7 @@ static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
   {
     LaunchScope ls(h, PGB_PROF_EXPAND);
     void* args[] = {(void*)&fd, (void*)&pd, (void*)&first};
-    CK(h, cudaLaunchCooperativeKernel(kfn, dim3((unsigned)(nc * pd.nb)), dim3(TPB), args, smA, s));
+    CK(h, cudaLaunchCooperativeKernel(kfn, dim3((unsigned)(nc * pd.npc)), dim3(TPB), args, smA, s));
   }
   LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
   LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
@@ -880,6 +893,8 @@ extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const
   return PGB_OK;
 }
 
+static float g_rollout_ms[2] = {0.f, 0.f};  // device time of the last pgb_rollout: {transpose of A, rollout kernel}
+
 template <int NX>
 static void launch_rollout(const FilterDev& fd, const RolloutDev& rd) {
   k_rollout<NX><<<(unsigned)((rd.K + 127) / 128), 128>>>(fd, rd);
@@ -936,7 +951,11 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   if (e) CK(h, dalloc(h, &rd.e, (size_t)K * H * ny, false));
   if (X) CK(h, dalloc(h, &rd.X, (size_t)K * (H + 1) * nx, false));
   if (Y) CK(h, dalloc(h, &rd.Y, (size_t)K * H * ny, false));
+  cudaEvent_t ev[3];
+  for (auto& evt : ev) CK(h, cudaEventCreate(&evt));
+  CK(h, cudaEventRecord(ev[0], 0));
   k_transpose_A<<<dim3((unsigned)((K + 31) / 32), (unsigned)((m + 31) / 32)), dim3(32, 8)>>>(dA, dAt, K, m);
+  CK(h, cudaEventRecord(ev[1], 0));
   rd.At = dAt; rd.Q = dQ; rd.w_m1 = dw; rd.x_m1 = dx; rd.u_m1 = dum; rd.u_init = dui;
   switch (nx) {
     case 1: launch_rollout<1>(fd, rd); break;
@@ -945,7 +964,11 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
     default: launch_rollout<4>(fd, rd); break;
   }
   CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(ev[2], 0));
   CK(h, cudaDeviceSynchronize());
+  cudaEventElapsedTime(&g_rollout_ms[0], ev[0], ev[1]);
+  cudaEventElapsedTime(&g_rollout_ms[1], ev[1], ev[2]);
+  for (auto& evt : ev) cudaEventDestroy(evt);
   int st = 0;
   CK(h, cudaMemcpy(&st, rd.status, 4, cudaMemcpyDeviceToHost));
   if (st & PGB_STATUS_NOT_POSDEF) return set_err(nullptr, PGB_ERR_NOT_POSDEF, "a scenario's Q is not positive definite");
@@ -957,10 +980,16 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   return PGB_OK;
 }
 
+extern "C" int pgb_rollout_last_ms(double* transpose_ms, double* kernel_ms) {
+  if (transpose_ms) *transpose_ms = g_rollout_ms[0];
+  if (kernel_ms) *kernel_ms = g_rollout_ms[1];
+  return PGB_OK;
+}
+
 extern "C" int pgb_get_phase_cycles(pgb_handle* h, double* avg_cycles /*[16]*/, int32_t* n_ctas) {
   NEED(h);
   CK(h, cudaStreamSynchronize(h->stream));
-  const int g = h->fd.nc * h->pd.nb;
+  const int g = h->fd.nc * h->pd.npc;
   std::vector<long long> v((size_t)1024 * P_NPROF);
   CK(h, cudaMemcpy(v.data(), h->pd.prof, v.size() * 8, cudaMemcpyDeviceToHost));
   for (int i = 0; i < P_NPROF; ++i) {

@@ -1,9 +1,13 @@
 // pgb_persist.cuh — the whole CPF-AS time loop (Julia/src/particle_Gibbs.jl:160-200) as ONE persistent
 // cooperative kernel: T-1 steps x 4 phases separated by grid barriers, instead of 13 launches per step.
 //
-// Work decomposition: chain `ch` owns nb consecutive CTAs; CTA c of a chain owns the aligned block of
-// `tpc` (power of two) consecutive 1024-element tiles [c*tpc, (c+1)*tpc).  Per-CTA partial sums are the
-// tree over that aligned block, so the grid-wide sums are still the balanced binary tree of the oracle.
+// Work decomposition: a chain's particles are cut into nb "blocks" of `tpc` (power of two) consecutive
+// 1024-element tiles, block c = tiles [c*tpc, (c+1)*tpc).  Per-block partial sums are the tree over that aligned
+// range, so the grid-wide sums are still the balanced binary tree of the oracle.  Chain `ch` owns npc consecutive
+// CTAs (npc <= nb, NOT a power of two: every co-resident slot of the GPU is used); a CTA processes the blocks
+// o, o+npc, o+2npc, ... where o is its rank in an SM-aware order (all first-resident CTAs of the SMs, then the
+// second-resident ones), so the blocks-per-SM counts differ by at most one (7/6 tiles per SM at N = 2^20 on 148 SMs
+// instead of 8/4 with one power-of-two block per CTA).
 //
 // Per step t (k > 1):                                                    grid barriers: 4
 //   A  w = e/S1, F = A*phi(x_{t-1}), waN = w*N(x'_t;F,Q); CTA sums of w, waN          | B1
@@ -21,8 +25,8 @@
 
 namespace pgb {
 
-constexpr int P_MAXNB = 640;      // max CTAs per chain (>= 148 * 4)
-constexpr int P_MAXTPC = 64;      // max tiles per CTA
+constexpr int P_MAXNB = 1024;     // max blocks per chain
+constexpr int P_MAXTPC = 64;      // max tiles per CTA (all of its blocks together)
 constexpr int P_MAXREC = 160;     // complex threads resolved per scan (more -> serial fallback)
 constexpr int P_HEAVY = 32;       // offspring count above which a particle goes to the cooperative list
 constexpr int P_HEAVY_MAX = 1 << 15;
@@ -36,7 +40,10 @@ struct HeavyEnt {
 };
 
 struct PersistDev {
-  int nb, tpc;
+  int nb, tpc;              // blocks per chain, tiles per block
+  int npc;                  // CTAs per chain
+  int* sm_slots;            // [1024] residency counter per SM id (zeroed before launch)
+  int* cta_key;             // [grid] (residency slot << 12) | SM id
   unsigned int* bar;        // [1] grid barrier counter (zeroed before launch)
   double *pe, *pw, *pa, *pa2;  // [nc][nb] CTA partial sums
   int32_t* star_idx;        // [nc]
@@ -103,16 +110,23 @@ struct PersistShared {
 
 // exclusive approximate scan of p[0..nb) into sh.pfx[0..nb] (every CTA computes identical values)
 __device__ __forceinline__ void approx_prefix(const double* p, int nb, PersistShared& sh) {
-  double carry = 0.0;
-  for (int base = 0; base < nb; base += TPB) {
-    int i = base + threadIdx.x;
-    double v = (i < nb) ? p[i] : 0.0;
-    double tot;
-    double ex = block_excl_scan_approx(v, sh.sm, &tot);
-    if (i < nb) sh.pfx[i] = __dadd_rn(carry, ex);
-    carry = __dadd_rn(carry, tot);
+  const int per = (nb + TPB - 1) / TPB;  // <= P_MAXNB / TPB consecutive entries per thread
+  const int i0 = threadIdx.x * per;
+  double v[P_MAXNB / TPB];
+  double run = 0.0;
+#pragma unroll
+  for (int j = 0; j < P_MAXNB / TPB; ++j) {
+    v[j] = (j < per && i0 + j < nb) ? p[i0 + j] : 0.0;
+    run = __dadd_rn(run, v[j]);
   }
-  if (threadIdx.x == 0) sh.pfx[nb] = carry;
+  double tot;
+  double ex = block_excl_scan_approx(run, sh.sm, &tot);
+#pragma unroll
+  for (int j = 0; j < P_MAXNB / TPB; ++j) {
+    if (j < per && i0 + j < nb) sh.pfx[i0 + j] = ex;
+    ex = __dadd_rn(ex, v[j]);
+  }
+  if (threadIdx.x == 0) sh.pfx[nb] = tot;
   __syncthreads();
 }
 
@@ -222,17 +236,26 @@ __device__ __forceinline__ void p_resolve(const ScanWS& ws, int chain, int nb, i
                                           int force_fallback, int* flagp) {
   const int tid = threadIdx.x;
   const pgb_agg* cagg = ws.tile_agg + (int64_t)chain * ws.nt;
-  pgb_agg carry = pgb_agg_identity();
-  for (int base = 0; base < nb; base += TPB) {
-    int i = base + tid;
-    pgb_agg v = (i < nb) ? cagg[i] : pgb_agg_identity();
-    pgb_agg tot;
-    pgb_agg ex = block_excl_scan_agg(v, sh.smagg, &tot);
-    if (i < nb) sh.cex[i] = pgb_agg_combine(carry, ex);
-    carry = pgb_agg_combine(carry, tot);
+  pgb_agg carry;
+  const int per = (nb + TPB - 1) / TPB;
+  const int i0 = tid * per;
+  pgb_agg v[P_MAXNB / TPB], exs[P_MAXNB / TPB];
+  {
+    pgb_agg run = pgb_agg_identity();
+#pragma unroll
+    for (int j = 0; j < P_MAXNB / TPB; ++j) {
+      v[j] = (j < per && i0 + j < nb) ? cagg[i0 + j] : pgb_agg_identity();
+      run = pgb_agg_combine(run, v[j]);
+    }
+    pgb_agg ex = block_excl_scan_agg(run, sh.smagg, &carry);
+#pragma unroll
+    for (int j = 0; j < P_MAXNB / TPB; ++j) {
+      exs[j] = ex;
+      if (j < per && i0 + j < nb) sh.cex[i0 + j] = ex;
+      ex = pgb_agg_combine(ex, v[j]);
+    }
   }
   if (tid == 0) sh.cex[nb] = carry;
-  __syncthreads();
   const int C = carry.cnt;
   if (C > P_MAXREC || force_fallback) {
     if (tid == 0) atomicOr(flagp, 1);
@@ -240,12 +263,14 @@ __device__ __forceinline__ void p_resolve(const ScanWS& ws, int chain, int nb, i
     __syncthreads();
     return;
   }
-  for (int b = tid; b < nb; b += TPB) {
-    int cnt = cagg[b].cnt;
+  // gather the complex threads' records of this thread's blocks (the aggregates are still in registers)
+#pragma unroll
+  for (int j = 0; j < P_MAXNB / TPB; ++j) {
+    int cnt = v[j].cnt;
     if (cnt > tpc * RMAX) cnt = tpc * RMAX;
-    pgb_agg te = sh.cex[b];
+    const pgb_agg te = exs[j];
     for (int i = 0; i < cnt; ++i) {
-      const ScanRec* r = &ws.recs[((int64_t)chain * ws.nt + (int64_t)b * tpc) * RMAX + i];
+      const ScanRec* r = &ws.recs[((int64_t)chain * ws.nt + (int64_t)(i0 + j) * tpc) * RMAX + i];
       int g = te.cnt + i;
       if (g < P_MAXREC) {
         pgb_agg e = pgb_agg_combine(te, r->ex);
@@ -661,11 +686,30 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
   PersistShared& sh = *reinterpret_cast<PersistShared*>(smem_raw);
   double* A_sm = reinterpret_cast<double*>(smem_raw + sizeof(PersistShared));
   const int tid = threadIdx.x;
-  const int nb = pd.nb, tpc = pd.tpc;
-  const int chain = blockIdx.x / nb, c = blockIdx.x % nb;
+  const int nb = pd.nb, tpc = pd.tpc, npc = pd.npc;
+  const int chain = blockIdx.x / npc;
   const int64_t N = fd.N, T = fd.T;
   const int nt = fd.nt;
   unsigned int bar_target = 0;
+  // SM-aware rank of this CTA inside its chain: first-resident CTAs of all SMs come first, so that the chain's
+  // blocks (dealt round-robin over ranks) spread evenly over SMs rather than over CTAs
+  if (tid == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const int slot = atomicAdd(&pd.sm_slots[smid & 1023], 1);
+    pd.cta_key[blockIdx.x] = (slot << 12) | (int)(smid & 1023);
+  }
+  grid_barrier(pd.bar, bar_target);
+  int o = 0;
+  {
+    const int mykey = __ldcg(&pd.cta_key[blockIdx.x]);
+    for (int pass = 0; pass < (npc + TPB - 1) / TPB; ++pass) {
+      const int i = pass * TPB + tid;
+      o += __syncthreads_count(i < npc && __ldcg(&pd.cta_key[chain * npc + i]) < mykey);
+    }
+  }
+  const bool lead = (o == 0);  // one designated CTA per chain for the scalar bookkeeping
+#define P_FOR_BLOCKS for (int vi = 0, c = o; c < nb; ++vi, c += npc)
   // section timers (thread 0 of every CTA; SM clock): see pgb_get_phase_cycles
   long long tacc[P_NPROF];
 #pragma unroll
@@ -687,7 +731,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
     double* x0 = fd.xh + (int64_t)chain * T * NX * N;
     const double* xp = fd.xprim + (int64_t)chain * NX * T;
     double lmax = -INFINITY;
-    for (int k = 0; k < tpc; ++k) {
+    P_FOR_BLOCKS for (int k = 0; k < tpc; ++k) {
       const int tile = c * tpc + k;
       if (tile >= nt) break;
       for (int i = 0; i < IPT; ++i) {
@@ -725,23 +769,25 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
     const double m = ordered_unkey(fd.maxkey[chain]);
     const double* lw = fd.lwbuf + (int64_t)chain * N;
     double* e = fd.ebuf + (int64_t)chain * N;
-    TreeAcc acc;
-    acc.init();
-    for (int k = 0; k < tpc; ++k) {
-      const int tile = c * tpc + k;
-      int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
-      double a[4], v[4];
+    P_FOR_BLOCKS {
+      TreeAcc acc;
+      acc.init();
+      for (int k = 0; k < tpc; ++k) {
+        const int tile = c * tpc + k;
+        int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
+        double a[4], v[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = (tile < nt && base + i < N) ? __dsub_rn(lw[base + i], m) : 0.0;
-      vexp<4>(a, v);
+        for (int i = 0; i < 4; ++i) a[i] = (tile < nt && base + i < N) ? __dsub_rn(lw[base + i], m) : 0.0;
+        vexp<4>(a, v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (tile < nt && base + i < N) e[base + i] = v[i];
-        else v[i] = 0.0;
+        for (int i = 0; i < 4; ++i) {
+          if (tile < nt && base + i < N) e[base + i] = v[i];
+          else v[i] = 0.0;
+        }
+        acc.push(block_tree_sum(tree4(v), sh.sm));
       }
-      acc.push(block_tree_sum(tree4(v), sh.sm));
+      if (tid == 0) pe[c] = acc.result();
     }
-    if (tid == 0) pe[c] = acc.result();
   };
   weights_phase();
   grid_barrier(pd.bar, bar_target);
@@ -757,7 +803,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
     {
       const double S1 = block_tree_sum_array(pe, nb, sh.sm);
       const InvDiv ivS1 = make_invdiv(S1);
-      if (c == 0 && tid == 0) {
+      if (lead && tid == 0) {
         fd.maxkey[chain] = 0ull;  // its readers finished before the last barrier
         pd.heavy_cnt[chain] = 0;
         pd.cand[2 * chain] = 0;
@@ -781,6 +827,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
         for (int d = 0; d < NX; ++d) xref[d] = fd.xprim[(int64_t)chain * NX * T + d + NX * t];
         c0 = fd.c0[chain];
       }
+      P_FOR_BLOCKS {
       TreeAcc accw, acca;
       accw.init();
       acca.init();
@@ -844,13 +891,14 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
           }
         }
         double sw = block_tree_sum(tree4(wv), sh.sm);
-        if (tid == 0) sh.tsum_w[k] = sw;
+        if (tid == 0) sh.tsum_w[vi * tpc + k] = sw;
         accw.push(sw);
         if (anc) acca.push(block_tree_sum(tree4(av), sh.sm));
       }
       if (tid == 0) {
         pw[c] = accw.result();
         if (anc) pa[c] = acca.result();
+      }
       }
     }
     P_TICK(1);
@@ -860,31 +908,33 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
     const double S2 = block_tree_sum_array(pw, nb, sh.sm);
     {
       approx_prefix(pw, nb, sh);
-      p_scan_local(fd.main, fd.wbuf, S2, sh.tsum_w, chain, c, nb, tpc, sh, fd.status, fmain);
+      P_FOR_BLOCKS p_scan_local(fd.main, fd.wbuf, S2, sh.tsum_w + vi * tpc, chain, c, nb, tpc, sh, fd.status, fmain);
       P_TICK(3);
       if (anc) {
         const double S3 = block_tree_sum_array(pa, nb, sh.sm);
         const InvDiv ivS3 = make_invdiv(S3);
         double* wa = fd.waN + (int64_t)chain * N;
-        TreeAcc acc;
-        acc.init();
-        for (int k = 0; k < tpc; ++k) {
-          const int tile = c * tpc + k;
-          int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
-          double v[4];
+        P_FOR_BLOCKS {
+          TreeAcc acc;
+          acc.init();
+          for (int k = 0; k < tpc; ++k) {
+            const int tile = c * tpc + k;
+            int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
+            double v[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[i] = 0.0;
-            if (tile < nt && base + i < N) {
-              v[i] = div_inv(wa[base + i], ivS3);
-              wa[base + i] = v[i];
+            for (int i = 0; i < 4; ++i) {
+              v[i] = 0.0;
+              if (tile < nt && base + i < N) {
+                v[i] = div_inv(wa[base + i], ivS3);
+                wa[base + i] = v[i];
+              }
             }
+            double s2 = block_tree_sum(tree4(v), sh.sm);
+            if (tid == 0) sh.tsum_a2[vi * tpc + k] = s2;
+            acc.push(s2);
           }
-          double s2 = block_tree_sum(tree4(v), sh.sm);
-          if (tid == 0) sh.tsum_a2[k] = s2;
-          acc.push(s2);
+          if (tid == 0) pa2[c] = acc.result();
         }
-        if (tid == 0) pa2[c] = acc.result();
       }
       P_TICK(4);
     }
@@ -896,7 +946,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
       P_TICK(6);
       if (tid == 0) {
         sh.sI = *fmain & 1;
-        if (c == 0) fd.main.counters[2 * chain + 1] += 1;
+        if (lead) fd.main.counters[2 * chain + 1] += 1;
       }
       __syncthreads();
       const bool skip = sh.sI != 0;
@@ -910,7 +960,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
       }
       EmitCtx<NX> ec;
       if (!last_only) emit_ctx_init<NX>(ec, fd, chain, t);
-      for (int k = 0; k < tpc && !skip; ++k) {
+      P_FOR_BLOCKS for (int k = 0; k < tpc && !skip; ++k) {
         const int tile = c * tpc + k;
         if (tile >= nt) break;
         double W[4], q[5];
@@ -929,7 +979,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
         approx_prefix(pa2, nb, sh);
         const double ua = fd.utab_anc[(int64_t)chain * T + t].u0[0];  // one draw: u = rand()
         const double delta = 6.0 * ((double)N + 4096.0) * 0x1p-53;
-        p_side_approx(fd.side, fd.waN, S4, sh.tsum_a2, chain, c, tpc, sh, ua, delta, pd.cand + 2 * chain);
+        P_FOR_BLOCKS p_side_approx(fd.side, fd.waN, S4, sh.tsum_a2 + vi * tpc, chain, c, tpc, sh, ua, delta, pd.cand + 2 * chain);
       }
       P_TICK(8);
     }
@@ -947,25 +997,25 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
         __syncthreads();
         const bool amb_any = sh.any_flag != 0;
         const bool amb_me = (pd.cand[2 * chain] == 0) || pd.force_fallback;
-        if (!amb_me && c == 0 && tid == 0) fd.ah[((int64_t)chain * T + t) * N + (N - 1)] = pd.cand[2 * chain + 1];
+        if (!amb_me && lead && tid == 0) fd.ah[((int64_t)chain * T + t) * N + (N - 1)] = pd.cand[2 * chain + 1];
         if (amb_any) {
           // rare: run the exact scan of the ancestor weights for the chains that need it (two extra barriers)
           const double S4 = block_tree_sum_array(pa2, nb, sh.sm);
           approx_prefix(pa2, nb, sh);
-          if (amb_me) p_scan_local(fd.side, fd.waN, S4, sh.tsum_a2, chain, c, nb, tpc, sh, fd.status, fside);
+          if (amb_me) P_FOR_BLOCKS p_scan_local(fd.side, fd.waN, S4, sh.tsum_a2 + vi * tpc, chain, c, nb, tpc, sh, fd.status, fside);
           grid_barrier(pd.bar, bar_target);
           if (amb_me) {
             p_resolve(fd.side, chain, nb, tpc, sh, pd.force_fallback & 1, fside);
             if (tid == 0) {
               sh.sI = *fside & 1;
-              if (c == 0) fd.side.counters[2 * chain + 1] += 1;
+              if (lead) fd.side.counters[2 * chain + 1] += 1;
             }
             __syncthreads();
             const bool skip = sh.sI != 0;
             double dummy = 0.0;
             const pgb_utable* ut = &fd.utab_anc[(int64_t)chain * T + t];
             int32_t* out = fd.ah + ((int64_t)chain * T + t) * N + (N - 1);
-            for (int k = 0; k < tpc && !skip; ++k) {
+            P_FOR_BLOCKS for (int k = 0; k < tpc && !skip; ++k) {
               const int tile = c * tpc + k;
               if (tile >= nt) break;
               double W[4], q[5];
@@ -989,14 +1039,14 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
           const int hc = pd.heavy_cnt[chain];
           double lmax = -INFINITY;
           if (hc > 0 && !(*fmain & 1))
-            p_heavy<NX>(fd, chain, c, nb, t, pd.heavy + (int64_t)chain * P_HEAVY_MAX, hc, &fd.main.pend[chain], lmax);
+            p_heavy<NX>(fd, chain, o, npc, t, pd.heavy + (int64_t)chain * P_HEAVY_MAX, hc, &fd.main.pend[chain], lmax);
           block_max_to_global(lmax, &fd.maxkey[chain], sh.sm);
           grid_barrier(pd.bar, bar_target);
         }
       }
       if (!last_only) weights_phase();
       // re-arm the other parity's flags for the next step (nobody touches them between B1(t) and B1(t+1))
-      if (c == 0 && tid == 0) {
+      if (lead && tid == 0) {
         fd.main.flag[chain + fd.nc * (int)((t + 1) & 1)] = 0;
         fd.side.flag[chain + fd.nc * (int)((t + 1) & 1)] = 0;
       }
@@ -1016,7 +1066,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
       if (sh.any_flag) {
         const int fm = *fmain & 1, fs = anc ? (*fside & 1) : 0;
         const double S4 = (anc && fs) ? block_tree_sum_array(pa2, nb, sh.sm) : 1.0;
-        if (c == 0) {
+        if (lead) {
           if (fm) {
             if (tid == 0) {
               fd.main.pend[chain] = 0;
@@ -1031,7 +1081,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
         }
         grid_barrier(pd.bar, bar_target);
         double lmax = -INFINITY;
-        for (int k = 0; k < tpc; ++k) {
+        P_FOR_BLOCKS for (int k = 0; k < tpc; ++k) {
           const int tile = c * tpc + k;
           if (tile >= nt) break;
           double W[4], q[5];
@@ -1061,7 +1111,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
         }
       }
       // merge the status bits raised by consumer passes that were not redone
-      if (c == 0 && tid == 0) {
+      if (lead && tid == 0) {
         int p = fd.main.pend[chain] | fd.side.pend[chain];
         if (p) atomicOr(&fd.status[chain], p);
         fd.main.pend[chain] = 0;
@@ -1075,6 +1125,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
     for (int i = 0; i < P_NPROF; ++i) pd.prof[(int64_t)blockIdx.x * P_NPROF + i] = tacc[i];
   }
 #undef P_TICK
+#undef P_FOR_BLOCKS
 }
 
 }  // namespace pgb

@@ -13,6 +13,7 @@
 
 namespace pgb {
 
+constexpr int W_MAXNB = 640;               // max CTAs (= blocks) per chain
 constexpr int W_MAXTPC = 16;              // warp-tiles per warp
 constexpr int W_MAXWT = 8 * W_MAXTPC;     // warp-tiles per CTA
 constexpr int W_STAGE = 64;               // complex threads staged per CTA and scan
@@ -29,8 +30,8 @@ struct WShared {
   double wtpfx[W_MAXWT + 1];
   pgb_agg wtagg[W_MAXWT];
   pgb_agg wtex[W_MAXWT + 1];
-  pgb_agg cex[P_MAXNB + 1];
-  double pfx[P_MAXNB + 1];
+  pgb_agg cex[W_MAXNB + 1];
+  double pfx[W_MAXNB + 1];
   pgb_map rf[P_MAXREC];
   double rW[P_MAXREC][4];
   double seeds[P_MAXREC + 1];

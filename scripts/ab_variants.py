@@ -22,7 +22,7 @@ print("%.1f us/step" % (1e3 * best / (T - 1)))
 model = sys.argv[1] if len(sys.argv) > 1 else "known"
 libs = sorted(f for f in os.listdir("pgopt_b200/lib") if f.startswith("libv_"))
 for l in libs:
-    for mode in (2, 1):
+    for mode in [int(m) for m in os.environ.get("AB_MODES", "1").split(",")]:
         env = dict(os.environ, PGOPT_B200_LIB=os.path.abspath(os.path.join("pgopt_b200/lib", l)))
         r = subprocess.run([sys.executable, "-c", code, model, "1048576", "80", str(mode)], env=env, capture_output=True, text=True)
         print(l, "mode", mode, r.stdout.strip(), r.stderr.strip()[-200:])

@@ -29,8 +29,16 @@ def rollout(K=100000, H=41, N=30, cpu_K=300):
     t0 = time.perf_counter()
     out = pg.scenario_rollout(samples, basis, pg.LinearMeasurement(Cm), 0.1, H, u_init=u_init, seed=1)
     dt = time.perf_counter() - t0
+    import ctypes as C
+    from pgopt_b200._lib import lib
+    tms, kms = C.c_double(0), C.c_double(0)
+    lib().pgb_rollout_last_ms(C.byref(tms), C.byref(kms))
+    a_bytes = K * n_x * n_phi * 8
     res = {"metric": "scenario rollout (host buffers in/out, incl. packing + H2D of A)", "K": K, "H": H, "n_x": n_x,
-           "n_phi": n_phi, "seconds": dt, "scenario_steps_per_s": K * H / dt}
+           "n_phi": n_phi, "seconds": dt, "scenario_steps_per_s": K * H / dt, "kernel_ms": kms.value,
+           "transpose_ms": tms.value, "kernel_scenario_steps_per_s": K * H / (kms.value * 1e-3),
+           "kernel_GBps_if_A_streamed_every_step": a_bytes * (H + 1) / (kms.value * 1e-3) / 1e9,
+           "kernel_fp64_tflops": 2.0 * K * (H + 1) * n_x * n_phi / (kms.value * 1e-3) / 1e12}
     try:
         import _oracle as O
         om = O.hilbert_model(4, 1, basis.count, basis.stride, basis.L)
