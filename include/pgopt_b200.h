@@ -165,8 +165,9 @@ int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Ph
 int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q, const double* w_m1,
                 const double* x_m1, const double* u_m1, const double* C, const double* Le, const double* u_init,
                 uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e, double* X, double* Y);
-/* Device time (CUDA events, ms) of the last pgb_rollout call of this process: transposition of A, rollout kernel. */
-int pgb_rollout_last_ms(double* transpose_ms, double* kernel_ms);
+/* Device-side time (CUDA events, ms) of the last pgb_rollout call of this process: allocation + host-to-device copies
+ * of the inputs, and the rollout kernel itself. */
+int pgb_rollout_last_ms(double* h2d_ms, double* kernel_ms);
 
 /* ---- test hooks (not part of the drop-in surface) ---------------------------------------------
  * pgb_test_force_fallback(1) makes every exact scan take the serial-walk fallback path, (2) makes the ancestor

@@ -121,6 +121,30 @@ static void eval_f(const orc_model* m, const double* A, const double* x, const d
   }
 }
 
+/* f(x,u) = PG_samples[k].A * phi(x,u) in the scenario rollout (optimal_control_Ipopt.jl:62,:121).  Julia hands this
+ * product to BLAS gemv, whose summation order is not pinned by the reference; here it is DEFINED as a blocked sum:
+ * the columns are cut into 128 runs of c = ceil(n_phi/128) consecutive columns, run j accumulates
+ * p_j = fma(A[d, i], phi[i], p_j) over its columns in increasing i (empty runs give +0.0), and the 128 partial sums
+ * are combined by the balanced binary tree over j.  (The filter's per-particle product, eval_f above, stays strictly
+ * sequential in i.) */
+#define ORC_ROLL_LANES 128
+static void eval_f_blocked(const orc_model* m, const double* A, const double* x, const double* u, double* phi_tmp,
+                           double* out) {
+  orc_phi(m, x, u, phi_tmp);
+  double part[ORC_ROLL_LANES];
+  const int c = (m->n_phi + ORC_ROLL_LANES - 1) / ORC_ROLL_LANES;
+  for (int d = 0; d < m->n_x; ++d) {
+    for (int j = 0; j < ORC_ROLL_LANES; ++j) {
+      double acc = 0.0;
+      for (int i = j * c; i < (j + 1) * c && i < m->n_phi; ++i) acc = fma(A[d + m->n_x * i], phi_tmp[i], acc);
+      part[j] = acc;
+    }
+    for (int w = 1; w < ORC_ROLL_LANES; w <<= 1)
+      for (int j = 0; j < ORC_ROLL_LANES; j += 2 * w) part[j] = part[j] + part[j + w];
+    out[d] = part[0];
+  }
+}
+
 /* ------------------------------------------------------------------ small dense helpers */
 /* Cholesky, right-looking / outer-product form: every entry (i,j) receives the updates
  * a_ij = fma(-l_ik, l_jk, a_ij) in increasing k — the order a parallel right-looking
@@ -558,7 +582,7 @@ int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const doubl
     status |= orc_systematic_resampling(&w_m1[k * N], N, 1, us, &star);
     if (star < 1) star = 1;
     /* x0 = f(x_m1, u_m1) + rand(mvn)   (:62) */
-    eval_f(m, Ak, &x_m1[(k * N + (star - 1)) * n_x], &u_m1[k * n_u], phi_tmp, f);
+    eval_f_blocked(m, Ak, &x_m1[(k * N + (star - 1)) * n_x], &u_m1[k * n_u], phi_tmp, f);
     stream_normals(&s, PGB_STREAM_ROLL, 0, 1, 0, n_x, z);
     for (int d = 0; d < n_x; ++d) {
       double acc = 0.0;
@@ -582,7 +606,7 @@ int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const doubl
     }
     for (int64_t t = 0; t < H; ++t) { /* :121-122 */
       const double* xt = &X[(k * (H + 1) + t) * n_x];
-      eval_f(m, Ak, xt, &u_init[n_u * t], phi_tmp, f);
+      eval_f_blocked(m, Ak, xt, &u_init[n_u * t], phi_tmp, f);
       for (int d = 0; d < n_x; ++d) X[(k * (H + 1) + t + 1) * n_x + d] = f[d] + v[(k * H + t) * n_x + d];
       for (int o = 0; o < n_y; ++o) {
         double g = 0.0;

@@ -893,11 +893,20 @@ extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const
   return PGB_OK;
 }
 
-static float g_rollout_ms[2] = {0.f, 0.f};  // device time of the last pgb_rollout: {transpose of A, rollout kernel}
+static float g_rollout_ms[2] = {0.f, 0.f};  // device time of the last pgb_rollout: {H2D copies, rollout kernel}
 
+template <int NX, int NI>
+static cudaError_t launch_rollout_ni(const FilterDev& fd, const RolloutDev& rd, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(k_rollout<NX, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_rollout<NX, NI><<<(unsigned)rd.K, R_TPB, smem>>>(fd, rd);
+  return cudaGetLastError();
+}
+// n_phi <= 128: one register-resident column of A per thread; otherwise five (n_phi <= 640 entirely in registers,
+// e.g. 5^4 = 625), any further columns are read from L2
 template <int NX>
-static void launch_rollout(const FilterDev& fd, const RolloutDev& rd) {
-  k_rollout<NX><<<(unsigned)((rd.K + 127) / 128), 128>>>(fd, rd);
+static cudaError_t launch_rollout(const FilterDev& fd, const RolloutDev& rd, size_t smem) {
+  return fd.n_phi <= R_TPB ? launch_rollout_ni<NX, 1>(fd, rd, smem) : launch_rollout_ni<NX, 5>(fd, rd, smem);
 }
 
 extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q,
@@ -931,9 +940,14 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   rd.K = K; rd.H = H; rd.N = N; rd.seed = seed; rd.k_offset = k_offset;
   for (int i = 0; i < ny * ny; ++i) rd.Le[i] = Le[i];
   const int m = nx * np;
-  double *dA, *dAt, *dQ, *dw, *dx, *dum, *dui;
+  const size_t smem = sizeof(RolloutShared) + ((size_t)H * (nx + ny + nu) + (size_t)(N < R_WSTAGE ? N : R_WSTAGE)) * 8;
+  if (smem > 200 * 1024 || K > 0x7fffffffLL)
+    return set_err(nullptr, PGB_ERR_INVALID, "rollout: horizon H = %lld (or K) too large", (long long)H);
+  double *dA, *dQ, *dw, *dx, *dum, *dui;
+  cudaEvent_t ev[3];
+  for (auto& evt : ev) CK(h, cudaEventCreate(&evt));
+  CK(h, cudaEventRecord(ev[0], 0));
   CK(h, dalloc(h, &dA, (size_t)K * m, false));
-  CK(h, dalloc(h, &dAt, (size_t)K * m, false));
   CK(h, dalloc(h, &dQ, (size_t)K * nx * nx, false));
   CK(h, dalloc(h, &dw, (size_t)K * N, false));
   CK(h, dalloc(h, &dx, (size_t)K * nx * N, false));
@@ -951,19 +965,14 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   if (e) CK(h, dalloc(h, &rd.e, (size_t)K * H * ny, false));
   if (X) CK(h, dalloc(h, &rd.X, (size_t)K * (H + 1) * nx, false));
   if (Y) CK(h, dalloc(h, &rd.Y, (size_t)K * H * ny, false));
-  cudaEvent_t ev[3];
-  for (auto& evt : ev) CK(h, cudaEventCreate(&evt));
-  CK(h, cudaEventRecord(ev[0], 0));
-  k_transpose_A<<<dim3((unsigned)((K + 31) / 32), (unsigned)((m + 31) / 32)), dim3(32, 8)>>>(dA, dAt, K, m);
   CK(h, cudaEventRecord(ev[1], 0));
-  rd.At = dAt; rd.Q = dQ; rd.w_m1 = dw; rd.x_m1 = dx; rd.u_m1 = dum; rd.u_init = dui;
+  rd.A = dA; rd.Q = dQ; rd.w_m1 = dw; rd.x_m1 = dx; rd.u_m1 = dum; rd.u_init = dui;
   switch (nx) {
-    case 1: launch_rollout<1>(fd, rd); break;
-    case 2: launch_rollout<2>(fd, rd); break;
-    case 3: launch_rollout<3>(fd, rd); break;
-    default: launch_rollout<4>(fd, rd); break;
+    case 1: CK(h, launch_rollout<1>(fd, rd, smem)); break;
+    case 2: CK(h, launch_rollout<2>(fd, rd, smem)); break;
+    case 3: CK(h, launch_rollout<3>(fd, rd, smem)); break;
+    default: CK(h, launch_rollout<4>(fd, rd, smem)); break;
   }
-  CK(h, cudaGetLastError());
   CK(h, cudaEventRecord(ev[2], 0));
   CK(h, cudaDeviceSynchronize());
   cudaEventElapsedTime(&g_rollout_ms[0], ev[0], ev[1]);
@@ -980,8 +989,8 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   return PGB_OK;
 }
 
-extern "C" int pgb_rollout_last_ms(double* transpose_ms, double* kernel_ms) {
-  if (transpose_ms) *transpose_ms = g_rollout_ms[0];
+extern "C" int pgb_rollout_last_ms(double* h2d_ms, double* kernel_ms) {
+  if (h2d_ms) *h2d_ms = g_rollout_ms[0];
   if (kernel_ms) *kernel_ms = g_rollout_ms[1];
   return PGB_OK;
 }

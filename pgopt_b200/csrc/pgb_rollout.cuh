@@ -1,18 +1,28 @@
 // pgb_rollout.cuh — scenario sampling + forward rollout for solve_PG_OCP
 // (Julia/src/optimal_control_Ipopt.jl:47-64 x_vec_0, :67-74 v_vec, :77-83 e_vec, :114-125 X_init/Y_init).
 //
-// One thread per scenario k keeps the evaluation order of the oracle (bit-exact), and the model
-// matrices are read through a scenario-fastest transposed copy At[i][d][k] so that the K-wide loads
-// of A_k coalesce.  Streams: scenario k uses Philox chain id k_offset + k, purpose ROLL with
-// t = 0 (star uniform), 1 (x0 noise), 2 (process noise, j = step), 3 (measurement noise, j = step).
+// One 128-thread CTA per scenario k.  The scenario's model matrix A_k (n_x x n_phi, 20 KB at n_phi = 625) is read
+// from HBM exactly once into REGISTERS: thread j keeps the c = ceil(n_phi/128) consecutive columns [j*c, (j+1)*c).
+// Every step of the horizon is then
+//   sines of the Hilbert basis (one per thread) -> phi_i = prod_k t_k[dig_k(i)] for the thread's columns (consecutive
+//   columns share all digits but the last: one prefix product + one multiplication per column) ->
+//   per-thread partial sums fma(A[d,i], phi_i, .) -> balanced tree over the 128 threads (shuffles + 4 warp sums)
+// which is bit for bit the blocked product the oracle defines for the rollout (oracle/pg_oracle.c eval_f_blocked).
+// All process / measurement noise of the horizon is drawn up front (it does not depend on the state), one step per
+// thread.  Streams: scenario k uses Philox chain id k_offset + k, purpose ROLL with t = 0 (star uniform),
+// 1 (x0 noise), 2 (process noise, j = step), 3 (measurement noise, j = step).
+// HBM traffic per scenario: A_k once + w_m1 + one column of x_m1 + outputs — the algorithmic minimum.
 #pragma once
 #include "pgb_filter.cuh"
 
 namespace pgb {
 
+constexpr int R_TPB = 128;  // threads per scenario (= number of interleaved partial sums of the blocked product)
+constexpr int R_WSTAGE = 1024;  // weights of the last filtering step staged in shared memory (the rest stay in L2)
+
 struct RolloutDev {
   int64_t K, H, N;
-  const double* At;    // [n_phi][n_x][K]   transposed A
+  const double* A;     // [K][n_x*n_phi]   column-major n_x x n_phi per scenario
   const double* Q;     // [K][n_x*n_x]
   const double* w_m1;  // [K][N]
   const double* x_m1;  // [K][n_x*N]  column-major n_x x N per scenario
@@ -25,158 +35,320 @@ struct RolloutDev {
   int* status;         // [1]
 };
 
-__global__ void k_transpose_A(const double* __restrict__ A, double* __restrict__ At, int64_t K, int m) {
-  // A: [K][m] -> At: [m][K]
-  __shared__ double tile[32][33];
-  int64_t k0 = (int64_t)blockIdx.x * 32;
-  int i0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int64_t k = k0 + r;
-    int i = i0 + threadIdx.x;
-    tile[r][threadIdx.x] = (k < K && i < m) ? A[k * m + i] : 0.0;
+struct RolloutShared {
+  double tk[PGB_MAX_Z_][MAXC];  // scaled sines of the current state, per input dimension
+  double red[R_TPB / 32][4];    // warp partial sums
+  double x[4];                  // current state
+  double x0n[4];                // noise of the initial state
+  double phi_known[5];
+  int sine_dim[PGB_MAX_Z_ * MAXC], sine_j[PGB_MAX_Z_ * MAXC];  // which sine thread s evaluates
+  int n_sines;
+};
+
+// Mixed-radix digits of basis-function index i (last dimension fastest): dimensions 0..nz-2 in 4-bit fields from
+// bit 0 (at most 7 of them), the last dimension's digit in bits 28..31.
+__device__ __forceinline__ unsigned int rollout_digits(const FilterDev& fd, int i) {
+  const int nz = fd.n_z;
+  int rem = i;
+  unsigned int g = (unsigned int)(rem % fd.hg_count[nz - 1]) << 28;
+  rem /= fd.hg_count[nz - 1];
+  for (int kk = nz - 2; kk >= 0; --kk) {
+    g |= (unsigned int)(rem % fd.hg_count[kk]) << (4 * kk);
+    rem /= fd.hg_count[kk];
   }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int i = i0 + r;
-    int64_t k = k0 + threadIdx.x;
-    if (k < K && i < m) At[(int64_t)i * K + k] = tile[threadIdx.x][r];
+  return g;
+}
+
+// 2*NP standard normals of the ROLL stream (chain cid, sweep 0, time index t, blocks j0 .. j0+NP-1): the same values
+// as pgb_normal_pair(pgb_stream_block(...)), through the branch-free vector routines.
+template <int NP>
+__device__ __forceinline__ void rollout_normals(uint64_t seed, uint32_t cid, uint32_t t, uint32_t j0, double (&z)[4]) {
+  pgb_u32x4 ctr[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    ctr[p].v[0] = j0 + p;
+    ctr[p].v[1] = t;
+    ctr[p].v[2] = 0u;
+    ctr[p].v[3] = ((uint32_t)PGB_STREAM_ROLL << 24) | (cid & 0x00ffffffu);
+  }
+  vphilox_wide<NP>(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+  double z0[NP], z1[NP];
+  vnormal_pairs_wide<NP>(ctr, z0, z1);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    z[2 * p] = z0[p];
+    z[2 * p + 1] = z1[p];
   }
 }
 
-// A_k * phi(x,u) with A read from the transposed copy (stride K between consecutive entries)
+// Run index of a thread: lane bits reversed, so that the shuffle distances 16, 8, 4, 2, 1 pair runs j and j^1, then
+// j^2, ... — the balanced binary tree over j = 0..127 with adjacent runs added first, as the oracle defines it.
+__device__ __forceinline__ int rollout_run(int tid) { return (tid & ~31) | (int)(__brev((unsigned int)(tid & 31)) >> 27); }
+
+// Role index of a thread: the warps of a CTA are rotated by the block index, so that the warp doing the serial work
+// (sines, state update, start-up) does not land on the same SM sub-partition (warp id mod 4) for every resident CTA.
+__device__ __forceinline__ int rollout_role(int tid) { return (tid + 32 * (int)(blockIdx.x & 3u)) & (R_TPB - 1); }
+
+__device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+// Tree sum over the warp's 32 runs of NX values per thread with 6 (instead of 20) shuffles for NX = 4: the first
+// levels exchange only the half of the values the partner keeps.  On return v[0] of lane 8*d (NX > 2) or 16*d
+// (NX = 2) holds the warp's sum of component d.
 template <int NX>
-__device__ __forceinline__ void eval_F_strided(const FilterDev& fd, const double* __restrict__ At, int64_t K,
-                                               const double x[NX], const double* __restrict__ u, double F[NX]) {
-  double acc[NX];
+__device__ __forceinline__ double warp_tree_multi(const double (&v)[NX], int lane) {
+  if (NX == 1) {
+    double b = v[0];
 #pragma unroll
-  for (int d = 0; d < NX; ++d) acc[d] = 0.0;
-  if (fd.basis == 0) {
-    double phi[5];
-    phi[0] = __dmul_rn(0.1, x[0]);
-    phi[1] = __dmul_rn(0.1, x[NX > 1 ? 1 : 0]);
-    phi[2] = u[0];
-    phi[3] = __dmul_rn(__dmul_rn(0.01, pgb_cos(__dmul_rn(3.0, x[0]))), x[NX > 1 ? 1 : 0]);
-    phi[4] = __dmul_rn(__dmul_rn(0.1, pgb_sin(__dmul_rn(2.0, x[NX > 1 ? 1 : 0]))), u[0]);
+    for (int o = 16; o > 0; o >>= 1) b = __dadd_rn(b, shfl_xor_d(b, o));
+    return b;
+  } else if (NX == 2) {
+    const bool hi = lane & 16;
+    double b = __dadd_rn(hi ? v[1] : v[0], shfl_xor_d(hi ? v[0] : v[1], 16));
 #pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-      for (int d = 0; d < NX; ++d) acc[d] = __fma_rn(At[(int64_t)(i * NX + d) * K], phi[i], acc[d]);
+    for (int o = 8; o > 0; o >>= 1) b = __dadd_rn(b, shfl_xor_d(b, o));
+    return b;
   } else {
-    const int nz = fd.n_z;
-    double tk[PGB_MAX_Z_][MAXC];
-    for (int k = 0; k < nz; ++k) {
-      double zk = (k < fd.n_u) ? u[k] : x[k - fd.n_u];
-      double zl = __dadd_rn(zk, fd.hg_L[k]);
-      for (int j = 0; j < fd.hg_count[k]; ++j)
-        tk[k][j] = __dmul_rn(fd.hg_lsi[k], pgb_sin(__dmul_rn(fd.hg_pij2l[k][j], zl)));
-    }
-    int dig[PGB_MAX_Z_];
-    double pp[PGB_MAX_Z_];
-    for (int k = 0; k < nz; ++k) dig[k] = 0;
-    int from = 0;
-    for (int i = 0; i < fd.n_phi; ++i) {
-      for (int k = from; k < nz; ++k) pp[k] = __dmul_rn(k ? pp[k - 1] : 1.0, tk[k][dig[k]]);
-      double p = pp[nz - 1];
+    const double v3 = (NX > 3) ? v[NX > 3 ? 3 : 0] : 0.0;
+    const bool hi = lane & 16;
+    const double a0 = __dadd_rn(hi ? v[2] : v[0], shfl_xor_d(hi ? v[0] : v[2], 16));
+    const double a1 = __dadd_rn(hi ? v3 : v[1], shfl_xor_d(hi ? v[1] : v3, 16));
+    const bool hi2 = lane & 8;
+    double b = __dadd_rn(hi2 ? a1 : a0, shfl_xor_d(hi2 ? a0 : a1, 8));
 #pragma unroll
-      for (int d = 0; d < NX; ++d) acc[d] = __fma_rn(At[(int64_t)(i * NX + d) * K], p, acc[d]);
-      int k = nz - 1;
-      while (k >= 0 && ++dig[k] == fd.hg_count[k]) dig[k--] = 0;
-      from = k < 0 ? 0 : k;
-    }
+    for (int o = 4; o > 0; o >>= 1) b = __dadd_rn(b, shfl_xor_d(b, o));
+    return b;
   }
-#pragma unroll
-  for (int d = 0; d < NX; ++d) F[d] = acc[d];
 }
 
-template <int NX>
-__global__ void __launch_bounds__(128) k_rollout(FilterDev fd, RolloutDev rd) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= rd.K) return;
+// F = A_k * phi(x, u) in the blocked order; component d of the result is returned to thread d (< NX) only.
+// Areg: the thread's columns of A_k.  Contains two __syncthreads(); the caller must place one more before the
+// next call (sh.red / sh.tk / sh.x are reused).
+template <int NX, int NI>
+__device__ __forceinline__ void rollout_eval_F(const FilterDev& fd, RolloutShared& sh, const double (&Areg)[NI][NX],
+                                               const double* __restrict__ Ag, int c, const unsigned int (&dig)[NI],
+                                               const double* __restrict__ u, double& Fd) {
+  const int tid = threadIdx.x, run = rollout_run(tid), vt = rollout_role(tid);
+  double part[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) part[d] = 0.0;
+  if (fd.basis == 0) {
+    // examples/PG_OCP_known_basis_functions_Altro.jl:34 (five functions; thread i < 5 owns column i)
+    if (run < 5) {
+      const double x0 = sh.x[0], x1 = sh.x[NX > 1 ? 1 : 0];
+      double p;
+      if (run == 0) p = __dmul_rn(0.1, x0);
+      else if (run == 1) p = __dmul_rn(0.1, x1);
+      else if (run == 2) p = u[0];
+      else if (run == 3) p = __dmul_rn(__dmul_rn(0.01, pgb_cos(__dmul_rn(3.0, x0))), x1);
+      else p = __dmul_rn(__dmul_rn(0.1, pgb_sin(__dmul_rn(2.0, x1))), u[0]);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) part[d] = __fma_rn(Areg[0][d], p, 0.0);
+    }
+  } else {
+    // Hilbert-space basis (examples/PG_OCP_generic_basis_functions_Altro.jl:85-99): one scaled sine per thread
+    if (vt < sh.n_sines) {
+      const int k = sh.sine_dim[vt], j = sh.sine_j[vt];
+      const double zk = (k < fd.n_u) ? u[k] : sh.x[k - fd.n_u];
+      const double zl = __dadd_rn(zk, fd.hg_L[k]);
+      // branch-free sine (the scalar routine's quadrant switch would serialise the warp's lanes); same bits
+      const double arg[1] = {__dmul_rn(fd.hg_pij2l[k][j], zl)};
+      double sn[1], cs[1];
+      vsincos_wide<1>(arg, sn, cs);
+      sh.tk[k][j] = __dmul_rn(fd.hg_lsi[k], sn[0]);
+    }
+    __syncthreads();
+    const int nz = fd.n_z, n_phi = fd.n_phi;
+    const double* tl = sh.tk[nz - 1];
+    // product over the dimensions 0..nz-2 (digits 4 bits each, from bit 0), in the oracle's left-to-right order
+    auto prefix = [&](unsigned int g) {
+      double p = 1.0;
+#pragma unroll
+      for (int k = 0; k < PGB_MAX_Z_ - 1; ++k)
+        if (k < nz - 1) p = __dmul_rn(p, sh.tk[k][(g >> (4 * k)) & 15u]);
+      return p;
+    };
+    const int i0 = run * c;
+    double pre = prefix(dig[0]);
+#pragma unroll
+    for (int m = 0; m < NI; ++m) {
+      // consecutive columns share every digit but the last one until the last dimension wraps; the vote keeps the
+      // recomputation behind a real (warp-uniform) branch instead of predicated-off instructions
+      const bool live = (m < c && i0 + m < n_phi);
+      if (m > 0) {
+        const bool wrap = live && (dig[m] & 0x0fffffffu) != (dig[m - 1] & 0x0fffffffu);
+        if (__any_sync(0xffffffffu, wrap)) {
+          const double pn = prefix(dig[m]);
+          if (wrap) pre = pn;
+        }
+      }
+      if (live) {
+        const double p = __dmul_rn(pre, tl[dig[m] >> 28]);
+#pragma unroll
+        for (int d = 0; d < NX; ++d) part[d] = __fma_rn(Areg[m][d], p, part[d]);
+      }
+    }
+    // columns beyond the register-resident ones (c > NI): A from global memory (L2), digits on the fly
+    for (int m = NI; m < c && i0 + m < n_phi; ++m) {
+      const unsigned int g = rollout_digits(fd, i0 + m);
+      const double p = __dmul_rn(prefix(g), tl[g >> 28]);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) part[d] = __fma_rn(Ag[(int64_t)NX * (i0 + m) + d], p, part[d]);
+    }
+  }
+  // balanced tree over the 128 partial sums: inside the warp by shuffles, then (w0 + w1) + (w2 + w3)
+  const int w = tid >> 5, l = tid & 31;
+  const double tot = warp_tree_multi<NX>(part, l);
+  constexpr int LSTEP = (NX == 1) ? 32 : (NX == 2 ? 16 : 8);  // lane LSTEP*d holds component d
+  if ((l % LSTEP) == 0 && l / LSTEP < NX) sh.red[w][l / LSTEP] = tot;
+  __syncthreads();
+  if (vt < NX) Fd = __dadd_rn(__dadd_rn(sh.red[0][vt], sh.red[1][vt]), __dadd_rn(sh.red[2][vt], sh.red[3][vt]));
+}
+
+#ifndef PGB_ROLLOUT_MINBLOCKS
+#define PGB_ROLLOUT_MINBLOCKS 6
+#endif
+template <int NX, int NI>
+__global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const __grid_constant__ FilterDev fd,
+                                                   const __grid_constant__ RolloutDev rd) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RolloutShared& sh = *reinterpret_cast<RolloutShared*>(smem_raw);
+  double* vs = reinterpret_cast<double*>(smem_raw + sizeof(RolloutShared));  // [H][NX] process noise
+  const int tid = threadIdx.x, vt = rollout_role(tid);
+  const int64_t k = blockIdx.x;
   const int64_t K = rd.K, H = rd.H, N = rd.N;
-  const int ny = fd.n_y, nu = fd.n_u;
+  (void)K;
+  const int ny = fd.n_y, nu = fd.n_u, n_phi = fd.n_phi, nz = fd.n_z;
+  double* es = vs + H * NX;  // [H][ny] measurement noise
+  double* us = es + H * ny;  // [H][nu] planned inputs u_init (read once, not once per step from L2)
+  double* ws = us + H * nu;  // [min(N, R_WSTAGE)] staged weights w_m1 (coalesced load; thread 0 walks them serially)
   const uint32_t cid = rd.k_offset + (uint32_t)k;
-  // chol(Q_k)
-  double Lq[16];
+  const double* Ag = rd.A + k * (int64_t)NX * n_phi;
+
+  // ---- A_k -> registers: thread j owns the c consecutive columns [j*c, (j+1)*c)
+  const int c = (n_phi + R_TPB - 1) / R_TPB;
+  double Areg[NI][NX];
+#pragma unroll
+  for (int m = 0; m < NI; ++m) {
+    const int i = rollout_run(tid) * c + m;
+#pragma unroll
+    for (int d = 0; d < NX; ++d) Areg[m][d] = (m < c && i < n_phi) ? Ag[(int64_t)NX * i + d] : 0.0;
+  }
+  unsigned int dig[NI];
+#pragma unroll
+  for (int m = 0; m < NI; ++m) dig[m] = (fd.basis != 0 && m < c && rollout_run(tid) * c + m < n_phi) ? rollout_digits(fd, rollout_run(tid) * c + m) : 0u;
+  if (vt == 0) {
+    int s = 0;
+    if (fd.basis != 0)
+      for (int kk = 0; kk < nz; ++kk)
+        for (int j = 0; j < fd.hg_count[kk]; ++j) {
+          sh.sine_dim[s] = kk;
+          sh.sine_j[s] = j;
+          ++s;
+        }
+    sh.n_sines = s;
+  }
+  for (int64_t i = tid; i < H * nu; i += R_TPB) us[i] = rd.u_init[i];
+  const int64_t nstage = N < R_WSTAGE ? N : R_WSTAGE;
+  for (int64_t i = tid; i < nstage; i += R_TPB) ws[i] = rd.w_m1[k * N + i];
+  // ---- chol(Q_k) (every thread; n_x <= 4)
+  double Lq[NX * NX];
+#pragma unroll
   for (int i = 0; i < NX * NX; ++i) Lq[i] = rd.Q[k * NX * NX + i];
-  if (small_chol(Lq, NX)) {
-    atomicOr(rd.status, 16);
+  const int notpd = small_chol(Lq, NX);
+  if (notpd) {
+    if (vt == 0) atomicOr(rd.status, 16);
     return;
   }
-  // star = systematic_resampling(w_m1, 1)  (:58): W = w/sum(w) (tree), first n with q_n >= u
-  const double* w = rd.w_m1 + k * N;
-  double st[40];
-  int sp = 0;
-  int64_t P = 1;
-  while (P < N) P <<= 1;
-  for (int64_t i = 0; i < P; ++i) {
-    double xv = (i < N) ? w[i] : 0.0;
-    int merges = __ffsll((long long)(i + 1)) - 1;
-    for (int m = 0; m < merges; ++m) xv = __dadd_rn(st[--sp], xv);
-    st[sp++] = xv;
+  // x0 noise (:62): drawn by thread 0, added by threads d < NX after the first evaluation of f
+  if (vt == 0) {
+    double z[4];
+    rollout_normals<(NX + 1) / 2>(rd.seed, cid, 1, 0u, z);
+#pragma unroll
+    for (int d = 0; d < NX; ++d) {
+      double acc = 0.0;
+#pragma unroll
+      for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
+      sh.x0n[d] = acc;
+    }
   }
-  const double S = st[0];
-  pgb_u32x4 b = pgb_stream_block(rd.seed, PGB_STREAM_ROLL, cid, 0, 0, 0);
-  const double us = pgb_u53_halfopen(b.v[0], b.v[1]);
-  int64_t star = 0;
-  {
+  // ---- noise of the whole horizon, one step per thread:  v_vec[:, t, k] (:72), e_vec[:, t, k] (:81)
+  for (int64_t t = vt; t < H; t += R_TPB) {
+    double z[4];
+    rollout_normals<(NX + 1) / 2>(rd.seed, cid, 2, (uint32_t)(t * ((NX + 1) / 2)), z);
+    for (int d = 0; d < NX; ++d) {
+      double acc = 0.0;
+      for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
+      vs[t * NX + d] = acc;
+      if (rd.v) rd.v[(k * H + t) * NX + d] = acc;
+    }
+    const int npairs = (ny + 1) / 2;
+    if (npairs == 1) rollout_normals<1>(rd.seed, cid, 3, (uint32_t)t, z);
+    else rollout_normals<2>(rd.seed, cid, 3, (uint32_t)(t * 2), z);
+    for (int o = 0; o < ny; ++o) {
+      double acc = 0.0;
+      for (int e2 = 0; e2 <= o; ++e2) acc = __fma_rn(rd.Le[o + ny * e2], z[e2], acc);
+      es[t * ny + o] = acc;
+      if (rd.e) rd.e[(k * H + t) * ny + o] = acc;
+    }
+  }
+  // ---- star = systematic_resampling(w_m1, 1) (:58): W = w/sum(w) (tree), first n with q_n >= u   (thread 0)
+  __syncthreads();
+  if (vt == 0) {
+    const double* wg = rd.w_m1 + k * N;
+#define R_W(i) ((i) < nstage ? ws[(i)] : wg[(i)])
+    double st[40];
+    int sp = 0;
+    int64_t P = 1;
+    while (P < N) P <<= 1;
+    for (int64_t i = 0; i < P; ++i) {
+      double xv = (i < N) ? R_W(i) : 0.0;
+      int merges = __ffsll((long long)(i + 1)) - 1;
+      for (int m = 0; m < merges; ++m) xv = __dadd_rn(st[--sp], xv);
+      st[sp++] = xv;
+    }
+    const double S = st[0];
+    pgb_u32x4 b = pgb_stream_block(rd.seed, PGB_STREAM_ROLL, cid, 0, 0, 0);
+    const double us = pgb_u53_halfopen(b.v[0], b.v[1]);
     double q = 0.0;
     int64_t n = 0;
     while (q < us) {
       n = n + 1;
       if (n > N) { atomicOr(rd.status, 1); n = N; break; }
-      q = __dadd_rn(q, __ddiv_rn(w[n - 1], S));
+      q = __dadd_rn(q, __ddiv_rn(R_W(n - 1), S));
     }
+#undef R_W
     if (n == 0) { atomicOr(rd.status, 2); n = 1; }
-    star = n - 1;
+    const int64_t star = n - 1;
+    for (int d = 0; d < NX; ++d) sh.x[d] = rd.x_m1[(k * N + star) * NX + d];
   }
-  double x[NX], F[NX], z[4];
-  for (int d = 0; d < NX; ++d) x[d] = rd.x_m1[(k * N + star) * NX + d];
-  const double* At = rd.At + k;
-  // x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62)
-  eval_F_strided<NX>(fd, At, K, x, rd.u_m1 + k * nu, F);
-  philox_normals<NX>(rd.seed, cid, 0, PGB_STREAM_ROLL, 1, 0, z);
-  for (int d = 0; d < NX; ++d) {
-    double acc = 0.0;
-    for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
-    x[d] = __dadd_rn(F[d], acc);
-    if (rd.x0) rd.x0[k * NX + d] = x[d];
-    if (rd.X) rd.X[(k * (H + 1)) * NX + d] = x[d];
+  __syncthreads();
+  // ---- x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62)
+  double Fd = 0.0;
+  rollout_eval_F<NX, NI>(fd, sh, Areg, Ag, c, dig, rd.u_m1 + k * nu, Fd);
+  if (vt < NX) {
+    const double xv = __dadd_rn(Fd, sh.x0n[vt]);
+    sh.x[vt] = xv;
+    if (rd.x0) rd.x0[k * NX + vt] = xv;
+    if (rd.X) rd.X[(k * (H + 1)) * NX + vt] = xv;
   }
+  __syncthreads();
+  // ---- horizon: Y[t] = g(X[t]) + e (:122), X[t+1] = f(X[t], u_t) + v (:121)
   for (int64_t t = 0; t < H; ++t) {
-    double vv[NX], ee[4];
-    philox_normals<NX>(rd.seed, cid, 0, PGB_STREAM_ROLL, 2, t, z);  // v_vec[:, t, k]  (:72)
-    for (int d = 0; d < NX; ++d) {
-      double acc = 0.0;
-      for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
-      vv[d] = acc;
-      if (rd.v) rd.v[(k * H + t) * NX + d] = acc;
-    }
-    {  // e_vec[:, t, k]  (:81)
-      const int npairs = (ny + 1) / 2;
-      for (int p = 0; p < npairs; ++p) {
-        double z0, z1;
-        pgb_normal_pair(pgb_stream_block(rd.seed, PGB_STREAM_ROLL, cid, 0, 3, (uint32_t)(t * npairs + p)), &z0, &z1);
-        z[2 * p] = z0;
-        if (2 * p + 1 < ny) z[2 * p + 1] = z1;
-      }
+    if (vt == 32 && rd.Y) {  // a lane of the next warp: the first role warp is busy with the sines
       for (int o = 0; o < ny; ++o) {
-        double acc = 0.0;
-        for (int e2 = 0; e2 <= o; ++e2) acc = __fma_rn(rd.Le[o + ny * e2], z[e2], acc);
-        ee[o] = acc;
-        if (rd.e) rd.e[(k * H + t) * ny + o] = acc;
+        double g = 0.0;
+#pragma unroll
+        for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[o + ny * d], sh.x[d], g);
+        rd.Y[(k * H + t) * ny + o] = __dadd_rn(g, es[t * ny + o]);
       }
     }
-    // Y[t] = g(X[t]) + e (:122), X[t+1] = f(X[t], u_t) + v (:121)
-    for (int o = 0; o < ny; ++o) {
-      double g = 0.0;
-      for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[o + ny * d], x[d], g);
-      if (rd.Y) rd.Y[(k * H + t) * ny + o] = __dadd_rn(g, ee[o]);
+    rollout_eval_F<NX, NI>(fd, sh, Areg, Ag, c, dig, us + (int64_t)nu * t, Fd);
+    if (vt < NX) {
+      const double xv = __dadd_rn(Fd, vs[t * NX + vt]);
+      sh.x[vt] = xv;
+      if (rd.X) rd.X[(k * (H + 1) + t + 1) * NX + vt] = xv;
     }
-    eval_F_strided<NX>(fd, At, K, x, rd.u_init + (int64_t)nu * t, F);
-    for (int d = 0; d < NX; ++d) {
-      x[d] = __dadd_rn(F[d], vv[d]);
-      if (rd.X) rd.X[(k * (H + 1) + t + 1) * NX + d] = x[d];
-    }
+    __syncthreads();
   }
 }
 
