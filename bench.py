@@ -31,6 +31,10 @@ sys.path.insert(0, ROOT)
 
 BYTES_PER_PARTICLE_STEP = lambda n_x: 16 * n_x + 20      # x r+w, w r+w, Int32 ancestor
 FLOPS_PER_PARTICLE_STEP = {"generic": 1250.0, "known": 100.0}
+# dram__bytes_read.sum + dram__bytes_write.sum of k_sweep_persistent per particle-step, from the committed `ncu --set full`
+# captures at N = 2^20, T = 24 (profiles/r01_persistent_generic_N2p20.md, profiles/r01_ncu_persistent_v1_known_N2p20.md)
+NCU_DRAM_BYTES_PER_PARTICLE_STEP = {"generic": (2.527836e9 + 282.65472e6) / (23 * 2 ** 20),
+                                    "known": (1.962611e9 + 61.51808e6) / (23 * 2 ** 20)}
 
 
 # ------------------------------------------------------------------------------------------- workload
@@ -294,7 +298,10 @@ def run_gpu(args):
             "gpu_launches": int(n1.value - n0.value),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_DRAM_BYTES_PER_PARTICLE_STEP[args.model] * N * (T - 1) / 1e9 if N == 2 ** 20 else None,
+                         "traffic_unit": "GB per launch (ncu DRAM bytes per particle-step at T=24, x this launch's particle-steps); "
+                                         "above the algorithmic bytes because the ~100 MB of rolling per-step buffers are written "
+                                         "back from L2 every step", "peak_source": peak_src,
                          "kernel": "k_sweep_persistent: one cooperative launch = one whole conditional sweep (T-1 steps x 4 grid barriers); "
                                    "%d launches per sweep in total" % ((n1.value - n0.value) // max(1, args.steps)),
                          "algorithmic_bytes_per_particle_step": bps,
@@ -311,10 +318,74 @@ def run_gpu(args):
         }
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
     eng.close()
+    eng = None
+    if rank == 0:
+        if world == 1 and not args.no_secondary:
+            try:
+                out["secondary"] = secondary_measurements()
+            except Exception as e:  # never let the side measurements take the headline line down
+                out["secondary"] = {"error": repr(e)}
+        print(json.dumps(out))
     if dist:
         dist.destroy_process_group()
+
+
+def secondary_measurements():
+    """The other SURVEY.md section-8 rows, bounded: scenario rollout at the BASELINE.json configs[4] shape
+    (K scaled to 20000) and chain-batched PG sweeps at the configs[3] shape (8 chains per GPU, one sweep)."""
+    import pgopt_b200 as pg
+    from pgopt_b200._lib import lib
+    res = {}
+    rng = np.random.default_rng(0)
+    K, H, Np = 20000, 41, 30
+    basis = pg.HilbertGPBasis([1, 5, 5, 5, 5], [4.0, 5.0, 6.0, 7.0, 8.0])  # n_x = 4, n_u = 1, n_phi = 625
+    n_x, n_phi = 4, basis.n_phi
+    A = rng.normal(0, 0.05, (K, n_x, n_phi))
+    B = rng.normal(0, 0.1, (K, n_x, n_x))
+    Q = B @ np.transpose(B, (0, 2, 1)) + 0.05 * np.eye(n_x)
+    w = rng.uniform(size=(K, Np))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, Np, n_x))
+    samples = [pg.PG_sample(A[k], Q[k], w[k], x[k].T, np.zeros(1)) for k in range(K)]
+    Cm = np.zeros((1, n_x))
+    Cm[0, 0] = 1.0
+    u_init = np.sin(np.arange(H))[None, :]
+    for _ in range(2):  # the first call pays the module load
+        t0 = time.perf_counter()
+        pg.scenario_rollout(samples, basis, pg.LinearMeasurement(Cm), 0.1, H, u_init=u_init, seed=1)
+        dt = time.perf_counter() - t0
+    h2d, kms = C.c_double(0), C.c_double(0)
+    lib().pgb_rollout_last_ms(C.byref(h2d), C.byref(kms))
+    bytes_alg = K * 8 * (n_x * n_phi + n_x * n_x + Np + n_x + 1 + (2 * H + 2) * n_x + 2 * H)
+    res["rollout"] = {"workload": "K=%d scenarios x H=%d, n_x=4, n_phi=625 (configs[4] shape, K scaled)" % (K, H),
+                      "kernel_ms": kms.value, "scenario_steps_per_s_kernel": K * H / (kms.value * 1e-3),
+                      "hbm_GBps_algorithmic": bytes_alg / (kms.value * 1e-3) / 1e9, "alloc_h2d_ms": h2d.value,
+                      "host_call_s_incl_python_packing": dt}
+    nc, Nc, Tc = 8, 2 ** 16, 2000
+    prob = build_problem("known", Tc, 0)
+    eng = pg.ParticleGibbsEngine(prob["basis"], 1, Nc, Tc, n_chains=nc)
+    try:
+        eng.set_data(prob["u"], prob["y"])
+        eng.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+        eng.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+        eng.set_prior(prob["V"], 100 * np.eye(2), 10.0)
+        for c in range(nc):
+            eng.set_state(prob["A"], prob["Q"], prob["x_prim"], 2, chain=c)
+        eng.set_rng_philox(7, 0)
+        eng.sweep(1)
+        eng.synchronize()
+        t0 = time.perf_counter()
+        eng.sweep(2)
+        eng.synchronize()
+        dt = time.perf_counter() - t0
+        res["chain_batch"] = {"workload": "%d chains x N=%d, T=%d on one GPU (configs[3] shape), known basis, "
+                                          "filter+trace+statistics+MNIW" % (nc, Nc, Tc),
+                              "pg_sweeps_per_s_all_chains": nc * 2 / dt, "particle_steps_per_s": nc * 2 * Nc * (Tc - 1) / dt,
+                              "status": list(eng.status(0))}
+    finally:
+        eng.close()
+    return res
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
@@ -373,6 +444,7 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=2 ** 13)
     ap.add_argument("--cpu-T", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the bounded rollout / chain-batch side measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -205,7 +205,7 @@ __device__ __forceinline__ void rollout_eval_F(const FilterDev& fd, RolloutShare
 }
 
 #ifndef PGB_ROLLOUT_MINBLOCKS
-#define PGB_ROLLOUT_MINBLOCKS 6
+#define PGB_ROLLOUT_MINBLOCKS 4
 #endif
 template <int NX, int NI>
 __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const __grid_constant__ FilterDev fd,
