@@ -436,3 +436,59 @@ def test_rollout_bit_exact(model):
     assert out["X_init"].shape == (n_x * K, H + 1) and out["Y_init"].shape == (K, H)
     np.testing.assert_array_equal(out["X_init"][n_x * 3:n_x * 4, 5], ref["X"][3, 5])
     np.testing.assert_array_equal(out["v_vec"][:, 7, 2], ref["v"][2, 7])
+
+
+# ------------------------------------------------------------------------------------------ other state / output dimensions
+def _general_problem(n_x, n_y, T, seed):
+    """A stable synthetic system with n_x states, 1 input and n_y outputs on a small Hilbert basis."""
+    rng = np.random.default_rng(seed)
+    dims = [2] + [3] * n_x if n_x < 4 else [1, 3, 3, 2, 2]
+    L = [6.0] + [8.0 + d for d in range(n_x)]
+    basis = pg.HilbertGPBasis(dims, L)
+    om = O.hilbert_model(n_x, 1, basis.count, basis.stride, basis.L, n_y=n_y)
+    A = rng.normal(0, 1.5, (n_x, basis.n_phi))
+    Bq = rng.normal(0, 0.2, (n_x, n_x))
+    Q = Bq @ Bq.T + 0.05 * np.eye(n_x)
+    Cm = rng.normal(0, 1, (n_y, n_x))
+    Br = rng.normal(0, 0.1, (n_y, n_y))
+    R = Br @ Br.T + 0.05 * np.eye(n_y) if n_y > 1 else 0.1
+    u = rng.normal(0, 1, (1, T))
+    y = rng.normal(0, 1, (n_y, T))
+    return basis, om, A, Q, Cm, R, u, y
+
+
+@pytest.mark.parametrize("persistent", [1, 2, 0])
+@pytest.mark.parametrize("n_x,n_y,N,T", [(1, 1, 700, 14), (3, 1, 1300, 12), (4, 1, 40, 30), (4, 2, 2100, 9), (2, 2, 1025, 10)])
+def test_sweep_bit_exact_other_dimensions(n_x, n_y, N, T, persistent):
+    """The sweep kernels are templated on n_x (1..4) and take n_y x n_y measurement noise: all instantiations, both the
+    first (bootstrap) and a conditional sweep, against the oracle."""
+    basis, om, A, Q, Cm, R, u, y = _general_problem(n_x, n_y, T, 100 + 10 * n_x + n_y)
+    x0m, x0c = np.zeros(n_x), np.eye(n_x)
+    s = P.injected_streams(N, T, n_x, basis.n_phi, 31)
+    st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
+    ref1 = O.sweep(om, N, T, u, y, Cm, R, x0m, x0c, A, Q, np.zeros((n_x, T)), True, st, 1)
+    ref2 = O.sweep(om, N, T, u, y, Cm, R, x0m, x0c, A, Q, ref1["x_prim"], False, st, 2)
+    with pg.ParticleGibbsEngine(basis, n_y, N, T, keep_w_history=True) as e:
+        e.set_mode(persistent)
+        e.set_data(u, y)
+        e.set_measurement(pg.LinearMeasurement(Cm), R)
+        e.set_init_dist(pg.MvNormal(x0m, 1.0))
+        e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+        for k, ref, xp in ((1, ref1, np.zeros((n_x, T))), (2, ref2, ref1["x_prim"])):
+            e.set_state(A, Q, xp, k)
+            e.sweep_filter()
+            a, x, w = e.get_history()
+            Phi, Psi, Sig, star = e.get_stats()
+            _, _, xprim, _ = e.get_state()
+            stat, nfb, _ = e.status(clear=True)
+            _assert_same("ancestors k=%d" % k, a[1:, :N - 1], ref["a"][1:, :N - 1])
+            if k > 1:
+                _assert_same("ancestor of the conditioned particle", a[1:, N - 1], ref["a"][1:, N - 1])
+            _assert_same("x_pf k=%d" % k, x, ref["x"])
+            _assert_same("w k=%d" % k, w, ref["w"])
+            assert star == ref["star"]
+            _assert_same("x_prim", xprim, ref["x_prim"])
+            _assert_same("Phi", Phi, ref["Phi"])
+            _assert_same("Psi", Psi, ref["Psi"])
+            _assert_same("Sigma", Sig, ref["Sigma"])
+            assert stat == ref["status"] and nfb == 0
