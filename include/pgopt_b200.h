@@ -50,6 +50,8 @@ enum {
   PGB_STATUS_NOT_POSDEF = 16
 };
 
+enum { PGB_X_HISTORY_AUTO = 0, PGB_X_HISTORY_STORE = 1, PGB_X_HISTORY_REPLAY = 2 };
+
 typedef struct {
   int32_t device;     /* CUDA device ordinal */
   int32_t n_x, n_u, n_y, n_phi;
@@ -65,6 +67,13 @@ typedef struct {
   int64_t T;          /* training length */
   int32_t n_chains;   /* independent PG chains batched on this handle (>= 1) */
   int32_t keep_w_history; /* 1: keep w[t,:] for every t (tests; costs T*N*8 bytes per chain) */
+  /* The reference allocates x_pf[n_x,N,T] (particle_Gibbs.jl:159) but reads only x_pf[:,:,t-1] while filtering, one
+   * ancestor lineage for the new x_prim (:213-218) and x_pf[:,:,end] for the sample.  PGB_X_HISTORY_REPLAY keeps two
+   * rows of x and recomputes that lineage from the stored ancestor indices and the random streams (bit-identical);
+   * PGB_X_HISTORY_STORE keeps everything (needed for the x output of pgb_get_history; 8*n_x*N*T bytes per chain);
+   * PGB_X_HISTORY_AUTO stores when the history is at most 1 GiB. */
+  int32_t x_history;
+  int32_t reserved_;
 } pgb_config;
 
 typedef struct pgb_handle pgb_handle;

@@ -44,6 +44,8 @@ struct PgbConfig
     device::Int32; n_x::Int32; n_u::Int32; n_y::Int32; n_phi::Int32; basis::Int32
     hg_count::NTuple{PGB_MAX_Z,Int32}; hg_stride::NTuple{PGB_MAX_Z,Int32}; hg_L::NTuple{PGB_MAX_Z,Float64}
     N::Int64; T::Int64; n_chains::Int32; keep_w_history::Int32
+    x_history::Int32   # 0 auto, 1 store x_pf, 2 replay (two rows + recomputed lineage)
+    reserved_::Int32
 end
 
 pad8(v, T) = ntuple(i -> i <= length(v) ? T(v[i]) : zero(T), PGB_MAX_Z)
@@ -51,7 +53,7 @@ pad8(v, T) = ntuple(i -> i <= length(v) ? T(v[i]) : zero(T), PGB_MAX_Z)
 function make_config(phi, n_y, N, T; device=0, n_chains=1)
     if phi isa KnownBasisVB
         return PgbConfig(device, 2, 1, n_y, 5, 0, pad8(Int[], Int32), pad8(Int[], Int32), pad8(Float64[], Float64),
-                         N, T, n_chains, 0), 2, 1, 5
+                         N, T, n_chains, 0, 0, 0), 2, 1, 5
     elseif phi isa HilbertGPBasis
         nz = length(phi.L)
         # the reference reverses the index vectors (:82): dimension k uses slot nz+1-k
@@ -59,7 +61,7 @@ function make_config(phi, n_y, N, T; device=0, n_chains=1)
         stride = [prod(phi.n_phi_dims[1:nz-k]) for k in 1:nz]
         n_phi = prod(phi.n_phi_dims)
         return PgbConfig(device, nz - phi.n_u, phi.n_u, n_y, n_phi, 1, pad8(count, Int32), pad8(stride, Int32),
-                         pad8(phi.L, Float64), N, T, n_chains, 0), nz - phi.n_u, phi.n_u, n_phi
+                         pad8(phi.L, Float64), N, T, n_chains, 0, 0, 0), nz - phi.n_u, phi.n_u, n_phi
     else
         throw(ArgumentError("phi must be a KnownBasisVB or HilbertGPBasis descriptor: arbitrary closures cannot " *
                             "cross the C ABI and there is no CPU fallback"))

@@ -16,7 +16,11 @@ class PgbConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_x", C.c_int32), ("n_u", C.c_int32), ("n_y", C.c_int32),
                 ("n_phi", C.c_int32), ("basis", C.c_int32), ("hg_count", C.c_int32 * PGB_MAX_Z),
                 ("hg_stride", C.c_int32 * PGB_MAX_Z), ("hg_L", C.c_double * PGB_MAX_Z), ("N", C.c_int64),
-                ("T", C.c_int64), ("n_chains", C.c_int32), ("keep_w_history", C.c_int32)]
+                ("T", C.c_int64), ("n_chains", C.c_int32), ("keep_w_history", C.c_int32), ("x_history", C.c_int32),
+                ("reserved_", C.c_int32)]
+
+
+X_HISTORY = {"auto": 0, "store": 1, "replay": 2}
 
 
 class PgoptError(RuntimeError):

@@ -131,12 +131,13 @@ def _meas(g):
     raise TypeError("g must be a LinearMeasurement (g(x,u) = C*x) or the matrix C")
 
 
-def _make_cfg(phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False):
+def _make_cfg(phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False, x_history="auto"):
     b = _basis(phi)
     cfg = PgbConfig()
     cfg.device, cfg.n_x, cfg.n_u, cfg.n_y, cfg.n_phi = device, b.n_x, b.n_u, n_y, b.n_phi
     b.fill(cfg)
     cfg.N, cfg.T, cfg.n_chains, cfg.keep_w_history = int(N), int(T), int(n_chains), int(keep_w_history)
+    cfg.x_history = _lib.X_HISTORY[x_history]
     return cfg
 
 
@@ -144,8 +145,10 @@ def _make_cfg(phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False):
 # engine (one handle = one device, one stream, n_chains batched chains)
 # ----------------------------------------------------------------------------------------------
 class ParticleGibbsEngine:
-    def __init__(self, phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False):
-        self.cfg = _make_cfg(phi, n_y, N, T, n_chains, device, keep_w_history)
+    def __init__(self, phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False, x_history="auto"):
+        """x_history: "store" keeps x_pf[n_x,N,T] on the device (get_history needs it), "replay" keeps two steps and
+        recomputes the traced trajectory (bit-identical, N*T no longer bounded by memory), "auto": store up to 1 GiB."""
+        self.cfg = _make_cfg(phi, n_y, N, T, n_chains, device, keep_w_history, x_history)
         self.n_x, self.n_u, self.n_y, self.n_phi = self.cfg.n_x, self.cfg.n_u, n_y, self.cfg.n_phi
         self.N, self.T, self.n_chains = int(N), int(T), int(n_chains)
         self._h = C.c_void_p()
@@ -244,9 +247,9 @@ class ParticleGibbsEngine:
         return PG_sample(A.reshape((self.n_x, self.n_phi), order="F"), Q.reshape((self.n_x, self.n_x), order="F"), w,
                          x.reshape((self.n_x, self.N), order="F"), u)
 
-    def get_history(self, chain=0, want_w=True):
+    def get_history(self, chain=0, want_w=True, want_x=True):
         a = np.zeros((self.T, self.N), dtype=np.int64)
-        x = np.zeros((self.T, self.N, self.n_x))
+        x = np.zeros((self.T, self.N, self.n_x)) if want_x else None
         w = np.zeros((self.T, self.N)) if want_w else None
         self._ck(lib().pgb_get_history(self._h, C.c_int32(chain), _p(a), _p(x), _p(w)))
         return a, x, w
@@ -315,7 +318,7 @@ def MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T, bartlett=None, Xmn=None,
 
 
 def particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist, g, R,
-                   x_prim=None, seed=0, chain=0, device=0, verbose=False):
+                   x_prim=None, seed=0, chain=0, device=0, verbose=False, x_history="auto"):
     """particle_Gibbs(u, y, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist, g, R; x_prim)
     — Julia/src/particle_Gibbs.jl:114-237.  Returns a list of K PG_sample.  `x_prim`, when given, is
     updated in place like the reference does (:214-217)."""
@@ -323,7 +326,7 @@ def particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q,
     y = np.atleast_2d(np.asarray(y_training, dtype=np.float64))
     A_init = np.atleast_2d(np.asarray(A_init, dtype=np.float64))
     n_y, T = y.shape
-    eng = ParticleGibbsEngine(phi, n_y, N, T, 1, device)
+    eng = ParticleGibbsEngine(phi, n_y, N, T, 1, device, x_history=x_history)
     try:
         eng.set_data(u, y)
         eng.set_measurement(g, R)

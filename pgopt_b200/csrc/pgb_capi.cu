@@ -239,7 +239,15 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
   CKC(dalloc(h, &fd.Lq, (size_t)nc * 16));
   CKC(dalloc(h, &fd.c0, (size_t)nc));
   CKC(dalloc(h, &fd.xprim, (size_t)nc * nx * T));
-  CKC(dalloc(h, &fd.xh, (size_t)nc * T * nx * N, false));
+  {  // x history: kept (needed by pgb_get_history) or rolling two rows + replay of the traced lineage
+    const double hist_bytes = (double)nc * (double)T * nx * (double)N * 8.0;
+    const bool store = cfg->x_history == PGB_X_HISTORY_STORE ||
+                       (cfg->x_history == PGB_X_HISTORY_AUTO && hist_bytes <= 1024.0 * 1024.0 * 1024.0);
+    fd.x_rows = store ? T : 2;
+    if (T < 2) fd.x_rows = T;
+  }
+  CKC(dalloc(h, &fd.xh, (size_t)nc * fd.x_rows * nx * N, false));
+  CKC(dalloc(h, &fd.lineage, (size_t)nc * T));
   CKC(dalloc(h, &fd.ah, (size_t)nc * T * N, false));
   CKC(cudaMemset(fd.ah, 0xff, (size_t)nc * T * N * sizeof(int32_t)));
   CKC(dalloc(h, &fd.wbuf, (size_t)nc * N));
@@ -524,7 +532,11 @@ static int run_filter_nx(pgb_handle* h) {
   // w_T, then star = systematic_resampling(w[end,:], 1)   (:213)
   LAUNCH(h, PGB_PROF_TAIL, (k_prep<NX><<<gt, TPB, smA, s>>>(fd, T, first)));
   launch_scan<NX, MODE_INDEX>(h, fd.main, fd.wbuf, fd.utab_star, 1, 0, h->d_star_idx, 1, 0, first, nullptr);
-  LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  if (fd.x_rows == T) {
+    LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  } else {
+    LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay<NX><<<nc, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out, first)));
+  }
   // statistics (:221-225)
   LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
   const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
@@ -588,7 +600,11 @@ static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
     void* args[] = {(void*)&fd, (void*)&pd, (void*)&first};
     CK(h, cudaLaunchCooperativeKernel(kfn, dim3((unsigned)(nc * pd.npc)), dim3(TPB), args, smA, s));
   }
-  LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  if (fd.x_rows == T) {
+    LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  } else {
+    LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay<NX><<<nc, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out, first)));
+  }
   LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
   const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
   LAUNCH(h, PGB_PROF_TAIL, (k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md)));
@@ -671,7 +687,8 @@ static int fetch_sample(pgb_handle* h, int chain, double* A, double* Q, double* 
   if (w_m1) CK(h, cudaMemcpyAsync(w_m1, h->fd.wbuf + (size_t)chain * N, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
   if (x_m1) {
     tmp.resize((size_t)nx * N);
-    CK(h, cudaMemcpyAsync(tmp.data(), h->fd.xh + ((size_t)chain * T + (T - 1)) * nx * N, (size_t)nx * N * 8,
+    const size_t row = (h->fd.x_rows == T) ? (size_t)(T - 1) : (size_t)((T - 1) & 1);
+    CK(h, cudaMemcpyAsync(tmp.data(), h->fd.xh + ((size_t)chain * h->fd.x_rows + row) * nx * N, (size_t)nx * N * 8,
                           cudaMemcpyDeviceToHost, s));
   }
   CK(h, cudaStreamSynchronize(s));
@@ -734,6 +751,9 @@ extern "C" int pgb_get_history(pgb_handle* h, int32_t chain, int64_t* a, double*
     for (int64_t n = 0; n < N; ++n) a[n] = 0;  // a[1,:] is never written by the reference
   }
   if (x) {
+    if (h->fd.x_rows != T)
+      return set_err(h, PGB_ERR_STATE, "the particle history x was not kept (x_history = replay); create the handle "
+                                       "with x_history = PGB_X_HISTORY_STORE");
     std::vector<double> tx((size_t)T * nx * N);
     CK(h, cudaMemcpy(tx.data(), h->fd.xh + (size_t)chain * T * nx * N, tx.size() * 8, cudaMemcpyDeviceToHost));
     for (int64_t t = 0; t < T; ++t)

@@ -32,7 +32,9 @@ struct FilterDev {
   double* Lq;        // [nc][16]  lower Cholesky of Q, column-major n_x x n_x
   double* c0;        // [nc]      -(n_x log 2pi + logdet Q)/2
   double* xprim;     // [nc][n_x*T]
-  double* xh;        // [nc][T][n_x][N]
+  double* xh;        // [nc][x_rows][n_x][N]: particle states, row xrow(t) holds x_t
+  int64_t x_rows;    // T: the whole history is kept; 2: rolling (replay mode, see k_trace_replay)
+  int32_t* lineage;  // [nc][T] traced ancestor path b_t (replay mode)
   int32_t* ah;       // [nc][T][N]
   double *wbuf, *ebuf, *lwbuf, *Fbuf, *waN;  // [nc][N] ([nc][n_x][N] for Fbuf)
   double* whist;     // [nc][T][N] or null
@@ -55,9 +57,41 @@ struct FilterDev {
   int ablate;  // timing experiments only (env PGB_ABLATE): see pgb_persist.cuh
 };
 
+// row of fd.xh that holds the particles of step t (0-based)
+__device__ __forceinline__ double* x_row(const FilterDev& fd, int chain, int64_t t) {
+  const int64_t r = (fd.x_rows == fd.T) ? t : (t & 1);
+  return fd.xh + ((int64_t)chain * fd.x_rows + r) * fd.n_x * fd.N;
+}
+
 // ------------------------------------------------------------------------------------------
 // model pieces (device restatement; the oracle has its own independent copy of the formulas)
 // ------------------------------------------------------------------------------------------
+// F = A * phi for the Hilbert-space basis, given the scaled sines tk[k][j] of every augmented dimension:
+// phi_i = ((1*t_0)*t_1)*... with dimension 0 slowest, F_d = fma(A[d,i], phi_i, F_d) in increasing i.
+template <int NX>
+__device__ __forceinline__ void hilbert_apply(const FilterDev& fd, const double* __restrict__ A_sm,
+                                              const double (*tk)[MAXC], double F[NX]) {
+  const int nz = fd.n_z;
+  int dig[PGB_MAX_Z_];
+  double pp[PGB_MAX_Z_];
+  double acc[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) acc[d] = 0.0;
+  for (int k = 0; k < nz; ++k) dig[k] = 0;
+  int from = 0;
+  for (int i = 0; i < fd.n_phi; ++i) {
+    for (int k = from; k < nz; ++k) pp[k] = __dmul_rn(k ? pp[k - 1] : 1.0, tk[k][dig[k]]);
+    double p = pp[nz - 1];
+#pragma unroll
+    for (int d = 0; d < NX; ++d) acc[d] = __fma_rn(A_sm[d + NX * i], p, acc[d]);
+    int k = nz - 1;
+    while (k >= 0 && ++dig[k] == fd.hg_count[k]) dig[k--] = 0;
+    from = k < 0 ? 0 : k;
+  }
+#pragma unroll
+  for (int d = 0; d < NX; ++d) F[d] = acc[d];
+}
+
 template <int NX>
 __device__ __forceinline__ void eval_F(const FilterDev& fd, const double* __restrict__ A_sm, const double x[NX],
                                        const double* __restrict__ u, double F[NX]) {
@@ -88,24 +122,7 @@ __device__ __forceinline__ void eval_F(const FilterDev& fd, const double* __rest
     for (int j = 0; j < fd.hg_count[k]; ++j)
       tk[k][j] = __dmul_rn(fd.hg_lsi[k], pgb_sin(__dmul_rn(fd.hg_pij2l[k][j], zl)));
   }
-  int dig[PGB_MAX_Z_];
-  double pp[PGB_MAX_Z_];
-  double acc[NX];
-#pragma unroll
-  for (int d = 0; d < NX; ++d) acc[d] = 0.0;
-  for (int k = 0; k < nz; ++k) dig[k] = 0;
-  int from = 0;
-  for (int i = 0; i < fd.n_phi; ++i) {
-    for (int k = from; k < nz; ++k) pp[k] = __dmul_rn(k ? pp[k - 1] : 1.0, tk[k][dig[k]]);
-    double p = pp[nz - 1];
-#pragma unroll
-    for (int d = 0; d < NX; ++d) acc[d] = __fma_rn(A_sm[d + NX * i], p, acc[d]);
-    int k = nz - 1;
-    while (k >= 0 && ++dig[k] == fd.hg_count[k]) dig[k--] = 0;
-    from = k < 0 ? 0 : k;
-  }
-#pragma unroll
-  for (int d = 0; d < NX; ++d) F[d] = acc[d];
+  hilbert_apply<NX>(fd, A_sm, tk, F);
 }
 
 // Hilbert-space basis with 5 x 5 x 5 functions over z = [u; x1; x2] (the reference's generic example), two particles
@@ -288,7 +305,7 @@ __global__ void __launch_bounds__(TPB) k_init(FilterDev fd, int first) {
   __shared__ double sm[NWARP + 1];
   const int chain = blockIdx.y;
   const int64_t N = fd.N;
-  double* x0 = fd.xh + (int64_t)chain * fd.T * NX * N;  // step 0
+  double* x0 = x_row(fd, chain, 0);  // step 0
   const double* xp = fd.xprim + (int64_t)chain * NX * fd.T;
   double lmax = -INFINITY;
   int64_t n = (int64_t)blockIdx.x * TPB + threadIdx.x;
@@ -370,7 +387,7 @@ __global__ void __launch_bounds__(TPB) k_prep(FilterDev fd, int64_t t, int first
   const double* e = fd.ebuf + (int64_t)chain * N;
   double* w = fd.wbuf + (int64_t)chain * N;
   double* wh = fd.whist ? fd.whist + ((int64_t)chain * T + (t - 1)) * N : nullptr;
-  const double* xp = fd.xh + ((int64_t)chain * T + (t - 1)) * NX * N;
+  const double* xp = x_row(fd, chain, t - 1);
   double* Fb = fd.Fbuf + (int64_t)chain * NX * N;
   double* wa = fd.waN + (int64_t)chain * N;
   const double* up = fd.u + (int64_t)fd.n_u * (t - 1);
@@ -505,7 +522,7 @@ __global__ void __launch_bounds__(TPB) k_expand(FilterDev fd, ScanWS ws, const d
 #pragma unroll
     for (int i = 0; i < NX * NX; ++i) Lq[i] = fd.Lq[chain * 16 + i];
     Fb = fd.Fbuf + (int64_t)chain * NX * fd.N;
-    xt = fd.xh + ((int64_t)chain * fd.T + t) * NX * fd.N;
+    xt = x_row(fd, chain, t);
     at = fd.ah + ((int64_t)chain * fd.T + t) * fd.N;
     lwb = fd.lwbuf + (int64_t)chain * fd.N;
     yt = fd.y + (int64_t)fd.n_y * t;
@@ -629,6 +646,91 @@ __global__ void k_trace(FilterDev fd, const int32_t* __restrict__ star_idx, int6
     star = ah[(t + 1) * N + star];
     if (star < 0) star = 0;
     for (int d = 0; d < NX; ++d) xp[d + NX * t] = xh[(t * NX + d) * N + star];
+  }
+}
+
+// Replay mode (x_rows == 2): the particle history is not kept.  The conditioned trajectory of the next sweep
+// (:213-218) is the state along ONE ancestor lineage, so it is recomputed: lane 0 walks the lineage backwards through
+// the stored ancestor indices, then the warp re-runs the T propagation steps of that single lineage with exactly the
+// arithmetic of the filter (same F evaluation order, same Philox / injected normals, x = F + L z), which reproduces
+// the stored values bit for bit.  One warp per chain; the lanes share the sines of the Hilbert basis.
+template <int NX>
+__global__ void __launch_bounds__(32) k_trace_replay(FilterDev fd, const int32_t* __restrict__ star_idx,
+                                                     int64_t* __restrict__ star_out, int first) {
+  __shared__ double tk[PGB_MAX_Z_][MAXC];
+  const int chain = blockIdx.x, lane = threadIdx.x;
+  const int64_t N = fd.N, T = fd.T;
+  double* xp = fd.xprim + (int64_t)chain * NX * T;
+  const int32_t* ah = fd.ah + (int64_t)chain * T * N;
+  int32_t* lin = fd.lineage + (int64_t)chain * T;
+  if (lane == 0) {
+    int64_t star = star_idx[chain];
+    if (star < 0) star = 0;
+    star_out[chain] = star + 1;
+    lin[T - 1] = (int32_t)star;
+    for (int64_t t = T - 2; t >= 0; --t) {
+      star = ah[(t + 1) * N + star];
+      if (star < 0) star = 0;
+      lin[t] = (int32_t)star;
+    }
+  }
+  __syncwarp();
+  const double* A = fd.A + (int64_t)chain * NX * fd.n_phi;
+  double Lq[NX * NX];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) Lq[i] = fd.Lq[chain * 16 + i];
+  double x[NX];
+  for (int64_t t = 0; t < T; ++t) {
+    const int64_t b = lin[t];
+    const bool pinned = (b == N - 1) && (t == 0 || !first);  // slot N holds the previous sweep's trajectory
+    if (pinned) {
+#pragma unroll
+      for (int d = 0; d < NX; ++d) x[d] = xp[d + NX * t];
+    } else if (t == 0) {
+      double z[NX];
+      draw_normals<NX>(fd, chain, PGB_STREAM_Z0, 0, b, fd.Z0 ? fd.Z0 + (int64_t)chain * NX * (N - 1) : nullptr, z);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e <= d; ++e) acc = __fma_rn(fd.x0_chol[d + NX * e], z[e], acc);
+        x[d] = __dadd_rn(fd.x0_mean[d], acc);
+      }
+    } else {
+      double F[NX], z[NX];
+      const double* u = fd.u + (int64_t)fd.n_u * (t - 1);
+      if (fd.basis == 0) {
+        eval_F<NX>(fd, A, x, u, F);
+      } else {
+        int ns = 0;
+        for (int k = 0; k < fd.n_z; ++k) ns += fd.hg_count[k];
+        for (int s0 = lane; s0 < ns; s0 += 32) {  // sine s0 -> (dimension k, frequency j)
+          int k = 0, j = s0;
+          while (j >= fd.hg_count[k]) j -= fd.hg_count[k++];
+          const double zk = (k < fd.n_u) ? u[k] : x[k - fd.n_u];
+          const double arg[1] = {__dmul_rn(fd.hg_pij2l[k][j], __dadd_rn(zk, fd.hg_L[k]))};
+          double sn[1], cs[1];
+          vsincos_wide<1>(arg, sn, cs);
+          tk[k][j] = __dmul_rn(fd.hg_lsi[k], sn[0]);
+        }
+        __syncwarp();
+        hilbert_apply<NX>(fd, A, tk, F);
+        __syncwarp();
+      }
+      draw_normals<NX>(fd, chain, PGB_STREAM_Z, (uint32_t)t, b, fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr, z);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e <= d; ++e) acc = __fma_rn(Lq[d + NX * e], z[e], acc);
+        x[d] = __dadd_rn(F[d], acc);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int d = 0; d < NX; ++d) xp[d + NX * t] = x[d];
+    }
+    __syncwarp();
   }
 }
 

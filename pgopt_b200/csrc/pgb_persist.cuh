@@ -363,7 +363,7 @@ __device__ __forceinline__ void emit_ctx_init(EmitCtx<NX>& ec, const FilterDev& 
 #pragma unroll
   for (int i = 0; i < NX * NX; ++i) ec.Lq[i] = fd.Lq[chain * 16 + i];
   ec.Fb = fd.Fbuf + (int64_t)chain * NX * N;
-  ec.xt = fd.xh + ((int64_t)chain * fd.T + t) * NX * N;
+  ec.xt = x_row(fd, chain, t);
   ec.at = fd.ah + ((int64_t)chain * fd.T + t) * N;
   ec.lwb = fd.lwbuf + (int64_t)chain * N;
   ec.yt = fd.y + (int64_t)fd.n_y * t;
@@ -728,7 +728,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
 
   // ---------------------------------------------------------------- t = 0: initial particles (:160-165)
   {
-    double* x0 = fd.xh + (int64_t)chain * T * NX * N;
+    double* x0 = x_row(fd, chain, 0);
     const double* xp = fd.xprim + (int64_t)chain * NX * T;
     double lmax = -INFINITY;
     P_FOR_BLOCKS for (int k = 0; k < tpc; ++k) {
@@ -811,7 +811,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
       const double* e = fd.ebuf + (int64_t)chain * N;
       double* w = fd.wbuf + (int64_t)chain * N;
       double* wh = fd.whist ? fd.whist + ((int64_t)chain * T + (t - 1)) * N : nullptr;
-      const double* xp = fd.xh + ((int64_t)chain * T + (t - 1)) * NX * N;
+      const double* xp = x_row(fd, chain, t - 1);
       double* Fb = fd.Fbuf + (int64_t)chain * NX * N;
       double* wa = fd.waN + (int64_t)chain * N;
       const double* up = fd.u + (int64_t)fd.n_u * (t - 1);

@@ -481,7 +481,7 @@ __device__ __noinline__ void w_phase_init(const WCtx& cx) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int chain = cx.chain, tpc = cx.tpc;
   const int64_t N = fd.N, T = fd.T;
-  double* x0 = fd.xh + (int64_t)chain * T * NX * N;
+  double* x0 = x_row(fd, chain, 0);
   const double* xp = fd.xprim + (int64_t)chain * NX * T;
   double lmax = -INFINITY;
   for (int j = 0; j < tpc; ++j) {
@@ -565,7 +565,7 @@ __device__ __noinline__ void w_phase_A(const WCtx& cx, int64_t t, bool last_only
   const double* e = fd.ebuf + (int64_t)chain * N;
   double* wgt = fd.wbuf + (int64_t)chain * N;
   double* wh = fd.whist ? fd.whist + ((int64_t)chain * T + (t - 1)) * N : nullptr;
-  const double* xp = fd.xh + ((int64_t)chain * T + (t - 1)) * NX * N;
+  const double* xp = x_row(fd, chain, t - 1);
   double* Fb = fd.Fbuf + (int64_t)chain * NX * N;
   double* wa = fd.waN + (int64_t)chain * N;
   const double* up = fd.u + (int64_t)fd.n_u * (t - 1);

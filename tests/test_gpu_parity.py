@@ -492,3 +492,64 @@ def test_sweep_bit_exact_other_dimensions(n_x, n_y, N, T, persistent):
             _assert_same("Psi", Psi, ref["Psi"])
             _assert_same("Sigma", Sig, ref["Sigma"])
             assert stat == ref["status"] and nfb == 0
+
+
+# ------------------------------------------------------------------------------------------ replay mode (no x history)
+@pytest.mark.parametrize("persistent", [1, 2, 0])
+@pytest.mark.parametrize("model,N,T,philox", [("known", 30, 150, True), ("known", 2500, 40, False), ("hilbert", 700, 30, True),
+                                               ("hilbert", 33, 60, False)])
+def test_replay_mode_reproduces_the_traced_trajectory(model, N, T, philox, persistent):
+    """x_history="replay" keeps two rows of x and recomputes the ancestor lineage of the new conditioned trajectory
+    (particle_Gibbs.jl:213-218): x_prim, the MNIW statistics, the kept sample and all ancestors must be those of the
+    oracle, over a first sweep and two conditional sweeps (the lineage passes through the pinned slot N sometimes)."""
+    basis, om, A = _models()[model]
+    u, y, _ = P.make_data(T, 17)
+    s = P.injected_streams(N, T, 2, basis.n_phi, 27)
+    kw = dict(philox=True, seed=321, chain=4) if philox else dict(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
+    xp = np.zeros((2, T))
+    with pg.ParticleGibbsEngine(basis, 1, N, T, x_history="replay") as e:
+        e.set_mode(persistent)
+        e.set_data(u, y)
+        e.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+        e.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+        if philox:
+            e.set_rng_philox(321, 4)
+        else:
+            e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+        for k in (1, 2, 3):
+            ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, k == 1, O.make_streams(**kw), k)
+            e.set_state(A, P.Q_TRUE, xp, k)
+            e.sweep_filter()
+            a, _, _ = e.get_history(want_w=False, want_x=False)
+            Phi, Psi, Sig, star = e.get_stats()
+            _, _, xprim, _ = e.get_state()
+            smp = e.get_sample()
+            stat, nfb, _ = e.status(clear=True)
+            assert star == ref["star"] and stat == ref["status"] == 0
+            _assert_same("ancestors k=%d" % k, a[1:, :N - 1], ref["a"][1:, :N - 1])
+            _assert_same("x_prim k=%d" % k, xprim, ref["x_prim"])
+            _assert_same("Phi", Phi, ref["Phi"])
+            _assert_same("Psi", Psi, ref["Psi"])
+            _assert_same("Sigma", Sig, ref["Sigma"])
+            _assert_same("w_m1", smp.w_m1, ref["w_last"])
+            _assert_same("x_m1", smp.x_m1.T, ref["x_last"])
+            xp = ref["x_prim"]
+        with pytest.raises(pg.PgoptError):
+            e.get_history(want_w=False)  # the x history does not exist in this mode
+
+
+def test_replay_mode_whole_sampler_matches_store_mode():
+    """particle_Gibbs end to end (filter + trace + statistics + MNIW, K kept samples) in replay mode == oracle."""
+    basis, om, _ = _models()["hilbert"]
+    N, T, K = 64, 40, 3
+    u, y, _ = P.make_data(T, 13)
+    V = pg.hilbert_gp_prior_V([5, 5, 5], [10, 20, 20], 2 * np.pi * np.ones(3), 100 ** 2 / (8 * np.pi ** 4))
+    ref = O.particle_gibbs(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), np.zeros((2, 125)), 100 * np.eye(2), V,
+                           100 * np.eye(2), 10.0, K, 2, 1, seed=5, chain=0)
+    smp = pg.particle_Gibbs(u, y, K, 2, 1, N, basis, 100 * np.eye(2), 10.0, 100 * np.eye(2), V, np.zeros((2, 125)),
+                            pg.MvNormal([2.0, 2.0], 1.0), pg.LinearMeasurement([[1.0, 0.0]]), 0.1, x_prim=np.zeros((2, T)),
+                            seed=5, chain=0, x_history="replay")
+    for k in range(K):
+        _assert_same("A[%d]" % k, smp[k].A, ref["A"][k])
+        _assert_same("Q[%d]" % k, smp[k].Q, ref["Q"][k])
+        _assert_same("x_m1[%d]" % k, smp[k].x_m1.T, ref["x"][k])
