@@ -287,11 +287,12 @@ def run_gpu(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_per_sweep, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "CPF-AS conditional sweep (k>1), %s-basis model n_x=2 n_phi=%d, N=%d particles, T=%d, "
-                                   "Philox streams, x/a history stored in HBM; BASELINE.json configs[2]"
-                                   % (args.model, n_phi, N, T),
+                                   "Philox streams, ancestor history stored in HBM, x history %s; BASELINE.json configs[2]"
+                                   % (args.model, n_phi, N, T, "stored" if N * T * n_x * 8 <= 2 ** 30 else
+                                      "replayed (two rows kept, traced lineage recomputed)"),
                        "N": N, "T": T, "n_phi": n_phi, "chains_per_gpu": 1,
-                       "l2": "per-step working set re-streamed; history (x: %d GB, a: %d GB) written once, larger than L2"
-                             % (N * T * n_x * 8 >> 30, N * T * 4 >> 30)},
+                       "l2": "per-step working set (~100 MB of rolling buffers) re-streamed every step; ancestor history "
+                             "(%d GB) written once, larger than L2" % (N * T * 4 >> 30)},
             "pg_sweeps_per_s": sweeps_per_s,
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "includes": "set_data+set_state H2D, filter+trace+stats+MNIW, get_sample D2H"},

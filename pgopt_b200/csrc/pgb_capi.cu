@@ -43,6 +43,7 @@ struct pgb_handle {
   std::vector<double> h_u;  // host copy of u (for u_m1)
   // the (A, Q) the last filter pass ran with (sample fields, particle_Gibbs.jl:204-205)
   double *d_A_used = nullptr, *d_Q_used = nullptr;
+  double* d_replay_noise = nullptr;  // [nc][T][n_x] noise along the traced lineage (replay mode)
   bool injected_ready = false;
   // persistent (single cooperative kernel) filter path
   int persistent = 1;  // 1: tile persistent kernel (default, fastest measured), 2: warp-tile persistent kernel, 0: one launch per phase
@@ -248,6 +249,7 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
   }
   CKC(dalloc(h, &fd.xh, (size_t)nc * fd.x_rows * nx * N, false));
   CKC(dalloc(h, &fd.lineage, (size_t)nc * T));
+  CKC(dalloc(h, &h->d_replay_noise, (size_t)nc * T * nx));
   CKC(dalloc(h, &fd.ah, (size_t)nc * T * N, false));
   CKC(cudaMemset(fd.ah, 0xff, (size_t)nc * T * N * sizeof(int32_t)));
   CKC(dalloc(h, &fd.wbuf, (size_t)nc * N));
@@ -535,7 +537,8 @@ static int run_filter_nx(pgb_handle* h) {
   if (fd.x_rows == T) {
     LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
   } else {
-    LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay<NX><<<nc, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out, first)));
+    LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay<NX><<<nc, TR_TPB, (size_t)fd.n_phi * 8, s>>>(fd, h->d_star_idx, h->d_star_out,
+                                                                                        h->d_replay_noise, first)));
   }
   // statistics (:221-225)
   LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
@@ -603,7 +606,8 @@ static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
   if (fd.x_rows == T) {
     LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
   } else {
-    LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay<NX><<<nc, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out, first)));
+    LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay<NX><<<nc, TR_TPB, (size_t)fd.n_phi * 8, s>>>(fd, h->d_star_idx, h->d_star_out,
+                                                                                        h->d_replay_noise, first)));
   }
   LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
   const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;

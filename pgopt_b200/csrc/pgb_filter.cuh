@@ -650,20 +650,26 @@ __global__ void k_trace(FilterDev fd, const int32_t* __restrict__ star_idx, int6
 }
 
 // Replay mode (x_rows == 2): the particle history is not kept.  The conditioned trajectory of the next sweep
-// (:213-218) is the state along ONE ancestor lineage, so it is recomputed: lane 0 walks the lineage backwards through
-// the stored ancestor indices, then the warp re-runs the T propagation steps of that single lineage with exactly the
-// arithmetic of the filter (same F evaluation order, same Philox / injected normals, x = F + L z), which reproduces
-// the stored values bit for bit.  One warp per chain; the lanes share the sines of the Hilbert basis.
+// (:213-218) is the state along ONE ancestor lineage, so it is recomputed: thread 0 walks the lineage backwards through
+// the stored ancestor indices, the noise L z(t, b_t) of every step is drawn in parallel (it does not depend on the
+// state), then the CTA re-runs the T propagation steps of that single lineage with exactly the arithmetic of the
+// filter (same sines, same product order, F_d = fma(A[d,i], phi_i, F_d) in increasing i, x = F + L z), which reproduces
+// the stored values bit for bit.  One 128-thread CTA per chain; dynamic shared memory: phi[n_phi].
+constexpr int TR_TPB = 128;
 template <int NX>
-__global__ void __launch_bounds__(32) k_trace_replay(FilterDev fd, const int32_t* __restrict__ star_idx,
-                                                     int64_t* __restrict__ star_out, int first) {
+__global__ void __launch_bounds__(TR_TPB) k_trace_replay(FilterDev fd, const int32_t* __restrict__ star_idx,
+                                                         int64_t* __restrict__ star_out, double* __restrict__ noise,
+                                                         int first) {
+  extern __shared__ double phi_sm[];
   __shared__ double tk[PGB_MAX_Z_][MAXC];
-  const int chain = blockIdx.x, lane = threadIdx.x;
+  __shared__ double xs[4];
+  const int chain = blockIdx.x, tid = threadIdx.x;
   const int64_t N = fd.N, T = fd.T;
   double* xp = fd.xprim + (int64_t)chain * NX * T;
   const int32_t* ah = fd.ah + (int64_t)chain * T * N;
   int32_t* lin = fd.lineage + (int64_t)chain * T;
-  if (lane == 0) {
+  double* nz_ = noise + (int64_t)chain * T * NX;
+  if (tid == 0) {
     int64_t star = star_idx[chain];
     if (star < 0) star = 0;
     star_out[chain] = star + 1;
@@ -674,63 +680,103 @@ __global__ void __launch_bounds__(32) k_trace_replay(FilterDev fd, const int32_t
       lin[t] = (int32_t)star;
     }
   }
-  __syncwarp();
-  const double* A = fd.A + (int64_t)chain * NX * fd.n_phi;
-  double Lq[NX * NX];
+  __syncthreads();
+  // noise of every step along the lineage: t = 0 initial draw (:161), t >= 1 process noise (:175|:188)
+  {
+    double Lq[NX * NX];
 #pragma unroll
-  for (int i = 0; i < NX * NX; ++i) Lq[i] = fd.Lq[chain * 16 + i];
-  double x[NX];
+    for (int i = 0; i < NX * NX; ++i) Lq[i] = fd.Lq[chain * 16 + i];
+    for (int64_t t = tid; t < T; t += TR_TPB) {
+      const int64_t b = lin[t];
+      double z[NX];
+      if (t == 0) {
+        if (b == N - 1) {
+#pragma unroll
+          for (int d = 0; d < NX; ++d) z[d] = 0.0;  // pinned slot: no draw
+        } else {
+          draw_normals<NX>(fd, chain, PGB_STREAM_Z0, 0, b, fd.Z0 ? fd.Z0 + (int64_t)chain * NX * (N - 1) : nullptr, z);
+        }
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+          double acc = 0.0;
+#pragma unroll
+          for (int e = 0; e <= d; ++e) acc = __fma_rn(fd.x0_chol[d + NX * e], z[e], acc);
+          nz_[t * NX + d] = acc;
+        }
+      } else {
+        draw_normals<NX>(fd, chain, PGB_STREAM_Z, (uint32_t)t, b, fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr, z);
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+          double acc = 0.0;
+#pragma unroll
+          for (int e = 0; e <= d; ++e) acc = __fma_rn(Lq[d + NX * e], z[e], acc);
+          nz_[t * NX + d] = acc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const double* A = fd.A + (int64_t)chain * NX * fd.n_phi;
+  const int nz = fd.n_z, n_phi = fd.n_phi;
+  int ns = 0;
+  if (fd.basis != 0)
+    for (int k = 0; k < nz; ++k) ns += fd.hg_count[k];
+  // the sine this thread evaluates (Hilbert basis): s -> (dimension sk, frequency sj)
+  int sk = 0, sj = tid;
+  if (tid < ns)
+    while (sj >= fd.hg_count[sk]) sj -= fd.hg_count[sk++];
   for (int64_t t = 0; t < T; ++t) {
     const int64_t b = lin[t];
     const bool pinned = (b == N - 1) && (t == 0 || !first);  // slot N holds the previous sweep's trajectory
     if (pinned) {
-#pragma unroll
-      for (int d = 0; d < NX; ++d) x[d] = xp[d + NX * t];
+      if (tid < NX) xs[tid] = xp[tid + NX * t];
     } else if (t == 0) {
-      double z[NX];
-      draw_normals<NX>(fd, chain, PGB_STREAM_Z0, 0, b, fd.Z0 ? fd.Z0 + (int64_t)chain * NX * (N - 1) : nullptr, z);
-#pragma unroll
-      for (int d = 0; d < NX; ++d) {
-        double acc = 0.0;
-#pragma unroll
-        for (int e = 0; e <= d; ++e) acc = __fma_rn(fd.x0_chol[d + NX * e], z[e], acc);
-        x[d] = __dadd_rn(fd.x0_mean[d], acc);
-      }
+      if (tid < NX) xs[tid] = __dadd_rn(fd.x0_mean[tid], nz_[tid]);
     } else {
-      double F[NX], z[NX];
       const double* u = fd.u + (int64_t)fd.n_u * (t - 1);
       if (fd.basis == 0) {
-        eval_F<NX>(fd, A, x, u, F);
+        if (tid == 0) {
+          double x[NX], F[NX];
+#pragma unroll
+          for (int d = 0; d < NX; ++d) x[d] = xs[d];
+          eval_F<NX>(fd, A, x, u, F);
+#pragma unroll
+          for (int d = 0; d < NX; ++d) xs[d] = __dadd_rn(F[d], nz_[t * NX + d]);
+        }
       } else {
-        int ns = 0;
-        for (int k = 0; k < fd.n_z; ++k) ns += fd.hg_count[k];
-        for (int s0 = lane; s0 < ns; s0 += 32) {  // sine s0 -> (dimension k, frequency j)
-          int k = 0, j = s0;
-          while (j >= fd.hg_count[k]) j -= fd.hg_count[k++];
-          const double zk = (k < fd.n_u) ? u[k] : x[k - fd.n_u];
-          const double arg[1] = {__dmul_rn(fd.hg_pij2l[k][j], __dadd_rn(zk, fd.hg_L[k]))};
+        if (tid < ns) {
+          const double zk = (sk < fd.n_u) ? u[sk] : xs[sk - fd.n_u];
+          const double arg[1] = {__dmul_rn(fd.hg_pij2l[sk][sj], __dadd_rn(zk, fd.hg_L[sk]))};
           double sn[1], cs[1];
           vsincos_wide<1>(arg, sn, cs);
-          tk[k][j] = __dmul_rn(fd.hg_lsi[k], sn[0]);
+          tk[sk][sj] = __dmul_rn(fd.hg_lsi[sk], sn[0]);
         }
-        __syncwarp();
-        hilbert_apply<NX>(fd, A, tk, F);
-        __syncwarp();
-      }
-      draw_normals<NX>(fd, chain, PGB_STREAM_Z, (uint32_t)t, b, fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr, z);
+        __syncthreads();
+        for (int i = tid; i < n_phi; i += TR_TPB) {  // phi_i = ((1*t_0)*t_1)*..., dimension 0 slowest
+          int dg[PGB_MAX_Z_];
+          int rem = i;
 #pragma unroll
-      for (int d = 0; d < NX; ++d) {
-        double acc = 0.0;
+          for (int k = PGB_MAX_Z_ - 1; k >= 0; --k)
+            if (k < nz) {
+              dg[k] = rem % fd.hg_count[k];
+              rem /= fd.hg_count[k];
+            }
+          double p = 1.0;
 #pragma unroll
-        for (int e = 0; e <= d; ++e) acc = __fma_rn(Lq[d + NX * e], z[e], acc);
-        x[d] = __dadd_rn(F[d], acc);
+          for (int k = 0; k < PGB_MAX_Z_; ++k)
+            if (k < nz) p = __dmul_rn(p, tk[k][dg[k]]);
+          phi_sm[i] = p;
+        }
+        __syncthreads();
+        if (tid < NX) {
+          double acc = 0.0;
+          for (int i = 0; i < n_phi; ++i) acc = __fma_rn(A[tid + NX * i], phi_sm[i], acc);
+          xs[tid] = __dadd_rn(acc, nz_[t * NX + tid]);
+        }
       }
     }
-    if (lane == 0) {
-#pragma unroll
-      for (int d = 0; d < NX; ++d) xp[d + NX * t] = x[d];
-    }
-    __syncwarp();
+    __syncthreads();
+    if (tid < NX) xp[tid + NX * t] = xs[tid];
   }
 }
 
