@@ -28,7 +28,10 @@ namespace pgb {
 constexpr int P_MAXNB = 1024;     // max blocks per chain
 constexpr int P_MAXTPC = 64;      // max tiles per CTA (all of its blocks together)
 constexpr int P_MAXREC = 160;     // complex threads resolved per scan (more -> serial fallback)
-constexpr int P_HEAVY = 32;       // offspring count above which a particle goes to the cooperative list
+#ifndef PGB_P_HEAVY
+#define PGB_P_HEAVY 512
+#endif
+constexpr int P_HEAVY = PGB_P_HEAVY;  // offspring count above which a particle goes to the cooperative list
 constexpr int P_HEAVY_MAX = 1 << 15;
 constexpr int P_NPROF = 16;
 constexpr int P_CAP = 2048;        // output slots staged per chunk in shared memory
