@@ -15,7 +15,10 @@
 namespace pgb {
 
 constexpr int PGB_MAX_Z_ = 8;     // = PGB_MAX_Z of the public header
-constexpr int TPB = 256;          // threads per CTA
+#ifndef PGB_TPB
+#define PGB_TPB 256
+#endif
+constexpr int TPB = PGB_TPB;      // threads per CTA
 constexpr int IPT = 4;            // consecutive elements per thread
 constexpr int TILE = TPB * IPT;   // elements per CTA tile (aligned power of two)
 constexpr int NWARP = TPB / 32;
