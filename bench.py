@@ -32,8 +32,8 @@ sys.path.insert(0, ROOT)
 BYTES_PER_PARTICLE_STEP = lambda n_x: 16 * n_x + 20      # x r+w, w r+w, Int32 ancestor
 FLOPS_PER_PARTICLE_STEP = {"generic": 1250.0, "known": 100.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of k_sweep_persistent per particle-step, from the committed `ncu --set full`
-# captures at N = 2^20, T = 24 (profiles/r01_persistent_generic_N2p20.md, profiles/r01_ncu_persistent_v1_known_N2p20.md)
-NCU_DRAM_BYTES_PER_PARTICLE_STEP = {"generic": (2.527836e9 + 282.65472e6) / (23 * 2 ** 20),
+# captures at N = 2^20, T = 24 (profiles/r01_final_persistent_generic_N2p20.md, profiles/r01_ncu_persistent_v1_known_N2p20.md)
+NCU_DRAM_BYTES_PER_PARTICLE_STEP = {"generic": (2.665312e9 + 430.749184e6) / (23 * 2 ** 20),
                                     "known": (1.962611e9 + 61.51808e6) / (23 * 2 ** 20)}
 
 
