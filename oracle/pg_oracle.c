@@ -561,7 +561,8 @@ int orc_particle_gibbs(const orc_model* m, int64_t N, int64_t T, const double* u
  * 2 (v, j = step*npairs+p), 3 (e). */
 int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const double* A, const double* Q,
                 const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
-                const double* u_init, uint64_t seed, double* x0, double* v, double* e, double* X, double* Y) {
+                const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e, double* X,
+                double* Y) {
   const int n_x = m->n_x, n_u = m->n_u, n_y = m->n_y, n_phi = m->n_phi;
   int status = 0;
   double* phi_tmp = (double*)malloc(sizeof(double) * (size_t)n_phi);
@@ -573,7 +574,7 @@ int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const doubl
     memset(&s, 0, sizeof(s));
     s.philox = 1;
     s.seed = seed;
-    s.chain = (uint32_t)k;
+    s.chain = k_offset + (uint32_t)k; /* scenario id: a shard of the K scenarios keeps its global stream */
     memcpy(Lq, &Q[k * n_x * n_x], sizeof(double) * (size_t)(n_x * n_x));
     if (orc_cholesky_lower(Lq, n_x)) { status |= 16; break; }
     /* star = systematic_resampling(w_m1, 1); x_m1 = x_m1[:, star]   (:58-59) */

@@ -108,7 +108,8 @@ int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const doubl
                 const double* Q /*K x n_x x n_x*/, const double* w_m1 /*K x N*/,
                 const double* x_m1 /*K x n_x x N*/, const double* u_m1 /*K x n_u*/,
                 const double* C, const double* Le, const double* u_init /*n_u x H*/,
-                uint64_t seed, double* x0 /*K x n_x*/, double* v /*K x H x n_x*/,
+                uint64_t seed, uint32_t k_offset /* global id of scenario 0 (stream id) */, double* x0 /*K x n_x*/,
+                double* v /*K x H x n_x*/,
                 double* e /*K x H x n_y*/, double* X /*K x (H+1) x n_x*/, double* Y /*K x H x n_y*/);
 
 #ifdef __cplusplus

@@ -43,6 +43,25 @@ def gather_packed(local_pack, n_total, dist=None, device=None):
     return np.concatenate(parts, axis=0)
 
 
+def rollout_sharded(rollout_fn, K, dist=None, device=None):
+    """Scenario rollout sharded over the process group (BASELINE.json configs[4]): rank r rolls the scenarios
+    [lo, hi) of `shard_range(K, r, world)` with `rollout_fn(lo, hi)` — which must key its random streams by the global
+    scenario id (`k_offset = lo`) — and the per-scenario outputs are all-gathered, so that every rank ends with exactly
+    the arrays of a single-process rollout.  rollout_fn returns a dict of arrays whose first axis is the scenario."""
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    lo, hi = shard_range(K, rank, world)
+    local = rollout_fn(lo, hi)
+    if world == 1:
+        return local
+    out = {}
+    for name in sorted(local):
+        a = np.ascontiguousarray(local[name], dtype=np.float64)
+        flat = a.reshape(a.shape[0], 1, -1)
+        out[name] = gather_packed(flat, K, dist, device).reshape((K,) + a.shape[1:])
+    return out
+
+
 def draw_x_T(w_s, x_s, n_x, seed, chain_ids, resample):
     """x_T = x_m1[:, star] with star ~ systematic_resampling(w_m1, 1) (optimal_control_Ipopt.jl:58-59), drawn on the
     rank that owns the chain so that the N-sized particle arrays never travel."""

@@ -165,7 +165,7 @@ def particle_gibbs(model, N, T, u, y, Cm, R, x0_mean, x0_chol, A_init, Q_init, V
                 w=w_s, x=x_s, x_prim=xp.reshape((n_x, T), order="F"))
 
 
-def rollout(model, K, H, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_init, seed):
+def rollout(model, K, H, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_init, seed, k_offset=0):
     """A (K,n_x,n_phi), Q (K,n_x,n_x), w_m1 (K,N), x_m1 (K,N,n_x), u_m1 (K,n_u), u_init (n_u,H)."""
     n_x, n_y = model.n_x, model.n_y
     Af = f64(np.transpose(A, (0, 2, 1)))  # per scenario column-major
@@ -175,5 +175,5 @@ def rollout(model, K, H, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_init, seed):
     X, Y = np.zeros((K, H + 1, n_x)), np.zeros((K, H, n_y))
     st = lib().orc_rollout(C.byref(model), C.c_int64(K), C.c_int64(H), C.c_int64(N), _p(Af), _p(Qf), _p(f64(w_m1)),
                            _p(f64(x_m1)), _p(f64(u_m1)), _p(fl(Cm)), _p(fl(np.atleast_2d(Le))), _p(fl(u_init)),
-                           C.c_uint64(seed), _p(x0), _p(v), _p(e), _p(X), _p(Y))
+                           C.c_uint64(seed), C.c_uint32(k_offset), _p(x0), _p(v), _p(e), _p(X), _p(Y))
     return dict(status=st, x0=x0, v=v, e=e, X=X, Y=Y)

@@ -553,3 +553,32 @@ def test_replay_mode_whole_sampler_matches_store_mode():
         _assert_same("A[%d]" % k, smp[k].A, ref["A"][k])
         _assert_same("Q[%d]" % k, smp[k].Q, ref["Q"][k])
         _assert_same("x_m1[%d]" % k, smp[k].x_m1.T, ref["x"][k])
+
+
+def test_rollout_shards_reproduce_the_unsharded_rollout():
+    """Scenario sharding (pgopt_b200.multi.rollout_sharded): shard [lo, hi) with k_offset = lo gives rows lo..hi of the
+    full rollout, and both equal the oracle."""
+    rng = np.random.default_rng(43)
+    basis, om = pg.KnownBasisVB(), O.known_model()
+    K, H, N = 23, 12, 30
+    A = rng.normal(0, 0.3, (K, 2, 5))
+    Q = np.stack([(lambda B: B @ B.T + 0.05 * np.eye(2))(rng.normal(0, 0.2, (2, 2))) for _ in range(K)])
+    w = rng.uniform(size=(K, N))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, N, 2))
+    um = rng.normal(0, 1, (K, 1))
+    u_init = rng.normal(0, 1, (1, H))
+    samples = [pg.PG_sample(A[k], Q[k], w[k], x[k].T, um[k]) for k in range(K)]
+    g = pg.LinearMeasurement([[1.0, 0.0]])
+    full = pg.scenario_rollout(samples, basis, g, 0.1, H, u_init=u_init, seed=3)["raw"]
+    ref = O.rollout(om, K, H, N, A, Q, w, x, um, [[1.0, 0.0]], [[0.1]], u_init, seed=3)
+    from pgopt_b200 import multi
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            lo, hi = multi.shard_range(K, r, world)
+            parts.append(pg.scenario_rollout(samples[lo:hi], basis, g, 0.1, H, u_init=u_init, seed=3, k_offset=lo)["raw"])
+        for name in ("x0", "v", "e", "X", "Y"):
+            cat = np.concatenate([p[name] for p in parts], axis=0)
+            _assert_same("%s world=%d" % (name, world), cat, full[name])
+            _assert_same("%s vs oracle" % name, cat, ref[name])

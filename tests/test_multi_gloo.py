@@ -81,3 +81,50 @@ def test_two_ranks_gather_equals_single_process(tmp_path):
         np.testing.assert_array_equal(got, ref)
     A, Q, xT = multi.unpack_samples(ref, 2, 5)
     assert A.shape == (N_CHAINS, K, 10) and Q.shape == (N_CHAINS, K, 4) and xT.shape == (N_CHAINS, K, 2)
+
+
+# ------------------------------------------------------------------------------------------ scenario sharding
+R_K, R_H, R_N = 7, 9, 12
+
+
+def _rollout_inputs():
+    rng = np.random.default_rng(5)
+    A = rng.normal(0, 0.3, (R_K, 2, 5))
+    Q = np.stack([(lambda B: B @ B.T + 0.05 * np.eye(2))(rng.normal(0, 0.2, (2, 2))) for _ in range(R_K)])
+    w = rng.uniform(size=(R_K, R_N))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (R_K, R_N, 2))
+    um = rng.normal(0, 1, (R_K, 1))
+    return A, Q, w, x, um, rng.normal(0, 1, (1, R_H))
+
+
+def _oracle_rollout(lo, hi):
+    A, Q, w, x, um, u_init = _rollout_inputs()
+    r = O.rollout(O.known_model(), hi - lo, R_H, R_N, A[lo:hi], Q[lo:hi], w[lo:hi], x[lo:hi], um[lo:hi], [[1.0, 0.0]], [[0.1]],
+                  u_init, seed=17, k_offset=lo)
+    assert r["status"] == 0
+    return {k: r[k] for k in ("x0", "v", "e", "X", "Y")}
+
+
+def _rollout_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        got = multi.rollout_sharded(_oracle_rollout, R_K, dist=dist)
+        np.savez(os.path.join(out_dir, "roll%d.npz" % rank), **got)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_scenario_rollout_equals_single_process(tmp_path):
+    """Scenarios sharded over two ranks (stream ids offset by the shard start) reproduce the unsharded rollout."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_rollout_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ref = _oracle_rollout(0, R_K)
+    for r in range(2):
+        got = np.load(os.path.join(str(tmp_path), "roll%d.npz" % r))
+        for k in ref:
+            assert got[k].shape == ref[k].shape
+            np.testing.assert_array_equal(got[k], ref[k])
