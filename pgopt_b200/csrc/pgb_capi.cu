@@ -917,6 +917,7 @@ extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const
   return PGB_OK;
 }
 
+static int g_rollout_kernel = -1;  // kernel the last pgb_rollout ran: 1 = warp per scenario, 0 = CTA per scenario
 static float g_rollout_ms[2] = {0.f, 0.f};  // device time of the last pgb_rollout: {H2D copies, rollout kernel}
 
 template <int NX, int NI>
@@ -931,6 +932,26 @@ static cudaError_t launch_rollout_ni(const FilterDev& fd, const RolloutDev& rd, 
 template <int NX>
 static cudaError_t launch_rollout(const FilterDev& fd, const RolloutDev& rd, size_t smem) {
   return fd.n_phi <= R_TPB ? launch_rollout_ni<NX, 1>(fd, rd, smem) : launch_rollout_ni<NX, 5>(fd, rd, smem);
+}
+
+// Warp-per-scenario kernel (default): A_k register-resident over 32 lanes, persistent grid of independent warps.
+template <int NX, int NI>
+static cudaError_t launch_rollout_warp_ni(const FilterDev& fd, const RolloutDev& rd, size_t smem, int n_sm) {
+  cudaError_t e = cudaFuncSetAttribute(k_rollout_warp<NX, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_warp<NX, NI>, RW_WPB * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (rd.K + RW_WPB - 1) / RW_WPB;
+  if (grid > (int64_t)n_sm * per_sm) grid = (int64_t)n_sm * per_sm;
+  k_rollout_warp<NX, NI><<<(unsigned)grid, RW_WPB * 32, smem>>>(fd, rd);
+  return cudaGetLastError();
+}
+template <int NX>
+static cudaError_t launch_rollout_warp(const FilterDev& fd, const RolloutDev& rd, size_t smem, int n_sm) {
+  return fd.n_phi <= 128 ? launch_rollout_warp_ni<NX, 1>(fd, rd, smem, n_sm)
+                         : launch_rollout_warp_ni<NX, RW_MAXNI>(fd, rd, smem, n_sm);
 }
 
 extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q,
@@ -991,11 +1012,33 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   if (Y) CK(h, dalloc(h, &rd.Y, (size_t)K * H * ny, false));
   CK(h, cudaEventRecord(ev[1], 0));
   rd.A = dA; rd.Q = dQ; rd.w_m1 = dw; rd.x_m1 = dx; rd.u_m1 = dum; rd.u_init = dui;
-  switch (nx) {
-    case 1: CK(h, launch_rollout<1>(fd, rd, smem)); break;
-    case 2: CK(h, launch_rollout<2>(fd, rd, smem)); break;
-    case 3: CK(h, launch_rollout<3>(fd, rd, smem)); break;
-    default: CK(h, launch_rollout<4>(fd, rd, smem)); break;
+  // kernel choice: one warp per scenario whenever A_k fits the registers of 32 lanes (n_phi <= 128 * RW_MAXNI) and
+  // the per-warp noise buffers fit shared memory; PGB_ROLLOUT_KERNEL=cta|warp forces one (tests run both)
+  const size_t smem_w = sizeof(RolloutWShared) +
+                        ((size_t)H * nu + (size_t)RW_WPB * (PGB_MAX_Z_ * MAXC + (size_t)H * (nx + ny))) * 8;
+  bool use_warp = np <= 128 * RW_MAXNI && smem_w <= 100 * 1024;
+  if (const char* kk = getenv("PGB_ROLLOUT_KERNEL")) {
+    if (!strcmp(kk, "cta")) use_warp = false;
+    else if (!strcmp(kk, "warp") && !use_warp)
+      return set_err(nullptr, PGB_ERR_INVALID, "rollout: warp kernel needs n_phi <= %d and a shorter horizon", 128 * RW_MAXNI);
+  }
+  g_rollout_kernel = use_warp ? 1 : 0;
+  if (use_warp) {
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
+    switch (nx) {
+      case 1: CK(h, launch_rollout_warp<1>(fd, rd, smem_w, n_sm)); break;
+      case 2: CK(h, launch_rollout_warp<2>(fd, rd, smem_w, n_sm)); break;
+      case 3: CK(h, launch_rollout_warp<3>(fd, rd, smem_w, n_sm)); break;
+      default: CK(h, launch_rollout_warp<4>(fd, rd, smem_w, n_sm)); break;
+    }
+  } else {
+    switch (nx) {
+      case 1: CK(h, launch_rollout<1>(fd, rd, smem)); break;
+      case 2: CK(h, launch_rollout<2>(fd, rd, smem)); break;
+      case 3: CK(h, launch_rollout<3>(fd, rd, smem)); break;
+      default: CK(h, launch_rollout<4>(fd, rd, smem)); break;
+    }
   }
   CK(h, cudaEventRecord(ev[2], 0));
   CK(h, cudaDeviceSynchronize());

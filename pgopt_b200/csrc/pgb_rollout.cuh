@@ -352,4 +352,392 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
   }
 }
 
+
+// ==========================================================================================================
+// k_rollout_warp — one WARP per scenario (default whenever A_k fits the registers of 32 lanes).
+//
+// The CTA-per-scenario kernel above spends most of its issue slots on idle lanes (20 sines on 128 threads), CTA
+// barriers (3 per step) and per-scenario start-up that nothing overlaps.  Here lane l owns the oracle's runs
+// 4l .. 4l+3 (4*c consecutive columns of A_k, register-resident for the whole horizon), so that
+//   * the first two levels of the oracle's balanced tree over the 128 runs are in-thread additions,
+//   * the remaining five levels are xor-butterflies at lane distance 1, 2, 4, 8, 16 (adjacent runs first), with the
+//     n_x components split over the lanes at the first levels (6 shuffles for n_x = 4),
+//   * the state x_t lives in registers of every lane (broadcast by shuffle), and nothing but __syncwarp() separates
+//     the steps: the warps of a CTA run different scenarios completely independently, one hides the other's
+//     latency-bound sines and start-up,
+//   * when a run is exactly one row of the last tensor dimension (c == n_phi_dims[end], e.g. 5^4 = 625 functions on
+//     128 runs) every column of a run shares its prefix product and column m has last digit m.
+// Same arithmetic, same order, same bits as the kernel above and as oracle/pg_oracle.c eval_f_blocked.
+// ==========================================================================================================
+constexpr int RW_WPB = 4;  // warps (independent scenarios) per CTA
+constexpr int RW_RPL = 4;  // runs per lane: 32 lanes x 4 = the 128 runs of the blocked product
+constexpr int RW_MAXNI = 5;
+
+struct __align__(16) RolloutWShared {
+  unsigned int dig[RW_RPL * RW_MAXNI * 32];  // packed digits of column m of run rr of lane l at [(rr*NI + m)*32 + l]
+  int sine_dim[PGB_MAX_Z_ * MAXC], sine_j[PGB_MAX_Z_ * MAXC];
+  int n_sines;
+};
+
+// Tree over the warp's lanes in the order lane^1, lane^2, lane^4, ...; component d of the result is valid in lane
+// rw_src<NX>(d) (and in every lane that agrees with it in the low bits).
+template <int NX>
+__device__ __forceinline__ double rw_tree(const double (&v)[NX], int lane) {
+  if (NX == 1) {
+    double b = v[0];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) b = __dadd_rn(b, shfl_xor_d(b, o));
+    return b;
+  } else if (NX == 2) {
+    const bool hi = lane & 1;
+    double b = __dadd_rn(hi ? v[1] : v[0], shfl_xor_d(hi ? v[0] : v[1], 1));
+#pragma unroll
+    for (int o = 2; o < 32; o <<= 1) b = __dadd_rn(b, shfl_xor_d(b, o));
+    return b;
+  } else {
+    const double v3 = (NX > 3) ? v[NX > 3 ? 3 : 0] : 0.0;
+    const bool hi = lane & 1;
+    const double a0 = __dadd_rn(hi ? v[2] : v[0], shfl_xor_d(hi ? v[0] : v[2], 1));
+    const double a1 = __dadd_rn(hi ? v3 : v[1], shfl_xor_d(hi ? v[1] : v3, 1));
+    const bool hi2 = lane & 2;
+    double b = __dadd_rn(hi2 ? a1 : a0, shfl_xor_d(hi2 ? a0 : a1, 2));
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) b = __dadd_rn(b, shfl_xor_d(b, o));
+    return b;
+  }
+}
+template <int NX>
+__device__ __forceinline__ int rw_src(int d) {
+  return NX == 1 ? 0 : (NX == 2 ? d : (((d & 1) << 1) | (d >> 1)));
+}
+
+template <int NX>
+__device__ __forceinline__ double rw_pick(const double (&x)[NX], int i) {
+  double r = x[0];
+#pragma unroll
+  for (int d = 1; d < NX; ++d) r = (i == d) ? x[d] : r;
+  return r;
+}
+
+// F = A_k * phi(x, u) in the blocked order; every lane returns all NX components.
+template <int NX, int NI>
+__device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWShared& sh, double* __restrict__ tkw,
+                                          const double (&Areg)[RW_RPL][NI][NX], const int (&ncols)[RW_RPL], int c,
+                                          int kl, const double (&x)[NX], const double* __restrict__ u,
+                                          double (&F)[NX]) {
+  const int lane = threadIdx.x & 31;
+  double P[NX];
+  if (fd.basis == 0) {
+    // examples/PG_OCP_known_basis_functions_Altro.jl:34 — five functions, run j = column j (c = 1): lane 0 owns
+    // columns 0..3, lane 1 column 4.  Every lane evaluates the five values (warp-uniform, no divergence).
+    const double x0 = x[0], x1 = x[NX > 1 ? 1 : 0], u0 = u[0];
+    const double a3[1] = {__dmul_rn(3.0, x0)}, a2[1] = {__dmul_rn(2.0, x1)};
+    double s3[1], c3[1], s2[1], c2[1];
+    vsincos_wide<1>(a3, s3, c3);
+    vsincos_wide<1>(a2, s2, c2);
+    double ph[5];
+    ph[0] = __dmul_rn(0.1, x0);
+    ph[1] = __dmul_rn(0.1, x1);
+    ph[2] = u0;
+    ph[3] = __dmul_rn(__dmul_rn(0.01, c3[0]), x1);
+    ph[4] = __dmul_rn(__dmul_rn(0.1, s2[0]), u0);
+    double part[RW_RPL][NX];
+#pragma unroll
+    for (int rr = 0; rr < RW_RPL; ++rr) {
+      const double p = (lane == 0) ? ph[rr] : ph[4];  // lane 1: only run 0 (= column 4) is live
+#pragma unroll
+      for (int d = 0; d < NX; ++d) part[rr][d] = (ncols[rr] > 0) ? __fma_rn(Areg[rr][0][d], p, 0.0) : 0.0;
+    }
+#pragma unroll
+    for (int d = 0; d < NX; ++d)
+      P[d] = __dadd_rn(__dadd_rn(part[0][d], part[1][d]), __dadd_rn(part[2][d], part[3][d]));
+  } else {
+    // Hilbert-space basis (examples/PG_OCP_generic_basis_functions_Altro.jl:85-99): one scaled sine per lane
+    for (int s = lane; s < sh.n_sines; s += 32) {
+      const int k = sh.sine_dim[s], j = sh.sine_j[s];
+      const double zk = (k < fd.n_u) ? u[k] : rw_pick<NX>(x, k - fd.n_u);
+      const double zl = __dadd_rn(zk, fd.hg_L[k]);
+      const double arg[1] = {__dmul_rn(fd.hg_pij2l[k][j], zl)};
+      double sn[1], cs[1];
+      vsincos_wide<1>(arg, sn, cs);
+      tkw[k * MAXC + j] = __dmul_rn(fd.hg_lsi[k], sn[0]);
+    }
+    __syncwarp();
+    const int nz = fd.n_z;
+    const double* tl = tkw + (nz - 1) * MAXC;
+    // product over the dimensions 0..nz-2 (digits 4 bits each, from bit 0), in the oracle's left-to-right order
+    // product over the dimensions 0..nk-1 (nk <= nz-1)
+    auto prefix_n = [&](unsigned int g, int nk) {
+      double p = 1.0;
+#pragma unroll
+      for (int k = 0; k < PGB_MAX_Z_ - 1; ++k)
+        if (k < nk) p = __dmul_rn(p, tkw[k * MAXC + ((g >> (4 * k)) & 15u)]);
+      return p;
+    };
+    auto prefix = [&](unsigned int g) { return prefix_n(g, nz - 1); };
+    double part[RW_RPL][NX];
+#pragma unroll
+    for (int rr = 0; rr < RW_RPL; ++rr)
+#pragma unroll
+      for (int d = 0; d < NX; ++d) part[rr][d] = 0.0;
+    if (kl >= 0) {
+      // aligned runs: a run is one full row of dimension kl (the last one with more than one function; at most one
+      // single-function dimension follows it) -> one prefix per run, column m has digit m in dimension kl
+      double tlm[NI];
+#pragma unroll
+      for (int m = 0; m < NI; ++m) tlm[m] = (m < c) ? tkw[kl * MAXC + m] : 0.0;
+      const bool has_tr = kl < nz - 1;
+      const double tr = tl[0];
+#pragma unroll
+      for (int rr = 0; rr < RW_RPL; ++rr) {
+        const double pre = prefix_n(sh.dig[(rr * NI) * 32 + lane], kl);
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+          if (m < ncols[rr]) {
+            double p = __dmul_rn(pre, tlm[m]);
+            if (has_tr) p = __dmul_rn(p, tr);
+#pragma unroll
+            for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(Areg[rr][m][d], p, part[rr][d]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < RW_RPL; ++rr) {
+        unsigned int gprev = 0u;
+        double pre = 1.0;
+#pragma unroll
+        for (int m = 0; m < NI; ++m) {
+          if (m < c) {  // warp-uniform
+            const unsigned int g = sh.dig[(rr * NI + m) * 32 + lane];
+            const bool live = m < ncols[rr];
+            const bool need = live && (m == 0 || (g & 0x0fffffffu) != (gprev & 0x0fffffffu));
+            if (__any_sync(0xffffffffu, need)) {
+              const double pn = prefix(g);
+              if (need) pre = pn;
+            }
+            if (live) {
+              const double p = __dmul_rn(pre, tl[g >> 28]);
+#pragma unroll
+              for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(Areg[rr][m][d], p, part[rr][d]);
+            }
+            gprev = g;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < NX; ++d)
+      P[d] = __dadd_rn(__dadd_rn(part[0][d], part[1][d]), __dadd_rn(part[2][d], part[3][d]));
+    __syncwarp();  // tkw is rewritten by the next evaluation
+  }
+  const double b = rw_tree<NX>(P, lane);
+#pragma unroll
+  for (int d = 0; d < NX; ++d) F[d] = __shfl_sync(0xffffffffu, b, rw_src<NX>(d));
+}
+
+#ifndef PGB_ROLLOUT_W_MINBLOCKS
+#define PGB_ROLLOUT_W_MINBLOCKS 2
+#endif
+template <int NX, int NI>
+__global__ void __launch_bounds__(RW_WPB * 32, PGB_ROLLOUT_W_MINBLOCKS)
+k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ RolloutDev rd) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RolloutWShared& sh = *reinterpret_cast<RolloutWShared*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t K = rd.K, H = rd.H, N = rd.N;
+  const int ny = fd.n_y, nu = fd.n_u, n_phi = fd.n_phi, nz = fd.n_z;
+  double* us = reinterpret_cast<double*>(smem_raw + sizeof(RolloutWShared));  // [H][nu] planned inputs (CTA-wide)
+  const int64_t per_warp = PGB_MAX_Z_ * MAXC + H * (NX + ny);
+  double* tkw = us + H * nu + (int64_t)warp * per_warp;  // [n_z][MAXC] scaled sines of the warp's scenario
+  double* vs = tkw + PGB_MAX_Z_ * MAXC;                  // [H][NX] process noise
+  double* es = vs + H * NX;                              // [H][ny] measurement noise
+
+  // ---- model tables shared by every scenario (CTA-wide, once)
+  const int c = (n_phi + 128 - 1) / 128;
+  for (int i = tid; i < RW_RPL * NI * 32; i += RW_WPB * 32) {
+    const int l = i & 31, rm = i >> 5, rr = rm / NI, m = rm % NI;
+    const int col = (RW_RPL * l + rr) * c + m;
+    sh.dig[i] = (fd.basis != 0 && m < c && col < n_phi) ? rollout_digits(fd, col) : 0u;
+  }
+  if (tid == 0) {
+    int s = 0;
+    if (fd.basis != 0)
+      for (int kk = 0; kk < nz; ++kk)
+        for (int j = 0; j < fd.hg_count[kk]; ++j) {
+          sh.sine_dim[s] = kk;
+          sh.sine_j[s] = j;
+          ++s;
+        }
+    sh.n_sines = s;
+  }
+  for (int64_t i = tid; i < H * nu; i += RW_WPB * 32) us[i] = rd.u_init[i];
+  __syncthreads();
+  int ncols[RW_RPL];
+#pragma unroll
+  for (int rr = 0; rr < RW_RPL; ++rr) {
+    const int first = (RW_RPL * lane + rr) * c;
+    int n = n_phi - first;
+    ncols[rr] = n < 0 ? 0 : (n > c ? c : n);
+  }
+  // aligned runs (see rw_eval_F): c columns per run = one full row of the last dimension that has more than one function
+  int kl = -1;
+  if (fd.basis != 0) {
+    int k2 = nz - 1;
+    while (k2 > 0 && fd.hg_count[k2] == 1) --k2;
+    if (c == fd.hg_count[k2] && nz - 1 - k2 <= 1) kl = k2;
+  }
+
+  for (int64_t k = (int64_t)blockIdx.x * RW_WPB + warp; k < K; k += (int64_t)gridDim.x * RW_WPB) {
+    const uint32_t cid = rd.k_offset + (uint32_t)k;
+    const double* Ag = rd.A + k * (int64_t)NX * n_phi;
+    // ---- A_k -> registers (read from HBM exactly once)
+    double Areg[RW_RPL][NI][NX];
+#pragma unroll
+    for (int rr = 0; rr < RW_RPL; ++rr)
+#pragma unroll
+      for (int m = 0; m < NI; ++m) {
+        const int64_t col = (int64_t)(RW_RPL * lane + rr) * c + m;
+        if (NX % 2 == 0) {
+#pragma unroll
+          for (int d = 0; d < NX; d += 2) {
+            double2 a = make_double2(0.0, 0.0);
+            if (m < ncols[rr]) a = __ldg(reinterpret_cast<const double2*>(Ag + NX * col + d));
+            Areg[rr][m][d] = a.x;
+            Areg[rr][m][d + 1 < NX ? d + 1 : d] = a.y;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < NX; ++d) Areg[rr][m][d] = (m < ncols[rr]) ? __ldg(Ag + NX * col + d) : 0.0;
+        }
+      }
+    // ---- chol(Q_k) (every lane; n_x <= 4)
+    double Lq[NX * NX];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) Lq[i] = rd.Q[k * NX * NX + i];
+    if (small_chol(Lq, NX)) {  // warp-uniform
+      if (lane == 0) atomicOr(rd.status, 16);
+      continue;
+    }
+    // ---- noise of the whole horizon, one step per lane:  v_vec[:, t, k] (:72), e_vec[:, t, k] (:81)
+    for (int64_t t = lane; t < H; t += 32) {
+      double z[4];
+      rollout_normals<(NX + 1) / 2>(rd.seed, cid, 2, (uint32_t)(t * ((NX + 1) / 2)), z);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
+        vs[t * NX + d] = acc;
+        if (rd.v) rd.v[(k * H + t) * NX + d] = acc;
+      }
+      const int npairs = (ny + 1) / 2;
+      if (npairs == 1) rollout_normals<1>(rd.seed, cid, 3, (uint32_t)t, z);
+      else rollout_normals<2>(rd.seed, cid, 3, (uint32_t)(t * 2), z);
+      for (int o = 0; o < ny; ++o) {
+        double acc = 0.0;
+        for (int e2 = 0; e2 <= o; ++e2) acc = __fma_rn(rd.Le[o + ny * e2], z[e2], acc);
+        es[t * ny + o] = acc;
+        if (rd.e) rd.e[(k * H + t) * ny + o] = acc;
+      }
+    }
+    // ---- x0 noise (:62), every lane redundantly
+    double x0n[NX];
+    {
+      double z[4];
+      rollout_normals<(NX + 1) / 2>(rd.seed, cid, 1, 0u, z);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
+        x0n[d] = acc;
+      }
+    }
+    // ---- star = systematic_resampling(w_m1, 1) (:58): S = tree sum of w; first n with q_n >= u, q sequential
+    double x[NX];
+    {
+      const double* wg = rd.w_m1 + k * N;
+      int64_t P = 1;
+      while (P < N) P <<= 1;
+      double S;
+      if (P >= 32) {
+        const int64_t per = P / 32, base = (int64_t)lane * per;
+        double st[40];
+        int sp = 0;
+        for (int64_t i = 0; i < per; ++i) {
+          double xv = (base + i < N) ? wg[base + i] : 0.0;
+          const int merges = __ffsll((long long)(i + 1)) - 1;
+          for (int m = 0; m < merges; ++m) xv = __dadd_rn(st[--sp], xv);
+          st[sp++] = xv;
+        }
+        S = st[0];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) S = __dadd_rn(S, shfl_xor_d(S, o));
+      } else {
+        S = (lane < N) ? wg[lane] : 0.0;
+        for (int o = 1; o < (int)P; o <<= 1) S = __dadd_rn(S, shfl_xor_d(S, o));
+        S = __shfl_sync(0xffffffffu, S, 0);
+      }
+      const pgb_u32x4 b = pgb_stream_block(rd.seed, PGB_STREAM_ROLL, cid, 0, 0, 0);
+      const double ust = pgb_u53_halfopen(b.v[0], b.v[1]);
+      double q = 0.0;
+      int64_t n = 0;
+      bool over = false;
+      for (int64_t base = 0;; base += 32) {  // every lane walks the same (uniform) path
+        if (!(q < ust)) break;
+        if (base >= N) { over = true; break; }
+        const double Wl = (base + lane < N) ? __ddiv_rn(wg[base + lane], S) : 0.0;
+        const int lim = (N - base < 32) ? (int)(N - base) : 32;
+        for (int l = 0; l < lim; ++l) {
+          if (!(q < ust)) break;
+          ++n;
+          q = __dadd_rn(q, __shfl_sync(0xffffffffu, Wl, l));
+        }
+      }
+      if (over) {
+        if (lane == 0) atomicOr(rd.status, 1);
+        n = N;
+      }
+      if (n == 0) {
+        if (lane == 0) atomicOr(rd.status, 2);
+        n = 1;
+      }
+      const int64_t star = n - 1;
+#pragma unroll
+      for (int d = 0; d < NX; ++d) x[d] = rd.x_m1[(k * N + star) * NX + d];
+    }
+    __syncwarp();
+    // ---- x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62)
+    double F[NX];
+    rw_eval_F<NX, NI>(fd, sh, tkw, Areg, ncols, c, kl, x, rd.u_m1 + k * nu, F);
+#pragma unroll
+    for (int d = 0; d < NX; ++d) x[d] = __dadd_rn(F[d], x0n[d]);
+    if (lane == 0) {
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        if (rd.x0) rd.x0[k * NX + d] = x[d];
+        if (rd.X) rd.X[(k * (H + 1)) * NX + d] = x[d];
+      }
+    }
+    // ---- horizon: Y[t] = g(X[t]) + e (:122), X[t+1] = f(X[t], u_t) + v (:121)
+    for (int64_t t = 0; t < H; ++t) {
+      if (lane < ny && rd.Y) {
+        double g = 0.0;
+#pragma unroll
+        for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[lane + ny * d], x[d], g);
+        rd.Y[(k * H + t) * ny + lane] = __dadd_rn(g, es[t * ny + lane]);
+      }
+      rw_eval_F<NX, NI>(fd, sh, tkw, Areg, ncols, c, kl, x, us + (int64_t)nu * t, F);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) x[d] = __dadd_rn(F[d], vs[t * NX + d]);
+      if (lane == 0 && rd.X) {
+#pragma unroll
+        for (int d = 0; d < NX; ++d) rd.X[(k * (H + 1) + t + 1) * NX + d] = x[d];
+      }
+    }
+    __syncwarp();  // vs / es are rewritten by the next scenario
+  }
+}
+
 }  // namespace pgb

@@ -405,8 +405,15 @@ def test_batched_chains_match_single_chains():
 
 
 # ------------------------------------------------------------------------------------------ rollout
+@pytest.fixture(params=["warp", "cta"])
+def rollout_kernel(request, monkeypatch):
+    """pgb_rollout picks the warp-per-scenario kernel by default; PGB_ROLLOUT_KERNEL forces either one."""
+    monkeypatch.setenv("PGB_ROLLOUT_KERNEL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("model", ["known", "hilbert4"])
-def test_rollout_bit_exact(model):
+def test_rollout_bit_exact(model, rollout_kernel):
     rng = np.random.default_rng(41)
     if model == "known":
         basis, om = pg.KnownBasisVB(), O.known_model()
@@ -436,6 +443,73 @@ def test_rollout_bit_exact(model):
     assert out["X_init"].shape == (n_x * K, H + 1) and out["Y_init"].shape == (K, H)
     np.testing.assert_array_equal(out["X_init"][n_x * 3:n_x * 4, 5], ref["X"][3, 5])
     np.testing.assert_array_equal(out["v_vec"][:, 7, 2], ref["v"][2, 7])
+
+
+@pytest.mark.parametrize("n_x,n_y,dims,N,K,H", [
+    (4, 1, [1, 5, 5, 5, 5], 30, 9, 41),      # configs[4] shape: n_phi = 625, runs aligned with the last dimension
+    (4, 2, [2, 3, 5, 3, 4], 33, 7, 17),      # n_phi = 360: 3 columns per run, last dimension 4 (unaligned runs)
+    (4, 1, [1, 5, 5, 5, 4], 1, 5, 9),        # n_phi = 500: ragged last runs, a single particle
+    (3, 1, [2, 5, 5, 5], 2500, 6, 12),       # n_x = 3; w_m1 longer than a warp chunk (tree + chunked walk)
+    (2, 2, [5, 5, 5], 100, 11, 70),          # configs[1] basis; horizon longer than a warp
+    (1, 1, [3, 7], 64, 8, 5),                # n_x = 1
+    (2, 1, [1, 8, 8], 4097, 4, 6),           # N just above a power of two
+])
+def test_rollout_bit_exact_shapes(n_x, n_y, dims, N, K, H, rollout_kernel):
+    rng = np.random.default_rng(47 + n_x + N)
+    L = [4.0 + k for k in range(len(dims))]
+    basis = pg.HilbertGPBasis(dims, L)
+    om = O.hilbert_model(n_x, len(dims) - n_x, basis.count, basis.stride, basis.L, n_y=n_y)
+    n_u, n_phi = len(dims) - n_x, basis.n_phi
+    A = rng.normal(0, 0.3, (K, n_x, n_phi))
+    Q = np.stack([(lambda B: B @ B.T + 0.05 * np.eye(n_x))(rng.normal(0, 0.2, (n_x, n_x))) for _ in range(K)])
+    w = rng.uniform(size=(K, N)) ** 3
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, N, n_x))
+    um = rng.normal(0, 1, (K, n_u))
+    Cm = rng.normal(0, 1, (n_y, n_x))
+    Br = rng.normal(0, 0.2, (n_y, n_y))
+    R = Br @ Br.T + 0.05 * np.eye(n_y)
+    u_init = rng.normal(0, 1, (n_u, H))
+    ref = O.rollout(om, K, H, N, A, Q, w, x, um, Cm, np.linalg.cholesky(R), u_init, seed=23, k_offset=5)
+    samples = [pg.PG_sample(A[k], Q[k], w[k], x[k].T, um[k]) for k in range(K)]
+    out = pg.scenario_rollout(samples, basis, pg.LinearMeasurement(Cm), R, H, u_init=u_init, seed=23, k_offset=5)
+    assert ref["status"] == 0
+    for name in ("x0", "v", "e", "X", "Y"):
+        _assert_same(name, out["raw"][name], ref[name])
+
+
+def test_rollout_many_scenarios_persistent_grid(rollout_kernel):
+    """More scenarios than resident warps: the warp kernel walks them with a grid stride; every one must still be the
+    oracle's (checked on a strided subset) and the two kernels must agree on all of them."""
+    rng = np.random.default_rng(5)
+    basis = pg.HilbertGPBasis([1, 5, 5, 5, 5], [4.0, 5.0, 6.0, 7.0, 8.0])
+    om = O.hilbert_model(4, 1, basis.count, basis.stride, basis.L)
+    K, H, N, n_x = 3001, 11, 30, 4
+    A = rng.normal(0, 0.05, (K, n_x, basis.n_phi))
+    Bq = rng.normal(0, 0.1, (K, n_x, n_x))
+    Q = Bq @ np.transpose(Bq, (0, 2, 1)) + 0.05 * np.eye(n_x)
+    w = rng.uniform(size=(K, N))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, N, n_x))
+    um = rng.normal(0, 1, (K, 1))
+    Cm = np.zeros((1, n_x))
+    Cm[0, 0] = 1.0
+    u_init = np.sin(np.arange(H))[None, :]
+    samples = [pg.PG_sample(A[k], Q[k], w[k], x[k].T, um[k]) for k in range(K)]
+    out = pg.scenario_rollout(samples, basis, pg.LinearMeasurement(Cm), 0.1, H, u_init=u_init, seed=1)["raw"]
+    sel = np.arange(0, K, 97)
+    for k in sel:
+        ref = O.rollout(om, 1, H, N, A[k:k + 1], Q[k:k + 1], w[k:k + 1], x[k:k + 1], um[k:k + 1], Cm, [[0.1]], u_init,
+                        seed=1, k_offset=int(k))
+        for name in ("x0", "v", "e", "X", "Y"):
+            _assert_same("%s[%d]" % (name, k), out[name][k:k + 1], ref[name])
+    import hashlib
+    digest = hashlib.sha256(b"".join(out[n].tobytes() for n in ("x0", "v", "e", "X", "Y"))).hexdigest()
+    seen = _ROLLOUT_DIGESTS.setdefault("many", digest)
+    assert seen == digest, "warp-per-scenario and CTA-per-scenario kernels disagree"
+
+
+_ROLLOUT_DIGESTS = {}
 
 
 # ------------------------------------------------------------------------------------------ other state / output dimensions
