@@ -419,12 +419,18 @@ __device__ __forceinline__ double rw_pick(const double (&x)[NX], int i) {
   return r;
 }
 
+// constants of the one sine a lane evaluates per step (n_sines <= 32): dimension, slot in tk, L_k, pi j / (2 L_k), 1/sqrt(L_k)
+struct RwSine {
+  int k, off;
+  double L, pij2l, lsi;
+};
+
 // F = A_k * phi(x, u) in the blocked order; every lane returns all NX components.
 template <int NX, int NI>
 __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWShared& sh, double* __restrict__ tkw,
                                           const double (&Areg)[RW_RPL][NI][NX], const int (&ncols)[RW_RPL], int c,
-                                          int kl, const double (&x)[NX], const double* __restrict__ u,
-                                          double (&F)[NX]) {
+                                          int kl, const RwSine& ls, const double (&x)[NX],
+                                          const double* __restrict__ u, double (&F)[NX]) {
   const int lane = threadIdx.x & 31;
   double P[NX];
   if (fd.basis == 0) {
@@ -453,28 +459,36 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
       P[d] = __dadd_rn(__dadd_rn(part[0][d], part[1][d]), __dadd_rn(part[2][d], part[3][d]));
   } else {
     // Hilbert-space basis (examples/PG_OCP_generic_basis_functions_Altro.jl:85-99): one scaled sine per lane
-    for (int s = lane; s < sh.n_sines; s += 32) {
-      const int k = sh.sine_dim[s], j = sh.sine_j[s];
-      const double zk = (k < fd.n_u) ? u[k] : rw_pick<NX>(x, k - fd.n_u);
-      const double zl = __dadd_rn(zk, fd.hg_L[k]);
-      const double arg[1] = {__dmul_rn(fd.hg_pij2l[k][j], zl)};
-      double sn[1], cs[1];
-      vsincos_wide<1>(arg, sn, cs);
-      tkw[k * MAXC + j] = __dmul_rn(fd.hg_lsi[k], sn[0]);
+    if (sh.n_sines <= 32) {  // the lane's sine is the same for every step and scenario: its constants sit in registers
+      if (lane < sh.n_sines) {
+        const double zk = (ls.k < fd.n_u) ? u[ls.k] : rw_pick<NX>(x, ls.k - fd.n_u);
+        const double arg[1] = {__dmul_rn(ls.pij2l, __dadd_rn(zk, ls.L))};
+        double sn[1], cs[1];
+        vsincos_wide<1>(arg, sn, cs);
+        tkw[ls.off] = __dmul_rn(ls.lsi, sn[0]);
+      }
+    } else {
+      for (int s = lane; s < sh.n_sines; s += 32) {
+        const int k = sh.sine_dim[s], j = sh.sine_j[s];
+        const double zk = (k < fd.n_u) ? u[k] : rw_pick<NX>(x, k - fd.n_u);
+        const double zl = __dadd_rn(zk, fd.hg_L[k]);
+        const double arg[1] = {__dmul_rn(fd.hg_pij2l[k][j], zl)};
+        double sn[1], cs[1];
+        vsincos_wide<1>(arg, sn, cs);
+        tkw[k * MAXC + j] = __dmul_rn(fd.hg_lsi[k], sn[0]);
+      }
     }
     __syncwarp();
     const int nz = fd.n_z;
     const double* tl = tkw + (nz - 1) * MAXC;
     // product over the dimensions 0..nz-2 (digits 4 bits each, from bit 0), in the oracle's left-to-right order
-    // product over the dimensions 0..nk-1 (nk <= nz-1)
-    auto prefix_n = [&](unsigned int g, int nk) {
+    auto prefix = [&](unsigned int g) {
       double p = 1.0;
 #pragma unroll
       for (int k = 0; k < PGB_MAX_Z_ - 1; ++k)
-        if (k < nk) p = __dmul_rn(p, tkw[k * MAXC + ((g >> (4 * k)) & 15u)]);
+        if (k < nz - 1) p = __dmul_rn(p, tkw[k * MAXC + ((g >> (4 * k)) & 15u)]);
       return p;
     };
-    auto prefix = [&](unsigned int g) { return prefix_n(g, nz - 1); };
     double part[RW_RPL][NX];
 #pragma unroll
     for (int rr = 0; rr < RW_RPL; ++rr)
@@ -482,24 +496,47 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
       for (int d = 0; d < NX; ++d) part[rr][d] = 0.0;
     if (kl >= 0) {
       // aligned runs: a run is one full row of dimension kl (the last one with more than one function; at most one
-      // single-function dimension follows it) -> one prefix per run, column m has digit m in dimension kl
-      double tlm[NI];
-#pragma unroll
-      for (int m = 0; m < NI; ++m) tlm[m] = (m < c) ? tkw[kl * MAXC + m] : 0.0;
-      const bool has_tr = kl < nz - 1;
-      const double tr = tl[0];
+      // single-function dimension follows it) -> one prefix per run, column m has digit m in dimension kl.
+      // Columns beyond n_phi carry A = 0 and digit 0: fma(0, p, acc) leaves acc unchanged (p is a finite product of
+      // sines unless the state itself is already non-finite), so there is no per-column predicate.
+      unsigned int g[RW_RPL];
+      double pre[RW_RPL];
 #pragma unroll
       for (int rr = 0; rr < RW_RPL; ++rr) {
-        const double pre = prefix_n(sh.dig[(rr * NI) * 32 + lane], kl);
+        g[rr] = sh.dig[(rr * NI) * 32 + lane];
+        pre[rr] = 1.0;
+      }
+      const double* tkk = tkw;
+      for (int k = 0; k < kl; ++k) {  // the four runs' prefix products, interleaved (left to right over the dimensions)
 #pragma unroll
-        for (int m = 0; m < NI; ++m) {
-          if (m < ncols[rr]) {
-            double p = __dmul_rn(pre, tlm[m]);
-            if (has_tr) p = __dmul_rn(p, tr);
+        for (int rr = 0; rr < RW_RPL; ++rr) {
+          pre[rr] = __dmul_rn(pre[rr], tkk[g[rr] & 15u]);
+          g[rr] >>= 4;
+        }
+        tkk += MAXC;
+      }
+      double tlm[NI];
+#pragma unroll
+      for (int m = 0; m < NI; ++m) tlm[m] = (m < c) ? tkk[m] : 0.0;
+      if (kl < nz - 1) {
+        const double tr = tl[0];
+#pragma unroll
+        for (int rr = 0; rr < RW_RPL; ++rr)
+#pragma unroll
+          for (int m = 0; m < NI; ++m) {
+            const double p = __dmul_rn(__dmul_rn(pre[rr], tlm[m]), tr);
 #pragma unroll
             for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(Areg[rr][m][d], p, part[rr][d]);
           }
-        }
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < RW_RPL; ++rr)
+#pragma unroll
+          for (int m = 0; m < NI; ++m) {
+            const double p = __dmul_rn(pre[rr], tlm[m]);
+#pragma unroll
+            for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(Areg[rr][m][d], p, part[rr][d]);
+          }
       }
     } else {
 #pragma unroll
@@ -586,6 +623,16 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
     int k2 = nz - 1;
     while (k2 > 0 && fd.hg_count[k2] == 1) --k2;
     if (c == fd.hg_count[k2] && nz - 1 - k2 <= 1) kl = k2;
+  }
+
+  RwSine ls;
+  ls.k = 0; ls.off = 0; ls.L = 0.0; ls.pij2l = 0.0; ls.lsi = 0.0;
+  if (fd.basis != 0 && lane < sh.n_sines) {
+    ls.k = sh.sine_dim[lane];
+    ls.off = ls.k * MAXC + sh.sine_j[lane];
+    ls.L = fd.hg_L[ls.k];
+    ls.pij2l = fd.hg_pij2l[ls.k][sh.sine_j[lane]];
+    ls.lsi = fd.hg_lsi[ls.k];
   }
 
   for (int64_t k = (int64_t)blockIdx.x * RW_WPB + warp; k < K; k += (int64_t)gridDim.x * RW_WPB) {
@@ -710,7 +757,7 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
     __syncwarp();
     // ---- x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62)
     double F[NX];
-    rw_eval_F<NX, NI>(fd, sh, tkw, Areg, ncols, c, kl, x, rd.u_m1 + k * nu, F);
+    rw_eval_F<NX, NI>(fd, sh, tkw, Areg, ncols, c, kl, ls, x, rd.u_m1 + k * nu, F);
 #pragma unroll
     for (int d = 0; d < NX; ++d) x[d] = __dadd_rn(F[d], x0n[d]);
     if (lane == 0) {
@@ -728,7 +775,7 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
         for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[lane + ny * d], x[d], g);
         rd.Y[(k * H + t) * ny + lane] = __dadd_rn(g, es[t * ny + lane]);
       }
-      rw_eval_F<NX, NI>(fd, sh, tkw, Areg, ncols, c, kl, x, us + (int64_t)nu * t, F);
+      rw_eval_F<NX, NI>(fd, sh, tkw, Areg, ncols, c, kl, ls, x, us + (int64_t)nu * t, F);
 #pragma unroll
       for (int d = 0; d < NX; ++d) x[d] = __dadd_rn(F[d], vs[t * NX + d]);
       if (lane == 0 && rd.X) {
