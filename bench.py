@@ -324,7 +324,7 @@ def run_gpu(args):
     if rank == 0:
         if world == 1 and not args.no_secondary:
             try:
-                out["secondary"] = secondary_measurements()
+                out["secondary"] = secondary_measurements(fp64_peak.value)
             except Exception as e:  # never let the side measurements take the headline line down
                 out["secondary"] = {"error": repr(e)}
         print(json.dumps(out))
@@ -332,7 +332,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def secondary_measurements():
+def secondary_measurements(fp64_peak_tflops=None):
     """The other SURVEY.md section-8 rows, bounded: scenario rollout at the BASELINE.json configs[4] shape
     (K scaled to 20000) and chain-batched PG sweeps at the configs[3] shape (8 chains per GPU, one sweep)."""
     import pgopt_b200 as pg
@@ -363,6 +363,14 @@ def secondary_measurements():
                       "kernel_ms": kms.value, "scenario_steps_per_s_kernel": K * H / (kms.value * 1e-3),
                       "hbm_GBps_algorithmic": bytes_alg / (kms.value * 1e-3) / 1e9, "alloc_h2d_ms": h2d.value,
                       "host_call_s_incl_python_packing": dt}
+    # FP64 side of the roofline (2 n_x n_phi + ~20 sines + ~780 multiplications ~ 6.6 kflop
+    # per scenario-step; AI ~ 12 flop/B, so the FP64 pipe binds before HBM does)
+    flops = 6600.0 * K * (H + 1)
+    res["rollout"]["fp64_tflops_algorithmic"] = flops / (kms.value * 1e-3) / 1e12
+    if fp64_peak_tflops:
+        res["rollout"]["fp64_frac_of_measured_dfma_peak"] = res["rollout"]["fp64_tflops_algorithmic"] / fp64_peak_tflops
+    peak_hbm, _ = measured_peaks()
+    res["rollout"]["hbm_frac"] = res["rollout"]["hbm_GBps_algorithmic"] / peak_hbm
     nc, Nc, Tc = 8, 2 ** 16, 2000
     prob = build_problem("known", Tc, 0)
     eng = pg.ParticleGibbsEngine(prob["basis"], 1, Nc, Tc, n_chains=nc)

@@ -917,6 +917,7 @@ extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const
   return PGB_OK;
 }
 
+static int g_rollout_grid[3] = {0, 0, 0};  // last warp-kernel launch: {CTAs, CTAs per SM, runs of A in shared memory}
 static int g_rollout_kernel = -1;  // kernel the last pgb_rollout ran: 1 = warp per scenario, 0 = CTA per scenario
 static float g_rollout_ms[2] = {0.f, 0.f};  // device time of the last pgb_rollout: {H2D copies, rollout kernel}
 
@@ -934,24 +935,35 @@ static cudaError_t launch_rollout(const FilterDev& fd, const RolloutDev& rd, siz
   return fd.n_phi <= R_TPB ? launch_rollout_ni<NX, 1>(fd, rd, smem) : launch_rollout_ni<NX, 5>(fd, rd, smem);
 }
 
-// Warp-per-scenario kernel (default): A_k register-resident over 32 lanes, persistent grid of independent warps.
-template <int NX, int NI>
-static cudaError_t launch_rollout_warp_ni(const FilterDev& fd, const RolloutDev& rd, size_t smem, int n_sm) {
-  cudaError_t e = cudaFuncSetAttribute(k_rollout_warp<NX, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// Warp-per-scenario kernel (default): A_k resident over 32 lanes (RS of each lane's 4 runs in shared memory, the
+// rest in registers), persistent grid of independent warps.
+static size_t rollout_warp_smem(int nx, int ny, int nu, int64_t H, int ni, int rs) {
+  return sizeof(RolloutWShared) +
+         ((size_t)H * nu + (size_t)RW_WPB * (PGB_MAX_Z_ * MAXC + (size_t)H * (nx + ny) + (size_t)rs * ni * nx * 32)) * 8;
+}
+template <int NX, int NI, int RS>
+static cudaError_t launch_rollout_warp_ni(const FilterDev& fd, const RolloutDev& rd, int n_sm) {
+  const size_t smem = rollout_warp_smem(NX, fd.n_y, fd.n_u, rd.H, NI, RS);
+  cudaError_t e = cudaFuncSetAttribute(k_rollout_warp<NX, NI, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_warp<NX, NI>, RW_WPB * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_warp<NX, NI, RS>, RW_WPB * 32, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (rd.K + RW_WPB - 1) / RW_WPB;
   if (grid > (int64_t)n_sm * per_sm) grid = (int64_t)n_sm * per_sm;
-  k_rollout_warp<NX, NI><<<(unsigned)grid, RW_WPB * 32, smem>>>(fd, rd);
+  g_rollout_grid[0] = (int)grid; g_rollout_grid[1] = per_sm; g_rollout_grid[2] = RS;
+  k_rollout_warp<NX, NI, RS><<<(unsigned)grid, RW_WPB * 32, smem>>>(fd, rd);
   return cudaGetLastError();
 }
 template <int NX>
-static cudaError_t launch_rollout_warp(const FilterDev& fd, const RolloutDev& rd, size_t smem, int n_sm) {
-  return fd.n_phi <= 128 ? launch_rollout_warp_ni<NX, 1>(fd, rd, smem, n_sm)
-                         : launch_rollout_warp_ni<NX, RW_MAXNI>(fd, rd, smem, n_sm);
+static cudaError_t launch_rollout_warp(const FilterDev& fd, const RolloutDev& rd, int n_sm, int rs) {
+  if (fd.n_phi <= 128) return launch_rollout_warp_ni<NX, 1, 0>(fd, rd, n_sm);
+  switch (rs) {
+    case 0: return launch_rollout_warp_ni<NX, RW_MAXNI, 0>(fd, rd, n_sm);
+    case 3: return launch_rollout_warp_ni<NX, RW_MAXNI, 3>(fd, rd, n_sm);
+    default: return launch_rollout_warp_ni<NX, RW_MAXNI, 2>(fd, rd, n_sm);
+  }
 }
 
 extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q,
@@ -1014,8 +1026,10 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   rd.A = dA; rd.Q = dQ; rd.w_m1 = dw; rd.x_m1 = dx; rd.u_m1 = dum; rd.u_init = dui;
   // kernel choice: one warp per scenario whenever A_k fits the registers of 32 lanes (n_phi <= 128 * RW_MAXNI) and
   // the per-warp noise buffers fit shared memory; PGB_ROLLOUT_KERNEL=cta|warp forces one (tests run both)
-  const size_t smem_w = sizeof(RolloutWShared) +
-                        ((size_t)H * nu + (size_t)RW_WPB * (PGB_MAX_Z_ * MAXC + (size_t)H * (nx + ny))) * 8;
+  int rs = 2;  // runs (of 4 per lane) of A_k kept in shared memory; PGB_ROLLOUT_RS=0|2|3 (experiments)
+  if (const char* e2 = getenv("PGB_ROLLOUT_RS")) rs = atoi(e2);
+  if (rs != 0 && rs != 3) rs = 2;
+  const size_t smem_w = rollout_warp_smem(nx, ny, nu, H, np <= 128 ? 1 : RW_MAXNI, np <= 128 ? 0 : rs);
   bool use_warp = np <= 128 * RW_MAXNI && smem_w <= 100 * 1024;
   if (const char* kk = getenv("PGB_ROLLOUT_KERNEL")) {
     if (!strcmp(kk, "cta")) use_warp = false;
@@ -1027,10 +1041,10 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
     switch (nx) {
-      case 1: CK(h, launch_rollout_warp<1>(fd, rd, smem_w, n_sm)); break;
-      case 2: CK(h, launch_rollout_warp<2>(fd, rd, smem_w, n_sm)); break;
-      case 3: CK(h, launch_rollout_warp<3>(fd, rd, smem_w, n_sm)); break;
-      default: CK(h, launch_rollout_warp<4>(fd, rd, smem_w, n_sm)); break;
+      case 1: CK(h, launch_rollout_warp<1>(fd, rd, n_sm, rs)); break;
+      case 2: CK(h, launch_rollout_warp<2>(fd, rd, n_sm, rs)); break;
+      case 3: CK(h, launch_rollout_warp<3>(fd, rd, n_sm, rs)); break;
+      default: CK(h, launch_rollout_warp<4>(fd, rd, n_sm, rs)); break;
     }
   } else {
     switch (nx) {

@@ -425,10 +425,22 @@ struct RwSine {
   double L, pij2l, lsi;
 };
 
+// Column m of run rr, component d of the lane's part of A_k: runs 0 .. RW_RPL-RS-1 sit in registers, the last RS
+// runs in the warp's shared-memory slice (lane-private slots [(rs*NI + m)*NX + d][lane]: conflict-free, no
+// synchronisation needed — a lane only reads what it wrote).
+template <int NX, int NI, int RS>
+__device__ __forceinline__ double rw_A(const double (&Areg)[RW_RPL - RS > 0 ? RW_RPL - RS : 1][NI][NX],
+                                       const double* __restrict__ As, int rr, int m, int d, int lane) {
+  constexpr int NR = RW_RPL - RS;
+  if (rr < NR) return Areg[rr < NR ? rr : 0][m][d];
+  return As[(((rr - NR) * NI + m) * NX + d) * 32 + lane];
+}
+
 // F = A_k * phi(x, u) in the blocked order; every lane returns all NX components.
-template <int NX, int NI>
+template <int NX, int NI, int RS>
 __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWShared& sh, double* __restrict__ tkw,
-                                          const double (&Areg)[RW_RPL][NI][NX], const int (&ncols)[RW_RPL], int c,
+                                          const double (&Areg)[RW_RPL - RS > 0 ? RW_RPL - RS : 1][NI][NX],
+                                          const double* __restrict__ As, const int (&ncols)[RW_RPL], int c,
                                           int kl, const RwSine& ls, const double (&x)[NX],
                                           const double* __restrict__ u, double (&F)[NX]) {
   const int lane = threadIdx.x & 31;
@@ -452,7 +464,7 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
     for (int rr = 0; rr < RW_RPL; ++rr) {
       const double p = (lane == 0) ? ph[rr] : ph[4];  // lane 1: only run 0 (= column 4) is live
 #pragma unroll
-      for (int d = 0; d < NX; ++d) part[rr][d] = (ncols[rr] > 0) ? __fma_rn(Areg[rr][0][d], p, 0.0) : 0.0;
+      for (int d = 0; d < NX; ++d) part[rr][d] = (ncols[rr] > 0) ? __fma_rn(rw_A<NX, NI, RS>(Areg, As, rr, 0, d, lane), p, 0.0) : 0.0;
     }
 #pragma unroll
     for (int d = 0; d < NX; ++d)
@@ -526,7 +538,7 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
           for (int m = 0; m < NI; ++m) {
             const double p = __dmul_rn(__dmul_rn(pre[rr], tlm[m]), tr);
 #pragma unroll
-            for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(Areg[rr][m][d], p, part[rr][d]);
+            for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(rw_A<NX, NI, RS>(Areg, As, rr, m, d, lane), p, part[rr][d]);
           }
       } else {
 #pragma unroll
@@ -535,7 +547,7 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
           for (int m = 0; m < NI; ++m) {
             const double p = __dmul_rn(pre[rr], tlm[m]);
 #pragma unroll
-            for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(Areg[rr][m][d], p, part[rr][d]);
+            for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(rw_A<NX, NI, RS>(Areg, As, rr, m, d, lane), p, part[rr][d]);
           }
       }
     } else {
@@ -556,7 +568,7 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
             if (live) {
               const double p = __dmul_rn(pre, tl[g >> 28]);
 #pragma unroll
-              for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(Areg[rr][m][d], p, part[rr][d]);
+              for (int d = 0; d < NX; ++d) part[rr][d] = __fma_rn(rw_A<NX, NI, RS>(Areg, As, rr, m, d, lane), p, part[rr][d]);
             }
             gprev = g;
           }
@@ -576,8 +588,8 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
 #ifndef PGB_ROLLOUT_W_MINBLOCKS
 #define PGB_ROLLOUT_W_MINBLOCKS 2
 #endif
-template <int NX, int NI>
-__global__ void __launch_bounds__(RW_WPB * 32, PGB_ROLLOUT_W_MINBLOCKS)
+template <int NX, int NI, int RS>
+__global__ void __launch_bounds__(RW_WPB * 32, RS >= 2 ? 3 : PGB_ROLLOUT_W_MINBLOCKS)
 k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ RolloutDev rd) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RolloutWShared& sh = *reinterpret_cast<RolloutWShared*>(smem_raw);
@@ -585,10 +597,11 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
   const int64_t K = rd.K, H = rd.H, N = rd.N;
   const int ny = fd.n_y, nu = fd.n_u, n_phi = fd.n_phi, nz = fd.n_z;
   double* us = reinterpret_cast<double*>(smem_raw + sizeof(RolloutWShared));  // [H][nu] planned inputs (CTA-wide)
-  const int64_t per_warp = PGB_MAX_Z_ * MAXC + H * (NX + ny);
+  const int64_t per_warp = PGB_MAX_Z_ * MAXC + H * (NX + ny) + RS * NI * NX * 32;
   double* tkw = us + H * nu + (int64_t)warp * per_warp;  // [n_z][MAXC] scaled sines of the warp's scenario
   double* vs = tkw + PGB_MAX_Z_ * MAXC;                  // [H][NX] process noise
   double* es = vs + H * NX;                              // [H][ny] measurement noise
+  double* As = es + H * ny;                              // [RS][NI][NX][32] the lanes' last RS runs of A_k
 
   // ---- model tables shared by every scenario (CTA-wide, once)
   const int c = (n_phi + 128 - 1) / 128;
@@ -639,23 +652,30 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
     const uint32_t cid = rd.k_offset + (uint32_t)k;
     const double* Ag = rd.A + k * (int64_t)NX * n_phi;
     // ---- A_k -> registers (read from HBM exactly once)
-    double Areg[RW_RPL][NI][NX];
+    constexpr int NR = RW_RPL - RS;
+    double Areg[NR > 0 ? NR : 1][NI][NX];
 #pragma unroll
     for (int rr = 0; rr < RW_RPL; ++rr)
 #pragma unroll
       for (int m = 0; m < NI; ++m) {
         const int64_t col = (int64_t)(RW_RPL * lane + rr) * c + m;
+        double av[NX];
         if (NX % 2 == 0) {
 #pragma unroll
           for (int d = 0; d < NX; d += 2) {
             double2 a = make_double2(0.0, 0.0);
             if (m < ncols[rr]) a = __ldg(reinterpret_cast<const double2*>(Ag + NX * col + d));
-            Areg[rr][m][d] = a.x;
-            Areg[rr][m][d + 1 < NX ? d + 1 : d] = a.y;
+            av[d] = a.x;
+            av[d + 1 < NX ? d + 1 : d] = a.y;
           }
         } else {
 #pragma unroll
-          for (int d = 0; d < NX; ++d) Areg[rr][m][d] = (m < ncols[rr]) ? __ldg(Ag + NX * col + d) : 0.0;
+          for (int d = 0; d < NX; ++d) av[d] = (m < ncols[rr]) ? __ldg(Ag + NX * col + d) : 0.0;
+        }
+#pragma unroll
+        for (int d = 0; d < NX; ++d) {
+          if (rr < NR) Areg[rr < NR ? rr : 0][m][d] = av[d];
+          else As[(((rr - NR) * NI + m) * NX + d) * 32 + lane] = av[d];
         }
       }
     // ---- chol(Q_k) (every lane; n_x <= 4)
@@ -757,7 +777,7 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
     __syncwarp();
     // ---- x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62)
     double F[NX];
-    rw_eval_F<NX, NI>(fd, sh, tkw, Areg, ncols, c, kl, ls, x, rd.u_m1 + k * nu, F);
+    rw_eval_F<NX, NI, RS>(fd, sh, tkw, Areg, As, ncols, c, kl, ls, x, rd.u_m1 + k * nu, F);
 #pragma unroll
     for (int d = 0; d < NX; ++d) x[d] = __dadd_rn(F[d], x0n[d]);
     if (lane == 0) {
@@ -775,7 +795,7 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
         for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[lane + ny * d], x[d], g);
         rd.Y[(k * H + t) * ny + lane] = __dadd_rn(g, es[t * ny + lane]);
       }
-      rw_eval_F<NX, NI>(fd, sh, tkw, Areg, ncols, c, kl, ls, x, us + (int64_t)nu * t, F);
+      rw_eval_F<NX, NI, RS>(fd, sh, tkw, Areg, As, ncols, c, kl, ls, x, us + (int64_t)nu * t, F);
 #pragma unroll
       for (int d = 0; d < NX; ++d) x[d] = __dadd_rn(F[d], vs[t * NX + d]);
       if (lane == 0 && rd.X) {
