@@ -174,7 +174,18 @@ int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Ph
 int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q, const double* w_m1,
                 const double* x_m1, const double* u_m1, const double* C, const double* Le, const double* u_init,
                 uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e, double* X, double* Y);
-/* Device-side time (CUDA events, ms) of the last pgb_rollout call of this process: allocation + host-to-device copies
+/* test_prediction(PG_samples, phi, g, R, k_n, u_test, y_test) (Julia/src/particle_Gibbs.jl:253-314): every one of the
+ * K models is simulated k_n times over the test input (T_test steps) on the rollout kernel; simulation (k, kn) is
+ * scenario s = k + K*kn (the order of the reference's reshape at :301-302) with Philox stream (seed, chain = s).
+ * Inputs as for pgb_rollout (A, Q, w_m1, x_m1, u_m1 hold K entries), u_test[n_u*T_test], y_test[n_y*T_test].
+ * Outputs (host; x_sim / y_sim may be NULL): x_sim[K*k_n][T_test+1][n_x] (the reference leaves its last column
+ * undefined, :278; here it holds one more transition), y_sim[K*k_n][T_test][n_y], *mean_rmse = the value printed at
+ * :311-312, its sum of squares reduced on the device in the oracle's tree order. */
+int pgb_test_prediction(const pgb_config* cfg, int64_t K, int64_t k_n, int64_t T_test, const double* A,
+                        const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
+                        const double* Le, const double* u_test, const double* y_test, uint64_t seed, double* x_sim,
+                        double* y_sim, double* mean_rmse);
+/* Device-side time (CUDA events, ms) of the last pgb_rollout / pgb_test_prediction call of this process: allocation + host-to-device copies
  * of the inputs, and the rollout kernel itself. */
 int pgb_rollout_last_ms(double* h2d_ms, double* kernel_ms);
 

@@ -12,9 +12,10 @@ module PGoptB200
 
 using LinearAlgebra
 using Distributions
+using Printf
 
 export PG_sample, KnownBasisVB, HilbertGPBasis, LinearMeasurement, particle_Gibbs, systematic_resampling,
-       MNIW_sample, scenario_rollout
+       MNIW_sample, scenario_rollout, test_prediction
 
 const LIB = get(ENV, "PGOPT_B200_LIB", "libpgopt_b200.so")
 const PGB_MAX_Z = 8
@@ -176,6 +177,32 @@ function scenario_rollout(PG_samples::Vector{PG_sample}, phi, g::LinearMeasureme
     X_init = reshape(permutedims(X, (1, 3, 2)), n_x * K, H + 1)
     Y_init = reshape(permutedims(Y, (1, 3, 2)), n_y * K, H)
     return vec(x0), v, e, X_init, Y_init
+end
+
+"""
+    test_prediction(PG_samples, phi, g, R, k_n, u_test, y_test)
+
+Julia/src/particle_Gibbs.jl:253-314 on the rollout kernel: every model simulated `k_n` times over the test input.
+Returns (x_test_sim (n_x, T_test+1, K*k_n), y_test_sim (n_y, T_test, K*k_n), mean_rmse) — the arrays the reference
+builds at :301-302 and the value it prints at :311-312.  Plotting (`plot_predictions`, :308) stays with the caller.
+"""
+function test_prediction(PG_samples::Vector{PG_sample}, phi, g::LinearMeasurement, R, k_n, u_test, y_test;
+                         seed=rand(UInt64), device=0)
+    K = length(PG_samples); N = length(PG_samples[1].w_m1); n_y = size(y_test, 1); T_test = size(y_test, 2)
+    cfg, n_x, n_u, n_phi = make_config(phi, n_y, N, 2; device=device)
+    Le = R isa Number ? fill(Float64(R), 1, 1) : Matrix{Float64}(cholesky(Matrix(R)).L)   # scalar R: a std (:261)
+    A = cat([s.A for s in PG_samples]...; dims=3); Q = cat([s.Q for s in PG_samples]...; dims=3)
+    w = hcat([s.w_m1 for s in PG_samples]...); x = cat([s.x_m1 for s in PG_samples]...; dims=3)
+    um = hcat([s.u_m1 for s in PG_samples]...)
+    ut = Matrix{Float64}(u_test[:, 1:T_test]); yt = Matrix{Float64}(y_test)
+    x_sim = Array{Float64}(undef, n_x, T_test + 1, K * k_n); y_sim = Array{Float64}(undef, n_y, T_test, K * k_n)
+    rmse = Ref{Float64}(0.0)
+    check(ccall((:pgb_test_prediction, LIB), Cint,
+                (Ref{PgbConfig}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                cfg, K, k_n, T_test, A, Q, w, x, um, g.C, Le, ut, yt, seed, x_sim, y_sim, rmse))
+    @printf("Mean rmse: %.2f\n", rmse[])
+    return x_sim, y_sim, rmse[]
 end
 
 end # module

@@ -559,31 +559,75 @@ int orc_particle_gibbs(const orc_model* m, int64_t N, int64_t T, const double* u
  * optimal_control_Ipopt.jl:47-64 (x0), :67-74 (v), :77-83 (e), :114-125 (X_init, Y_init).
  * Streams: scenario k uses chain = k; purposes ROLL with t = 0 (star), 1 (x0 noise),
  * 2 (v, j = step*npairs+p), 3 (e). */
+static int rollout_impl(const orc_model* m, int64_t K, int64_t n_models, int64_t H, int64_t N, const double* A,
+                        const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
+                        const double* Le, const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v,
+                        double* e, double* X, double* Y);
+
 int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const double* A, const double* Q,
                 const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
                 const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e, double* X,
                 double* Y) {
+  return rollout_impl(m, K, 0, H, N, A, Q, w_m1, x_m1, u_m1, C, Le, u_init, seed, k_offset, x0, v, e, X, Y);
+}
+
+/* test_prediction (particle_Gibbs.jl:253-314): every one of the K models is simulated k_n times over the test
+ * input.  Simulation (k, kn) is scenario s = k + K*kn of a rollout over K*k_n scenarios that reads model s mod K
+ * (the order of the reference's reshape (n_y, T_test, K*k_n) at :301-302, k fastest): star ~ w_m1 (:288),
+ * x_1 = f(x_m1[:, star], u_m1) + v (:290), x_t = f(x_{t-1}, u_test[:, t-1]) + v (:295), y_t = g(x_t) + e (:297) -
+ * i.e. orc_rollout with H = T_test and u_init = u_test: x_loop[:, t] = X[t-1], y_loop[:, t] = Y[t-1] (the reference
+ * leaves x_loop[:, T_test+1] undefined; here it holds one more transition).  mean_rmse (:311) =
+ * sqrt(sum((y_sim - y_test)^2) / (n_y*T_test*K*k_n)) with the sum taken by the balanced tree over the column-major
+ * (n_y, T_test, K*k_n) array. */
+int orc_test_prediction(const orc_model* m, int64_t K, int64_t k_n, int64_t T_test, int64_t N, const double* A,
+                        const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
+                        const double* Le, const double* u_test, const double* y_test, uint64_t seed, double* x_sim,
+                        double* y_sim, double* mean_rmse) {
+  const int64_t S = K * k_n, M = S * T_test * m->n_y;
+  int st = rollout_impl(m, S, K, T_test, N, A, Q, w_m1, x_m1, u_m1, C, Le, u_test, seed, 0, NULL, NULL, NULL, x_sim, y_sim);
+  double* sq = (double*)malloc(sizeof(double) * (size_t)M);
+  for (int64_t s2 = 0; s2 < S; ++s2)
+    for (int64_t t = 0; t < T_test; ++t)
+      for (int o = 0; o < m->n_y; ++o) {
+        const int64_t i = (s2 * T_test + t) * m->n_y + o;
+        const double d = y_sim[i] - y_test[t * m->n_y + o];
+        sq[i] = d * d;
+      }
+  *mean_rmse = sqrt(orc_pairwise_sum(sq, M) / (double)M);
+  free(sq);
+  return st;
+}
+
+static int rollout_impl(const orc_model* m, int64_t K, int64_t n_models, int64_t H, int64_t N, const double* A,
+                        const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
+                        const double* Le, const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v,
+                        double* e, double* X, double* Y) {
   const int n_x = m->n_x, n_u = m->n_u, n_y = m->n_y, n_phi = m->n_phi;
   int status = 0;
   double* phi_tmp = (double*)malloc(sizeof(double) * (size_t)n_phi);
   double Lq[ORC_MAX_Z * ORC_MAX_Z], z[ORC_MAX_Z], f[ORC_MAX_Z];
   const double* Lr = Le; /* lower factor the measurement noise is unwhitened with (see header) */
+  double *x0_own = NULL, *v_own = NULL, *e_own = NULL; /* optional outputs */
+  if (!x0) x0 = x0_own = (double*)malloc(sizeof(double) * (size_t)(K * n_x));
+  if (!v) v = v_own = (double*)malloc(sizeof(double) * (size_t)(K * H * n_x));
+  if (!e) e = e_own = (double*)malloc(sizeof(double) * (size_t)(K * H * n_y));
   for (int64_t k = 0; k < K && !(status & 16); ++k) {
-    const double* Ak = &A[k * n_x * n_phi];
+    const int64_t km = n_models > 0 ? k % n_models : k; /* model (PG sample) scenario k simulates */
+    const double* Ak = &A[km * n_x * n_phi];
     orc_streams s;
     memset(&s, 0, sizeof(s));
     s.philox = 1;
     s.seed = seed;
     s.chain = k_offset + (uint32_t)k; /* scenario id: a shard of the K scenarios keeps its global stream */
-    memcpy(Lq, &Q[k * n_x * n_x], sizeof(double) * (size_t)(n_x * n_x));
+    memcpy(Lq, &Q[km * n_x * n_x], sizeof(double) * (size_t)(n_x * n_x));
     if (orc_cholesky_lower(Lq, n_x)) { status |= 16; break; }
     /* star = systematic_resampling(w_m1, 1); x_m1 = x_m1[:, star]   (:58-59) */
     int64_t star;
     double us = stream_uniform(&s, PGB_STREAM_ROLL, 0, 0);
-    status |= orc_systematic_resampling(&w_m1[k * N], N, 1, us, &star);
+    status |= orc_systematic_resampling(&w_m1[km * N], N, 1, us, &star);
     if (star < 1) star = 1;
     /* x0 = f(x_m1, u_m1) + rand(mvn)   (:62) */
-    eval_f_blocked(m, Ak, &x_m1[(k * N + (star - 1)) * n_x], &u_m1[k * n_u], phi_tmp, f);
+    eval_f_blocked(m, Ak, &x_m1[(km * N + (star - 1)) * n_x], &u_m1[km * n_u], phi_tmp, f);
     stream_normals(&s, PGB_STREAM_ROLL, 0, 1, 0, n_x, z);
     for (int d = 0; d < n_x; ++d) {
       double acc = 0.0;
@@ -617,5 +661,6 @@ int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const doubl
     }
   }
   free(phi_tmp);
+  free(x0_own); free(v_own); free(e_own);
   return status;
 }

@@ -383,3 +383,39 @@ def scenario_rollout(PG_samples, phi, g, R, H, u_init=None, seed=0, k_offset=0, 
     return dict(x_vec_0=x0.reshape(-1), v_vec=np.transpose(v, (2, 1, 0)), e_vec=np.transpose(e, (2, 1, 0)),
                 X_init=np.transpose(X, (0, 2, 1)).reshape(K * n_x, H + 1),
                 Y_init=np.transpose(Y, (0, 2, 1)).reshape(K * n_y, H), raw=dict(x0=x0, v=v, e=e, X=X, Y=Y))
+
+
+def test_prediction(PG_samples, phi, g, R, k_n, u_test, y_test, seed=0, device=0):
+    """Simulate the PG samples forward over the test input and compare with the test output
+    (Julia/src/particle_Gibbs.jl:253-314): every model k_n times, on the scenario-rollout kernel.
+    Returns dict(x_test_sim (n_x, T_test+1, K*k_n), y_test_sim (n_y, T_test, K*k_n), mean_rmse) with the
+    reference's layouts after its reshape (:301-302); it does not plot (plot_predictions is out of scope).
+    The reference leaves x_test_sim[:, T_test+1, :] undefined (:278); here it holds one more transition."""
+    b = _basis(phi)
+    gm = _meas(g)
+    K = len(PG_samples)
+    n_x, n_u = b.n_x, b.n_u
+    n_y = gm.C.shape[0]
+    N = PG_samples[0].w_m1.size
+    u_test = np.atleast_2d(np.asarray(u_test, dtype=np.float64))
+    y_test = np.atleast_2d(np.asarray(y_test, dtype=np.float64))
+    T_test = y_test.shape[1]
+    if np.ndim(R) == 0:
+        Le = np.array([[float(R)]])  # MvNormal(zeros(n_y), R::Real) reads R as a std (reference quirk, :261)
+    else:
+        Le = np.linalg.cholesky(np.atleast_2d(np.asarray(R, dtype=np.float64)))
+    cfg = _make_cfg(b, n_y, N, 2, 1, device)
+    A = np.ascontiguousarray(np.stack([_f(s.A) for s in PG_samples]))
+    Q = np.ascontiguousarray(np.stack([_f(s.Q) for s in PG_samples]))
+    w = np.ascontiguousarray(np.stack([np.asarray(s.w_m1, dtype=np.float64).ravel() for s in PG_samples]))
+    x = np.ascontiguousarray(np.stack([_f(s.x_m1) for s in PG_samples]))
+    um = np.ascontiguousarray(np.stack([np.asarray(s.u_m1, dtype=np.float64).ravel() for s in PG_samples]))
+    S = K * int(k_n)
+    xs, ys = np.empty((S, T_test + 1, n_x)), np.empty((S, T_test, n_y))
+    rmse = C.c_double(0.0)
+    check(lib().pgb_test_prediction(C.byref(cfg), C.c_int64(K), C.c_int64(int(k_n)), C.c_int64(T_test), _p(A), _p(Q),
+                                    _p(w), _p(x), _p(um), _p(_f(gm.C)), _p(_f(Le)), _p(_f(u_test[:, :T_test])),
+                                    _p(_f(y_test)), C.c_uint64(seed), _p(xs), _p(ys), C.byref(rmse)))
+    return dict(x_test_sim=np.transpose(xs, (2, 1, 0)), y_test_sim=np.transpose(ys, (2, 1, 0)),
+                mean_rmse=rmse.value, raw=dict(x_sim=xs, y_sim=ys))
+

@@ -939,7 +939,7 @@ static cudaError_t launch_rollout(const FilterDev& fd, const RolloutDev& rd, siz
 // rest in registers), persistent grid of independent warps.
 static size_t rollout_warp_smem(int nx, int ny, int nu, int64_t H, int ni, int rs) {
   return sizeof(RolloutWShared) +
-         ((size_t)H * nu + (size_t)RW_WPB * (PGB_MAX_Z_ * MAXC + (size_t)H * (nx + ny) + (size_t)rs * ni * nx * 32)) * 8;
+         ((size_t)H * nu + (size_t)RW_WPB * (PGB_MAX_Z_ * MAXC + (size_t)H * (nx + ny) + (size_t)rs * ni * nx * 32 + (size_t)(H + 2) * nx)) * 8;
 }
 template <int NX, int NI, int RS>
 static cudaError_t launch_rollout_warp_ni(const FilterDev& fd, const RolloutDev& rd, int n_sm) {
@@ -966,12 +966,15 @@ static cudaError_t launch_rollout_warp(const FilterDev& fd, const RolloutDev& rd
   }
 }
 
-extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q,
-                           const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
-                           const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e,
-                           double* X, double* Y) {
+// Shared body of pgb_rollout (n_models = 0, y_test = null) and pgb_test_prediction (K scenarios over n_models models,
+// scenario k simulating model k mod n_models; sum_sq_err = tree sum of (Y - y_test)^2).
+static int rollout_run(const pgb_config* cfg, int64_t K, int64_t n_models, int64_t H, const double* A, const double* Q,
+                       const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
+                       const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e,
+                       double* X, double* Y, const double* y_test, double* sum_sq_err) {
   int rc = validate_cfg(cfg);
   if (rc) return rc;
+  const int64_t KM = n_models > 0 ? n_models : K;  // number of models (PG samples) behind the K scenarios
   if (!A || !Q || !w_m1 || !x_m1 || !u_m1 || !C || !Le || !u_init || K < 1 || H < 1 || cfg->N < 1)
     return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
   int ndev = 0;
@@ -994,7 +997,7 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   for (int i = 0; i < ny * nx; ++i) fd.C[i] = C[i];
   RolloutDev rd;
   memset(&rd, 0, sizeof(rd));
-  rd.K = K; rd.H = H; rd.N = N; rd.seed = seed; rd.k_offset = k_offset;
+  rd.K = K; rd.H = H; rd.N = N; rd.seed = seed; rd.k_offset = k_offset; rd.n_models = n_models;
   for (int i = 0; i < ny * ny; ++i) rd.Le[i] = Le[i];
   const int m = nx * np;
   const size_t smem = sizeof(RolloutShared) + ((size_t)H * (nx + ny + nu) + (size_t)(N < R_WSTAGE ? N : R_WSTAGE)) * 8;
@@ -1004,24 +1007,24 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   cudaEvent_t ev[3];
   for (auto& evt : ev) CK(h, cudaEventCreate(&evt));
   CK(h, cudaEventRecord(ev[0], 0));
-  CK(h, dalloc(h, &dA, (size_t)K * m, false));
-  CK(h, dalloc(h, &dQ, (size_t)K * nx * nx, false));
-  CK(h, dalloc(h, &dw, (size_t)K * N, false));
-  CK(h, dalloc(h, &dx, (size_t)K * nx * N, false));
-  CK(h, dalloc(h, &dum, (size_t)K * nu, false));
+  CK(h, dalloc(h, &dA, (size_t)KM * m, false));
+  CK(h, dalloc(h, &dQ, (size_t)KM * nx * nx, false));
+  CK(h, dalloc(h, &dw, (size_t)KM * N, false));
+  CK(h, dalloc(h, &dx, (size_t)KM * nx * N, false));
+  CK(h, dalloc(h, &dum, (size_t)KM * nu, false));
   CK(h, dalloc(h, &dui, (size_t)nu * H, false));
   CK(h, dalloc(h, &rd.status, 1));
-  CK(h, cudaMemcpy(dA, A, (size_t)K * m * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(dQ, Q, (size_t)K * nx * nx * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(dw, w_m1, (size_t)K * N * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(dx, x_m1, (size_t)K * nx * N * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(dum, u_m1, (size_t)K * nu * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dA, A, (size_t)KM * m * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dQ, Q, (size_t)KM * nx * nx * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dw, w_m1, (size_t)KM * N * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dx, x_m1, (size_t)KM * nx * N * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(dum, u_m1, (size_t)KM * nu * 8, cudaMemcpyHostToDevice));
   CK(h, cudaMemcpy(dui, u_init, (size_t)nu * H * 8, cudaMemcpyHostToDevice));
   if (x0) CK(h, dalloc(h, &rd.x0, (size_t)K * nx, false));
   if (v) CK(h, dalloc(h, &rd.v, (size_t)K * H * nx, false));
   if (e) CK(h, dalloc(h, &rd.e, (size_t)K * H * ny, false));
   if (X) CK(h, dalloc(h, &rd.X, (size_t)K * (H + 1) * nx, false));
-  if (Y) CK(h, dalloc(h, &rd.Y, (size_t)K * H * ny, false));
+  if (Y || y_test) CK(h, dalloc(h, &rd.Y, (size_t)K * H * ny, false));
   CK(h, cudaEventRecord(ev[1], 0));
   rd.A = dA; rd.Q = dQ; rd.w_m1 = dw; rd.x_m1 = dx; rd.u_m1 = dum; rd.u_init = dui;
   // kernel choice: one warp per scenario whenever A_k fits the registers of 32 lanes (n_phi <= 128 * RW_MAXNI) and
@@ -1055,7 +1058,20 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
     }
   }
   CK(h, cudaEventRecord(ev[2], 0));
+  double* d_sse = nullptr;
+  if (y_test && sum_sq_err) {  // squared prediction errors, tree-summed on the device (particle_Gibbs.jl:311)
+    const int64_t M = K * H * ny, ntile = (M + TILE - 1) / TILE;
+    double *d_yt, *d_tiles;
+    CK(h, dalloc(h, &d_yt, (size_t)H * ny, false));
+    CK(h, dalloc(h, &d_tiles, (size_t)ntile, false));
+    CK(h, dalloc(h, &d_sse, 1, false));
+    CK(h, cudaMemcpy(d_yt, y_test, (size_t)H * ny * 8, cudaMemcpyHostToDevice));
+    k_sqerr_tiles<<<(unsigned)ntile, TPB>>>(rd.Y, d_yt, M, H * ny, d_tiles);
+    k_tree_final<<<1, TPB>>>(d_tiles, ntile, d_sse);
+    CK(h, cudaGetLastError());
+  }
   CK(h, cudaDeviceSynchronize());
+  if (d_sse) CK(h, cudaMemcpy(sum_sq_err, d_sse, 8, cudaMemcpyDeviceToHost));
   cudaEventElapsedTime(&g_rollout_ms[0], ev[0], ev[1]);
   cudaEventElapsedTime(&g_rollout_ms[1], ev[1], ev[2]);
   for (auto& evt : ev) cudaEventDestroy(evt);
@@ -1067,6 +1083,26 @@ extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const do
   if (e) CK(h, cudaMemcpy(e, rd.e, (size_t)K * H * ny * 8, cudaMemcpyDeviceToHost));
   if (X) CK(h, cudaMemcpy(X, rd.X, (size_t)K * (H + 1) * nx * 8, cudaMemcpyDeviceToHost));
   if (Y) CK(h, cudaMemcpy(Y, rd.Y, (size_t)K * H * ny * 8, cudaMemcpyDeviceToHost));
+  return PGB_OK;
+}
+
+extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q,
+                           const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
+                           const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e,
+                           double* X, double* Y) {
+  return rollout_run(cfg, K, 0, H, A, Q, w_m1, x_m1, u_m1, C, Le, u_init, seed, k_offset, x0, v, e, X, Y, nullptr, nullptr);
+}
+
+extern "C" int pgb_test_prediction(const pgb_config* cfg, int64_t K, int64_t k_n, int64_t T_test, const double* A,
+                                   const double* Q, const double* w_m1, const double* x_m1, const double* u_m1,
+                                   const double* C, const double* Le, const double* u_test, const double* y_test,
+                                   uint64_t seed, double* x_sim, double* y_sim, double* mean_rmse) {
+  if (K < 1 || k_n < 1 || T_test < 1 || !y_test || !mean_rmse) return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
+  double sse = 0.0;
+  int rc = rollout_run(cfg, K * k_n, K, T_test, A, Q, w_m1, x_m1, u_m1, C, Le, u_test, seed, 0, nullptr, nullptr, nullptr,
+                       x_sim, y_sim, y_test, &sse);
+  if (rc) return rc;
+  *mean_rmse = std::sqrt(sse / (double)(K * k_n * T_test * cfg->n_y));
   return PGB_OK;
 }
 

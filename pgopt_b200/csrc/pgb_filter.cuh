@@ -129,44 +129,15 @@ __device__ __forceinline__ void eval_F(const FilterDev& fd, const double* __rest
 // at once: the 15 sines of each particle are evaluated 5-wide, the 125 tensor-product terms are fully unrolled with
 // the per-dimension factors in registers, and every A entry read from shared memory feeds both particles.  Same
 // products and the same fma order as eval_F (i increasing), hence the same bits.
-// The input u_{t-1} is common to every particle of a step, so the five scaled sines of dimension 0 (z_0 = u) can be
-// evaluated once per thread and step instead of once per particle (same expression, same bits): HilbertU5.
-struct HilbertU5 {
-  double v[5];
-  int valid;
-};
-__device__ __forceinline__ HilbertU5 hilbert355_u_sines(const FilterDev& fd, const double* __restrict__ u) {
-  HilbertU5 r;
-  const double zl = __dadd_rn(u[0], fd.hg_L[0]);
-  double arg[5], sn[5], cs[5];
-#pragma unroll
-  for (int j = 0; j < 5; ++j) arg[j] = __dmul_rn(fd.hg_pij2l[0][j], zl);
-  vsincos_wide<5>(arg, sn, cs);
-#pragma unroll
-  for (int j = 0; j < 5; ++j) r.v[j] = __dmul_rn(fd.hg_lsi[0], sn[j]);
-  r.valid = 1;
-  return r;
-}
-__device__ __forceinline__ bool is_hilbert355(const FilterDev& fd, int nx) {
-  return fd.basis != 0 && nx == 2 && fd.n_z == 3 && fd.n_u == 1 && fd.hg_count[0] == 5 && fd.hg_count[1] == 5 &&
-         fd.hg_count[2] == 5;
-}
-
 template <int NX>
 __device__ __noinline__ void eval_F_hilbert355_pair(const FilterDev& fd, const double* __restrict__ A_sm,
                                                        const double xa[NX], const double xb[NX],
-                                                       const double* __restrict__ u, const HilbertU5 tu, double Fa[NX],
-                                                       double Fb2[NX]) {
+                                                       const double* __restrict__ u, double Fa[NX], double Fb2[NX]) {
   double t[2][3][5];
-  if (tu.valid) {
-#pragma unroll
-    for (int j = 0; j < 5; ++j) t[0][0][j] = t[1][0][j] = tu.v[j];
-  }
 #pragma unroll
   for (int p = 0; p < 2; ++p)
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      if (k == 0 && tu.valid) continue;
       const double zk = (k < fd.n_u) ? u[k] : (p == 0 ? xa[(k - fd.n_u) < NX ? (k - fd.n_u) : 0] : xb[(k - fd.n_u) < NX ? (k - fd.n_u) : 0]);
       const double zl = __dadd_rn(zk, fd.hg_L[k]);
       double arg[5], sn[5], cs[5];
@@ -210,7 +181,7 @@ __device__ __noinline__ void eval_F_hilbert355_pair(const FilterDev& fd, const d
 // F for the thread's four particles at once (known basis: the four sin/cos chains are interleaved)
 template <int NX>
 __device__ __forceinline__ void eval_F4(const FilterDev& fd, const double* __restrict__ A_sm, const double (&x)[4][NX],
-                                        const double* __restrict__ u, double (&F)[4][NX], const HilbertU5* tu = nullptr) {
+                                        const double* __restrict__ u, double (&F)[4][NX]) {
   if (fd.basis == 0) {
     double a3[4], a2[4], s3[4], c3[4], s2[4], c2[4];
 #pragma unroll
@@ -240,10 +211,7 @@ __device__ __forceinline__ void eval_F4(const FilterDev& fd, const double* __res
   }
   if (NX == 2 && fd.n_z == 3 && fd.hg_count[0] == 5 && fd.hg_count[1] == 5 && fd.hg_count[2] == 5) {
 #pragma unroll 1
-    HilbertU5 tuv;
-    if (tu) tuv = *tu;
-    else tuv = hilbert355_u_sines(fd, u);  // once per four particles when the caller did not hoist it further
-    for (int k = 0; k < 4; k += 2) eval_F_hilbert355_pair<NX>(fd, A_sm, x[k], x[k + 1], u, tuv, F[k], F[k + 1]);
+    for (int k = 0; k < 4; k += 2) eval_F_hilbert355_pair<NX>(fd, A_sm, x[k], x[k + 1], u, F[k], F[k + 1]);
     return;
   }
 #pragma unroll 1

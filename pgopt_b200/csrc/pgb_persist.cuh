@@ -830,9 +830,6 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
         for (int d = 0; d < NX; ++d) xref[d] = fd.xprim[(int64_t)chain * NX * T + d + NX * t];
         c0 = fd.c0[chain];
       }
-      HilbertU5 tu;
-      tu.valid = 0;
-      if (!last_only && is_hilbert355(fd, NX)) tu = hilbert355_u_sines(fd, up);  // u_{t-1} is common to all particles
       P_FOR_BLOCKS {
       TreeAcc accw, acca;
       accw.init();
@@ -865,7 +862,7 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
 #pragma unroll
               for (int d = 0; d < NX; ++d) F[i][d] = x[i][d];
           } else {
-            eval_F4<NX>(fd, A_sm, x, up, F, tu.valid ? &tu : nullptr);
+            eval_F4<NX>(fd, A_sm, x, up, F);
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i)

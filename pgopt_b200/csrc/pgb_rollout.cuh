@@ -22,6 +22,7 @@ constexpr int R_WSTAGE = 1024;  // weights of the last filtering step staged in 
 
 struct RolloutDev {
   int64_t K, H, N;
+  int64_t n_models;    // 0: scenario k reads model k; > 0: scenario k reads model k mod n_models (test_prediction)
   const double* A;     // [K][n_x*n_phi]   column-major n_x x n_phi per scenario
   const double* Q;     // [K][n_x*n_x]
   const double* w_m1;  // [K][N]
@@ -222,7 +223,8 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
   double* us = es + H * ny;  // [H][nu] planned inputs u_init (read once, not once per step from L2)
   double* ws = us + H * nu;  // [min(N, R_WSTAGE)] staged weights w_m1 (coalesced load; thread 0 walks them serially)
   const uint32_t cid = rd.k_offset + (uint32_t)k;
-  const double* Ag = rd.A + k * (int64_t)NX * n_phi;
+  const int64_t km = rd.n_models > 0 ? k % rd.n_models : k;  // model (PG sample) this scenario simulates
+  const double* Ag = rd.A + km * (int64_t)NX * n_phi;
 
   // ---- A_k -> registers: thread j owns the c consecutive columns [j*c, (j+1)*c)
   const int c = (n_phi + R_TPB - 1) / R_TPB;
@@ -249,11 +251,11 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
   }
   for (int64_t i = tid; i < H * nu; i += R_TPB) us[i] = rd.u_init[i];
   const int64_t nstage = N < R_WSTAGE ? N : R_WSTAGE;
-  for (int64_t i = tid; i < nstage; i += R_TPB) ws[i] = rd.w_m1[k * N + i];
+  for (int64_t i = tid; i < nstage; i += R_TPB) ws[i] = rd.w_m1[km * N + i];
   // ---- chol(Q_k) (every thread; n_x <= 4)
   double Lq[NX * NX];
 #pragma unroll
-  for (int i = 0; i < NX * NX; ++i) Lq[i] = rd.Q[k * NX * NX + i];
+  for (int i = 0; i < NX * NX; ++i) Lq[i] = rd.Q[km * NX * NX + i];
   const int notpd = small_chol(Lq, NX);
   if (notpd) {
     if (vt == 0) atomicOr(rd.status, 16);
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
   // ---- star = systematic_resampling(w_m1, 1) (:58): W = w/sum(w) (tree), first n with q_n >= u   (thread 0)
   __syncthreads();
   if (vt == 0) {
-    const double* wg = rd.w_m1 + k * N;
+    const double* wg = rd.w_m1 + km * N;
 #define R_W(i) ((i) < nstage ? ws[(i)] : wg[(i)])
     double st[40];
     int sp = 0;
@@ -319,12 +321,12 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
 #undef R_W
     if (n == 0) { atomicOr(rd.status, 2); n = 1; }
     const int64_t star = n - 1;
-    for (int d = 0; d < NX; ++d) sh.x[d] = rd.x_m1[(k * N + star) * NX + d];
+    for (int d = 0; d < NX; ++d) sh.x[d] = rd.x_m1[(km * N + star) * NX + d];
   }
   __syncthreads();
   // ---- x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62)
   double Fd = 0.0;
-  rollout_eval_F<NX, NI>(fd, sh, Areg, Ag, c, dig, rd.u_m1 + k * nu, Fd);
+  rollout_eval_F<NX, NI>(fd, sh, Areg, Ag, c, dig, rd.u_m1 + km * nu, Fd);
   if (vt < NX) {
     const double xv = __dadd_rn(Fd, sh.x0n[vt]);
     sh.x[vt] = xv;
@@ -410,6 +412,11 @@ template <int NX>
 __device__ __forceinline__ int rw_src(int d) {
   return NX == 1 ? 0 : (NX == 2 ? d : (((d & 1) << 1) | (d >> 1)));
 }
+// component of the tree result that lane holds (inverse of rw_src on the low lane bits; may be >= NX for NX = 3)
+template <int NX>
+__device__ __forceinline__ int rw_comp(int lane) {
+  return NX == 1 ? 0 : (NX == 2 ? (lane & 1) : (((lane & 1) << 1) | ((lane >> 1) & 1)));
+}
 
 template <int NX>
 __device__ __forceinline__ double rw_pick(const double (&x)[NX], int i) {
@@ -441,8 +448,8 @@ template <int NX, int NI, int RS>
 __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWShared& sh, double* __restrict__ tkw,
                                           const double (&Areg)[RW_RPL - RS > 0 ? RW_RPL - RS : 1][NI][NX],
                                           const double* __restrict__ As, const int (&ncols)[RW_RPL], int c,
-                                          int kl, const RwSine& ls, const double (&x)[NX],
-                                          const double* __restrict__ u, double (&F)[NX]) {
+                                          int kl, const RwSine& ls, const double* __restrict__ x,
+                                          const double* __restrict__ u, double& Fb) {
   const int lane = threadIdx.x & 31;
   double P[NX];
   if (fd.basis == 0) {
@@ -473,7 +480,7 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
     // Hilbert-space basis (examples/PG_OCP_generic_basis_functions_Altro.jl:85-99): one scaled sine per lane
     if (sh.n_sines <= 32) {  // the lane's sine is the same for every step and scenario: its constants sit in registers
       if (lane < sh.n_sines) {
-        const double zk = (ls.k < fd.n_u) ? u[ls.k] : rw_pick<NX>(x, ls.k - fd.n_u);
+        const double zk = (ls.k < fd.n_u) ? u[ls.k] : x[ls.k - fd.n_u];
         const double arg[1] = {__dmul_rn(ls.pij2l, __dadd_rn(zk, ls.L))};
         double sn[1], cs[1];
         vsincos_wide<1>(arg, sn, cs);
@@ -482,7 +489,7 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
     } else {
       for (int s = lane; s < sh.n_sines; s += 32) {
         const int k = sh.sine_dim[s], j = sh.sine_j[s];
-        const double zk = (k < fd.n_u) ? u[k] : rw_pick<NX>(x, k - fd.n_u);
+        const double zk = (k < fd.n_u) ? u[k] : x[k - fd.n_u];
         const double zl = __dadd_rn(zk, fd.hg_L[k]);
         const double arg[1] = {__dmul_rn(fd.hg_pij2l[k][j], zl)};
         double sn[1], cs[1];
@@ -580,9 +587,7 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
       P[d] = __dadd_rn(__dadd_rn(part[0][d], part[1][d]), __dadd_rn(part[2][d], part[3][d]));
     __syncwarp();  // tkw is rewritten by the next evaluation
   }
-  const double b = rw_tree<NX>(P, lane);
-#pragma unroll
-  for (int d = 0; d < NX; ++d) F[d] = __shfl_sync(0xffffffffu, b, rw_src<NX>(d));
+  Fb = rw_tree<NX>(P, lane);
 }
 
 #ifndef PGB_ROLLOUT_W_MINBLOCKS
@@ -597,11 +602,13 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
   const int64_t K = rd.K, H = rd.H, N = rd.N;
   const int ny = fd.n_y, nu = fd.n_u, n_phi = fd.n_phi, nz = fd.n_z;
   double* us = reinterpret_cast<double*>(smem_raw + sizeof(RolloutWShared));  // [H][nu] planned inputs (CTA-wide)
-  const int64_t per_warp = PGB_MAX_Z_ * MAXC + H * (NX + ny) + RS * NI * NX * 32;
+  const int64_t per_warp = PGB_MAX_Z_ * MAXC + H * (NX + ny) + RS * NI * NX * 32 + (H + 2) * NX;
   double* tkw = us + H * nu + (int64_t)warp * per_warp;  // [n_z][MAXC] scaled sines of the warp's scenario
   double* vs = tkw + PGB_MAX_Z_ * MAXC;                  // [H][NX] process noise
   double* es = vs + H * NX;                              // [H][ny] measurement noise
   double* As = es + H * ny;                              // [RS][NI][NX][32] the lanes' last RS runs of A_k
+  double* xs = As + RS * NI * NX * 32;                   // [H+1][NX] trajectory X[:, t] (outputs are written at the end)
+  double* xin = xs + (H + 1) * NX;                       // [NX] x_m1[:, star]
 
   // ---- model tables shared by every scenario (CTA-wide, once)
   const int c = (n_phi + 128 - 1) / 128;
@@ -650,7 +657,8 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
 
   for (int64_t k = (int64_t)blockIdx.x * RW_WPB + warp; k < K; k += (int64_t)gridDim.x * RW_WPB) {
     const uint32_t cid = rd.k_offset + (uint32_t)k;
-    const double* Ag = rd.A + k * (int64_t)NX * n_phi;
+    const int64_t km = rd.n_models > 0 ? k % rd.n_models : k;  // model (PG sample) this scenario simulates
+    const double* Ag = rd.A + km * (int64_t)NX * n_phi;
     // ---- A_k -> registers (read from HBM exactly once)
     constexpr int NR = RW_RPL - RS;
     double Areg[NR > 0 ? NR : 1][NI][NX];
@@ -681,7 +689,7 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
     // ---- chol(Q_k) (every lane; n_x <= 4)
     double Lq[NX * NX];
 #pragma unroll
-    for (int i = 0; i < NX * NX; ++i) Lq[i] = rd.Q[k * NX * NX + i];
+    for (int i = 0; i < NX * NX; ++i) Lq[i] = rd.Q[km * NX * NX + i];
     if (small_chol(Lq, NX)) {  // warp-uniform
       if (lane == 0) atomicOr(rd.status, 16);
       continue;
@@ -722,9 +730,8 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
       }
     }
     // ---- star = systematic_resampling(w_m1, 1) (:58): S = tree sum of w; first n with q_n >= u, q sequential
-    double x[NX];
     {
-      const double* wg = rd.w_m1 + k * N;
+      const double* wg = rd.w_m1 + km * N;
       int64_t P = 1;
       while (P < N) P <<= 1;
       double S;
@@ -771,40 +778,68 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
         n = 1;
       }
       const int64_t star = n - 1;
-#pragma unroll
-      for (int d = 0; d < NX; ++d) x[d] = rd.x_m1[(k * N + star) * NX + d];
+      if (lane < NX) xin[lane] = rd.x_m1[(km * N + star) * NX + lane];
     }
     __syncwarp();
-    // ---- x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62)
-    double F[NX];
-    rw_eval_F<NX, NI, RS>(fd, sh, tkw, Areg, As, ncols, c, kl, ls, x, rd.u_m1 + k * nu, F);
+    // ---- x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62).  The tree leaves component rw_comp(lane) of F in every
+    // lane; the lanes add that component's noise and the first holders store X[:, t] in shared memory, from where
+    // the sine lanes read their input of the next step.  Global outputs are written once, after the horizon.
+    const int comp = rw_comp<NX>(lane);
+    const int compc = comp < NX ? comp : 0;
+    const bool holder = lane < (NX == 1 ? 1 : (NX == 2 ? 2 : 4)) && comp < NX;
+    double Fb;
+    rw_eval_F<NX, NI, RS>(fd, sh, tkw, Areg, As, ncols, c, kl, ls, xin, rd.u_m1 + km * nu, Fb);
+    {
+      double nz0 = x0n[0];
 #pragma unroll
-    for (int d = 0; d < NX; ++d) x[d] = __dadd_rn(F[d], x0n[d]);
-    if (lane == 0) {
-#pragma unroll
-      for (int d = 0; d < NX; ++d) {
-        if (rd.x0) rd.x0[k * NX + d] = x[d];
-        if (rd.X) rd.X[(k * (H + 1)) * NX + d] = x[d];
-      }
+      for (int d = 1; d < NX; ++d) nz0 = (compc == d) ? x0n[d] : nz0;
+      if (holder) xs[compc] = __dadd_rn(Fb, nz0);
     }
-    // ---- horizon: Y[t] = g(X[t]) + e (:122), X[t+1] = f(X[t], u_t) + v (:121)
+    __syncwarp();
+    // ---- horizon: X[t+1] = f(X[t], u_t) + v (:121)
     for (int64_t t = 0; t < H; ++t) {
-      if (lane < ny && rd.Y) {
-        double g = 0.0;
-#pragma unroll
-        for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[lane + ny * d], x[d], g);
-        rd.Y[(k * H + t) * ny + lane] = __dadd_rn(g, es[t * ny + lane]);
-      }
-      rw_eval_F<NX, NI, RS>(fd, sh, tkw, Areg, As, ncols, c, kl, ls, x, us + (int64_t)nu * t, F);
-#pragma unroll
-      for (int d = 0; d < NX; ++d) x[d] = __dadd_rn(F[d], vs[t * NX + d]);
-      if (lane == 0 && rd.X) {
-#pragma unroll
-        for (int d = 0; d < NX; ++d) rd.X[(k * (H + 1) + t + 1) * NX + d] = x[d];
-      }
+      rw_eval_F<NX, NI, RS>(fd, sh, tkw, Areg, As, ncols, c, kl, ls, xs + t * NX, us + (int64_t)nu * t, Fb);
+      if (holder) xs[(t + 1) * NX + compc] = __dadd_rn(Fb, vs[t * NX + compc]);
+      __syncwarp();
     }
+    // ---- outputs: x_vec_0, X (coalesced copy of the trajectory), Y[t] = g(X[t]) + e (:122), one step per lane
+    if (rd.x0 && lane < NX) rd.x0[k * NX + lane] = xs[lane];
+    if (rd.X)
+      for (int64_t i = lane; i < (H + 1) * NX; i += 32) rd.X[k * (H + 1) * NX + i] = xs[i];
+    if (rd.Y)
+      for (int64_t t = lane; t < H; t += 32)
+        for (int o = 0; o < ny; ++o) {
+          double g = 0.0;
+#pragma unroll
+          for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[o + ny * d], xs[t * NX + d], g);
+          rd.Y[(k * H + t) * ny + o] = __dadd_rn(g, es[t * ny + o]);
+        }
     __syncwarp();  // vs / es are rewritten by the next scenario
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// mean_rmse of test_prediction (Julia/src/particle_Gibbs.jl:311): sum over the column-major (n_y, T_test, K*k_n) array
+// of (y_sim - y_test)^2 as the balanced tree the oracle defines (tile sums, then the tree over the tiles).
+__global__ void __launch_bounds__(TPB) k_sqerr_tiles(const double* __restrict__ Y, const double* __restrict__ y_test,
+                                                      int64_t M, int64_t per, double* __restrict__ tile_sums) {
+  __shared__ double sm[NWARP + 1];
+  const int64_t base = (int64_t)blockIdx.x * TILE + (int64_t)threadIdx.x * IPT;
+  double v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t n = base + i;
+    double d = 0.0;
+    if (n < M) d = __dsub_rn(Y[n], y_test[n % per]);
+    v[i] = __dmul_rn(d, d);
+  }
+  const double s = block_tree_sum(tree4(v), sm);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(TPB) k_tree_final(const double* __restrict__ p, int64_t n, double* __restrict__ out) {
+  __shared__ double sm[NWARP + 1];
+  const double s = block_tree_sum_array(p, n, sm);
+  if (threadIdx.x == 0) *out = s;
 }
 
 }  // namespace pgb

@@ -177,3 +177,20 @@ def rollout(model, K, H, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_init, seed, k_offs
                            _p(f64(x_m1)), _p(f64(u_m1)), _p(fl(Cm)), _p(fl(np.atleast_2d(Le))), _p(fl(u_init)),
                            C.c_uint64(seed), C.c_uint32(k_offset), _p(x0), _p(v), _p(e), _p(X), _p(Y))
     return dict(status=st, x0=x0, v=v, e=e, X=X, Y=Y)
+
+
+def test_prediction(model, K, k_n, T_test, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_test, y_test, seed):
+    """orc_test_prediction: x_sim (K*k_n, T_test+1, n_x), y_sim (K*k_n, T_test, n_y), mean_rmse."""
+    n_x, n_y = model.n_x, model.n_y
+    Af = f64(np.transpose(A, (0, 2, 1)))
+    Qf = f64(np.transpose(Q, (0, 2, 1)))
+    fl = lambda v: f64(np.asfortranarray(v).ravel(order="F"))
+    S = K * k_n
+    xs, ys = np.zeros((S, T_test + 1, n_x)), np.zeros((S, T_test, n_y))
+    rmse = C.c_double(0.0)
+    st = lib().orc_test_prediction(C.byref(model), C.c_int64(K), C.c_int64(k_n), C.c_int64(T_test), C.c_int64(N), _p(Af),
+                                   _p(Qf), _p(f64(w_m1)), _p(f64(x_m1)), _p(f64(u_m1)), _p(fl(Cm)),
+                                   _p(fl(np.atleast_2d(Le))), _p(fl(np.atleast_2d(u_test))), _p(fl(np.atleast_2d(y_test))),
+                                   C.c_uint64(seed), _p(xs), _p(ys), C.byref(rmse))
+    return dict(status=st, x_sim=xs, y_sim=ys, mean_rmse=rmse.value)
+

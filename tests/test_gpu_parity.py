@@ -512,6 +512,41 @@ def test_rollout_many_scenarios_persistent_grid(rollout_kernel):
 _ROLLOUT_DIGESTS = {}
 
 
+@pytest.mark.parametrize("model,K,k_n,T_test,N", [("known", 5, 3, 40, 30), ("hilbert", 3, 4, 300, 64),
+                                                    ("hilbert4", 4, 2, 20, 30)])
+def test_prediction_bit_exact(model, K, k_n, T_test, N, rollout_kernel):
+    """pgopt_b200.test_prediction (particle_Gibbs.jl:253-314) against the oracle: simulated trajectories and outputs
+    bit for bit, mean_rmse (device tree reduction) bit for bit."""
+    rng = np.random.default_rng(61)
+    if model == "known":
+        basis, om, n_x = pg.KnownBasisVB(), O.known_model(), 2
+    elif model == "hilbert":
+        basis = pg.HilbertGPBasis([5, 5, 5], [10.0, 20.0, 20.0])
+        om, n_x = O.hilbert_model(2, 1, basis.count, basis.stride, basis.L), 2
+    else:
+        basis = pg.HilbertGPBasis([1, 5, 5, 5, 5], [4.0, 5.0, 6.0, 7.0, 8.0])
+        om, n_x = O.hilbert_model(4, 1, basis.count, basis.stride, basis.L), 4
+    A = rng.normal(0, 0.2, (K, n_x, basis.n_phi))
+    Q = np.stack([(lambda B: B @ B.T + 0.05 * np.eye(n_x))(rng.normal(0, 0.2, (n_x, n_x))) for _ in range(K)])
+    w = rng.uniform(size=(K, N))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, N, n_x))
+    um = rng.normal(0, 1, (K, 1))
+    Cm = np.zeros((1, n_x))
+    Cm[0, 0] = 1.0
+    u_test = rng.normal(0, 1, (1, T_test))
+    y_test = rng.normal(0, 1, (1, T_test))
+    ref = O.test_prediction(om, K, k_n, T_test, N, A, Q, w, x, um, Cm, [[0.1]], u_test, y_test, seed=29)
+    samples = [pg.PG_sample(A[k], Q[k], w[k], x[k].T, um[k]) for k in range(K)]
+    out = pg.test_prediction(samples, basis, pg.LinearMeasurement(Cm), 0.1, k_n, u_test, y_test, seed=29)
+    assert ref["status"] == 0
+    _assert_same("x_sim", out["raw"]["x_sim"], ref["x_sim"])
+    _assert_same("y_sim", out["raw"]["y_sim"], ref["y_sim"])
+    assert out["mean_rmse"] == ref["mean_rmse"]
+    assert out["y_test_sim"].shape == (1, T_test, K * k_n) and out["x_test_sim"].shape == (n_x, T_test + 1, K * k_n)
+    np.testing.assert_array_equal(out["y_test_sim"][:, 7, K + 1], ref["y_sim"][K + 1, 7])
+
+
 # ------------------------------------------------------------------------------------------ other state / output dimensions
 def _general_problem(n_x, n_y, T, seed):
     """A stable synthetic system with n_x states, 1 input and n_y outputs on a small Hilbert basis."""

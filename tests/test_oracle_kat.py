@@ -183,3 +183,41 @@ def test_particle_gibbs_learns_the_system():
     pred = np.stack([A @ O.phi(m, xm[:, t], u[:, t]) for t in range(T)], axis=1)
     err = pred[0] - xm[0, 1:T + 1]
     assert np.sqrt(np.mean(err ** 2)) < 0.5 * np.std(x[0])
+
+
+def _prediction_case(seed=3, K=4, k_n=3, T_test=25, N=30):
+    rng = np.random.default_rng(seed)
+    om = O.known_model()
+    A = rng.normal(0, 0.3, (K, 2, 5))
+    Q = np.stack([(lambda B: B @ B.T + 0.05 * np.eye(2))(rng.normal(0, 0.2, (2, 2))) for _ in range(K)])
+    w = rng.uniform(size=(K, N))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, N, 2))
+    um = rng.normal(0, 1, (K, 1))
+    u_test = rng.normal(0, 1, (1, T_test))
+    y_test = rng.normal(0, 1, (1, T_test))
+    return om, K, k_n, T_test, N, A, Q, w, x, um, u_test, y_test
+
+
+def test_prediction_follows_reference_structure():
+    """test_prediction (particle_Gibbs.jl:253-314) restated as one scenario per (model, repetition): simulation
+    (k, kn) must equal a single-scenario rollout of model k over the test input with stream id k + K*kn, laid out in
+    the order of the reference's reshape (:301-302), and mean_rmse must be the printed quantity (:311)."""
+    om, K, k_n, T_test, N, A, Q, w, x, um, u_test, y_test = _prediction_case()
+    Cm = [[1.0, 0.0]]
+    out = O.test_prediction(om, K, k_n, T_test, N, A, Q, w, x, um, Cm, [[0.1]], u_test, y_test, seed=9)
+    assert out["status"] == 0
+    for kn in range(k_n):
+        for k in range(K):
+            s = k + K * kn
+            one = O.rollout(om, 1, T_test, N, A[k:k + 1], Q[k:k + 1], w[k:k + 1], x[k:k + 1], um[k:k + 1], Cm, [[0.1]],
+                            u_test, seed=9, k_offset=s)
+            np.testing.assert_array_equal(out["x_sim"][s], one["X"][0])
+            np.testing.assert_array_equal(out["y_sim"][s], one["Y"][0])
+    # reference: sqrt(mean((y_test_sim .- repeat(y_test', 1, 1, K*k_n)).^2)) over the (n_y, T_test, K*k_n) array
+    y_sim = np.transpose(out["y_sim"], (2, 1, 0))
+    ref = np.sqrt(np.mean((y_sim - y_test[:, :, None]) ** 2))
+    assert abs(out["mean_rmse"] - ref) <= 1e-14 * ref
+    # different repetitions of one model are different draws
+    assert not np.array_equal(out["y_sim"][0], out["y_sim"][K])
+
