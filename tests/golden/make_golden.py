@@ -136,6 +136,22 @@ def rollout_case():
                 v=ref["v"], e=ref["e"], X=ref["X"], Y=ref["Y"])
 
 
+def prediction_case():
+    """test_prediction (particle_Gibbs.jl:253-314) on the models of the rollout fixture: K = 9 models x k_n = 2."""
+    g = rollout_case()
+    from pgopt_b200.api import HilbertGPBasis
+    hb = HilbertGPBasis([int(c) for c in g["count"]], [float(v) for v in g["L"]])
+    om = O.hilbert_model(4, 1, hb.count, hb.stride, hb.L)
+    rng = np.random.default_rng(43)
+    K, N, k_n, T_test = g["A"].shape[0], g["w"].shape[1], 2, 12
+    u_test, y_test = rng.normal(0, 1, (1, T_test)), rng.normal(0, 1, (1, T_test))
+    ref = O.test_prediction(om, K, k_n, T_test, N, g["A"], g["Q"], g["w"], g["x"], g["um"], g["Cm"], [[0.1]], u_test, y_test,
+                            seed=19)
+    assert ref["status"] == 0
+    return dict(k_n=np.array(k_n), u_test=u_test, y_test=y_test, x_sim=ref["x_sim"], y_sim=ref["y_sim"],
+                mean_rmse=np.array(ref["mean_rmse"]))
+
+
 def main():
     save = lambda name, d: np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
     save("resampling", resampling_cases())
@@ -145,6 +161,7 @@ def main():
     save("pg_hilbert", pg_case("hilbert", 30, 30, 2, 1, 0))
     save("mniw", mniw_case())
     save("rollout", rollout_case())
+    save("prediction", prediction_case())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

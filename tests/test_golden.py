@@ -85,7 +85,34 @@ def test_oracle_reproduces_mniw_and_rollout_fixtures():
         same(k, r[k], g[k])
 
 
+def _prediction_inputs():
+    g, gp = load("rollout"), load("prediction")
+    hb = pg.HilbertGPBasis([int(c) for c in g["count"]], [float(v) for v in g["L"]])
+    return g, gp, hb
+
+
+def test_oracle_reproduces_prediction_fixture():
+    g, gp, hb = _prediction_inputs()
+    om = O.hilbert_model(4, 1, hb.count, hb.stride, hb.L)
+    K, T_test = g["A"].shape[0], gp["y_test"].shape[1]
+    r = O.test_prediction(om, K, int(gp["k_n"]), T_test, g["w"].shape[1], g["A"], g["Q"], g["w"], g["x"], g["um"], g["Cm"],
+                          [[0.1]], gp["u_test"], gp["y_test"], seed=19)
+    same("x_sim", r["x_sim"], gp["x_sim"]); same("y_sim", r["y_sim"], gp["y_sim"])
+    assert r["mean_rmse"] == float(gp["mean_rmse"])
+
+
 # ------------------------------------------------------------------------------------------ GPU: CUDA path vs fixtures
+@pytest.mark.gpu
+def test_gpu_reproduces_prediction_fixture():
+    g, gp, hb = _prediction_inputs()
+    K = g["A"].shape[0]
+    samples = [pg.PG_sample(g["A"][k], g["Q"][k], g["w"][k], g["x"][k].T, g["um"][k]) for k in range(K)]
+    out = pg.test_prediction(samples, hb, pg.LinearMeasurement(g["Cm"]), 0.1, int(gp["k_n"]), gp["u_test"], gp["y_test"],
+                             seed=19)
+    same("x_sim", out["raw"]["x_sim"], gp["x_sim"]); same("y_sim", out["raw"]["y_sim"], gp["y_sim"])
+    assert out["mean_rmse"] == float(gp["mean_rmse"])
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_resampling_fixture():
     g = load("resampling")

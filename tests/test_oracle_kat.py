@@ -221,3 +221,48 @@ def test_prediction_follows_reference_structure():
     # different repetitions of one model are different draws
     assert not np.array_equal(out["y_sim"][0], out["y_sim"][K])
 
+
+def test_rollout_follows_reference_array_code():
+    """Literal NumPy transcription of the scenario code of solve_PG_OCP_Ipopt (optimal_control_Ipopt.jl:47-83,
+    :114-125) fed the oracle's own normals: x_vec_0 = A*phi(x_m1[:, star], u_m1) + L*z (:62) for a particle `star` of
+    the sample, v_vec[:, t, k] = L_Q z (:72), e_vec = R*z for scalar R (:79-81), and the recurrences
+    X[:, t+1] = A*phi(X[:, t], u_init[:, t]) + v_vec[:, t, k], Y[:, t] = g(X[:, t]) + e_vec[:, t, k] (:118-125),
+    with BLAS-order products (tolerance) instead of the oracle's defined order."""
+    rng = np.random.default_rng(12)
+    from pgopt_b200.api import HilbertGPBasis
+    hb = HilbertGPBasis([2, 3, 4], [5.0, 6.0, 7.0])
+    om = O.hilbert_model(2, 1, hb.count, hb.stride, hb.L)
+    K, H, N, n_x, seed, ROLL = 6, 15, 30, 2, 21, 7
+    A = rng.normal(0, 0.4, (K, n_x, om.n_phi))
+    Q = np.stack([(lambda B: B @ B.T + 0.05 * np.eye(n_x))(rng.normal(0, 0.2, (n_x, n_x))) for _ in range(K)])
+    w = rng.uniform(size=(K, N))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, N, n_x))
+    um = rng.normal(0, 1, (K, 1))
+    Cm = np.array([[1.0, 0.0]])
+    u_init = rng.normal(0, 1, (1, H))
+    R = 0.1
+    ref = O.rollout(om, K, H, N, A, Q, w, x, um, Cm, [[R]], u_init, seed=seed)
+    assert ref["status"] == 0
+    f = lambda k, xx, uu: A[k] @ O.phi(om, xx, uu)  # f(x, u) = PG_samples[k].A * phi(x, u)
+    for k in range(K):
+        L = np.linalg.cholesky(Q[k])
+        # noise arrays (:67-83): the normals of scenario k's stream, unwhitened like rand(MvNormal(0, Q), H)
+        zv = O.normal_pairs(seed, ROLL, k, 0, 2, H * ((n_x + 1) // 2)).reshape(H, -1)[:, :n_x]
+        ze = O.normal_pairs(seed, ROLL, k, 0, 3, H).reshape(H, 2)[:, 0]
+        np.testing.assert_allclose(ref["v"][k], zv @ L.T, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(ref["e"][k][:, 0], R * ze, rtol=1e-12, atol=1e-15)
+        # initial state (:58-62): x0 - L z0 must be f(x_m1[:, star], u_m1) for one particle of the sample
+        z0 = O.normal_pairs(seed, ROLL, k, 0, 1, (n_x + 1) // 2)[:n_x]
+        cand = np.stack([f(k, x[k, n], um[k]) for n in range(N)])
+        err = np.abs(cand - (ref["x0"][k] - L @ z0)).max(axis=1)
+        assert err.min() <= 1e-12 and w[k, int(err.argmin())] > 0
+        np.testing.assert_array_equal(ref["X"][k, 0], ref["x0"][k])
+        # recurrences (:118-125)
+        X = np.empty((H + 1, n_x))
+        X[0] = ref["x0"][k]
+        for t in range(H):
+            X[t + 1] = f(k, X[t], u_init[:, t]) + ref["v"][k, t]
+            np.testing.assert_allclose(ref["Y"][k, t], Cm @ X[t] + ref["e"][k, t], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(ref["X"][k], X, rtol=1e-9, atol=1e-11)
+
