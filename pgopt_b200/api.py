@@ -174,11 +174,13 @@ class ParticleGibbsEngine:
     def _ck(self, rc):
         check(rc, self._h)
 
-    def set_mode(self, persistent=1):
-        """1 / True (library default): tile persistent kernel, one cooperative launch per sweep; 2: warp-tile
-        persistent kernel (alternative formulation, slower); 0 / False: multi-kernel path (13 launches per step;
-        per-kernel profiling and cross-check).  All three are bit-identical."""
-        mode = 1 if persistent is True else int(persistent)
+    def set_mode(self, persistent=True):
+        """True / -1 (library default): automatic — the warp-per-chain kernel for N <= 32 (the reference's examples use
+        N = 30), otherwise the tile persistent kernel; 1: tile persistent kernel, one cooperative launch per sweep;
+        2: warp-tile persistent kernel (alternative formulation, slower); 0 / False: multi-kernel path (13 launches per
+        step; per-kernel profiling and cross-check); 3: warp-per-chain kernel (falls back to 1 when N > 32).
+        All of them are bit-identical."""
+        mode = -1 if persistent is True else int(persistent)
         self._ck(lib().pgb_set_mode(self._h, C.c_int32(mode)))
 
     def set_data(self, u, y):

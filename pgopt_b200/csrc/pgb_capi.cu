@@ -16,6 +16,7 @@
 #include "pgb_rollout.cuh"
 #include "pgb_persist.cuh"
 #include "pgb_persist_w.cuh"
+#include "pgb_small.cuh"
 
 using namespace pgb;
 
@@ -46,7 +47,7 @@ struct pgb_handle {
   double* d_replay_noise = nullptr;  // [nc][T][n_x] noise along the traced lineage (replay mode)
   bool injected_ready = false;
   // persistent (single cooperative kernel) filter path
-  int persistent = 1;  // 1: tile persistent kernel (default, fastest measured), 2: warp-tile persistent kernel, 0: one launch per phase
+  int persistent = -1;  // -1: automatic (warp-per-chain kernel when N <= 32, else the tile persistent kernel), 1: tile persistent kernel, 2: warp-tile persistent kernel, 0: one launch per phase, 3: warp-per-chain kernel (N <= 32 only)
   PersistDev pd;
   int num_sms = 0;
   // measurement
@@ -313,7 +314,7 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
     const char* abl = getenv("PGB_ABLATE");
     fd.ablate = abl ? atoi(abl) : 0;
     const char* env = getenv("PGB_PERSISTENT");
-    if (env && env[0] >= '0' && env[0] <= '2') h->persistent = env[0] - '0';
+    if (env && env[0] >= '0' && env[0] <= '3') h->persistent = env[0] - '0';
   }
   h->have_state.assign(nc, 0);
   h->h_u.assign((size_t)nu * T, 0.0);
@@ -616,8 +617,48 @@ static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
   return PGB_OK;
 }
 
+// Small particle counts (N <= 32, stored history): one warp per chain, the whole time loop in one ordinary launch
+// (pgb_small.cuh).  Returns -1 when the configuration does not qualify.
+template <int NX>
+static int run_filter_small_nx(pgb_handle* h) {
+  FilterDev& fd = h->fd;
+  MniwDev& md = h->md;
+  cudaStream_t s = h->stream;
+  const int64_t T = fd.T;
+  const int nc = fd.nc;
+  if (fd.N > SMALL_MAXN || fd.x_rows != T) return -1;
+  const size_t smem = ((size_t)((NX * fd.n_phi + 1) & ~1) + (size_t)NX * 32 + 32) * 8;
+  if (smem > 200 * 1024) return -1;
+  int first = (h->sweep_index == 1);
+  fd.sweep = (uint32_t)h->sweep_index;
+  md.sweep = fd.sweep;
+  const size_t nA = (size_t)nc * NX * fd.n_phi * 8, nQ = (size_t)nc * NX * NX * 8;
+  CK(h, cudaMemcpyAsync(h->d_A_used, fd.A, nA, cudaMemcpyDeviceToDevice, s));
+  CK(h, cudaMemcpyAsync(h->d_Q_used, h->d_Q, nQ, cudaMemcpyDeviceToDevice, s));
+  CK(h, cudaFuncSetAttribute(k_sweep_small<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LAUNCH(h, PGB_PROF_EXPAND, (k_sweep_small<NX><<<nc, 32, smem, s>>>(fd, h->pd.star_idx, first)));
+  LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
+  const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
+  LAUNCH(h, PGB_PROF_TAIL, (k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md)));
+  CK(h, cudaGetLastError());
+  return PGB_OK;
+}
+
 static int run_filter(pgb_handle* h) {
-  for (int mode = h->persistent; mode >= 1; --mode) {  // a configuration that does not fit falls through
+  int mode0 = h->persistent;
+  if (mode0 < 0 || mode0 == 3) {
+    int rc;
+    switch (h->cfg.n_x) {
+      case 1: rc = run_filter_small_nx<1>(h); break;
+      case 2: rc = run_filter_small_nx<2>(h); break;
+      case 3: rc = run_filter_small_nx<3>(h); break;
+      default: rc = run_filter_small_nx<4>(h); break;
+    }
+    if (rc >= 0) return rc;
+    mode0 = 1;
+  }
+  for (int mode = mode0; mode >= 1; --mode) {  // a configuration that does not fit falls through
     int rc;
     const bool wt = (mode == 2);
     switch (h->cfg.n_x) {
@@ -1128,7 +1169,7 @@ extern "C" int pgb_get_phase_cycles(pgb_handle* h, double* avg_cycles /*[16]*/, 
 }
 extern "C" int pgb_set_mode(pgb_handle* h, int32_t persistent) {
   NEED(h);
-  h->persistent = persistent < 0 ? 0 : (persistent > 2 ? 2 : persistent);
+  h->persistent = persistent < 0 ? -1 : (persistent > 3 ? 3 : persistent);
   return PGB_OK;
 }
 extern "C" int pgb_timer_start(pgb_handle* h) {

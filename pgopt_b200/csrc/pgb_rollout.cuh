@@ -1,6 +1,8 @@
 // pgb_rollout.cuh — scenario sampling + forward rollout for solve_PG_OCP
 // (Julia/src/optimal_control_Ipopt.jl:47-64 x_vec_0, :67-74 v_vec, :77-83 e_vec, :114-125 X_init/Y_init).
 //
+// Two kernels, identical bits: k_rollout_warp (below, default: one WARP per scenario) and k_rollout (one 128-thread CTA
+// per scenario; kept for n_phi > 640, very long horizons and as a cross-check).  Description of k_rollout:
 // One 128-thread CTA per scenario k.  The scenario's model matrix A_k (n_x x n_phi, 20 KB at n_phi = 625) is read
 // from HBM exactly once into REGISTERS: thread j keeps the c = ceil(n_phi/128) consecutive columns [j*c, (j+1)*c).
 // Every step of the horizon is then
@@ -364,9 +366,12 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
 //   * the first two levels of the oracle's balanced tree over the 128 runs are in-thread additions,
 //   * the remaining five levels are xor-butterflies at lane distance 1, 2, 4, 8, 16 (adjacent runs first), with the
 //     n_x components split over the lanes at the first levels (6 shuffles for n_x = 4),
-//   * the state x_t lives in registers of every lane (broadcast by shuffle), and nothing but __syncwarp() separates
+//   * the trajectory X[:, 0..H] lives in the warp's shared-memory slice (the lanes holding component d after the tree
+//     add the noise and store it; the sine lanes read their input from there) and nothing but __syncwarp() separates
 //     the steps: the warps of a CTA run different scenarios completely independently, one hides the other's
-//     latency-bound sines and start-up,
+//     latency-bound sines and start-up; x_vec_0 / X / Y go to global memory once per scenario, after the horizon,
+//   * RS of a lane's four runs of A_k sit in lane-private shared-memory slots instead of registers (168 instead of
+//     255 registers: 12 instead of 8 warps per SM),
 //   * when a run is exactly one row of the last tensor dimension (c == n_phi_dims[end], e.g. 5^4 = 625 functions on
 //     128 runs) every column of a run shares its prefix product and column m has last digit m.
 // Same arithmetic, same order, same bits as the kernel above and as oracle/pg_oracle.c eval_f_blocked.
@@ -416,14 +421,6 @@ __device__ __forceinline__ int rw_src(int d) {
 template <int NX>
 __device__ __forceinline__ int rw_comp(int lane) {
   return NX == 1 ? 0 : (NX == 2 ? (lane & 1) : (((lane & 1) << 1) | ((lane >> 1) & 1)));
-}
-
-template <int NX>
-__device__ __forceinline__ double rw_pick(const double (&x)[NX], int i) {
-  double r = x[0];
-#pragma unroll
-  for (int d = 1; d < NX; ++d) r = (i == d) ? x[d] : r;
-  return r;
 }
 
 // constants of the one sine a lane evaluates per step (n_sines <= 32): dimension, slot in tk, L_k, pi j / (2 L_k), 1/sqrt(L_k)

@@ -1,0 +1,212 @@
+// pgb_small.cuh — the CPF-AS time loop (Julia/src/particle_Gibbs.jl:160-200) for SMALL particle counts (N <= 32, the
+// reference's own examples use N = 30): one WARP per chain, lane n = particle n, the whole T loop in one launch.
+//
+// The tile kernels (pgb_persist.cuh) are built for throughput at N >> 10^4: four grid barriers, block scans and a
+// dozen dependent global-memory round trips per step cost ~50 us per time step however few particles there are
+// (N = 30, T = 2000: 10 sweeps/s on a B200, slower than one host core).  At N <= 32 nothing needs a barrier:
+//   * sum(v) is the balanced tree over the index range padded to 32 = the xor-butterfly over the lanes,
+//   * the strictly sequential recurrence q = q + W[n] (:28) is simply executed — every lane walks the N additions
+//     itself (broadcast reads from shared memory) and counts how many prefixes lie below ITS draw u_i, where u_i is
+//     the repeated sum u = u + 1/N (:31) taken i times: idx[i] = #{n >= 0 : q_n < u_i}, exactly the while loop of
+//     :26-29 because both sequences are non-decreasing,
+//   * the gather F[a_j] goes through shared memory, everything else (basis functions, ancestor weights, normals,
+//     log-weights) is per-lane arithmetic with the same device functions as the other kernels.
+// Same definitions, same order, same bits as the oracle and as the tile kernels (tests run all of them).  The ancestor
+// history a[t, :], the particle history x_pf (always stored: N*T is tiny here) and the final weights are left in
+// the handle's buffers exactly as the tile kernels leave them, so trace / statistics / MNIW run unchanged.
+#pragma once
+#include "pgb_filter.cuh"
+
+namespace pgb {
+
+constexpr int SMALL_MAXN = 32;
+
+struct SmallRes {
+  int idx;       // 1-based index (0: the reference's index 0; N on overrun)
+  int status;    // PGB_STATUS bits raised by this draw
+};
+
+// systematic_resampling(v, n_draw) (:17-34) for the warp: v = this lane's un-normalised weight (0 for lanes >= N),
+// rnd = rand() (:21).  Lane i < n_draw receives idx[i]; Ws is a 32-double shared scratch.
+__device__ __forceinline__ SmallRes small_resample(double v, int N, int n_draw, double rnd, double* Ws, int lane) {
+  SmallRes r;
+  r.status = 0;
+  const double S = warp_tree_sum(v);                      // :19
+  const double W = (lane < N) ? __ddiv_rn(v, S) : 0.0;
+  if (lane < N && !(W >= 0.0 && W <= 1.7976931348623157e308)) r.status |= 4;
+  __syncwarp();
+  Ws[lane] = W;
+  __syncwarp();
+  const double inc = __ddiv_rn(1.0, (double)n_draw);
+  double u = __dmul_rn(inc, rnd);                         // :21
+  for (int j = 0; j < n_draw - 1; ++j)                    // :31, taken `lane` times
+    if (j < lane) u = __dadd_rn(u, inc);
+  double q = 0.0;                                         // :23
+  int cnt = 0;
+  for (int n = 0; n < N; ++n) {                           // :26-28: q_n for n = 0 .. N-1
+    cnt += (q < u) ? 1 : 0;
+    q = __dadd_rn(q, Ws[n]);
+  }
+  if (lane < n_draw) {
+    if (cnt == N && q < u) r.status |= 1;                 // q_N < u_i: BoundsError in the reference
+    if (cnt == 0) r.status |= 2;
+  }
+  r.idx = cnt;
+  return r;
+}
+
+template <int NX>
+__global__ void __launch_bounds__(32) k_sweep_small(const __grid_constant__ FilterDev fd, int32_t* __restrict__ star_idx,
+                                                    int first) {
+  extern __shared__ __align__(16) double sm_small[];
+  double* A_sm = sm_small;                                   // [NX * n_phi]
+  double* Fs = A_sm + ((NX * fd.n_phi + 1) & ~1);             // [NX][32]  F of every particle (gather source)
+  double* Ws = Fs + NX * 32;                                  // [32]      normalised weights of the running draw
+  const int chain = blockIdx.x, lane = threadIdx.x;
+  const int N = (int)fd.N;
+  const int64_t T = fd.T;
+  const bool live = lane < N;
+  const uint32_t cid = fd.chain_base + chain;
+  int stat = 0;
+  {
+    const double* Ag = fd.A + (int64_t)chain * NX * fd.n_phi;
+    for (int i = lane; i < NX * fd.n_phi; i += 32) A_sm[i] = Ag[i];
+  }
+  double Lq[NX * NX];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) Lq[i] = fd.Lq[chain * 16 + i];
+  const double c0 = fd.c0[chain];
+  const double* xprim = fd.xprim + (int64_t)chain * NX * T;
+  double* wb = fd.wbuf + (int64_t)chain * N;
+  __syncwarp();
+
+  // ---------------------------------------------------------------- t = 0: initial particles (:160-165)
+  double x[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) x[d] = 0.0;
+  double lw = -INFINITY;
+  if (live) {
+    if (lane == N - 1) {
+#pragma unroll
+      for (int d = 0; d < NX; ++d) x[d] = xprim[d];
+    } else {
+      double z[NX];
+      draw_normals<NX>(fd, chain, PGB_STREAM_Z0, 0, lane, fd.Z0 ? fd.Z0 + (int64_t)chain * NX * (N - 1) : nullptr, z);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e <= d; ++e) acc = __fma_rn(fd.x0_chol[d + NX * e], z[e], acc);
+        x[d] = __dadd_rn(fd.x0_mean[d], acc);
+      }
+    }
+    double* x0 = x_row(fd, chain, 0);
+#pragma unroll
+    for (int d = 0; d < NX; ++d) x0[(int64_t)d * N + lane] = x[d];
+    lw = log_weight<NX>(fd, x, fd.y);
+    if (!(lw == lw)) stat |= 4;
+  }
+
+  for (int64_t t = 1; t <= T; ++t) {
+    // ---- weights of step t-1 (:198-199): e = exp(lw - max), w = e / sum(e)
+    double m = lw;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const double e = live ? pgb_exp(__dsub_rn(lw, m)) : 0.0;
+    const double S1 = warp_tree_sum(e);
+    const double w = live ? __ddiv_rn(e, S1) : 0.0;
+    if (live) {
+      wb[lane] = w;
+      if (fd.whist) fd.whist[((int64_t)chain * T + (t - 1)) * N + lane] = w;
+    }
+    if (t == T) {
+      // ---- star = systematic_resampling(w[T, :], 1)[1] (:213)
+      double us;
+      if (fd.philox) {
+        const pgb_u32x4 b = pgb_stream_block(fd.seed, PGB_STREAM_USTAR, cid, fd.sweep, 0, 0);
+        us = pgb_u53_halfopen(b.v[0], b.v[1]);
+      } else {
+        us = fd.Ustar[chain];
+      }
+      const SmallRes rs = small_resample(w, N, 1, us, Ws, lane);
+      stat |= __shfl_sync(0xffffffffu, rs.status, 0) | (rs.status & 4);
+      if (lane == 0) star_idx[chain] = rs.idx - 1;
+      break;
+    }
+    const bool anc = !first;
+    const double* up = fd.u + (int64_t)fd.n_u * (t - 1);
+    double ur, ua = 0.0;
+    if (fd.philox) {
+      pgb_u32x4 b = pgb_stream_block(fd.seed, PGB_STREAM_URES, cid, fd.sweep, (uint32_t)t, 0);
+      ur = pgb_u53_halfopen(b.v[0], b.v[1]);
+      if (anc) {
+        b = pgb_stream_block(fd.seed, PGB_STREAM_UANC, cid, fd.sweep, (uint32_t)t, 0);
+        ua = pgb_u53_halfopen(b.v[0], b.v[1]);
+      }
+    } else {
+      ur = fd.Ures[(int64_t)chain * T + t];
+      if (anc) ua = fd.Uanc[(int64_t)chain * T + t];
+    }
+    // ---- F = A * phi(x_{t-1}, u_{t-1}) once per particle (:175 and :179 evaluate the same function)
+    double F[NX];
+    eval_F<NX>(fd, A_sm, x, up, F);
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < NX; ++d) Fs[d * 32 + lane] = F[d];
+    // ---- ancestor of the conditioned trajectory (:178-181)
+    int a_last = 0;
+    if (anc) {
+      double r[NX], sq = 0.0;
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = __dsub_rn(F[d], xprim[d + NX * t]);
+#pragma unroll
+        for (int e2 = 0; e2 < d; ++e2) acc = __fma_rn(-Lq[d + NX * e2], r[e2], acc);
+        r[d] = __ddiv_rn(acc, Lq[d + NX * d]);
+        sq = __fma_rn(r[d], r[d], sq);
+      }
+      double wa = live ? __dmul_rn(w, pgb_exp(__dsub_rn(c0, __dmul_rn(sq, 0.5)))) : 0.0;
+      const double S3 = warp_tree_sum(wa);                 // :180
+      wa = live ? __ddiv_rn(wa, S3) : 0.0;
+      const SmallRes ra = small_resample(wa, N, 1, ua, Ws, lane);   // :181
+      a_last = __shfl_sync(0xffffffffu, ra.idx, 0);
+      stat |= __shfl_sync(0xffffffffu, ra.status, 0) | (ra.status & 4);
+    }
+    // ---- a[t, 1:n_draw] = systematic_resampling(w[t-1, :], n_draw) (:172 | :185)
+    const int n_draw = first ? N : N - 1;
+    const SmallRes rr = small_resample(w, N, n_draw, ur, Ws, lane);
+    stat |= rr.status;
+    // ---- x_t = f(x_{t-1}[a]) + L z (:175 | :188); slot N stays the conditioned trajectory (:160)
+    int32_t* at = fd.ah + ((int64_t)chain * T + t) * N;
+    if (lane < n_draw) {
+      const int aj = rr.idx < 1 ? 0 : rr.idx - 1;
+      double z[NX];
+      draw_normals<NX>(fd, chain, PGB_STREAM_Z, (uint32_t)t, lane,
+                       fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr, z);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
+        x[d] = __dadd_rn(Fs[d * 32 + aj], acc);
+      }
+      at[lane] = rr.idx - 1;
+    } else if (live) {  // lane == N-1, conditional sweep
+#pragma unroll
+      for (int d = 0; d < NX; ++d) x[d] = xprim[d + NX * t];
+      at[lane] = a_last - 1;
+    }
+    if (live) {
+      double* xt = x_row(fd, chain, t);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) xt[(int64_t)d * N + lane] = x[d];
+      lw = log_weight<NX>(fd, x, fd.y + (int64_t)fd.n_y * t);  // :193-197
+      if (!(lw == lw)) stat |= 4;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) stat |= __shfl_xor_sync(0xffffffffu, stat, o);
+  if (lane == 0 && stat) atomicOr(&fd.status[chain], stat);
+}
+
+}  // namespace pgb

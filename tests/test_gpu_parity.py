@@ -230,6 +230,74 @@ def test_sweep_bit_exact_injected_streams(model, first, N, T, persistent):
     assert (T <= nscan <= 2 * T - 1) if (persistent and not first) else nscan == (T if first else 2 * T - 1)
 
 
+@pytest.mark.parametrize("model", ["known", "hilbert"])
+@pytest.mark.parametrize("first", [False, True])
+@pytest.mark.parametrize("N,T", [(30, 200), (32, 40), (17, 60), (2, 30), (5, 25)])
+def test_small_n_kernel_bit_exact_injected_streams(model, first, N, T):
+    """The warp-per-chain kernel (mode 3; the automatic choice for N <= 32, the reference's examples use N = 30)
+    against the oracle: every ancestor index, particle, weight and statistic bit for bit."""
+    basis, om, A = _models()[model]
+    u, y, _ = P.make_data(T, 13)
+    s = P.injected_streams(N, T, 2, basis.n_phi, 23)
+    st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
+    xp = np.zeros((2, T))
+    if not first:
+        xp = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, True, st, 1)["x_prim"]
+    k = 1 if first else 2
+    ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, first, st, k)
+    for mode in (3, True):
+        with _engine(basis, N, T, u, y, persistent=mode) as e:
+            e.set_state(A, P.Q_TRUE, xp, k)
+            e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+            e.sweep_filter()
+            a, x, w = e.get_history()
+            Phi, Psi, Sig, star = e.get_stats()
+            _, _, xprim, _ = e.get_state()
+            smp = e.get_sample()
+            stat, nfb, nscan = e.status()
+        _assert_same("ancestors", a[1:], ref["a"][1:])
+        _assert_same("x_pf", x, ref["x"])
+        _assert_same("w", w, ref["w"])
+        assert star == ref["star"]
+        _assert_same("x_prim", xprim, ref["x_prim"])
+        _assert_same("Phi", Phi, ref["Phi"])
+        _assert_same("Psi", Psi, ref["Psi"])
+        _assert_same("Sigma", Sig, ref["Sigma"])
+        _assert_same("w_m1", smp.w_m1, ref["w_last"])
+        _assert_same("x_m1", smp.x_m1.T, ref["x_last"])
+        assert stat == ref["status"] == 0 and nfb == 0 and nscan == 0  # no exact-scan machinery on this path
+
+
+def test_small_n_kernel_matches_tile_kernel_on_whole_sampler():
+    """particle_Gibbs at the reference's N = 30 through the automatic (warp-per-chain) path and through the tile
+    persistent kernel: identical samples; both equal the oracle (Philox streams)."""
+    basis, om, _ = _models()["hilbert"]
+    N, T, K, K_b, k_d = 30, 80, 3, 2, 1
+    u, y, _ = P.make_data(T, 3)
+    V = pg.hilbert_gp_prior_V([5, 5, 5], [10, 20, 20], 2 * np.pi * np.ones(3), 100 ** 2 / (8 * np.pi ** 4))
+    ref = O.particle_gibbs(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), np.zeros((2, 125)),
+                           100 * np.eye(2), V, 100 * np.eye(2), 10.0, K, K_b, k_d, seed=5, chain=4)
+    outs = []
+    for mode in (True, 1):
+        e = pg.ParticleGibbsEngine(basis, 1, N, T)
+        try:
+            e.set_mode(mode)
+            e.set_data(u, y)
+            e.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+            e.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+            e.set_prior(V, 100 * np.eye(2), 10.0)
+            e.set_state(np.zeros((2, 125)), 100 * np.eye(2), np.zeros((2, T)), 1)
+            e.set_rng_philox(5, 4)
+            outs.append(e.particle_gibbs(K, K_b, k_d))
+        finally:
+            e.close()
+    for name, i in (("A", 0), ("Q", 1), ("w", 2), ("x", 3)):
+        _assert_same(name + " auto vs tile", outs[0][i], outs[1][i])
+    for kk in range(K):
+        _assert_same("A[%d]" % kk, outs[0][0][0, kk].reshape((2, 125), order="F"), ref["A"][kk])
+        _assert_same("w[%d]" % kk, outs[0][2][0, kk], ref["w"][kk])
+
+
 @pytest.mark.parametrize("persistent", [2, 1, 0])
 def test_sweep_with_degenerate_weights(persistent):
     """A very sharp likelihood makes a handful of particles own almost all offspring (the cooperative
@@ -453,6 +521,8 @@ def test_rollout_bit_exact(model, rollout_kernel):
     (2, 2, [5, 5, 5], 100, 11, 70),          # configs[1] basis; horizon longer than a warp
     (1, 1, [3, 7], 64, 8, 5),                # n_x = 1
     (2, 1, [1, 8, 8], 4097, 4, 6),           # N just above a power of two
+    (2, 1, [5, 5, 5], 30, 1, 8),             # a single scenario (three of the CTA's four warps idle)
+    (4, 1, [1, 5, 5, 5, 5], 2, 2, 3),        # two scenarios, two particles
 ])
 def test_rollout_bit_exact_shapes(n_x, n_y, dims, N, K, H, rollout_kernel):
     rng = np.random.default_rng(47 + n_x + N)
