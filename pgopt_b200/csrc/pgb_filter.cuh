@@ -178,6 +178,43 @@ __device__ __noinline__ void eval_F_hilbert355_pair(const FilterDev& fd, const d
   }
 }
 
+// The same specialisation for ONE particle (warp-per-chain kernel, pgb_small.cuh): branch-free 5-wide sines, the 125
+// tensor-product terms fully unrolled, factors in registers.  Same products, same fma order, same bits as eval_F.
+template <int NX>
+__device__ __forceinline__ void eval_F_hilbert355_one(const FilterDev& fd, const double* __restrict__ A_sm,
+                                                      const double x[NX], const double* __restrict__ u, double F[NX]) {
+  double t[3][5];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double zk = (k < fd.n_u) ? u[k] : x[(k - fd.n_u) < NX ? (k - fd.n_u) : 0];
+    const double zl = __dadd_rn(zk, fd.hg_L[k]);
+    double arg[5], sn[5], cs[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) arg[j] = __dmul_rn(fd.hg_pij2l[k][j], zl);
+    vsincos_wide<5>(arg, sn, cs);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) t[k][j] = __dmul_rn(fd.hg_lsi[k], sn[j]);
+  }
+  double acc[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) acc[d] = 0.0;
+#pragma unroll
+  for (int j0 = 0; j0 < 5; ++j0)
+#pragma unroll
+    for (int j1 = 0; j1 < 5; ++j1) {
+      const double pa = __dmul_rn(t[0][j0], t[1][j1]);
+#pragma unroll
+      for (int j2 = 0; j2 < 5; ++j2) {
+        const int i = (j0 * 5 + j1) * 5 + j2;
+        const double qa = __dmul_rn(pa, t[2][j2]);
+#pragma unroll
+        for (int d = 0; d < NX; ++d) acc[d] = __fma_rn(A_sm[d + NX * i], qa, acc[d]);
+      }
+    }
+#pragma unroll
+  for (int d = 0; d < NX; ++d) F[d] = acc[d];
+}
+
 // F for the thread's four particles at once (known basis: the four sin/cos chains are interleaved)
 template <int NX>
 __device__ __forceinline__ void eval_F4(const FilterDev& fd, const double* __restrict__ A_sm, const double (&x)[4][NX],

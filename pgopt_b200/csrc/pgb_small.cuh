@@ -8,7 +8,7 @@
 //   * the strictly sequential recurrence q = q + W[n] (:28) is simply executed — every lane walks the N additions
 //     itself (broadcast reads from shared memory) and counts how many prefixes lie below ITS draw u_i, where u_i is
 //     the repeated sum u = u + 1/N (:31) taken i times: idx[i] = #{n >= 0 : q_n < u_i}, exactly the while loop of
-//     :26-29 because both sequences are non-decreasing,
+//     :26-29 because both sequences are non-decreasing (weights with n_draw <= 32 only: u needs at most 31 steps),
 //   * the gather F[a_j] goes through shared memory, everything else (basis functions, ancestor weights, normals,
 //     log-weights) is per-lane arithmetic with the same device functions as the other kernels.
 // Same definitions, same order, same bits as the oracle and as the tile kernels (tests run all of them).  The ancestor
@@ -39,14 +39,20 @@ __device__ __forceinline__ SmallRes small_resample(double v, int N, int n_draw, 
   __syncwarp();
   const double inc = __ddiv_rn(1.0, (double)n_draw);
   double u = __dmul_rn(inc, rnd);                         // :21
-  for (int j = 0; j < n_draw - 1; ++j)                    // :31, taken `lane` times
-    if (j < lane) u = __dadd_rn(u, inc);
+  // the draws' grid u_i (:31, the increment taken `lane` times) and the prefix sums q_n (:28) are two independent
+  // sequential chains advanced by one unrolled loop; the prefixes stay in registers and are counted against the
+  // lane's final u afterwards (32 independent comparisons).  Beyond N the loop adds +0.0, which leaves q = q_N.
+  double qs[SMALL_MAXN];
   double q = 0.0;                                         // :23
-  int cnt = 0;
-  for (int n = 0; n < N; ++n) {                           // :26-28: q_n for n = 0 .. N-1
-    cnt += (q < u) ? 1 : 0;
-    q = __dadd_rn(q, Ws[n]);
+#pragma unroll
+  for (int n = 0; n < SMALL_MAXN; ++n) {
+    qs[n] = q;                                            // q_n
+    q = __dadd_rn(q, n < N ? Ws[n] : 0.0);
+    if (n < n_draw - 1 && n < lane) u = __dadd_rn(u, inc);
   }
+  int cnt = 0;
+#pragma unroll
+  for (int n = 0; n < SMALL_MAXN; ++n) cnt += (n < N && qs[n] < u) ? 1 : 0;
   if (lane < n_draw) {
     if (cnt == N && q < u) r.status |= 1;                 // q_N < u_i: BoundsError in the reference
     if (cnt == 0) r.status |= 2;
@@ -56,7 +62,7 @@ __device__ __forceinline__ SmallRes small_resample(double v, int N, int n_draw, 
 }
 
 template <int NX>
-__global__ void __launch_bounds__(32) k_sweep_small(const __grid_constant__ FilterDev fd, int32_t* __restrict__ star_idx,
+__global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ FilterDev fd, int32_t* __restrict__ star_idx,
                                                     int first) {
   extern __shared__ __align__(16) double sm_small[];
   double* A_sm = sm_small;                                   // [NX * n_phi]
@@ -67,6 +73,8 @@ __global__ void __launch_bounds__(32) k_sweep_small(const __grid_constant__ Filt
   const int64_t T = fd.T;
   const bool live = lane < N;
   const uint32_t cid = fd.chain_base + chain;
+  const bool hil355 = fd.basis != 0 && NX == 2 && fd.n_z == 3 && fd.n_u == 1 && fd.hg_count[0] == 5 &&
+                      fd.hg_count[1] == 5 && fd.hg_count[2] == 5;  // the reference's generic example
   int stat = 0;
   {
     const double* Ag = fd.A + (int64_t)chain * NX * fd.n_phi;
@@ -108,6 +116,16 @@ __global__ void __launch_bounds__(32) k_sweep_small(const __grid_constant__ Filt
   }
 
   for (int64_t t = 1; t <= T; ++t) {
+    // the per-step scalars (u_{t-1}, y_t, x'_t, injected uniforms) are read sequentially in t: pull the cache line
+    // of 16 steps ahead into L1 so that no step of this latency-bound loop waits for L2 / HBM
+    if (lane < 5 && t + 16 < T) {
+      const void* p = lane == 0 ? (const void*)(fd.u + (int64_t)fd.n_u * (t + 15))
+                    : lane == 1 ? (const void*)(fd.y + (int64_t)fd.n_y * (t + 16))
+                    : lane == 2 ? (const void*)(xprim + NX * (t + 16))
+                    : lane == 3 ? (const void*)(fd.philox ? (const double*)fd.u : fd.Ures + (int64_t)chain * T + t + 16)
+                                : (const void*)(fd.philox ? (const double*)fd.u : fd.Uanc + (int64_t)chain * T + t + 16);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
     // ---- weights of step t-1 (:198-199): e = exp(lw - max), w = e / sum(e)
     double m = lw;
 #pragma unroll
@@ -149,7 +167,8 @@ __global__ void __launch_bounds__(32) k_sweep_small(const __grid_constant__ Filt
     }
     // ---- F = A * phi(x_{t-1}, u_{t-1}) once per particle (:175 and :179 evaluate the same function)
     double F[NX];
-    eval_F<NX>(fd, A_sm, x, up, F);
+    if (hil355) eval_F_hilbert355_one<NX>(fd, A_sm, x, up, F);
+    else eval_F<NX>(fd, A_sm, x, up, F);
     __syncwarp();
 #pragma unroll
     for (int d = 0; d < NX; ++d) Fs[d * 32 + lane] = F[d];
