@@ -394,7 +394,35 @@ def secondary_measurements(fp64_peak_tflops=None):
                               "status": list(eng.status(0))}
     finally:
         eng.close()
+    # the reference's own examples (BASELINE.json configs[0], configs[1]): N = 30 particles, T = 2000, on the
+    # warp-per-chain kernel; PG sweeps/s (filter + trace + statistics + MNIW) for one chain and for 256 batched chains
+    ex = {}
+    for model in ("known", "generic"):
+        ex[model] = {"one_chain": _small_config(model, 1, 10), "256_chains_batched": _small_config(model, 256, 5)}
+    res["reference_examples_N30_T2000_pg_sweeps_per_s"] = ex
     return res
+
+
+def _small_config(model, n_chains, sweeps, N=30, T=2000):
+    import pgopt_b200 as pg
+    prob = build_problem(model, T, 0)
+    eng = pg.ParticleGibbsEngine(prob["basis"], 1, N, T, n_chains=n_chains)
+    try:
+        eng.set_data(prob["u"], prob["y"])
+        eng.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+        eng.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+        eng.set_prior(prob["V"], 100 * np.eye(2), 10.0)
+        for c in range(n_chains):
+            eng.set_state(prob["A"], prob["Q"], prob["x_prim"], 2, chain=c)
+        eng.set_rng_philox(7, 0)
+        eng.sweep(2)
+        eng.synchronize()
+        t0 = time.perf_counter()
+        eng.sweep(sweeps)
+        eng.synchronize()
+        return n_chains * sweeps / (time.perf_counter() - t0)
+    finally:
+        eng.close()
 
 
 # ------------------------------------------------------------------------------------------- CPU arm

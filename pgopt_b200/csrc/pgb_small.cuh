@@ -44,15 +44,18 @@ __device__ __forceinline__ SmallRes small_resample(double v, int N, int n_draw, 
   // lane's final u afterwards (32 independent comparisons).  Beyond N the loop adds +0.0, which leaves q = q_N.
   double qs[SMALL_MAXN];
   double q = 0.0;                                         // :23
+  const int nu = (lane < n_draw - 1) ? lane : n_draw - 1;  // increments of u this lane takes
 #pragma unroll
   for (int n = 0; n < SMALL_MAXN; ++n) {
-    qs[n] = q;                                            // q_n
-    q = __dadd_rn(q, n < N ? Ws[n] : 0.0);
-    if (n < n_draw - 1 && n < lane) u = __dadd_rn(u, inc);
+    qs[n] = q;                                            // q_n (= q_N for n >= N: lanes >= N stored W = 0)
+    q = __dadd_rn(q, Ws[n]);
+    if (n < nu) u = __dadd_rn(u, inc);
   }
+  // all 32 entries are compared: the entries n >= N equal q_N, so a count above N means q_N < u (the overrun case)
   int cnt = 0;
 #pragma unroll
-  for (int n = 0; n < SMALL_MAXN; ++n) cnt += (n < N && qs[n] < u) ? 1 : 0;
+  for (int n = 0; n < SMALL_MAXN; ++n) cnt += (qs[n] < u) ? 1 : 0;
+  if (cnt > N) cnt = N;
   if (lane < n_draw) {
     if (cnt == N && q < u) r.status |= 1;                 // q_N < u_i: BoundsError in the reference
     if (cnt == 0) r.status |= 2;
@@ -130,7 +133,13 @@ __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ F
     double m = lw;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const double e = live ? pgb_exp(__dsub_rn(lw, m)) : 0.0;
+    double e;
+    {
+      const double ea[1] = {live ? __dsub_rn(lw, m) : 0.0};
+      double ev[1];
+      vexp_wide<1>(ea, ev);  // branch-free, bit-identical to pgb_exp (the lanes' arguments fall in different ranges)
+      e = live ? ev[0] : 0.0;
+    }
     const double S1 = warp_tree_sum(e);
     const double w = live ? __ddiv_rn(e, S1) : 0.0;
     if (live) {
@@ -167,8 +176,30 @@ __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ F
     }
     // ---- F = A * phi(x_{t-1}, u_{t-1}) once per particle (:175 and :179 evaluate the same function)
     double F[NX];
-    if (hil355) eval_F_hilbert355_one<NX>(fd, A_sm, x, up, F);
-    else eval_F<NX>(fd, A_sm, x, up, F);
+    if (hil355) {
+      eval_F_hilbert355_one<NX>(fd, A_sm, x, up, F);
+    } else if (fd.basis == 0) {
+      // examples/PG_OCP_known_basis_functions_Altro.jl:34 with the two trigonometric chains interleaved, branch-free
+      const double x1 = x[NX > 1 ? 1 : 0], u0 = up[0];
+      const double ang[2] = {__dmul_rn(3.0, x[0]), __dmul_rn(2.0, x1)};
+      double sn[2], cs[2];
+      vsincos_wide<2>(ang, sn, cs);
+      double phi[5];
+      phi[0] = __dmul_rn(0.1, x[0]);
+      phi[1] = __dmul_rn(0.1, x1);
+      phi[2] = u0;
+      phi[3] = __dmul_rn(__dmul_rn(0.01, cs[0]), x1);
+      phi[4] = __dmul_rn(__dmul_rn(0.1, sn[1]), u0);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) acc = __fma_rn(A_sm[d + NX * i], phi[i], acc);
+        F[d] = acc;
+      }
+    } else {
+      eval_F<NX>(fd, A_sm, x, up, F);
+    }
     __syncwarp();
 #pragma unroll
     for (int d = 0; d < NX; ++d) Fs[d * 32 + lane] = F[d];
@@ -184,7 +215,10 @@ __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ F
         r[d] = __ddiv_rn(acc, Lq[d + NX * d]);
         sq = __fma_rn(r[d], r[d], sq);
       }
-      double wa = live ? __dmul_rn(w, pgb_exp(__dsub_rn(c0, __dmul_rn(sq, 0.5)))) : 0.0;
+      const double pa[1] = {__dsub_rn(c0, __dmul_rn(sq, 0.5))};
+      double pv[1];
+      vexp_wide<1>(pa, pv);
+      double wa = live ? __dmul_rn(w, pv[0]) : 0.0;
       const double S3 = warp_tree_sum(wa);                 // :180
       wa = live ? __ddiv_rn(wa, S3) : 0.0;
       const SmallRes ra = small_resample(wa, N, 1, ua, Ws, lane);   // :181
@@ -200,8 +234,29 @@ __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ F
     if (lane < n_draw) {
       const int aj = rr.idx < 1 ? 0 : rr.idx - 1;
       double z[NX];
-      draw_normals<NX>(fd, chain, PGB_STREAM_Z, (uint32_t)t, lane,
-                       fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr, z);
+      if (fd.philox) {  // the branch-free Philox / Box-Muller routines (same bits as pgb_normal_pair)
+        constexpr int NP = (NX + 1) / 2;
+        pgb_u32x4 ctr[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          ctr[p].v[0] = (uint32_t)(lane * NP + p);
+          ctr[p].v[1] = (uint32_t)t;
+          ctr[p].v[2] = fd.sweep;
+          ctr[p].v[3] = ((uint32_t)PGB_STREAM_Z << 24) | (cid & 0x00ffffffu);
+        }
+        vphilox_wide<NP>(ctr, (uint32_t)fd.seed, (uint32_t)(fd.seed >> 32));
+        double z0[NP], z1[NP];
+        vnormal_pairs_wide<NP>(ctr, z0, z1);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          z[2 * p] = z0[p];
+          if (2 * p + 1 < NX) z[2 * p + 1] = z1[p];
+        }
+      } else {
+        const double* zin = fd.Z + ((int64_t)chain * T + t) * NX * N;
+#pragma unroll
+        for (int d = 0; d < NX; ++d) z[d] = zin[lane * NX + d];
+      }
 #pragma unroll
       for (int d = 0; d < NX; ++d) {
         double acc = 0.0;

@@ -362,7 +362,7 @@ def test_ancestor_draw_shortcut_equals_exact_scan(model, N, T):
     for force in (0, 2):
         _lib.lib().pgb_test_force_fallback(force)
         try:
-            with _engine(basis, N, T, u, y, persistent=True) as e:
+            with _engine(basis, N, T, u, y, persistent=1) as e:
                 e.set_state(A, P.Q_TRUE, xp, 2)
                 e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
                 e.sweep_filter()
