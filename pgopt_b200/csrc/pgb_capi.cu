@@ -637,7 +637,7 @@ static int run_filter_small_nx(pgb_handle* h) {
   CK(h, cudaMemcpyAsync(h->d_Q_used, h->d_Q, nQ, cudaMemcpyDeviceToDevice, s));
   CK(h, cudaFuncSetAttribute(k_sweep_small<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   LAUNCH(h, PGB_PROF_EXPAND, (k_sweep_small<NX><<<nc, 32, smem, s>>>(fd, h->pd.star_idx, first)));
-  LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  LAUNCH(h, PGB_PROF_TAIL, (k_trace_small<NX><<<nc, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
   LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
   const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
   LAUNCH(h, PGB_PROF_TAIL, (k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md)));

@@ -283,4 +283,37 @@ __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ F
   if (lane == 0 && stat) atomicOr(&fd.status[chain], stat);
 }
 
+// Backward trace of the ancestor path (:213-218) for N <= 32, one warp per chain.  k_trace walks the T dependent
+// loads a[t+1, star] with one thread (2.6 ms at T = 2000, a quarter of a small-N sweep); here lane n loads a[t, n] and
+// x_pf[:, n, t] of a whole row — addresses that do not depend on the path, so the loads of many steps are in flight
+// at once — and the hop itself is a shuffle.
+template <int NX>
+__global__ void __launch_bounds__(32) k_trace_small(FilterDev fd, const int32_t* __restrict__ star_idx,
+                                                    int64_t* __restrict__ star_out) {
+  const int chain = blockIdx.x, lane = threadIdx.x;
+  const int N = (int)fd.N;
+  const int64_t T = fd.T;
+  int b = star_idx[chain];
+  if (b < 0) b = 0;
+  if (lane == 0) star_out[chain] = (int64_t)b + 1;
+  double* xp = fd.xprim + (int64_t)chain * NX * T;
+  const double* xh = fd.xh + (int64_t)chain * T * NX * N;
+  const int32_t* ah = fd.ah + (int64_t)chain * T * N;
+  const int ln = lane < N ? lane : 0;
+#pragma unroll 8
+  for (int64_t t = T - 1; t >= 0; --t) {
+    double xv[NX];
+#pragma unroll
+    for (int d = 0; d < NX; ++d) xv[d] = __ldg(xh + (t * NX + d) * N + ln);
+    const int a = (t > 0) ? __ldg(ah + t * N + ln) : 0;
+#pragma unroll
+    for (int d = 0; d < NX; ++d) {
+      const double xb = __shfl_sync(0xffffffffu, xv[d], b);
+      if (lane == 0) xp[d + NX * t] = xb;
+    }
+    b = __shfl_sync(0xffffffffu, a, b);  // star = a[t, star]  (:216)
+    if (b < 0) b = 0;
+  }
+}
+
 }  // namespace pgb
