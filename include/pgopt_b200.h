@@ -140,11 +140,12 @@ int pgb_synchronize(pgb_handle* h);
  * pgb_get_launch_count returns the number of kernels this handle has launched so far. */
 enum { PGB_PROF_PREP = 0, PGB_PROF_NORM, PGB_PROF_SCAN_LOCAL, PGB_PROF_RESOLVE, PGB_PROF_EXPAND, PGB_PROF_SEQ,
        PGB_PROF_EXPAND_FB, PGB_PROF_WEIGHTS, PGB_PROF_INIT, PGB_PROF_TAIL, PGB_PROF_MNIW, PGB_PROF_NCLASS };
-/* Filter kernel of a sweep.  -1 (default): automatic - the warp-per-chain kernel when N <= 32 (the reference's
- * examples run N = 30) and the particle history is stored, otherwise mode 1.  1: the whole T loop as one cooperative
- * persistent kernel with 1024-particle CTA tiles; 2: the same in the warp-tile formulation; 0: one launch per phase
- * (13 launches per time step); 3: the warp-per-chain kernel (falls back to 1 when N > 32).  The alternatives are
- * kept for profiling and as cross-checks; all of them are bit-identical. */
+/* Filter kernel of a sweep.  -1 (default): automatic - when the particle history is stored, the warp-per-chain kernel
+ * for N <= 32 (the reference's examples run N = 30) and the one-CTA-per-chain kernel for N <= 1024; otherwise mode 1.
+ * 1: the whole T loop as one cooperative persistent kernel with 1024-particle CTA tiles; 2: the same in the warp-tile
+ * formulation; 0: one launch per phase (13 launches per time step); 3: the warp / one-CTA-per-chain kernels (falls
+ * back to 1 when N > 1024 or the history is replayed).  The alternatives are kept for profiling and as
+ * cross-checks; all of them are bit-identical. */
 int pgb_set_mode(pgb_handle* h, int32_t persistent);
 /* average over CTAs of the SM-clock cycles thread 0 spent in each section of the last persistent sweep
  * (section ids documented in pgb_persist.cuh: 1 phase A, 2 wait B1, 3 scan-local main, 4 normalise side, 5 wait B2,

@@ -176,10 +176,10 @@ class ParticleGibbsEngine:
 
     def set_mode(self, persistent=True):
         """True / -1 (library default): automatic — the warp-per-chain kernel for N <= 32 (the reference's examples use
-        N = 30), otherwise the tile persistent kernel; 1: tile persistent kernel, one cooperative launch per sweep;
-        2: warp-tile persistent kernel (alternative formulation, slower); 0 / False: multi-kernel path (13 launches per
-        step; per-kernel profiling and cross-check); 3: warp-per-chain kernel (falls back to 1 when N > 32).
-        All of them are bit-identical."""
+        N = 30), the one-CTA-per-chain kernel for N <= 1024, otherwise the tile persistent kernel; 1: tile persistent
+        kernel, one cooperative launch per sweep; 2: warp-tile persistent kernel (alternative formulation, slower);
+        0 / False: multi-kernel path (13 launches per step; per-kernel profiling and cross-check); 3: warp / one-CTA
+        kernels (fall back to 1 when N > 1024).  All of them are bit-identical."""
         mode = -1 if persistent is True else int(persistent)
         self._ck(lib().pgb_set_mode(self._h, C.c_int32(mode)))
 

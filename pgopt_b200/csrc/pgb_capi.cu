@@ -617,17 +617,23 @@ static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
   return PGB_OK;
 }
 
+static int64_t g_small_auto_max = CTA_MAXN;  // largest N the automatic mode gives to the warp / one-CTA-per-chain kernels
+                                               // (measured faster than the tile kernel up to 1024, profiles/r01_mid_n_kernel.md)
+
 // Small particle counts (N <= 32, stored history): one warp per chain, the whole time loop in one ordinary launch
 // (pgb_small.cuh).  Returns -1 when the configuration does not qualify.
 template <int NX>
-static int run_filter_small_nx(pgb_handle* h) {
+static int run_filter_small_nx(pgb_handle* h, int64_t n_max) {
   FilterDev& fd = h->fd;
   MniwDev& md = h->md;
   cudaStream_t s = h->stream;
   const int64_t T = fd.T;
   const int nc = fd.nc;
-  if (fd.N > SMALL_MAXN || fd.x_rows != T) return -1;
-  const size_t smem = ((size_t)((NX * fd.n_phi + 1) & ~1) + (size_t)NX * 32 + 32) * 8;
+  if (fd.N > n_max || fd.N > CTA_MAXN || fd.x_rows != T) return -1;
+  const bool cta = fd.N > SMALL_MAXN;  // mid-size N: one CTA per chain (k_sweep_cta), thread = particle
+  const int np_thr = (int)((fd.N + 31) / 32) * 32;
+  const size_t smem = cta ? ((size_t)((NX * fd.n_phi + 1) & ~1) + (size_t)(NX + 2) * np_thr + 2) * 8 + sizeof(CtaShared)
+                          : ((size_t)((NX * fd.n_phi + 1) & ~1) + (size_t)NX * 32 + 32) * 8;
   if (smem > 200 * 1024) return -1;
   int first = (h->sweep_index == 1);
   fd.sweep = (uint32_t)h->sweep_index;
@@ -635,9 +641,15 @@ static int run_filter_small_nx(pgb_handle* h) {
   const size_t nA = (size_t)nc * NX * fd.n_phi * 8, nQ = (size_t)nc * NX * NX * 8;
   CK(h, cudaMemcpyAsync(h->d_A_used, fd.A, nA, cudaMemcpyDeviceToDevice, s));
   CK(h, cudaMemcpyAsync(h->d_Q_used, h->d_Q, nQ, cudaMemcpyDeviceToDevice, s));
-  CK(h, cudaFuncSetAttribute(k_sweep_small<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  LAUNCH(h, PGB_PROF_EXPAND, (k_sweep_small<NX><<<nc, 32, smem, s>>>(fd, h->pd.star_idx, first)));
-  LAUNCH(h, PGB_PROF_TAIL, (k_trace_small<NX><<<nc, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  if (cta) {
+    CK(h, cudaFuncSetAttribute(k_sweep_cta<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(h, PGB_PROF_EXPAND, (k_sweep_cta<NX><<<nc, np_thr, smem, s>>>(fd, h->pd.star_idx, first)));
+    LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  } else {
+    CK(h, cudaFuncSetAttribute(k_sweep_small<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(h, PGB_PROF_EXPAND, (k_sweep_small<NX><<<nc, 32, smem, s>>>(fd, h->pd.star_idx, first)));
+    LAUNCH(h, PGB_PROF_TAIL, (k_trace_small<NX><<<nc, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+  }
   LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
   const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
   LAUNCH(h, PGB_PROF_TAIL, (k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md)));
@@ -649,11 +661,13 @@ static int run_filter(pgb_handle* h) {
   int mode0 = h->persistent;
   if (mode0 < 0 || mode0 == 3) {
     int rc;
+    // the warp kernel up to N = 32, the one-CTA-per-chain kernel up to N = 1024 (automatic and mode 3)
+    const int64_t n_max = (mode0 == 3) ? CTA_MAXN : g_small_auto_max;
     switch (h->cfg.n_x) {
-      case 1: rc = run_filter_small_nx<1>(h); break;
-      case 2: rc = run_filter_small_nx<2>(h); break;
-      case 3: rc = run_filter_small_nx<3>(h); break;
-      default: rc = run_filter_small_nx<4>(h); break;
+      case 1: rc = run_filter_small_nx<1>(h, n_max); break;
+      case 2: rc = run_filter_small_nx<2>(h, n_max); break;
+      case 3: rc = run_filter_small_nx<3>(h, n_max); break;
+      default: rc = run_filter_small_nx<4>(h, n_max); break;
     }
     if (rc >= 0) return rc;
     mode0 = 1;

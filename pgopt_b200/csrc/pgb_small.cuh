@@ -316,4 +316,307 @@ __global__ void __launch_bounds__(32) k_trace_small(FilterDev fd, const int32_t*
   }
 }
 
+// ==========================================================================================================
+// k_sweep_cta — the same idea for mid-size particle counts (32 < N <= 1024): one CTA per chain, thread n = particle n,
+// the whole T loop in one ordinary launch.  sum(v) = warp butterfly, then the butterfly over the warp totals (aligned
+// 32-leaf subtrees of the oracle's balanced tree); the sequential prefix q_n = q_{n-1} + W[n] (:28) is walked ONCE by
+// thread 0 into shared memory while every other thread builds its own u_i = u + 1/N + ... (:31, i additions) — the two
+// sequential chains of the reference run side by side — and idx[i] = #{n : q_n < u_i} is a binary search in the
+// monotone prefix array.  Everything else is the per-particle arithmetic of k_sweep_small.
+// ==========================================================================================================
+constexpr int CTA_MAXN = 1024;
+
+struct CtaShared {
+  double red[2][32];   // warp partials of the block reductions (double-buffered)
+  int bci[4];          // broadcast: index / status of a single draw
+};
+
+__device__ __forceinline__ double cta_tree_sum(double v, CtaShared& cs, int W, int& flip) {
+  v = warp_tree_sum(v);
+  if (W == 1) return v;
+  double* r = cs.red[flip];
+  flip ^= 1;
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  return warp_tree_sum(lane < W ? r[lane] : 0.0);
+}
+__device__ __forceinline__ double cta_max(double v, CtaShared& cs, int W, int& flip) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (W == 1) return v;
+  double* r = cs.red[flip];
+  flip ^= 1;
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  double p = lane < W ? r[lane] : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) p = fmax(p, __shfl_xor_sync(0xffffffffu, p, o));
+  return p;
+}
+
+// systematic_resampling(v, n_draw) (:17-34) for the CTA; thread i < n_draw receives idx[i].
+__device__ __forceinline__ SmallRes cta_resample(double v, int N, int n_draw, double rnd, double* Ws, double* qs,
+                                                 CtaShared& cs, int W, int& flip) {
+  const int tid = threadIdx.x;
+  SmallRes r;
+  r.status = 0;
+  const double S = cta_tree_sum(v, cs, W, flip);           // :19
+  const double Wn = (tid < N) ? __ddiv_rn(v, S) : 0.0;
+  if (tid < N && !(Wn >= 0.0 && Wn <= 1.7976931348623157e308)) r.status |= 4;
+  __syncthreads();                                         // readers of the previous draw's Ws / qs are done
+  Ws[tid] = Wn;
+  __syncthreads();
+  const double inc = __ddiv_rn(1.0, (double)n_draw);
+  double u = __dmul_rn(inc, rnd);                          // :21
+  if (tid == 0) {
+    double q = 0.0;                                        // :23
+    const int Np = (int)blockDim.x;                        // multiple of 32; Ws[n] = 0 for n >= N, so q stays q_N there
+    for (int n = 0; n < Np; n += 8) {                      // :28, strictly left to right
+      double wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = Ws[n + j];       // the loads do not wait for the stores of the chain
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        qs[n + j] = q;
+        q = __dadd_rn(q, wv[j]);
+      }
+    }
+    qs[Np] = q;                                            // = q_N (also qs[N] when N < Np)
+  } else {
+    const int nu = (tid < n_draw - 1) ? tid : n_draw - 1;  // :31, the increment taken tid times
+    for (int j = 0; j < nu; ++j) u = __dadd_rn(u, inc);
+  }
+  __syncthreads();
+  // idx = #{n in 0..N-1 : q_n < u} (q_0 = 0): first position of the monotone prefix array that is >= u
+  int lo = 0, hi = N;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (qs[mid] < u) lo = mid + 1;
+    else hi = mid;
+  }
+  if (tid < n_draw) {
+    if (lo == N && qs[N] < u) r.status |= 1;
+    if (lo == 0) r.status |= 2;
+  }
+  r.idx = lo;
+  return r;
+}
+
+template <int NX>
+__global__ void __launch_bounds__(CTA_MAXN, 1) k_sweep_cta(const __grid_constant__ FilterDev fd,
+                                                           int32_t* __restrict__ star_idx, int first) {
+  extern __shared__ __align__(16) double sm_cta[];
+  const int tid = threadIdx.x;
+  const int W = blockDim.x >> 5, Np = blockDim.x;
+  double* A_sm = sm_cta;                                      // [NX * n_phi]
+  double* Fs = A_sm + ((NX * fd.n_phi + 1) & ~1);             // [NX][Np]
+  double* Ws = Fs + NX * Np;                                  // [Np]
+  double* qs = Ws + Np;                                       // [Np + 2]
+  CtaShared& cs = *reinterpret_cast<CtaShared*>(qs + Np + 2);
+  const int chain = blockIdx.x;
+  const int N = (int)fd.N;
+  const int64_t T = fd.T;
+  const bool live = tid < N;
+  const uint32_t cid = fd.chain_base + chain;
+  const bool hil355 = fd.basis != 0 && NX == 2 && fd.n_z == 3 && fd.n_u == 1 && fd.hg_count[0] == 5 &&
+                      fd.hg_count[1] == 5 && fd.hg_count[2] == 5;
+  int stat = 0, flip = 0;
+  {
+    const double* Ag = fd.A + (int64_t)chain * NX * fd.n_phi;
+    for (int i = tid; i < NX * fd.n_phi; i += Np) A_sm[i] = Ag[i];
+  }
+  double Lq[NX * NX];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) Lq[i] = fd.Lq[chain * 16 + i];
+  const double c0 = fd.c0[chain];
+  const double* xprim = fd.xprim + (int64_t)chain * NX * T;
+  double* wb = fd.wbuf + (int64_t)chain * N;
+  __syncthreads();
+
+  // ---------------------------------------------------------------- t = 0 (:160-165)
+  double x[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) x[d] = 0.0;
+  double lw = -INFINITY;
+  if (live) {
+    if (tid == N - 1) {
+#pragma unroll
+      for (int d = 0; d < NX; ++d) x[d] = xprim[d];
+    } else {
+      double z[NX];
+      draw_normals<NX>(fd, chain, PGB_STREAM_Z0, 0, tid, fd.Z0 ? fd.Z0 + (int64_t)chain * NX * (N - 1) : nullptr, z);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e = 0; e <= d; ++e) acc = __fma_rn(fd.x0_chol[d + NX * e], z[e], acc);
+        x[d] = __dadd_rn(fd.x0_mean[d], acc);
+      }
+    }
+    double* x0 = x_row(fd, chain, 0);
+#pragma unroll
+    for (int d = 0; d < NX; ++d) x0[(int64_t)d * N + tid] = x[d];
+    lw = log_weight<NX>(fd, x, fd.y);
+    if (!(lw == lw)) stat |= 4;
+  }
+
+  for (int64_t t = 1; t <= T; ++t) {
+    // ---- weights of step t-1 (:198-199)
+    const double m = cta_max(lw, cs, W, flip);
+    double e;
+    {
+      const double ea[1] = {live ? __dsub_rn(lw, m) : 0.0};
+      double ev[1];
+      vexp_wide<1>(ea, ev);
+      e = live ? ev[0] : 0.0;
+    }
+    const double S1 = cta_tree_sum(e, cs, W, flip);
+    const double w = live ? __ddiv_rn(e, S1) : 0.0;
+    if (live) {
+      wb[tid] = w;
+      if (fd.whist) fd.whist[((int64_t)chain * T + (t - 1)) * N + tid] = w;
+    }
+    if (t == T) {  // star = systematic_resampling(w[T, :], 1)[1] (:213)
+      double us;
+      if (fd.philox) {
+        const pgb_u32x4 b = pgb_stream_block(fd.seed, PGB_STREAM_USTAR, cid, fd.sweep, 0, 0);
+        us = pgb_u53_halfopen(b.v[0], b.v[1]);
+      } else {
+        us = fd.Ustar[chain];
+      }
+      const SmallRes rs = cta_resample(w, N, 1, us, Ws, qs, cs, W, flip);
+      stat |= (rs.status & 4);
+      if (tid == 0) {
+        stat |= rs.status;
+        star_idx[chain] = rs.idx - 1;
+      }
+      break;
+    }
+    const bool anc = !first;
+    const double* up = fd.u + (int64_t)fd.n_u * (t - 1);
+    double ur, ua = 0.0;
+    if (fd.philox) {
+      pgb_u32x4 b = pgb_stream_block(fd.seed, PGB_STREAM_URES, cid, fd.sweep, (uint32_t)t, 0);
+      ur = pgb_u53_halfopen(b.v[0], b.v[1]);
+      if (anc) {
+        b = pgb_stream_block(fd.seed, PGB_STREAM_UANC, cid, fd.sweep, (uint32_t)t, 0);
+        ua = pgb_u53_halfopen(b.v[0], b.v[1]);
+      }
+    } else {
+      ur = fd.Ures[(int64_t)chain * T + t];
+      if (anc) ua = fd.Uanc[(int64_t)chain * T + t];
+    }
+    // ---- F = A * phi(x_{t-1}, u_{t-1})
+    double F[NX];
+    if (hil355) {
+      eval_F_hilbert355_one<NX>(fd, A_sm, x, up, F);
+    } else if (fd.basis == 0) {
+      const double x1 = x[NX > 1 ? 1 : 0], u0 = up[0];
+      const double ang[2] = {__dmul_rn(3.0, x[0]), __dmul_rn(2.0, x1)};
+      double sn[2], csn[2];
+      vsincos_wide<2>(ang, sn, csn);
+      double phi[5];
+      phi[0] = __dmul_rn(0.1, x[0]);
+      phi[1] = __dmul_rn(0.1, x1);
+      phi[2] = u0;
+      phi[3] = __dmul_rn(__dmul_rn(0.01, csn[0]), x1);
+      phi[4] = __dmul_rn(__dmul_rn(0.1, sn[1]), u0);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) acc = __fma_rn(A_sm[d + NX * i], phi[i], acc);
+        F[d] = acc;
+      }
+    } else {
+      eval_F<NX>(fd, A_sm, x, up, F);
+    }
+    __syncthreads();  // the previous step's gathers from Fs are done
+#pragma unroll
+    for (int d = 0; d < NX; ++d) Fs[d * Np + tid] = F[d];
+    // ---- ancestor of the conditioned trajectory (:178-181)
+    int a_last = 0;
+    if (anc) {
+      double r[NX], sq = 0.0;
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = __dsub_rn(F[d], xprim[d + NX * t]);
+#pragma unroll
+        for (int e2 = 0; e2 < d; ++e2) acc = __fma_rn(-Lq[d + NX * e2], r[e2], acc);
+        r[d] = __ddiv_rn(acc, Lq[d + NX * d]);
+        sq = __fma_rn(r[d], r[d], sq);
+      }
+      const double pa[1] = {__dsub_rn(c0, __dmul_rn(sq, 0.5))};
+      double pv[1];
+      vexp_wide<1>(pa, pv);
+      double wa = live ? __dmul_rn(w, pv[0]) : 0.0;
+      const double S3 = cta_tree_sum(wa, cs, W, flip);      // :180
+      wa = live ? __ddiv_rn(wa, S3) : 0.0;
+      const SmallRes ra = cta_resample(wa, N, 1, ua, Ws, qs, cs, W, flip);   // :181
+      stat |= (ra.status & 4);
+      if (tid == 0) {
+        stat |= ra.status;
+        cs.bci[0] = ra.idx;
+      }
+      __syncthreads();
+      a_last = cs.bci[0];
+    }
+    // ---- a[t, 1:n_draw] = systematic_resampling(w[t-1, :], n_draw) (:172 | :185)
+    const int n_draw = first ? N : N - 1;
+    const SmallRes rr = cta_resample(w, N, n_draw, ur, Ws, qs, cs, W, flip);
+    stat |= rr.status;
+    // ---- x_t = f(x_{t-1}[a]) + L z (:175 | :188)
+    int32_t* at = fd.ah + ((int64_t)chain * T + t) * N;
+    if (tid < n_draw) {
+      const int aj = rr.idx < 1 ? 0 : rr.idx - 1;
+      double z[NX];
+      if (fd.philox) {
+        constexpr int NP = (NX + 1) / 2;
+        pgb_u32x4 ctr[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          ctr[p].v[0] = (uint32_t)(tid * NP + p);
+          ctr[p].v[1] = (uint32_t)t;
+          ctr[p].v[2] = fd.sweep;
+          ctr[p].v[3] = ((uint32_t)PGB_STREAM_Z << 24) | (cid & 0x00ffffffu);
+        }
+        vphilox_wide<NP>(ctr, (uint32_t)fd.seed, (uint32_t)(fd.seed >> 32));
+        double z0[NP], z1[NP];
+        vnormal_pairs_wide<NP>(ctr, z0, z1);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          z[2 * p] = z0[p];
+          if (2 * p + 1 < NX) z[2 * p + 1] = z1[p];
+        }
+      } else {
+        const double* zin = fd.Z + ((int64_t)chain * T + t) * NX * N;
+#pragma unroll
+        for (int d = 0; d < NX; ++d) z[d] = zin[tid * NX + d];
+      }
+#pragma unroll
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+#pragma unroll
+        for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
+        x[d] = __dadd_rn(Fs[d * Np + aj], acc);
+      }
+      at[tid] = rr.idx - 1;
+    } else if (live) {  // tid == N-1, conditional sweep (:160)
+#pragma unroll
+      for (int d = 0; d < NX; ++d) x[d] = xprim[d + NX * t];
+      at[tid] = a_last - 1;
+    }
+    if (live) {
+      double* xt = x_row(fd, chain, t);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) xt[(int64_t)d * N + tid] = x[d];
+      lw = log_weight<NX>(fd, x, fd.y + (int64_t)fd.n_y * t);  // :193-197
+      if (!(lw == lw)) stat |= 4;
+    }
+  }
+  if (stat) atomicOr(&fd.status[chain], stat);
+}
+
 }  // namespace pgb

@@ -5,7 +5,11 @@ BASELINE.json configs[0]) up to the point where the OCP solver takes over: data 
 wall times, PG sweeps/s, the mean RMSE of the forward simulations against the test output (the number the
 reference prints, particle_Gibbs.jl:311-312) next to the standard deviation of the test output.
 
-    python scripts/example_known_basis.py [K] [K_b] [k_d]      (defaults 100, 1000, 50: K_total = 6050 sweeps)
+    python scripts/example_end_to_end.py [K] [K_b] [k_d] [basis]      (defaults 100, 1000, 50, known: K_total = 6050)
+
+basis = generic runs the same data through the setup of examples/PG_OCP_generic_basis_functions_Altro.jl (paper
+Sec. V-C, BASELINE.json configs[1]): the reduced-rank GP basis with 5 x 5 x 5 functions on L = [10, 20, 20] (:34-48) and
+the squared-exponential prior V with l = 2 pi, s_f = 100^2 / (8 pi^4) (:111-115).
 """
 import json
 import os
@@ -42,18 +46,25 @@ def main():
         y[0, t] = x[0, t] + R * rng.normal()
     u_tr, y_tr, u_te, y_te = u[:, :T], y[:, :T], u[:, T:], y[:, T:]
 
-    basis, g = pg.KnownBasisVB(), pg.LinearMeasurement([[1.0, 0.0]])
+    which = sys.argv[4] if len(sys.argv) > 4 else "known"
+    g = pg.LinearMeasurement([[1.0, 0.0]])
+    if which == "generic":
+        basis = pg.HilbertGPBasis([5, 5, 5], [10.0, 20.0, 20.0])
+        n_phi = basis.n_phi
+        V = pg.hilbert_gp_prior_V([5, 5, 5], [10, 20, 20], 2 * np.pi * np.ones(3), 100 ** 2 / (8 * np.pi ** 4))
+    else:
+        basis, V = pg.KnownBasisVB(), 10 * np.ones(n_phi)
     K_total = K_b + 1 + (K - 1) * (k_d + 1)  # particle_Gibbs.jl:116
     t0 = time.perf_counter()
     samples = pg.particle_Gibbs(u_tr, y_tr, K, K_b, k_d, N, basis, 100 * np.eye(n_x), 10.0, 100 * np.eye(n_x),
-                                10 * np.ones(n_phi), np.zeros((n_x, n_phi)), pg.MvNormal([2.0, 2.0], 1.0), g, R, seed=82)
+                                V, np.zeros((n_x, n_phi)), pg.MvNormal([2.0, 2.0], 1.0), g, R, seed=82)
     t_pg = time.perf_counter() - t0
     t0 = time.perf_counter()
     tp = pg.test_prediction(samples, basis, g, R, 10, u_te, y_te, seed=83)
     t_tp = time.perf_counter() - t0
     print(json.dumps({
-        "example": "PG_OCP_known_basis_functions (paper Sec. V-B): N=30, T=2000, K=%d, K_b=%d, k_d=%d -> K_total=%d sweeps"
-                   % (K, K_b, k_d, K_total),
+        "example": "PG_OCP_%s_basis_functions (paper Sec. V-%s): N=30, T=2000, n_phi=%d, K=%d, K_b=%d, k_d=%d -> K_total=%d sweeps"
+                   % (which, "C" if which == "generic" else "B", n_phi, K, K_b, k_d, K_total),
         "particle_gibbs_seconds": t_pg, "pg_sweeps_per_s": K_total / t_pg,
         "test_prediction_seconds": t_tp, "test_prediction_simulations": K * 10, "T_test": T_test,
         "mean_rmse": tp["mean_rmse"], "std_of_y_test": float(np.std(y_te))}))

@@ -268,6 +268,41 @@ def test_small_n_kernel_bit_exact_injected_streams(model, first, N, T):
         assert stat == ref["status"] == 0 and nfb == 0 and nscan == 0  # no exact-scan machinery on this path
 
 
+@pytest.mark.parametrize("model", ["known", "hilbert"])
+@pytest.mark.parametrize("first", [False, True])
+@pytest.mark.parametrize("N,T", [(33, 40), (64, 30), (100, 60), (257, 25), (1000, 12), (1024, 10)])
+def test_mid_n_cta_kernel_bit_exact_injected_streams(model, first, N, T):
+    """The one-CTA-per-chain kernel (mode 3 for 32 < N <= 1024; thread = particle, block tree sums, sequential prefix
+    walked once into shared memory, binary search) against the oracle, bit for bit."""
+    basis, om, A = _models()[model]
+    u, y, _ = P.make_data(T, 14)
+    s = P.injected_streams(N, T, 2, basis.n_phi, 25)
+    st = O.make_streams(philox=False, **{kk: s[kk] for kk in ("Z0", "Ures", "Z", "Uanc", "Ustar")})
+    xp = np.zeros((2, T))
+    if not first:
+        xp = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, True, st, 1)["x_prim"]
+    k = 1 if first else 2
+    ref = O.sweep(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A, P.Q_TRUE, xp, first, st, k)
+    with _engine(basis, N, T, u, y, persistent=3) as e:
+        e.set_state(A, P.Q_TRUE, xp, k)
+        e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+        e.sweep_filter()
+        a, x, w = e.get_history()
+        Phi, Psi, Sig, star = e.get_stats()
+        _, _, xprim, _ = e.get_state()
+        smp = e.get_sample()
+        stat, nfb, nscan = e.status()
+    _assert_same("ancestors", a[1:], ref["a"][1:])
+    _assert_same("x_pf", x, ref["x"])
+    _assert_same("w", w, ref["w"])
+    assert star == ref["star"]
+    _assert_same("x_prim", xprim, ref["x_prim"])
+    _assert_same("Sigma", Sig, ref["Sigma"])
+    _assert_same("w_m1", smp.w_m1, ref["w_last"])
+    _assert_same("x_m1", smp.x_m1.T, ref["x_last"])
+    assert stat == ref["status"] == 0 and nfb == 0 and nscan == 0
+
+
 def test_small_n_kernel_matches_tile_kernel_on_whole_sampler():
     """particle_Gibbs at the reference's N = 30 through the automatic (warp-per-chain) path and through the tile
     persistent kernel: identical samples; both equal the oracle (Philox streams)."""
@@ -429,7 +464,8 @@ def test_mniw_bit_exact(model):
 
 
 @pytest.mark.parametrize("model,N,T,K,K_b,k_d", [("known", 30, 150, 4, 6, 2), ("hilbert", 30, 60, 3, 3, 1),
-                                                 ("known", 2500, 30, 3, 2, 1)])
+                                                 ("known", 2500, 30, 3, 2, 1), ("hilbert", 300, 25, 2, 2, 1),
+                                                 ("known", 1024, 20, 2, 1, 1)])
 def test_particle_gibbs_bit_exact_philox(model, N, T, K, K_b, k_d):
     """Whole sampler (particle_Gibbs.jl:114-237) with counter-based streams: every kept sample identical."""
     basis, om, _ = _models()[model]
