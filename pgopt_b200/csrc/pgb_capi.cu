@@ -632,7 +632,7 @@ static int run_filter_small_nx(pgb_handle* h, int64_t n_max) {
   if (fd.N > n_max || fd.N > CTA_MAXN || fd.x_rows != T) return -1;
   const bool cta = fd.N > SMALL_MAXN;  // mid-size N: one CTA per chain (k_sweep_cta), thread = particle
   const int np_thr = (int)((fd.N + 31) / 32) * 32;
-  const size_t smem = cta ? ((size_t)((NX * fd.n_phi + 1) & ~1) + (size_t)(NX + 2) * np_thr + 2) * 8 + sizeof(CtaShared)
+  const size_t smem = cta ? ((size_t)((NX * fd.n_phi + 1) & ~1) + (size_t)(NX + 4) * np_thr + 4) * 8 + sizeof(CtaShared)
                           : ((size_t)((NX * fd.n_phi + 1) & ~1) + (size_t)NX * 32 + 32) * 8;
   if (smem > 200 * 1024) return -1;
   int first = (h->sweep_index == 1);

@@ -356,6 +356,23 @@ __device__ __forceinline__ double cta_max(double v, CtaShared& cs, int W, int& f
   return p;
 }
 
+// q_n = q_{n-1} + W[n] (:28) for n = 0 .. Np-1 by the calling thread, strictly left to right; qs[n] = q_n, qs[Np] = q_Np
+// (= q_N: W[n] = 0 beyond N).  The weights are loaded eight at a time so that the loads do not wait for the stores.
+__device__ __forceinline__ void cta_prefix_walk(const double* __restrict__ Wv, double* __restrict__ qv, int Np) {
+  double q = 0.0;  // :23
+  for (int n = 0; n < Np; n += 8) {
+    double wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wv[j] = Wv[n + j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      qv[n + j] = q;
+      q = __dadd_rn(q, wv[j]);
+    }
+  }
+  qv[Np] = q;
+}
+
 // systematic_resampling(v, n_draw) (:17-34) for the CTA; thread i < n_draw receives idx[i].
 __device__ __forceinline__ SmallRes cta_resample(double v, int N, int n_draw, double rnd, double* Ws, double* qs,
                                                  CtaShared& cs, int W, int& flip) {
@@ -371,19 +388,7 @@ __device__ __forceinline__ SmallRes cta_resample(double v, int N, int n_draw, do
   const double inc = __ddiv_rn(1.0, (double)n_draw);
   double u = __dmul_rn(inc, rnd);                          // :21
   if (tid == 0) {
-    double q = 0.0;                                        // :23
-    const int Np = (int)blockDim.x;                        // multiple of 32; Ws[n] = 0 for n >= N, so q stays q_N there
-    for (int n = 0; n < Np; n += 8) {                      // :28, strictly left to right
-      double wv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) wv[j] = Ws[n + j];       // the loads do not wait for the stores of the chain
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        qs[n + j] = q;
-        q = __dadd_rn(q, wv[j]);
-      }
-    }
-    qs[Np] = q;                                            // = q_N (also qs[N] when N < Np)
+    cta_prefix_walk(Ws, qs, (int)blockDim.x);
   } else {
     const int nu = (tid < n_draw - 1) ? tid : n_draw - 1;  // :31, the increment taken tid times
     for (int j = 0; j < nu; ++j) u = __dadd_rn(u, inc);
@@ -404,6 +409,64 @@ __device__ __forceinline__ SmallRes cta_resample(double v, int N, int n_draw, do
   return r;
 }
 
+// The two resampling calls of a conditional step — a[t, 1:N-1] = systematic_resampling(w, N-1) (:172) and
+// a[t, N] = systematic_resampling(waN, 1)[1] (:181) — are independent of each other, so their sequential prefix walks
+// run concurrently: thread 0 walks the weights, thread 32 (another warp) the ancestor weights, everybody else builds
+// u_i meanwhile.  Thread i < n_draw receives idx[i] of the first call in .idx; *a_last = the index of the second call
+// (all threads).  Same arithmetic per call as cta_resample.
+__device__ __forceinline__ SmallRes cta_resample_pair(double v, int N, int n_draw, double rnd, double va, double rnda,
+                                                      int* a_last, double* Ws, double* qs, double* Ws2, double* qs2,
+                                                      CtaShared& cs, int W, int& flip) {
+  const int tid = threadIdx.x, Np = (int)blockDim.x;
+  SmallRes r;
+  r.status = 0;
+  const double S = cta_tree_sum(v, cs, W, flip);            // :19 (first call)
+  const double Sa = cta_tree_sum(va, cs, W, flip);          // :19 (second call)
+  const double Wn = (tid < N) ? __ddiv_rn(v, S) : 0.0;
+  const double Wa = (tid < N) ? __ddiv_rn(va, Sa) : 0.0;
+  if (tid < N && !(Wn >= 0.0 && Wn <= 1.7976931348623157e308)) r.status |= 4;
+  if (tid < N && !(Wa >= 0.0 && Wa <= 1.7976931348623157e308)) r.status |= 4;
+  __syncthreads();
+  Ws[tid] = Wn;
+  Ws2[tid] = Wa;
+  __syncthreads();
+  const double inc = __ddiv_rn(1.0, (double)n_draw);
+  double u = __dmul_rn(inc, rnd);                           // :21
+  if (tid == 0) cta_prefix_walk(Ws, qs, Np);
+  if (tid == 32) cta_prefix_walk(Ws2, qs2, Np);
+  if (tid != 0) {
+    const int nu = (tid < n_draw - 1) ? tid : n_draw - 1;   // :31, the increment taken tid times
+    for (int j = 0; j < nu; ++j) u = __dadd_rn(u, inc);
+  }
+  __syncthreads();
+  int lo = 0, hi = N;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (qs[mid] < u) lo = mid + 1;
+    else hi = mid;
+  }
+  if (tid < n_draw) {
+    if (lo == N && qs[N] < u) r.status |= 1;
+    if (lo == 0) r.status |= 2;
+  }
+  r.idx = lo;
+  if (tid == 0) {  // the single draw of the second call: u = (1/1) * rnda
+    const double ua = __dmul_rn(1.0, rnda);
+    int l2 = 0, h2 = N;
+    while (l2 < h2) {
+      const int mid = (l2 + h2) >> 1;
+      if (qs2[mid] < ua) l2 = mid + 1;
+      else h2 = mid;
+    }
+    if (l2 == N && qs2[N] < ua) r.status |= 1;
+    if (l2 == 0) r.status |= 2;
+    cs.bci[0] = l2;
+  }
+  __syncthreads();
+  *a_last = cs.bci[0];
+  return r;
+}
+
 template <int NX>
 __global__ void __launch_bounds__(CTA_MAXN, 1) k_sweep_cta(const __grid_constant__ FilterDev fd,
                                                            int32_t* __restrict__ star_idx, int first) {
@@ -414,7 +477,9 @@ __global__ void __launch_bounds__(CTA_MAXN, 1) k_sweep_cta(const __grid_constant
   double* Fs = A_sm + ((NX * fd.n_phi + 1) & ~1);             // [NX][Np]
   double* Ws = Fs + NX * Np;                                  // [Np]
   double* qs = Ws + Np;                                       // [Np + 2]
-  CtaShared& cs = *reinterpret_cast<CtaShared*>(qs + Np + 2);
+  double* Ws2 = qs + Np + 2;                                  // [Np]      the ancestor draw's weights / prefixes
+  double* qs2 = Ws2 + Np;                                     // [Np + 2]
+  CtaShared& cs = *reinterpret_cast<CtaShared*>(qs2 + Np + 2);
   const int chain = blockIdx.x;
   const int N = (int)fd.N;
   const int64_t T = fd.T;
@@ -538,6 +603,7 @@ __global__ void __launch_bounds__(CTA_MAXN, 1) k_sweep_cta(const __grid_constant
     for (int d = 0; d < NX; ++d) Fs[d * Np + tid] = F[d];
     // ---- ancestor of the conditioned trajectory (:178-181)
     int a_last = 0;
+    double wan = 0.0;  // waN ./ sum(waN) (:180)
     if (anc) {
       double r[NX], sq = 0.0;
 #pragma unroll
@@ -553,19 +619,14 @@ __global__ void __launch_bounds__(CTA_MAXN, 1) k_sweep_cta(const __grid_constant
       vexp_wide<1>(pa, pv);
       double wa = live ? __dmul_rn(w, pv[0]) : 0.0;
       const double S3 = cta_tree_sum(wa, cs, W, flip);      // :180
-      wa = live ? __ddiv_rn(wa, S3) : 0.0;
-      const SmallRes ra = cta_resample(wa, N, 1, ua, Ws, qs, cs, W, flip);   // :181
-      stat |= (ra.status & 4);
-      if (tid == 0) {
-        stat |= ra.status;
-        cs.bci[0] = ra.idx;
-      }
-      __syncthreads();
-      a_last = cs.bci[0];
+      wan = live ? __ddiv_rn(wa, S3) : 0.0;
     }
-    // ---- a[t, 1:n_draw] = systematic_resampling(w[t-1, :], n_draw) (:172 | :185)
+    // ---- a[t, 1:n_draw] = systematic_resampling(w[t-1, :], n_draw) (:172 | :185) and, for a conditional sweep,
+    //      a[t, N] = systematic_resampling(waN, 1)[1] (:181): independent draws, their prefix walks run concurrently
     const int n_draw = first ? N : N - 1;
-    const SmallRes rr = cta_resample(w, N, n_draw, ur, Ws, qs, cs, W, flip);
+    SmallRes rr;
+    if (anc) rr = cta_resample_pair(w, N, n_draw, ur, wan, ua, &a_last, Ws, qs, Ws2, qs2, cs, W, flip);
+    else rr = cta_resample(w, N, n_draw, ur, Ws, qs, cs, W, flip);
     stat |= rr.status;
     // ---- x_t = f(x_{t-1}[a]) + L z (:175 | :188)
     int32_t* at = fd.ah + ((int64_t)chain * T + t) * N;
