@@ -37,6 +37,50 @@ class PG_sample:
     u_m1: np.ndarray   # (n_u,)
 
 
+class PGSampleBatch:
+    """K posterior samples as stacked arrays — the same content as a Vector{PG_sample} (PGopt.jl:23-29), without one
+    Python object per sample: A (K, n_x, n_phi), Q (K, n_x, n_x), w_m1 (K, N), x_m1 (K, n_x, N), u_m1 (K, n_u).
+    `scenario_rollout` / `test_prediction` take it in place of the list and skip the per-sample packing (2 s of Python
+    at K = 10^5).  Indexing gives the PG_sample view of one entry."""
+
+    def __init__(self, A, Q, w_m1, x_m1, u_m1):
+        self.A, self.Q = np.asarray(A, dtype=np.float64), np.asarray(Q, dtype=np.float64)
+        self.w_m1, self.x_m1 = np.asarray(w_m1, dtype=np.float64), np.asarray(x_m1, dtype=np.float64)
+        self.u_m1 = np.asarray(u_m1, dtype=np.float64).reshape(self.A.shape[0], -1)
+        K = self.A.shape[0]
+        if not (self.Q.shape[0] == self.w_m1.shape[0] == self.x_m1.shape[0] == K):
+            raise ValueError("all arrays must have K entries along the first axis")
+
+    def __len__(self):
+        return self.A.shape[0]
+
+    def __getitem__(self, k):
+        return PG_sample(self.A[k], self.Q[k], self.w_m1[k], self.x_m1[k], self.u_m1[k])
+
+    @classmethod
+    def from_samples(cls, samples):
+        return cls(np.stack([s.A for s in samples]), np.stack([s.Q for s in samples]),
+                   np.stack([np.ravel(s.w_m1) for s in samples]), np.stack([s.x_m1 for s in samples]),
+                   np.stack([np.ravel(s.u_m1) for s in samples]))
+
+
+def _pack_samples(PG_samples):
+    """(A, Q, w, x, um, N) in the C ABI's layout: per scenario column-major A (n_x x n_phi), Q, x_m1 (n_x x N)."""
+    if isinstance(PG_samples, PGSampleBatch):
+        b = PG_samples
+        K = len(b)
+        A = np.ascontiguousarray(np.transpose(b.A, (0, 2, 1))).reshape(K, -1)
+        Q = np.ascontiguousarray(np.transpose(b.Q, (0, 2, 1))).reshape(K, -1)
+        x = np.ascontiguousarray(np.transpose(b.x_m1, (0, 2, 1))).reshape(K, -1)
+        return A, Q, np.ascontiguousarray(b.w_m1), x, np.ascontiguousarray(b.u_m1), b.w_m1.shape[1]
+    A = np.ascontiguousarray(np.stack([_f(s.A) for s in PG_samples]))
+    Q = np.ascontiguousarray(np.stack([_f(s.Q) for s in PG_samples]))
+    w = np.ascontiguousarray(np.stack([np.asarray(s.w_m1, dtype=np.float64).ravel() for s in PG_samples]))
+    x = np.ascontiguousarray(np.stack([_f(s.x_m1) for s in PG_samples]))
+    um = np.ascontiguousarray(np.stack([np.asarray(s.u_m1, dtype=np.float64).ravel() for s in PG_samples]))
+    return A, Q, w, x, um, PG_samples[0].w_m1.size
+
+
 class KnownBasisVB:
     """phi of Julia/examples/PG_OCP_known_basis_functions_Altro.jl:34 (n_x = 2, n_u = 1, n_phi = 5)."""
     n_x, n_u, n_phi = 2, 1, 5
@@ -364,7 +408,7 @@ def scenario_rollout(PG_samples, phi, g, R, H, u_init=None, seed=0, k_offset=0, 
     K = len(PG_samples)
     n_x, n_u, n_phi = b.n_x, b.n_u, b.n_phi
     n_y = gm.C.shape[0]
-    N = PG_samples[0].w_m1.size
+    A, Q, w, x, um, N = _pack_samples(PG_samples)
     if np.ndim(R) == 0:
         Le = np.array([[float(R)]])  # MvNormal(zeros(n_y), R::Real) reads R as a std (reference quirk, :79)
     else:
@@ -372,11 +416,6 @@ def scenario_rollout(PG_samples, phi, g, R, H, u_init=None, seed=0, k_offset=0, 
     if u_init is None:
         u_init = np.zeros((n_u, H))  # :110
     cfg = _make_cfg(b, n_y, N, 2, 1, device)
-    A = np.ascontiguousarray(np.stack([_f(s.A) for s in PG_samples]))
-    Q = np.ascontiguousarray(np.stack([_f(s.Q) for s in PG_samples]))
-    w = np.ascontiguousarray(np.stack([np.asarray(s.w_m1, dtype=np.float64).ravel() for s in PG_samples]))
-    x = np.ascontiguousarray(np.stack([_f(s.x_m1) for s in PG_samples]))
-    um = np.ascontiguousarray(np.stack([np.asarray(s.u_m1, dtype=np.float64).ravel() for s in PG_samples]))
     x0, v, e = np.empty((K, n_x)), np.empty((K, H, n_x)), np.empty((K, H, n_y))
     X, Y = np.empty((K, H + 1, n_x)), np.empty((K, H, n_y))
     check(lib().pgb_rollout(C.byref(cfg), C.c_int64(K), C.c_int64(H), _p(A), _p(Q), _p(w), _p(x), _p(um), _p(_f(gm.C)),
@@ -398,7 +437,7 @@ def test_prediction(PG_samples, phi, g, R, k_n, u_test, y_test, seed=0, device=0
     K = len(PG_samples)
     n_x, n_u = b.n_x, b.n_u
     n_y = gm.C.shape[0]
-    N = PG_samples[0].w_m1.size
+    A, Q, w, x, um, N = _pack_samples(PG_samples)
     u_test = np.atleast_2d(np.asarray(u_test, dtype=np.float64))
     y_test = np.atleast_2d(np.asarray(y_test, dtype=np.float64))
     T_test = y_test.shape[1]
@@ -407,11 +446,6 @@ def test_prediction(PG_samples, phi, g, R, k_n, u_test, y_test, seed=0, device=0
     else:
         Le = np.linalg.cholesky(np.atleast_2d(np.asarray(R, dtype=np.float64)))
     cfg = _make_cfg(b, n_y, N, 2, 1, device)
-    A = np.ascontiguousarray(np.stack([_f(s.A) for s in PG_samples]))
-    Q = np.ascontiguousarray(np.stack([_f(s.Q) for s in PG_samples]))
-    w = np.ascontiguousarray(np.stack([np.asarray(s.w_m1, dtype=np.float64).ravel() for s in PG_samples]))
-    x = np.ascontiguousarray(np.stack([_f(s.x_m1) for s in PG_samples]))
-    um = np.ascontiguousarray(np.stack([np.asarray(s.u_m1, dtype=np.float64).ravel() for s in PG_samples]))
     S = K * int(k_n)
     xs, ys = np.empty((S, T_test + 1, n_x)), np.empty((S, T_test, n_y))
     rmse = C.c_double(0.0)

@@ -33,9 +33,14 @@ def rollout(K=100000, H=41, N=30, cpu_K=300):
     from pgopt_b200._lib import lib
     tms, kms = C.c_double(0), C.c_double(0)
     lib().pgb_rollout_last_ms(C.byref(tms), C.byref(kms))
+    batch = pg.PGSampleBatch(A, Q, w, np.transpose(x, (0, 2, 1)), um)  # stacked arrays: no per-sample Python packing
+    t0 = time.perf_counter()
+    out_b = pg.scenario_rollout(batch, basis, pg.LinearMeasurement(Cm), 0.1, H, u_init=u_init, seed=1)
+    dt_batch = time.perf_counter() - t0
     a_bytes = K * n_x * n_phi * 8
     res = {"metric": "scenario rollout (host buffers in/out, incl. packing + H2D of A)", "K": K, "H": H, "n_x": n_x,
-           "n_phi": n_phi, "seconds": dt, "scenario_steps_per_s": K * H / dt, "kernel_ms": kms.value,
+           "n_phi": n_phi, "seconds": dt, "scenario_steps_per_s": K * H / dt, "seconds_with_PGSampleBatch": dt_batch,
+           "batch_equals_list": bool(np.array_equal(out_b["raw"]["X"], out["raw"]["X"])), "kernel_ms": kms.value,
            "alloc_h2d_ms": tms.value, "kernel_scenario_steps_per_s": K * H / (kms.value * 1e-3),
            "kernel_GBps_algorithmic": (a_bytes + K * (N + n_x + (2 * H + 2) * n_x + 2 * H) * 8) / (kms.value * 1e-3) / 1e9,
            "kernel_fp64_tflops": 2.0 * K * (H + 1) * n_x * n_phi / (kms.value * 1e-3) / 1e12}

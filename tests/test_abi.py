@@ -68,3 +68,22 @@ def test_no_cpu_fallback():
     with pytest.raises(pgopt_b200.PgoptError) as ei:
         pgopt_b200.ParticleGibbsEngine(pgopt_b200.KnownBasisVB(), 1, 30, 100)
     assert ei.value.code == _lib.PGB_ERR_CUDA
+
+
+def test_sample_batch_packs_like_the_sample_list():
+    """PGSampleBatch (stacked arrays) must hand the C ABI exactly the bytes the Vector{PG_sample} mirror does."""
+    from pgopt_b200.api import _pack_samples
+    rng = np.random.default_rng(0)
+    K, nx, nphi, N = 7, 3, 11, 5
+    A, Q = rng.normal(size=(K, nx, nphi)), rng.normal(size=(K, nx, nx))
+    w, x, um = rng.uniform(size=(K, N)), rng.normal(size=(K, nx, N)), rng.normal(size=(K, 2))
+    lst = [pgopt_b200.PG_sample(A[k], Q[k], w[k], x[k], um[k]) for k in range(K)]
+    ref = _pack_samples(lst)
+    for other in (_pack_samples(pgopt_b200.PGSampleBatch(A, Q, w, x, um)),
+                  _pack_samples(pgopt_b200.PGSampleBatch.from_samples(lst))):
+        for a, b in zip(ref[:5], other[:5]):
+            assert np.array_equal(np.ravel(a), np.ravel(b))
+        assert ref[5] == other[5]
+    b = pgopt_b200.PGSampleBatch(A, Q, w, x, um)
+    assert len(b) == K and np.array_equal(b[3].A, A[3]) and np.array_equal(b[3].x_m1, x[3])
+

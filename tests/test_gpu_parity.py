@@ -582,6 +582,10 @@ def test_rollout_bit_exact_shapes(n_x, n_y, dims, N, K, H, rollout_kernel):
     assert ref["status"] == 0
     for name in ("x0", "v", "e", "X", "Y"):
         _assert_same(name, out["raw"][name], ref[name])
+    batch = pg.PGSampleBatch(A, Q, w, np.transpose(x, (0, 2, 1)), um)  # stacked arrays instead of the sample list
+    out2 = pg.scenario_rollout(batch, basis, pg.LinearMeasurement(Cm), R, H, u_init=u_init, seed=23, k_offset=5)
+    for name in ("x0", "v", "e", "X", "Y"):
+        _assert_same(name + " (batch)", out2["raw"][name], ref[name])
 
 
 def test_rollout_many_scenarios_persistent_grid(rollout_kernel):
