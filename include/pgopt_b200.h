@@ -188,6 +188,14 @@ int pgb_test_prediction(const pgb_config* cfg, int64_t K, int64_t k_n, int64_t T
                         const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
                         const double* Le, const double* u_test, const double* y_test, uint64_t seed, double* x_sim,
                         double* y_sim, double* mean_rmse);
+/* Scenario screening of the greedy support-sub-sample search (Julia/src/optimal_control_Ipopt.jl:334-338,
+ * optimal_control_Altro.jl:496-500) for box output constraints, the h_scenario of every reference example
+ * (examples/PG_OCP_known_basis_functions_Ipopt.jl:198-214): h_max[k] = maximum over the finite bounds (n, t) of
+ * y_min[n,t] - y[n,t,k] and y[n,t,k] - y_max[n,t]; order (may be NULL) = sortperm(h_max; rev=true), 1-based.
+ * Y[K][H][n_y] as written by pgb_rollout; y_min / y_max [n_y*H] column-major, +-Inf = no bound.  All bounds
+ * infinite -> PGB_ERR_INVALID (Julia's maximum of an empty collection throws). */
+int pgb_scenario_constraint_max(int32_t device, int64_t K, int64_t H, int32_t n_y, const double* Y,
+                                const double* y_min, const double* y_max, double* h_max, int64_t* order);
 /* Device-side time (CUDA events, ms) of the last pgb_rollout / pgb_test_prediction call of this process: allocation + host-to-device copies
  * of the inputs, and the rollout kernel itself. */
 int pgb_rollout_last_ms(double* h2d_ms, double* kernel_ms);

@@ -15,7 +15,7 @@ using Distributions
 using Printf
 
 export PG_sample, KnownBasisVB, HilbertGPBasis, LinearMeasurement, particle_Gibbs, systematic_resampling,
-       MNIW_sample, scenario_rollout, test_prediction
+       MNIW_sample, scenario_rollout, test_prediction, scenario_constraint_max
 
 const LIB = get(ENV, "PGOPT_B200_LIB", "libpgopt_b200.so")
 const PGB_MAX_Z = 8
@@ -203,6 +203,25 @@ function test_prediction(PG_samples::Vector{PG_sample}, phi, g::LinearMeasuremen
                 cfg, K, k_n, T_test, A, Q, w, x, um, g.C, Le, ut, yt, seed, x_sim, y_sim, rmse))
     @printf("Mean rmse: %.2f\n", rmse[])
     return x_sim, y_sim, rmse[]
+end
+
+"""
+    scenario_constraint_max(y_opt, y_min, y_max)
+
+The scenario ordering of the greedy support-sub-sample search (Julia/src/optimal_control_Ipopt.jl:334-338,
+optimal_control_Altro.jl:496-500) for the examples' box output constraints: returns
+(h_scenario_max::Vector{Float64}, scenarios_sorted::Vector{Int}) with `scenarios_sorted = sortperm(h_scenario_max; rev=true)`.
+`y_opt` is (n_y, H, K); `y_min` / `y_max` are (n_y, H) with +-Inf where there is no bound.
+"""
+function scenario_constraint_max(y_opt::Array{Float64,3}, y_min, y_max; device=0)
+    n_y, H, K = size(y_opt)
+    lo = Matrix{Float64}(y_min); hi = Matrix{Float64}(y_max)
+    h_max = Vector{Float64}(undef, K); order = Vector{Int64}(undef, K)
+    # column-major (n_y, H, K) is exactly the scenario-major K x H x n_y layout of the C ABI
+    check(ccall((:pgb_scenario_constraint_max, LIB), Cint,
+                (Int32, Int64, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                device, K, H, n_y, y_opt, lo, hi, h_max, order))
+    return h_max, order
 end
 
 end # module

@@ -664,3 +664,38 @@ static int rollout_impl(const orc_model* m, int64_t K, int64_t n_models, int64_t
   free(x0_own); free(v_own); free(e_own);
   return status;
 }
+
+/* ---- scenario screening (optimal_control_Ipopt.jl:334-338; h_scenario of the examples, ..._Ipopt.jl:198-214) ---------- */
+/* Julia's isless on Float64: NaN is the largest value, -0.0 sorts before 0.0. */
+static int orc_isless(double a, double b) {
+  if (isnan(a)) return 0;
+  if (isnan(b)) return 1;
+  if (a == 0.0 && b == 0.0) return signbit(a) && !signbit(b);
+  return a < b;
+}
+
+int orc_scenario_constraint_max(int64_t K, int64_t H, int32_t n_y, const double* Y, const double* y_min,
+                                const double* y_max, double* h_max, int64_t* order) {
+  int64_t n_fin = 0;
+  for (int64_t i = 0; i < (int64_t)n_y * H; ++i) n_fin += (isfinite(y_min[i]) != 0) + (isfinite(y_max[i]) != 0);
+  if (n_fin == 0) return 1;
+  for (int64_t k = 0; k < K; ++k) {
+    double m = -INFINITY;
+    int nan = 0;
+    for (int64_t t = 0; t < H; ++t)      /* loop order of h_scenario: t outer, n inner, min before max */
+      for (int32_t n = 0; n < n_y; ++n) {
+        double y = Y[(k * H + t) * n_y + n];
+        if (isfinite(y_min[n + (int64_t)n_y * t])) { double h = y_min[n + (int64_t)n_y * t] - y; if (isnan(h)) nan = 1; else if (h > m || (h == m && !signbit(h))) m = h; }
+        if (isfinite(y_max[n + (int64_t)n_y * t])) { double h = y - y_max[n + (int64_t)n_y * t]; if (isnan(h)) nan = 1; else if (h > m || (h == m && !signbit(h))) m = h; }
+      }
+    h_max[k] = nan ? NAN : m;
+  }
+  if (order) { /* stable insertion of each element: sortperm(...; rev=true) keeps ties in their original order */
+    for (int64_t k = 0; k < K; ++k) {
+      int64_t j = k;
+      while (j > 0 && orc_isless(h_max[order[j - 1] - 1], h_max[k])) { order[j] = order[j - 1]; --j; }
+      order[j] = k + 1;
+    }
+  }
+  return 0;
+}

@@ -120,6 +120,14 @@ int orc_test_prediction(const orc_model* m, int64_t K, int64_t k_n, int64_t T_te
                         const double* Le, const double* u_test /*n_u x T_test*/, const double* y_test /*n_y x T_test*/,
                         uint64_t seed, double* x_sim, double* y_sim, double* mean_rmse);
 
+/* Scenario screening of the greedy support-sub-sample search (optimal_control_Ipopt.jl:334-338, Altro.jl:496-500) for the
+ * examples' box output constraints (examples/PG_OCP_known_basis_functions_Ipopt.jl:198-214): h_max[k] = maximum over the
+ * finite entries (n, t) of y_min[n,t] - y[n,t,k] and y[n,t,k] - y_max[n,t] (NaN propagates like Julia's maximum), then
+ * order = sortperm(h_max; rev=true) (stable, isless ordering), 1-based.  Y is scenario-major K x H x n_y; y_min / y_max
+ * are n_y x H column-major.  Returns 1 when no bound is finite (maximum of an empty collection throws in Julia). */
+int orc_scenario_constraint_max(int64_t K, int64_t H, int32_t n_y, const double* Y, const double* y_min,
+                                const double* y_max, double* h_max, int64_t* order);
+
 #ifdef __cplusplus
 }
 #endif

@@ -455,3 +455,30 @@ def test_prediction(PG_samples, phi, g, R, k_n, u_test, y_test, seed=0, device=0
     return dict(x_test_sim=np.transpose(xs, (2, 1, 0)), y_test_sim=np.transpose(ys, (2, 1, 0)),
                 mean_rmse=rmse.value, raw=dict(x_sim=xs, y_sim=ys))
 
+
+def scenario_constraint_max(y, y_min, y_max, device=0):
+    """The scenario ordering of the greedy support-sub-sample search (Julia/src/optimal_control_Ipopt.jl:334-338,
+    optimal_control_Altro.jl:496-500) for the examples' box output constraints
+    (examples/PG_OCP_known_basis_functions_Ipopt.jl:198-214): `y` is y_opt (n_y, H, K) — or the scenario-major
+    (K, H, n_y) array `scenario_rollout(...)["raw"]["Y"]` when `y_min` has shape (n_y, H) and y.shape[0] != n_y.
+    Returns (h_scenario_max (K,), scenarios_sorted (K,) 1-based = sortperm(h_scenario_max; rev=true))."""
+    y_min = np.atleast_2d(np.asarray(y_min, dtype=np.float64))
+    y_max = np.atleast_2d(np.asarray(y_max, dtype=np.float64))
+    n_y, H = y_min.shape
+    if y_max.shape != (n_y, H):
+        raise ValueError("y_min and y_max must both be (n_y, H)")
+    y = np.asarray(y, dtype=np.float64)
+    if y.ndim != 3:
+        raise ValueError("y must be (n_y, H, K) or (K, H, n_y)")
+    if y.shape[:2] == (n_y, H):
+        Y = np.ascontiguousarray(np.transpose(y, (2, 1, 0)))
+    elif y.shape[1:] == (H, n_y):
+        Y = np.ascontiguousarray(y)
+    else:
+        raise ValueError("y %s does not match bounds (n_y=%d, H=%d)" % (y.shape, n_y, H))
+    K = Y.shape[0]
+    h = np.empty(K)
+    order = np.empty(K, dtype=np.int64)
+    check(lib().pgb_scenario_constraint_max(C.c_int32(device), C.c_int64(K), C.c_int64(H), C.c_int32(n_y), _p(Y),
+                                            _p(_f(y_min)), _p(_f(y_max)), _p(h), _p(order)))
+    return h, order

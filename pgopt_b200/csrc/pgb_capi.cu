@@ -3,6 +3,7 @@
 // computes needs a CUDA device and fails with PGB_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1164,6 +1165,89 @@ extern "C" int pgb_test_prediction(const pgb_config* cfg, int64_t K, int64_t k_n
 extern "C" int pgb_rollout_last_ms(double* h2d_ms, double* kernel_ms) {
   if (h2d_ms) *h2d_ms = g_rollout_ms[0];
   if (kernel_ms) *kernel_ms = g_rollout_ms[1];
+  return PGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scenario screening for the greedy support-sub-sample search (optimal_control_Ipopt.jl:334-338, Altro.jl:496-500)
+// ------------------------------------------------------------------------------------------------
+// One warp per scenario, grid-stride: the scenario's H*n_y outputs are contiguous (coalesced 256 B per warp request);
+// the bounds (n_y x H column-major = the same element index) stay in L1.  HBM-bound: 8 B read per output value.
+__device__ __forceinline__ double hmax_take(double m, double h) {
+  return (h > m || (h == m && !signbit(h))) ? h : m;  // Julia's max on non-NaN values (0.0 above -0.0)
+}
+__global__ void __launch_bounds__(256) k_scenario_constraint_max(int64_t K, int64_t E, const double* __restrict__ Y,
+                                                                 const double* __restrict__ lo,
+                                                                 const double* __restrict__ hi,
+                                                                 double* __restrict__ h_max) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < K; k += nwarp) {
+    const double* y = Y + k * E;
+    double m = -INFINITY;
+    int nan = 0;
+    for (int64_t e = lane; e < E; e += 32) {
+      const double v = y[e], a = __ldg(lo + e), b = __ldg(hi + e);
+      if (isfinite(a)) { const double h = a - v; if (isnan(h)) nan = 1; else m = hmax_take(m, h); }
+      if (isfinite(b)) { const double h = v - b; if (isnan(h)) nan = 1; else m = hmax_take(m, h); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      m = hmax_take(m, __shfl_xor_sync(0xffffffffu, m, o));
+      nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+    }
+    if (lane == 0) h_max[k] = nan ? __longlong_as_double(0x7ff8000000000000ll) : m;
+  }
+}
+
+static inline bool jl_isless(double a, double b) {  // Julia's isless on Float64
+  if (std::isnan(a)) return false;
+  if (std::isnan(b)) return true;
+  if (a == 0.0 && b == 0.0) return std::signbit(a) && !std::signbit(b);
+  return a < b;
+}
+
+extern "C" int pgb_scenario_constraint_max(int32_t device, int64_t K, int64_t H, int32_t n_y, const double* Y,
+                                           const double* y_min, const double* y_max, double* h_max, int64_t* order) {
+  if (!Y || !y_min || !y_max || !h_max || K < 1 || H < 1 || n_y < 1)
+    return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
+  const int64_t E = H * (int64_t)n_y;
+  int64_t n_fin = 0;
+  for (int64_t i = 0; i < E; ++i) n_fin += (std::isfinite(y_min[i]) ? 1 : 0) + (std::isfinite(y_max[i]) ? 1 : 0);
+  if (n_fin == 0)  // Julia: maximum of an empty collection throws (optimal_control_Ipopt.jl:336)
+    return set_err(nullptr, PGB_ERR_INVALID, "ArgumentError: no finite output bound: maximum over an empty collection");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s); pgopt_b200 has no CPU fallback",
+                   cudaGetErrorString(e));
+  pgb_handle tmp;  // only used as an allocation list / error sink
+  pgb_handle* h = &tmp;
+  h->cfg.device = device;
+  struct Cleanup {
+    pgb_handle* h;
+    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
+  } cleanup{h};
+  CK(h, cudaSetDevice(device));
+  double *d_Y = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_h = nullptr;
+  CK(h, dalloc(h, &d_Y, (size_t)(K * E)));
+  CK(h, dalloc(h, &d_lo, (size_t)E));
+  CK(h, dalloc(h, &d_hi, (size_t)E));
+  CK(h, dalloc(h, &d_h, (size_t)K));
+  CK(h, cudaMemcpy(d_Y, Y, (size_t)(K * E) * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(d_lo, y_min, (size_t)E * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaMemcpy(d_hi, y_max, (size_t)E * 8, cudaMemcpyHostToDevice));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int64_t want = (K + 7) / 8;  // 8 warps (scenarios) per CTA
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 8);
+  k_scenario_constraint_max<<<grid, 256>>>(K, E, d_Y, d_lo, d_hi, d_h);
+  CK(h, cudaGetLastError());
+  CK(h, cudaMemcpy(h_max, d_h, (size_t)K * 8, cudaMemcpyDeviceToHost));
+  if (order) {  // sortperm(h_scenario_max; rev=true): stable, ties keep their original order; 1-based
+    for (int64_t k = 0; k < K; ++k) order[k] = k + 1;
+    std::stable_sort(order, order + K, [&](int64_t a, int64_t b) { return jl_isless(h_max[b - 1], h_max[a - 1]); });
+  }
   return PGB_OK;
 }
 

@@ -194,3 +194,15 @@ def test_prediction(model, K, k_n, T_test, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_
                                    C.c_uint64(seed), _p(xs), _p(ys), C.byref(rmse))
     return dict(status=st, x_sim=xs, y_sim=ys, mean_rmse=rmse.value)
 
+
+
+def scenario_constraint_max(Y, y_min, y_max):
+    """orc_scenario_constraint_max: Y (K, H, n_y) scenario-major; y_min / y_max (n_y, H).  Returns h_max (K,), order (K,) 1-based."""
+    Y = f64(Y)
+    K, H, n_y = Y.shape
+    fl = lambda v: f64(np.asfortranarray(np.atleast_2d(v)).ravel(order="F"))
+    h = np.zeros(K)
+    order = np.zeros(K, dtype=np.int64)
+    st = lib().orc_scenario_constraint_max(C.c_int64(K), C.c_int64(H), C.c_int32(n_y), _p(Y), _p(fl(y_min)), _p(fl(y_max)),
+                                           _p(h), _p(order))
+    return dict(status=st, h_max=h, order=order)

@@ -801,3 +801,47 @@ def test_rollout_shards_reproduce_the_unsharded_rollout():
             cat = np.concatenate([p[name] for p in parts], axis=0)
             _assert_same("%s world=%d" % (name, world), cat, full[name])
             _assert_same("%s vs oracle" % name, cat, ref[name])
+
+
+# ---- scenario screening of the greedy support search (optimal_control_Ipopt.jl:334-338) ------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,H,n_y,ties", [(1, 7, 1, False), (200, 41, 1, False), (333, 41, 2, True), (5000, 100, 3, True),
+                                          (3, 1, 1, False)])
+def test_scenario_constraint_max_bit_exact(K, H, n_y, ties):
+    from test_oracle_kat import scenario_screening_case
+    y, y_min, y_max = scenario_screening_case(K, H, n_y, seed=K + H, ties=ties)
+    if H == 1:
+        y_max[0, 0] = 0.5
+    ref = O.scenario_constraint_max(np.transpose(y, (2, 1, 0)), y_min, y_max)
+    h, order = pg.scenario_constraint_max(y, y_min, y_max)  # reference layout (n_y, H, K)
+    assert np.array_equal(h, ref["h_max"]) and np.array_equal(order, ref["order"])
+    h2, order2 = pg.scenario_constraint_max(np.transpose(y, (2, 1, 0)), y_min, y_max)  # rollout layout (K, H, n_y)
+    assert np.array_equal(h2, h) and np.array_equal(order2, order)
+
+
+@pytest.mark.gpu
+def test_scenario_constraint_max_nan_and_errors():
+    from test_oracle_kat import scenario_screening_case
+    y, y_min, y_max = scenario_screening_case(64, 41, 1, seed=9)
+    y[0, 22, 5] = np.nan  # inside the bounded window: maximum() propagates NaN, sortperm(rev=true) puts it first
+    y[0, 0, 6] = np.nan   # outside every finite bound: not evaluated
+    ref = O.scenario_constraint_max(np.transpose(y, (2, 1, 0)), y_min, y_max)
+    h, order = pg.scenario_constraint_max(y, y_min, y_max)
+    assert np.isnan(h[5]) and not np.isnan(h[6]) and order[0] == 6
+    assert np.array_equal(h, ref["h_max"], equal_nan=True) and np.array_equal(order, ref["order"])
+    with pytest.raises(pg.PgoptError):
+        pg.scenario_constraint_max(y, np.full((1, 41), -np.inf), np.full((1, 41), np.inf))
+
+
+@pytest.mark.gpu
+def test_scenario_constraint_max_full_size_properties():
+    """configs[4] size (K = 1e5, H = 41): sortedness, permutation, and equality with a vectorised NumPy maximum."""
+    K, H = 100000, 41
+    rng = np.random.default_rng(3)
+    Y = rng.normal(size=(K, H, 1)) * 3
+    y_min = np.full((1, H), -np.inf); y_min[0, 20:26] = 2.0
+    y_max = np.full((1, H), np.inf); y_max[0, 30:] = 6.0
+    h, order = pg.scenario_constraint_max(Y, y_min, y_max)
+    expect = np.maximum((2.0 - Y[:, 20:26, 0]).max(axis=1), (Y[:, 30:, 0] - 6.0).max(axis=1))
+    assert np.array_equal(h, expect)
+    assert np.array_equal(np.sort(order), np.arange(1, K + 1)) and np.all(np.diff(h[order - 1]) <= 0)

@@ -266,3 +266,50 @@ def test_rollout_follows_reference_array_code():
             np.testing.assert_allclose(ref["Y"][k, t], Cm @ X[t] + ref["e"][k, t], rtol=1e-11, atol=1e-13)
         np.testing.assert_allclose(ref["X"][k], X, rtol=1e-9, atol=1e-11)
 
+
+
+def _ref_h_scenario_max(y, y_min, y_max):
+    """NumPy transcription of optimal_control_Ipopt.jl:334-338 with the examples' h_scenario
+    (examples/PG_OCP_known_basis_functions_Ipopt.jl:198-214); y is y_opt (n_y, H, K)."""
+    n_y, H, K = y.shape
+    h_max = np.empty(K)
+    for k in range(K):
+        h = []
+        for t in range(H):
+            for n in range(n_y):
+                if np.isfinite(y_min[n, t]):
+                    h.append(y_min[n, t] - y[n, t, k])
+                if np.isfinite(y_max[n, t]):
+                    h.append(y[n, t, k] - y_max[n, t])
+        h_max[k] = np.max(h)
+    order = np.argsort(-h_max, kind="stable") + 1  # sortperm(h_scenario_max; rev=true)
+    return h_max, order
+
+
+def scenario_screening_case(K, H, n_y, seed, ties=False):
+    rng = np.random.default_rng(seed)
+    y = rng.normal(size=(n_y, H, K)) * 3
+    y_min = np.full((n_y, H), -np.inf)
+    y_max = np.full((n_y, H), np.inf)
+    y_min[0, H // 2:H // 2 + 6] = 2.0  # the known-basis example: y >= 2 for six steps (..._Ipopt.jl:173-174)
+    if n_y > 1:
+        y_max[1, ::3] = rng.normal(size=y_max[1, ::3].shape)
+    if ties:  # repeated scenarios -> equal maxima, sortperm must keep them in their original order
+        y[:, :, K // 2:] = y[:, :, :K - K // 2]
+    return y, y_min, y_max
+
+
+@pytest.mark.parametrize("K,H,n_y,ties", [(1, 7, 1, False), (200, 41, 1, False), (333, 41, 2, True), (50, 100, 3, True)])
+def test_scenario_constraint_max_follows_reference(K, H, n_y, ties):
+    y, y_min, y_max = scenario_screening_case(K, H, n_y, seed=K + H, ties=ties)
+    ref_h, ref_order = _ref_h_scenario_max(y, y_min, y_max)
+    out = O.scenario_constraint_max(np.transpose(y, (2, 1, 0)), y_min, y_max)
+    assert out["status"] == 0
+    assert np.array_equal(out["h_max"], ref_h) and np.array_equal(out["order"], ref_order)
+    assert np.all(np.diff(out["h_max"][out["order"] - 1]) <= 0)  # sorted, largest first
+
+
+def test_scenario_constraint_max_no_finite_bound():
+    y = np.zeros((3, 5, 1))
+    out = O.scenario_constraint_max(y, np.full((1, 5), -np.inf), np.full((1, 5), np.inf))
+    assert out["status"] == 1  # Julia: maximum over an empty collection throws
