@@ -196,6 +196,8 @@ int pgb_test_prediction(const pgb_config* cfg, int64_t K, int64_t k_n, int64_t T
  * infinite -> PGB_ERR_INVALID (Julia's maximum of an empty collection throws). */
 int pgb_scenario_constraint_max(int32_t device, int64_t K, int64_t H, int32_t n_y, const double* Y,
                                 const double* y_min, const double* y_max, double* h_max, int64_t* order);
+/* Device-side time (CUDA events, ms) of the last pgb_scenario_constraint_max call of this process: H2D copies, kernel. */
+int pgb_scenario_constraint_last_ms(double* h2d_ms, double* kernel_ms);
 /* Device-side time (CUDA events, ms) of the last pgb_rollout / pgb_test_prediction call of this process: allocation + host-to-device copies
  * of the inputs, and the rollout kernel itself. */
 int pgb_rollout_last_ms(double* h2d_ms, double* kernel_ms);

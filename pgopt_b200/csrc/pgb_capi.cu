@@ -1176,29 +1176,51 @@ extern "C" int pgb_rollout_last_ms(double* h2d_ms, double* kernel_ms) {
 __device__ __forceinline__ double hmax_take(double m, double h) {
   return (h > m || (h == m && !signbit(h))) ? h : m;  // Julia's max on non-NaN values (0.0 above -0.0)
 }
+constexpr int SCREEN_U = 4;  // scenarios per warp iteration: independent loads in flight (the kernel is latency-bound otherwise)
 __global__ void __launch_bounds__(256) k_scenario_constraint_max(int64_t K, int64_t E, const double* __restrict__ Y,
                                                                  const double* __restrict__ lo,
                                                                  const double* __restrict__ hi,
                                                                  double* __restrict__ h_max) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t k = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < K; k += nwarp) {
-    const double* y = Y + k * E;
-    double m = -INFINITY;
-    int nan = 0;
+  for (int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SCREEN_U; k0 < K;
+       k0 += nwarp * SCREEN_U) {
+    const double* y[SCREEN_U];
+    double m[SCREEN_U];
+    int nan[SCREEN_U];
+#pragma unroll
+    for (int u = 0; u < SCREEN_U; ++u) {
+      y[u] = Y + (k0 + u < K ? k0 + u : K - 1) * E;  // tail: re-read the last scenario, never written
+      m[u] = -INFINITY;
+      nan[u] = 0;
+    }
+#pragma unroll 2
     for (int64_t e = lane; e < E; e += 32) {
-      const double v = y[e], a = __ldg(lo + e), b = __ldg(hi + e);
-      if (isfinite(a)) { const double h = a - v; if (isnan(h)) nan = 1; else m = hmax_take(m, h); }
-      if (isfinite(b)) { const double h = v - b; if (isnan(h)) nan = 1; else m = hmax_take(m, h); }
+      const double a = __ldg(lo + e), b = __ldg(hi + e);
+      double v[SCREEN_U];
+#pragma unroll
+      for (int u = 0; u < SCREEN_U; ++u) v[u] = y[u][e];
+#pragma unroll
+      for (int u = 0; u < SCREEN_U; ++u) {
+        if (isfinite(a)) { const double h = a - v[u]; if (isnan(h)) nan[u] = 1; else m[u] = hmax_take(m[u], h); }
+        if (isfinite(b)) { const double h = v[u] - b; if (isnan(h)) nan[u] = 1; else m[u] = hmax_take(m[u], h); }
+      }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
-      m = hmax_take(m, __shfl_xor_sync(0xffffffffu, m, o));
-      nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+#pragma unroll
+      for (int u = 0; u < SCREEN_U; ++u) {
+        m[u] = hmax_take(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
+        nan[u] |= __shfl_xor_sync(0xffffffffu, nan[u], o);
+      }
     }
-    if (lane == 0) h_max[k] = nan ? __longlong_as_double(0x7ff8000000000000ll) : m;
+#pragma unroll
+    for (int u = 0; u < SCREEN_U; ++u)
+      if (lane == u && k0 + u < K) h_max[k0 + u] = nan[u] ? __longlong_as_double(0x7ff8000000000000ll) : m[u];
   }
 }
+
+static float g_screen_ms[2] = {0.f, 0.f};  // device time of the last pgb_scenario_constraint_max: {H2D copies, kernel}
 
 static inline bool jl_isless(double a, double b) {  // Julia's isless on Float64
   if (std::isnan(a)) return false;
@@ -1234,20 +1256,38 @@ extern "C" int pgb_scenario_constraint_max(int32_t device, int64_t K, int64_t H,
   CK(h, dalloc(h, &d_lo, (size_t)E));
   CK(h, dalloc(h, &d_hi, (size_t)E));
   CK(h, dalloc(h, &d_h, (size_t)K));
+  cudaEvent_t ev[3];
+  for (auto& v : ev) CK(h, cudaEventCreate(&v));
+  struct EvCleanup {
+    cudaEvent_t* ev;
+    ~EvCleanup() { for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]); }
+  } ev_cleanup{ev};
+  CK(h, cudaEventRecord(ev[0], 0));
   CK(h, cudaMemcpy(d_Y, Y, (size_t)(K * E) * 8, cudaMemcpyHostToDevice));
   CK(h, cudaMemcpy(d_lo, y_min, (size_t)E * 8, cudaMemcpyHostToDevice));
   CK(h, cudaMemcpy(d_hi, y_max, (size_t)E * 8, cudaMemcpyHostToDevice));
+  CK(h, cudaEventRecord(ev[1], 0));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int64_t want = (K + 7) / 8;  // 8 warps (scenarios) per CTA
+  const int64_t want = (K + 8 * SCREEN_U - 1) / (8 * SCREEN_U);  // 8 warps x SCREEN_U scenarios per CTA iteration
   const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 8);
   k_scenario_constraint_max<<<grid, 256>>>(K, E, d_Y, d_lo, d_hi, d_h);
   CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(ev[2], 0));
+  CK(h, cudaEventSynchronize(ev[2]));
+  cudaEventElapsedTime(&g_screen_ms[0], ev[0], ev[1]);
+  cudaEventElapsedTime(&g_screen_ms[1], ev[1], ev[2]);
   CK(h, cudaMemcpy(h_max, d_h, (size_t)K * 8, cudaMemcpyDeviceToHost));
   if (order) {  // sortperm(h_scenario_max; rev=true): stable, ties keep their original order; 1-based
     for (int64_t k = 0; k < K; ++k) order[k] = k + 1;
     std::stable_sort(order, order + K, [&](int64_t a, int64_t b) { return jl_isless(h_max[b - 1], h_max[a - 1]); });
   }
+  return PGB_OK;
+}
+
+extern "C" int pgb_scenario_constraint_last_ms(double* h2d_ms, double* kernel_ms) {
+  if (h2d_ms) *h2d_ms = g_screen_ms[0];
+  if (kernel_ms) *kernel_ms = g_screen_ms[1];
   return PGB_OK;
 }
 
