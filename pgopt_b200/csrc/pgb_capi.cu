@@ -1197,6 +1197,7 @@ __global__ void __launch_bounds__(256) k_scenario_constraint_max(int64_t K, int6
 #pragma unroll 2
     for (int64_t e = lane; e < E; e += 32) {
       const double a = __ldg(lo + e), b = __ldg(hi + e);
+      if (!isfinite(a) && !isfinite(b)) continue;  // column without a bound: its outputs are never read
       double v[SCREEN_U];
 #pragma unroll
       for (int u = 0; u < SCREEN_U; ++u) v[u] = y[u][e];
