@@ -224,11 +224,6 @@ def run_gpu(args):
             if launches[i]}
     tot_prof = sum(v["ms"] for v in prof.values()) or 1.0
     dom = max(prof, key=lambda k: prof[k]["ms"])
-    cyc = (C.c_double * 16)()
-    ncta = C.c_int32(0)
-    check(lib().pgb_get_phase_cycles(eng._h, cyc, C.byref(ncta)), eng._h)
-    tot_cyc = sum(cyc) or 1.0
-    phases = {PHASE_NAMES[i]: round(100 * cyc[i] / tot_cyc, 1) for i in range(len(PHASE_NAMES)) if cyc[i]}
     fp64_peak = C.c_double(0)
     check(lib().pgb_test_fp64_peak(local, C.byref(fp64_peak)))
 
@@ -313,8 +308,6 @@ def run_gpu(args):
                          "note": "measured: the path is instruction-/latency-bound in FP64 (divisions, exp/log/sin/cos, Philox, "
                                  "exact-scan integer algebra) with DRAM ~5% busy; see DESIGN.md section 5 and profiles/"},
             "kernel_profile_ms_per_sweep": prof,
-            "persistent_kernel_phase_share_pct": phases,
-            "persistent_ctas": int(ncta.value),
             "resampling": {"status_bits": st, "exact_scans": nscan, "serial_fallbacks": nfb},
         }
         if cpu:

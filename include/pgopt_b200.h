@@ -141,16 +141,12 @@ int pgb_synchronize(pgb_handle* h);
 enum { PGB_PROF_PREP = 0, PGB_PROF_NORM, PGB_PROF_SCAN_LOCAL, PGB_PROF_RESOLVE, PGB_PROF_EXPAND, PGB_PROF_SEQ,
        PGB_PROF_EXPAND_FB, PGB_PROF_WEIGHTS, PGB_PROF_INIT, PGB_PROF_TAIL, PGB_PROF_MNIW, PGB_PROF_NCLASS };
 /* Filter kernel of a sweep.  -1 (default): automatic - when the particle history is stored, the warp-per-chain kernel
- * for N <= 32 (the reference's examples run N = 30) and the one-CTA-per-chain kernel for N <= 1024; otherwise mode 1.
- * 1: the whole T loop as one cooperative persistent kernel with 1024-particle CTA tiles; 2: the same in the warp-tile
- * formulation; 0: one launch per phase (13 launches per time step); 3: the warp / one-CTA-per-chain kernels (falls
- * back to 1 when N > 1024 or the history is replayed).  The alternatives are kept for profiling and as
- * cross-checks; all of them are bit-identical. */
+ * for N <= 32 (the reference's examples run N = 30) and the one-CTA-per-chain kernel for N <= 1024; otherwise mode 4.
+ * 4: the chunk-stationary sweep kernel (one cooperative launch per sweep, pgb_v2.cuh); 1: the 1024-particle tile
+ * persistent kernel of round 1 (cross-check); 0: one launch per phase (13 launches per time step, per-kernel
+ * profiling); 3: the warp / one-CTA-per-chain kernels (fall back to 1 when N > 1024 or the history is replayed).
+ * All of them are bit-identical. */
 int pgb_set_mode(pgb_handle* h, int32_t persistent);
-/* average over CTAs of the SM-clock cycles thread 0 spent in each section of the last persistent sweep
- * (section ids documented in pgb_persist.cuh: 1 phase A, 2 wait B1, 3 scan-local main, 4 normalise side, 5 wait B2,
- * 6 resolve, 7 prefixes+expansion, 8 scan-local side, 9 wait B3, 10 side resolve+index, 11 weights, 12 wait B4, 13 fix-up test) */
-int pgb_get_phase_cycles(pgb_handle* h, double* avg_cycles /*[16]*/, int32_t* n_ctas);
 int pgb_timer_start(pgb_handle* h);
 int pgb_timer_stop(pgb_handle* h, double* elapsed_ms);
 int pgb_profile(pgb_handle* h, int32_t on);
@@ -182,8 +178,10 @@ int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, co
  * scenario s = k + K*kn (the order of the reference's reshape at :301-302) with Philox stream (seed, chain = s).
  * Inputs as for pgb_rollout (A, Q, w_m1, x_m1, u_m1 hold K entries), u_test[n_u*T_test], y_test[n_y*T_test].
  * Outputs (host; x_sim / y_sim may be NULL): x_sim[K*k_n][T_test+1][n_x] (the reference leaves its last column
- * undefined, :278; here it holds one more transition), y_sim[K*k_n][T_test][n_y], *mean_rmse = the value printed at
- * :311-312, its sum of squares reduced on the device in the oracle's tree order. */
+ * undefined, :278; here it holds one more transition), y_sim[K*k_n][T_test][n_y], *mean_rmse = the time-matched RMSE
+ * sqrt(mean((y_sim[:, t, s] - y_test[:, t])^2)), its sum of squares reduced on the device in the oracle's tree order.
+ * Stated deviation: the Julia line :311 subtracts repeat(y_test', 1, 1, K*k_n) (shape T_test x n_y x S), which for
+ * n_y = 1 broadcasts to T_test x T_test cross terms and for n_y > 1 throws; the MATLAB twin matches in time. */
 int pgb_test_prediction(const pgb_config* cfg, int64_t K, int64_t k_n, int64_t T_test, const double* A,
                         const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
                         const double* Le, const double* u_test, const double* y_test, uint64_t seed, double* x_sim,
@@ -211,8 +209,8 @@ void pgb_test_force_fallback(int32_t on);
 int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_t n);
 /* DFMA micro-benchmark (8 independent chains per thread, all SMs): measured FP64 FMA rate of the device. */
 int pgb_test_fp64_peak(int32_t device, double* tflops);
-/* one elementwise phase in isolation inside a persistent loop with grid barriers (0: exp + tree sums, 1: copy, 2: divide) */
-int pgb_test_microbench(int32_t device, int32_t variant, int64_t N, int32_t iters, double* us_per_iter);
+/* rollout kernel choice for the tests: -1 automatic (default), 0 CTA per scenario, 1 warp per scenario */
+void pgb_test_rollout_kernel(int32_t which);
 
 #ifdef __cplusplus
 }

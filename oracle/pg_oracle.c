@@ -576,9 +576,14 @@ int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const doubl
  * (the order of the reference's reshape (n_y, T_test, K*k_n) at :301-302, k fastest): star ~ w_m1 (:288),
  * x_1 = f(x_m1[:, star], u_m1) + v (:290), x_t = f(x_{t-1}, u_test[:, t-1]) + v (:295), y_t = g(x_t) + e (:297) -
  * i.e. orc_rollout with H = T_test and u_init = u_test: x_loop[:, t] = X[t-1], y_loop[:, t] = Y[t-1] (the reference
- * leaves x_loop[:, T_test+1] undefined; here it holds one more transition).  mean_rmse (:311) =
- * sqrt(sum((y_sim - y_test)^2) / (n_y*T_test*K*k_n)) with the sum taken by the balanced tree over the column-major
- * (n_y, T_test, K*k_n) array. */
+ * leaves x_loop[:, T_test+1] undefined; here it holds one more transition).
+ * mean_rmse = sqrt(sum((y_sim - y_test)^2) / (n_y*T_test*K*k_n)), errors matched in TIME (y_sim[:, t, s] against
+ * y_test[:, t]), the sum taken by the balanced tree over the column-major (n_y, T_test, K*k_n) array.  DEVIATION from
+ * the Julia source, stated: :311 subtracts repeat(y_test', 1, 1, K*k_n), an array of shape (T_test, n_y, K*k_n), from
+ * the (n_y, T_test, K*k_n) simulations; for n_y = 1 Julia broadcasts that to T_test x T_test x S cross terms (every
+ * simulated output against every test output) and for n_y > 1 it throws.  The time-matched value is the quantity the
+ * MATLAB twin computes (MATLAB/src/test_prediction.m) and the one a prediction RMSE means; the drop-in therefore
+ * prints a different number than the Julia reference does. */
 int orc_test_prediction(const orc_model* m, int64_t K, int64_t k_n, int64_t T_test, int64_t N, const double* A,
                         const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
                         const double* Le, const double* u_test, const double* y_test, uint64_t seed, double* x_sim,

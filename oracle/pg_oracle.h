@@ -114,7 +114,7 @@ int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const doubl
 
 /* test_prediction (particle_Gibbs.jl:253-314): K models x k_n simulations over the test input, simulation (k, kn) =
  * scenario k + K*kn with its own stream; x_sim K*k_n x (T_test+1) x n_x, y_sim K*k_n x T_test x n_y (scenario-major),
- * mean_rmse as printed at :311-312. */
+ * mean_rmse = the time-matched RMSE (NOT the cross-term broadcast the Julia line :311 evaluates; see pg_oracle.c). */
 int orc_test_prediction(const orc_model* m, int64_t K, int64_t k_n, int64_t T_test, int64_t N, const double* A,
                         const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
                         const double* Le, const double* u_test /*n_u x T_test*/, const double* y_test /*n_y x T_test*/,

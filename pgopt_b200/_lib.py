@@ -34,8 +34,8 @@ EXPORTS = ["pgb_version", "pgb_last_error", "pgb_create", "pgb_destroy", "pgb_se
            "pgb_set_init_dist", "pgb_set_prior", "pgb_set_state", "pgb_get_state", "pgb_set_rng_philox",
            "pgb_set_rng_injected", "pgb_sweep", "pgb_sweep_filter", "pgb_sweep_mniw", "pgb_particle_gibbs",
            "pgb_get_sample", "pgb_get_history", "pgb_get_stats", "pgb_get_status", "pgb_synchronize",
-           "pgb_systematic_resampling", "pgb_mniw_sample", "pgb_rollout", "pgb_test_prediction", "pgb_scenario_constraint_max", "pgb_scenario_constraint_last_ms", "pgb_rollout_last_ms", "pgb_test_force_fallback", "pgb_test_math", "pgb_test_fp64_peak", "pgb_test_microbench",
-           "pgb_set_mode", "pgb_get_phase_cycles", "pgb_timer_start", "pgb_timer_stop", "pgb_profile", "pgb_get_profile", "pgb_get_launch_count"]
+           "pgb_systematic_resampling", "pgb_mniw_sample", "pgb_rollout", "pgb_test_prediction", "pgb_scenario_constraint_max", "pgb_scenario_constraint_last_ms", "pgb_rollout_last_ms", "pgb_test_force_fallback", "pgb_test_math", "pgb_test_fp64_peak", "pgb_test_rollout_kernel",
+           "pgb_set_mode", "pgb_timer_start", "pgb_timer_stop", "pgb_profile", "pgb_get_profile", "pgb_get_launch_count"]
 
 
 def lib():

@@ -1,92 +1,12 @@
 // pgb_capi.cu — host side of libpgopt_b200.so: the C ABI of include/pgopt_b200.h, device memory
-// management and the launch sequences.  No torch types, no CPU compute path: every entry point that
-// computes needs a CUDA device and fails with PGB_ERR_CUDA otherwise.
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/pgopt_b200.h"
-#include "pgb_mniw.cuh"
-#include "pgb_rollout.cuh"
-#include "pgb_persist.cuh"
-#include "pgb_persist_w.cuh"
-#include "pgb_small.cuh"
+// management and the launch sequences shared by every filter path.  No torch types, no CPU compute path: every
+// entry point that computes needs a CUDA device and fails with PGB_ERR_CUDA otherwise.
+#include "pgb_internal.h"
 
 using namespace pgb;
 
 static thread_local std::string g_last_error;
-static int g_force_fallback = 0;
-
-struct pgb_handle {
-  pgb_config cfg;
-  cudaStream_t stream = nullptr;
-  std::vector<void*> allocs;
-  std::string err;
-  FilterDev fd;
-  MniwDev md;
-  bool have_data = false, have_meas = false, have_init = false, have_prior = false, have_rng = false;
-  std::vector<char> have_state;
-  int64_t sweep_index = 1;
-  // device
-  double *d_u = nullptr, *d_y = nullptr, *d_Q = nullptr, *d_Vdiag = nullptr, *d_LambdaQ = nullptr;
-  double *d_Z0 = nullptr, *d_Z = nullptr, *d_Ures = nullptr, *d_Uanc = nullptr, *d_Ustar = nullptr;
-  double *d_bart = nullptr, *d_Xmn = nullptr;
-  int32_t* d_star_idx = nullptr;
-  int64_t* d_star_out = nullptr;
-  long long* d_counters_main = nullptr;
-  long long* d_counters_side = nullptr;
-  std::vector<double> h_u;  // host copy of u (for u_m1)
-  // the (A, Q) the last filter pass ran with (sample fields, particle_Gibbs.jl:204-205)
-  double *d_A_used = nullptr, *d_Q_used = nullptr;
-  double* d_replay_noise = nullptr;  // [nc][T][n_x] noise along the traced lineage (replay mode)
-  bool injected_ready = false;
-  // persistent (single cooperative kernel) filter path
-  int persistent = -1;  // -1: automatic (warp-per-chain kernel when N <= 32, else the tile persistent kernel), 1: tile persistent kernel, 2: warp-tile persistent kernel, 0: one launch per phase, 3: warp-per-chain kernel (N <= 32 only)
-  PersistDev pd;
-  int num_sms = 0;
-  // measurement
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool profile = false;
-  int64_t n_launch = 0;
-  std::vector<cudaEvent_t> ev_pool;
-  std::vector<int> ev_class;   // class of pair i (events 2i, 2i+1)
-  size_t ev_used = 0;
-  int64_t prof_launches[PGB_PROF_NCLASS] = {0};
-  double prof_ms[PGB_PROF_NCLASS] = {0};
-};
-
-// Bracket one launch: counts it and, in profiling mode, records an event pair around it.
-struct LaunchScope {
-  pgb_handle* h;
-  cudaEvent_t e1 = nullptr;
-  LaunchScope(pgb_handle* h_, int cls) : h(h_) {
-    h->n_launch += 1;
-    if (!h->profile) return;
-    if (h->ev_used + 2 > h->ev_pool.size()) {
-      for (int i = 0; i < 2; ++i) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        h->ev_pool.push_back(e);
-      }
-    }
-    cudaEvent_t e0 = h->ev_pool[h->ev_used];
-    e1 = h->ev_pool[h->ev_used + 1];
-    h->ev_used += 2;
-    h->ev_class.push_back(cls);
-    cudaEventRecord(e0, h->stream);
-  }
-  ~LaunchScope() {
-    if (e1) cudaEventRecord(e1, h->stream);
-  }
-};
-#define LAUNCH(h, cls, ...) do { LaunchScope ls_(h, cls); __VA_ARGS__; } while (0)
+int g_pgb_force_fallback = 0;
 
 static void profile_collect(pgb_handle* h) {
   if (!h->ev_used) return;
@@ -101,7 +21,7 @@ static void profile_collect(pgb_handle* h) {
   h->ev_class.clear();
 }
 
-static int set_err(pgb_handle* h, int code, const char* fmt, ...) {
+int pgb_set_err(pgb_handle* h, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -112,46 +32,19 @@ static int set_err(pgb_handle* h, int code, const char* fmt, ...) {
   return code;
 }
 
-#define CK(h, call)                                                                                   \
-  do {                                                                                                \
-    cudaError_t e_ = (call);                                                                          \
-    if (e_ != cudaSuccess)                                                                            \
-      return set_err(h, PGB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-  } while (0)
-
-template <typename T>
-static cudaError_t dalloc(pgb_handle* h, T** p, size_t count, bool zero = true) {
-  void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
-  if (e != cudaSuccess) return e;
-  if (h) h->allocs.push_back(q);
-  if (zero) {
-    e = cudaMemset(q, 0, count * sizeof(T));
-    if (e != cudaSuccess) return e;
-  }
-  *p = (T*)q;
-  return cudaSuccess;
+int pgb_require_device(void) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s); pgopt_b200 has no CPU fallback",
+                   cudaGetErrorString(e));
+  return PGB_OK;
 }
 
-extern "C" const char* pgb_version(void) { return "pgopt_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* pgb_version(void) { return "pgopt_b200 0.2.0 (sm_100a)"; }
 extern "C" const char* pgb_last_error(const pgb_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
-static cudaError_t alloc_scanws(pgb_handle* h, ScanWS* ws, int64_t N, int nc, long long** counters) {
-  cudaError_t e;
-  memset(ws, 0, sizeof(*ws));
-  ws->N = N;
-  ws->nt = (int)((N + TILE - 1) / TILE);
-  const int64_t nt = ws->nt;
-#define A_(field, count) if ((e = dalloc(h, &ws->field, (size_t)(count))) != cudaSuccess) return e;
-  A_(S, nc) A_(tsum, nc * nt) A_(tile_prefix, nc * (nt + 1)) A_(thr_ex, nc * nt * TPB) A_(tile_agg, nc * nt)
-  A_(tile_ex, nc * (nt + 1)) A_(recs, nc * nt * RMAX) A_(crec, (int64_t)nc * CMAX) A_(seeds, (int64_t)nc * (CMAX + 1))
-  A_(qin_fb, nc * nt * TPB) A_(Wn, nc * nt * TILE) A_(ticket, nc) A_(flag, 2 * nc) A_(pend, nc) A_(counters, 2 * nc)
-#undef A_
-  if (counters) *counters = ws->counters;
-  return cudaSuccess;
-}
-
-static int validate_cfg(const pgb_config* c) {
+int pgb_validate_cfg(const pgb_config* c) {
   if (!c) return set_err(nullptr, PGB_ERR_INVALID, "config is NULL");
   if (c->n_x < 1 || c->n_x > 4) return set_err(nullptr, PGB_ERR_INVALID, "n_x must be 1..4 (got %d)", c->n_x);
   if (c->n_u < 1 || c->n_u > 4) return set_err(nullptr, PGB_ERR_INVALID, "n_u must be 1..4 (got %d)", c->n_u);
@@ -178,7 +71,7 @@ static int validate_cfg(const pgb_config* c) {
   return PGB_OK;
 }
 
-static void fill_model(FilterDev& fd, const pgb_config* c) {
+void pgb_fill_model(FilterDev& fd, const pgb_config* c) {
   fd.n_x = c->n_x; fd.n_u = c->n_u; fd.n_y = c->n_y; fd.n_phi = c->n_phi; fd.basis = c->basis;
   fd.n_z = c->n_x + c->n_u;
   if (c->basis == PGB_BASIS_HILBERT_GP) {
@@ -200,7 +93,7 @@ static void fill_model(FilterDev& fd, const pgb_config* c) {
 extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
   if (!out) return set_err(nullptr, PGB_ERR_INVALID, "out is NULL");
   *out = nullptr;
-  int rc = validate_cfg(cfg);
+  int rc = pgb_validate_cfg(cfg);
   if (rc) return rc;
   if (cfg->N < 2 || cfg->T < 2 || cfg->n_chains < 1)
     return set_err(nullptr, PGB_ERR_INVALID, "need N >= 2, T >= 2, n_chains >= 1");
@@ -228,7 +121,7 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
   const int nc = cfg->n_chains, nx = cfg->n_x, np = cfg->n_phi, nu = cfg->n_u, ny = cfg->n_y;
   FilterDev& fd = h->fd;
   memset(&fd, 0, sizeof(fd));
-  fill_model(fd, cfg);
+  pgb_fill_model(fd, cfg);
   fd.N = N; fd.T = T; fd.nc = nc;
   fd.nt = (int)((N + TILE - 1) / TILE);
   const int64_t nt = fd.nt;
@@ -253,7 +146,7 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
   CKC(dalloc(h, &fd.lineage, (size_t)nc * T));
   CKC(dalloc(h, &h->d_replay_noise, (size_t)nc * T * nx));
   CKC(dalloc(h, &fd.ah, (size_t)nc * T * N, false));
-  CKC(cudaMemset(fd.ah, 0xff, (size_t)nc * T * N * sizeof(int32_t)));
+  CKC(cudaMemsetAsync(fd.ah, 0xff, (size_t)nc * T * N * sizeof(int32_t), h->stream));
   CKC(dalloc(h, &fd.wbuf, (size_t)nc * N));
   CKC(dalloc(h, &fd.ebuf, (size_t)nc * N));
   CKC(dalloc(h, &fd.lwbuf, (size_t)nc * N));
@@ -271,8 +164,8 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
   CKC(dalloc(h, &fd.utab_res, (size_t)nc * T, false));
   CKC(dalloc(h, &fd.utab_anc, (size_t)nc * T, false));
   CKC(dalloc(h, &fd.utab_star, (size_t)nc, false));
-  CKC(alloc_scanws(h, &fd.main, N, nc, &h->d_counters_main));
-  CKC(alloc_scanws(h, &fd.side, N, nc, &h->d_counters_side));
+  CKC(pgb_alloc_scanws(h, &fd.main, N, nc, &h->d_counters_main));
+  CKC(pgb_alloc_scanws(h, &fd.side, N, nc, &h->d_counters_side));
   CKC(dalloc(h, &h->d_star_idx, (size_t)nc));
   CKC(dalloc(h, &h->d_star_out, (size_t)nc));
   // MNIW
@@ -305,20 +198,16 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
     pd.star_idx = h->d_star_idx;
     CKC(dalloc(h, &pd.heavy, (size_t)nc * P_HEAVY_MAX));
     CKC(dalloc(h, &pd.heavy_cnt, (size_t)nc));
-    CKC(dalloc(h, &pd.prof, (size_t)1024 * P_NPROF));
     CKC(dalloc(h, &pd.cand, (size_t)2 * nc));
     CKC(dalloc(h, &pd.sm_slots, (size_t)1024));
     CKC(dalloc(h, &pd.cta_key, (size_t)4096));
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
     h->num_sms = prop.multiProcessorCount;
-    const char* abl = getenv("PGB_ABLATE");
-    fd.ablate = abl ? atoi(abl) : 0;
-    const char* env = getenv("PGB_PERSISTENT");
-    if (env && env[0] >= '0' && env[0] <= '3') h->persistent = env[0] - '0';
   }
   h->have_state.assign(nc, 0);
   h->h_u.assign((size_t)nu * T, 0.0);
+  CKC(cudaStreamSynchronize(h->stream));  // every zero-fill above has landed before the handle is handed out
 #undef CKC
   *out = h;
   return PGB_OK;
@@ -337,10 +226,6 @@ extern "C" void pgb_destroy(pgb_handle* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
 }
-
-#define NEED(h) \
-  if (!h) return set_err(nullptr, PGB_ERR_INVALID, "handle is NULL"); \
-  CK(h, cudaSetDevice(h->cfg.device))
 
 extern "C" int pgb_set_data(pgb_handle* h, const double* u, const double* y) {
   NEED(h);
@@ -443,6 +328,10 @@ extern "C" int pgb_get_state(pgb_handle* h, int32_t chain, double* A, double* Q,
 
 extern "C" int pgb_set_rng_philox(pgb_handle* h, uint64_t seed, uint32_t chain_base) {
   NEED(h);
+  // the stream id (chain_base + chain) occupies 24 bits of the Philox counter (pgb_math.h: pgb_stream_block)
+  if ((uint64_t)chain_base + (uint64_t)h->cfg.n_chains > (1ull << 24))
+    return set_err(h, PGB_ERR_INVALID, "chain_base + n_chains = %llu exceeds the 2^24 Philox stream ids",
+                   (unsigned long long)chain_base + (unsigned long long)h->cfg.n_chains);
   h->fd.philox = 1; h->fd.seed = seed; h->fd.chain_base = chain_base;
   h->md.philox = 1; h->md.seed = seed; h->md.chain_base = chain_base;
   h->have_rng = true;
@@ -488,128 +377,38 @@ static int check_ready(pgb_handle* h) {
   return PGB_OK;
 }
 
-// Launch sequence of one exact scan + consumer on stream s.
-template <int NX, int MODE>
-static void launch_scan(pgb_handle* h, const ScanWS& ws, const double* v, const pgb_utable* utab, int64_t utab_stride,
-                        int64_t utab_index, int32_t* out_idx, int64_t out_stride, int64_t t, int first,
-                        unsigned long long* maxkey_reset) {
-  const FilterDev& fd = h->fd;
-  cudaStream_t s = h->stream;
-  dim3 gt(ws.nt, fd.nc), g1(1, fd.nc);
-  LAUNCH(h, PGB_PROF_SCAN_LOCAL, (k_scan_local<<<gt, TPB, 0, s>>>(ws, v, fd.status)));
-  LAUNCH(h, PGB_PROF_RESOLVE, (k_resolve<<<g1, TPB, 0, s>>>(ws, g_force_fallback & 1)));
-  LAUNCH(h, PGB_PROF_EXPAND, (k_expand<NX, MODE><<<gt, TPB, 0, s>>>(fd, ws, v, utab, utab_stride, utab_index, out_idx,
-                                                                    out_stride, t, first, 0)));
-  LAUNCH(h, PGB_PROF_SEQ, (k_seq_exact<<<g1, 32, 0, s>>>(ws, v, fd.status, maxkey_reset)));
-  LAUNCH(h, PGB_PROF_EXPAND_FB, (k_expand<NX, MODE><<<gt, TPB, 0, s>>>(fd, ws, v, utab, utab_stride, utab_index, out_idx,
-                                                                       out_stride, t, first, 1)));
-}
-
-template <int NX>
-static int run_filter_nx(pgb_handle* h) {
+// What every filter path does first: remember the (A, Q) this sweep runs with (sample fields :204-205), publish the
+// sweep counter to the kernels, reset the running max of the log-weights.
+int pgb_filter_prologue(pgb_handle* h, int* first) {
   FilterDev& fd = h->fd;
-  MniwDev& md = h->md;
   cudaStream_t s = h->stream;
-  const int64_t N = fd.N, T = fd.T;
-  const int nc = fd.nc;
-  const int first = (h->sweep_index == 1);
+  const int nc = fd.nc, nx = fd.n_x;
+  *first = (h->sweep_index == 1);
   fd.sweep = (uint32_t)h->sweep_index;
-  md.sweep = fd.sweep;
-  const size_t nA = (size_t)nc * NX * fd.n_phi * 8, nQ = (size_t)nc * NX * NX * 8;
+  h->md.sweep = fd.sweep;
+  const size_t nA = (size_t)nc * nx * fd.n_phi * 8, nQ = (size_t)nc * nx * nx * 8;
   CK(h, cudaMemcpyAsync(h->d_A_used, fd.A, nA, cudaMemcpyDeviceToDevice, s));
   CK(h, cudaMemcpyAsync(h->d_Q_used, h->d_Q, nQ, cudaMemcpyDeviceToDevice, s));
   CK(h, cudaMemsetAsync(fd.maxkey, 0, (size_t)nc * 8, s));
-  dim3 gt(fd.nt, nc);
-  const size_t smA = (size_t)NX * fd.n_phi * 8;
-  LAUNCH(h, PGB_PROF_INIT, (k_build_utabs<<<dim3((unsigned)((T + 127) / 128), nc), 128, 0, s>>>(fd, first)));
-  LAUNCH(h, PGB_PROF_INIT, (k_init<NX><<<dim3((unsigned)((N + TPB - 1) / TPB), nc), TPB, 0, s>>>(fd, first)));
-  LAUNCH(h, PGB_PROF_WEIGHTS, (k_weights<<<gt, TPB, 0, s>>>(fd)));
-  for (int64_t t = 1; t < T; ++t) {
-    LAUNCH(h, PGB_PROF_PREP, (k_prep<NX><<<gt, TPB, smA, s>>>(fd, t, first)));
-    launch_scan<NX, MODE_PROPAGATE>(h, fd.main, fd.wbuf, fd.utab_res, T, t, nullptr, 0, t, first, fd.maxkey);
-    if (!first) {
-      LAUNCH(h, PGB_PROF_NORM, (k_norm<<<gt, TPB, 0, s>>>(fd)));
-      launch_scan<NX, MODE_INDEX>(h, fd.side, fd.waN, fd.utab_anc, T, t, fd.ah + t * N + (N - 1), T * N, t, first, nullptr);
+  return PGB_OK;
+}
+
+// ... and last: backward trace of the ancestor path (:213-218; replayed when the particle history is not kept)
+// and the sufficient statistics (:221-225).
+template <int NX>
+static int trace_and_stats_nx(pgb_handle* h, int first, bool trace_done) {
+  FilterDev& fd = h->fd;
+  MniwDev& md = h->md;
+  cudaStream_t s = h->stream;
+  const int64_t T = fd.T;
+  const int nc = fd.nc;
+  if (!trace_done) {
+    if (fd.x_rows == T) {
+      LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+    } else {
+      LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay<NX><<<nc, TR_TPB, (size_t)fd.n_phi * 8, s>>>(fd, h->d_star_idx, h->d_star_out,
+                                                                                          h->d_replay_noise, first)));
     }
-    LAUNCH(h, PGB_PROF_WEIGHTS, (k_weights<<<gt, TPB, 0, s>>>(fd)));
-  }
-  // w_T, then star = systematic_resampling(w[end,:], 1)   (:213)
-  LAUNCH(h, PGB_PROF_TAIL, (k_prep<NX><<<gt, TPB, smA, s>>>(fd, T, first)));
-  launch_scan<NX, MODE_INDEX>(h, fd.main, fd.wbuf, fd.utab_star, 1, 0, h->d_star_idx, 1, 0, first, nullptr);
-  if (fd.x_rows == T) {
-    LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
-  } else {
-    LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay<NX><<<nc, TR_TPB, (size_t)fd.n_phi * 8, s>>>(fd, h->d_star_idx, h->d_star_out,
-                                                                                        h->d_replay_noise, first)));
-  }
-  // statistics (:221-225)
-  LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
-  const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
-  LAUNCH(h, PGB_PROF_TAIL, (k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md)));
-  CK(h, cudaGetLastError());
-  return PGB_OK;
-}
-
-// One cooperative launch for the whole time loop.  Returns -1 when the configuration does not fit
-// (too many chains / tiles for the co-resident grid); the caller then uses the multi-kernel path.
-template <int NX>
-static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
-  FilterDev& fd = h->fd;
-  MniwDev& md = h->md;
-  PersistDev& pd = h->pd;
-  cudaStream_t s = h->stream;
-  const int64_t T = fd.T;
-  const int nc = fd.nc;
-  const size_t smA = (warp_tiles ? sizeof(WShared) : sizeof(PersistShared)) + (size_t)NX * fd.n_phi * 8;
-  const void* kfn = warp_tiles ? (const void*)k_sweep_w<NX> : (const void*)k_sweep_persistent<NX>;
-  int occ = 0;
-  CK(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA));
-  if (warp_tiles) CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_w<NX>, TPB, smA));
-  else CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_persistent<NX>, TPB, smA));
-  const int max_ctas = occ * h->num_sms;
-  if (max_ctas > 4096) return -1;
-  int nbmax = max_ctas / nc;
-  if (nbmax < 1) return -1;
-  int tpc = 1;
-  if (warp_tiles) {  // one block per CTA
-    if (nbmax > W_MAXNB) nbmax = W_MAXNB;
-    while ((fd.nt + tpc - 1) / tpc > nbmax) tpc *= 2;
-    if (tpc > W_MAXTPC) return -1;
-    pd.tpc = tpc;
-    pd.nb = (fd.nt + tpc - 1) / tpc;
-    pd.npc = pd.nb;
-  } else {  // finest blocks the per-chain tables allow, dealt over every co-resident CTA slot
-    while ((fd.nt + tpc - 1) / tpc > P_MAXNB) tpc *= 2;
-    pd.tpc = tpc;
-    pd.nb = (fd.nt + tpc - 1) / tpc;
-    pd.npc = pd.nb < nbmax ? pd.nb : nbmax;
-    if (((pd.nb + pd.npc - 1) / pd.npc) * tpc > P_MAXTPC) return -1;
-  }
-  pd.force_fallback = g_force_fallback;
-  int first = (h->sweep_index == 1);
-  fd.sweep = (uint32_t)h->sweep_index;
-  md.sweep = fd.sweep;
-  const size_t nA = (size_t)nc * NX * fd.n_phi * 8, nQ = (size_t)nc * NX * NX * 8;
-  CK(h, cudaMemcpyAsync(h->d_A_used, fd.A, nA, cudaMemcpyDeviceToDevice, s));
-  CK(h, cudaMemcpyAsync(h->d_Q_used, h->d_Q, nQ, cudaMemcpyDeviceToDevice, s));
-  CK(h, cudaMemsetAsync(fd.maxkey, 0, (size_t)nc * 8, s));
-  CK(h, cudaMemsetAsync(pd.bar, 0, 4, s));
-  CK(h, cudaMemsetAsync(pd.sm_slots, 0, (size_t)1024 * 4, s));
-  CK(h, cudaMemsetAsync(pd.heavy_cnt, 0, (size_t)nc * 4, s));
-  CK(h, cudaMemsetAsync(pd.cand, 0, (size_t)2 * nc * 4, s));
-  CK(h, cudaMemsetAsync(fd.main.flag, 0, (size_t)2 * nc * 4, s));
-  CK(h, cudaMemsetAsync(fd.side.flag, 0, (size_t)2 * nc * 4, s));
-  LAUNCH(h, PGB_PROF_INIT, (k_build_utabs<<<dim3((unsigned)((T + 127) / 128), nc), 128, 0, s>>>(fd, first)));
-  {
-    LaunchScope ls(h, PGB_PROF_EXPAND);
-    void* args[] = {(void*)&fd, (void*)&pd, (void*)&first};
-    CK(h, cudaLaunchCooperativeKernel(kfn, dim3((unsigned)(nc * pd.npc)), dim3(TPB), args, smA, s));
-  }
-  if (fd.x_rows == T) {
-    LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
-  } else {
-    LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay<NX><<<nc, TR_TPB, (size_t)fd.n_phi * 8, s>>>(fd, h->d_star_idx, h->d_star_out,
-                                                                                        h->d_replay_noise, first)));
   }
   LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
   const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
@@ -617,79 +416,32 @@ static int run_filter_persistent_nx(pgb_handle* h, bool warp_tiles) {
   CK(h, cudaGetLastError());
   return PGB_OK;
 }
-
-static int64_t g_small_auto_max = CTA_MAXN;  // largest N the automatic mode gives to the warp / one-CTA-per-chain kernels
-                                               // (measured faster than the tile kernel up to 1024, profiles/r01_mid_n_kernel.md)
-
-// Small particle counts (N <= 32, stored history): one warp per chain, the whole time loop in one ordinary launch
-// (pgb_small.cuh).  Returns -1 when the configuration does not qualify.
-template <int NX>
-static int run_filter_small_nx(pgb_handle* h, int64_t n_max) {
-  FilterDev& fd = h->fd;
-  MniwDev& md = h->md;
-  cudaStream_t s = h->stream;
-  const int64_t T = fd.T;
-  const int nc = fd.nc;
-  if (fd.N > n_max || fd.N > CTA_MAXN || fd.x_rows != T) return -1;
-  const bool cta = fd.N > SMALL_MAXN;  // mid-size N: one CTA per chain (k_sweep_cta), thread = particle
-  const int np_thr = (int)((fd.N + 31) / 32) * 32;
-  const size_t smem = cta ? ((size_t)((NX * fd.n_phi + 1) & ~1) + (size_t)(NX + 4) * np_thr + 4) * 8 + sizeof(CtaShared)
-                          : ((size_t)((NX * fd.n_phi + 1) & ~1) + (size_t)NX * 32 + 32) * 8;
-  if (smem > 200 * 1024) return -1;
-  int first = (h->sweep_index == 1);
-  fd.sweep = (uint32_t)h->sweep_index;
-  md.sweep = fd.sweep;
-  const size_t nA = (size_t)nc * NX * fd.n_phi * 8, nQ = (size_t)nc * NX * NX * 8;
-  CK(h, cudaMemcpyAsync(h->d_A_used, fd.A, nA, cudaMemcpyDeviceToDevice, s));
-  CK(h, cudaMemcpyAsync(h->d_Q_used, h->d_Q, nQ, cudaMemcpyDeviceToDevice, s));
-  if (cta) {
-    CK(h, cudaFuncSetAttribute(k_sweep_cta<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH(h, PGB_PROF_EXPAND, (k_sweep_cta<NX><<<nc, np_thr, smem, s>>>(fd, h->pd.star_idx, first)));
-    LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
-  } else {
-    CK(h, cudaFuncSetAttribute(k_sweep_small<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH(h, PGB_PROF_EXPAND, (k_sweep_small<NX><<<nc, 32, smem, s>>>(fd, h->pd.star_idx, first)));
-    LAUNCH(h, PGB_PROF_TAIL, (k_trace_small<NX><<<nc, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+int pgb_launch_trace_and_stats(pgb_handle* h, int first, bool small_trace_done) {
+  switch (h->cfg.n_x) {
+    case 1: return trace_and_stats_nx<1>(h, first, small_trace_done);
+    case 2: return trace_and_stats_nx<2>(h, first, small_trace_done);
+    case 3: return trace_and_stats_nx<3>(h, first, small_trace_done);
+    default: return trace_and_stats_nx<4>(h, first, small_trace_done);
   }
-  LAUNCH(h, PGB_PROF_TAIL, (k_stats_z<NX><<<dim3((unsigned)((T - 1 + 127) / 128), nc), 128, 0, s>>>(fd, md)));
-  const int64_t nent = (int64_t)NX * NX + (int64_t)NX * fd.n_phi + (int64_t)fd.n_phi * fd.n_phi;
-  LAUNCH(h, PGB_PROF_TAIL, (k_stats<<<dim3((unsigned)nent, nc), TPB, 0, s>>>(md)));
-  CK(h, cudaGetLastError());
-  return PGB_OK;
 }
 
 static int run_filter(pgb_handle* h) {
-  int mode0 = h->persistent;
-  if (mode0 < 0 || mode0 == 3) {
-    int rc;
+  int mode = h->persistent;
+  int rc;
+  if (mode < 0 || mode == 3) {
     // the warp kernel up to N = 32, the one-CTA-per-chain kernel up to N = 1024 (automatic and mode 3)
-    const int64_t n_max = (mode0 == 3) ? CTA_MAXN : g_small_auto_max;
-    switch (h->cfg.n_x) {
-      case 1: rc = run_filter_small_nx<1>(h, n_max); break;
-      case 2: rc = run_filter_small_nx<2>(h, n_max); break;
-      case 3: rc = run_filter_small_nx<3>(h, n_max); break;
-      default: rc = run_filter_small_nx<4>(h, n_max); break;
-    }
+    rc = pgb_run_filter_small(h, 1024);
     if (rc >= 0) return rc;
-    mode0 = 1;
+    mode = (mode == 3) ? 1 : 4;
   }
-  for (int mode = mode0; mode >= 1; --mode) {  // a configuration that does not fit falls through
-    int rc;
-    const bool wt = (mode == 2);
-    switch (h->cfg.n_x) {
-      case 1: rc = run_filter_persistent_nx<1>(h, wt); break;
-      case 2: rc = run_filter_persistent_nx<2>(h, wt); break;
-      case 3: rc = run_filter_persistent_nx<3>(h, wt); break;
-      default: rc = run_filter_persistent_nx<4>(h, wt); break;
-    }
+  if (mode == 4) {  // a configuration that does not fit falls through to the tile kernels
+    mode = 1;
+  }
+  if (mode >= 1) {
+    rc = pgb_run_filter_tile_persistent(h);
     if (rc >= 0) return rc;
   }
-  switch (h->cfg.n_x) {
-    case 1: return run_filter_nx<1>(h);
-    case 2: return run_filter_nx<2>(h);
-    case 3: return run_filter_nx<3>(h);
-    default: return run_filter_nx<4>(h);
-  }
+  return pgb_run_filter_tile_multikernel(h);
 }
 
 static int run_mniw(pgb_handle* h) {
@@ -776,12 +528,16 @@ extern "C" int pgb_particle_gibbs(pgb_handle* h, int64_t K, int64_t K_b, int64_t
   if (!h->fd.philox) return set_err(h, PGB_ERR_INVALID, "pgb_particle_gibbs needs Philox streams");
   if (!h->have_prior) return set_err(h, PGB_ERR_STATE, "pgb_set_prior missing");
   if (K < 1 || K_b < 0 || k_d < 0) return set_err(h, PGB_ERR_INVALID, "bad K/K_b/k_d");
+  // particle_Gibbs.jl:154 always starts at k = 1 (bootstrap filter on the first iteration, also with a supplied x_prim)
+  if (h->sweep_index != 1)
+    return set_err(h, PGB_ERR_STATE, "pgb_particle_gibbs starts a sampler at sweep 1: call pgb_set_state(..., sweep_index = 1) "
+                                     "first (handle is at sweep %lld)", (long long)h->sweep_index);
   const int nc = h->cfg.n_chains, nx = h->cfg.n_x, np = h->cfg.n_phi;
   const int64_t N = h->cfg.N;
   const int64_t K_total = K_b + 1 + (K - 1) * (k_d + 1);  // particle_Gibbs.jl:116
   std::vector<double> tmp;
   int64_t cur = 0;
-  for (int64_t k = h->sweep_index; k <= K_total; ++k) {
+  for (int64_t k = 1; k <= K_total; ++k) {
     if ((rc = run_filter(h))) return rc;
     if (K_b < k && ((k - (K_b + 1)) % (k_d + 1) == 0) && cur < K) {  // :203
       for (int c = 0; c < nc; ++c) {
@@ -860,64 +616,6 @@ extern "C" int pgb_get_status(pgb_handle* h, int32_t chain, int32_t* status_bits
   return PGB_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// stand-alone helpers
-// ------------------------------------------------------------------------------------------------
-__global__ void k_build_one_utab(pgb_utable* ut, int64_t M, double rnd) { pgb_utable_build(ut, M, rnd); }
-
-extern "C" int pgb_systematic_resampling(int32_t device, const double* W, int64_t n_w, int64_t n_draw, double rnd,
-                                         int64_t* idx, int32_t* status) {
-  if (!W || !idx || n_w < 1 || n_draw < 1) return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
-  if (n_w >= (1ll << 31) - TILE) return set_err(nullptr, PGB_ERR_INVALID, "n_w too large");
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev <= 0)
-    return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s); pgopt_b200 has no CPU fallback",
-                   cudaGetErrorString(e));
-  pgb_handle tmp;  // only used as an allocation list / error sink
-  pgb_handle* h = &tmp;
-  h->cfg.device = device;
-  struct Cleanup {
-    pgb_handle* h;
-    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
-  } cleanup{h};
-  CK(h, cudaSetDevice(device));
-  FilterDev fd;
-  memset(&fd, 0, sizeof(fd));
-  fd.nc = 1; fd.N = n_w; fd.T = 1; fd.n_x = 1; fd.n_y = 1; fd.n_u = 1;
-  ScanWS ws;
-  CK(h, alloc_scanws(h, &ws, n_w, 1, nullptr));
-  fd.nt = ws.nt;
-  double* d_W = nullptr;
-  int32_t* d_idx = nullptr;
-  pgb_utable* d_ut = nullptr;
-  CK(h, dalloc(h, &d_W, (size_t)n_w));
-  CK(h, dalloc(h, &d_idx, (size_t)n_draw));
-  CK(h, dalloc(h, &d_ut, 1));
-  CK(h, dalloc(h, &fd.status, 1));
-  CK(h, cudaMemcpy(d_W, W, (size_t)n_w * 8, cudaMemcpyHostToDevice));
-  cudaStream_t s = 0;
-  h->stream = s;
-  h->fd = fd;
-  k_build_one_utab<<<1, 1, 0, s>>>(d_ut, n_draw, rnd);
-  k_tile_sums<<<dim3(ws.nt, 1), TPB, 0, s>>>(ws, d_W);
-  launch_scan<1, MODE_INDEX>(h, ws, d_W, d_ut, 1, 0, d_idx, n_draw, 0, 0, nullptr);
-  CK(h, cudaGetLastError());
-  CK(h, cudaDeviceSynchronize());
-  std::vector<int32_t> t32((size_t)n_draw);
-  int st = 0;
-  CK(h, cudaMemcpy(t32.data(), d_idx, (size_t)n_draw * 4, cudaMemcpyDeviceToHost));
-  CK(h, cudaMemcpy(&st, fd.status, 4, cudaMemcpyDeviceToHost));
-  for (int64_t i = 0; i < n_draw; ++i) idx[i] = (int64_t)t32[i] + 1;
-  if (status) {
-    long long c[2];
-    CK(h, cudaMemcpy(c, ws.counters, 16, cudaMemcpyDeviceToHost));
-    *status = st | (c[0] ? 0x100 : 0);  // bit 8: the serial exact fallback ran
-  }
-  h->stream = nullptr;
-  return PGB_OK;
-}
-
 extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Phi, const double* Psi,
                                const double* Sigma, const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t T,
                                const double* bartlett, const double* Xmn, uint64_t seed, uint32_t chain,
@@ -973,342 +671,9 @@ extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const
   return PGB_OK;
 }
 
-static int g_rollout_grid[3] = {0, 0, 0};  // last warp-kernel launch: {CTAs, CTAs per SM, runs of A in shared memory}
-static int g_rollout_kernel = -1;  // kernel the last pgb_rollout ran: 1 = warp per scenario, 0 = CTA per scenario
-static float g_rollout_ms[2] = {0.f, 0.f};  // device time of the last pgb_rollout: {H2D copies, rollout kernel}
-
-template <int NX, int NI>
-static cudaError_t launch_rollout_ni(const FilterDev& fd, const RolloutDev& rd, size_t smem) {
-  cudaError_t e = cudaFuncSetAttribute(k_rollout<NX, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k_rollout<NX, NI><<<(unsigned)rd.K, R_TPB, smem>>>(fd, rd);
-  return cudaGetLastError();
-}
-// n_phi <= 128: one register-resident column of A per thread; otherwise five (n_phi <= 640 entirely in registers,
-// e.g. 5^4 = 625), any further columns are read from L2
-template <int NX>
-static cudaError_t launch_rollout(const FilterDev& fd, const RolloutDev& rd, size_t smem) {
-  return fd.n_phi <= R_TPB ? launch_rollout_ni<NX, 1>(fd, rd, smem) : launch_rollout_ni<NX, 5>(fd, rd, smem);
-}
-
-// Warp-per-scenario kernel (default): A_k resident over 32 lanes (RS of each lane's 4 runs in shared memory, the
-// rest in registers), persistent grid of independent warps.
-static size_t rollout_warp_smem(int nx, int ny, int nu, int64_t H, int ni, int rs) {
-  return sizeof(RolloutWShared) +
-         ((size_t)H * nu + (size_t)RW_WPB * (PGB_MAX_Z_ * MAXC + (size_t)H * (nx + ny) + (size_t)rs * ni * nx * 32 + (size_t)(H + 2) * nx)) * 8;
-}
-template <int NX, int NI, int RS>
-static cudaError_t launch_rollout_warp_ni(const FilterDev& fd, const RolloutDev& rd, int n_sm) {
-  const size_t smem = rollout_warp_smem(NX, fd.n_y, fd.n_u, rd.H, NI, RS);
-  cudaError_t e = cudaFuncSetAttribute(k_rollout_warp<NX, NI, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rollout_warp<NX, NI, RS>, RW_WPB * 32, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) per_sm = 1;
-  int64_t grid = (rd.K + RW_WPB - 1) / RW_WPB;
-  if (grid > (int64_t)n_sm * per_sm) grid = (int64_t)n_sm * per_sm;
-  g_rollout_grid[0] = (int)grid; g_rollout_grid[1] = per_sm; g_rollout_grid[2] = RS;
-  k_rollout_warp<NX, NI, RS><<<(unsigned)grid, RW_WPB * 32, smem>>>(fd, rd);
-  return cudaGetLastError();
-}
-template <int NX>
-static cudaError_t launch_rollout_warp(const FilterDev& fd, const RolloutDev& rd, int n_sm, int rs) {
-  if (fd.n_phi <= 128) return launch_rollout_warp_ni<NX, 1, 0>(fd, rd, n_sm);
-  switch (rs) {
-    case 0: return launch_rollout_warp_ni<NX, RW_MAXNI, 0>(fd, rd, n_sm);
-    case 3: return launch_rollout_warp_ni<NX, RW_MAXNI, 3>(fd, rd, n_sm);
-    default: return launch_rollout_warp_ni<NX, RW_MAXNI, 2>(fd, rd, n_sm);
-  }
-}
-
-// Shared body of pgb_rollout (n_models = 0, y_test = null) and pgb_test_prediction (K scenarios over n_models models,
-// scenario k simulating model k mod n_models; sum_sq_err = tree sum of (Y - y_test)^2).
-static int rollout_run(const pgb_config* cfg, int64_t K, int64_t n_models, int64_t H, const double* A, const double* Q,
-                       const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
-                       const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e,
-                       double* X, double* Y, const double* y_test, double* sum_sq_err) {
-  int rc = validate_cfg(cfg);
-  if (rc) return rc;
-  const int64_t KM = n_models > 0 ? n_models : K;  // number of models (PG samples) behind the K scenarios
-  if (!A || !Q || !w_m1 || !x_m1 || !u_m1 || !C || !Le || !u_init || K < 1 || H < 1 || cfg->N < 1)
-    return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
-  int ndev = 0;
-  cudaError_t ce = cudaGetDeviceCount(&ndev);
-  if (ce != cudaSuccess || ndev <= 0)
-    return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s); pgopt_b200 has no CPU fallback",
-                   cudaGetErrorString(ce));
-  pgb_handle tmp;
-  pgb_handle* h = &tmp;
-  struct Cleanup {
-    pgb_handle* h;
-    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
-  } cleanup{h};
-  CK(h, cudaSetDevice(cfg->device));
-  const int nx = cfg->n_x, np = cfg->n_phi, nu = cfg->n_u, ny = cfg->n_y;
-  const int64_t N = cfg->N;
-  FilterDev fd;
-  memset(&fd, 0, sizeof(fd));
-  fill_model(fd, cfg);
-  for (int i = 0; i < ny * nx; ++i) fd.C[i] = C[i];
-  RolloutDev rd;
-  memset(&rd, 0, sizeof(rd));
-  rd.K = K; rd.H = H; rd.N = N; rd.seed = seed; rd.k_offset = k_offset; rd.n_models = n_models;
-  for (int i = 0; i < ny * ny; ++i) rd.Le[i] = Le[i];
-  const int m = nx * np;
-  const size_t smem = sizeof(RolloutShared) + ((size_t)H * (nx + ny + nu) + (size_t)(N < R_WSTAGE ? N : R_WSTAGE)) * 8;
-  if (smem > 200 * 1024 || K > 0x7fffffffLL)
-    return set_err(nullptr, PGB_ERR_INVALID, "rollout: horizon H = %lld (or K) too large", (long long)H);
-  double *dA, *dQ, *dw, *dx, *dum, *dui;
-  cudaEvent_t ev[3];
-  for (auto& evt : ev) CK(h, cudaEventCreate(&evt));
-  CK(h, cudaEventRecord(ev[0], 0));
-  CK(h, dalloc(h, &dA, (size_t)KM * m, false));
-  CK(h, dalloc(h, &dQ, (size_t)KM * nx * nx, false));
-  CK(h, dalloc(h, &dw, (size_t)KM * N, false));
-  CK(h, dalloc(h, &dx, (size_t)KM * nx * N, false));
-  CK(h, dalloc(h, &dum, (size_t)KM * nu, false));
-  CK(h, dalloc(h, &dui, (size_t)nu * H, false));
-  CK(h, dalloc(h, &rd.status, 1));
-  CK(h, cudaMemcpy(dA, A, (size_t)KM * m * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(dQ, Q, (size_t)KM * nx * nx * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(dw, w_m1, (size_t)KM * N * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(dx, x_m1, (size_t)KM * nx * N * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(dum, u_m1, (size_t)KM * nu * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(dui, u_init, (size_t)nu * H * 8, cudaMemcpyHostToDevice));
-  if (x0) CK(h, dalloc(h, &rd.x0, (size_t)K * nx, false));
-  if (v) CK(h, dalloc(h, &rd.v, (size_t)K * H * nx, false));
-  if (e) CK(h, dalloc(h, &rd.e, (size_t)K * H * ny, false));
-  if (X) CK(h, dalloc(h, &rd.X, (size_t)K * (H + 1) * nx, false));
-  if (Y || y_test) CK(h, dalloc(h, &rd.Y, (size_t)K * H * ny, false));
-  CK(h, cudaEventRecord(ev[1], 0));
-  rd.A = dA; rd.Q = dQ; rd.w_m1 = dw; rd.x_m1 = dx; rd.u_m1 = dum; rd.u_init = dui;
-  // kernel choice: one warp per scenario whenever A_k fits the registers of 32 lanes (n_phi <= 128 * RW_MAXNI) and
-  // the per-warp noise buffers fit shared memory; PGB_ROLLOUT_KERNEL=cta|warp forces one (tests run both)
-  int rs = 2;  // runs (of 4 per lane) of A_k kept in shared memory; PGB_ROLLOUT_RS=0|2|3 (experiments)
-  if (const char* e2 = getenv("PGB_ROLLOUT_RS")) rs = atoi(e2);
-  if (rs != 0 && rs != 3) rs = 2;
-  const size_t smem_w = rollout_warp_smem(nx, ny, nu, H, np <= 128 ? 1 : RW_MAXNI, np <= 128 ? 0 : rs);
-  bool use_warp = np <= 128 * RW_MAXNI && smem_w <= 100 * 1024;
-  if (const char* kk = getenv("PGB_ROLLOUT_KERNEL")) {
-    if (!strcmp(kk, "cta")) use_warp = false;
-    else if (!strcmp(kk, "warp") && !use_warp)
-      return set_err(nullptr, PGB_ERR_INVALID, "rollout: warp kernel needs n_phi <= %d and a shorter horizon", 128 * RW_MAXNI);
-  }
-  g_rollout_kernel = use_warp ? 1 : 0;
-  if (use_warp) {
-    int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, cfg->device);
-    switch (nx) {
-      case 1: CK(h, launch_rollout_warp<1>(fd, rd, n_sm, rs)); break;
-      case 2: CK(h, launch_rollout_warp<2>(fd, rd, n_sm, rs)); break;
-      case 3: CK(h, launch_rollout_warp<3>(fd, rd, n_sm, rs)); break;
-      default: CK(h, launch_rollout_warp<4>(fd, rd, n_sm, rs)); break;
-    }
-  } else {
-    switch (nx) {
-      case 1: CK(h, launch_rollout<1>(fd, rd, smem)); break;
-      case 2: CK(h, launch_rollout<2>(fd, rd, smem)); break;
-      case 3: CK(h, launch_rollout<3>(fd, rd, smem)); break;
-      default: CK(h, launch_rollout<4>(fd, rd, smem)); break;
-    }
-  }
-  CK(h, cudaEventRecord(ev[2], 0));
-  double* d_sse = nullptr;
-  if (y_test && sum_sq_err) {  // squared prediction errors, tree-summed on the device (particle_Gibbs.jl:311)
-    const int64_t M = K * H * ny, ntile = (M + TILE - 1) / TILE;
-    double *d_yt, *d_tiles;
-    CK(h, dalloc(h, &d_yt, (size_t)H * ny, false));
-    CK(h, dalloc(h, &d_tiles, (size_t)ntile, false));
-    CK(h, dalloc(h, &d_sse, 1, false));
-    CK(h, cudaMemcpy(d_yt, y_test, (size_t)H * ny * 8, cudaMemcpyHostToDevice));
-    k_sqerr_tiles<<<(unsigned)ntile, TPB>>>(rd.Y, d_yt, M, H * ny, d_tiles);
-    k_tree_final<<<1, TPB>>>(d_tiles, ntile, d_sse);
-    CK(h, cudaGetLastError());
-  }
-  CK(h, cudaDeviceSynchronize());
-  if (d_sse) CK(h, cudaMemcpy(sum_sq_err, d_sse, 8, cudaMemcpyDeviceToHost));
-  cudaEventElapsedTime(&g_rollout_ms[0], ev[0], ev[1]);
-  cudaEventElapsedTime(&g_rollout_ms[1], ev[1], ev[2]);
-  for (auto& evt : ev) cudaEventDestroy(evt);
-  int st = 0;
-  CK(h, cudaMemcpy(&st, rd.status, 4, cudaMemcpyDeviceToHost));
-  if (st & PGB_STATUS_NOT_POSDEF) return set_err(nullptr, PGB_ERR_NOT_POSDEF, "a scenario's Q is not positive definite");
-  if (x0) CK(h, cudaMemcpy(x0, rd.x0, (size_t)K * nx * 8, cudaMemcpyDeviceToHost));
-  if (v) CK(h, cudaMemcpy(v, rd.v, (size_t)K * H * nx * 8, cudaMemcpyDeviceToHost));
-  if (e) CK(h, cudaMemcpy(e, rd.e, (size_t)K * H * ny * 8, cudaMemcpyDeviceToHost));
-  if (X) CK(h, cudaMemcpy(X, rd.X, (size_t)K * (H + 1) * nx * 8, cudaMemcpyDeviceToHost));
-  if (Y) CK(h, cudaMemcpy(Y, rd.Y, (size_t)K * H * ny * 8, cudaMemcpyDeviceToHost));
-  return PGB_OK;
-}
-
-extern "C" int pgb_rollout(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q,
-                           const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
-                           const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e,
-                           double* X, double* Y) {
-  return rollout_run(cfg, K, 0, H, A, Q, w_m1, x_m1, u_m1, C, Le, u_init, seed, k_offset, x0, v, e, X, Y, nullptr, nullptr);
-}
-
-extern "C" int pgb_test_prediction(const pgb_config* cfg, int64_t K, int64_t k_n, int64_t T_test, const double* A,
-                                   const double* Q, const double* w_m1, const double* x_m1, const double* u_m1,
-                                   const double* C, const double* Le, const double* u_test, const double* y_test,
-                                   uint64_t seed, double* x_sim, double* y_sim, double* mean_rmse) {
-  if (K < 1 || k_n < 1 || T_test < 1 || !y_test || !mean_rmse) return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
-  double sse = 0.0;
-  int rc = rollout_run(cfg, K * k_n, K, T_test, A, Q, w_m1, x_m1, u_m1, C, Le, u_test, seed, 0, nullptr, nullptr, nullptr,
-                       x_sim, y_sim, y_test, &sse);
-  if (rc) return rc;
-  *mean_rmse = std::sqrt(sse / (double)(K * k_n * T_test * cfg->n_y));
-  return PGB_OK;
-}
-
-extern "C" int pgb_rollout_last_ms(double* h2d_ms, double* kernel_ms) {
-  if (h2d_ms) *h2d_ms = g_rollout_ms[0];
-  if (kernel_ms) *kernel_ms = g_rollout_ms[1];
-  return PGB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// scenario screening for the greedy support-sub-sample search (optimal_control_Ipopt.jl:334-338, Altro.jl:496-500)
-// ------------------------------------------------------------------------------------------------
-// One warp per scenario, grid-stride: the scenario's H*n_y outputs are contiguous (coalesced 256 B per warp request);
-// the bounds (n_y x H column-major = the same element index) stay in L1.  HBM-bound: 8 B read per output value.
-__device__ __forceinline__ double hmax_take(double m, double h) {
-  return (h > m || (h == m && !signbit(h))) ? h : m;  // Julia's max on non-NaN values (0.0 above -0.0)
-}
-constexpr int SCREEN_U = 4;  // scenarios per warp iteration: independent loads in flight (the kernel is latency-bound otherwise)
-__global__ void __launch_bounds__(256) k_scenario_constraint_max(int64_t K, int64_t E, const double* __restrict__ Y,
-                                                                 const double* __restrict__ lo,
-                                                                 const double* __restrict__ hi,
-                                                                 double* __restrict__ h_max) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SCREEN_U; k0 < K;
-       k0 += nwarp * SCREEN_U) {
-    const double* y[SCREEN_U];
-    double m[SCREEN_U];
-    int nan[SCREEN_U];
-#pragma unroll
-    for (int u = 0; u < SCREEN_U; ++u) {
-      y[u] = Y + (k0 + u < K ? k0 + u : K - 1) * E;  // tail: re-read the last scenario, never written
-      m[u] = -INFINITY;
-      nan[u] = 0;
-    }
-#pragma unroll 2
-    for (int64_t e = lane; e < E; e += 32) {
-      const double a = __ldg(lo + e), b = __ldg(hi + e);
-      if (!isfinite(a) && !isfinite(b)) continue;  // column without a bound: its outputs are never read
-      double v[SCREEN_U];
-#pragma unroll
-      for (int u = 0; u < SCREEN_U; ++u) v[u] = y[u][e];
-#pragma unroll
-      for (int u = 0; u < SCREEN_U; ++u) {
-        if (isfinite(a)) { const double h = a - v[u]; if (isnan(h)) nan[u] = 1; else m[u] = hmax_take(m[u], h); }
-        if (isfinite(b)) { const double h = v[u] - b; if (isnan(h)) nan[u] = 1; else m[u] = hmax_take(m[u], h); }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-#pragma unroll
-      for (int u = 0; u < SCREEN_U; ++u) {
-        m[u] = hmax_take(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
-        nan[u] |= __shfl_xor_sync(0xffffffffu, nan[u], o);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < SCREEN_U; ++u)
-      if (lane == u && k0 + u < K) h_max[k0 + u] = nan[u] ? __longlong_as_double(0x7ff8000000000000ll) : m[u];
-  }
-}
-
-static float g_screen_ms[2] = {0.f, 0.f};  // device time of the last pgb_scenario_constraint_max: {H2D copies, kernel}
-
-static inline bool jl_isless(double a, double b) {  // Julia's isless on Float64
-  if (std::isnan(a)) return false;
-  if (std::isnan(b)) return true;
-  if (a == 0.0 && b == 0.0) return std::signbit(a) && !std::signbit(b);
-  return a < b;
-}
-
-extern "C" int pgb_scenario_constraint_max(int32_t device, int64_t K, int64_t H, int32_t n_y, const double* Y,
-                                           const double* y_min, const double* y_max, double* h_max, int64_t* order) {
-  if (!Y || !y_min || !y_max || !h_max || K < 1 || H < 1 || n_y < 1)
-    return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
-  const int64_t E = H * (int64_t)n_y;
-  int64_t n_fin = 0;
-  for (int64_t i = 0; i < E; ++i) n_fin += (std::isfinite(y_min[i]) ? 1 : 0) + (std::isfinite(y_max[i]) ? 1 : 0);
-  if (n_fin == 0)  // Julia: maximum of an empty collection throws (optimal_control_Ipopt.jl:336)
-    return set_err(nullptr, PGB_ERR_INVALID, "ArgumentError: no finite output bound: maximum over an empty collection");
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev <= 0)
-    return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s); pgopt_b200 has no CPU fallback",
-                   cudaGetErrorString(e));
-  pgb_handle tmp;  // only used as an allocation list / error sink
-  pgb_handle* h = &tmp;
-  h->cfg.device = device;
-  struct Cleanup {
-    pgb_handle* h;
-    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
-  } cleanup{h};
-  CK(h, cudaSetDevice(device));
-  double *d_Y = nullptr, *d_lo = nullptr, *d_hi = nullptr, *d_h = nullptr;
-  CK(h, dalloc(h, &d_Y, (size_t)(K * E)));
-  CK(h, dalloc(h, &d_lo, (size_t)E));
-  CK(h, dalloc(h, &d_hi, (size_t)E));
-  CK(h, dalloc(h, &d_h, (size_t)K));
-  cudaEvent_t ev[3];
-  for (auto& v : ev) CK(h, cudaEventCreate(&v));
-  struct EvCleanup {
-    cudaEvent_t* ev;
-    ~EvCleanup() { for (int i = 0; i < 3; ++i) cudaEventDestroy(ev[i]); }
-  } ev_cleanup{ev};
-  CK(h, cudaEventRecord(ev[0], 0));
-  CK(h, cudaMemcpy(d_Y, Y, (size_t)(K * E) * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(d_lo, y_min, (size_t)E * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaMemcpy(d_hi, y_max, (size_t)E * 8, cudaMemcpyHostToDevice));
-  CK(h, cudaEventRecord(ev[1], 0));
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int64_t want = (K + 8 * SCREEN_U - 1) / (8 * SCREEN_U);  // 8 warps x SCREEN_U scenarios per CTA iteration
-  const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 8);
-  k_scenario_constraint_max<<<grid, 256>>>(K, E, d_Y, d_lo, d_hi, d_h);
-  CK(h, cudaGetLastError());
-  CK(h, cudaEventRecord(ev[2], 0));
-  CK(h, cudaEventSynchronize(ev[2]));
-  cudaEventElapsedTime(&g_screen_ms[0], ev[0], ev[1]);
-  cudaEventElapsedTime(&g_screen_ms[1], ev[1], ev[2]);
-  CK(h, cudaMemcpy(h_max, d_h, (size_t)K * 8, cudaMemcpyDeviceToHost));
-  if (order) {  // sortperm(h_scenario_max; rev=true): stable, ties keep their original order; 1-based
-    for (int64_t k = 0; k < K; ++k) order[k] = k + 1;
-    std::stable_sort(order, order + K, [&](int64_t a, int64_t b) { return jl_isless(h_max[b - 1], h_max[a - 1]); });
-  }
-  return PGB_OK;
-}
-
-extern "C" int pgb_scenario_constraint_last_ms(double* h2d_ms, double* kernel_ms) {
-  if (h2d_ms) *h2d_ms = g_screen_ms[0];
-  if (kernel_ms) *kernel_ms = g_screen_ms[1];
-  return PGB_OK;
-}
-
-extern "C" int pgb_get_phase_cycles(pgb_handle* h, double* avg_cycles /*[16]*/, int32_t* n_ctas) {
-  NEED(h);
-  CK(h, cudaStreamSynchronize(h->stream));
-  const int g = h->fd.nc * h->pd.npc;
-  std::vector<long long> v((size_t)1024 * P_NPROF);
-  CK(h, cudaMemcpy(v.data(), h->pd.prof, v.size() * 8, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < P_NPROF; ++i) {
-    double s = 0;
-    for (int c = 0; c < g && c < 1024; ++c) s += (double)v[(size_t)c * P_NPROF + i];
-    avg_cycles[i] = g > 0 ? s / g : 0.0;
-  }
-  if (n_ctas) *n_ctas = g;
-  return PGB_OK;
-}
 extern "C" int pgb_set_mode(pgb_handle* h, int32_t persistent) {
   NEED(h);
-  h->persistent = persistent < 0 ? -1 : (persistent > 3 ? 3 : persistent);
+  h->persistent = persistent < 0 ? -1 : (persistent > 4 ? 4 : persistent);
   return PGB_OK;
 }
 extern "C" int pgb_timer_start(pgb_handle* h) {
@@ -1354,7 +719,7 @@ extern "C" int pgb_get_launch_count(pgb_handle* h, int64_t* n) {
 // ------------------------------------------------------------------------------------------------
 // test hooks
 // ------------------------------------------------------------------------------------------------
-extern "C" void pgb_test_force_fallback(int32_t on) { g_force_fallback = on; }
+extern "C" void pgb_test_force_fallback(int32_t on) { g_pgb_force_fallback = on; }
 
 __global__ void k_test_math(int fn, const double* __restrict__ x, double* __restrict__ y, int64_t n, uint64_t seed) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1430,15 +795,9 @@ __global__ void k_test_vmath(int fn, const double* __restrict__ x, double* __res
 
 extern "C" int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_t n) {
   if (!x || !y || n < 1) return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev <= 0) return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
-  pgb_handle tmp;
+  if (int rcd = pgb_require_device()) return rcd;
+  TmpHandle tmp;
   pgb_handle* h = &tmp;
-  struct Cleanup {
-    pgb_handle* h;
-    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
-  } cleanup{h};
   CK(h, cudaSetDevice(device));
   const bool pairs = (fn == 4 || fn == 14);
   const int64_t nout = pairs ? 2 * n : n;
@@ -1468,15 +827,9 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
 
 extern "C" int pgb_test_fp64_peak(int32_t device, double* tflops) {
   if (!tflops) return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev <= 0) return set_err(nullptr, PGB_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
-  pgb_handle tmp;
+  if (int rcd = pgb_require_device()) return rcd;
+  TmpHandle tmp;
   pgb_handle* h = &tmp;
-  struct Cleanup {
-    pgb_handle* h;
-    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
-  } cleanup{h};
   CK(h, cudaSetDevice(device));
   cudaDeviceProp prop;
   CK(h, cudaGetDeviceProperties(&prop, device));
@@ -1501,131 +854,5 @@ extern "C" int pgb_test_fp64_peak(int32_t device, double* tflops) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *tflops = best;
-  return PGB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// micro-benchmark of one elementwise phase in isolation (what a persistent phase can reach):
-// variant 0: y = exp(x - m) with per-CTA tree sums (the weight phase), 1: plain copy, 2: y = x / s
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) k_micro(int variant, const double* __restrict__ x, double* __restrict__ y,
-                                                  double* part, unsigned int* bar, int64_t N, int iters, int tpc) {
-  __shared__ double wpart[8][2];
-  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int c = blockIdx.x, nwt = 8 * tpc;
-  unsigned int target = 0;
-  for (int it = 0; it < iters; ++it) {
-    TreeAcc acc;
-    acc.init();
-    const double m = 0.25 + 1e-3 * it;
-    for (int j = 0; j < tpc; ++j) {
-      const int64_t base = ((int64_t)c * nwt + w * tpc + j) * 128 + lane * 4;
-      double a[4], v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = (base + i < N) ? x[base + i] : 0.0;
-      if (variant == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = __dsub_rn(a[i], m);
-        vexp<4>(a, v);
-      } else if (variant == 2) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = __ddiv_rn(a[i], m);
-      } else if (variant == 3) {  // Philox + Box-Muller for 4 outputs
-        pgb_u32x4 ctr[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          ctr[i].v[0] = (uint32_t)(base + i); ctr[i].v[1] = it; ctr[i].v[2] = 1; ctr[i].v[3] = 7;
-        }
-        vphilox<4>(ctr, 123u, 456u);
-        double z0[4], z1[4];
-        vnormal_pairs<4>(ctr, z0, z1);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = __dadd_rn(z0[i], __dadd_rn(z1[i], a[i]));
-      } else if (variant == 4) {  // two sincos per element (known-basis F)
-        double s1[4], c1[4], s2[4], c2[4];
-        vsincos<4>(a, s1, c1);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = __dmul_rn(a[i], 2.0);
-        vsincos<4>(a, s2, c2);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = __dadd_rn(c1[i], s2[i]);
-      } else if (variant == 5) {  // classify + maps + warp segmented scan (scan-local without the division)
-        double s1 = a[0], s2 = __dadd_rn(s1, a[1]), s3 = __dadd_rn(s2, a[2]), s4 = __dadd_rn(s3, a[3]);
-        double inc = s4;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          double t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc = __dadd_rn(t, inc);
-        }
-        double P = __dadd_rn(0.25 + 1e-3 * j, __dsub_rn(inc, s4));
-        double Pn = __shfl_down_sync(0xffffffffu, P, 1);
-        double qt[5] = {P, __dadd_rn(P, s1), __dadd_rn(P, s2), __dadd_rn(P, s3), Pn};
-        pgb_agg agg = pgb_classify4(a, qt);
-        pgb_agg total;
-        pgb_agg ex = warp_excl_scan_agg(agg, &total);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = a[i] + (double)(ex.f.c0 + total.f.c1 + ex.cnt);
-      } else if (variant == 6) {  // sampling-grid counts (5 per thread) on a synthetic table
-        __shared__ pgb_utable ut;
-        if (it == 0 && j == 0) {
-          if (tid == 0) pgb_utable_build(&ut, N - 1, 0.37);
-          __syncthreads();
-        }
-        int row = -1;
-        long long r = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r += pgb_utable_count_le_hint(&ut, __dmul_rn(a[i], 1e-6 * (double)(base + i)), &row);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = a[i] + (double)r;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = a[i];
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (base + i < N) y[base + i] = v[i];
-      acc.push(warp_tree_sum(tree4(v)));
-    }
-    if (lane == 0) wpart[w][0] = acc.result();
-    __syncthreads();
-    if (tid == 0) part[c] = tree8(wpart, 0);
-    grid_barrier(bar, target);
-  }
-}
-
-extern "C" int pgb_test_microbench(int32_t device, int32_t variant, int64_t N, int32_t iters, double* us_per_iter) {
-  pgb_handle tmp;
-  pgb_handle* h = &tmp;
-  struct Cleanup {
-    pgb_handle* h;
-    ~Cleanup() { for (void* p : h->allocs) cudaFree(p); }
-  } cleanup{h};
-  CK(h, cudaSetDevice(device));
-  double *x, *y, *part;
-  unsigned int* bar;
-  CK(h, dalloc(h, &x, (size_t)N));
-  CK(h, dalloc(h, &y, (size_t)N));
-  CK(h, dalloc(h, &part, 1024));
-  CK(h, dalloc(h, &bar, 4));
-  int tpc = 1;
-  const int nt = (int)((N + 1023) / 1024);
-  while ((nt + tpc - 1) / tpc > 256) tpc *= 2;
-  const int grid = (nt + tpc - 1) / tpc;
-  cudaEvent_t e0, e1;
-  CK(h, cudaEventCreate(&e0));
-  CK(h, cudaEventCreate(&e1));
-  for (int rep = 0; rep < 2; ++rep) {
-    CK(h, cudaMemset(bar, 0, 4));
-    void* args[] = {(void*)&variant, (void*)&x, (void*)&y, (void*)&part, (void*)&bar, (void*)&N, (void*)&iters, (void*)&tpc};
-    CK(h, cudaEventRecord(e0));
-    CK(h, cudaLaunchCooperativeKernel((const void*)k_micro, dim3(grid), dim3(256), args, 0, 0));
-    CK(h, cudaEventRecord(e1));
-    CK(h, cudaEventSynchronize(e1));
-  }
-  float ms = 0.f;
-  CK(h, cudaEventElapsedTime(&ms, e0, e1));
-  *us_per_iter = 1e3 * ms / iters;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   return PGB_OK;
 }

@@ -171,7 +171,7 @@ __device__ __forceinline__ InvDiv make_invdiv(double d) {
   iv.ok = (ad >= 0x1p-500) && (ad <= 0x1p500);
   return iv;
 }
-__device__ __noinline__ double ddiv_slow(double a, double d) { return __ddiv_rn(a, d); }
+static __device__ __noinline__ double ddiv_slow(double a, double d) { return __ddiv_rn(a, d); }
 __device__ __forceinline__ double div_inv(double a, const InvDiv& iv) {
   const double aa = fabs(a);
   if (iv.ok && aa >= 0x1p-500 && aa <= 0x1p500) {

@@ -54,7 +54,6 @@ struct FilterDev {
   const double *Z0, *Z, *Ures, *Uanc, *Ustar;  // injected: [nc][n_x*(N-1)], [nc][T][n_x*N], [nc][T], [nc][T], [nc]
   pgb_utable *utab_res, *utab_anc, *utab_star; // [nc][T], [nc][T], [nc]
   ScanWS main, side;
-  int ablate;  // timing experiments only (env PGB_ABLATE): see pgb_persist.cuh
 };
 
 // row of fd.xh that holds the particles of step t (0-based)
@@ -375,7 +374,7 @@ __global__ void __launch_bounds__(TPB) k_init(FilterDev fd, int first) {
 // ------------------------------------------------------------------------------------------
 // e = exp(lw - max), tile sums; last CTA: S1
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_weights(FilterDev fd) {
+static __global__ void __launch_bounds__(TPB) k_weights(FilterDev fd) {
   __shared__ double sm[NWARP + 1];
   __shared__ int sflag;
   const int chain = blockIdx.y, tile = blockIdx.x;
@@ -495,7 +494,7 @@ __global__ void __launch_bounds__(TPB) k_prep(FilterDev fd, int64_t t, int first
 }
 
 // waN ./= sum(waN) (:180) in place, then tile sums for the resampler's own normalisation (:19)
-__global__ void __launch_bounds__(TPB) k_norm(FilterDev fd) {
+static __global__ void __launch_bounds__(TPB) k_norm(FilterDev fd) {
   __shared__ double sm[NWARP + 1];
   __shared__ int sflag;
   const int chain = blockIdx.y, tile = blockIdx.x;
@@ -634,7 +633,7 @@ __global__ void __launch_bounds__(TPB) k_expand(FilterDev fd, ScanWS ws, const d
 // ------------------------------------------------------------------------------------------
 // sampling-grid tables for every step of the sweep (independent of the weights)
 // ------------------------------------------------------------------------------------------
-__global__ void k_build_utabs(FilterDev fd, int first) {
+static __global__ void k_build_utabs(FilterDev fd, int first) {
   const int chain = blockIdx.y;
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= fd.T) return;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128) k_stats_z(FilterDev fd, MniwDev md) {
 }
 
 // One CTA per output entry: Phi = zeta zeta', Psi = zeta z', Sigma = z z' as tree sums over t.
-__global__ void __launch_bounds__(TPB) k_stats(MniwDev md) {
+static __global__ void __launch_bounds__(TPB) k_stats(MniwDev md) {
   __shared__ double sm[NWARP + 1];
   const int chain = blockIdx.y;
   const int nx = md.n_x, np = md.n_phi;
@@ -173,7 +173,7 @@ __device__ inline int chain_params_from_Q(const double* Q, int n, double* Lq16, 
   for (int i = 0; i < 16; ++i) Lq16[i] = (i < n * n) ? L[i] : 0.0;
   return 0;
 }
-__global__ void k_chain_params(int chain, int n_x, const double* Q, double* Lq, double* c0, int* status) {
+static __global__ void k_chain_params(int chain, int n_x, const double* Q, double* Lq, double* c0, int* status) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   if (chain_params_from_Q(Q + (int64_t)chain * n_x * n_x, n_x, Lq + chain * 16, c0 + chain))
     atomicOr(&status[chain], 16);
@@ -257,7 +257,7 @@ __device__ inline void cta_chol_solve(const double* L, int n, double* B, int nrh
 }
 
 // MNIW_sample + refresh of the chain parameters used by the next sweep.  One CTA per chain.
-__global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md) {
+static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md) {
   __shared__ int s_fail;
   __shared__ double s_small[8][16];  // covM, Lc, S, B, LB, Wm, Qn, Lq
   const int chain = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;

@@ -403,12 +403,7 @@ PGB_DEV_HELPER void emit_offspring4(const FilterDev& fd, const EmitCtx<NX>& ec, 
   constexpr int NP = (NX + 1) / 2;
   const int64_t N = fd.N;
   double z[4][2 * NP];
-  if (fd.ablate & 4) {  // timing experiment: no Philox / Box-Muller
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int d = 0; d < 2 * NP; ++d) z[k][d] = 0.25 * (double)(jj[k] & 7);
-  } else if (fd.philox) {
+  if (fd.philox) {
     pgb_u32x4 ctr[4 * NP];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -445,7 +440,7 @@ PGB_DEV_HELPER void emit_offspring4(const FilterDev& fd, const EmitCtx<NX>& ec, 
       for (int e = 0; e <= d; ++e) acc = __fma_rn(ec.Lq[d + NX * e], z[k][e], acc);
       x[d] = __dadd_rn(F[k][d], acc);
     }
-    double lw = (fd.ablate & 8) ? -x[0] * x[0] : log_weight_iv<NX>(fd, x, ec.yt, ec.ivR);
+    double lw = log_weight_iv<NX>(fd, x, ec.yt, ec.ivR);
     if (act[k]) {
       ec.at[jj[k]] = a0[k];
 #pragma unroll
@@ -558,10 +553,7 @@ __device__ __forceinline__ void p_consume_by_output(const FilterDev& fd, const E
   const int64_t base = (int64_t)tile * TILE + (int64_t)tid * IPT;
   int64_t rr[5];
   int64_t zero_upto = 0;
-  if (base < N && (fd.ablate & 16)) {  // timing experiment: one offspring per particle, no grid counts
-#pragma unroll
-    for (int i = 0; i < 5; ++i) rr[i] = (base + i < M) ? base + i : M;
-  } else if (base < N) {
+  if (base < N) {
     int row = -1;
     rr[0] = pgb_utable_count_le_hint(ut, q[0], &row);
     if (base == 0) {
@@ -713,12 +705,16 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
   }
   const bool lead = (o == 0);  // one designated CTA per chain for the scalar bookkeeping
 #define P_FOR_BLOCKS for (int vi = 0, c = o; c < nb; ++vi, c += npc)
-  // section timers (thread 0 of every CTA; SM clock): see pgb_get_phase_cycles
+  // section timers (thread 0 of every CTA; SM clock) exist only in -DPGB_EXPERIMENT builds, never in the shipped library
+#ifdef PGB_EXPERIMENT
   long long tacc[P_NPROF];
 #pragma unroll
   for (int i = 0; i < P_NPROF; ++i) tacc[i] = 0;
   long long tlast = clock64();
 #define P_TICK(idx) do { if (tid == 0) { long long now_ = clock64(); tacc[idx] += now_ - tlast; tlast = now_; } } while (0)
+#else
+#define P_TICK(idx) do { } while (0)
+#endif
   double* pe = pd.pe + (int64_t)chain * nb;
   double* pw = pd.pw + (int64_t)chain * nb;
   double* pa = pd.pa + (int64_t)chain * nb;
@@ -856,21 +852,14 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
           for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int d = 0; d < NX; ++d) x[i][d] = live[i] ? xp[(int64_t)d * N + base + i] : 0.0;
-          if (fd.ablate & 1) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int d = 0; d < NX; ++d) F[i][d] = x[i][d];
-          } else {
-            eval_F4<NX>(fd, A_sm, x, up, F);
-          }
+          eval_F4<NX>(fd, A_sm, x, up, F);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (live[i]) {
 #pragma unroll
               for (int d = 0; d < NX; ++d) Fb[(int64_t)d * N + base + i] = F[i][d];
             }
-          if (anc && !(fd.ablate & 2)) {
+          if (anc) {
             double ea[4], pv[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -1123,10 +1112,12 @@ k_sweep_persistent(const __grid_constant__ FilterDev fd, const __grid_constant__
     }
     P_TICK(13);
   }
+#ifdef PGB_EXPERIMENT
   if (pd.prof && tid == 0) {
 #pragma unroll
     for (int i = 0; i < P_NPROF; ++i) pd.prof[(int64_t)blockIdx.x * P_NPROF + i] = tacc[i];
   }
+#endif
 #undef P_TICK
 #undef P_FOR_BLOCKS
 }

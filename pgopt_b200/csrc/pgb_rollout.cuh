@@ -818,7 +818,7 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
 // ---------------------------------------------------------------------------------------------------------
 // mean_rmse of test_prediction (Julia/src/particle_Gibbs.jl:311): sum over the column-major (n_y, T_test, K*k_n) array
 // of (y_sim - y_test)^2 as the balanced tree the oracle defines (tile sums, then the tree over the tiles).
-__global__ void __launch_bounds__(TPB) k_sqerr_tiles(const double* __restrict__ Y, const double* __restrict__ y_test,
+static __global__ void __launch_bounds__(TPB) k_sqerr_tiles(const double* __restrict__ Y, const double* __restrict__ y_test,
                                                       int64_t M, int64_t per, double* __restrict__ tile_sums) {
   __shared__ double sm[NWARP + 1];
   const int64_t base = (int64_t)blockIdx.x * TILE + (int64_t)threadIdx.x * IPT;
@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(TPB) k_sqerr_tiles(const double* __restrict__ 
   const double s = block_tree_sum(tree4(v), sm);
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
 }
-__global__ void __launch_bounds__(TPB) k_tree_final(const double* __restrict__ p, int64_t n, double* __restrict__ out) {
+static __global__ void __launch_bounds__(TPB) k_tree_final(const double* __restrict__ p, int64_t n, double* __restrict__ out) {
   __shared__ double sm[NWARP + 1];
   const double s = block_tree_sum_array(p, n, sm);
   if (threadIdx.x == 0) *out = s;

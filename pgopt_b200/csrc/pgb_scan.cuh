@@ -60,7 +60,7 @@ __device__ __forceinline__ void finalize_tile_sums(const double* __restrict__ ts
 }
 
 // Stand-alone tile-sum kernel (used by the stand-alone resampling entry point and the star draw).
-__global__ void __launch_bounds__(TPB) k_tile_sums(ScanWS ws, const double* __restrict__ v) {
+static __global__ void __launch_bounds__(TPB) k_tile_sums(ScanWS ws, const double* __restrict__ v) {
   __shared__ double sm[NWARP + 1];
   __shared__ int sflag;
   const int chain = blockIdx.y, tile = blockIdx.x;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(TPB) k_tile_sums(ScanWS ws, const double* __re
   }
 }
 
-__global__ void __launch_bounds__(TPB) k_scan_local(ScanWS ws, const double* __restrict__ v, int* __restrict__ status) {
+static __global__ void __launch_bounds__(TPB) k_scan_local(ScanWS ws, const double* __restrict__ v, int* __restrict__ status) {
   __shared__ double sm[NWARP + 1];
   __shared__ pgb_agg smagg[NWARP + 1];
   __shared__ double sP[TPB];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(TPB) k_scan_local(ScanWS ws, const double* __r
 
 constexpr int RESOLVE_SMEM_RECS = 512;
 
-__global__ void __launch_bounds__(TPB) k_resolve(ScanWS ws, int force_fallback) {
+static __global__ void __launch_bounds__(TPB) k_resolve(ScanWS ws, int force_fallback) {
   __shared__ pgb_agg smagg[NWARP + 1];
   __shared__ pgb_map s_f[RESOLVE_SMEM_RECS];
   __shared__ double s_W[RESOLVE_SMEM_RECS][4];
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(TPB) k_resolve(ScanWS ws, int force_fallback) 
 // Serial exact walk (one warp per chain).  Runs only if the chain's flag is raised.
 // Normal case (flag clear): merge the consumer's pending status bits and return.  Flag raised:
 // discard what the failed pass produced (pending status, running max) and walk serially.
-__global__ void __launch_bounds__(32) k_seq_exact(ScanWS ws, const double* __restrict__ v, int* __restrict__ status,
+static __global__ void __launch_bounds__(32) k_seq_exact(ScanWS ws, const double* __restrict__ v, int* __restrict__ status,
                                                   unsigned long long* __restrict__ maxkey_reset) {
   const int chain = blockIdx.y, lane = threadIdx.x;
   if ((ws.flag[chain] & 1) == 0) {

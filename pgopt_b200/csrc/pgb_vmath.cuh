@@ -217,7 +217,7 @@ __device__ __forceinline__ void vphilox(pgb_u32x4 (&ctr)[K], uint32_t k0, uint32
   vphilox_wide<K>(ctr, k0, k1);
 #endif
 }
-__device__ __noinline__ void normal_pair_noinline(pgb_u32x4 bits, double* z0, double* z1) { pgb_normal_pair(bits, z0, z1); }
+static __device__ __noinline__ void normal_pair_noinline(pgb_u32x4 bits, double* z0, double* z1) { pgb_normal_pair(bits, z0, z1); }
 template <int K>
 __device__ __forceinline__ void vnormal_pairs(const pgb_u32x4 (&bits)[K], double (&z0)[K], double (&z1)[K]) {
 #if PGB_SMALL_CODE

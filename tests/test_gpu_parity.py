@@ -191,7 +191,7 @@ def _assert_same(name, a, b):
         name, bad.sum(), bad.size, np.argwhere(bad)[0], a[tuple(np.argwhere(bad)[0])], b[tuple(np.argwhere(bad)[0])])
 
 
-@pytest.mark.parametrize("persistent", [2, 1, 0])
+@pytest.mark.parametrize("persistent", [4, 1, 0])
 @pytest.mark.parametrize("model", ["known", "hilbert"])
 @pytest.mark.parametrize("first", [False, True])
 @pytest.mark.parametrize("N,T", [(30, 120), (1500, 25), (9000, 12)])
@@ -333,7 +333,7 @@ def test_small_n_kernel_matches_tile_kernel_on_whole_sampler():
         _assert_same("w[%d]" % kk, outs[0][2][0, kk], ref["w"][kk])
 
 
-@pytest.mark.parametrize("persistent", [2, 1, 0])
+@pytest.mark.parametrize("persistent", [4, 1, 0])
 def test_sweep_with_degenerate_weights(persistent):
     """A very sharp likelihood makes a handful of particles own almost all offspring (the cooperative
     heavy-particle expansion of the persistent kernel); results must not change."""
@@ -358,7 +358,7 @@ def test_sweep_with_degenerate_weights(persistent):
     _assert_same("w", w, ref["w"])
 
 
-@pytest.mark.parametrize("persistent", [2, 1, 0])
+@pytest.mark.parametrize("persistent", [4, 1, 0])
 def test_sweep_with_underflowing_ancestor_weights(persistent):
     """An implausible conditioned trajectory makes every ancestor weight underflow: waN ./ sum(waN) is NaN
     (particle_Gibbs.jl:180).  The reference carries on silently (index 1); so do we, bit for bit, and the
@@ -411,7 +411,7 @@ def test_ancestor_draw_shortcut_equals_exact_scan(model, N, T):
     assert hist[1] == 2 * T - 1 and hist[0] < hist[1]  # the shortcut really skipped exact scans
 
 
-@pytest.mark.parametrize("persistent", [2, 1, 0])
+@pytest.mark.parametrize("persistent", [4, 1, 0])
 @pytest.mark.parametrize("N", [300, 5000])
 def test_sweep_forced_fallback_is_still_exact(persistent, N):
     basis, om, A = _models()["known"]
@@ -510,10 +510,12 @@ def test_batched_chains_match_single_chains():
 
 # ------------------------------------------------------------------------------------------ rollout
 @pytest.fixture(params=["warp", "cta"])
-def rollout_kernel(request, monkeypatch):
-    """pgb_rollout picks the warp-per-scenario kernel by default; PGB_ROLLOUT_KERNEL forces either one."""
-    monkeypatch.setenv("PGB_ROLLOUT_KERNEL", request.param)
-    return request.param
+def rollout_kernel(request):
+    """pgb_rollout picks the warp-per-scenario kernel whenever A_k fits 32 lanes (n_phi <= 640); the test hook
+    pgb_test_rollout_kernel forces the CTA-per-scenario kernel (production: n_phi > 640) on the same shapes."""
+    _lib.lib().pgb_test_rollout_kernel(1 if request.param == "warp" else 0)
+    yield request.param
+    _lib.lib().pgb_test_rollout_kernel(-1)
 
 
 @pytest.mark.parametrize("model", ["known", "hilbert4"])
@@ -845,3 +847,33 @@ def test_scenario_constraint_max_full_size_properties():
     expect = np.maximum((2.0 - Y[:, 20:26, 0]).max(axis=1), (Y[:, 30:, 0] - 6.0).max(axis=1))
     assert np.array_equal(h, expect)
     assert np.array_equal(np.sort(order), np.arange(1, K + 1)) and np.all(np.diff(h[order - 1]) <= 0)
+
+
+# ------------------------------------------------------------------------------------------ reference-held vectors
+import _reffix as RF  # noqa: E402
+
+
+@pytest.mark.skipif(not RF.fixtures(), reason=RF.SKIP_REASON)
+@pytest.mark.parametrize("path", RF.fixtures() or ["-"])
+def test_gpu_against_reference_held_vectors(path):
+    """The CUDA path fed the streams the unmodified Julia reference consumed (julia/make_fixtures.jl): final particles
+    and weights of every sweep and the traced trajectory within 1e-10 relative of the real Julia run."""
+    g = RF.load(path)
+    _, hil = RF.oracle_model(g)
+    basis = pg.KnownBasisVB() if hil is None else pg.HilbertGPBasis(hil[0], hil[1])
+    N, T, K = int(RF.scalar(g, "N")), int(RF.scalar(g, "T")), int(RF.scalar(g, "K"))
+    xp = np.zeros((basis.n_x, T))
+    with pg.ParticleGibbsEngine(basis, 1, N, T) as e:
+        e.set_data(g["u"], g["y"])
+        e.set_measurement(pg.LinearMeasurement(g["C"]), RF.scalar(g, "R"))
+        e.set_init_dist(pg.MvNormal(np.ravel(g["x0_mean"]), g["x0_chol"] @ g["x0_chol"].T))
+        for k in range(1, K + 1):
+            s, A, Q = RF.sweep_inputs(g, k)
+            e.set_state(A, Q, xp, k)
+            e.set_rng_injected(s["Z0"], s["Ures"], s["Z"], s["Uanc"], s["Ustar"])
+            e.sweep_filter()
+            smp = e.get_sample()
+            np.testing.assert_allclose(smp.w_m1, np.ravel(g["w_m1_%d" % k]), rtol=1e-9, atol=1e-300)
+            np.testing.assert_allclose(smp.x_m1, g["x_m1_%d" % k], rtol=1e-10, atol=1e-12)
+            xp = e.get_state()[2]
+    np.testing.assert_allclose(xp, g["x_prim_final"], rtol=1e-10, atol=1e-12)

@@ -202,7 +202,9 @@ def _prediction_case(seed=3, K=4, k_n=3, T_test=25, N=30):
 def test_prediction_follows_reference_structure():
     """test_prediction (particle_Gibbs.jl:253-314) restated as one scenario per (model, repetition): simulation
     (k, kn) must equal a single-scenario rollout of model k over the test input with stream id k + K*kn, laid out in
-    the order of the reference's reshape (:301-302), and mean_rmse must be the printed quantity (:311)."""
+    the order of the reference's reshape (:301-302), and mean_rmse must be the TIME-MATCHED RMSE.  (Not a literal
+    transcription of :311: Julia subtracts repeat(y_test', 1, 1, K*k_n), shape (T_test, n_y, S), which for n_y = 1
+    broadcasts to T_test x T_test cross terms and for n_y > 1 throws; the MATLAB twin and this library match in time.)"""
     om, K, k_n, T_test, N, A, Q, w, x, um, u_test, y_test = _prediction_case()
     Cm = [[1.0, 0.0]]
     out = O.test_prediction(om, K, k_n, T_test, N, A, Q, w, x, um, Cm, [[0.1]], u_test, y_test, seed=9)
@@ -214,7 +216,7 @@ def test_prediction_follows_reference_structure():
                             u_test, seed=9, k_offset=s)
             np.testing.assert_array_equal(out["x_sim"][s], one["X"][0])
             np.testing.assert_array_equal(out["y_sim"][s], one["Y"][0])
-    # reference: sqrt(mean((y_test_sim .- repeat(y_test', 1, 1, K*k_n)).^2)) over the (n_y, T_test, K*k_n) array
+    # intended quantity: sqrt(mean((y_test_sim .- y_test).^2)) over the (n_y, T_test, K*k_n) array, matched in time
     y_sim = np.transpose(out["y_sim"], (2, 1, 0))
     ref = np.sqrt(np.mean((y_sim - y_test[:, :, None]) ** 2))
     assert abs(out["mean_rmse"] - ref) <= 1e-14 * ref
