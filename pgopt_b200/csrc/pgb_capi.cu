@@ -435,6 +435,8 @@ static int run_filter(pgb_handle* h) {
     mode = (mode == 3) ? 1 : 4;
   }
   if (mode == 4) {  // a configuration that does not fit falls through to the tile kernels
+    rc = pgb_run_filter_v2(h);
+    if (rc >= 0) return rc;
     mode = 1;
   }
   if (mode >= 1) {

@@ -294,6 +294,15 @@ PGB_HD_HELPER int64_t pgb_utable_count_le(const pgb_utable* T, double q) {
   }
   return pgb_utable_count_in_row(T, lo, q);
 }
+// last row whose first grid point is <= q (0 when there is none): binary search, the starting hint of a lane's queries
+PGB_HD int pgb_utable_row_of(const pgb_utable* T, double q) {
+  int lo = 0, hi = T->nrows - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (T->u0[mid] <= q) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
 // same, for a non-decreasing sequence of queries: *row is the row found for the previous query
 PGB_HD_HELPER int64_t pgb_utable_count_le_hint(const pgb_utable* T, double q, int* row) {
   if (q != q) return T->M;

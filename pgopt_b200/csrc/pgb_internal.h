@@ -16,6 +16,7 @@
 #include "../../include/pgopt_b200.h"
 #include "pgb_mniw.cuh"
 #include "pgb_persist.cuh"
+#include "pgb_v2_types.h"
 
 struct pgb_samples;
 
@@ -47,6 +48,7 @@ struct pgb_handle {
   // phase, 3 the warp / one-CTA kernels
   int persistent = -1;
   pgb::PersistDev pd;
+  pgb::V2Dev v2 = {};
   int num_sms = 0;
   // measurement
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
