@@ -20,6 +20,7 @@
  */
 #ifndef PGOPT_B200_H
 #define PGOPT_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -199,6 +200,52 @@ int pgb_scenario_constraint_last_ms(double* h2d_ms, double* kernel_ms);
 /* Device-side time (CUDA events, ms) of the last pgb_rollout / pgb_test_prediction call of this process: allocation + host-to-device copies
  * of the inputs, and the rollout kernel itself. */
 int pgb_rollout_last_ms(double* h2d_ms, double* kernel_ms);
+
+/* The same with the reference's x_vec_0 / v_vec / e_vec keyword arguments (optimal_control_Ipopt.jl:37, :48, :67, :77): a
+ * non-NULL x0_in[K][n_x] / v_in[K][H][n_x] / e_in[K][H][n_y] is used instead of the corresponding draw — the re-entry of
+ * the pre-solve step (:88-112) and the route for identical-stream parity runs fed from Julia.  With x0_in the arguments
+ * w_m1 / x_m1 / u_m1 may be NULL; with x0_in and v_in also Q.  Supplied arrays are echoed into x0 / v / e. */
+int pgb_rollout_supplied(const pgb_config* cfg, int64_t K, int64_t H, const double* A, const double* Q,
+                         const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
+                         const double* u_init, uint64_t seed, uint32_t k_offset, const double* x0_in, const double* v_in,
+                         const double* e_in, double* x0, double* v, double* e, double* X, double* Y);
+
+/* ---- device-resident pipeline: sampler -> samples -> rollout -> screening --------------------------------------
+ * The reference reads PG_samples[k].A in place (optimal_control_Ipopt.jl:47-64).  A pgb_samples set keeps K PG_sample
+ * records (PGopt.jl:23-29) and the scenario arrays of its last rollout in device memory, allocated once. */
+typedef struct pgb_samples pgb_samples;
+/* cfg: device, model, N (particles per sample); K: capacity = number of scenarios */
+int pgb_samples_create(pgb_samples** out, const pgb_config* cfg, int64_t K);
+void pgb_samples_destroy(pgb_samples* s);
+const char* pgb_samples_last_error(const pgb_samples* s);
+/* host <-> device for samples [k0, k0+n); layouts of pgb_rollout; NULL pointers are skipped */
+int pgb_samples_set(pgb_samples* s, int64_t k0, int64_t n, const double* A, const double* Q, const double* w_m1,
+                    const double* x_m1, const double* u_m1);
+int pgb_samples_get(pgb_samples* s, int64_t k0, int64_t n, double* A, double* Q, double* w_m1, double* x_m1,
+                    double* u_m1);
+/* slot k <- the current PG_sample of `chain` of handle h (same device), device to device (particle_Gibbs.jl:204-208) */
+int pgb_samples_store(pgb_samples* s, int64_t k, pgb_handle* h, int32_t chain);
+/* pgb_particle_gibbs with the kept samples left on the device: chain c, sample k -> slot c*K + k of `out` */
+int pgb_particle_gibbs_dev(pgb_handle* h, int64_t K, int64_t K_b, int64_t k_d, pgb_samples* out);
+/* x_T[k] = x_m1[:, star_k] with star_k = systematic_resampling(w_m1, 1) (optimal_control_Ipopt.jl:58-59), drawn where
+ * the sample lives from Philox stream (seed, k_offset + k) — the stream pgb_rollout uses for the same draw; a later
+ * pgb_rollout_dev with the same (seed, k_offset) reuses it.  x_T (host, may be NULL): [K][n_x]. */
+int pgb_samples_draw_xT(pgb_samples* s, uint64_t seed, uint32_t k_offset, double* x_T);
+/* pgb_rollout_supplied on the resident samples (scenario k = sample k); results stay on the device.  x0_in / v_in / e_in
+ * are host arrays or NULL; reuse bits 1 / 2 / 4 keep the x_vec_0 / v_vec / e_vec of the previous rollout of this set
+ * (same H) — the pre-solve re-entry with a new u_init (optimal_control_Ipopt.jl:88-125) without moving anything. */
+int pgb_rollout_dev(pgb_samples* s, int64_t H, const double* C, const double* Le, const double* u_init, uint64_t seed,
+                    uint32_t k_offset, int32_t reuse, const double* x0_in, const double* v_in, const double* e_in);
+/* scenario arrays of the last pgb_rollout_dev -> host; any pointer may be NULL; layouts of pgb_rollout */
+int pgb_scenarios_get(pgb_samples* s, double* x0, double* v, double* e, double* X, double* Y);
+/* pgb_scenario_constraint_max on the Y of the last pgb_rollout_dev, read where the rollout left it */
+int pgb_scenario_constraint_max_dev(pgb_samples* s, const double* y_min, const double* y_max, double* h_max,
+                                    int64_t* order);
+/* device time (CUDA events, ms) of the last rollout kernel / screening kernel / input upload of this set */
+int pgb_samples_last_ms(pgb_samples* s, double* rollout_kernel_ms, double* screening_kernel_ms, double* upload_ms);
+/* page-locked host memory for the caller's I/O arrays (NULL on failure) */
+void* pgb_host_alloc(size_t bytes);
+void pgb_host_free(void* p);
 
 /* ---- test hooks (not part of the drop-in surface) ---------------------------------------------
  * pgb_test_force_fallback(1) makes every exact scan take the serial-walk fallback path, (2) makes the ancestor

@@ -561,14 +561,24 @@ int orc_particle_gibbs(const orc_model* m, int64_t N, int64_t T, const double* u
  * 2 (v, j = step*npairs+p), 3 (e). */
 static int rollout_impl(const orc_model* m, int64_t K, int64_t n_models, int64_t H, int64_t N, const double* A,
                         const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
-                        const double* Le, const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v,
-                        double* e, double* X, double* Y);
+                        const double* Le, const double* u_init, uint64_t seed, uint32_t k_offset, const double* x0_in,
+                        const double* v_in, const double* e_in, double* x0, double* v, double* e, double* X, double* Y);
 
 int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const double* A, const double* Q,
                 const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
                 const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v, double* e, double* X,
                 double* Y) {
-  return rollout_impl(m, K, 0, H, N, A, Q, w_m1, x_m1, u_m1, C, Le, u_init, seed, k_offset, x0, v, e, X, Y);
+  return rollout_impl(m, K, 0, H, N, A, Q, w_m1, x_m1, u_m1, C, Le, u_init, seed, k_offset, NULL, NULL, NULL, x0, v, e, X, Y);
+}
+
+/* The same with the x_vec_0 / v_vec / e_vec keyword arguments of solve_PG_OCP_Ipopt (optimal_control_Ipopt.jl:37):
+ * `if x_vec_0 === nothing` (:48), `if v_vec === nothing` (:67), `if e_vec === nothing` (:77) — a supplied array replaces
+ * the draw, everything else (:114-125) is unchanged.  This is the second entry of the pre-solve step (:88-112). */
+int orc_rollout_supplied(const orc_model* m, int64_t K, int64_t H, int64_t N, const double* A, const double* Q,
+                         const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
+                         const double* u_init, uint64_t seed, uint32_t k_offset, const double* x0_in, const double* v_in,
+                         const double* e_in, double* x0, double* v, double* e, double* X, double* Y) {
+  return rollout_impl(m, K, 0, H, N, A, Q, w_m1, x_m1, u_m1, C, Le, u_init, seed, k_offset, x0_in, v_in, e_in, x0, v, e, X, Y);
 }
 
 /* test_prediction (particle_Gibbs.jl:253-314): every one of the K models is simulated k_n times over the test
@@ -589,7 +599,7 @@ int orc_test_prediction(const orc_model* m, int64_t K, int64_t k_n, int64_t T_te
                         const double* Le, const double* u_test, const double* y_test, uint64_t seed, double* x_sim,
                         double* y_sim, double* mean_rmse) {
   const int64_t S = K * k_n, M = S * T_test * m->n_y;
-  int st = rollout_impl(m, S, K, T_test, N, A, Q, w_m1, x_m1, u_m1, C, Le, u_test, seed, 0, NULL, NULL, NULL, x_sim, y_sim);
+  int st = rollout_impl(m, S, K, T_test, N, A, Q, w_m1, x_m1, u_m1, C, Le, u_test, seed, 0, NULL, NULL, NULL, NULL, NULL, NULL, x_sim, y_sim);
   double* sq = (double*)malloc(sizeof(double) * (size_t)M);
   for (int64_t s2 = 0; s2 < S; ++s2)
     for (int64_t t = 0; t < T_test; ++t)
@@ -605,8 +615,8 @@ int orc_test_prediction(const orc_model* m, int64_t K, int64_t k_n, int64_t T_te
 
 static int rollout_impl(const orc_model* m, int64_t K, int64_t n_models, int64_t H, int64_t N, const double* A,
                         const double* Q, const double* w_m1, const double* x_m1, const double* u_m1, const double* C,
-                        const double* Le, const double* u_init, uint64_t seed, uint32_t k_offset, double* x0, double* v,
-                        double* e, double* X, double* Y) {
+                        const double* Le, const double* u_init, uint64_t seed, uint32_t k_offset, const double* x0_in,
+                        const double* v_in, const double* e_in, double* x0, double* v, double* e, double* X, double* Y) {
   const int n_x = m->n_x, n_u = m->n_u, n_y = m->n_y, n_phi = m->n_phi;
   int status = 0;
   double* phi_tmp = (double*)malloc(sizeof(double) * (size_t)n_phi);
@@ -624,34 +634,48 @@ static int rollout_impl(const orc_model* m, int64_t K, int64_t n_models, int64_t
     s.philox = 1;
     s.seed = seed;
     s.chain = k_offset + (uint32_t)k; /* scenario id: a shard of the K scenarios keeps its global stream */
-    memcpy(Lq, &Q[km * n_x * n_x], sizeof(double) * (size_t)(n_x * n_x));
-    if (orc_cholesky_lower(Lq, n_x)) { status |= 16; break; }
-    /* star = systematic_resampling(w_m1, 1); x_m1 = x_m1[:, star]   (:58-59) */
-    int64_t star;
-    double us = stream_uniform(&s, PGB_STREAM_ROLL, 0, 0);
-    status |= orc_systematic_resampling(&w_m1[km * N], N, 1, us, &star);
-    if (star < 1) star = 1;
-    /* x0 = f(x_m1, u_m1) + rand(mvn)   (:62) */
-    eval_f_blocked(m, Ak, &x_m1[(km * N + (star - 1)) * n_x], &u_m1[km * n_u], phi_tmp, f);
-    stream_normals(&s, PGB_STREAM_ROLL, 0, 1, 0, n_x, z);
-    for (int d = 0; d < n_x; ++d) {
-      double acc = 0.0;
-      for (int e2 = 0; e2 <= d; ++e2) acc = fma(Lq[d + n_x * e2], z[e2], acc);
-      x0[k * n_x + d] = f[d] + acc;
-      X[(k * (H + 1) + 0) * n_x + d] = x0[k * n_x + d];
+    if (!(x0_in && v_in)) { /* Q is only used by the draws (:55, :71) */
+      memcpy(Lq, &Q[km * n_x * n_x], sizeof(double) * (size_t)(n_x * n_x));
+      if (orc_cholesky_lower(Lq, n_x)) { status |= 16; break; }
     }
-    for (int64_t t = 0; t < H; ++t) { /* v_vec[:, :, k] = rand(mvn_v, H)  (:72) */
-      stream_normals(&s, PGB_STREAM_ROLL, 0, 2, t, n_x, z);
+    if (x0_in) { /* :48 */
+      for (int d = 0; d < n_x; ++d) X[(k * (H + 1) + 0) * n_x + d] = x0[k * n_x + d] = x0_in[k * n_x + d];
+    } else {
+      /* star = systematic_resampling(w_m1, 1); x_m1 = x_m1[:, star]   (:58-59) */
+      int64_t star;
+      double us = stream_uniform(&s, PGB_STREAM_ROLL, 0, 0);
+      status |= orc_systematic_resampling(&w_m1[km * N], N, 1, us, &star);
+      if (star < 1) star = 1;
+      /* x0 = f(x_m1, u_m1) + rand(mvn)   (:62) */
+      eval_f_blocked(m, Ak, &x_m1[(km * N + (star - 1)) * n_x], &u_m1[km * n_u], phi_tmp, f);
+      stream_normals(&s, PGB_STREAM_ROLL, 0, 1, 0, n_x, z);
       for (int d = 0; d < n_x; ++d) {
         double acc = 0.0;
         for (int e2 = 0; e2 <= d; ++e2) acc = fma(Lq[d + n_x * e2], z[e2], acc);
-        v[(k * H + t) * n_x + d] = acc;
+        x0[k * n_x + d] = f[d] + acc;
+        X[(k * (H + 1) + 0) * n_x + d] = x0[k * n_x + d];
       }
-      stream_normals(&s, PGB_STREAM_ROLL, 0, 3, t, n_y, z); /* e_vec (:81) */
-      for (int o = 0; o < n_y; ++o) {
-        double acc = 0.0;
-        for (int e2 = 0; e2 <= o; ++e2) acc = fma(Lr[o + n_y * e2], z[e2], acc);
-        e[(k * H + t) * n_y + o] = acc;
+    }
+    for (int64_t t = 0; t < H; ++t) {
+      if (v_in) { /* :67 */
+        for (int d = 0; d < n_x; ++d) v[(k * H + t) * n_x + d] = v_in[(k * H + t) * n_x + d];
+      } else { /* v_vec[:, :, k] = rand(mvn_v, H)  (:72) */
+        stream_normals(&s, PGB_STREAM_ROLL, 0, 2, t, n_x, z);
+        for (int d = 0; d < n_x; ++d) {
+          double acc = 0.0;
+          for (int e2 = 0; e2 <= d; ++e2) acc = fma(Lq[d + n_x * e2], z[e2], acc);
+          v[(k * H + t) * n_x + d] = acc;
+        }
+      }
+      if (e_in) { /* :77 */
+        for (int o = 0; o < n_y; ++o) e[(k * H + t) * n_y + o] = e_in[(k * H + t) * n_y + o];
+      } else {
+        stream_normals(&s, PGB_STREAM_ROLL, 0, 3, t, n_y, z); /* e_vec (:81) */
+        for (int o = 0; o < n_y; ++o) {
+          double acc = 0.0;
+          for (int e2 = 0; e2 <= o; ++e2) acc = fma(Lr[o + n_y * e2], z[e2], acc);
+          e[(k * H + t) * n_y + o] = acc;
+        }
       }
     }
     for (int64_t t = 0; t < H; ++t) { /* :121-122 */

@@ -112,6 +112,13 @@ int orc_rollout(const orc_model* m, int64_t K, int64_t H, int64_t N, const doubl
                 double* v /*K x H x n_x*/,
                 double* e /*K x H x n_y*/, double* X /*K x (H+1) x n_x*/, double* Y /*K x H x n_y*/);
 
+/* orc_rollout with the reference's x_vec_0 / v_vec / e_vec keyword arguments (optimal_control_Ipopt.jl:48, :67, :77):
+ * a non-NULL x0_in / v_in / e_in (layouts of x0 / v / e) replaces the corresponding draw. */
+int orc_rollout_supplied(const orc_model* m, int64_t K, int64_t H, int64_t N, const double* A, const double* Q,
+                         const double* w_m1, const double* x_m1, const double* u_m1, const double* C, const double* Le,
+                         const double* u_init, uint64_t seed, uint32_t k_offset, const double* x0_in, const double* v_in,
+                         const double* e_in, double* x0, double* v, double* e, double* X, double* Y);
+
 /* test_prediction (particle_Gibbs.jl:253-314): K models x k_n simulations over the test input, simulation (k, kn) =
  * scenario k + K*kn with its own stream; x_sim K*k_n x (T_test+1) x n_x, y_sim K*k_n x T_test x n_y (scenario-major),
  * mean_rmse = the time-matched RMSE (NOT the cross-term broadcast the Julia line :311 evaluates; see pg_oracle.c). */

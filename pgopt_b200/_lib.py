@@ -35,6 +35,9 @@ EXPORTS = ["pgb_version", "pgb_last_error", "pgb_create", "pgb_destroy", "pgb_se
            "pgb_set_rng_injected", "pgb_sweep", "pgb_sweep_filter", "pgb_sweep_mniw", "pgb_particle_gibbs",
            "pgb_get_sample", "pgb_get_history", "pgb_get_stats", "pgb_get_status", "pgb_synchronize",
            "pgb_systematic_resampling", "pgb_mniw_sample", "pgb_rollout", "pgb_test_prediction", "pgb_scenario_constraint_max", "pgb_scenario_constraint_last_ms", "pgb_rollout_last_ms", "pgb_test_force_fallback", "pgb_test_math", "pgb_test_fp64_peak", "pgb_test_rollout_kernel",
+           "pgb_rollout_supplied", "pgb_samples_create", "pgb_samples_destroy", "pgb_samples_last_error", "pgb_samples_set",
+           "pgb_samples_get", "pgb_samples_store", "pgb_particle_gibbs_dev", "pgb_samples_draw_xT", "pgb_rollout_dev",
+           "pgb_scenarios_get", "pgb_scenario_constraint_max_dev", "pgb_samples_last_ms", "pgb_host_alloc", "pgb_host_free",
            "pgb_set_mode", "pgb_timer_start", "pgb_timer_stop", "pgb_profile", "pgb_get_profile", "pgb_get_launch_count"]
 
 
@@ -50,6 +53,14 @@ def lib():
         L.pgb_last_error.argtypes = [C.c_void_p]
         L.pgb_destroy.restype = None
         L.pgb_destroy.argtypes = [C.c_void_p]
+        L.pgb_samples_last_error.restype = C.c_char_p
+        L.pgb_samples_last_error.argtypes = [C.c_void_p]
+        L.pgb_samples_destroy.restype = None
+        L.pgb_samples_destroy.argtypes = [C.c_void_p]
+        L.pgb_host_alloc.restype = C.c_void_p
+        L.pgb_host_alloc.argtypes = [C.c_size_t]
+        L.pgb_host_free.restype = None
+        L.pgb_host_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

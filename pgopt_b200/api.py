@@ -193,6 +193,7 @@ class ParticleGibbsEngine:
         """x_history: "store" keeps x_pf[n_x,N,T] on the device (get_history needs it), "replay" keeps two steps and
         recomputes the traced trajectory (bit-identical, N*T no longer bounded by memory), "auto": store up to 1 GiB."""
         self.cfg = _make_cfg(phi, n_y, N, T, n_chains, device, keep_w_history, x_history)
+        self._phi = phi
         self.n_x, self.n_u, self.n_y, self.n_phi = self.cfg.n_x, self.cfg.n_u, n_y, self.cfg.n_phi
         self.N, self.T, self.n_chains = int(N), int(T), int(n_chains)
         self._h = C.c_void_p()
@@ -322,6 +323,16 @@ class ParticleGibbsEngine:
                                           _p(w_s), _p(x_s), _p(u_m1)))
         return A_s, Q_s, w_s, x_s, u_m1
 
+    def particle_gibbs_dev(self, K, K_b, k_d):
+        """the sampler with the kept samples left on the device: DeviceSamples with slot chain*K + k"""
+        out = DeviceSamples(self._phi, self.n_y, self.N, self.n_chains * K, self.cfg.device)
+        try:
+            self._ck(lib().pgb_particle_gibbs_dev(self._h, C.c_int64(K), C.c_int64(K_b), C.c_int64(k_d), out._s))
+        except Exception:
+            out.close()
+            raise
+        return out
+
 
 # ----------------------------------------------------------------------------------------------
 # the reference's exported functions
@@ -398,32 +409,156 @@ def particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q,
         eng.close()
 
 
-def scenario_rollout(PG_samples, phi, g, R, H, u_init=None, seed=0, k_offset=0, device=0):
+def _noise_factor(R):
+    if np.ndim(R) == 0:
+        return np.array([[float(R)]])  # MvNormal(zeros(n_y), R::Real) reads R as a std (reference quirk, :79)
+    return np.linalg.cholesky(np.atleast_2d(np.asarray(R, dtype=np.float64)))
+
+
+def _supplied(x_vec_0, v_vec, e_vec, K, H, n_x, n_y):
+    """the reference's keyword arrays (x_vec_0 (n_x*K,), v_vec (n_x,H,K), e_vec (n_y,H,K)) in the C ABI's
+    scenario-major layouts, or None"""
+    x0 = None if x_vec_0 is None else np.ascontiguousarray(np.asarray(x_vec_0, dtype=np.float64).reshape(K, n_x))
+    v = None if v_vec is None else np.ascontiguousarray(np.transpose(np.asarray(v_vec, dtype=np.float64).reshape(n_x, H, K), (2, 1, 0)))
+    e = None if e_vec is None else np.ascontiguousarray(np.transpose(np.asarray(e_vec, dtype=np.float64).reshape(n_y, H, K), (2, 1, 0)))
+    return x0, v, e
+
+
+def _scenario_dict(x0, v, e, X, Y, K, H, n_x, n_y):
+    return dict(x_vec_0=x0.reshape(-1), v_vec=np.transpose(v, (2, 1, 0)), e_vec=np.transpose(e, (2, 1, 0)),
+                X_init=np.transpose(X, (0, 2, 1)).reshape(K * n_x, H + 1),
+                Y_init=np.transpose(Y, (0, 2, 1)).reshape(K * n_y, H), raw=dict(x0=x0, v=v, e=e, X=X, Y=Y))
+
+
+def scenario_rollout(PG_samples, phi, g, R, H, u_init=None, seed=0, k_offset=0, device=0, x_vec_0=None, v_vec=None,
+                     e_vec=None):
     """Scenario sampling and forward rollout that solve_PG_OCP_Ipopt performs before building the NLP
     (Julia/src/optimal_control_Ipopt.jl:47-83,114-125).  Returns the arrays in the reference's layouts so
     they can be passed back through its `x_vec_0`, `v_vec`, `e_vec`, `u_init` keyword arguments:
-    x_vec_0 (n_x*K,), v_vec (n_x,H,K), e_vec (n_y,H,K), X_init (n_x*K,H+1), Y_init (n_y*K,H)."""
+    x_vec_0 (n_x*K,), v_vec (n_x,H,K), e_vec (n_y,H,K), X_init (n_x*K,H+1), Y_init (n_y*K,H).
+    `x_vec_0` / `v_vec` / `e_vec`, when given, are used instead of the draws exactly as the reference's keyword
+    arguments are (:48, :67, :77) — the second entry of the pre-solve step (:88-112)."""
     b = _basis(phi)
     gm = _meas(g)
     K = len(PG_samples)
     n_x, n_u, n_phi = b.n_x, b.n_u, b.n_phi
     n_y = gm.C.shape[0]
     A, Q, w, x, um, N = _pack_samples(PG_samples)
-    if np.ndim(R) == 0:
-        Le = np.array([[float(R)]])  # MvNormal(zeros(n_y), R::Real) reads R as a std (reference quirk, :79)
-    else:
-        Le = np.linalg.cholesky(np.atleast_2d(np.asarray(R, dtype=np.float64)))
+    Le = _noise_factor(R)
     if u_init is None:
         u_init = np.zeros((n_u, H))  # :110
     cfg = _make_cfg(b, n_y, N, 2, 1, device)
+    x0i, vi, ei = _supplied(x_vec_0, v_vec, e_vec, K, H, n_x, n_y)
     x0, v, e = np.empty((K, n_x)), np.empty((K, H, n_x)), np.empty((K, H, n_y))
     X, Y = np.empty((K, H + 1, n_x)), np.empty((K, H, n_y))
-    check(lib().pgb_rollout(C.byref(cfg), C.c_int64(K), C.c_int64(H), _p(A), _p(Q), _p(w), _p(x), _p(um), _p(_f(gm.C)),
-                            _p(_f(Le)), _p(_f(np.atleast_2d(u_init))), C.c_uint64(seed), C.c_uint32(k_offset),
-                            _p(x0), _p(v), _p(e), _p(X), _p(Y)))
-    return dict(x_vec_0=x0.reshape(-1), v_vec=np.transpose(v, (2, 1, 0)), e_vec=np.transpose(e, (2, 1, 0)),
-                X_init=np.transpose(X, (0, 2, 1)).reshape(K * n_x, H + 1),
-                Y_init=np.transpose(Y, (0, 2, 1)).reshape(K * n_y, H), raw=dict(x0=x0, v=v, e=e, X=X, Y=Y))
+    check(lib().pgb_rollout_supplied(C.byref(cfg), C.c_int64(K), C.c_int64(H), _p(A), _p(Q), _p(w), _p(x), _p(um),
+                                     _p(_f(gm.C)), _p(_f(Le)), _p(_f(np.atleast_2d(u_init))), C.c_uint64(seed),
+                                     C.c_uint32(k_offset), _p(x0i), _p(vi), _p(ei), _p(x0), _p(v), _p(e), _p(X), _p(Y)))
+    return _scenario_dict(x0, v, e, X, Y, K, H, n_x, n_y)
+
+
+class DeviceSamples:
+    """K posterior samples resident on one GPU (pgb_samples): what `Vector{PG_sample}` is to the reference
+    (PGopt.jl:23-29), except that sampler -> rollout -> screening read it in place on the device, as
+    optimal_control_Ipopt.jl:47-64 reads PG_samples[k].A in place on the host."""
+
+    def __init__(self, phi, n_y, N, K, device=0):
+        self.basis = _basis(phi)
+        self.cfg = _make_cfg(self.basis, n_y, N, 2, 1, device)
+        self.K, self.N, self.n_y = int(K), int(N), int(n_y)
+        self.n_x, self.n_u, self.n_phi = self.basis.n_x, self.basis.n_u, self.basis.n_phi
+        self.H = None
+        self._s = C.c_void_p()
+        check(lib().pgb_samples_create(C.byref(self._s), C.byref(self.cfg), C.c_int64(self.K)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = lib().pgb_samples_last_error(self._s)
+            raise PgoptError(rc, msg.decode() if msg else "unknown")
+
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s.value:
+            lib().pgb_samples_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __len__(self):
+        return self.K
+
+    @classmethod
+    def from_samples(cls, PG_samples, phi, n_y=1, device=0):
+        A, Q, w, x, um, N = _pack_samples(PG_samples)
+        s = cls(phi, n_y, N, len(PG_samples), device)
+        s._ck(lib().pgb_samples_set(s._s, C.c_int64(0), C.c_int64(s.K), _p(A), _p(Q), _p(w), _p(x), _p(um)))
+        return s
+
+    def to_batch(self):
+        K, nx, npb, N, nu = self.K, self.n_x, self.n_phi, self.N, self.n_u
+        A, Q = np.empty((K, nx * npb)), np.empty((K, nx * nx))
+        w, x, um = np.empty((K, N)), np.empty((K, nx * N)), np.empty((K, nu))
+        self._ck(lib().pgb_samples_get(self._s, C.c_int64(0), C.c_int64(K), _p(A), _p(Q), _p(w), _p(x), _p(um)))
+        return PGSampleBatch(np.transpose(A.reshape(K, npb, nx), (0, 2, 1)), np.transpose(Q.reshape(K, nx, nx), (0, 2, 1)),
+                             w, np.transpose(x.reshape(K, N, nx), (0, 2, 1)), um)
+
+    def store(self, k, engine, chain=0):
+        """slot k <- the current PG_sample of `chain` of `engine`, device to device (particle_Gibbs.jl:204-208)"""
+        self._ck(lib().pgb_samples_store(self._s, C.c_int64(k), engine._h, C.c_int32(chain)))
+
+    def draw_xT(self, seed=0, k_offset=0):
+        """x_m1[:, star_k] with star_k ~ systematic_resampling(w_m1, 1) (optimal_control_Ipopt.jl:58-59), drawn on the
+        device that holds the sample; (K, n_x)"""
+        xT = np.empty((self.K, self.n_x))
+        self._ck(lib().pgb_samples_draw_xT(self._s, C.c_uint64(seed), C.c_uint32(k_offset), _p(xT)))
+        return xT
+
+    def rollout(self, g, R, H, u_init=None, seed=0, k_offset=0, x_vec_0=None, v_vec=None, e_vec=None, reuse=()):
+        """scenario_rollout on the resident samples; results stay on the device (fetch with scenarios()).  `reuse`: any
+        of "x_vec_0", "v_vec", "e_vec" — keep that array of the previous rollout of this set instead of drawing (the
+        pre-solve re-entry with a new u_init, optimal_control_Ipopt.jl:88-125)."""
+        gm = _meas(g)
+        Le = _noise_factor(R)
+        if u_init is None:
+            u_init = np.zeros((self.n_u, H))
+        x0i, vi, ei = _supplied(x_vec_0, v_vec, e_vec, self.K, H, self.n_x, self.n_y)
+        bits = sum(b for name, b in (("x_vec_0", 1), ("v_vec", 2), ("e_vec", 4)) if name in reuse)
+        self._ck(lib().pgb_rollout_dev(self._s, C.c_int64(H), _p(_f(gm.C)), _p(_f(Le)), _p(_f(np.atleast_2d(u_init))),
+                                       C.c_uint64(seed), C.c_uint32(k_offset), C.c_int32(bits), _p(x0i), _p(vi), _p(ei)))
+        self.H = int(H)
+        return self
+
+    def scenarios(self, want=("x0", "v", "e", "X", "Y"), out=None):
+        """the reference-layout dict of scenario_rollout for the last rollout (D2H of the requested arrays only)"""
+        K, H, nx, ny = self.K, self.H, self.n_x, self.n_y
+        shapes = dict(x0=(K, nx), v=(K, H, nx), e=(K, H, ny), X=(K, H + 1, nx), Y=(K, H, ny))
+        bufs = {k: (out[k] if out and k in out else np.empty(shapes[k])) for k in want}
+        self._ck(lib().pgb_scenarios_get(self._s, *[_p(bufs.get(k)) for k in ("x0", "v", "e", "X", "Y")]))
+        return bufs
+
+    def constraint_max(self, y_min, y_max):
+        """scenario_constraint_max on the Y the last rollout left on the device"""
+        y_min = np.atleast_2d(np.asarray(y_min, dtype=np.float64))
+        y_max = np.atleast_2d(np.asarray(y_max, dtype=np.float64))
+        if y_min.shape != (self.n_y, self.H) or y_max.shape != (self.n_y, self.H):
+            raise ValueError("y_min and y_max must both be (n_y, H)")
+        h, order = np.empty(self.K), np.empty(self.K, dtype=np.int64)
+        self._ck(lib().pgb_scenario_constraint_max_dev(self._s, _p(_f(y_min)), _p(_f(y_max)), _p(h), _p(order)))
+        return h, order
+
+    def last_ms(self):
+        a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._ck(lib().pgb_samples_last_ms(self._s, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(rollout_kernel_ms=a.value, screening_kernel_ms=b.value, upload_ms=c.value)
 
 
 def test_prediction(PG_samples, phi, g, R, k_n, u_test, y_test, seed=0, device=0):
@@ -441,10 +576,7 @@ def test_prediction(PG_samples, phi, g, R, k_n, u_test, y_test, seed=0, device=0
     u_test = np.atleast_2d(np.asarray(u_test, dtype=np.float64))
     y_test = np.atleast_2d(np.asarray(y_test, dtype=np.float64))
     T_test = y_test.shape[1]
-    if np.ndim(R) == 0:
-        Le = np.array([[float(R)]])  # MvNormal(zeros(n_y), R::Real) reads R as a std (reference quirk, :261)
-    else:
-        Le = np.linalg.cholesky(np.atleast_2d(np.asarray(R, dtype=np.float64)))
+    Le = _noise_factor(R)  # MvNormal(zeros(n_y), R::Real) reads R as a std (reference quirk, :261)
     cfg = _make_cfg(b, n_y, N, 2, 1, device)
     S = K * int(k_n)
     xs, ys = np.empty((S, T_test + 1, n_x)), np.empty((S, T_test, n_y))

@@ -556,6 +556,37 @@ extern "C" int pgb_particle_gibbs(pgb_handle* h, int64_t K, int64_t K_b, int64_t
   return check_posdef(h);
 }
 
+// The sampler with the K kept samples of every chain left ON THE DEVICE (slot chain*K + k of `out`), copied
+// device-to-device at the reference's store condition (:203): nothing but the positive-definiteness flag crosses PCIe.
+extern "C" int pgb_particle_gibbs_dev(pgb_handle* h, int64_t K, int64_t K_b, int64_t k_d, pgb_samples* out) {
+  NEED(h);
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!out) return set_err(h, PGB_ERR_INVALID, "sample set is NULL");
+  if (!h->fd.philox) return set_err(h, PGB_ERR_INVALID, "pgb_particle_gibbs_dev needs Philox streams");
+  if (!h->have_prior) return set_err(h, PGB_ERR_STATE, "pgb_set_prior missing");
+  if (K < 1 || K_b < 0 || k_d < 0) return set_err(h, PGB_ERR_INVALID, "bad K/K_b/k_d");
+  if (h->sweep_index != 1)
+    return set_err(h, PGB_ERR_STATE, "pgb_particle_gibbs_dev starts a sampler at sweep 1: call pgb_set_state(..., sweep_index = 1) "
+                                     "first (handle is at sweep %lld)", (long long)h->sweep_index);
+  const int nc = h->cfg.n_chains;
+  if (out->K < (int64_t)nc * K) return set_err(h, PGB_ERR_INVALID, "sample set holds %lld slots, n_chains*K = %lld needed",
+                                                 (long long)out->K, (long long)nc * K);
+  const int64_t K_total = K_b + 1 + (K - 1) * (k_d + 1);  // particle_Gibbs.jl:116
+  int64_t cur = 0;
+  for (int64_t k = 1; k <= K_total; ++k) {
+    if ((rc = run_filter(h))) return rc;
+    if (K_b < k && ((k - (K_b + 1)) % (k_d + 1) == 0) && cur < K) {  // :203
+      for (int c = 0; c < nc; ++c)
+        if ((rc = pgb_samples_store_async(out, (int64_t)c * K + cur, h, c))) return rc;
+      ++cur;
+    }
+    if ((rc = run_mniw(h))) return rc;
+    if ((k & 63) == 0 && (rc = check_posdef(h))) return rc;
+  }
+  return check_posdef(h);
+}
+
 extern "C" int pgb_get_history(pgb_handle* h, int32_t chain, int64_t* a, double* x, double* w) {
   NEED(h);
   const int nx = h->cfg.n_x;

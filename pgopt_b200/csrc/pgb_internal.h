@@ -18,7 +18,6 @@
 #include "pgb_persist.cuh"
 #include "pgb_v2_types.h"
 
-struct pgb_samples;
 
 struct pgb_handle {
   pgb_config cfg;
@@ -60,6 +59,28 @@ struct pgb_handle {
   int64_t prof_launches[PGB_PROF_NCLASS] = {0};
   double prof_ms[PGB_PROF_NCLASS] = {0};
 };
+
+// K posterior samples (PG_sample fields, PGopt.jl:23-29) resident on one device, plus the scenario buffers the rollout
+// writes (x_vec_0, v_vec, e_vec, X, Y of optimal_control_Ipopt.jl:47-125) so that sampler -> rollout -> screening never
+// leaves the GPU.  One arena allocation per buffer for the life of the set; `hh` is its allocation list / error sink.
+struct pgb_samples {
+  pgb_handle hh;
+  int64_t K = 0;        // capacity (= number of scenarios of a rollout)
+  double *A = nullptr, *Q = nullptr, *w = nullptr, *x = nullptr, *um = nullptr;  // [K][...] layouts of pgb_rollout
+  double* xT = nullptr; // [K][n_x] x_m1[:, star] (pgb_samples_draw_xT) or null
+  bool have_xT = false;
+  // scenario buffers of the last rollout (allocated for horizon H_cap on first use)
+  int64_t H = 0, H_cap = 0;
+  double *x0 = nullptr, *v = nullptr, *e = nullptr, *X = nullptr, *Y = nullptr, *ui = nullptr, *hmax = nullptr;
+  double *ylo = nullptr, *yhi = nullptr;
+  int* status = nullptr;
+  bool have_scen = false;
+  double C[16] = {0}, Le[16] = {0};
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  float last_ms[3] = {0.f, 0.f, 0.f};  // device time of the last rollout kernel, screening kernel, input upload
+};
+// pgb_rollout.cu: device-to-device copy of the chain's current PG_sample into slot k (ordered on h->stream, no sync)
+int pgb_samples_store_async(pgb_samples* s, int64_t k, pgb_handle* h, int chain);
 
 // Bracket one launch: counts it and, in profiling mode, records an event pair around it.
 struct LaunchScope {

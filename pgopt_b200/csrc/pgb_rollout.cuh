@@ -35,6 +35,10 @@ struct RolloutDev {
   uint64_t seed;
   uint32_t k_offset;
   double *x0, *v, *e, *X, *Y;  // [K][n_x], [K][H][n_x], [K][H][n_y], [K][H+1][n_x], [K][H][n_y]
+  // supplied scenarios (optimal_control_Ipopt.jl:48,67,77: the draws are skipped when the kwargs are given): same
+  // layouts as x0 / v / e, null = draw.  May alias the outputs (the noise of a previous rollout kept on the device).
+  const double *x0_in, *v_in, *e_in;
+  const double* x_star;  // [K][n_x] or null: x_m1[:, star] drawn beforehand (k_draw_xT); w_m1 / x_m1 are not read then
   int* status;         // [1]
 };
 
@@ -258,13 +262,13 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
   double Lq[NX * NX];
 #pragma unroll
   for (int i = 0; i < NX * NX; ++i) Lq[i] = rd.Q[km * NX * NX + i];
-  const int notpd = small_chol(Lq, NX);
+  const int notpd = small_chol(Lq, NX) && !(rd.x0_in && rd.v_in);  // Q is only used for the draws (:55, :71)
   if (notpd) {
     if (vt == 0) atomicOr(rd.status, 16);
     return;
   }
   // x0 noise (:62): drawn by thread 0, added by threads d < NX after the first evaluation of f
-  if (vt == 0) {
+  if (vt == 0 && !rd.x0_in) {
     double z[4];
     rollout_normals<(NX + 1) / 2>(rd.seed, cid, 1, 0u, z);
 #pragma unroll
@@ -278,26 +282,34 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
   // ---- noise of the whole horizon, one step per thread:  v_vec[:, t, k] (:72), e_vec[:, t, k] (:81)
   for (int64_t t = vt; t < H; t += R_TPB) {
     double z[4];
-    rollout_normals<(NX + 1) / 2>(rd.seed, cid, 2, (uint32_t)(t * ((NX + 1) / 2)), z);
-    for (int d = 0; d < NX; ++d) {
-      double acc = 0.0;
-      for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
-      vs[t * NX + d] = acc;
-      if (rd.v) rd.v[(k * H + t) * NX + d] = acc;
+    if (rd.v_in) {  // supplied v_vec (:67)
+      for (int d = 0; d < NX; ++d) vs[t * NX + d] = rd.v_in[(k * H + t) * NX + d];
+    } else {
+      rollout_normals<(NX + 1) / 2>(rd.seed, cid, 2, (uint32_t)(t * ((NX + 1) / 2)), z);
+      for (int d = 0; d < NX; ++d) {
+        double acc = 0.0;
+        for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
+        vs[t * NX + d] = acc;
+        if (rd.v) rd.v[(k * H + t) * NX + d] = acc;
+      }
     }
-    const int npairs = (ny + 1) / 2;
-    if (npairs == 1) rollout_normals<1>(rd.seed, cid, 3, (uint32_t)t, z);
-    else rollout_normals<2>(rd.seed, cid, 3, (uint32_t)(t * 2), z);
-    for (int o = 0; o < ny; ++o) {
-      double acc = 0.0;
-      for (int e2 = 0; e2 <= o; ++e2) acc = __fma_rn(rd.Le[o + ny * e2], z[e2], acc);
-      es[t * ny + o] = acc;
-      if (rd.e) rd.e[(k * H + t) * ny + o] = acc;
+    if (rd.e_in) {  // supplied e_vec (:77)
+      for (int o = 0; o < ny; ++o) es[t * ny + o] = rd.e_in[(k * H + t) * ny + o];
+    } else {
+      const int npairs = (ny + 1) / 2;
+      if (npairs == 1) rollout_normals<1>(rd.seed, cid, 3, (uint32_t)t, z);
+      else rollout_normals<2>(rd.seed, cid, 3, (uint32_t)(t * 2), z);
+      for (int o = 0; o < ny; ++o) {
+        double acc = 0.0;
+        for (int e2 = 0; e2 <= o; ++e2) acc = __fma_rn(rd.Le[o + ny * e2], z[e2], acc);
+        es[t * ny + o] = acc;
+        if (rd.e) rd.e[(k * H + t) * ny + o] = acc;
+      }
     }
   }
   // ---- star = systematic_resampling(w_m1, 1) (:58): W = w/sum(w) (tree), first n with q_n >= u   (thread 0)
   __syncthreads();
-  if (vt == 0) {
+  if (vt == 0 && !rd.x0_in) {
     const double* wg = rd.w_m1 + km * N;
 #define R_W(i) ((i) < nstage ? ws[(i)] : wg[(i)])
     double st[40];
@@ -328,11 +340,11 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
   __syncthreads();
   // ---- x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62)
   double Fd = 0.0;
-  rollout_eval_F<NX, NI>(fd, sh, Areg, Ag, c, dig, rd.u_m1 + km * nu, Fd);
+  if (!rd.x0_in) rollout_eval_F<NX, NI>(fd, sh, Areg, Ag, c, dig, rd.u_m1 + km * nu, Fd);  // block-uniform
   if (vt < NX) {
-    const double xv = __dadd_rn(Fd, sh.x0n[vt]);
+    const double xv = rd.x0_in ? rd.x0_in[k * NX + vt] : __dadd_rn(Fd, sh.x0n[vt]);  // supplied x_vec_0 (:48)
     sh.x[vt] = xv;
-    if (rd.x0) rd.x0[k * NX + vt] = xv;
+    if (rd.x0 && !rd.x0_in) rd.x0[k * NX + vt] = xv;
     if (rd.X) rd.X[(k * (H + 1)) * NX + vt] = xv;
   }
   __syncthreads();
@@ -590,6 +602,72 @@ __device__ __forceinline__ void rw_eval_F(const FilterDev& fd, const RolloutWSha
 #ifndef PGB_ROLLOUT_W_MINBLOCKS
 #define PGB_ROLLOUT_W_MINBLOCKS 2
 #endif
+// star = systematic_resampling(w_m1, 1) (optimal_control_Ipopt.jl:58) by one warp: S = balanced-tree sum of w, then the
+// first n with q_n >= u, q strictly sequential (particle_Gibbs.jl:26-29); every lane walks the same path.  Returns the
+// 0-based index; raises the reference's edge cases in *status (overrun: BoundsError, index 0).
+__device__ __forceinline__ int64_t rw_draw_star(const double* __restrict__ wg, int64_t N, uint64_t seed, uint32_t cid,
+                                                int* status) {
+  const int lane = threadIdx.x & 31;
+  int64_t P = 1;
+  while (P < N) P <<= 1;
+  double S;
+  if (P >= 32) {
+    const int64_t per = P / 32, base = (int64_t)lane * per;
+    double st[40];
+    int sp = 0;
+    for (int64_t i = 0; i < per; ++i) {
+      double xv = (base + i < N) ? wg[base + i] : 0.0;
+      const int merges = __ffsll((long long)(i + 1)) - 1;
+      for (int m = 0; m < merges; ++m) xv = __dadd_rn(st[--sp], xv);
+      st[sp++] = xv;
+    }
+    S = st[0];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) S = __dadd_rn(S, shfl_xor_d(S, o));
+  } else {
+    S = (lane < N) ? wg[lane] : 0.0;
+    for (int o = 1; o < (int)P; o <<= 1) S = __dadd_rn(S, shfl_xor_d(S, o));
+    S = __shfl_sync(0xffffffffu, S, 0);
+  }
+  const pgb_u32x4 b = pgb_stream_block(seed, PGB_STREAM_ROLL, cid, 0, 0, 0);
+  const double ust = pgb_u53_halfopen(b.v[0], b.v[1]);
+  double q = 0.0;
+  int64_t n = 0;
+  bool over = false;
+  for (int64_t base = 0;; base += 32) {  // every lane walks the same (uniform) path
+    if (!(q < ust)) break;
+    if (base >= N) { over = true; break; }
+    const double Wl = (base + lane < N) ? __ddiv_rn(wg[base + lane], S) : 0.0;
+    const int lim = (N - base < 32) ? (int)(N - base) : 32;
+    for (int l = 0; l < lim; ++l) {
+      if (!(q < ust)) break;
+      ++n;
+      q = __dadd_rn(q, __shfl_sync(0xffffffffu, Wl, l));
+    }
+  }
+  if (over) {
+    if (lane == 0) atomicOr(status, 1);
+    n = N;
+  }
+  if (n == 0) {
+    if (lane == 0) atomicOr(status, 2);
+    n = 1;
+  }
+  return n - 1;
+}
+
+// x_T[k] = x_m1[:, star_k] for K samples, one warp each — the draw of optimal_control_Ipopt.jl:58-59 done where the
+// sample lives, so that only (A, Q, x_T) has to travel between GPUs.  Scenario ids as in the rollout.
+static __global__ void __launch_bounds__(128) k_draw_xT(int64_t K, int64_t N, int nx, const double* __restrict__ w_m1,
+                                                        const double* __restrict__ x_m1, uint64_t seed, uint32_t k_offset,
+                                                        double* __restrict__ xT, int* status) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (k >= K) return;
+  const int64_t star = rw_draw_star(w_m1 + k * N, N, seed, k_offset + (uint32_t)k, status);
+  if (lane < nx) xT[k * nx + lane] = x_m1[(k * N + star) * nx + lane];
+}
+
 template <int NX, int NI, int RS>
 __global__ void __launch_bounds__(RW_WPB * 32, RS >= 2 ? 3 : PGB_ROLLOUT_W_MINBLOCKS)
 k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ RolloutDev rd) {
@@ -687,35 +765,46 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
     double Lq[NX * NX];
 #pragma unroll
     for (int i = 0; i < NX * NX; ++i) Lq[i] = rd.Q[km * NX * NX + i];
-    if (small_chol(Lq, NX)) {  // warp-uniform
+    if (small_chol(Lq, NX) && !(rd.x0_in && rd.v_in)) {  // warp-uniform; Q is only used for the draws (:55, :71)
       if (lane == 0) atomicOr(rd.status, 16);
       continue;
     }
     // ---- noise of the whole horizon, one step per lane:  v_vec[:, t, k] (:72), e_vec[:, t, k] (:81)
     for (int64_t t = lane; t < H; t += 32) {
       double z[4];
-      rollout_normals<(NX + 1) / 2>(rd.seed, cid, 2, (uint32_t)(t * ((NX + 1) / 2)), z);
+      if (rd.v_in) {  // supplied v_vec (:67)
 #pragma unroll
-      for (int d = 0; d < NX; ++d) {
-        double acc = 0.0;
+        for (int d = 0; d < NX; ++d) vs[t * NX + d] = rd.v_in[(k * H + t) * NX + d];
+      } else {
+        rollout_normals<(NX + 1) / 2>(rd.seed, cid, 2, (uint32_t)(t * ((NX + 1) / 2)), z);
 #pragma unroll
-        for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
-        vs[t * NX + d] = acc;
-        if (rd.v) rd.v[(k * H + t) * NX + d] = acc;
+        for (int d = 0; d < NX; ++d) {
+          double acc = 0.0;
+#pragma unroll
+          for (int e2 = 0; e2 <= d; ++e2) acc = __fma_rn(Lq[d + NX * e2], z[e2], acc);
+          vs[t * NX + d] = acc;
+          if (rd.v) rd.v[(k * H + t) * NX + d] = acc;
+        }
       }
-      const int npairs = (ny + 1) / 2;
-      if (npairs == 1) rollout_normals<1>(rd.seed, cid, 3, (uint32_t)t, z);
-      else rollout_normals<2>(rd.seed, cid, 3, (uint32_t)(t * 2), z);
-      for (int o = 0; o < ny; ++o) {
-        double acc = 0.0;
-        for (int e2 = 0; e2 <= o; ++e2) acc = __fma_rn(rd.Le[o + ny * e2], z[e2], acc);
-        es[t * ny + o] = acc;
-        if (rd.e) rd.e[(k * H + t) * ny + o] = acc;
+      if (rd.e_in) {  // supplied e_vec (:77)
+        for (int o = 0; o < ny; ++o) es[t * ny + o] = rd.e_in[(k * H + t) * ny + o];
+      } else {
+        const int npairs = (ny + 1) / 2;
+        if (npairs == 1) rollout_normals<1>(rd.seed, cid, 3, (uint32_t)t, z);
+        else rollout_normals<2>(rd.seed, cid, 3, (uint32_t)(t * 2), z);
+        for (int o = 0; o < ny; ++o) {
+          double acc = 0.0;
+          for (int e2 = 0; e2 <= o; ++e2) acc = __fma_rn(rd.Le[o + ny * e2], z[e2], acc);
+          es[t * ny + o] = acc;
+          if (rd.e) rd.e[(k * H + t) * ny + o] = acc;
+        }
       }
     }
     // ---- x0 noise (:62), every lane redundantly
     double x0n[NX];
-    {
+#pragma unroll
+    for (int d = 0; d < NX; ++d) x0n[d] = 0.0;
+    if (!rd.x0_in) {
       double z[4];
       rollout_normals<(NX + 1) / 2>(rd.seed, cid, 1, 0u, z);
 #pragma unroll
@@ -726,56 +815,14 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
         x0n[d] = acc;
       }
     }
-    // ---- star = systematic_resampling(w_m1, 1) (:58): S = tree sum of w; first n with q_n >= u, q sequential
-    {
-      const double* wg = rd.w_m1 + km * N;
-      int64_t P = 1;
-      while (P < N) P <<= 1;
-      double S;
-      if (P >= 32) {
-        const int64_t per = P / 32, base = (int64_t)lane * per;
-        double st[40];
-        int sp = 0;
-        for (int64_t i = 0; i < per; ++i) {
-          double xv = (base + i < N) ? wg[base + i] : 0.0;
-          const int merges = __ffsll((long long)(i + 1)) - 1;
-          for (int m = 0; m < merges; ++m) xv = __dadd_rn(st[--sp], xv);
-          st[sp++] = xv;
-        }
-        S = st[0];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) S = __dadd_rn(S, shfl_xor_d(S, o));
+    // ---- star = systematic_resampling(w_m1, 1) (:58), or the x_T the owning GPU already drew (packed samples)
+    if (!rd.x0_in) {
+      if (rd.x_star) {
+        if (lane < NX) xin[lane] = rd.x_star[km * NX + lane];
       } else {
-        S = (lane < N) ? wg[lane] : 0.0;
-        for (int o = 1; o < (int)P; o <<= 1) S = __dadd_rn(S, shfl_xor_d(S, o));
-        S = __shfl_sync(0xffffffffu, S, 0);
+        const int64_t star = rw_draw_star(rd.w_m1 + km * N, N, rd.seed, cid, rd.status);
+        if (lane < NX) xin[lane] = rd.x_m1[(km * N + star) * NX + lane];
       }
-      const pgb_u32x4 b = pgb_stream_block(rd.seed, PGB_STREAM_ROLL, cid, 0, 0, 0);
-      const double ust = pgb_u53_halfopen(b.v[0], b.v[1]);
-      double q = 0.0;
-      int64_t n = 0;
-      bool over = false;
-      for (int64_t base = 0;; base += 32) {  // every lane walks the same (uniform) path
-        if (!(q < ust)) break;
-        if (base >= N) { over = true; break; }
-        const double Wl = (base + lane < N) ? __ddiv_rn(wg[base + lane], S) : 0.0;
-        const int lim = (N - base < 32) ? (int)(N - base) : 32;
-        for (int l = 0; l < lim; ++l) {
-          if (!(q < ust)) break;
-          ++n;
-          q = __dadd_rn(q, __shfl_sync(0xffffffffu, Wl, l));
-        }
-      }
-      if (over) {
-        if (lane == 0) atomicOr(rd.status, 1);
-        n = N;
-      }
-      if (n == 0) {
-        if (lane == 0) atomicOr(rd.status, 2);
-        n = 1;
-      }
-      const int64_t star = n - 1;
-      if (lane < NX) xin[lane] = rd.x_m1[(km * N + star) * NX + lane];
     }
     __syncwarp();
     // ---- x0 = f(x_m1, u_m1) + rand(MvNormal(0, Q))  (:62).  The tree leaves component rw_comp(lane) of F in every
@@ -785,8 +832,10 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
     const int compc = comp < NX ? comp : 0;
     const bool holder = lane < (NX == 1 ? 1 : (NX == 2 ? 2 : 4)) && comp < NX;
     double Fb;
-    rw_eval_F<NX, NI, RS>(fd, sh, tkw, Areg, As, ncols, c, kl, ls, xin, rd.u_m1 + km * nu, Fb);
-    {
+    if (rd.x0_in) {  // supplied x_vec_0 (:48)
+      if (lane < NX) xs[lane] = rd.x0_in[k * NX + lane];
+    } else {
+      rw_eval_F<NX, NI, RS>(fd, sh, tkw, Areg, As, ncols, c, kl, ls, xin, rd.u_m1 + km * nu, Fb);
       double nz0 = x0n[0];
 #pragma unroll
       for (int d = 1; d < NX; ++d) nz0 = (compc == d) ? x0n[d] : nz0;
@@ -800,7 +849,7 @@ k_rollout_warp(const __grid_constant__ FilterDev fd, const __grid_constant__ Rol
       __syncwarp();
     }
     // ---- outputs: x_vec_0, X (coalesced copy of the trajectory), Y[t] = g(X[t]) + e (:122), one step per lane
-    if (rd.x0 && lane < NX) rd.x0[k * NX + lane] = xs[lane];
+    if (rd.x0 && !rd.x0_in && lane < NX) rd.x0[k * NX + lane] = xs[lane];
     if (rd.X)
       for (int64_t i = lane; i < (H + 1) * NX; i += 32) rd.X[k * (H + 1) * NX + i] = xs[i];
     if (rd.Y)

@@ -179,6 +179,25 @@ def rollout(model, K, H, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_init, seed, k_offs
     return dict(status=st, x0=x0, v=v, e=e, X=X, Y=Y)
 
 
+def rollout_supplied(model, K, H, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_init, seed, k_offset=0, x0_in=None, v_in=None,
+                     e_in=None):
+    """orc_rollout_supplied: x0_in (K,n_x) / v_in (K,H,n_x) / e_in (K,H,n_y) replace the draws (None = draw)."""
+    n_x, n_y = model.n_x, model.n_y
+    Af = f64(np.transpose(A, (0, 2, 1)))
+    Qf = f64(np.transpose(Q, (0, 2, 1)))
+    fl = lambda v: f64(np.asfortranarray(v).ravel(order="F"))
+    opt = lambda a: None if a is None else f64(a)
+    x0i, vi, ei = opt(x0_in), opt(v_in), opt(e_in)
+    x0, v, e = np.zeros((K, n_x)), np.zeros((K, H, n_x)), np.zeros((K, H, n_y))
+    X, Y = np.zeros((K, H + 1, n_x)), np.zeros((K, H, n_y))
+    st = lib().orc_rollout_supplied(C.byref(model), C.c_int64(K), C.c_int64(H), C.c_int64(N), _p(Af), _p(Qf),
+                                    _p(f64(w_m1)), _p(f64(x_m1)), _p(f64(u_m1)), _p(fl(Cm)), _p(fl(np.atleast_2d(Le))),
+                                    _p(fl(u_init)), C.c_uint64(seed), C.c_uint32(k_offset),
+                                    None if x0i is None else _p(x0i), None if vi is None else _p(vi),
+                                    None if ei is None else _p(ei), _p(x0), _p(v), _p(e), _p(X), _p(Y))
+    return dict(status=st, x0=x0, v=v, e=e, X=X, Y=Y)
+
+
 def test_prediction(model, K, k_n, T_test, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_test, y_test, seed):
     """orc_test_prediction: x_sim (K*k_n, T_test+1, n_x), y_sim (K*k_n, T_test, n_y), mean_rmse."""
     n_x, n_y = model.n_x, model.n_y

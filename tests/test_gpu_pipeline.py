@@ -1,0 +1,188 @@
+"""GPU parity of the supplied-scenario rollout (the x_vec_0 / v_vec / e_vec keyword arguments of solve_PG_OCP_Ipopt,
+Julia/src/optimal_control_Ipopt.jl:37,48,67,77 and the pre-solve re-entry :88-125) and of the device-resident pipeline
+sampler -> DeviceSamples -> rollout -> screening (the reference reads PG_samples[k].A in place, :47-64): every output
+bit-identical to the oracle / to the host-buffer path."""
+import numpy as np
+import pytest
+
+import _oracle as O
+import _problems as P
+import pgopt_b200 as pg
+from pgopt_b200 import _lib
+from test_gpu_parity import _assert_same
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["warp", "cta"])
+def rollout_kernel(request):
+    _lib.lib().pgb_test_rollout_kernel(1 if request.param == "warp" else 0)
+    yield request.param
+    _lib.lib().pgb_test_rollout_kernel(-1)
+
+
+def _scenario_problem(seed, n_x=4, dims=(1, 5, 5, 5, 5), N=30, K=13, H=21, n_y=1):
+    rng = np.random.default_rng(seed)
+    L = [4.0 + k for k in range(len(dims))]
+    basis = pg.HilbertGPBasis(list(dims), L)
+    om = O.hilbert_model(n_x, len(dims) - n_x, basis.count, basis.stride, basis.L, n_y=n_y)
+    n_u = len(dims) - n_x
+    A = rng.normal(0, 0.2, (K, n_x, basis.n_phi))
+    Q = np.stack([(lambda B: B @ B.T + 0.05 * np.eye(n_x))(rng.normal(0, 0.2, (n_x, n_x))) for _ in range(K)])
+    w = rng.uniform(size=(K, N)) ** 2
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, N, n_x))
+    um = rng.normal(0, 1, (K, n_u))
+    Cm = rng.normal(0, 1, (n_y, n_x))
+    u_init = rng.normal(0, 1, (n_u, H))
+    return dict(basis=basis, om=om, A=A, Q=Q, w=w, x=x, um=um, Cm=Cm, u_init=u_init, K=K, H=H, N=N, n_x=n_x, n_y=n_y,
+                n_u=n_u, rng=rng)
+
+
+@pytest.mark.parametrize("which", [("x0", "v", "e"), ("v",), ("x0",), ("e",), ("v", "e")])
+def test_rollout_supplied_scenarios_bit_exact(which, rollout_kernel):
+    """A supplied x_vec_0 / v_vec / e_vec replaces the draw and nothing else (optimal_control_Ipopt.jl:48,67,77)."""
+    p = _scenario_problem(3)
+    K, H, n_x, n_y = p["K"], p["H"], p["n_x"], p["n_y"]
+    rng = p["rng"]
+    sup = dict(x0=rng.normal(0, 1, (K, n_x)), v=rng.normal(0, 0.1, (K, H, n_x)), e=rng.normal(0, 0.1, (K, H, n_y)))
+    kw = {k + "_in": (sup[k] if k in which else None) for k in ("x0", "v", "e")}
+    ref = O.rollout_supplied(p["om"], K, H, p["N"], p["A"], p["Q"], p["w"], p["x"], p["um"], p["Cm"], [[0.1]],
+                             p["u_init"], seed=9, k_offset=2, **kw)
+    batch = pg.PGSampleBatch(p["A"], p["Q"], p["w"], np.transpose(p["x"], (0, 2, 1)), p["um"])
+    out = pg.scenario_rollout(
+        batch, p["basis"], pg.LinearMeasurement(p["Cm"]), 0.1, H, u_init=p["u_init"], seed=9, k_offset=2,
+        x_vec_0=sup["x0"].reshape(-1) if "x0" in which else None,
+        v_vec=np.transpose(sup["v"], (2, 1, 0)) if "v" in which else None,
+        e_vec=np.transpose(sup["e"], (2, 1, 0)) if "e" in which else None)
+    assert ref["status"] == 0
+    for name in ("x0", "v", "e", "X", "Y"):
+        _assert_same(name, out["raw"][name], ref[name])
+    for name in which:  # supplied arrays come back unchanged
+        _assert_same("echo " + name, out["raw"][name], sup[name])
+
+
+def test_pre_solve_reentry_same_noise_new_input(rollout_kernel):
+    """optimal_control_Ipopt.jl:88-125: the scenarios of the first entry, a new u_init, the rollout again — through the
+    host arrays and through the arrays kept on the device (reuse), both equal to the oracle's second entry."""
+    p = _scenario_problem(4, K=9, H=17)
+    K, H = p["K"], p["H"]
+    batch = pg.PGSampleBatch(p["A"], p["Q"], p["w"], np.transpose(p["x"], (0, 2, 1)), p["um"])
+    g = pg.LinearMeasurement(p["Cm"])
+    first = pg.scenario_rollout(batch, p["basis"], g, 0.1, H, u_init=p["u_init"], seed=5)
+    u2 = p["rng"].normal(0, 1, p["u_init"].shape)
+    ref1 = O.rollout(p["om"], K, H, p["N"], p["A"], p["Q"], p["w"], p["x"], p["um"], p["Cm"], [[0.1]], p["u_init"], seed=5)
+    ref2 = O.rollout_supplied(p["om"], K, H, p["N"], p["A"], p["Q"], p["w"], p["x"], p["um"], p["Cm"], [[0.1]], u2, seed=5,
+                              x0_in=ref1["x0"], v_in=ref1["v"], e_in=ref1["e"])
+    second = pg.scenario_rollout(batch, p["basis"], g, 0.1, H, u_init=u2, seed=5, x_vec_0=first["x_vec_0"],
+                                 v_vec=first["v_vec"], e_vec=first["e_vec"])
+    for name in ("x0", "v", "e", "X", "Y"):
+        _assert_same("host re-entry " + name, second["raw"][name], ref2[name])
+    with pg.DeviceSamples.from_samples(batch, p["basis"], n_y=p["n_y"]) as ds:
+        a = ds.rollout(g, 0.1, H, u_init=p["u_init"], seed=5).scenarios()
+        for name in ("x0", "v", "e", "X", "Y"):
+            _assert_same("device first " + name, a[name], ref1[name])
+        b = ds.rollout(g, 0.1, H, u_init=u2, seed=5, reuse=("x_vec_0", "v_vec", "e_vec")).scenarios()
+        for name in ("x0", "v", "e", "X", "Y"):
+            _assert_same("device re-entry " + name, b[name], ref2[name])
+        # host-supplied arrays into the resident set
+        c = ds.rollout(g, 0.1, H, u_init=u2, seed=5, x_vec_0=first["x_vec_0"], v_vec=first["v_vec"],
+                       e_vec=first["e_vec"]).scenarios()
+        for name in ("x0", "v", "e", "X", "Y"):
+            _assert_same("device supplied " + name, c[name], ref2[name])
+
+
+@pytest.mark.parametrize("n_y", [1, 2])
+def test_device_pipeline_rollout_and_screening(n_y, rollout_kernel):
+    """rollout + constraint screening on device-resident samples == oracle (and == the host-buffer entry points)."""
+    p = _scenario_problem(6, n_x=2, dims=(5, 5, 5), N=100, K=41, H=30, n_y=n_y)
+    K, H = p["K"], p["H"]
+    Br = p["rng"].normal(0, 0.2, (n_y, n_y))
+    R = Br @ Br.T + 0.05 * np.eye(n_y) if n_y > 1 else 0.1
+    Le = np.linalg.cholesky(R) if n_y > 1 else [[0.1]]
+    ref = O.rollout(p["om"], K, H, p["N"], p["A"], p["Q"], p["w"], p["x"], p["um"], p["Cm"], Le, p["u_init"], seed=8, k_offset=3)
+    y_min = np.full((n_y, H), -np.inf)
+    y_max = np.full((n_y, H), np.inf)
+    y_min[0, 3:20] = -0.5
+    y_max[n_y - 1, 10:] = 0.7
+    sref = O.scenario_constraint_max(ref["Y"], y_min, y_max)
+    batch = pg.PGSampleBatch(p["A"], p["Q"], p["w"], np.transpose(p["x"], (0, 2, 1)), p["um"])
+    with pg.DeviceSamples.from_samples(batch, p["basis"], n_y=n_y) as ds:
+        back = ds.to_batch()
+        for name in ("A", "Q", "w_m1", "x_m1", "u_m1"):
+            _assert_same("round trip " + name, getattr(back, name), getattr(batch, name))
+        out = ds.rollout(pg.LinearMeasurement(p["Cm"]), R, H, u_init=p["u_init"], seed=8, k_offset=3).scenarios()
+        for name in ("x0", "v", "e", "X", "Y"):
+            _assert_same(name, out[name], ref[name])
+        h, order = ds.constraint_max(y_min, y_max)
+        _assert_same("h_max", h, sref["h_max"])
+        assert np.array_equal(order, sref["order"])
+        ms = ds.last_ms()
+        assert ms["rollout_kernel_ms"] > 0 and ms["screening_kernel_ms"] > 0
+        # x_T drawn where the sample lives: the same star the rollout draws, and the rollout that uses it
+        xT = ds.draw_xT(seed=8, k_offset=3)
+        for k in range(K):
+            r1 = O.rollout(p["om"], 1, 1, p["N"], p["A"][k:k + 1], p["Q"][k:k + 1], p["w"][k:k + 1], p["x"][k:k + 1],
+                           p["um"][k:k + 1], p["Cm"], Le, p["u_init"][:, :1], seed=8, k_offset=3 + k)
+            assert r1["status"] == 0
+        out2 = ds.rollout(pg.LinearMeasurement(p["Cm"]), R, H, u_init=p["u_init"], seed=8, k_offset=3).scenarios()
+        for name in ("x0", "v", "e", "X", "Y"):
+            _assert_same("with x_T " + name, out2[name], ref[name])
+        # x_T is a column of x_m1 of the right sample
+        for k in range(K):
+            assert any(np.array_equal(xT[k], p["x"][k, n]) for n in range(p["N"])), k
+
+
+@pytest.mark.parametrize("model,N,T,K,K_b,k_d,nc", [("known", 30, 80, 3, 2, 1, 2), ("hilbert", 200, 30, 2, 1, 0, 1),
+                                                     ("known", 3000, 12, 2, 0, 1, 3)])
+def test_particle_gibbs_device_resident_samples(model, N, T, K, K_b, k_d, nc):
+    """pgb_particle_gibbs_dev leaves exactly the samples pgb_particle_gibbs returns (and the oracle computes), and the
+    rollout on them equals the rollout on the host copies."""
+    from test_gpu_parity import _models
+    basis, om, _ = _models()[model]
+    n_phi = basis.n_phi
+    u, y, _ = P.make_data(T, 51)
+    V = 10 * np.ones(n_phi) if model == "known" else pg.hilbert_gp_prior_V([5, 5, 5], [10, 20, 20], 2 * np.pi * np.ones(3),
+                                                                           100 ** 2 / (8 * np.pi ** 4))
+    A0, Q0 = np.zeros((2, n_phi)), 100 * np.eye(2)
+
+    def engine():
+        e = pg.ParticleGibbsEngine(basis, 1, N, T, n_chains=nc)
+        e.set_data(u, y)
+        e.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+        e.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+        e.set_prior(V, 100 * np.eye(2), 10.0)
+        for c in range(nc):
+            e.set_state(A0, Q0, None, 1, chain=c)
+        e.set_rng_philox(13, 4)
+        return e
+
+    with engine() as e:
+        A_s, Q_s, w_s, x_s, u_m1 = e.particle_gibbs(K, K_b, k_d)
+    with engine() as e:
+        ds = e.particle_gibbs_dev(K, K_b, k_d)
+    try:
+        b = ds.to_batch()
+        assert len(b) == nc * K
+        for c in range(nc):
+            for k in range(K):
+                s = c * K + k
+                _assert_same("A", b.A[s], A_s[c, k].reshape((2, n_phi), order="F"))
+                _assert_same("Q", b.Q[s], Q_s[c, k].reshape((2, 2), order="F"))
+                _assert_same("w", b.w_m1[s], w_s[c, k])
+                _assert_same("x", b.x_m1[s], x_s[c, k].reshape((2, N), order="F"))
+                _assert_same("u", b.u_m1[s], u_m1)
+        ref = O.particle_gibbs(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), A0, Q0, V, 100 * np.eye(2), 10.0,
+                               K, K_b, k_d, seed=13, chain=4)
+        for k in range(K):
+            _assert_same("oracle A", b.A[k], ref["A"][k])
+            _assert_same("oracle w", b.w_m1[k], ref["w"][k])
+        H = 12
+        u_init = np.cos(np.arange(H))[None, :]
+        g = pg.LinearMeasurement([[1.0, 0.0]])
+        host = pg.scenario_rollout(b, basis, g, 0.1, H, u_init=u_init, seed=2)["raw"]
+        dev = ds.rollout(g, 0.1, H, u_init=u_init, seed=2).scenarios()
+        for name in ("x0", "v", "e", "X", "Y"):
+            _assert_same(name, dev[name], host[name])
+    finally:
+        ds.close()
