@@ -52,6 +52,12 @@ enum {
 };
 
 enum { PGB_X_HISTORY_AUTO = 0, PGB_X_HISTORY_STORE = 1, PGB_X_HISTORY_REPLAY = 2 };
+/* Arithmetic of the particle filter.  F64: everything in FP64 (the reference).  F32 ("FP32 particle state" of the
+ * north star): particle states, basis functions, A*phi, process noise, log-weights and the two exponentials per
+ * particle in FP32 — bit-defined FP32 elementary functions shared with the oracle (pgb_mathf.h), so indices stay
+ * bit-exact against the oracle's F32 mode — while weight normalisation, the cumulative sums of the two systematic
+ * resampling draws, the backward trace, statistics and the MNIW draw stay FP64.  8 n_x + 12 bytes per particle-step. */
+enum { PGB_PRECISION_F64 = 0, PGB_PRECISION_F32 = 1 };
 
 typedef struct {
   int32_t device;     /* CUDA device ordinal */
@@ -74,7 +80,7 @@ typedef struct {
    * PGB_X_HISTORY_STORE keeps everything (needed for the x output of pgb_get_history; 8*n_x*N*T bytes per chain);
    * PGB_X_HISTORY_AUTO stores when the history is at most 1 GiB. */
   int32_t x_history;
-  int32_t reserved_;
+  int32_t precision;  /* PGB_PRECISION_F64 (0, default) or PGB_PRECISION_F32: see pgb_set_precision notes below */
 } pgb_config;
 
 typedef struct pgb_handle pgb_handle;
@@ -246,6 +252,65 @@ int pgb_samples_last_ms(pgb_samples* s, double* rollout_kernel_ms, double* scree
 /* page-locked host memory for the caller's I/O arrays (NULL on failure) */
 void* pgb_host_alloc(size_t bytes);
 void pgb_host_free(void* p);
+
+/* ---- several GPUs of one node: independent chains and independent scenarios -------------
+ * One process drives the listed devices (one host thread per device while they work, in-process ncclCommInitAll);
+ * cfg->device is ignored and cfg->n_chains is the TOTAL number of chains, dealt to the devices in contiguous balanced
+ * blocks.  Global chain c always uses Philox stream id chain_base + c and global sample g = c*K + k the scenario
+ * stream id g, so results do not depend on the number of devices.  The only collective is the NCCL all-gather at the
+ * end, device buffer to device buffer. */
+typedef struct pgb_multi pgb_multi;
+int pgb_multi_create(pgb_multi** out, const pgb_config* cfg, const int32_t* devices, int32_t n_devices);
+void pgb_multi_destroy(pgb_multi* m);
+const char* pgb_multi_last_error(const pgb_multi* m);
+int pgb_multi_n_devices(const pgb_multi* m);
+int pgb_multi_set_data(pgb_multi* m, const double* u, const double* y);
+int pgb_multi_set_measurement(pgb_multi* m, const double* C, const double* R);
+int pgb_multi_set_init_dist(pgb_multi* m, const double* mean, const double* chol_lower);
+int pgb_multi_set_prior(pgb_multi* m, const double* V_diag, const double* Lambda_Q, double ell_Q);
+/* chain: global index, or -1 = every chain */
+int pgb_multi_set_state(pgb_multi* m, int32_t chain, const double* A, const double* Q, const double* x_prim,
+                        int64_t sweep_index);
+int pgb_multi_set_rng_philox(pgb_multi* m, uint64_t seed, uint32_t chain_base);
+/* packed posterior-sample record (also the wire format of the gather and of pgb_samples_pack):
+ * [A n_x*n_phi column-major | Q n_x*n_x | x_T n_x | u_m1 n_u] doubles */
+int64_t pgb_packed_record_doubles(int32_t n_x, int32_t n_phi, int32_t n_u);
+/* particle_Gibbs on every chain; the kept samples stay on the device that produced them; x_T = x_m1[:, star] is drawn
+ * there (optimal_control_Ipopt.jl:58-59, seed roll_seed, stream id c*K + k) and the packed records are all-gathered to
+ * every device.  packed (host, may be NULL): [n_chains*K][record], chain-major. */
+int pgb_multi_particle_gibbs(pgb_multi* m, int64_t K, int64_t K_b, int64_t k_d, uint64_t roll_seed, double* packed);
+int pgb_multi_get_packed(pgb_multi* m, int32_t which_device, double* packed);
+/* PG_sample k of global chain c from the device that holds it (w_m1 / x_m1 are never gathered) */
+int pgb_multi_get_sample(pgb_multi* m, int32_t chain, int64_t k, double* A, double* Q, double* w_m1, double* x_m1,
+                         double* u_m1);
+/* K_total host samples dealt to the devices in contiguous blocks and kept resident (the configs[4] shape); layouts of
+ * pgb_rollout; x_T drawn on the owning device with (roll_seed, stream id = scenario index) */
+int pgb_multi_set_samples(pgb_multi* m, int64_t K_total, const double* A, const double* Q, const double* w_m1,
+                          const double* x_m1, const double* u_m1, uint64_t roll_seed);
+/* scenario rollout of all resident samples, each device its own, then one all-gather of x_vec_0 / X / Y; host outputs
+ * (may be NULL) in global order, layouts of pgb_rollout.  seed = the roll_seed the x_T were drawn with. */
+int pgb_multi_rollout(pgb_multi* m, int64_t H, const double* C, const double* Le, const double* u_init, uint64_t seed,
+                      double* x0, double* X, double* Y);
+/* device-side times (CUDA events, ms): NCCL gather of the packed samples; slowest device's rollout kernel; NCCL gather
+ * of the scenario arrays */
+int pgb_multi_last_ms(pgb_multi* m, double* sample_gather_ms, double* rollout_kernel_ms_max, double* scenario_gather_ms);
+
+/* ---- sample serialisation and checkpoint / resume ----------------------------------
+ * The reference keeps PG_sample only in memory (PGopt.jl:23-29) and warm-starts through the x_prim keyword
+ * (particle_Gibbs.jl:114,126-128).  Packed layout, little-endian, version 1:
+ *   64-byte header {char magic[8] = "PGB200S\0"; u32 version; u32 flags (bit 0: particles follow); i32 n_x, n_u, n_phi,
+ *   n_y; i64 N; i64 K; u64 reserved[2]} | K records [A | Q | x_T | u_m1] (pgb_packed_record_doubles) | if flags&1:
+ *   K x [w_m1 N | x_m1 n_x*N column-major].  x_T is filled by pgb_samples_draw_xT (zeros before). */
+int64_t pgb_samples_pack_bytes(const pgb_samples* s, int32_t with_particles);
+int pgb_samples_pack(pgb_samples* s, int32_t with_particles, void* buf, int64_t buf_bytes);
+/* the inverse: validates magic / version / shapes against the set (PGB_ERR_INVALID on mismatch) */
+int pgb_samples_unpack(pgb_samples* s, const void* buf, int64_t buf_bytes);
+/* Sampler checkpoint: everything a later pgb_checkpoint_load on a handle of the same configuration needs to continue
+ * the chains bit-identically (per chain A, Q, x_prim; sweep index; Philox seed and chain_base).  Same header with
+ * magic "PGB200C\0". */
+int64_t pgb_checkpoint_bytes(const pgb_handle* h);
+int pgb_checkpoint_save(pgb_handle* h, void* buf, int64_t buf_bytes);
+int pgb_checkpoint_load(pgb_handle* h, const void* buf, int64_t buf_bytes);
 
 /* ---- test hooks (not part of the drop-in surface) ---------------------------------------------
  * pgb_test_force_fallback(1) makes every exact scan take the serial-walk fallback path, (2) makes the ancestor

@@ -46,7 +46,7 @@ struct PgbConfig
     hg_count::NTuple{PGB_MAX_Z,Int32}; hg_stride::NTuple{PGB_MAX_Z,Int32}; hg_L::NTuple{PGB_MAX_Z,Float64}
     N::Int64; T::Int64; n_chains::Int32; keep_w_history::Int32
     x_history::Int32   # 0 auto, 1 store x_pf, 2 replay (two rows + recomputed lineage)
-    reserved_::Int32
+    precision::Int32
 end
 
 pad8(v, T) = ntuple(i -> i <= length(v) ? T(v[i]) : zero(T), PGB_MAX_Z)

@@ -694,6 +694,24 @@ static int rollout_impl(const orc_model* m, int64_t K, int64_t n_models, int64_t
   return status;
 }
 
+/* x_T = x_m1[:, star], star = systematic_resampling(w_m1, 1) (optimal_control_Ipopt.jl:58-59) for ONE sample, with the
+ * uniform of scenario stream `cid` — the first draw rollout_impl makes for that scenario.  This is what the owning GPU
+ * computes before the packed (A, Q, x_T) records are gathered. */
+int orc_draw_xT(int64_t N, int n_x, const double* w_m1, const double* x_m1 /* N x n_x */, uint64_t seed, uint32_t cid,
+                double* xT) {
+  orc_streams s;
+  memset(&s, 0, sizeof(s));
+  s.philox = 1;
+  s.seed = seed;
+  s.chain = cid;
+  int64_t star;
+  double us = stream_uniform(&s, PGB_STREAM_ROLL, 0, 0);
+  int status = orc_systematic_resampling(w_m1, N, 1, us, &star);
+  if (star < 1) star = 1;
+  for (int d = 0; d < n_x; ++d) xT[d] = x_m1[(star - 1) * n_x + d];
+  return status;
+}
+
 /* ---- scenario screening (optimal_control_Ipopt.jl:334-338; h_scenario of the examples, ..._Ipopt.jl:198-214) ---------- */
 /* Julia's isless on Float64: NaN is the largest value, -0.0 sorts before 0.0. */
 static int orc_isless(double a, double b) {

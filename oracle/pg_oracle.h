@@ -119,6 +119,10 @@ int orc_rollout_supplied(const orc_model* m, int64_t K, int64_t H, int64_t N, co
                          const double* u_init, uint64_t seed, uint32_t k_offset, const double* x0_in, const double* v_in,
                          const double* e_in, double* x0, double* v, double* e, double* X, double* Y);
 
+/* x_T = x_m1[:, star] with star = systematic_resampling(w_m1, 1) (optimal_control_Ipopt.jl:58-59), scenario stream cid */
+int orc_draw_xT(int64_t N, int n_x, const double* w_m1, const double* x_m1 /* N x n_x */, uint64_t seed, uint32_t cid,
+                double* xT);
+
 /* test_prediction (particle_Gibbs.jl:253-314): K models x k_n simulations over the test input, simulation (k, kn) =
  * scenario k + K*kn with its own stream; x_sim K*k_n x (T_test+1) x n_x, y_sim K*k_n x T_test x n_y (scenario-major),
  * mean_rmse = the time-matched RMSE (NOT the cross-term broadcast the Julia line :311 evaluates; see pg_oracle.c). */

@@ -17,7 +17,7 @@ class PgbConfig(C.Structure):
                 ("n_phi", C.c_int32), ("basis", C.c_int32), ("hg_count", C.c_int32 * PGB_MAX_Z),
                 ("hg_stride", C.c_int32 * PGB_MAX_Z), ("hg_L", C.c_double * PGB_MAX_Z), ("N", C.c_int64),
                 ("T", C.c_int64), ("n_chains", C.c_int32), ("keep_w_history", C.c_int32), ("x_history", C.c_int32),
-                ("reserved_", C.c_int32)]
+                ("precision", C.c_int32)]
 
 
 X_HISTORY = {"auto": 0, "store": 1, "replay": 2}
@@ -38,6 +38,12 @@ EXPORTS = ["pgb_version", "pgb_last_error", "pgb_create", "pgb_destroy", "pgb_se
            "pgb_rollout_supplied", "pgb_samples_create", "pgb_samples_destroy", "pgb_samples_last_error", "pgb_samples_set",
            "pgb_samples_get", "pgb_samples_store", "pgb_particle_gibbs_dev", "pgb_samples_draw_xT", "pgb_rollout_dev",
            "pgb_scenarios_get", "pgb_scenario_constraint_max_dev", "pgb_samples_last_ms", "pgb_host_alloc", "pgb_host_free",
+           "pgb_multi_create", "pgb_multi_destroy", "pgb_multi_last_error", "pgb_multi_n_devices", "pgb_multi_set_data",
+           "pgb_multi_set_measurement", "pgb_multi_set_init_dist", "pgb_multi_set_prior", "pgb_multi_set_state",
+           "pgb_multi_set_rng_philox", "pgb_packed_record_doubles", "pgb_multi_particle_gibbs", "pgb_multi_get_packed",
+           "pgb_multi_get_sample", "pgb_multi_set_samples", "pgb_multi_rollout", "pgb_multi_last_ms",
+           "pgb_samples_pack_bytes", "pgb_samples_pack", "pgb_samples_unpack", "pgb_checkpoint_bytes",
+           "pgb_checkpoint_save", "pgb_checkpoint_load",
            "pgb_set_mode", "pgb_timer_start", "pgb_timer_stop", "pgb_profile", "pgb_get_profile", "pgb_get_launch_count"]
 
 
@@ -59,6 +65,12 @@ def lib():
         L.pgb_samples_destroy.argtypes = [C.c_void_p]
         L.pgb_host_alloc.restype = C.c_void_p
         L.pgb_host_alloc.argtypes = [C.c_size_t]
+        L.pgb_multi_last_error.restype = C.c_char_p
+        L.pgb_multi_last_error.argtypes = [C.c_void_p]
+        L.pgb_multi_destroy.restype = None
+        L.pgb_multi_destroy.argtypes = [C.c_void_p]
+        for f in (L.pgb_packed_record_doubles, L.pgb_samples_pack_bytes, L.pgb_checkpoint_bytes):
+            f.restype = C.c_int64
         L.pgb_host_free.restype = None
         L.pgb_host_free.argtypes = [C.c_void_p]
         _lib = L

@@ -323,6 +323,28 @@ class ParticleGibbsEngine:
                                           _p(w_s), _p(x_s), _p(u_m1)))
         return A_s, Q_s, w_s, x_s, u_m1
 
+    def particle_gibbs_packed(self, K, K_b, k_d, roll_seed, k_offset):
+        """the sampler, then x_T = x_m1[:, star] drawn on the device (scenario stream ids k_offset + chain*K + k):
+        (n_chains, K, R) packed records [A | Q | x_T | u_m1]; the particle arrays never reach the host"""
+        ds = self.particle_gibbs_dev(K, K_b, k_d)
+        try:
+            ds.draw_xT(roll_seed, k_offset)
+            return ds.records().reshape(self.n_chains, K, -1)
+        finally:
+            ds.close()
+
+    def checkpoint(self):
+        """everything needed to continue the chains bit-identically on a handle of the same configuration
+        (per chain A, Q, x_prim; sweep index; Philox seed / chain_base) as a uint8 array"""
+        n = lib().pgb_checkpoint_bytes(self._h)
+        buf = np.empty(n, dtype=np.uint8)
+        self._ck(lib().pgb_checkpoint_save(self._h, _p(buf), C.c_int64(n)))
+        return buf
+
+    def restore(self, buf):
+        buf = np.ascontiguousarray(np.frombuffer(buf, dtype=np.uint8))
+        self._ck(lib().pgb_checkpoint_load(self._h, _p(buf), C.c_int64(buf.size)))
+
     def particle_gibbs_dev(self, K, K_b, k_d):
         """the sampler with the kept samples left on the device: DeviceSamples with slot chain*K + k"""
         out = DeviceSamples(self._phi, self.n_y, self.N, self.n_chains * K, self.cfg.device)
@@ -332,6 +354,115 @@ class ParticleGibbsEngine:
             out.close()
             raise
         return out
+
+
+class MultiGPUEngine:
+    """pgb_multi_*: independent chains / independent scenarios over several GPUs of one node driven from ONE process
+    (what the Julia shim uses: `device = [0, 1, ...]`).  n_chains is the TOTAL over all devices; results are independent
+    of the device count (global Philox stream ids)."""
+
+    def __init__(self, phi, n_y, N, T, n_chains, devices, x_history="auto"):
+        self.cfg = _make_cfg(phi, n_y, N, T, n_chains, 0, False, x_history)
+        self.basis = _basis(phi)
+        self.n_x, self.n_u, self.n_y, self.n_phi = self.cfg.n_x, self.cfg.n_u, int(n_y), self.cfg.n_phi
+        self.N, self.T, self.n_chains = int(N), int(T), int(n_chains)
+        self.devices = [int(d) for d in devices]
+        self.K = None
+        self._n_scen = None
+        self._m = C.c_void_p()
+        dv = (C.c_int32 * len(self.devices))(*self.devices)
+        check(lib().pgb_multi_create(C.byref(self._m), C.byref(self.cfg), dv, C.c_int32(len(self.devices))))
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = lib().pgb_multi_last_error(self._m)
+            raise PgoptError(rc, msg.decode() if msg else "unknown")
+
+    def close(self):
+        if getattr(self, "_m", None) is not None and self._m.value:
+            lib().pgb_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def record_doubles(self):
+        return int(lib().pgb_packed_record_doubles(C.c_int32(self.n_x), C.c_int32(self.n_phi), C.c_int32(self.n_u)))
+
+    def set_data(self, u, y):
+        self._ck(lib().pgb_multi_set_data(self._m, _p(_f(np.atleast_2d(u))), _p(_f(np.atleast_2d(y)))))
+
+    def set_measurement(self, g, R):
+        g = _meas(g)
+        self._ck(lib().pgb_multi_set_measurement(self._m, _p(_f(g.C)), _p(_f(np.atleast_2d(np.asarray(R, dtype=np.float64))))))
+
+    def set_init_dist(self, dist):
+        self._ck(lib().pgb_multi_set_init_dist(self._m, _p(_f(dist.mean)), _p(_f(dist.chol))))
+
+    def set_prior(self, V, Lambda_Q, ell_Q):
+        V = np.asarray(V, dtype=np.float64)
+        if V.ndim == 2:
+            V = np.diag(V)
+        self._ck(lib().pgb_multi_set_prior(self._m, _p(_f(V)), _p(_f(np.asarray(Lambda_Q, dtype=np.float64))), C.c_double(float(ell_Q))))
+
+    def set_state(self, A, Q, x_prim=None, sweep_index=1, chain=-1):
+        xp = None if x_prim is None else _f(x_prim)
+        self._ck(lib().pgb_multi_set_state(self._m, C.c_int32(chain), _p(_f(A)), _p(_f(Q)), _p(xp), C.c_int64(sweep_index)))
+
+    def set_rng_philox(self, seed, chain_base=0):
+        self._ck(lib().pgb_multi_set_rng_philox(self._m, C.c_uint64(seed), C.c_uint32(chain_base)))
+
+    def particle_gibbs(self, K, K_b, k_d, roll_seed=0):
+        """(n_chains, K, R) packed records [A | Q | x_T | u_m1], gathered over NCCL to every device and read from the first"""
+        out = np.empty((self.n_chains, K, self.record_doubles))
+        self._ck(lib().pgb_multi_particle_gibbs(self._m, C.c_int64(K), C.c_int64(K_b), C.c_int64(k_d), C.c_uint64(roll_seed), _p(out)))
+        self.K, self._n_scen = int(K), self.n_chains * int(K)
+        return out
+
+    def packed_on(self, which_device):
+        out = np.empty((self._n_scen, self.record_doubles))
+        self._ck(lib().pgb_multi_get_packed(self._m, C.c_int32(which_device), _p(out)))
+        return out
+
+    def get_sample(self, chain, k):
+        A, Q = np.empty(self.n_x * self.n_phi), np.empty(self.n_x * self.n_x)
+        w, x, u = np.empty(self.N), np.empty(self.n_x * self.N), np.empty(self.n_u)
+        self._ck(lib().pgb_multi_get_sample(self._m, C.c_int32(chain), C.c_int64(k), _p(A), _p(Q), _p(w), _p(x), _p(u)))
+        return PG_sample(A.reshape((self.n_x, self.n_phi), order="F"), Q.reshape((self.n_x, self.n_x), order="F"), w,
+                         x.reshape((self.n_x, self.N), order="F"), u)
+
+    def set_samples(self, PG_samples, roll_seed=0):
+        A, Q, w, x, um, N = _pack_samples(PG_samples)
+        assert N == self.N
+        self._ck(lib().pgb_multi_set_samples(self._m, C.c_int64(len(PG_samples)), _p(A), _p(Q), _p(w), _p(x), _p(um), C.c_uint64(roll_seed)))
+        self._n_scen = len(PG_samples)
+
+    def rollout(self, g, R, H, u_init=None, seed=0, want=("x0", "X", "Y"), out=None):
+        gm = _meas(g)
+        Le = _noise_factor(R)
+        if u_init is None:
+            u_init = np.zeros((self.n_u, H))
+        Kt, nx, ny = self._n_scen, self.n_x, self.n_y
+        shapes = dict(x0=(Kt, nx), X=(Kt, H + 1, nx), Y=(Kt, H, ny))
+        bufs = {k: (out[k] if out and k in out else np.empty(shapes[k])) for k in want}
+        self._ck(lib().pgb_multi_rollout(self._m, C.c_int64(H), _p(_f(gm.C)), _p(_f(Le)), _p(_f(np.atleast_2d(u_init))), C.c_uint64(seed),
+                                         _p(bufs.get("x0")), _p(bufs.get("X")), _p(bufs.get("Y"))))
+        return bufs
+
+    def last_ms(self):
+        a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._ck(lib().pgb_multi_last_ms(self._m, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(sample_gather_ms=a.value, rollout_kernel_ms_max=b.value, scenario_gather_ms=c.value)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -554,6 +685,25 @@ class DeviceSamples:
         h, order = np.empty(self.K), np.empty(self.K, dtype=np.int64)
         self._ck(lib().pgb_scenario_constraint_max_dev(self._s, _p(_f(y_min)), _p(_f(y_max)), _p(h), _p(order)))
         return h, order
+
+    def pack(self, with_particles=True):
+        """the versioned packed layout (include/pgopt_b200.h: header + [A | Q | x_T | u_m1] records [+ particle blocks])
+        as a bytes-like uint8 array — the on-disk / on-wire form of a Vector{PG_sample}"""
+        n = lib().pgb_samples_pack_bytes(self._s, C.c_int32(int(with_particles)))
+        buf = np.empty(n, dtype=np.uint8)
+        self._ck(lib().pgb_samples_pack(self._s, C.c_int32(int(with_particles)), _p(buf), C.c_int64(n)))
+        return buf
+
+    def unpack(self, buf):
+        buf = np.ascontiguousarray(np.frombuffer(buf, dtype=np.uint8))
+        self._ck(lib().pgb_samples_unpack(self._s, _p(buf), C.c_int64(buf.size)))
+        return self
+
+    def records(self):
+        """(K, R) array of packed records [A | Q | x_T | u_m1] (x_T zeros until draw_xT)"""
+        buf = self.pack(with_particles=False)
+        R = int(lib().pgb_packed_record_doubles(C.c_int32(self.n_x), C.c_int32(self.n_phi), C.c_int32(self.n_u)))
+        return buf[64:].view(np.float64).reshape(-1, R).copy()
 
     def last_ms(self):
         a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)

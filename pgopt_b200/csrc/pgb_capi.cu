@@ -49,6 +49,8 @@ int pgb_validate_cfg(const pgb_config* c) {
   if (c->n_x < 1 || c->n_x > 4) return set_err(nullptr, PGB_ERR_INVALID, "n_x must be 1..4 (got %d)", c->n_x);
   if (c->n_u < 1 || c->n_u > 4) return set_err(nullptr, PGB_ERR_INVALID, "n_u must be 1..4 (got %d)", c->n_u);
   if (c->n_y < 1 || c->n_y > 4) return set_err(nullptr, PGB_ERR_INVALID, "n_y must be 1..4 (got %d)", c->n_y);
+  if (c->precision != PGB_PRECISION_F64 && c->precision != PGB_PRECISION_F32)
+    return set_err(nullptr, PGB_ERR_INVALID, "precision must be PGB_PRECISION_F64 or PGB_PRECISION_F32 (got %d)", c->precision);
   if (c->basis == PGB_BASIS_KNOWN_VB) {
     if (c->n_x != 2 || c->n_u != 1 || c->n_phi != 5)
       return set_err(nullptr, PGB_ERR_INVALID, "KNOWN_VB basis needs n_x=2, n_u=1, n_phi=5");

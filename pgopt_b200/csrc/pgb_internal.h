@@ -65,7 +65,8 @@ struct pgb_handle {
 // leaves the GPU.  One arena allocation per buffer for the life of the set; `hh` is its allocation list / error sink.
 struct pgb_samples {
   pgb_handle hh;
-  int64_t K = 0;        // capacity (= number of scenarios of a rollout)
+  int64_t K = 0;        // capacity
+  int64_t K_active = 0; // slots in use (= number of scenarios of a rollout); = K unless a multi-GPU shard is ragged
   double *A = nullptr, *Q = nullptr, *w = nullptr, *x = nullptr, *um = nullptr;  // [K][...] layouts of pgb_rollout
   double* xT = nullptr; // [K][n_x] x_m1[:, star] (pgb_samples_draw_xT) or null
   bool have_xT = false;

@@ -359,7 +359,7 @@ extern "C" int pgb_samples_create(pgb_samples** out, const pgb_config* cfg, int6
   pgb_samples* s = new pgb_samples();
   pgb_handle* h = &s->hh;
   h->cfg = *cfg;
-  s->K = K;
+  s->K = s->K_active = K;
   const int nx = cfg->n_x, np = cfg->n_phi, nu = cfg->n_u;
   const int64_t N = cfg->N;
   auto fail = [&](cudaError_t e, const char* what) {
@@ -476,11 +476,12 @@ extern "C" int pgb_samples_store(pgb_samples* s, int64_t k, pgb_handle* h, int32
 // (seed, k_offset) uses it instead of walking w_m1 again.  x_T (host, may be NULL): [K][n_x].
 extern "C" int pgb_samples_draw_xT(pgb_samples* s, uint64_t seed, uint32_t k_offset, double* x_T) {
   NEEDS(s);
-  if ((uint64_t)k_offset + (uint64_t)s->K > (1ull << 24)) return set_err(h, PGB_ERR_INVALID, "k_offset + K exceeds the 2^24 Philox stream ids");
+  const int64_t K = s->K_active;
+  if ((uint64_t)k_offset + (uint64_t)K > (1ull << 24)) return set_err(h, PGB_ERR_INVALID, "k_offset + K exceeds the 2^24 Philox stream ids");
   CK(h, cudaMemsetAsync(s->status, 0, 4, h->stream));
-  k_draw_xT<<<(unsigned)((s->K + 3) / 4), 128, 0, h->stream>>>(s->K, h->cfg.N, h->cfg.n_x, s->w, s->x, seed, k_offset, s->xT, s->status);
+  k_draw_xT<<<(unsigned)((K + 3) / 4), 128, 0, h->stream>>>(K, h->cfg.N, h->cfg.n_x, s->w, s->x, seed, k_offset, s->xT, s->status);
   CK(h, cudaGetLastError());
-  if (x_T) CK(h, cudaMemcpyAsync(x_T, s->xT, (size_t)s->K * h->cfg.n_x * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (x_T) CK(h, cudaMemcpyAsync(x_T, s->xT, (size_t)K * h->cfg.n_x * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   s->have_xT = true;
   return PGB_OK;
@@ -514,12 +515,12 @@ extern "C" int pgb_rollout_dev(pgb_samples* s, int64_t H, const double* C, const
                                const double* e_in) {
   NEEDS(s);
   if (!C || !Le || !u_init || H < 1) return set_err(h, PGB_ERR_INVALID, "bad arguments");
-  if ((uint64_t)k_offset + (uint64_t)s->K > (1ull << 24)) return set_err(h, PGB_ERR_INVALID, "k_offset + K exceeds the 2^24 Philox stream ids");
+  if ((uint64_t)k_offset + (uint64_t)s->K_active > (1ull << 24)) return set_err(h, PGB_ERR_INVALID, "k_offset + K exceeds the 2^24 Philox stream ids");
   if (reuse && (!s->have_scen || H != s->H)) return set_err(h, PGB_ERR_STATE, "reuse needs a previous rollout of this set with the same horizon");
   int rc = samples_scen_alloc(s, H);
   if (rc) return rc;
   const int nx = h->cfg.n_x, ny = h->cfg.n_y, nu = h->cfg.n_u;
-  const int64_t K = s->K;
+  const int64_t K = s->K_active;
   cudaStream_t st = h->stream;
   FilterDev fd;
   memset(&fd, 0, sizeof(fd));
@@ -560,7 +561,7 @@ extern "C" int pgb_scenarios_get(pgb_samples* s, double* x0, double* v, double* 
   NEEDS(s);
   if (!s->have_scen) return set_err(h, PGB_ERR_STATE, "no rollout has run on this set");
   const int nx = h->cfg.n_x, ny = h->cfg.n_y;
-  const int64_t K = s->K, H = s->H;
+  const int64_t K = s->K_active, H = s->H;
   cudaStream_t st = h->stream;
   if (x0) CK(h, cudaMemcpyAsync(x0, s->x0, (size_t)K * nx * 8, cudaMemcpyDeviceToHost, st));
   if (v) CK(h, cudaMemcpyAsync(v, s->v, (size_t)K * H * nx * 8, cudaMemcpyDeviceToHost, st));
@@ -583,7 +584,7 @@ extern "C" int pgb_scenario_constraint_max_dev(pgb_samples* s, const double* y_m
   NEEDS(s);
   if (!y_min || !y_max || !h_max) return set_err(h, PGB_ERR_INVALID, "bad arguments");
   if (!s->have_scen) return set_err(h, PGB_ERR_STATE, "no rollout has run on this set");
-  const int64_t K = s->K, E = s->H * (int64_t)h->cfg.n_y;
+  const int64_t K = s->K_active, E = s->H * (int64_t)h->cfg.n_y;
   int64_t n_fin = 0;
   for (int64_t i = 0; i < E; ++i) n_fin += (std::isfinite(y_min[i]) ? 1 : 0) + (std::isfinite(y_max[i]) ? 1 : 0);
   if (n_fin == 0) return set_err(h, PGB_ERR_INVALID, "ArgumentError: no finite output bound: maximum over an empty collection");

@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
   }
   for (int64_t i = tid; i < H * nu; i += R_TPB) us[i] = rd.u_init[i];
   const int64_t nstage = N < R_WSTAGE ? N : R_WSTAGE;
-  for (int64_t i = tid; i < nstage; i += R_TPB) ws[i] = rd.w_m1[km * N + i];
+  if (!rd.x0_in && !rd.x_star)  // the weights are only read by the star draw
+    for (int64_t i = tid; i < nstage; i += R_TPB) ws[i] = rd.w_m1[km * N + i];
   // ---- chol(Q_k) (every thread; n_x <= 4)
   double Lq[NX * NX];
 #pragma unroll
@@ -309,7 +310,9 @@ __global__ void __launch_bounds__(R_TPB, PGB_ROLLOUT_MINBLOCKS) k_rollout(const 
   }
   // ---- star = systematic_resampling(w_m1, 1) (:58): W = w/sum(w) (tree), first n with q_n >= u   (thread 0)
   __syncthreads();
-  if (vt == 0 && !rd.x0_in) {
+  if (vt == 0 && !rd.x0_in && rd.x_star) {  // x_m1[:, star] drawn beforehand where the sample lives (k_draw_xT)
+    for (int d = 0; d < NX; ++d) sh.x[d] = rd.x_star[km * NX + d];
+  } else if (vt == 0 && !rd.x0_in) {
     const double* wg = rd.w_m1 + km * N;
 #define R_W(i) ((i) < nstage ? ws[(i)] : wg[(i)])
     double st[40];

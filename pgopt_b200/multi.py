@@ -14,14 +14,10 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def pack_samples(A_s, Q_s, x_T):
-    """A_s (n, K, n_x*n_phi), Q_s (n, K, n_x*n_x), x_T (n, K, n_x) -> (n, K, P) float64"""
-    return np.ascontiguousarray(np.concatenate([A_s, Q_s, x_T], axis=2), dtype=np.float64)
-
-
-def unpack_samples(pack, n_x, n_phi):
+def unpack_samples(pack, n_x, n_phi, n_u=1):
+    """packed records [A | Q | x_T | u_m1] (include/pgopt_b200.h: pgb_packed_record_doubles) -> (A, Q, x_T, u_m1)"""
     a, q = n_x * n_phi, n_x * n_x
-    return pack[..., :a], pack[..., a:a + q], pack[..., a + q:a + q + n_x]
+    return pack[..., :a], pack[..., a:a + q], pack[..., a + q:a + q + n_x], pack[..., a + q + n_x:a + q + n_x + n_u]
 
 
 def gather_packed(local_pack, n_total, dist=None, device=None):
@@ -62,33 +58,24 @@ def rollout_sharded(rollout_fn, K, dist=None, device=None):
     return out
 
 
-def draw_x_T(w_s, x_s, n_x, seed, chain_ids, resample):
-    """x_T = x_m1[:, star] with star ~ systematic_resampling(w_m1, 1) (optimal_control_Ipopt.jl:58-59), drawn on the
-    rank that owns the chain so that the N-sized particle arrays never travel."""
-    n, K, N = w_s.shape
-    out = np.empty((n, K, n_x))
-    for i in range(n):
-        rng = np.random.default_rng([seed, int(chain_ids[i])])
-        for k in range(K):
-            star = int(resample(w_s[i, k], 1, rng.random())[0])
-            out[i, k] = x_s[i, k].reshape((n_x, N), order="F")[:, max(star, 1) - 1]
-    return out
-
-
-def run_chains(engine_factory, n_chains, K, K_b, k_d, seed, dist=None, device=None, resample=None):
-    """Run `n_chains` independent chains sharded over the process group and gather packed (A, Q, x_T).
-    engine_factory(n_local, chain_base) -> a configured ParticleGibbsEngine (data, prior, state set)."""
+def run_chains(engine_factory, n_chains, K, K_b, k_d, seed, dist=None, device=None, roll_seed=0, record_doubles=None):
+    """Run `n_chains` independent chains sharded over the process group (one process per GPU) and gather the packed
+    [A | Q | x_T | u_m1] records.  engine_factory(n_local, chain_base) -> a configured ParticleGibbsEngine (data, prior,
+    state set).  x_T = x_m1[:, star] is drawn on the rank that owns the chain, on the device, from the scenario's own
+    Philox stream (roll_seed, id = global sample index) — the same star pgb_rollout would draw — so the N-sized particle
+    arrays never travel.  A rank that owns no chain creates no engine and contributes an empty block."""
     rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     lo, hi = shard_range(n_chains, rank, world)
-    if resample is None:
-        from .api import systematic_resampling as resample
-    eng = engine_factory(hi - lo, lo)
-    try:
-        eng.set_rng_philox(seed, lo)
-        A_s, Q_s, w_s, x_s, _ = eng.particle_gibbs(K, K_b, k_d)
-        x_T = draw_x_T(w_s, x_s, eng.n_x, seed, range(lo, hi), resample)
-        local = pack_samples(A_s, Q_s, x_T)
-    finally:
-        eng.close()
+    if hi > lo:
+        eng = engine_factory(hi - lo, lo)
+        try:
+            eng.set_rng_philox(seed, lo)
+            local = np.ascontiguousarray(eng.particle_gibbs_packed(K, K_b, k_d, roll_seed, lo * K), dtype=np.float64)
+        finally:
+            eng.close()
+    else:
+        if record_doubles is None:
+            raise ValueError("a rank without chains needs record_doubles to size its empty block")
+        local = np.zeros((0, K, record_doubles))
     return gather_packed(local, n_chains, dist, device)

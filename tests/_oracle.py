@@ -198,6 +198,16 @@ def rollout_supplied(model, K, H, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_init, see
     return dict(status=st, x0=x0, v=v, e=e, X=X, Y=Y)
 
 
+def draw_xT(w_m1, x_m1, seed, cid):
+    """x_m1 (N, n_x); returns x_m1[star] for star ~ systematic_resampling(w_m1, 1) with scenario stream cid"""
+    x_m1 = f64(x_m1)
+    N, n_x = x_m1.shape
+    out = np.zeros(n_x)
+    st = lib().orc_draw_xT(C.c_int64(N), C.c_int(n_x), _p(f64(w_m1)), _p(x_m1), C.c_uint64(seed), C.c_uint32(cid), _p(out))
+    assert st == 0
+    return out
+
+
 def test_prediction(model, K, k_n, T_test, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_test, y_test, seed):
     """orc_test_prediction: x_sim (K*k_n, T_test+1, n_x), y_sim (K*k_n, T_test, n_y), mean_rmse."""
     n_x, n_y = model.n_x, model.n_y

@@ -23,7 +23,7 @@ def _have_gpu():
 
 def test_exports_match_header():
     hdr = open(os.path.join(ROOT, "include", "pgopt_b200.h")).read()
-    declared = set(re.findall(r"\b(pgb_[a-z_0-9]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(pgb_[A-Za-z_0-9]+)\s*\(", hdr))
     declared.discard("pgb_last_error")  # matched below as well; keep explicit
     declared.add("pgb_last_error")
     L = _lib.lib()

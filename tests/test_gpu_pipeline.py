@@ -122,15 +122,10 @@ def test_device_pipeline_rollout_and_screening(n_y, rollout_kernel):
         # x_T drawn where the sample lives: the same star the rollout draws, and the rollout that uses it
         xT = ds.draw_xT(seed=8, k_offset=3)
         for k in range(K):
-            r1 = O.rollout(p["om"], 1, 1, p["N"], p["A"][k:k + 1], p["Q"][k:k + 1], p["w"][k:k + 1], p["x"][k:k + 1],
-                           p["um"][k:k + 1], p["Cm"], Le, p["u_init"][:, :1], seed=8, k_offset=3 + k)
-            assert r1["status"] == 0
+            _assert_same("x_T[%d]" % k, xT[k], O.draw_xT(p["w"][k], p["x"][k], 8, 3 + k))
         out2 = ds.rollout(pg.LinearMeasurement(p["Cm"]), R, H, u_init=p["u_init"], seed=8, k_offset=3).scenarios()
         for name in ("x0", "v", "e", "X", "Y"):
             _assert_same("with x_T " + name, out2[name], ref[name])
-        # x_T is a column of x_m1 of the right sample
-        for k in range(K):
-            assert any(np.array_equal(xT[k], p["x"][k, n]) for n in range(p["N"])), k
 
 
 @pytest.mark.parametrize("model,N,T,K,K_b,k_d,nc", [("known", 30, 80, 3, 2, 1, 2), ("hilbert", 200, 30, 2, 1, 0, 1),
@@ -186,3 +181,88 @@ def test_particle_gibbs_device_resident_samples(model, N, T, K, K_b, k_d, nc):
             _assert_same(name, dev[name], host[name])
     finally:
         ds.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# serialisation / checkpoint
+# ------------------------------------------------------------------------------------------------------------------
+def test_samples_pack_unpack_round_trip():
+    p = _scenario_problem(7, n_x=2, dims=(5, 5, 5), N=50, K=9, H=11)
+    batch = pg.PGSampleBatch(p["A"], p["Q"], p["w"], np.transpose(p["x"], (0, 2, 1)), p["um"])
+    g = pg.LinearMeasurement(p["Cm"])
+    with pg.DeviceSamples.from_samples(batch, p["basis"]) as ds:
+        ref = ds.rollout(g, 0.1, p["H"], u_init=p["u_init"], seed=3).scenarios()
+        full = ds.pack(with_particles=True)
+        xT = ds.draw_xT(seed=3)
+        slim = ds.pack(with_particles=False)
+        rec = ds.records()
+    assert bytes(full[:7]) == b"PGB200S" and int(np.frombuffer(full[8:12].tobytes(), dtype=np.uint32)[0]) == 1
+    R = 2 * 125 + 4 + 2 + 1
+    assert slim.size == 64 + 9 * R * 8 and full.size == 64 + 9 * (R + 50 + 100) * 8
+    for k in range(9):  # record = [A column-major | Q | x_T | u_m1]
+        _assert_same("A", rec[k, :250], p["A"][k].ravel(order="F"))
+        _assert_same("Q", rec[k, 250:254], p["Q"][k].ravel(order="F"))
+        _assert_same("x_T", rec[k, 254:256], xT[k])
+        _assert_same("u_m1", rec[k, 256:], p["um"][k])
+    # full layout -> a fresh set -> identical rollout (star re-drawn from w_m1 / x_m1)
+    with pg.DeviceSamples(p["basis"], 1, 50, 9) as d2:
+        d2.unpack(full)
+        b2 = d2.to_batch()
+        _assert_same("w", b2.w_m1, batch.w_m1)
+        _assert_same("x", b2.x_m1, batch.x_m1)
+        out = d2.rollout(g, 0.1, p["H"], u_init=p["u_init"], seed=3).scenarios()
+        for name in ("x0", "v", "e", "X", "Y"):
+            _assert_same("full " + name, out[name], ref[name])
+    # records only (what the NCCL gather moves): the rollout runs from x_T, no particle arrays needed
+    with pg.DeviceSamples(p["basis"], 1, 50, 12) as d3:
+        d3.unpack(slim)
+        out = d3.rollout(g, 0.1, p["H"], u_init=p["u_init"], seed=3).scenarios()
+        for name in ("x0", "v", "e", "X", "Y"):
+            _assert_same("slim " + name, out[name][:9], ref[name])
+        bad = slim.copy()
+        bad[0] = ord("X")
+        with pytest.raises(pg.PgoptError):
+            d3.unpack(bad)
+        with pytest.raises(pg.PgoptError):
+            d3.unpack(slim[:100])
+
+
+def test_checkpoint_resume_is_bit_identical():
+    """3 + 2 sweeps with a checkpoint / restore into a NEW handle in between == 5 sweeps straight (warm start of
+    particle_Gibbs.jl:114,126-128 made exact)."""
+    from test_gpu_parity import _models
+    basis, om, _ = _models()["known"]
+    N, T, nc = 500, 40, 2
+    u, y, _ = P.make_data(T, 61)
+
+    def engine():
+        e = pg.ParticleGibbsEngine(basis, 1, N, T, n_chains=nc)
+        e.set_data(u, y)
+        e.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+        e.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+        e.set_prior(10 * np.ones(5), 100 * np.eye(2), 10.0)
+        return e
+
+    with engine() as e:
+        for c in range(nc):
+            e.set_state(np.zeros((2, 5)), 100 * np.eye(2), None, 1, chain=c)
+        e.set_rng_philox(5, 7)
+        e.sweep(5)
+        ref = [e.get_state(c) for c in range(nc)]
+    with engine() as e:
+        for c in range(nc):
+            e.set_state(np.zeros((2, 5)), 100 * np.eye(2), None, 1, chain=c)
+        e.set_rng_philox(5, 7)
+        e.sweep(3)
+        ck = e.checkpoint()
+    assert bytes(ck[:7]) == b"PGB200C"
+    with engine() as e:
+        e.restore(ck)
+        e.sweep(2)
+        got = [e.get_state(c) for c in range(nc)]
+    for c in range(nc):
+        for a, b, name in zip(got[c], ref[c], ("A", "Q", "x_prim", "sweep_index")):
+            if name == "sweep_index":
+                assert a == b == 6
+            else:
+                _assert_same("chain %d %s" % (c, name), a, b)

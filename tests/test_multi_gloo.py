@@ -41,19 +41,26 @@ class OracleEngine:
             x_s[i] = r["x"].reshape(K_, -1)  # (N, n_x) C-order == (n_x, N) F-order
         return A_s, Q_s, w_s, x_s, self.u[:, -1]
 
+    def particle_gibbs_packed(self, K_, K_b, k_d, roll_seed, k_offset):
+        """what ParticleGibbsEngine.particle_gibbs_packed computes on the device: records [A | Q | x_T | u_m1] with the
+        star drawn from the scenario's Philox stream (optimal_control_Ipopt.jl:58-59)"""
+        A_s, Q_s, w_s, x_s, u_m1 = self.particle_gibbs(K_, K_b, k_d)
+        rec = np.empty((self.n_local, K_, 10 + 4 + 2 + 1))
+        for i in range(self.n_local):
+            for k in range(K_):
+                xT = O.draw_xT(w_s[i, k], x_s[i, k].reshape(N, 2), roll_seed, k_offset + i * K_ + k)
+                rec[i, k] = np.concatenate([A_s[i, k], Q_s[i, k], xT, u_m1])
+        return rec
+
     def close(self):
         pass
 
 
-def _resample(w, n, rnd):
-    return O.systematic_resampling(w, n, rnd)[0]
-
-
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, n_chains):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        got = multi.run_chains(OracleEngine, N_CHAINS, K, 3, 1, seed=9, dist=dist, resample=_resample)
+        got = multi.run_chains(OracleEngine, n_chains, K, 3, 1, seed=9, dist=dist, roll_seed=4, record_doubles=17)
         np.save(os.path.join(out_dir, "rank%d.npy" % rank), got)
     finally:
         dist.destroy_process_group()
@@ -69,18 +76,20 @@ def test_shard_range_covers_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_two_ranks_gather_equals_single_process(tmp_path):
+@pytest.mark.parametrize("n_chains", [N_CHAINS, 1])
+def test_two_ranks_gather_equals_single_process(tmp_path, n_chains):
+    """n_chains = 1: the second rank owns no chain, creates no engine and still takes part in the gather"""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    ref = multi.run_chains(OracleEngine, N_CHAINS, K, 3, 1, seed=9, dist=None, resample=_resample)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), n_chains), nprocs=2, join=True)
+    ref = multi.run_chains(OracleEngine, n_chains, K, 3, 1, seed=9, dist=None, roll_seed=4)
     for r in range(2):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npy" % r))
-        assert got.shape == (N_CHAINS, K, 10 + 4 + 2)
+        assert got.shape == (n_chains, K, 10 + 4 + 2 + 1)
         np.testing.assert_array_equal(got, ref)
-    A, Q, xT = multi.unpack_samples(ref, 2, 5)
-    assert A.shape == (N_CHAINS, K, 10) and Q.shape == (N_CHAINS, K, 4) and xT.shape == (N_CHAINS, K, 2)
+    A, Q, xT, um = multi.unpack_samples(ref, 2, 5)
+    assert A.shape == (n_chains, K, 10) and Q.shape == (n_chains, K, 4) and xT.shape == (n_chains, K, 2) and um.shape == (n_chains, K, 1)
 
 
 # ------------------------------------------------------------------------------------------ scenario sharding
