@@ -29,12 +29,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_PARTICLE_STEP = lambda n_x: 16 * n_x + 20      # x r+w, w r+w, Int32 ancestor
+BYTES_PER_PARTICLE_STEP = lambda n_x, f32=False: (8 * n_x + 12) if f32 else (16 * n_x + 20)  # x r+w, w r+w, Int32 ancestor
 FLOPS_PER_PARTICLE_STEP = {"generic": 1250.0, "known": 100.0}
-# dram__bytes_read.sum + dram__bytes_write.sum of k_sweep_persistent per particle-step, from the committed `ncu --set full`
-# captures at N = 2^20, T = 24 (profiles/r01_final_persistent_generic_N2p20.md, profiles/r01_ncu_persistent_v1_known_N2p20.md)
-NCU_DRAM_BYTES_PER_PARTICLE_STEP = {"generic": (2.665312e9 + 430.749184e6) / (23 * 2 ** 20),
-                                    "known": (1.962611e9 + 61.51808e6) / (23 * 2 ** 20)}
+# dram__bytes_read.sum + dram__bytes_write.sum of the sweep kernel (k_sweep_v2) per particle-step, from the committed
+# `ncu --set full` captures at N = 2^20, T = 24 (profiles/r02_v2_sweep_kernel_N2p20.md)
+NCU_DRAM_BYTES_PER_PARTICLE_STEP = {"generic": (3.514112e6 + 891.111936e6) / (23 * 2 ** 20),
+                                    "known": (1.25184e6 + 798.978304e6) / (23 * 2 ** 20)}
 
 
 # ------------------------------------------------------------------------------------------- workload
@@ -134,7 +134,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-PROF_NAMES = ["k_prep", "k_norm", "k_scan_local", "k_resolve", "k_sweep_persistent (whole T loop)", "k_seq_exact",
+PROF_NAMES = ["k_prep", "k_norm", "k_scan_local", "k_resolve", "k_sweep_v2 (whole T loop)", "k_seq_exact",
               "k_expand_fallback", "k_weights", "k_build_utabs", "tail(trace+stats)", "k_mniw"]
 PHASE_NAMES = ["init", "A prep (w, F, waN)", "wait B1", "B scan-local main", "B normalise side", "wait B2", "C resolve",
                "C exact prefixes + expansion", "C ancestor shortcut", "wait B3", "D ancestor index", "D heavy + weights",
@@ -176,7 +176,8 @@ def run_gpu(args):
     N, T = args.particles, args.T
     prob = build_problem(args.model, T, seed=0)
     n_x, n_u, n_y, n_phi = 2, 1, 1, prob["n_phi"]
-    eng = pg.ParticleGibbsEngine(prob["basis"], 1, N, T, n_chains=1, device=local)
+    f32 = args.dtype == "f32"
+    eng = pg.ParticleGibbsEngine(prob["basis"], 1, N, T, n_chains=1, device=local, precision=args.dtype)
     eng.set_data(prob["u"], prob["y"])
     eng.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
     eng.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
@@ -270,43 +271,44 @@ def run_gpu(args):
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_sample(args.model, args.cpu_particles, args.cpu_T)
+        cpu = cpu_sample(args.model, args.cpu_particles, args.cpu_T, f32=f32)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        bps = BYTES_PER_PARTICLE_STEP(n_x)
+        bps = BYTES_PER_PARTICLE_STEP(n_x, f32)
         t_per_sweep = t_total / args.steps
         achieved = bps * N * (T - 1) / t_per_sweep / 1e9
         out = {
             "metric": "CPF-AS particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_per_sweep, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "CPF-AS conditional sweep (k>1), %s-basis model n_x=2 n_phi=%d, N=%d particles, T=%d, "
                                    "Philox streams, ancestor history stored in HBM, x history %s; BASELINE.json configs[2]"
                                    % (args.model, n_phi, N, T, "stored" if N * T * n_x * 8 <= 2 ** 30 else
                                       "replayed (two rows kept, traced lineage recomputed)"),
                        "N": N, "T": T, "n_phi": n_phi, "chains_per_gpu": 1,
-                       "l2": "per-step working set (~100 MB of rolling buffers) re-streamed every step; ancestor history "
-                             "(%d GB) written once, larger than L2" % (N * T * 4 >> 30)},
+                       "l2": "inputs of a step (x_{t-1}, lw, F: 40 MB at N = 2^20) are re-read from L2 every step; the ancestor "
+                             "history (%d GB) is written once, larger than L2" % (N * T * 4 >> 30)},
             "pg_sweeps_per_s": sweeps_per_s,
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "includes": "set_data+set_state H2D, filter+trace+stats+MNIW, get_sample D2H"},
             "gpu_launches": int(n1.value - n0.value),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_PARTICLE_STEP[args.model] * N * (T - 1) / 1e9 if N == 2 ** 20 else None,
-                         "traffic_unit": "GB per launch (ncu DRAM bytes per particle-step at T=24, x this launch's particle-steps); "
-                                         "above the algorithmic bytes because the ~100 MB of rolling per-step buffers are written "
-                                         "back from L2 every step", "peak_source": peak_src,
-                         "kernel": "k_sweep_persistent: one cooperative launch = one whole conditional sweep (T-1 steps x 4 grid barriers); "
-                                   "%d launches per sweep in total" % ((n1.value - n0.value) // max(1, args.steps)),
+                         "traffic": NCU_DRAM_BYTES_PER_PARTICLE_STEP[args.model] * N * (T - 1) / 1e9 if (N == 2 ** 20 and not f32) else None,
+                         "traffic_unit": "GB per launch (ncu DRAM bytes per particle-step of the FP64 kernel at T=24, x this launch's "
+                                         "particle-steps); below the algorithmic bytes: x_{t-1} / F / lw are re-read out of L2, the per-CTA "
+                                         "weight arrays never leave shared memory", "peak_source": peak_src,
+                         "kernel": "k_sweep_v2 (chunk-stationary): one cooperative launch = one whole conditional sweep (T-1 steps x 4 grid "
+                                   "barriers); %d launches per sweep in total" % ((n1.value - n0.value) // max(1, args.steps)),
                          "algorithmic_bytes_per_particle_step": bps,
                          "dominant_kernel": dom, "dominant_share": prof[dom]["ms"] / tot_prof,
                          "fp64": {"algorithmic_tflops_achieved": FLOPS_PER_PARTICLE_STEP[args.model] * N * (T - 1) / t_per_sweep / 1e12,
                                   "dfma_peak_tflops_measured": fp64_peak.value,
                                   "flops_per_particle_step": FLOPS_PER_PARTICLE_STEP[args.model]},
-                         "note": "measured: the path is instruction-/latency-bound in FP64 (divisions, exp/log/sin/cos, Philox, "
-                                 "exact-scan integer algebra) with DRAM ~5% busy; see DESIGN.md section 5 and profiles/"},
+                         "note": "measured (ncu, profiles/r02_v2_sweep_kernel_N2p20.md): instruction-bound — 2 600 (generic) / 1 600 (known) "
+                                 "thread instructions per particle-step (bit-defined exp/log/sin/cos, Philox, exact divisions, "
+                                 "exact-scan integer algebra), issue slots 55 % busy, DRAM ~10 % busy"},
             "kernel_profile_ms_per_sweep": prof,
             "resampling": {"status_bits": st, "exact_scans": nscan, "serial_fallbacks": nfb},
         }
@@ -418,8 +420,113 @@ def _small_config(model, n_chains, sweeps, N=30, T=2000):
         eng.close()
 
 
+# ------------------------------------------------------------------------------------------- sharded workloads
+def _c5_problem(K, H=41, N=30, seed=7):
+    import pgopt_b200 as pg
+    basis = pg.HilbertGPBasis([1, 5, 5, 5, 5], [4.0, 5.0, 6.0, 7.0, 8.0])  # n_x = 4, n_u = 1, n_phi = 5^4 = 625
+    n_x, n_phi = 4, basis.n_phi
+    rng = np.random.default_rng(seed)
+    A = rng.normal(0, 0.05, (K, n_x, n_phi))
+    B = rng.normal(0, 0.1, (K, n_x, n_x))
+    Q = B @ np.transpose(B, (0, 2, 1)) + 0.05 * np.eye(n_x)
+    w = rng.uniform(size=(K, N))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, n_x, N))
+    um = rng.normal(0, 1, (K, 1))
+    Cm = np.zeros((1, n_x))
+    Cm[0, 0] = 1.0
+    return dict(basis=basis, batch=pg.PGSampleBatch(A, Q, w, x, um), Cm=Cm, u_init=np.sin(np.arange(H))[None, :], H=H, N=N,
+                n_x=n_x, n_phi=n_phi)
+
+
+def run_c5(args):
+    """BASELINE.json configs[4]: K = 10^5 posterior samples x H = 41, n_x = 4, n_phi = 625, scenario-sharded over the
+    GPUs of the node through pgb_multi_* (ONE process, in-process NCCL): the samples are resident where they live
+    (uploaded once, untimed — in the pipeline they come from the chains that ran there), the timed call is the whole
+    pgb_multi_rollout: rollout kernels on every device + NCCL all-gather of x_vec_0 / X / Y + D2H into pinned host
+    arrays.  Strong scaling (K fixed)."""
+    import pgopt_b200 as pg
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    K, n_dev = args.scenarios, args.gpus
+    p = _c5_problem(K)
+    H, n_x = p["H"], p["n_x"]
+    g = pg.LinearMeasurement(p["Cm"])
+    out = dict(x0=pg.pinned_empty((K, n_x)), X=pg.pinned_empty((K, H + 1, n_x)), Y=pg.pinned_empty((K, H, 1)))
+    with pg.MultiGPUEngine(p["basis"], 1, p["N"], 2, n_dev, list(range(n_dev))) as m:
+        t0 = time.perf_counter()
+        m.set_samples(p["batch"], roll_seed=1)
+        t_up = time.perf_counter() - t0
+        calls = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            m.rollout(g, 0.1, H, u_init=p["u_init"], seed=1, out=out)
+            if i >= args.warmup:
+                calls.append(time.perf_counter() - t0)
+        ms = m.last_ms()
+    call = float(np.mean(calls))
+    bytes_alg = K * 8 * (n_x * p["n_phi"] + n_x * n_x + n_x + 1 + (2 * H + 2) * n_x + 2 * H)
+    peak, _ = measured_peaks()
+    print(json.dumps({
+        "workload": "c5", "metric": "scenario-steps/s, whole host call (kernels on all GPUs + NCCL gather + D2H)",
+        "value": K * H / call, "unit": "scenario-steps/s", "n_gpus": n_dev, "scaling": "strong", "steps": args.steps,
+        "warmup": args.warmup, "host_call_ms": 1e3 * call, "rollout_kernel_ms_max_over_devices": ms["rollout_kernel_ms_max"],
+        "nccl_gather_ms": ms["scenario_gather_ms"], "kernel_scenario_steps_per_s": K * H / (1e-3 * ms["rollout_kernel_ms_max"]),
+        "d2h_bytes_per_call": int(sum(v.nbytes for v in out.values())), "sample_upload_s_untimed": t_up,
+        "roofline": {"bound": "fp64", "flops_per_scenario_step": 6600.0,
+                     "achieved_tflops": 6600.0 * K * (H + 1) / (1e-3 * ms["rollout_kernel_ms_max"]) / 1e12 / n_dev,
+                     "hbm_GBps_per_gpu": bytes_alg / n_dev / (1e-3 * ms["rollout_kernel_ms_max"]) / 1e9, "hbm_peak_GBps": peak},
+        "config": {"workload": "scenario rollout K=%d x H=%d, n_x=4, n_phi=625 (BASELINE.json configs[4]), sharded over %d GPU(s) "
+                               "through pgb_multi_rollout" % (K, H, n_dev)},
+        "finite": bool(np.isfinite(out["X"]).all())}))
+
+
+def run_c4(args):
+    """BASELINE.json configs[3]: 64 independent PG chains x N = 2^16 (T = 2000, known basis), chain-sharded over the GPUs
+    of the node through pgb_multi_* (one process, one host thread per device), K kept samples per chain (K_b = k_d = 0,
+    so K sweeps per chain), then x_T drawn on the owning GPU and ONE NCCL all-gather of the packed [A | Q | x_T | u_m1]
+    records.  Strong scaling (64 chains fixed).  `value` counts the whole sampler call incl. the gather and the D2H of
+    the records; handle creation (4 GB of ancestor history per 8 chains) is reported beside it."""
+    import pgopt_b200 as pg
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    n_chains, N, T, K, n_dev = args.chains, args.chain_particles, args.T, args.kept, args.gpus
+    prob = build_problem("known", T, 0)
+    t0 = time.perf_counter()
+    m = pg.MultiGPUEngine(prob["basis"], 1, N, T, n_chains, list(range(n_dev)))
+    t_create = time.perf_counter() - t0
+    try:
+        m.set_data(prob["u"], prob["y"])
+        m.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+        m.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+        m.set_prior(prob["V"], 100 * np.eye(2), 10.0)
+        times = []
+        for i in range(2):  # first pass = warm-up (module load, first cooperative launch), second timed
+            m.set_state(prob["A"], prob["Q"], prob["x_prim"], 1)
+            m.set_rng_philox(7, 0)
+            t0 = time.perf_counter()
+            rec = m.particle_gibbs(K if i else 1, 0, 0, roll_seed=3)
+            times.append(time.perf_counter() - t0)
+        ms = m.last_ms()
+    finally:
+        m.close()
+    dt = times[1]
+    print(json.dumps({
+        "workload": "c4", "metric": "PG sweeps/s over all chains (filter + trace + statistics + MNIW + device-side sample store), "
+                                     "incl. the x_T draw, the NCCL gather of the packed records and their D2H",
+        "value": n_chains * K / dt, "unit": "PG sweeps/s", "n_gpus": n_dev, "scaling": "strong", "n_chains": n_chains,
+        "N": N, "T": T, "K_kept_per_chain": K, "seconds": dt, "particle_steps_per_s": n_chains * K * N * (T - 1) / dt,
+        "nccl_gather_ms": ms["sample_gather_ms"], "handle_creation_s": t_create, "warmup_call_s": times[0],
+        "records_shape": list(rec.shape), "finite": bool(np.isfinite(rec).all()),
+        "config": {"workload": "%d chains x N=%d, T=%d, known basis, K=%d kept samples per chain (BASELINE.json configs[3] with K "
+                               "bounded), sharded over %d GPU(s) through pgb_multi_particle_gibbs" % (n_chains, N, T, K, n_dev)}}))
+
+
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(model, Ns, Ts, threads=None):
+_SINGLE_CORE = {}
+
+
+def cpu_sample(model, Ns, Ts, threads=None, f32=False):
     """Oracle (C restatement of particle_Gibbs.jl) timed on a bounded sample of the workload.  The reference sampler
     is single-threaded (particle_Gibbs.jl:154-230); the host cores are used the only way the path shards — one
     independent chain per thread (ctypes releases the GIL during the C call) — and the aggregate is reported."""
@@ -434,21 +541,25 @@ def cpu_sample(model, Ns, Ts, threads=None):
         om = O.known_model() if model == "known" else O.hilbert_model(2, 1, b.count, b.stride, b.L)
         st = O.make_streams(philox=True, seed=1234, chain=chain)
         O.sweep(om, Ns, Ts, prob["u"], prob["y"], [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), prob["A"], prob["Q"],
-                prob["x_prim"], False, st, 2, hist=False)
+                prob["x_prim"], False, st, 2, hist=False, f32=f32)
 
     O.lib()
-    t0 = time.perf_counter()
-    one(0)
-    t1 = time.perf_counter() - t0
+    key = (model, Ns, Ts, f32)
+    if key not in _SINGLE_CORE:  # the like-for-like figure (the reference sampler is single-threaded): measured once
+        t0 = time.perf_counter()
+        one(0)
+        _SINGLE_CORE[key] = time.perf_counter() - t0
+    t1 = _SINGLE_CORE[key]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
         list(ex.map(one, range(threads)))
     dt = time.perf_counter() - t0
     return {"value": threads * Ns * (Ts - 1) / dt, "unit": "particle-steps/s", "cores": threads, "kind": "port",
             "single_core_value": Ns * (Ts - 1) / t1,
-            "sample": "%d independent conditional sweeps of the same model at N=%d, T=%d, one per host thread (%.1f s wall; "
-                      "one sweep alone: %.1f s); the reference sampler itself is single-threaded "
-                      "(particle_Gibbs.jl:154-230)" % (threads, Ns, Ts, dt, t1)}
+            "sample": "%d independent conditional sweeps of the same model at the workload's N=%d with T reduced to %d, one per "
+                      "host thread (%.1f s wall; one sweep alone on one thread: %.1f s); the reference sampler itself is "
+                      "single-threaded (particle_Gibbs.jl:154-230), so single_core_value is the like-for-like figure and "
+                      "value the best the box's cores can do with independent chains" % (threads, Ns, Ts, dt, t1)}
 
 
 def run_reference(args):
@@ -457,7 +568,8 @@ def run_reference(args):
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_sample(args.model, args.cpu_particles, args.cpu_T)
+        # warm-up passes (page faults of the history arrays, thread pool) run 2 time steps; the timed ones the stated sample
+        r = cpu_sample(args.model, args.cpu_particles, args.cpu_T if i >= args.warmup else 3, f32=(args.dtype == "f32"))
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([r["value"] for r in vals]))
@@ -465,9 +577,11 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "CPF-AS particle-steps/sec", "value": v, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "CPF-AS conditional sweep (k>1), %s-basis model, bounded sample N=%d, T=%d of the "
-                               "N=%d, T=%d workload" % (args.model, args.cpu_particles, args.cpu_T, args.particles, args.T)},
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "CPF-AS conditional sweep (k>1), %s-basis model, N=%d particles, T=%d (bounded sample of the "
+                               "N=%d, T=%d workload: same N, fewer time steps; the per-particle-step cost does not depend on T)"
+                               % (args.model, args.cpu_particles, args.cpu_T, args.particles, args.T),
+                   "N": args.cpu_particles, "T": args.cpu_T, "same_N_as_gpu_arm": args.cpu_particles == args.particles},
         "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": vals[-1]["cores"], "kind": "port",
                          "single_core_value": vals[-1]["single_core_value"], "sample": vals[-1]["sample"]},
         "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -482,16 +596,32 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="generic", choices=["generic", "known"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="f64: the reference's arithmetic (default, the headline); f32: the F32 precision mode "
+                         "(FP32 particle state / basis / noise / log-weights, FP64 normalisation and cumulative sums)")
     ap.add_argument("--particles", type=int, default=2 ** 20)
     ap.add_argument("--T", type=int, default=2000)
-    ap.add_argument("--cpu-particles", type=int, default=2 ** 13)
-    ap.add_argument("--cpu-T", type=int, default=200)
+    ap.add_argument("--cpu-particles", type=int, default=2 ** 20,
+                    help="particles of the CPU sample: the workload's own N = 2^20 by default (the oracle's rate per particle-step is "
+                         "flat in N: README, profiles/r02_cpu_oracle_rate_vs_N.json)")
+    ap.add_argument("--cpu-T", type=int, default=6, help="time steps of the CPU sample (reduced from T = 2000: stated in the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the bounded rollout / chain-batch side measurements")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "c4", "c5"],
+                    help="sweep: the headline CPF-AS sweep (default; the driver's contract).  c4 / c5: BASELINE.json configs[3] / [4] "
+                         "sharded over --gpus devices from ONE process through pgb_multi_* (run with plain python)")
+    ap.add_argument("--scenarios", type=int, default=100000)
+    ap.add_argument("--chains", type=int, default=64)
+    ap.add_argument("--chain-particles", type=int, default=2 ** 16)
+    ap.add_argument("--kept", type=int, default=8)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "c5":
+        run_c5(args)
+    elif args.workload == "c4":
+        run_c4(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -247,6 +247,18 @@ int pgb_scenarios_get(pgb_samples* s, double* x0, double* v, double* e, double* 
 /* pgb_scenario_constraint_max on the Y of the last pgb_rollout_dev, read where the rollout left it */
 int pgb_scenario_constraint_max_dev(pgb_samples* s, const double* y_min, const double* y_max, double* h_max,
                                     int64_t* order);
+/* One step of the stacked K-scenario model and its Jacobians on the resident samples:
+ * RobotDynamics.discrete_dynamics[!] of PGS_model_obj, x_vec_n[k] = A_k*phi(x_vec[k], u) + v_vec[:, t+1, k]
+ * (Julia/src/optimal_control_Altro.jl:79-107), and what RobotDynamics.@autodiff (:51) derives from it.
+ * x_vec: host [K*n_x] in the reference's stacking (scenario k = rows n_x*(k-1)+1 .. n_x*k); u [n_u]; t >= 0 adds the
+ * process noise column t (0-based) the last pgb_rollout_dev left on the device, t < 0 adds none; phi_variant 0 = the
+ * rounding of phi_sampling, 1 = of the examples' phi_opt (examples/PG_OCP_generic_basis_functions_Altro.jl:204-217).
+ * Outputs (host): x_next [K*n_x]; dfdx [K][n_x*n_x] — the diagonal blocks of the (K n_x) x (K n_x) Jacobian, column-major;
+ * dfdu [K][n_x*n_u] — the rows of the (K n_x) x n_u Jacobian, column-major per scenario.  dfdx / dfdu may be NULL.
+ * With phi_variant 0, x_next is bit-identical to the X[t+1] the rollout computes from the same state. */
+int pgb_dynamics_dev(pgb_samples* s, const double* x_vec, const double* u, int64_t t, int32_t phi_variant, double* x_next,
+                     double* dfdx, double* dfdu);
+int pgb_dynamics_last_ms(pgb_samples* s, double* kernel_ms);
 /* device time (CUDA events, ms) of the last rollout kernel / screening kernel / input upload of this set */
 int pgb_samples_last_ms(pgb_samples* s, double* rollout_kernel_ms, double* screening_kernel_ms, double* upload_ms);
 /* page-locked host memory for the caller's I/O arrays (NULL on failure) */
@@ -288,9 +300,13 @@ int pgb_multi_get_sample(pgb_multi* m, int32_t chain, int64_t k, double* A, doub
 int pgb_multi_set_samples(pgb_multi* m, int64_t K_total, const double* A, const double* Q, const double* w_m1,
                           const double* x_m1, const double* u_m1, uint64_t roll_seed);
 /* scenario rollout of all resident samples, each device its own, then one all-gather of x_vec_0 / X / Y; host outputs
- * (may be NULL) in global order, layouts of pgb_rollout.  seed = the roll_seed the x_T were drawn with. */
+ * (may be NULL) in global order, layouts of pgb_rollout — each device sends its own block over its own PCIe link while
+ * the NVLink gather runs.  seed = the roll_seed the x_T were drawn with. */
 int pgb_multi_rollout(pgb_multi* m, int64_t H, const double* C, const double* Le, const double* u_init, uint64_t seed,
                       double* x0, double* X, double* Y);
+/* the gathered scenario arrays as device which_device of the list holds them after pgb_multi_rollout (every device holds
+ * all of them: what a solver running on any GPU reads); host outputs may be NULL */
+int pgb_multi_get_scenarios(pgb_multi* m, int32_t which_device, double* x0, double* X, double* Y);
 /* device-side times (CUDA events, ms): NCCL gather of the packed samples; slowest device's rollout kernel; NCCL gather
  * of the scenario arrays */
 int pgb_multi_last_ms(pgb_multi* m, double* sample_gather_ms, double* rollout_kernel_ms_max, double* scenario_gather_ms);
@@ -316,7 +332,9 @@ int pgb_checkpoint_load(pgb_handle* h, const void* buf, int64_t buf_bytes);
  * pgb_test_force_fallback(1) makes every exact scan take the serial-walk fallback path, (2) makes the ancestor
  * draw use the exact scan instead of the certified approximate shortcut (results must not change); pgb_test_math evaluates the device build of pgb_math.h: fn 0 exp, 1 log, 2 sin, 3 cos,
  * 4 Box-Muller pairs from Philox (x[0] = seed, y gets 2n normals of purpose Z, sweep 1, t 5);
- * 10..14: the same through the 4-wide branch-free versions of pgb_vmath.cuh (11: positive normal arguments). */
+ * 10..14: the same through the 4-wide branch-free versions of pgb_vmath.cuh (11: positive normal arguments);
+ * 30..34: the FP32 functions of pgb_mathf.h (exp, log, sin, cos, wide-range exp) on (float)x, result widened; 35: y gets
+ * 4n FP32 normals (pgf_stream_normals of particles 0..n-1, x[0] = seed). */
 void pgb_test_force_fallback(int32_t on);
 int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_t n);
 /* DFMA micro-benchmark (8 independent chains per thread, all SMs): measured FP64 FMA rate of the device. */

@@ -15,7 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../pgopt_b200/csrc/pgb_math.h"
+#include "../pgopt_b200/csrc/pgb_mathf.h"
 
 #define LOG2PI 1.8378770664093453 /* Float64(log(2*pi)) */
 
@@ -28,6 +28,14 @@ void orc_vnormal_pairs(uint64_t seed, uint32_t purpose, uint32_t chain, uint32_t
                        int64_t npairs, double* z) {
   for (int64_t j = 0; j < npairs; ++j)
     pgb_normal_pair(pgb_stream_block(seed, purpose, chain, sweep, t, (uint32_t)j), &z[2 * j], &z[2 * j + 1]);
+}
+void orc_vmathf(int fn, const float* x, float* y, int64_t n) {
+  for (int64_t i = 0; i < n; ++i)
+    y[i] = fn == 0 ? pgf_exp(x[i]) : fn == 1 ? pgf_log_pos_normal(x[i]) : fn == 2 ? pgf_sin(x[i]) : fn == 3 ? pgf_cos(x[i]) : (float)pgf_exp_wide(x[i]);
+}
+void orc_vnormal_pairs_f32(uint64_t seed, uint32_t purpose, uint32_t chain, uint32_t sweep, uint32_t t, int64_t n,
+                           int n_x, float* z) {
+  for (int64_t j = 0; j < n; ++j) pgf_stream_normals(seed, purpose, chain, sweep, t, (uint32_t)j, n_x, &z[j * n_x]);
 }
 int orc_selftest(void) { return pgb_math_selftest(); }
 
@@ -235,11 +243,105 @@ static double log_weight(const orc_model* m, const double* C, const double* R, c
 }
 
 /* ------------------------------------------------------------------ one PG sweep */
+/* ------------------------------------------------------------------ F32 precision mode (PGB_PRECISION_F32)
+ * The north star's "FP32 particle state": particle states, basis functions, A*phi, process noise, log-weights and the two
+ * exponentials per particle are evaluated in FP32 with the bit-defined functions of pgb_mathf.h; every model constant is
+ * rounded to FP32 ONCE ((float)A, (float)chol(Q), (float)C, ...).  The un-normalised weights e = exp(lw - max) and the
+ * transition densities are widened to FP64 and everything downstream — the two normalisations, the sequential
+ * cumulative sums of systematic resampling / ancestor sampling, the backward trace, the statistics, MNIW — is the FP64
+ * code above, so index parity with the kernels is again bit-exact.  The history arrays keep FP64 storage holding
+ * FP32 values. */
+static void orc_phi_f32(const orc_model* m, const float* x, const double* u, float* phi) {
+  if (m->basis == ORC_BASIS_KNOWN_VB) {
+    const float u0 = (float)u[0];
+    phi[0] = PGF_MUL(0.1f, x[0]);
+    phi[1] = PGF_MUL(0.1f, x[1]);
+    phi[2] = u0;
+    phi[3] = PGF_MUL(PGF_MUL(0.01f, pgf_cos(PGF_MUL(3.0f, x[0]))), x[1]);
+    phi[4] = PGF_MUL(PGF_MUL(0.1f, pgf_sin(PGF_MUL(2.0f, x[1]))), u0);
+    return;
+  }
+  int n_z = m->n_u + m->n_x;
+  float z[ORC_MAX_Z];
+  for (int k = 0; k < m->n_u; ++k) z[k] = (float)u[k];
+  for (int k = 0; k < m->n_x; ++k) z[m->n_u + k] = x[k];
+  const double PI = 3.141592653589793;
+  for (int i = 0; i < m->n_phi; ++i) {
+    float p = 1.0f;
+    for (int k = 0; k < n_z; ++k) {
+      double j = (double)((i / m->stride[k]) % m->count[k] + 1);
+      const float pij2l = (float)((PI * j) / (2.0 * m->L[k])); /* the FP64 constants of orc_phi, rounded once */
+      const float lsi = (float)(1.0 / sqrt(m->L[k]));
+      const float arg = PGF_MUL(pij2l, PGF_ADD(z[k], (float)m->L[k]));
+      p = PGF_MUL(p, PGF_MUL(lsi, pgf_sin(arg)));
+    }
+    phi[i] = p;
+  }
+}
+static void eval_f_f32(const orc_model* m, const double* A, const float* x, const double* u, float* phi_tmp, float* out) {
+  orc_phi_f32(m, x, u, phi_tmp);
+  for (int d = 0; d < m->n_x; ++d) {
+    float acc = 0.0f;
+    for (int i = 0; i < m->n_phi; ++i) acc = PGF_FMA((float)A[d + m->n_x * i], phi_tmp[i], acc);
+    out[d] = acc;
+  }
+}
+static float log_weight_f32(const orc_model* m, const double* C, const double* R, const double* Rchol, const float* x,
+                            const double* y) {
+  int n_y = m->n_y, n_x = m->n_x;
+  if (n_y == 1) {
+    float g = 0.0f;
+    for (int d = 0; d < n_x; ++d) g = PGF_FMA((float)C[n_y * d], x[d], g);
+    const float dd = PGF_SUB(g, (float)y[0]);
+    return PGF_DIV(PGF_MUL(-PGF_MUL(dd, dd), 0.5f), (float)R[0]);
+  }
+  float r[ORC_MAX_Z];
+  for (int o = 0; o < n_y; ++o) {
+    float g = 0.0f;
+    for (int d = 0; d < n_x; ++d) g = PGF_FMA((float)C[o + n_y * d], x[d], g);
+    r[o] = PGF_SUB((float)y[o], g);
+  }
+  for (int d = 0; d < n_y; ++d) { /* forward substitution with (float)chol(R) */
+    float acc = r[d];
+    for (int e = 0; e < d; ++e) acc = PGF_FMA(-(float)Rchol[d + n_y * e], r[e], acc);
+    r[d] = PGF_DIV(acc, (float)Rchol[d + n_y * d]);
+  }
+  float sacc = 0.0f;
+  for (int o = 0; o < n_y; ++o) sacc = PGF_FMA(r[o], r[o], sacc);
+  return PGF_MUL(-sacc, 0.5f);
+}
+static void stream_normals_f32(const orc_streams* s, uint32_t purpose, uint32_t sweep, uint32_t t, int64_t j, int n_x, float* z) {
+  pgf_stream_normals(s->seed, purpose, s->chain, sweep, t, (uint32_t)j, n_x, z);
+}
+
+static int sweep_impl(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y, const double* C,
+              const double* R, const double* x0_mean, const double* x0_chol, const double* A, const double* Q,
+              double* x_prim, int first, const orc_streams* s, uint32_t sweep_index, int64_t* a_hist,
+              double* x_hist, double* w_hist, double* w_last, double* x_last, double* Phi, double* Psi,
+              double* Sigma, int64_t* star_out, int f32);
+
 int orc_sweep(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y, const double* C,
               const double* R, const double* x0_mean, const double* x0_chol, const double* A, const double* Q,
               double* x_prim, int first, const orc_streams* s, uint32_t sweep_index, int64_t* a_hist,
               double* x_hist, double* w_hist, double* w_last, double* x_last, double* Phi, double* Psi,
               double* Sigma, int64_t* star_out) {
+  return sweep_impl(m, N, T, u, y, C, R, x0_mean, x0_chol, A, Q, x_prim, first, s, sweep_index, a_hist, x_hist, w_hist, w_last,
+                    x_last, Phi, Psi, Sigma, star_out, 0);
+}
+int orc_sweep_f32(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y, const double* C,
+                  const double* R, const double* x0_mean, const double* x0_chol, const double* A, const double* Q,
+                  double* x_prim, int first, const orc_streams* s, uint32_t sweep_index, int64_t* a_hist,
+                  double* x_hist, double* w_hist, double* w_last, double* x_last, double* Phi, double* Psi,
+                  double* Sigma, int64_t* star_out) {
+  return sweep_impl(m, N, T, u, y, C, R, x0_mean, x0_chol, A, Q, x_prim, first, s, sweep_index, a_hist, x_hist, w_hist, w_last,
+                    x_last, Phi, Psi, Sigma, star_out, 1);
+}
+
+static int sweep_impl(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y, const double* C,
+              const double* R, const double* x0_mean, const double* x0_chol, const double* A, const double* Q,
+              double* x_prim, int first, const orc_streams* s, uint32_t sweep_index, int64_t* a_hist,
+              double* x_hist, double* w_hist, double* w_last, double* x_last, double* Phi, double* Psi,
+              double* Sigma, int64_t* star_out, int f32) {
   const int n_x = m->n_x, n_u = m->n_u, n_y = m->n_y, n_phi = m->n_phi;
   int status = 0;
   /* full histories are needed for the backward trace (:213-218) */
@@ -251,6 +353,7 @@ int orc_sweep(const orc_model* m, int64_t N, int64_t T, const double* u, const d
   double* waN = (double*)malloc(sizeof(double) * (size_t)N);
   double* F = (double*)malloc(sizeof(double) * (size_t)(N * n_x));
   double* phi_tmp = (double*)malloc(sizeof(double) * (size_t)n_phi);
+  float* phi_tmp_f = (float*)malloc(sizeof(float) * (size_t)n_phi);
   int64_t* idx = (int64_t*)malloc(sizeof(int64_t) * (size_t)N);
   double Lq[ORC_MAX_Z * ORC_MAX_Z], Rchol[ORC_MAX_Z * ORC_MAX_Z], z[ORC_MAX_Z], r[ORC_MAX_Z];
 
@@ -269,9 +372,20 @@ int orc_sweep(const orc_model* m, int64_t N, int64_t T, const double* u, const d
 
   /* x_pf[:, end, :] .= x_prim (:160) */
   for (int64_t t = 0; t < T; ++t)
-    for (int d = 0; d < n_x; ++d) xh[(t * N + (N - 1)) * n_x + d] = x_prim[d + n_x * t];
+    for (int d = 0; d < n_x; ++d) xh[(t * N + (N - 1)) * n_x + d] = f32 ? (double)(float)x_prim[d + n_x * t] : x_prim[d + n_x * t];
   /* initial states (:163-165): rand(x_init_dist) = mean + L*z */
+  float zf[ORC_MAX_Z], xf[ORC_MAX_Z], Ff[ORC_MAX_Z];
   for (int64_t n = 0; n < N - 1; ++n) {
+    if (f32) {
+      if (s->philox) stream_normals_f32(s, PGB_STREAM_Z0, sweep_index, 0, n, n_x, zf);
+      else for (int d = 0; d < n_x; ++d) zf[d] = (float)s->Z0[n * n_x + d];
+      for (int d = 0; d < n_x; ++d) {
+        float acc = 0.0f;
+        for (int e = 0; e <= d; ++e) acc = PGF_FMA((float)x0_chol[d + n_x * e], zf[e], acc);
+        xh[(0 * N + n) * n_x + d] = (double)PGF_ADD((float)x0_mean[d], acc);
+      }
+      continue;
+    }
     if (s->philox) stream_normals(s, PGB_STREAM_Z0, sweep_index, 0, n, n_x, z);
     else for (int d = 0; d < n_x; ++d) z[d] = s->Z0[n * n_x + d];
     for (int d = 0; d < n_x; ++d) {
@@ -290,11 +404,29 @@ int orc_sweep(const orc_model* m, int64_t N, int64_t T, const double* u, const d
       double ures = s->philox ? stream_uniform(s, PGB_STREAM_URES, sweep_index, (uint32_t)t) : s->Ures[t];
       /* f evaluated once per particle; the reference evaluates it on the gathered columns (:175) and
        * again on all columns (:179) — identical values, f is a pure per-column function */
-      for (int64_t n = 0; n < N; ++n) eval_f(m, A, &xp[n * n_x], up, phi_tmp, &F[n * n_x]);
+      for (int64_t n = 0; n < N; ++n) {
+        if (f32) {
+          for (int d = 0; d < n_x; ++d) xf[d] = (float)xp[n * n_x + d];
+          eval_f_f32(m, A, xf, up, phi_tmp_f, Ff);
+          for (int d = 0; d < n_x; ++d) F[n * n_x + d] = (double)Ff[d];
+        } else {
+          eval_f(m, A, &xp[n * n_x], up, phi_tmp, &F[n * n_x]);
+        }
+      }
       status |= orc_systematic_resampling(wprev, N, ndraw, ures, idx); /* :172 | :185 */
       for (int64_t j = 0; j < ndraw; ++j) {
         int64_t aj = idx[j] < 1 ? 1 : idx[j];
         ah[t * N + j] = idx[j];
+        if (f32) {
+          if (s->philox) stream_normals_f32(s, PGB_STREAM_Z, sweep_index, (uint32_t)t, j, n_x, zf);
+          else for (int d = 0; d < n_x; ++d) zf[d] = (float)s->Z[t * (N * n_x) + j * n_x + d];
+          for (int d = 0; d < n_x; ++d) {
+            float acc = 0.0f;
+            for (int e = 0; e <= d; ++e) acc = PGF_FMA((float)Lq[d + n_x * e], zf[e], acc);
+            xt[j * n_x + d] = (double)PGF_ADD((float)F[(aj - 1) * n_x + d], acc);
+          }
+          continue;
+        }
         if (s->philox) stream_normals(s, PGB_STREAM_Z, sweep_index, (uint32_t)t, j, n_x, z);
         else for (int d = 0; d < n_x; ++d) z[d] = s->Z[t * (N * n_x) + j * n_x + d];
         for (int d = 0; d < n_x; ++d) { /* :175 | :188   f(x[a]) + L*z */
@@ -308,6 +440,17 @@ int orc_sweep(const orc_model* m, int64_t N, int64_t T, const double* u, const d
         double uanc = s->philox ? stream_uniform(s, PGB_STREAM_UANC, sweep_index, (uint32_t)t) : s->Uanc[t];
         const double* xref = &xt[(N - 1) * n_x];
         for (int64_t n = 0; n < N; ++n) {
+          if (f32) {
+            float rf[ORC_MAX_Z], sqf = 0.0f;
+            for (int d = 0; d < n_x; ++d) {
+              float acc = PGF_SUB((float)F[n * n_x + d], (float)xref[d]);
+              for (int e = 0; e < d; ++e) acc = PGF_FMA(-(float)Lq[d + n_x * e], rf[e], acc);
+              rf[d] = PGF_DIV(acc, (float)Lq[d + n_x * d]);
+              sqf = PGF_FMA(rf[d], rf[d], sqf);
+            }
+            waN[n] = wprev[n] * pgf_exp_wide(PGF_SUB((float)c0, PGF_MUL(sqf, 0.5f))); /* FP32 polynomial, FP64 exponent range */
+            continue;
+          }
           for (int d = 0; d < n_x; ++d) r[d] = F[n * n_x + d] - xref[d];
           fwd_subst(Lq, n_x, r);
           double sq = 0.0;
@@ -324,10 +467,15 @@ int orc_sweep(const orc_model* m, int64_t N, int64_t T, const double* u, const d
     /* weights (:193-199) */
     double mx = -INFINITY;
     for (int64_t n = 0; n < N; ++n) {
-      lw[n] = log_weight(m, C, R, Rchol, &xt[n * n_x], &y[n_y * t]);
+      if (f32) {
+        for (int d = 0; d < n_x; ++d) xf[d] = (float)xt[n * n_x + d];
+        lw[n] = (double)log_weight_f32(m, C, R, Rchol, xf, &y[n_y * t]);
+      } else {
+        lw[n] = log_weight(m, C, R, Rchol, &xt[n * n_x], &y[n_y * t]);
+      }
       if (lw[n] > mx) mx = lw[n];
     }
-    for (int64_t n = 0; n < N; ++n) w[n] = pgb_exp(lw[n] - mx);
+    for (int64_t n = 0; n < N; ++n) w[n] = f32 ? (double)pgf_exp(PGF_SUB((float)lw[n], (float)mx)) : pgb_exp(lw[n] - mx);
     double sw = orc_pairwise_sum(w, N);
     for (int64_t n = 0; n < N; ++n) w[n] = w[n] / sw;
     if (w_hist) memcpy(&w_hist[t * N], w, sizeof(double) * (size_t)N);
@@ -380,7 +528,7 @@ int orc_sweep(const orc_model* m, int64_t N, int64_t T, const double* u, const d
   if (a_hist) memcpy(a_hist, ah, sizeof(int64_t) * (size_t)(T * N));
   if (x_hist) memcpy(x_hist, xh, sizeof(double) * (size_t)(T * N * n_x));
 done:
-  free(xh); free(ah); free(w); free(wprev); free(lw); free(waN); free(F); free(phi_tmp); free(idx);
+  free(xh); free(ah); free(w); free(wprev); free(lw); free(waN); free(F); free(phi_tmp); free(idx); free(phi_tmp_f);
   return status;
 }
 
@@ -710,6 +858,95 @@ int orc_draw_xT(int64_t N, int n_x, const double* w_m1, const double* x_m1 /* N 
   if (star < 1) star = 1;
   for (int d = 0; d < n_x; ++d) xT[d] = x_m1[(star - 1) * n_x + d];
   return status;
+}
+
+/* ---- one step of the stacked K-scenario model and its Jacobians ---------------------------
+ * RobotDynamics.discrete_dynamics[!] of PGS_model_obj (optimal_control_Altro.jl:79-107):
+ *   x_vec_n[k] = PG_samples[k].A * phi(x_vec[k], u) + v_vec[:, t+1, k]          (t: 0-based time index)
+ * and the Jacobians RobotDynamics.@autodiff (:51) obtains by forward-mode differentiation of exactly that expression:
+ *   d x_vec_n[k] / d x_vec[k] = A_k * dphi/dx  (block diagonal, n_x x n_x per scenario),   d x_vec_n[k] / d u = A_k * dphi/du.
+ * phi_variant 0: the rounding of phi_sampling (orc_phi); 1: the rounding of the examples' phi_opt
+ * (examples/PG_OCP_generic_basis_functions_Altro.jl:204-217): arg = (pi*j*(z + L)) / (2L).  Derivatives are the analytic
+ * ones: d/dz [lsi*sin(arg)] = lsi * (cos(arg) * w) with w = (pi*j)/(2L); every product over the augmented dimensions
+ * runs left to right (k = 0 .. n_z-1) with the differentiated factor in its place.  A_k * (.) uses the rollout's blocked
+ * order (eval_f_blocked): 128 runs of consecutive columns, fma in increasing i, balanced tree over the runs — so x_next
+ * with variant 0 equals the X[t+1] the rollout computes from the same state, bit for bit.  Against ForwardDiff the
+ * Jacobians agree to a few ulp (different association), which is the tolerance the tests state. */
+static void phi_and_jac(const orc_model* m, const double* x, const double* u, int variant, double* phi, double* dphi /* n_z x n_phi */) {
+  const int n_z = m->n_u + m->n_x, n_phi = m->n_phi;
+  if (m->basis == ORC_BASIS_KNOWN_VB) {
+    /* z = [u; x1; x2]; rows of dphi: d/du, d/dx1, d/dx2 */
+    const double c3 = pgb_cos(3.0 * x[0]), s3 = pgb_sin(3.0 * x[0]), s2 = pgb_sin(2.0 * x[1]), c2 = pgb_cos(2.0 * x[1]);
+    phi[0] = 0.1 * x[0]; phi[1] = 0.1 * x[1]; phi[2] = u[0]; phi[3] = (0.01 * c3) * x[1]; phi[4] = (0.1 * s2) * u[0];
+    for (int i = 0; i < 3 * 5; ++i) dphi[i] = 0.0;
+    dphi[0 + 3 * 2] = 1.0;                         /* d phi_3 / du */
+    dphi[0 + 3 * 4] = 0.1 * s2;                    /* d phi_5 / du */
+    dphi[1 + 3 * 0] = 0.1;                         /* d phi_1 / dx1 */
+    dphi[1 + 3 * 3] = (0.01 * (-(s3 * 3.0))) * x[1]; /* d phi_4 / dx1 */
+    dphi[2 + 3 * 1] = 0.1;                         /* d phi_2 / dx2 */
+    dphi[2 + 3 * 3] = 0.01 * c3;                   /* d phi_4 / dx2 */
+    dphi[2 + 3 * 4] = (0.1 * (c2 * 2.0)) * u[0];   /* d phi_5 / dx2 */
+    return;
+  }
+  double z[ORC_MAX_Z];
+  for (int k = 0; k < m->n_u; ++k) z[k] = u[k];
+  for (int k = 0; k < m->n_x; ++k) z[m->n_u + k] = x[k];
+  const double PI = 3.141592653589793;
+  double tk[ORC_MAX_Z][16], dk[ORC_MAX_Z][16];
+  for (int k = 0; k < n_z; ++k)
+    for (int j = 0; j < m->count[k]; ++j) {
+      const double jj = (double)(j + 1), w = (PI * jj) / (2.0 * m->L[k]), lsi = 1.0 / sqrt(m->L[k]);
+      const double arg = variant ? ((PI * jj) * (z[k] + m->L[k])) / (2.0 * m->L[k]) : w * (z[k] + m->L[k]);
+      tk[k][j] = lsi * pgb_sin(arg);
+      dk[k][j] = lsi * (pgb_cos(arg) * w);
+    }
+  for (int i = 0; i < n_phi; ++i) {
+    int dg[ORC_MAX_Z];
+    for (int k = 0; k < n_z; ++k) dg[k] = (i / m->stride[k]) % m->count[k];
+    double p = 1.0;
+    for (int k = 0; k < n_z; ++k) p = p * tk[k][dg[k]];
+    phi[i] = p;
+    for (int mm = 0; mm < n_z; ++mm) {
+      double q = 1.0;
+      for (int k = 0; k < n_z; ++k) q = q * (k == mm ? dk[k][dg[k]] : tk[k][dg[k]]);
+      dphi[mm + n_z * i] = q;
+    }
+  }
+}
+/* out = A (n_x x n_phi, column-major) * vec, in the rollout's blocked order; vec read with stride */
+static double blocked_dot(const double* A, int n_x, int d, const double* vec, int stride, int n_phi) {
+  double part[ORC_ROLL_LANES];
+  const int c = (n_phi + ORC_ROLL_LANES - 1) / ORC_ROLL_LANES;
+  for (int j = 0; j < ORC_ROLL_LANES; ++j) {
+    double acc = 0.0;
+    for (int i = j * c; i < (j + 1) * c && i < n_phi; ++i) acc = fma(A[d + n_x * i], vec[(int64_t)stride * i], acc);
+    part[j] = acc;
+  }
+  for (int w = 1; w < ORC_ROLL_LANES; w <<= 1)
+    for (int j = 0; j < ORC_ROLL_LANES; j += 2 * w) part[j] = part[j] + part[j + w];
+  return part[0];
+}
+int orc_dynamics(const orc_model* m, int64_t K, const double* A /* K x n_x x n_phi col-major */, const double* x_vec /* K x n_x */,
+                 const double* u, const double* v /* K x H x n_x or NULL */, int64_t H, int64_t t, int variant,
+                 double* x_next /* K x n_x */, double* dfdx /* K x (n_x x n_x col-major) or NULL */,
+                 double* dfdu /* K x (n_x x n_u col-major) or NULL */) {
+  const int n_x = m->n_x, n_u = m->n_u, n_phi = m->n_phi, n_z = n_x + n_u;
+  double* phi = (double*)malloc(sizeof(double) * (size_t)n_phi);
+  double* dphi = (double*)malloc(sizeof(double) * (size_t)n_phi * (size_t)n_z);
+  for (int64_t k = 0; k < K; ++k) {
+    const double* Ak = &A[k * n_x * n_phi];
+    phi_and_jac(m, &x_vec[k * n_x], u, variant, phi, dphi);
+    for (int d = 0; d < n_x; ++d) {
+      const double f = blocked_dot(Ak, n_x, d, phi, 1, n_phi);
+      x_next[k * n_x + d] = v ? f + v[(k * H + t) * n_x + d] : f;
+      if (dfdu)
+        for (int c = 0; c < n_u; ++c) dfdu[k * n_x * n_u + d + n_x * c] = blocked_dot(Ak, n_x, d, dphi + c, n_z, n_phi);
+      if (dfdx)
+        for (int c = 0; c < n_x; ++c) dfdx[k * n_x * n_x + d + n_x * c] = blocked_dot(Ak, n_x, d, dphi + n_u + c, n_z, n_phi);
+    }
+  }
+  free(phi); free(dphi);
+  return 0;
 }
 
 /* ---- scenario screening (optimal_control_Ipopt.jl:334-338; h_scenario of the examples, ..._Ipopt.jl:198-214) ---------- */

@@ -90,6 +90,19 @@ int orc_mniw_sample(int n_x, int n_phi, const double* Phi, const double* Psi, co
                     const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t Tm1,
                     const orc_streams* s, uint32_t sweep_index, double* A_out, double* Q_out);
 
+/* orc_sweep in the F32 precision mode (PGB_PRECISION_F32; see pg_oracle.c): FP32 particle states / basis functions /
+ * noise / log-weights / exponentials with the bit-defined functions of pgb_mathf.h, FP64 normalisation and cumulative
+ * sums.  Same arguments; the history arrays hold FP32 values widened to FP64. */
+int orc_sweep_f32(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y, const double* C,
+                  const double* R, const double* x0_mean, const double* x0_chol, const double* A, const double* Q,
+                  double* x_prim, int first, const orc_streams* s, uint32_t sweep_index, int64_t* a_hist,
+                  double* x_hist, double* w_hist, double* w_last, double* x_last, double* Phi, double* Psi,
+                  double* Sigma, int64_t* star_out);
+/* FP32 math wrappers for tests/test_mathf.py: fn 0 exp, 1 log (positive normal), 2 sin, 3 cos */
+void orc_vmathf(int fn, const float* x, float* y, int64_t n);
+void orc_vnormal_pairs_f32(uint64_t seed, uint32_t purpose, uint32_t chain, uint32_t sweep, uint32_t t, int64_t n,
+                           int n_x, float* z /* n x n_x */);
+
 /* Full sampler (particle_Gibbs.jl:114-237) with Philox streams. Outputs K samples. */
 int orc_particle_gibbs(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y,
                        const double* C, const double* R, const double* x0_mean, const double* x0_chol,
@@ -122,6 +135,11 @@ int orc_rollout_supplied(const orc_model* m, int64_t K, int64_t H, int64_t N, co
 /* x_T = x_m1[:, star] with star = systematic_resampling(w_m1, 1) (optimal_control_Ipopt.jl:58-59), scenario stream cid */
 int orc_draw_xT(int64_t N, int n_x, const double* w_m1, const double* x_m1 /* N x n_x */, uint64_t seed, uint32_t cid,
                 double* xT);
+
+/* One step of the stacked scenario model and its Jacobians (optimal_control_Altro.jl:79-107, @autodiff :51); see pg_oracle.c.
+ * v: K x H x n_x (the rollout's layout) or NULL (no noise); t: 0-based time index; variant 0 phi_sampling, 1 phi_opt rounding. */
+int orc_dynamics(const orc_model* m, int64_t K, const double* A, const double* x_vec, const double* u, const double* v,
+                 int64_t H, int64_t t, int variant, double* x_next, double* dfdx, double* dfdu);
 
 /* test_prediction (particle_Gibbs.jl:253-314): K models x k_n simulations over the test input, simulation (k, kn) =
  * scenario k + K*kn with its own stream; x_sim K*k_n x (T_test+1) x n_x, y_sim K*k_n x T_test x n_y (scenario-major),

@@ -175,13 +175,17 @@ def _meas(g):
     raise TypeError("g must be a LinearMeasurement (g(x,u) = C*x) or the matrix C")
 
 
-def _make_cfg(phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False, x_history="auto"):
+PRECISION = {"f64": 0, "f32": 1, None: 0}
+
+
+def _make_cfg(phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False, x_history="auto", precision="f64"):
     b = _basis(phi)
     cfg = PgbConfig()
     cfg.device, cfg.n_x, cfg.n_u, cfg.n_y, cfg.n_phi = device, b.n_x, b.n_u, n_y, b.n_phi
     b.fill(cfg)
     cfg.N, cfg.T, cfg.n_chains, cfg.keep_w_history = int(N), int(T), int(n_chains), int(keep_w_history)
     cfg.x_history = _lib.X_HISTORY[x_history]
+    cfg.precision = PRECISION[precision]
     return cfg
 
 
@@ -189,10 +193,13 @@ def _make_cfg(phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False, x_hist
 # engine (one handle = one device, one stream, n_chains batched chains)
 # ----------------------------------------------------------------------------------------------
 class ParticleGibbsEngine:
-    def __init__(self, phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False, x_history="auto"):
+    def __init__(self, phi, n_y, N, T, n_chains=1, device=0, keep_w_history=False, x_history="auto", precision="f64"):
         """x_history: "store" keeps x_pf[n_x,N,T] on the device (get_history needs it), "replay" keeps two steps and
-        recomputes the traced trajectory (bit-identical, N*T no longer bounded by memory), "auto": store up to 1 GiB."""
-        self.cfg = _make_cfg(phi, n_y, N, T, n_chains, device, keep_w_history, x_history)
+        recomputes the traced trajectory (bit-identical, N*T no longer bounded by memory), "auto": store up to 1 GiB.
+        precision: "f64" (the reference's arithmetic) or "f32" — FP32 particle states / basis functions / noise /
+        log-weights with bit-defined FP32 functions, FP64 weight normalisation and cumulative sums (include/pgopt_b200.h:
+        PGB_PRECISION_F32); indices stay bit-exact against the oracle's F32 mode."""
+        self.cfg = _make_cfg(phi, n_y, N, T, n_chains, device, keep_w_history, x_history, precision)
         self._phi = phi
         self.n_x, self.n_u, self.n_y, self.n_phi = self.cfg.n_x, self.cfg.n_u, n_y, self.cfg.n_phi
         self.N, self.T, self.n_chains = int(N), int(T), int(n_chains)
@@ -459,6 +466,13 @@ class MultiGPUEngine:
                                          _p(bufs.get("x0")), _p(bufs.get("X")), _p(bufs.get("Y"))))
         return bufs
 
+    def scenarios_on(self, which_device, H):
+        """the all-gathered x_vec_0 / X / Y as device `which_device` holds them after rollout()"""
+        Kt, nx, ny = self._n_scen, self.n_x, self.n_y
+        bufs = dict(x0=np.empty((Kt, nx)), X=np.empty((Kt, H + 1, nx)), Y=np.empty((Kt, H, ny)))
+        self._ck(lib().pgb_multi_get_scenarios(self._m, C.c_int32(which_device), _p(bufs["x0"]), _p(bufs["X"]), _p(bufs["Y"])))
+        return bufs
+
     def last_ms(self):
         a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
         self._ck(lib().pgb_multi_last_ms(self._m, C.byref(a), C.byref(b), C.byref(c)))
@@ -506,7 +520,7 @@ def MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T, bartlett=None, Xmn=None,
 
 
 def particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist, g, R,
-                   x_prim=None, seed=0, chain=0, device=0, verbose=False, x_history="auto"):
+                   x_prim=None, seed=0, chain=0, device=0, verbose=False, x_history="auto", precision="f64"):
     """particle_Gibbs(u, y, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist, g, R; x_prim)
     — Julia/src/particle_Gibbs.jl:114-237.  Returns a list of K PG_sample.  `x_prim`, when given, is
     updated in place like the reference does (:214-217)."""
@@ -514,7 +528,7 @@ def particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q,
     y = np.atleast_2d(np.asarray(y_training, dtype=np.float64))
     A_init = np.atleast_2d(np.asarray(A_init, dtype=np.float64))
     n_y, T = y.shape
-    eng = ParticleGibbsEngine(phi, n_y, N, T, 1, device, x_history=x_history)
+    eng = ParticleGibbsEngine(phi, n_y, N, T, 1, device, x_history=x_history, precision=precision)
     try:
         eng.set_data(u, y)
         eng.set_measurement(g, R)
@@ -586,6 +600,39 @@ def scenario_rollout(PG_samples, phi, g, R, H, u_init=None, seed=0, k_offset=0, 
                                      _p(_f(gm.C)), _p(_f(Le)), _p(_f(np.atleast_2d(u_init))), C.c_uint64(seed),
                                      C.c_uint32(k_offset), _p(x0i), _p(vi), _p(ei), _p(x0), _p(v), _p(e), _p(X), _p(Y)))
     return _scenario_dict(x0, v, e, X, Y, K, H, n_x, n_y)
+
+
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            lib().pgb_host_free(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """NumPy array over page-locked host memory (pgb_host_alloc): D2H / H2D of the scenario arrays run at PCIe speed
+    instead of the pageable-copy rate (a pageable cudaMemcpy of the configs[4] inputs was 261 ms of a 0.74 s call)"""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib().pgb_host_alloc(C.c_size_t(max(n, 16)))
+    if not ptr:
+        raise MemoryError("pgb_host_alloc(%d) failed" % n)
+    owner = _PinnedOwner(ptr)
+    buf = (C.c_char * max(n, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    arr = arr.view(_PinnedArray)
+    arr._owner = owner
+    return arr
+
+
+class _PinnedArray(np.ndarray):
+    """ndarray that keeps its page-locked allocation alive"""
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
 
 
 class DeviceSamples:
@@ -704,6 +751,23 @@ class DeviceSamples:
         buf = self.pack(with_particles=False)
         R = int(lib().pgb_packed_record_doubles(C.c_int32(self.n_x), C.c_int32(self.n_phi), C.c_int32(self.n_u)))
         return buf[64:].view(np.float64).reshape(-1, R).copy()
+
+    def dynamics(self, x_vec, u, t=None, phi_variant=0, jacobians=True):
+        """discrete_dynamics of the stacked scenario model (Julia/src/optimal_control_Altro.jl:79-107) and its Jacobians
+        (RobotDynamics.@autodiff, :51): x_vec (K*n_x,) stacked as in the reference, u (n_u,), t = 0-based time index whose
+        process noise v_vec[:, t+1, k] (from the last rollout of this set) is added, None = no noise.  Returns
+        (x_vec_next (K*n_x,), dfdx (K, n_x, n_x), dfdu (K, n_x, n_u)); the full Jacobian w.r.t. x_vec is block diagonal."""
+        K, nx, nu = self.K, self.n_x, self.n_u
+        xv = np.ascontiguousarray(np.asarray(x_vec, dtype=np.float64).reshape(-1))
+        assert xv.size == K * nx
+        xn = np.empty(K * nx)
+        jx = np.empty((K, nx, nx)) if jacobians else None
+        ju = np.empty((K, nu, nx)) if jacobians else None
+        self._ck(lib().pgb_dynamics_dev(self._s, _p(xv), _p(_f(np.atleast_1d(u))), C.c_int64(-1 if t is None else int(t)),
+                                        C.c_int32(int(phi_variant)), _p(xn), _p(jx), _p(ju)))
+        if not jacobians:
+            return xn, None, None
+        return xn, np.transpose(jx, (0, 2, 1)), np.transpose(ju, (0, 2, 1))
 
     def last_ms(self):
         a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)

@@ -2,6 +2,7 @@
 // management and the launch sequences shared by every filter path.  No torch types, no CPU compute path: every
 // entry point that computes needs a CUDA device and fails with PGB_ERR_CUDA otherwise.
 #include "pgb_internal.h"
+#include "pgb_trace_f32.cuh"
 
 using namespace pgb;
 
@@ -125,6 +126,7 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
   memset(&fd, 0, sizeof(fd));
   pgb_fill_model(fd, cfg);
   fd.N = N; fd.T = T; fd.nc = nc;
+  fd.f32 = (cfg->precision == PGB_PRECISION_F32) ? 1 : 0;
   fd.nt = (int)((N + TILE - 1) / TILE);
   const int64_t nt = fd.nt;
   CKC(dalloc(h, &h->d_u, (size_t)nu * T));
@@ -138,13 +140,14 @@ extern "C" int pgb_create(pgb_handle** out, const pgb_config* cfg) {
   CKC(dalloc(h, &fd.c0, (size_t)nc));
   CKC(dalloc(h, &fd.xprim, (size_t)nc * nx * T));
   {  // x history: kept (needed by pgb_get_history) or rolling two rows + replay of the traced lineage
-    const double hist_bytes = (double)nc * (double)T * nx * (double)N * 8.0;
+    const double hist_bytes = (double)nc * (double)T * nx * (double)N * (fd.f32 ? 4.0 : 8.0);
     const bool store = cfg->x_history == PGB_X_HISTORY_STORE ||
                        (cfg->x_history == PGB_X_HISTORY_AUTO && hist_bytes <= 1024.0 * 1024.0 * 1024.0);
     fd.x_rows = store ? T : 2;
     if (T < 2) fd.x_rows = T;
   }
-  CKC(dalloc(h, &fd.xh, (size_t)nc * fd.x_rows * nx * N, false));
+  // F32 mode: the same buffer holds FP32 values (half the FP64 element count, rounded up)
+  CKC(dalloc(h, &fd.xh, fd.f32 ? ((size_t)nc * fd.x_rows * nx * N + 1) / 2 : (size_t)nc * fd.x_rows * nx * N, false));
   CKC(dalloc(h, &fd.lineage, (size_t)nc * T));
   CKC(dalloc(h, &h->d_replay_noise, (size_t)nc * T * nx));
   CKC(dalloc(h, &fd.ah, (size_t)nc * T * N, false));
@@ -404,7 +407,14 @@ static int trace_and_stats_nx(pgb_handle* h, int first, bool trace_done) {
   cudaStream_t s = h->stream;
   const int64_t T = fd.T;
   const int nc = fd.nc;
-  if (!trace_done) {
+  if (!trace_done && fd.f32) {
+    if (fd.x_rows == T) {
+      LAUNCH(h, PGB_PROF_TAIL, (k_trace_f32<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
+    } else {
+      LAUNCH(h, PGB_PROF_TAIL, (k_trace_replay_f32<NX><<<nc, 128, (size_t)fd.n_phi * 4, s>>>(fd, h->d_star_idx, h->d_star_out,
+                                                                                           h->d_replay_noise, first)));
+    }
+  } else if (!trace_done) {
     if (fd.x_rows == T) {
       LAUNCH(h, PGB_PROF_TAIL, (k_trace<NX><<<(nc + 31) / 32, 32, 0, s>>>(fd, h->d_star_idx, h->d_star_out)));
     } else {
@@ -430,6 +440,12 @@ int pgb_launch_trace_and_stats(pgb_handle* h, int first, bool small_trace_done) 
 static int run_filter(pgb_handle* h) {
   int mode = h->persistent;
   int rc;
+  if (h->fd.f32) {  // the F32 precision mode exists in the chunk-stationary sweep kernel only
+    rc = pgb_run_filter_v2(h);
+    if (rc >= 0) return rc;
+    return set_err(h, PGB_ERR_INVALID, "PGB_PRECISION_F32: this shape (n_chains = %d, N = %lld) does not fit the sweep kernel", h->fd.nc,
+                   (long long)h->fd.N);
+  }
   if (mode < 0 || mode == 3) {
     // the warp kernel up to N = 32, the one-CTA-per-chain kernel up to N = 1024 (automatic and mode 3)
     rc = pgb_run_filter_small(h, 1024);
@@ -501,16 +517,22 @@ static int fetch_sample(pgb_handle* h, int chain, double* A, double* Q, double* 
   if (A) CK(h, cudaMemcpyAsync(A, h->d_A_used + (size_t)chain * nx * np, (size_t)nx * np * 8, cudaMemcpyDeviceToHost, s));
   if (Q) CK(h, cudaMemcpyAsync(Q, h->d_Q_used + (size_t)chain * nx * nx, (size_t)nx * nx * 8, cudaMemcpyDeviceToHost, s));
   if (w_m1) CK(h, cudaMemcpyAsync(w_m1, h->fd.wbuf + (size_t)chain * N, (size_t)N * 8, cudaMemcpyDeviceToHost, s));
+  const bool f32 = h->fd.f32 != 0;
   if (x_m1) {
     tmp.resize((size_t)nx * N);
     const size_t row = (h->fd.x_rows == T) ? (size_t)(T - 1) : (size_t)((T - 1) & 1);
-    CK(h, cudaMemcpyAsync(tmp.data(), h->fd.xh + ((size_t)chain * h->fd.x_rows + row) * nx * N, (size_t)nx * N * 8,
-                          cudaMemcpyDeviceToHost, s));
+    const size_t off = ((size_t)chain * h->fd.x_rows + row) * nx * N;
+    if (f32)
+      CK(h, cudaMemcpyAsync(tmp.data(), reinterpret_cast<const float*>(h->fd.xh) + off, (size_t)nx * N * 4, cudaMemcpyDeviceToHost, s));
+    else
+      CK(h, cudaMemcpyAsync(tmp.data(), h->fd.xh + off, (size_t)nx * N * 8, cudaMemcpyDeviceToHost, s));
   }
   CK(h, cudaStreamSynchronize(s));
-  if (x_m1)
+  if (x_m1) {
+    const float* tf = reinterpret_cast<const float*>(tmp.data());
     for (int64_t n = 0; n < N; ++n)
-      for (int d = 0; d < nx; ++d) x_m1[d + nx * n] = tmp[(size_t)d * N + n];
+      for (int d = 0; d < nx; ++d) x_m1[d + nx * n] = f32 ? (double)tf[(size_t)d * N + n] : tmp[(size_t)d * N + n];
+  }
   if (u_m1)
     for (int c = 0; c < nu; ++c) u_m1[c] = h->h_u[(size_t)nu * (T - 1) + c];
   return PGB_OK;
@@ -606,10 +628,18 @@ extern "C" int pgb_get_history(pgb_handle* h, int32_t chain, int64_t* a, double*
       return set_err(h, PGB_ERR_STATE, "the particle history x was not kept (x_history = replay); create the handle "
                                        "with x_history = PGB_X_HISTORY_STORE");
     std::vector<double> tx((size_t)T * nx * N);
-    CK(h, cudaMemcpy(tx.data(), h->fd.xh + (size_t)chain * T * nx * N, tx.size() * 8, cudaMemcpyDeviceToHost));
+    const bool f32 = h->fd.f32 != 0;
+    if (f32)
+      CK(h, cudaMemcpy(tx.data(), reinterpret_cast<const float*>(h->fd.xh) + (size_t)chain * T * nx * N, tx.size() * 4, cudaMemcpyDeviceToHost));
+    else
+      CK(h, cudaMemcpy(tx.data(), h->fd.xh + (size_t)chain * T * nx * N, tx.size() * 8, cudaMemcpyDeviceToHost));
+    const float* tf = reinterpret_cast<const float*>(tx.data());
     for (int64_t t = 0; t < T; ++t)
       for (int64_t n = 0; n < N; ++n)
-        for (int d = 0; d < nx; ++d) x[(t * N + n) * nx + d] = tx[((size_t)t * nx + d) * N + n];
+        for (int d = 0; d < nx; ++d) {
+          const size_t i = ((size_t)t * nx + d) * N + n;
+          x[(t * N + n) * nx + d] = f32 ? (double)tf[i] : tx[i];
+        }
   }
   if (w) {
     if (!h->fd.whist) return set_err(h, PGB_ERR_STATE, "w history was not kept (keep_w_history = 0)");
@@ -765,6 +795,19 @@ __global__ void k_test_math(int fn, const double* __restrict__ x, double* __rest
     case 2: y[i] = pgb_sin(x[i]); break;
     case 3: y[i] = pgb_cos(x[i]); break;
     case 4: pgb_normal_pair(pgb_stream_block(seed, PGB_STREAM_Z, 0, 1, 5, (uint32_t)i), &y[2 * i], &y[2 * i + 1]); break;
+    // 30..35: the FP32 functions of pgb_mathf.h (F32 precision mode) through FP64 in/out: x is rounded to FP32, the FP32
+    // result widened — bit identity of the device build with the host build (oracle) is checked on these
+    case 30: y[i] = (double)pgf_exp((float)x[i]); break;
+    case 31: y[i] = (double)pgf_log_pos_normal((float)x[i]); break;
+    case 32: y[i] = (double)pgf_sin((float)x[i]); break;
+    case 33: y[i] = (double)pgf_cos((float)x[i]); break;
+    case 34: y[i] = pgf_exp_wide((float)x[i]); break;
+    case 35: {  // x[0] = seed (read by the host wrapper); 4 FP32 normals of particle i, purpose Z, sweep 1, t 5
+      float z[4];
+      pgf_stream_normals(seed, PGB_STREAM_Z, 0, 1, 5, (uint32_t)i, 4, z);
+      for (int d = 0; d < 4; ++d) y[4 * i + d] = (double)z[d];
+      break;
+    }
     case 20: {  // x holds pairs (a, d): y[i] = 1 if div_inv(a, d) == a / d bitwise (or both NaN)
       double a = x[2 * i], d = x[2 * i + 1];
       InvDiv iv = make_invdiv(d);
@@ -834,8 +877,8 @@ extern "C" int pgb_test_math(int32_t device, int32_t fn, const double* x, double
   TmpHandle tmp;
   pgb_handle* h = &tmp;
   CK(h, cudaSetDevice(device));
-  const bool pairs = (fn == 4 || fn == 14);
-  const int64_t nout = pairs ? 2 * n : n;
+  const bool pairs = (fn == 4 || fn == 14 || fn == 35);
+  const int64_t nout = fn == 35 ? 4 * n : (pairs ? 2 * n : n);
   const int64_t nin = pairs ? 1 : (fn == 20 ? 2 * n : n);
   double *dx, *dy;
   CK(h, dalloc(h, &dx, (size_t)nin));

@@ -21,6 +21,7 @@ constexpr int MAXC = 8;  // max basis functions per augmented dimension (Hilbert
 struct FilterDev {
   int64_t N, T;
   int nc, n_x, n_u, n_y, n_phi, basis, nt, n_z;
+  int f32;           // PGB_PRECISION_F32: xh / Fbuf / lwbuf hold FP32 values (pgb_real.cuh); everything else FP64
   int hg_count[PGB_MAX_Z_];
   double hg_L[PGB_MAX_Z_], hg_lsi[PGB_MAX_Z_];
   double hg_pij2l[PGB_MAX_Z_][MAXC];

@@ -79,6 +79,9 @@ struct pgb_samples {
   double C[16] = {0}, Le[16] = {0};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   float last_ms[3] = {0.f, 0.f, 0.f};  // device time of the last rollout kernel, screening kernel, input upload
+  // pgb_dynamics_dev scratch (allocated on first use): stacked state in, next state and Jacobian blocks out
+  double *dyn_x = nullptr, *dyn_xn = nullptr, *dyn_jx = nullptr, *dyn_ju = nullptr;
+  float dyn_ms = 0.f;
 };
 // pgb_rollout.cu: device-to-device copy of the chain's current PG_sample into slot k (ordered on h->stream, no sync)
 int pgb_samples_store_async(pgb_samples* s, int64_t k, pgb_handle* h, int chain);

@@ -70,6 +70,7 @@ struct pgb_multi_dev {
   pgb_samples* S = nullptr;       // the device's own kept samples, capacity `cap` (created by the first sampler run)
   ncclComm_t comm = nullptr;
   cudaStream_t stream = nullptr;  // gather stream
+  cudaStream_t stream2 = nullptr; // device-to-host stream (the owning device's block of the outputs, concurrent with the gather)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // gathered arrays, [n_dev][cap][...]: packed records, scenario outputs
   double* g_rec = nullptr;
@@ -142,6 +143,7 @@ extern "C" void pgb_multi_destroy(pgb_multi* m) {
     if (D.ev0) cudaEventDestroy(D.ev0);
     if (D.ev1) cudaEventDestroy(D.ev1);
     if (D.stream) cudaStreamDestroy(D.stream);
+    if (D.stream2) cudaStreamDestroy(D.stream2);
   }
   delete m;
 }
@@ -181,7 +183,8 @@ extern "C" int pgb_multi_create(pgb_multi** out, const pgb_config* cfg, const in
     c.n_chains = D.nc;
     int r = pgb_create(&D.h, &c);
     if (r) return r;
-    if (cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&D.ev0) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&D.stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&D.ev0) != cudaSuccess ||
         cudaEventCreate(&D.ev1) != cudaSuccess)
       return pgb_set_err(nullptr, PGB_ERR_CUDA, "stream / event creation failed");
     return PGB_OK;
@@ -402,6 +405,16 @@ extern "C" int pgb_multi_rollout(pgb_multi* m, int64_t H, const double* C, const
   if (rc) return rc;
   m->rollout_kernel_ms_max = 0.0;
   for (auto& D : m->dev) m->rollout_kernel_ms_max = std::max(m->rollout_kernel_ms_max, (double)D.S->last_ms[0]);
+  // host outputs: every device sends ITS OWN block over its own PCIe link (stream2), concurrently with the NVLink gather
+  for (auto& D : m->dev) {
+    cudaSetDevice(D.device);
+    const size_t n = (size_t)D.gn, o = (size_t)D.g0;
+    cudaError_t e = cudaSuccess;
+    if (x0 && e == cudaSuccess) e = cudaMemcpyAsync(x0 + o * nx, D.S->x0, n * nx * 8, cudaMemcpyDeviceToHost, D.stream2);
+    if (X && e == cudaSuccess) e = cudaMemcpyAsync(X + o * (H + 1) * nx, D.S->X, n * (H + 1) * nx * 8, cudaMemcpyDeviceToHost, D.stream2);
+    if (Y && e == cudaSuccess) e = cudaMemcpyAsync(Y + o * H * ny, D.S->Y, n * H * ny * 8, cudaMemcpyDeviceToHost, D.stream2);
+    if (e != cudaSuccess) return merr(m, PGB_ERR_CUDA, "D2H failed on device %d: %s", D.device, cudaGetErrorString(e));
+  }
   cudaSetDevice(m->dev[0].device);
   cudaEventRecord(m->dev[0].ev0, m->dev[0].stream);
   struct Arr { double* pgb_multi_dev::*g; double* pgb_samples::*s; size_t per; };
@@ -418,12 +431,24 @@ extern "C" int pgb_multi_rollout(pgb_multi* m, int64_t H, const double* C, const
   cudaEventRecord(m->dev[0].ev1, m->dev[0].stream);
   for (auto& D : m->dev) {
     cudaSetDevice(D.device);
-    if (cudaStreamSynchronize(D.stream) != cudaSuccess) return merr(m, PGB_ERR_CUDA, "scenario gather failed on device %d", D.device);
+    if (cudaStreamSynchronize(D.stream) != cudaSuccess || cudaStreamSynchronize(D.stream2) != cudaSuccess)
+      return merr(m, PGB_ERR_CUDA, "scenario gather / D2H failed on device %d", D.device);
   }
   cudaSetDevice(m->dev[0].device);
   cudaEventElapsedTime(&m->rollout_gather_ms, m->dev[0].ev0, m->dev[0].ev1);
   m->have_scen = true;
-  pgb_multi_dev& W = m->dev[0];
+  return PGB_OK;
+}
+
+// the gathered scenario arrays as device `which_device` of the list holds them (every device holds all) -> host
+extern "C" int pgb_multi_get_scenarios(pgb_multi* m, int32_t which_device, double* x0, double* X, double* Y) {
+  NEEDM(m);
+  if (!m->have_scen) return merr(m, PGB_ERR_STATE, "no rollout has run");
+  if (which_device < 0 || which_device >= m->n_dev) return merr(m, PGB_ERR_INVALID, "bad device index %d", which_device);
+  const int nx = m->cfg.n_x, ny = m->cfg.n_y;
+  const int64_t cap = m->cap, H = m->dev[0].gH;
+  pgb_multi_dev& W = m->dev[which_device];
+  cudaSetDevice(W.device);
   for (int d = 0; d < m->n_dev; ++d) {
     const pgb_multi_dev& D = m->dev[d];
     const size_t n = (size_t)D.gn, o = (size_t)D.g0, g = (size_t)d * cap;

@@ -434,10 +434,11 @@ extern "C" int pgb_samples_get(pgb_samples* s, int64_t k0, int64_t n, double* A,
 }
 
 // x_pf[:, :, T] is kept as [n_x][N] by the filter; PG_sample.x_m1 is n_x x N column-major
-static __global__ void k_soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, int64_t N, int nx) {
+template <typename RT>
+static __global__ void k_soa_to_aos(const RT* __restrict__ src, double* __restrict__ dst, int64_t N, int nx) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  for (int d = 0; d < nx; ++d) dst[n * nx + d] = src[(int64_t)d * N + n];
+  for (int d = 0; d < nx; ++d) dst[n * nx + d] = (double)src[(int64_t)d * N + n];
 }
 
 int pgb_samples_store_async(pgb_samples* s, int64_t k, pgb_handle* h, int chain) {
@@ -455,8 +456,12 @@ int pgb_samples_store_async(pgb_samples* s, int64_t k, pgb_handle* h, int chain)
   CK(h, cudaMemcpyAsync(s->w + (size_t)k * N, h->fd.wbuf + (size_t)chain * N, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
   CK(h, cudaMemcpyAsync(s->um + (size_t)k * nu, h->d_u + (size_t)nu * (T - 1), (size_t)nu * 8, cudaMemcpyDeviceToDevice, st));
   const size_t row = (h->fd.x_rows == T) ? (size_t)(T - 1) : (size_t)((T - 1) & 1);
-  k_soa_to_aos<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h->fd.xh + ((size_t)chain * h->fd.x_rows + row) * nx * N,
-                                                            s->x + (size_t)k * nx * N, N, nx);
+  const size_t xoff = ((size_t)chain * h->fd.x_rows + row) * nx * N;
+  if (h->fd.f32)  // F32 precision mode: the particle rows hold FP32 values
+    k_soa_to_aos<float><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float*>(h->fd.xh) + xoff,
+                                                                     s->x + (size_t)k * nx * N, N, nx);
+  else
+    k_soa_to_aos<double><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h->fd.xh + xoff, s->x + (size_t)k * nx * N, N, nx);
   CK(h, cudaGetLastError());
   s->have_xT = false;
   return PGB_OK;

@@ -44,12 +44,12 @@ extern "C" int pgb_experiment_phase_cycles(pgb_handle* h, double* avg /*[16]*/) 
 }
 #endif
 
-template <int NX, int BASIS, bool FIRST, int CA>
+template <int NX, int BASIS, bool FIRST, int CA, typename RT>
 static int launch_v2(pgb_handle* h, size_t smem) {
-  const void* kfn = (const void*)k_sweep_v2<NX, BASIS, FIRST, CA>;
+  const void* kfn = (const void*)k_sweep_v2<NX, BASIS, FIRST, CA, RT>;
   CK(h, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_v2<NX, BASIS, FIRST, CA>, V2_NT, smem));
+  CK(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_v2<NX, BASIS, FIRST, CA, RT>, V2_NT, smem));
   if (occ < 1) return -1;
   LaunchScope ls(h, PGB_PROF_EXPAND);
   void* args[] = {(void*)&h->fd, (void*)&h->v2};
@@ -59,7 +59,9 @@ static int launch_v2(pgb_handle* h, size_t smem) {
 
 template <int NX, int BASIS, int CA = 0>
 static int launch_v2_first(pgb_handle* h, size_t smem, int first) {
-  return first ? launch_v2<NX, BASIS, true, CA>(h, smem) : launch_v2<NX, BASIS, false, CA>(h, smem);
+  if (h->fd.f32)
+    return first ? launch_v2<NX, BASIS, true, CA, float>(h, smem) : launch_v2<NX, BASIS, false, CA, float>(h, smem);
+  return first ? launch_v2<NX, BASIS, true, CA, double>(h, smem) : launch_v2<NX, BASIS, false, CA, double>(h, smem);
 }
 
 int pgb_run_filter_v2(pgb_handle* h) {
@@ -102,7 +104,13 @@ int pgb_run_filter_v2(pgb_handle* h) {
                     fd.hg_count[1] == 5 && fd.hg_count[2] == 5;
   if (fd.basis == PGB_BASIS_KNOWN_VB) rc = launch_v2_first<2, 0>(h, smem, first);
   else if (h355 && nc == 1) {  // single chain: A as constant-bank operands of the contraction
-    CK(h, cudaMemcpyToSymbolAsync(c_v2A, fd.A, (size_t)n_A * 8, 0, cudaMemcpyDeviceToDevice, s));
+    if (fd.f32) {
+      float* stage = reinterpret_cast<float*>(vd.Wn);  // scratch of the fix-up path, idle between sweeps
+      k_round_to_f32<<<(n_A + 255) / 256, 256, 0, s>>>(fd.A, stage, n_A);
+      CK(h, cudaMemcpyToSymbolAsync(c_v2Af, stage, (size_t)n_A * 4, 0, cudaMemcpyDeviceToDevice, s));
+    } else {
+      CK(h, cudaMemcpyToSymbolAsync(c_v2A, fd.A, (size_t)n_A * 8, 0, cudaMemcpyDeviceToDevice, s));
+    }
     rc = launch_v2_first<2, 1, 1>(h, smem, first);
   } else if (h355) rc = launch_v2_first<2, 1, 0>(h, smem, first);
   else {

@@ -31,8 +31,7 @@
 //       certified approximate scan                                                                  | B0
 //   (rare, grid-uniform: exact scan of the ancestor weights; serial exact walk after a failed seam check)
 #pragma once
-#include "pgb_lmath.cuh"
-#include "pgb_persist.cuh"
+#include "pgb_real.cuh"
 #include "pgb_v2_types.h"
 
 namespace pgb {
@@ -240,107 +239,14 @@ __device__ __forceinline__ double v2_warp_incl_scan(double v) {
 // loads per particle (ncu of the first version: the contraction line stalled on the short scoreboard, i.e. on LDS).
 constexpr int V2_CA_MAX = 2560;
 static __constant__ double c_v2A[V2_CA_MAX];
-
-// F = A*phi(x, u) for ONE particle, specialised at compile time: BASIS 0 = known basis (n_x = 2), 1 = Hilbert basis
-// with 5 x 5 x 5 functions over z = [u; x1; x2] (n_x = 2, n_u = 1), 2 = general Hilbert basis.  Same products and the same
-// fma order (increasing i) as eval_F / the oracle.  tku: scaled sines of the input dimensions, evaluated once per
-// step and CTA (u_{t-1} is common to all particles).
-template <int NX, int BASIS, int CA>
-__device__ __forceinline__ void v2_eval_F(const FilterDev& fd, const double* __restrict__ A_sm, const double (&x)[NX],
-                                          const double* __restrict__ u, const double* __restrict__ tku, double (&F)[NX]) {
-  if (BASIS == 0) {
-    const double x0 = x[0], x1 = x[NX > 1 ? 1 : 0], u0 = u[0];
-    double phi[5];
-    phi[0] = __dmul_rn(0.1, x0);
-    phi[1] = __dmul_rn(0.1, x1);
-    phi[2] = u0;
-    phi[3] = __dmul_rn(__dmul_rn(0.01, lcos(__dmul_rn(3.0, x0))), x1);
-    phi[4] = __dmul_rn(__dmul_rn(0.1, lsin(__dmul_rn(2.0, x1))), u0);
-#pragma unroll
-    for (int d = 0; d < NX; ++d) {
-      double acc = 0.0;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) acc = __fma_rn(A_sm[d + NX * i], phi[i], acc);
-      F[d] = acc;
-    }
-  } else if (BASIS == 1) {
-    double t1[5], t2[5];
-    {
-      const double zl1 = __dadd_rn(x[0], fd.hg_L[1]), zl2 = __dadd_rn(x[NX > 1 ? 1 : 0], fd.hg_L[2]);
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        t1[j] = __dmul_rn(fd.hg_lsi[1], lsin(__dmul_rn(fd.hg_pij2l[1][j], zl1)));
-        t2[j] = __dmul_rn(fd.hg_lsi[2], lsin(__dmul_rn(fd.hg_pij2l[2][j], zl2)));
-      }
-    }
-    double acc[NX];
-#pragma unroll
-    for (int d = 0; d < NX; ++d) acc[d] = 0.0;
-#pragma unroll
-    for (int j0 = 0; j0 < 5; ++j0) {
-      const double t0 = tku[j0];  // = (1 * t_0): the product with 1.0 is exact
-#pragma unroll
-      for (int j1 = 0; j1 < 5; ++j1) {
-        const double pa = __dmul_rn(t0, t1[j1]);
-#pragma unroll
-        for (int j2 = 0; j2 < 5; ++j2) {
-          const int i = (j0 * 5 + j1) * 5 + j2;
-          const double q = __dmul_rn(pa, t2[j2]);
-#pragma unroll
-          for (int d = 0; d < NX; ++d) acc[d] = __fma_rn(CA ? c_v2A[d + NX * i] : A_sm[d + NX * i], q, acc[d]);
-        }
-      }
-    }
-#pragma unroll
-    for (int d = 0; d < NX; ++d) F[d] = acc[d];
-  } else {
-    const int nz = fd.n_z, nu = fd.n_u;
-    double tk[PGB_MAX_Z_][MAXC];
-    for (int k = 0; k < nz; ++k) {
-      if (k < nu) {
-        for (int j = 0; j < fd.hg_count[k]; ++j) tk[k][j] = tku[k * MAXC + j];
-      } else {
-        const double zl = __dadd_rn(x[k - nu], fd.hg_L[k]);
-        for (int j = 0; j < fd.hg_count[k]; ++j) tk[k][j] = __dmul_rn(fd.hg_lsi[k], lsin(__dmul_rn(fd.hg_pij2l[k][j], zl)));
-      }
-    }
-    hilbert_apply<NX>(fd, A_sm, tk, F);
-  }
-}
-
-// measurement log-weight (:194 | :196) with the scalar-R quotient through a shared reciprocal
-template <int NX>
-__device__ __forceinline__ double v2_log_weight(const FilterDev& fd, const double (&x)[NX], const double* __restrict__ y,
-                                                const InvDiv& ivR) {
-  if (fd.n_y == 1) {
-    double g = 0.0;
-#pragma unroll
-    for (int d = 0; d < NX; ++d) g = __fma_rn(fd.C[d], x[d], g);
-    const double dd = __dsub_rn(g, y[0]);
-    return div_inv(__dmul_rn(-__dmul_rn(dd, dd), 0.5), ivR);
-  }
-  return log_weight<NX>(fd, x, y);
-}
-
-// standard normals of output slot j (all NX dims) — Philox block j*NP + p gives dims (2p, 2p+1); or the injected stream
-template <int NX>
-__device__ __forceinline__ void v2_normals(const FilterDev& fd, uint32_t stream_word, uint32_t t, int64_t j,
-                                           const double* __restrict__ inj, double (&z)[NX]) {
-  if (fd.philox) {
-    constexpr int NP = (NX + 1) / 2;
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      uint32_t c0 = (uint32_t)(j * NP + p), c1 = t, c2 = fd.sweep, c3 = stream_word;
-      lphilox(c0, c1, c2, c3, (uint32_t)fd.seed, (uint32_t)(fd.seed >> 32));
-      double z0, z1;
-      lnormal_pair(c0, c1, c2, c3, z0, z1);
-      z[2 * p] = z0;
-      if (2 * p + 1 < NX) z[2 * p + 1] = z1;
-    }
-  } else {
-#pragma unroll
-    for (int d = 0; d < NX; ++d) z[d] = inj[j * NX + d];
-  }
+static __constant__ float c_v2Af[V2_CA_MAX];  // the same rounded to FP32 (F32 precision mode)
+template <typename RT> __device__ __forceinline__ const RT* v2_const_A();
+template <> __device__ __forceinline__ const double* v2_const_A<double>() { return c_v2A; }
+template <> __device__ __forceinline__ const float* v2_const_A<float>() { return c_v2Af; }
+// FP64 -> FP32 staging of A for the constant bank
+static __global__ void k_round_to_f32(const double* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
 }
 
 // ---------------------------------------------------------------------------------------------------- the exact scan
@@ -641,7 +547,7 @@ __device__ __forceinline__ void v2_seq_exact(const double* __restrict__ Wn, doub
 }
 
 // ---------------------------------------------------------------------------------------------------- the kernel
-template <int NX, int BASIS, bool FIRST, int CA>
+template <int NX, int BASIS, bool FIRST, int CA, typename RT>
 __global__ void __launch_bounds__(V2_NT, 1)
 k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev vd) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -662,7 +568,7 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
   double* chpfx = reinterpret_cast<double*>(smem_raw + L.chpfx);    // [2][mch+1]
   pgb_agg* chagg = reinterpret_cast<pgb_agg*>(smem_raw + L.chagg);
   pgb_agg* chex = reinterpret_cast<pgb_agg*>(smem_raw + L.chex);
-  double* A_sm = reinterpret_cast<double*>(smem_raw + L.A);
+  RT* A_sm = reinterpret_cast<RT*>(smem_raw + L.A);  // the chain's A as RT (F32 mode: rounded once)
   int* s_anc = reinterpret_cast<int*>(smem_raw + L.sanc);
   const int64_t NP = (int64_t)nt * TILE;
   double* E = vd.stationary ? reinterpret_cast<double*>(smem_raw + L.E) : vd.gE + (int64_t)chain * NP + p0;
@@ -684,13 +590,14 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
   double* pw = vd.pw + (int64_t)chain * nt;
   double* pa = vd.pa + (int64_t)chain * nt;
   double* pa2 = vd.pa2 + (int64_t)chain * nt;
-  double* lwg = fd.lwbuf + (int64_t)chain * N;
+  RT* lwg = reinterpret_cast<RT*>(fd.lwbuf) + (int64_t)chain * N;
   const uint32_t stream_z = ((uint32_t)PGB_STREAM_Z << 24) | ((fd.chain_base + chain) & 0x00ffffffu);
-  for (int i = tid; i < NX * fd.n_phi; i += V2_NT) A_sm[i] = fd.A[(int64_t)chain * NX * fd.n_phi + i];
-  double Lq[NX * NX];
+  for (int i = tid; i < NX * fd.n_phi; i += V2_NT) A_sm[i] = (RT)fd.A[(int64_t)chain * NX * fd.n_phi + i];
+  RT Lq[NX * NX];
 #pragma unroll
-  for (int i = 0; i < NX * NX; ++i) Lq[i] = fd.Lq[chain * 16 + i];
-  const InvDiv ivR = make_invdiv(fd.R[0]);
+  for (int i = 0; i < NX * NX; ++i) Lq[i] = (RT)fd.Lq[chain * 16 + i];
+  RDiv<RT> ivR;
+  ivR.set(fd.R[0]);
 
   V2Scan sm_;  // main scan
   sm_.v = E; sm_.TE = TE; sm_.chsum = chs + mch; sm_.chpfx = chpfx; sm_.chagg = chagg; sm_.chex = chex;
@@ -734,36 +641,36 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
 
   // ------------------------------------------------------------------ t = 0: initial particles (:160-165)
   {
-    double* x0 = x_row(fd, chain, 0);
+    RT* x0 = r_x_row<RT>(fd, chain, 0);
     const double* xp = fd.xprim + (int64_t)chain * NX * T;
     const double* z0in = fd.Z0 ? fd.Z0 + (int64_t)chain * NX * (N - 1) : nullptr;
     const uint32_t stream_z0 = ((uint32_t)PGB_STREAM_Z0 << 24) | ((fd.chain_base + chain) & 0x00ffffffu);
-    double lmax = -INFINITY;
+    RT lmax = (RT)-INFINITY;
     const int pend = p0 + nch * V2_CHUNK;
     for (int n = p0 + tid; n < pend && n < N; n += V2_NT) {
-      double x[NX];
+      RT x[NX];
       if (n == N - 1) {
 #pragma unroll
-        for (int d = 0; d < NX; ++d) x[d] = xp[d];
+        for (int d = 0; d < NX; ++d) x[d] = (RT)xp[d];
       } else {
-        double z[NX];
-        v2_normals<NX>(fd, stream_z0, 0, n, z0in, z);
+        RT z[NX];
+        r_normals<NX>(fd, stream_z0, 0, n, z0in, z);
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
-          double acc = 0.0;
+          RT acc = (RT)0.0;
 #pragma unroll
-          for (int e = 0; e <= d; ++e) acc = __fma_rn(fd.x0_chol[d + NX * e], z[e], acc);
-          x[d] = __dadd_rn(fd.x0_mean[d], acc);
+          for (int e = 0; e <= d; ++e) acc = rfma((RT)fd.x0_chol[d + NX * e], z[e], acc);
+          x[d] = radd((RT)fd.x0_mean[d], acc);
         }
       }
 #pragma unroll
       for (int d = 0; d < NX; ++d) x0[(int64_t)d * N + n] = x[d];
-      const double lw = v2_log_weight<NX>(fd, x, fd.y, ivR);
+      const RT lw = r_log_weight<NX>(fd, x, fd.y, ivR);
       lwg[n] = lw;
       lmax = fmax(lmax, lw);
       if (!(lw == lw)) atomicOr(&fd.status[chain], 4);
     }
-    block_max(lmax);
+    block_max((double)lmax);
   }
   v2_grid_barrier(vd.bar, bar_target);
 
@@ -776,39 +683,28 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
     ss_.flagp = fside;
     // ================================================================ PA: e, F, pdf
     {
-      const double m = ordered_unkey(__ldcg(&fd.maxkey[chain]));
-      const double* xp = x_row(fd, chain, t - 1);
-      double* Fb = fd.Fbuf + (int64_t)chain * NX * N;
+      const RT m = (RT)ordered_unkey(__ldcg(&fd.maxkey[chain]));  // the maximum of RT values: the conversion is exact
+      const RT* xp = r_x_row<RT>(fd, chain, t - 1);
+      RT* Fb = reinterpret_cast<RT*>(fd.Fbuf) + (int64_t)chain * NX * N;
       const double* up = fd.u + (int64_t)fd.n_u * (t - 1);
-      double tku[BASIS == 1 ? 5 : (BASIS == 2 ? PGB_MAX_Z_ * MAXC : 1)];
-      if (!last_only) {  // scaled sines of the input dimensions: the same for every particle of this step
-        if (BASIS == 1) {
-          const double zl = __dadd_rn(up[0], fd.hg_L[0]);
-#pragma unroll
-          for (int j = 0; j < 5; ++j) tku[j] = __dmul_rn(fd.hg_lsi[0], lsin(__dmul_rn(fd.hg_pij2l[0][j], zl)));
-        } else if (BASIS == 2) {
-          for (int k = 0; k < fd.n_u; ++k) {
-            const double zl = __dadd_rn(up[k], fd.hg_L[k]);
-            for (int j = 0; j < fd.hg_count[k]; ++j) tku[k * MAXC + j] = __dmul_rn(fd.hg_lsi[k], lsin(__dmul_rn(fd.hg_pij2l[k][j], zl)));
-          }
-        }
-      }
-      double xref[NX];
-      InvDiv ivL[NX];
-      double c0 = 0.0;
+      RT tku[BASIS == 1 ? 5 : (BASIS == 2 ? PGB_MAX_Z_ * MAXC : 1)];
+      if (!last_only) r_input_sines<BASIS, RT>(fd, up, tku);  // the same for every particle of this step
+      RT xref[NX];
+      RDiv<RT> ivL[NX];
+      RT c0 = (RT)0.0;
       if (anc) {
 #pragma unroll
         for (int d = 0; d < NX; ++d) {
-          xref[d] = fd.xprim[(int64_t)chain * NX * T + d + NX * t];
-          ivL[d] = make_invdiv(Lq[d + NX * d]);
+          xref[d] = (RT)fd.xprim[(int64_t)chain * NX * T + d + NX * t];
+          ivL[d].set(fd.Lq[chain * 16 + d + NX * d]);
         }
-        c0 = fd.c0[chain];
+        c0 = (RT)fd.c0[chain];
       }
       // strided mapping: coalesced scalar accesses, one particle at a time; the inputs of the NEXT particle are
       // loaded before the current one is processed (the loop is latency-bound on these L2 reads otherwise)
-      double lw_n = 0.0, x_n[NX];
+      RT lw_n = (RT)0.0, x_n[NX];
 #pragma unroll
-      for (int d = 0; d < NX; ++d) x_n[d] = 0.0;
+      for (int d = 0; d < NX; ++d) x_n[d] = (RT)0.0;
       {
         const int n = p0 + warp * V2_CHUNK + lane;
         if (warp < nch && n < N) {
@@ -824,8 +720,8 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
         for (int k = 0; k < 4; ++k) {
           const int loc = cc * V2_CHUNK + k * 32 + lane;
           const int n = p0 + loc;
-          const double lw_c = lw_n;
-          double x[NX];
+          const RT lw_c = lw_n;
+          RT x[NX];
 #pragma unroll
           for (int d = 0; d < NX; ++d) x[d] = x_n[d];
           {  // prefetch
@@ -841,23 +737,23 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
           }
           double e = 0.0, pdf = 0.0;
           if (n < N) {
-            e = lexp(__dsub_rn(lw_c, m));
+            e = (double)rexp(rsub(lw_c, m));  // F32 mode: the FP32 exponential, widened exactly
             if (!last_only) {
-              double F[NX];
-              v2_eval_F<NX, BASIS, CA>(fd, A_sm, x, up, tku, F);
+              RT F[NX];
+              r_eval_F<NX, BASIS, CA, RT>(fd, A_sm, v2_const_A<RT>(), x, up, tku, F);
 #pragma unroll
               for (int d = 0; d < NX; ++d) Fb[(int64_t)d * N + n] = F[d];
               if (anc) {  // pdf(MvNormal(x'_t, Q), F) = exp(c0 - |L^-1 (F - x'_t)|^2 / 2)    (:178-179)
-                double rv[NX], sq = 0.0;
+                RT rv[NX], sq = (RT)0.0;
 #pragma unroll
                 for (int d = 0; d < NX; ++d) {
-                  double acc = __dsub_rn(F[d], xref[d]);
+                  RT acc = rsub(F[d], xref[d]);
 #pragma unroll
-                  for (int e2 = 0; e2 < d; ++e2) acc = __fma_rn(-Lq[d + NX * e2], rv[e2], acc);
-                  rv[d] = div_inv(acc, ivL[d]);
-                  sq = __fma_rn(rv[d], rv[d], sq);
+                  for (int e2 = 0; e2 < d; ++e2) acc = rfma(-Lq[d + NX * e2], rv[e2], acc);
+                  rv[d] = ivL[d](acc);
+                  sq = rfma(rv[d], rv[d], sq);
                 }
-                pdf = lexp(__dsub_rn(c0, __dmul_rn(sq, 0.5)));
+                pdf = rexp_wide(rsub(c0, rmul(sq, (RT)0.5)));
               }
             }
           }
@@ -1006,9 +902,9 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
               if (n0 + i < N && slot[i + 1] > slot[i]) vd.star_idx[chain] = (slot[i] < slot[5]) ? -1 : n0 + i;
           }
         } else {
-          double* xt = x_row(fd, chain, t);
+          RT* xt = r_x_row<RT>(fd, chain, t);
           int32_t* at = fd.ah + ((int64_t)chain * T + t) * N;
-          const double* Fb = fd.Fbuf + (int64_t)chain * NX * N;
+          const RT* Fb = reinterpret_cast<const RT*>(fd.Fbuf) + (int64_t)chain * NX * N;
           const double* yt = fd.y + (int64_t)fd.n_y * t;
           const double* zin = fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr;
           for (int ps = J0; ps < J1; ps += V2_CAP) {
@@ -1043,14 +939,14 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
             // (3) propagate: every thread takes output slots (:175 | :188, :194)
             const int cnt = pe_ - ps;
             int a_n = (tid < cnt) ? s_anc[tid] : 0;
-            double F_n[NX];
+            RT F_n[NX];
 #pragma unroll
-            for (int d = 0; d < NX; ++d) F_n[d] = (tid < cnt) ? __ldcg(Fb + (int64_t)d * N + (a_n < 0 ? 0 : a_n)) : 0.0;
+            for (int d = 0; d < NX; ++d) F_n[d] = (tid < cnt) ? __ldcg(Fb + (int64_t)d * N + (a_n < 0 ? 0 : a_n)) : (RT)0.0;
 #pragma unroll 1
             for (int o = tid; o < cnt; o += V2_NT) {
               const int jj = ps + o;
               const int a0 = a_n;
-              double F[NX], z[NX], x[NX];
+              RT F[NX], z[NX], x[NX];
 #pragma unroll
               for (int d = 0; d < NX; ++d) F[d] = F_n[d];
               if (o + V2_NT < cnt) {  // the gathered F of the next slot is in flight while this one is propagated
@@ -1058,33 +954,33 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
 #pragma unroll
                 for (int d = 0; d < NX; ++d) F_n[d] = __ldcg(Fb + (int64_t)d * N + (a_n < 0 ? 0 : a_n));
               }
-              v2_normals<NX>(fd, stream_z, (uint32_t)t, jj, zin, z);
+              r_normals<NX>(fd, stream_z, (uint32_t)t, jj, zin, z);
 #pragma unroll
               for (int d = 0; d < NX; ++d) {
-                double acc = 0.0;
+                RT acc = (RT)0.0;
 #pragma unroll
-                for (int e = 0; e <= d; ++e) acc = __fma_rn(Lq[d + NX * e], z[e], acc);
-                x[d] = __dadd_rn(F[d], acc);
+                for (int e = 0; e <= d; ++e) acc = rfma(Lq[d + NX * e], z[e], acc);
+                x[d] = radd(F[d], acc);
                 xt[(int64_t)d * N + jj] = x[d];
               }
               at[jj] = a0;
-              const double lw = v2_log_weight<NX>(fd, x, yt, ivR);
+              const RT lw = r_log_weight<NX>(fd, x, yt, ivR);
               lwg[jj] = lw;
-              lmax = fmax(lmax, lw);
+              lmax = fmax(lmax, (double)lw);
               if (!(lw == lw)) atomicOr(pend, 4);
             }
             __syncthreads();
           }
           if (ANC && lead && tid == 0) {  // the conditioned trajectory keeps slot N-1 (:160)
-            double x[NX];
+            RT x[NX];
 #pragma unroll
             for (int d = 0; d < NX; ++d) {
-              x[d] = fd.xprim[(int64_t)chain * NX * T + d + NX * t];
+              x[d] = (RT)fd.xprim[(int64_t)chain * NX * T + d + NX * t];
               xt[(int64_t)d * N + (N - 1)] = x[d];
             }
-            const double lw = v2_log_weight<NX>(fd, x, yt, ivR);
+            const RT lw = r_log_weight<NX>(fd, x, yt, ivR);
             lwg[N - 1] = lw;
-            lmax = fmax(lmax, lw);
+            lmax = fmax(lmax, (double)lw);
           }
         }
       }
@@ -1227,33 +1123,33 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
                 for (int i = 0; i < 4; ++i)
                   if (n0 + i < N && rr[i + 1] > rr[i]) *iout = (rr[i] < zu) ? -1 : n0 + i;
               } else {  // by-input expansion (rare path: simplicity over balance)
-                double* xt = x_row(fd, chain, t);
+                RT* xt = r_x_row<RT>(fd, chain, t);
                 int32_t* at = fd.ah + ((int64_t)chain * T + t) * N;
-                const double* Fb = fd.Fbuf + (int64_t)chain * NX * N;
+                const RT* Fb = reinterpret_cast<const RT*>(fd.Fbuf) + (int64_t)chain * NX * N;
                 const double* yt = fd.y + (int64_t)fd.n_y * t;
                 const double* zin = fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr;
 #pragma unroll 1
                 for (int i = 0; i < 4; ++i) {
                   const int n = n0 + i;
                   if (n >= N || rr[i + 1] <= rr[i]) continue;
-                  double F[NX];
+                  RT F[NX];
 #pragma unroll
                   for (int d = 0; d < NX; ++d) F[d] = __ldcg(Fb + (int64_t)d * N + n);
                   for (int jj = rr[i]; jj < rr[i + 1]; ++jj) {
-                    double z[NX], x[NX];
-                    v2_normals<NX>(fd, stream_z, (uint32_t)t, jj, zin, z);
+                    RT z[NX], x[NX];
+                    r_normals<NX>(fd, stream_z, (uint32_t)t, jj, zin, z);
 #pragma unroll
                     for (int d = 0; d < NX; ++d) {
-                      double acc = 0.0;
+                      RT acc = (RT)0.0;
 #pragma unroll
-                      for (int e = 0; e <= d; ++e) acc = __fma_rn(Lq[d + NX * e], z[e], acc);
-                      x[d] = __dadd_rn(F[d], acc);
+                      for (int e = 0; e <= d; ++e) acc = rfma(Lq[d + NX * e], z[e], acc);
+                      x[d] = radd(F[d], acc);
                       xt[(int64_t)d * N + jj] = x[d];
                     }
                     at[jj] = (jj < zu) ? -1 : n;
-                    const double lw = v2_log_weight<NX>(fd, x, yt, ivR);
+                    const RT lw = r_log_weight<NX>(fd, x, yt, ivR);
                     lwg[jj] = lw;
-                    lmax = fmax(lmax, lw);
+                    lmax = fmax(lmax, (double)lw);
                     if (!(lw == lw)) atomicOr(&fd.status[chain], 4);
                   }
                 }
@@ -1262,16 +1158,16 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
             if (pass == 0 && !last_only) {
               if (ANC && lead && tid == 0) {  // the conditioned trajectory keeps slot N-1 (:160)
                 const double* yt = fd.y + (int64_t)fd.n_y * t;
-                double* xt = x_row(fd, chain, t);
-                double x[NX];
+                RT* xt = r_x_row<RT>(fd, chain, t);
+                RT x[NX];
 #pragma unroll
                 for (int d = 0; d < NX; ++d) {
-                  x[d] = fd.xprim[(int64_t)chain * NX * T + d + NX * t];
+                  x[d] = (RT)fd.xprim[(int64_t)chain * NX * T + d + NX * t];
                   xt[(int64_t)d * N + (N - 1)] = x[d];
                 }
-                const double lw = v2_log_weight<NX>(fd, x, yt, ivR);
+                const RT lw = r_log_weight<NX>(fd, x, yt, ivR);
                 lwg[N - 1] = lw;
-                lmax = fmax(lmax, lw);
+                lmax = fmax(lmax, (double)lw);
               }
               block_max(lmax);
             }

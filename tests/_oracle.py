@@ -34,7 +34,7 @@ def lib():
     if _lib is None:
         so = os.path.join(ORACLE_DIR, "libpg_oracle.so")
         src = [os.path.join(ORACLE_DIR, f) for f in ("pg_oracle.c", "pg_oracle.h")] + [
-            os.path.join(ROOT, "pgopt_b200", "csrc", "pgb_math.h")]
+            os.path.join(ROOT, "pgopt_b200", "csrc", "pgb_math.h"), os.path.join(ROOT, "pgopt_b200", "csrc", "pgb_mathf.h")]
         if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
             subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
         _lib = C.CDLL(so)
@@ -115,8 +115,8 @@ def make_streams(philox=True, seed=0, chain=0, Z0=None, Ures=None, Z=None, Uanc=
     return s
 
 
-def sweep(model, N, T, u, y, Cm, R, x0_mean, x0_chol, A, Q, x_prim, first, streams, sweep_index, hist=True):
-    """Returns dict with a (T,N) 1-based, x (T,N,n_x), w (T,N), w_last, x_last (N,n_x), Phi, Psi, Sigma,
+def sweep(model, N, T, u, y, Cm, R, x0_mean, x0_chol, A, Q, x_prim, first, streams, sweep_index, hist=True, f32=False):
+    """f32: the F32 precision mode (orc_sweep_f32).  Returns dict with a (T,N) 1-based, x (T,N,n_x), w (T,N), w_last, x_last (N,n_x), Phi, Psi, Sigma,
     star, x_prim (n_x,T) Fortran-order arrays where the reference uses matrices."""
     n_x, n_phi = model.n_x, model.n_phi
     u, y, Cm, R = f64(np.asfortranarray(u).ravel(order="F")), f64(np.asfortranarray(y).ravel(order="F")), \
@@ -131,9 +131,10 @@ def sweep(model, N, T, u, y, Cm, R, x0_mean, x0_chol, A, Q, x_prim, first, strea
     w_last, x_last = np.zeros(N), np.zeros((N, n_x))
     Phi, Psi, Sig = np.zeros(n_x * n_x), np.zeros(n_x * n_phi), np.zeros(n_phi * n_phi)
     star = C.c_int64(0)
-    st = lib().orc_sweep(C.byref(model), C.c_int64(N), C.c_int64(T), _p(u), _p(y), _p(Cm), _p(R), _p(x0m), _p(x0c),
-                         _p(A), _p(Q), _p(xp), C.c_int(int(first)), C.byref(streams), C.c_uint32(sweep_index),
-                         _p(a), _p(xh), _p(wh), _p(w_last), _p(x_last), _p(Phi), _p(Psi), _p(Sig), C.byref(star))
+    fn = lib().orc_sweep_f32 if f32 else lib().orc_sweep
+    st = fn(C.byref(model), C.c_int64(N), C.c_int64(T), _p(u), _p(y), _p(Cm), _p(R), _p(x0m), _p(x0c),
+            _p(A), _p(Q), _p(xp), C.c_int(int(first)), C.byref(streams), C.c_uint32(sweep_index),
+            _p(a), _p(xh), _p(wh), _p(w_last), _p(x_last), _p(Phi), _p(Psi), _p(Sig), C.byref(star))
     return dict(status=st, a=a, x=xh, w=wh, w_last=w_last, x_last=x_last,
                 Phi=Phi.reshape((n_x, n_x), order="F"), Psi=Psi.reshape((n_x, n_phi), order="F"),
                 Sigma=Sig.reshape((n_phi, n_phi), order="F"), star=star.value,
@@ -206,6 +207,21 @@ def draw_xT(w_m1, x_m1, seed, cid):
     st = lib().orc_draw_xT(C.c_int64(N), C.c_int(n_x), _p(f64(w_m1)), _p(x_m1), C.c_uint64(seed), C.c_uint32(cid), _p(out))
     assert st == 0
     return out
+
+
+def dynamics(model, A, x_vec, u, v=None, t=0, variant=0):
+    """orc_dynamics: A (K,n_x,n_phi), x_vec (K,n_x), u (n_u,), v (K,H,n_x) or None -> x_next (K,n_x), dfdx (K,n_x,n_x),
+    dfdu (K,n_x,n_u) (matrices as NumPy row-major views of the column-major blocks: [k, row, col])"""
+    K, n_x, n_phi = A.shape
+    n_u = model.n_u
+    Af = f64(np.transpose(A, (0, 2, 1)))
+    xn, jx, ju = np.zeros((K, n_x)), np.zeros((K, n_x, n_x)), np.zeros((K, n_u, n_x))
+    vv = None if v is None else f64(v)
+    H = 0 if v is None else v.shape[1]
+    st = lib().orc_dynamics(C.byref(model), C.c_int64(K), _p(Af), _p(f64(x_vec)), _p(f64(u)), None if vv is None else _p(vv),
+                            C.c_int64(H), C.c_int64(t), C.c_int(variant), _p(xn), _p(jx), _p(ju))
+    assert st == 0
+    return xn, np.transpose(jx, (0, 2, 1)), np.transpose(ju, (0, 2, 1))
 
 
 def test_prediction(model, K, k_n, T_test, N, A, Q, w_m1, x_m1, u_m1, Cm, Le, u_test, y_test, seed):

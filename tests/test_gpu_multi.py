@@ -96,3 +96,7 @@ def test_multi_scenario_sharded_rollout():
             out = m.rollout(pg.LinearMeasurement(Cm), 0.1, H, u_init=u_init, seed=6)
             for name in ("x0", "X", "Y"):
                 _assert_same("%s on %s" % (name, devs), out[name], ref[name])
+            for d in range(len(devs)):  # ... and every device holds all of them after the all-gather
+                got = m.scenarios_on(d, H)
+                for name in ("x0", "X", "Y"):
+                    _assert_same("%s gathered on device %d of %s" % (name, d, devs), got[name], ref[name])

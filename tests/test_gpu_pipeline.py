@@ -266,3 +266,56 @@ def test_checkpoint_resume_is_bit_identical():
                 assert a == b == 6
             else:
                 _assert_same("chain %d %s" % (c, name), a, b)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# stacked-scenario dynamics + Jacobians (optimal_control_Altro.jl:79-107, @autodiff :51)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("model,variant", [("known", 0), ("hilbert4", 0), ("hilbert4", 1), ("hilbert2", 0)])
+def test_stacked_dynamics_and_jacobians(model, variant):
+    rng = np.random.default_rng(91)
+    if model == "known":
+        basis, om, n_x = pg.KnownBasisVB(), O.known_model(), 2
+    elif model == "hilbert4":
+        basis = pg.HilbertGPBasis([1, 5, 5, 5, 5], [4.0, 5.0, 6.0, 7.0, 8.0])
+        om, n_x = O.hilbert_model(4, 1, basis.count, basis.stride, basis.L), 4
+    else:
+        basis = pg.HilbertGPBasis([3, 4, 2], [6.0, 9.0, 11.0])
+        om, n_x = O.hilbert_model(2, 1, basis.count, basis.stride, basis.L), 2
+    K, H, N = 77, 7, 12
+    A = rng.normal(0, 0.3, (K, n_x, basis.n_phi))
+    Bq = rng.normal(0, 0.1, (K, n_x, n_x))
+    Q = Bq @ np.transpose(Bq, (0, 2, 1)) + 0.05 * np.eye(n_x)
+    w = rng.uniform(size=(K, N))
+    w /= w.sum(1, keepdims=True)
+    x = rng.normal(0, 1, (K, N, n_x))
+    um = rng.normal(0, 1, (K, 1))
+    Cm = np.zeros((1, n_x))
+    Cm[0, 0] = 1.0
+    u_init = rng.normal(0, 1, (1, H))
+    batch = pg.PGSampleBatch(A, Q, w, np.transpose(x, (0, 2, 1)), um)
+    with pg.DeviceSamples.from_samples(batch, basis) as ds:
+        sc = ds.rollout(pg.LinearMeasurement(Cm), 0.1, H, u_init=u_init, seed=4).scenarios()
+        t = 3
+        xn, jx, ju = ds.dynamics(sc["X"][:, t].reshape(-1), u_init[:, t], t=t, phi_variant=variant)
+        rx, rjx, rju = O.dynamics(om, A, sc["X"][:, t], u_init[:, t], sc["v"], t, variant)
+        _assert_same("x_next", xn.reshape(K, n_x), rx)
+        _assert_same("df/dx", jx, rjx)
+        _assert_same("df/du", ju, rju)
+        if variant == 0:  # the same function the rollout iterates: X[t+1], bit for bit
+            _assert_same("x_next == X[t+1]", xn.reshape(K, n_x), sc["X"][:, t + 1])
+        # without the noise term, and against central differences of the kernel itself
+        x0 = sc["X"][:, t].copy()
+        f0, _, _ = ds.dynamics(x0.reshape(-1), u_init[:, t], t=None, phi_variant=variant, jacobians=False)
+        _assert_same("no noise", f0.reshape(K, n_x), O.dynamics(om, A, x0, u_init[:, t], None, 0, variant)[0])
+        eps = 1e-6
+        for c in range(n_x):
+            xp, xm = x0.copy(), x0.copy()
+            xp[:, c] += eps
+            xm[:, c] -= eps
+            fd = (ds.dynamics(xp.reshape(-1), u_init[:, t], t=None, phi_variant=variant, jacobians=False)[0]
+                  - ds.dynamics(xm.reshape(-1), u_init[:, t], t=None, phi_variant=variant, jacobians=False)[0]) / (2 * eps)
+            np.testing.assert_allclose(jx[:, :, c], fd.reshape(K, n_x), rtol=0, atol=2e-8)
+        fu = (ds.dynamics(x0.reshape(-1), u_init[:, t] + eps, t=None, phi_variant=variant, jacobians=False)[0]
+              - ds.dynamics(x0.reshape(-1), u_init[:, t] - eps, t=None, phi_variant=variant, jacobians=False)[0]) / (2 * eps)
+        np.testing.assert_allclose(ju[:, :, 0], fu.reshape(K, n_x), rtol=0, atol=2e-8)
