@@ -51,10 +51,10 @@ end
 
 pad8(v, T) = ntuple(i -> i <= length(v) ? T(v[i]) : zero(T), PGB_MAX_Z)
 
-function make_config(phi, n_y, N, T; device=0, n_chains=1)
+function make_config(phi, n_y, N, T; device=0, n_chains=1, precision=0)   # precision: 0 = Float64 (reference), 1 = PGB_PRECISION_F32
     if phi isa KnownBasisVB
         return PgbConfig(device, 2, 1, n_y, 5, 0, pad8(Int[], Int32), pad8(Int[], Int32), pad8(Float64[], Float64),
-                         N, T, n_chains, 0, 0, 0), 2, 1, 5
+                         N, T, n_chains, 0, 0, precision), 2, 1, 5
     elseif phi isa HilbertGPBasis
         nz = length(phi.L)
         # the reference reverses the index vectors (:82): dimension k uses slot nz+1-k
@@ -62,7 +62,7 @@ function make_config(phi, n_y, N, T; device=0, n_chains=1)
         stride = [prod(phi.n_phi_dims[1:nz-k]) for k in 1:nz]
         n_phi = prod(phi.n_phi_dims)
         return PgbConfig(device, nz - phi.n_u, phi.n_u, n_y, n_phi, 1, pad8(count, Int32), pad8(stride, Int32),
-                         pad8(phi.L, Float64), N, T, n_chains, 0, 0, 0), nz - phi.n_u, phi.n_u, n_phi
+                         pad8(phi.L, Float64), N, T, n_chains, 0, 0, precision), nz - phi.n_u, phi.n_u, n_phi
     else
         throw(ArgumentError("phi must be a KnownBasisVB or HilbertGPBasis descriptor: arbitrary closures cannot " *
                             "cross the C ABI and there is no CPU fallback"))
@@ -111,9 +111,9 @@ end
 Same signature as Julia/src/particle_Gibbs.jl:114; `phi` / `g` are descriptors.
 """
 function particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist,
-                        g::LinearMeasurement, R; x_prim=nothing, seed=rand(UInt64), chain=0, device=0)
+                        g::LinearMeasurement, R; x_prim=nothing, seed=rand(UInt64), chain=0, device=0, precision=0)
     n_y, T = size(y_training)
-    cfg, n_x, n_u, n_phi = make_config(phi, n_y, N, T; device=device)
+    cfg, n_x, n_u, n_phi = make_config(phi, n_y, N, T; device=device, precision=precision)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:pgb_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{PgbConfig}), h, cfg))
     try
@@ -158,6 +158,7 @@ The sampling + forward rollout solve_PG_OCP_Ipopt does before building the NLP
 reference's layouts — pass the first three back as keyword arguments of solve_PG_OCP_Ipopt.
 """
 function scenario_rollout(PG_samples::Vector{PG_sample}, phi, g::LinearMeasurement, R, H; u_init=nothing,
+                          x_vec_0=nothing, v_vec=nothing, e_vec=nothing,   # the reference's kwargs (:37, :48, :67, :77)
                           seed=rand(UInt64), k_offset=0, device=0)
     K = length(PG_samples); N = length(PG_samples[1].w_m1); n_y = size(g.C, 1)
     cfg, n_x, n_u, n_phi = make_config(phi, n_y, N, 2; device=device)
@@ -169,11 +170,12 @@ function scenario_rollout(PG_samples::Vector{PG_sample}, phi, g::LinearMeasureme
     um = hcat([s.u_m1 for s in PG_samples]...)
     x0 = Array{Float64}(undef, n_x, K); v = Array{Float64}(undef, n_x, H, K); e = Array{Float64}(undef, n_y, H, K)
     X = Array{Float64}(undef, n_x, H + 1, K); Y = Array{Float64}(undef, n_y, H, K)
-    check(ccall((:pgb_rollout, LIB), Cint,
+    opt(a) = a === nothing ? C_NULL : Array{Float64}(a)   # (n_x*K,), (n_x,H,K), (n_y,H,K): column-major = the ABI's layouts
+    check(ccall((:pgb_rollout_supplied, LIB), Cint,
                 (Ref{PgbConfig}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
                  Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, UInt64, UInt32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-                 Ptr{Float64}, Ptr{Float64}),
-                cfg, K, H, A, Q, w, x, um, g.C, Le, u0, seed, k_offset, x0, v, e, X, Y))
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                cfg, K, H, A, Q, w, x, um, g.C, Le, u0, seed, k_offset, opt(x_vec_0), opt(v_vec), opt(e_vec), x0, v, e, X, Y))
     X_init = reshape(permutedims(X, (1, 3, 2)), n_x * K, H + 1)
     Y_init = reshape(permutedims(Y, (1, 3, 2)), n_y * K, H)
     return vec(x0), v, e, X_init, Y_init
@@ -222,6 +224,76 @@ function scenario_constraint_max(y_opt::Array{Float64,3}, y_min, y_max; device=0
                 (Int32, Int64, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
                 device, K, H, n_y, y_opt, lo, hi, h_max, order))
     return h_max, order
+end
+
+# ---------------------------------------------------------------------------------------------------------------------
+# several GPUs (`devices = [0, 1, ...]`), device-resident samples, stacked dynamics — include/pgopt_b200.h: pgb_multi_*,
+# pgb_samples_*, pgb_dynamics_dev.  Thin stubs over the C ABI, in the order a maintainer would wire them.
+# ---------------------------------------------------------------------------------------------------------------------
+"""
+    particle_Gibbs_multi(u, y, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist, g, R; n_chains, devices)
+
+`n_chains` independent chains of `particle_Gibbs` dealt to `devices` (one process, in-process NCCL).  The kept samples
+stay on the GPU that produced them; returns the packed records `[A | Q | x_T | u_m1]` of all chains, a
+`(record, K, n_chains)` array (x_T = x_m1[:, star] drawn on the owning GPU, optimal_control_Ipopt.jl:58-59), and the handle
+for `multi_rollout`.
+"""
+function particle_Gibbs_multi(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, ell_Q, Q_init, V, A_init, x_init_dist,
+                              g::LinearMeasurement, R; n_chains, devices=[0], seed=rand(UInt64), roll_seed=rand(UInt64))
+    n_y, T = size(y_training)
+    cfg, n_x, n_u, n_phi = make_config(phi, n_y, N, T; n_chains=n_chains)
+    m = Ref{Ptr{Cvoid}}(C_NULL)
+    dv = Vector{Int32}(devices)
+    mcheck(rc) = rc == 0 ? nothing : error("pgopt_b200 error $rc: " * unsafe_string(ccall((:pgb_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), m[])))
+    mcheck(ccall((:pgb_multi_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{PgbConfig}, Ptr{Int32}, Int32), m, cfg, dv, length(dv)))
+    mcheck(ccall((:pgb_multi_set_data, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m[], Matrix{Float64}(u_training), Matrix{Float64}(y_training)))
+    Rm = R isa Number ? fill(Float64(R), 1, 1) : Matrix{Float64}(R)
+    mcheck(ccall((:pgb_multi_set_measurement, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m[], g.C, Rm))
+    mu = Vector{Float64}(mean(x_init_dist)); Lc = Matrix{Float64}(cholesky(Matrix(cov(x_init_dist))).L)
+    mcheck(ccall((:pgb_multi_set_init_dist, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m[], mu, Lc))
+    Vd = V isa Diagonal ? Vector{Float64}(V.diag) : Vector{Float64}(diag(V))
+    mcheck(ccall((:pgb_multi_set_prior, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), m[], Vd, Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q)))
+    mcheck(ccall((:pgb_multi_set_state, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
+                 m[], -1, Matrix{Float64}(A_init), Matrix{Float64}(Q_init * I(n_x)), C_NULL, 1))
+    mcheck(ccall((:pgb_multi_set_rng_philox, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt32), m[], seed, 0))
+    R_ = ccall((:pgb_packed_record_doubles, LIB), Int64, (Int32, Int32, Int32), n_x, n_phi, n_u)
+    packed = Array{Float64}(undef, R_, K, n_chains)
+    mcheck(ccall((:pgb_multi_particle_gibbs, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, UInt64, Ptr{Float64}), m[], K, K_b, k_d, roll_seed, packed))
+    return packed, m[]          # release with ccall((:pgb_multi_destroy, LIB), Cvoid, (Ptr{Cvoid},), m)
+end
+
+"""
+    multi_rollout(m, g, R, H, n_x, K_total; u_init, seed)   ->  (x_vec_0, X_init, Y_init)
+
+Scenario rollout of every resident sample, each GPU its own, outputs gathered (NCCL) and returned in the reference's
+layouts.  `seed` must be the `roll_seed` of `particle_Gibbs_multi`.
+"""
+function multi_rollout(m::Ptr{Cvoid}, g::LinearMeasurement, R, H, n_x, n_u, K_total; u_init=nothing, seed)
+    n_y = size(g.C, 1)
+    Le = R isa Number ? fill(Float64(R), 1, 1) : Matrix{Float64}(cholesky(Matrix(R)).L)
+    u0 = u_init === nothing ? zeros(n_u, H) : Matrix{Float64}(u_init)
+    x0 = Array{Float64}(undef, n_x, K_total); X = Array{Float64}(undef, n_x, H + 1, K_total); Y = Array{Float64}(undef, n_y, H, K_total)
+    rc = ccall((:pgb_multi_rollout, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+               m, H, g.C, Le, u0, seed, x0, X, Y)
+    rc == 0 || error("pgopt_b200 error $rc: " * unsafe_string(ccall((:pgb_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), m)))
+    return vec(x0), reshape(permutedims(X, (1, 3, 2)), n_x * K_total, H + 1), reshape(permutedims(Y, (1, 3, 2)), n_y * K_total, H)
+end
+
+"""
+    discrete_dynamics_jacobians(samples, x_vec, u, t; phi_variant=1)  ->  (x_vec_n, dfdx, dfdu)
+
+RobotDynamics.discrete_dynamics of PGS_model_obj (Julia/src/optimal_control_Altro.jl:79-107) and the Jacobians @autodiff
+(:51) derives from it, on a device-resident sample set (`samples::Ptr{Cvoid}` from pgb_samples_create / pgb_particle_gibbs_dev
+after a pgb_rollout_dev that left v_vec on the device).  dfdx[:, :, k] is the k-th diagonal block, dfdu[:, :, k] rows
+n_x*(k-1)+1 .. n_x*k of the (K n_x) x n_u Jacobian.  phi_variant 1 = the rounding of the examples' phi_opt.
+"""
+function discrete_dynamics_jacobians(samples::Ptr{Cvoid}, x_vec::Vector{Float64}, u::Vector{Float64}, t::Integer, n_x, n_u; phi_variant=1)
+    K = div(length(x_vec), n_x)
+    xn = Vector{Float64}(undef, K * n_x); jx = Array{Float64}(undef, n_x, n_x, K); ju = Array{Float64}(undef, n_x, n_u, K)
+    rc = ccall((:pgb_dynamics_dev, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+               samples, x_vec, u, t, phi_variant, xn, jx, ju)
+    rc == 0 || error("pgopt_b200 error $rc: " * unsafe_string(ccall((:pgb_samples_last_error, LIB), Cstring, (Ptr{Cvoid},), samples)))
+    return xn, jx, ju
 end
 
 end # module

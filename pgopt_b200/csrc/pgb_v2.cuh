@@ -25,11 +25,11 @@
 //   PA  e = exp(lw - max) (:198), F = A*phi(x_{t-1}), pdf = N(x'_t; F, Q); tile sums of e          | B1
 //   PB  w = e/S1 (:199), waN = w*pdf (:179); tile sums of w, waN                                    | B2
 //   PC  W = w/S2 (:19), binade prediction, integer maps, composition scan per chunk / CTA;
-//       waN ./= S3 (:180), tile sums                                                                | B3
+//       ancestor draw of slot N (:181) by the certified approximate scan of the raw waN             | B3
 //   PD  resolve -> exact prefixes, seam check -> offspring counts -> by-output expansion:
-//       a[t,:], x_t = F[a] + L z (:175|:188), lw (:194), max;  ancestor draw of slot N (:181) by the
-//       certified approximate scan                                                                  | B0
-//   (rare, grid-uniform: exact scan of the ancestor weights; serial exact walk after a failed seam check)
+//       a[t,:], x_t = F[a] + L z (:175|:188), lw (:194), max                                        | B0
+//   (rare, grid-uniform: waN ./= S3 (:180) + exact scan of the ancestor weights when the shortcut is undecided;
+//    serial exact walk after a failed seam check)
 #pragma once
 #include "pgb_real.cuh"
 #include "pgb_v2_types.h"
@@ -46,6 +46,8 @@ struct V2Shared {
   double seeds[V2_MAXREC + 1];
   pgb_utable ut;
   double tp_lo, tp_hi;          // approximate raw prefix of the tile sums at the CTA's first / past-the-last tile
+  double tq_lo;                 // the same for the second array of v2_tiles_collective2 (first tile only)
+  double redqlo[2][8];
   long long J0, J1;
   int flag_sh, any_sh, nrec, pad_;
 };
@@ -156,38 +158,42 @@ __device__ __forceinline__ double v2_tiles_collective2(const double* __restrict_
                                                        int at_lo, int at_hi, V2Shared& sh, int& par, double* Sq) {
   const int tid = threadIdx.x;
   if (tid < 256) {
-    double lo = 0.0, hi = 0.0, d0 = 0.0, d1 = 0.0, v, w;
-    if (n <= 256) { v = v2_tree_load<1>(p, tid, n, at_lo, at_hi, lo, hi); w = v2_tree_load<1>(q, tid, n, 0, 0, d0, d1); }
-    else if (n <= 512) { v = v2_tree_load<2>(p, tid * 2, n, at_lo, at_hi, lo, hi); w = v2_tree_load<2>(q, tid * 2, n, 0, 0, d0, d1); }
-    else if (n <= 1024) { v = v2_tree_load<4>(p, tid * 4, n, at_lo, at_hi, lo, hi); w = v2_tree_load<4>(q, tid * 4, n, 0, 0, d0, d1); }
-    else if (n <= 2048) { v = v2_tree_load<8>(p, tid * 8, n, at_lo, at_hi, lo, hi); w = v2_tree_load<8>(q, tid * 8, n, 0, 0, d0, d1); }
-    else { v = v2_tree_load<16>(p, tid * 16, n, at_lo, at_hi, lo, hi); w = v2_tree_load<16>(q, tid * 16, n, 0, 0, d0, d1); }
+    double lo = 0.0, hi = 0.0, d0 = 0.0, d1 = 0.0, v, w;  // d0: raw prefix of q at at_lo
+    if (n <= 256) { v = v2_tree_load<1>(p, tid, n, at_lo, at_hi, lo, hi); w = v2_tree_load<1>(q, tid, n, at_lo, 0, d0, d1); }
+    else if (n <= 512) { v = v2_tree_load<2>(p, tid * 2, n, at_lo, at_hi, lo, hi); w = v2_tree_load<2>(q, tid * 2, n, at_lo, 0, d0, d1); }
+    else if (n <= 1024) { v = v2_tree_load<4>(p, tid * 4, n, at_lo, at_hi, lo, hi); w = v2_tree_load<4>(q, tid * 4, n, at_lo, 0, d0, d1); }
+    else if (n <= 2048) { v = v2_tree_load<8>(p, tid * 8, n, at_lo, at_hi, lo, hi); w = v2_tree_load<8>(q, tid * 8, n, at_lo, 0, d0, d1); }
+    else { v = v2_tree_load<16>(p, tid * 16, n, at_lo, at_hi, lo, hi); w = v2_tree_load<16>(q, tid * 16, n, at_lo, 0, d0, d1); }
     v = warp_tree_sum(v);
     w = warp_tree_sum(w);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       lo = __dadd_rn(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = __dadd_rn(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      d0 = __dadd_rn(d0, __shfl_xor_sync(0xffffffffu, d0, o));
     }
     if ((tid & 31) == 0) {
       sh.red[par][tid >> 5] = v;
       sh.redq[par][tid >> 5] = w;
       sh.redlo[par][tid >> 5] = lo;
       sh.redhi[par][tid >> 5] = hi;
+      sh.redqlo[par][tid >> 5] = d0;
     }
   }
   __syncthreads();
   const double* s = sh.red[par];
   const double* sq = sh.redq[par];
   if (tid == 0) {
-    double lo = 0.0, hi = 0.0;
+    double lo = 0.0, hi = 0.0, ql = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       lo = __dadd_rn(lo, sh.redlo[par][i]);
       hi = __dadd_rn(hi, sh.redhi[par][i]);
+      ql = __dadd_rn(ql, sh.redqlo[par][i]);
     }
     sh.tp_lo = lo;
     sh.tp_hi = hi;
+    sh.tq_lo = ql;
   }
   par ^= 1;
   *Sq = __dadd_rn(__dadd_rn(__dadd_rn(sq[0], sq[1]), __dadd_rn(sq[2], sq[3])),
@@ -822,6 +828,7 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
       publish_tiles(1, pw);
       if (anc) publish_tiles(2, pa);
       if (warp == V2_NW - 1) chunk_prefix(1, chpfx);
+      if (anc && warp == V2_NW - 2) chunk_prefix(2, chpfx + (mch + 1));  // raw prefix of the waN chunk sums: ancestor shortcut (PC)
     }
     V2_TICK(3);
     v2_grid_barrier(vd.bar, bar_target);  // B2
@@ -834,23 +841,39 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
       __syncthreads();  // sh.tp_lo / tp_hi (written by thread 0 after the collective's barrier)
       v2_scan_local(sm_, S2, sh);
       if (anc) {
-        const InvDiv ivS3 = make_invdiv(S3);
+        // Ancestor draw of slot N (:181) by the CERTIFIED shortcut, straight from the un-normalised waN: the reference
+        // normalises twice (waN' = waN/S3 at :180, W' = waN'/S4 inside systematic_resampling :19) and walks q += W'[n];
+        // S3 and S4 are balanced-tree sums, so |S4 - 1| <= 44 eps and W'_n = (waN_n/S3)(1 +- 46 eps), and the sequential
+        // walk adds at most n eps: |q_n - sum_{i<=n} waN_i/S3| <= (N + 46) eps.  The approximate prefix below (tile /
+        // chunk / lane prefixes of waN times fl(1/S3)) is within ~100 eps of that sum, so delta = 6 (N + 4096) eps bounds
+        // their distance with a wide margin; a draw farther than delta from both neighbouring prefixes is decided here,
+        // the others (about 1e-3 of the steps) take the exact scan after B0 — which is also where waN', its sums and S4
+        // are computed now: the common path no longer touches them.
+        const double inv3 = __ddiv_rn(1.0, S3);
+        const double tqa = sh.tq_lo;
+        const double ua = fd.utab_anc[(int64_t)chain * T + t].u0[0];  // one draw: u = rand()
+        const double delta = 6.0 * ((double)N + 4096.0) * 0x1p-53;
+        const double* cpa = chpfx + (mch + 1);
         for (int cc = warp; cc < nch; cc += V2_NW) {
           const int loc = cc * V2_CHUNK + lane * 4;
           const int n0 = p0 + loc;
           const double2 c = *reinterpret_cast<const double2*>(Pv + loc), d2 = *reinterpret_cast<const double2*>(Pv + loc + 2);
           const double av[4] = {c.x, c.y, d2.x, d2.y};
-          double v[4];
+          double W[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = (n0 + i < N) ? div_inv(av[i], ivS3) : 0.0;
-          *reinterpret_cast<double2*>(Pv + loc) = make_double2(v[0], v[1]);
-          *reinterpret_cast<double2*>(Pv + loc + 2) = make_double2(v[2], v[3]);
-          const double s = warp_tree_sum(tree4(v));
-          if (lane == 0) chs[3 * mch + cc] = s;
+          for (int i = 0; i < 4; ++i) W[i] = (n0 + i < N) ? __dmul_rn(av[i], inv3) : 0.0;
+          const double s1 = W[0], s2 = __dadd_rn(s1, W[1]), s3 = __dadd_rn(s2, W[2]), s4 = __dadd_rn(s3, W[3]);
+          const double inc = v2_warp_incl_scan(s4);
+          const double P = __dadd_rn(__dmul_rn(__dadd_rn(tqa, cpa[cc]), inv3), __dsub_rn(inc, s4));
+          const double qt[5] = {P, __dadd_rn(P, s1), __dadd_rn(P, s2), __dadd_rn(P, s3), __dadd_rn(P, s4)};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (n0 + i < N && (qt[i] + delta < ua) && (ua <= qt[i + 1] - delta)) {
+              atomicAdd(&vd.cand[2 * chain], 1);
+              vd.cand[2 * chain + 1] = n0 + i;
+            }
+          }
         }
-        __syncthreads();
-        publish_tiles(3, pa2);
-        if (warp == V2_NW - 1) chunk_prefix(3, chpfx + (mch + 1));
       }
     }
     V2_TICK(5);
@@ -858,16 +881,16 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
     V2_TICK(6);
     // ================================================================ PD: resolve, exact prefixes, expansion; side shortcut
     {
+      {  // the step's sampling grid -> shared memory; issued first so that its L2 latency hides behind the resolve
+        const pgb_utable* utg = last_only ? &fd.utab_star[chain] : &fd.utab_res[(int64_t)chain * T + t];
+        const int* src = reinterpret_cast<const int*>(utg);
+        int* dst = reinterpret_cast<int*>(&sh.ut);
+        for (int i = tid; i < (int)(sizeof(pgb_utable) / 4); i += V2_NT) dst[i] = src[i];
+      }
       const bool ok = v2_resolve(sm_, sh, vd.force_fallback & 1);
       if (tid == 0) {
         sh.flag_sh = __ldcg(fmain) & 1;
         if (lead) fd.main.counters[2 * chain + 1] += 1;
-      }
-      const pgb_utable* utg = last_only ? &fd.utab_star[chain] : &fd.utab_res[(int64_t)chain * T + t];
-      {
-        const int* src = reinterpret_cast<const int*>(utg);
-        int* dst = reinterpret_cast<int*>(&sh.ut);
-        for (int i = tid; i < (int)(sizeof(pgb_utable) / 4); i += V2_NT) dst[i] = src[i];
       }
       __syncthreads();
       const bool skip = !ok || sh.flag_sh != 0;
@@ -986,36 +1009,6 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
       }
       if (!last_only) block_max(lmax);
       V2_TICK(7);
-      // side chain: certified approximate draw of the ancestor of slot N (:181)
-      if (anc) {
-        const double S4 = v2_tiles_collective(pa2, nt, t0tile, t0tile + ntile, sh, par);
-        __syncthreads();
-        const double tpa = sh.tp_lo;
-        const InvDiv ivS4 = make_invdiv(S4);
-        const double ua = fd.utab_anc[(int64_t)chain * T + t].u0[0];  // one draw: u = rand()
-        const double delta = 6.0 * ((double)N + 4096.0) * 0x1p-53;
-        const double* cpa = chpfx + (mch + 1);
-        for (int cc = warp; cc < nch; cc += V2_NW) {
-          const int loc = cc * V2_CHUNK + lane * 4;
-          const int n0 = p0 + loc;
-          const double2 c = *reinterpret_cast<const double2*>(Pv + loc), d2 = *reinterpret_cast<const double2*>(Pv + loc + 2);
-          const double av[4] = {c.x, c.y, d2.x, d2.y};
-          double W[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) W[i] = (n0 + i < N) ? div_inv(av[i], ivS4) : 0.0;
-          const double s1 = W[0], s2 = __dadd_rn(s1, W[1]), s3 = __dadd_rn(s2, W[2]), s4 = __dadd_rn(s3, W[3]);
-          const double inc = v2_warp_incl_scan(s4);
-          const double P = __dadd_rn(__dmul_rn(__dadd_rn(tpa, cpa[cc]), ivS4.y), __dsub_rn(inc, s4));
-          const double qt[5] = {P, __dadd_rn(P, s1), __dadd_rn(P, s2), __dadd_rn(P, s3), __dadd_rn(P, s4)};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (n0 + i < N && (qt[i] + delta < ua) && (ua <= qt[i + 1] - delta)) {
-              atomicAdd(&vd.cand[2 * chain], 1);
-              vd.cand[2 * chain + 1] = n0 + i;
-            }
-          }
-        }
-      }
     }
     V2_TICK(8);
     v2_grid_barrier(vd.bar, bar_target);  // B0
@@ -1032,6 +1025,29 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
         int32_t* aout = fd.ah + ((int64_t)chain * T + t) * N + (N - 1);
         if (!amb_me && lead && tid == 0) *aout = __ldcg(&vd.cand[2 * chain + 1]);
         if (amb_any) {
+          // waN' = waN / S3 (:180) with its chunk / tile sums and chunk prefixes: only this exact scan needs them
+          if (amb_me) {
+            const InvDiv ivS3 = make_invdiv(S3);
+            for (int cc = warp; cc < nch; cc += V2_NW) {
+              const int loc = cc * V2_CHUNK + lane * 4;
+              const int n0 = p0 + loc;
+              const double2 c = *reinterpret_cast<const double2*>(Pv + loc), d2 = *reinterpret_cast<const double2*>(Pv + loc + 2);
+              const double av[4] = {c.x, c.y, d2.x, d2.y};
+              double v[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[i] = (n0 + i < N) ? div_inv(av[i], ivS3) : 0.0;
+              *reinterpret_cast<double2*>(Pv + loc) = make_double2(v[0], v[1]);
+              *reinterpret_cast<double2*>(Pv + loc + 2) = make_double2(v[2], v[3]);
+              const double sv = warp_tree_sum(tree4(v));
+              if (lane == 0) chs[3 * mch + cc] = sv;
+            }
+          }
+          __syncthreads();
+          if (amb_me) {
+            publish_tiles(3, pa2);
+            if (warp == V2_NW - 1) chunk_prefix(3, chpfx + (mch + 1));
+          }
+          v2_grid_barrier(vd.bar, bar_target);  // every CTA of the chain has published its tile sums of waN'
           const double S4 = v2_tiles_collective(pa2, nt, t0tile, t0tile + ntile, sh, par);
           if (tid == 0) sh.nrec = 0;
           __syncthreads();
@@ -1077,17 +1093,8 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
           const bool mine = pass == 0 ? fm != 0 : fs != 0;
           const V2Scan& sc = pass == 0 ? sm_ : ss_;
           if (mine) {  // dump this CTA's normalised weights (the stationary array still holds them)
-            if (pass == 1) {  // side: Pv holds waN' (W' = waN'/S4 was never stored unless the exact side scan ran)
-              const double S4 = v2_tiles_collective(pa2, nt, 0, -1, sh, par);
-              const InvDiv ivS4 = make_invdiv(S4);
-              const bool scanned = (__ldcg(&vd.cand[2 * chain]) == 0) || (vd.force_fallback != 0);
-              for (int i = tid; i < nch * V2_CHUNK; i += V2_NT) {
-                const double v = sc.v[i];
-                Wn[p0 + i] = scanned ? v : ((p0 + i < N) ? div_inv(v, ivS4) : 0.0);
-              }
-            } else {
-              for (int i = tid; i < nch * V2_CHUNK; i += V2_NT) Wn[p0 + i] = sc.v[i];
-            }
+            // (a side flag can only have been raised by the exact side scan above, which left W' = waN'/S4 in Pv)
+            for (int i = tid; i < nch * V2_CHUNK; i += V2_NT) Wn[p0 + i] = sc.v[i];
           }
           v2_grid_barrier(vd.bar, bar_target);
           if (mine && lead) {
