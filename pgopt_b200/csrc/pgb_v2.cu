@@ -59,9 +59,16 @@ static int launch_v2(pgb_handle* h, size_t smem) {
 
 template <int NX, int BASIS, int CA = 0>
 static int launch_v2_first(pgb_handle* h, size_t smem, int first) {
-  if (h->fd.f32)
-    return first ? launch_v2<NX, BASIS, true, CA, float>(h, smem) : launch_v2<NX, BASIS, false, CA, float>(h, smem);
-  return first ? launch_v2<NX, BASIS, true, CA, double>(h, smem) : launch_v2<NX, BASIS, false, CA, double>(h, smem);
+#ifdef PGB_V2_ONLY_MAIN  // experiment builds: compile the headline kernels only (known / 5x5x5 Hilbert basis)
+  if constexpr (BASIS == 2) {
+    return -1;
+  } else
+#endif
+  {
+    if (h->fd.f32)
+      return first ? launch_v2<NX, BASIS, true, CA, float>(h, smem) : launch_v2<NX, BASIS, false, CA, float>(h, smem);
+    return first ? launch_v2<NX, BASIS, true, CA, double>(h, smem) : launch_v2<NX, BASIS, false, CA, double>(h, smem);
+  }
 }
 
 int pgb_run_filter_v2(pgb_handle* h) {

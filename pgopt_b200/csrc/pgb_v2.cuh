@@ -784,6 +784,7 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
     // ================================================================ PB: w = e/S1, waN = w*pdf
     {
       const double S1 = v2_tiles_collective(pe, nt, 0, -1, sh, par);
+      V2_TICK(13);
       const InvDiv ivS1 = make_invdiv(S1);
       if (tid == 0) sh.nrec = 0;  // record pool of this step's scan-local (PC)
       if (lead && tid == 0) {
@@ -839,7 +840,9 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
                           : v2_tiles_collective(pw, nt, t0tile, t0tile + ntile, sh, par);
     {
       __syncthreads();  // sh.tp_lo / tp_hi (written by thread 0 after the collective's barrier)
+      V2_TICK(14);
       v2_scan_local(sm_, S2, sh);
+      V2_TICK(15);
       if (anc) {
         // Ancestor draw of slot N (:181) by the CERTIFIED shortcut, straight from the un-normalised waN: the reference
         // normalises twice (waN' = waN/S3 at :180, W' = waN'/S4 inside systematic_resampling :19) and walks q += W'[n];
@@ -959,6 +962,7 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
               }
             }
             __syncthreads();
+            V2_TICK(0);
             // (3) propagate: every thread takes output slots (:175 | :188, :194)
             const int cnt = pe_ - ps;
             int a_n = (tid < cnt) ? s_anc[tid] : 0;

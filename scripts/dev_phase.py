@@ -7,11 +7,12 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 from pgopt_b200._lib import lib, check
 model = sys.argv[1] if len(sys.argv) > 1 else "generic"
+dtype = sys.argv[4] if len(sys.argv) > 4 else "f64"
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 2 ** 20
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 import pgopt_b200 as pg
 prob = bench.build_problem(model, T, seed=0)
-eng = pg.ParticleGibbsEngine(prob["basis"], 1, N, T, n_chains=1)
+eng = pg.ParticleGibbsEngine(prob["basis"], 1, N, T, n_chains=1, precision=dtype)
 eng.set_data(prob["u"], prob["y"])
 eng.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
 eng.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
@@ -22,8 +23,8 @@ for _ in range(2):
 eng.synchronize()
 cyc = (C.c_double * 16)()
 check(lib().pgb_experiment_phase_cycles(eng._h, cyc), eng._h)
-names = {1: "PA", 2: "wait B1", 3: "PB", 4: "wait B2", 5: "PC", 6: "wait B3", 12: "PD resolve", 11: "PD prefixes+counts", 7: "PD scatter+emit", 8: "PD side", 9: "wait B0", 10: "rare"}
+names = {1: "PA", 2: "wait B1", 13: "PB collective", 3: "PB rest", 4: "wait B2", 14: "PC collective", 15: "PC scan-local", 5: "PC shortcut+rest", 6: "wait B3", 12: "PD resolve", 11: "PD prefixes+counts", 0: "PD scatter", 7: "PD emit+max", 8: "(PD end)", 9: "wait B0", 10: "rare"}
 tot = sum(cyc)
-for i in (1, 2, 3, 4, 5, 6, 12, 11, 7, 8, 9, 10):
+for i in (1, 2, 13, 3, 4, 14, 15, 5, 6, 12, 11, 0, 7, 8, 9, 10):
     print("%-22s %8.1f cyc/step  %5.1f %%" % (names[i], cyc[i] / (T - 1), 100 * cyc[i] / tot))
 print("total %.1f cycles/step = %.1f us at 1.965 GHz" % (tot / (T - 1), tot / (T - 1) / 1965.0))
