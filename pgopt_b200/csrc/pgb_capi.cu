@@ -466,7 +466,9 @@ static int run_filter(pgb_handle* h) {
 
 static int run_mniw(pgb_handle* h) {
   if (!h->have_prior) return set_err(h, PGB_ERR_STATE, "pgb_set_prior must be called before the MNIW draw");
-  LAUNCH(h, PGB_PROF_MNIW, (k_mniw<<<h->fd.nc, MNIW_TPB, 0, h->stream>>>(h->md)));
+  const size_t sm = mniw_smem_bytes(h->md.n_phi);
+  if (sm) CK(h, cudaFuncSetAttribute(k_mniw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  LAUNCH(h, PGB_PROF_MNIW, (k_mniw<<<h->fd.nc, MNIW_TPB, sm, h->stream>>>(h->md, sm ? 1 : 0)));
   CK(h, cudaGetLastError());
   h->sweep_index += 1;
   return PGB_OK;
@@ -725,7 +727,9 @@ extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const
   } else {
     md.philox = 1; md.seed = seed; md.chain_base = chain; md.sweep = sweep_index;
   }
-  k_mniw<<<1, MNIW_TPB>>>(md);
+  const size_t sm = mniw_smem_bytes(n_phi);
+  if (sm) CK(h, cudaFuncSetAttribute(k_mniw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_mniw<<<1, MNIW_TPB, sm>>>(md, sm ? 1 : 0);
   CK(h, cudaGetLastError());
   CK(h, cudaDeviceSynchronize());
   int st = 0;

@@ -10,7 +10,7 @@
 
 namespace pgb {
 
-constexpr int MNIW_TPB = 512;
+constexpr int MNIW_TPB = 1024;
 
 struct MniwDev {
   int nc, n_x, n_phi;
@@ -199,73 +199,100 @@ __device__ inline double mt_chi2_dev(uint64_t seed, uint32_t cid, uint32_t sweep
   }
 }
 
-// right-looking Cholesky of an n x n column-major matrix in global memory by one CTA
+// right-looking Cholesky of an n x n column-major matrix (global or shared memory) by one CTA.  Threads form a
+// 32 x (nth/32) grid: lane = row offset, warp = column offset — no integer division in the inner loops (the 64-bit
+// div / mod per element of the first version cost more than the arithmetic: 1.7 ms of a 2 ms kernel at n = 125).
 __device__ inline int cta_cholesky(double* A, int n, int* s_fail) {
   const int tid = threadIdx.x, nth = blockDim.x;
+  const int lx = tid & 31, wy = tid >> 5, nw = nth >> 5;
   for (int k = 0; k < n; ++k) {
     __syncthreads();
     if (tid == 0) {
-      double d = A[k + (int64_t)n * k];
+      double d = A[k + n * k];
       if (!(d > 0.0)) *s_fail = 1;
-      else A[k + (int64_t)n * k] = __dsqrt_rn(d);
+      else A[k + n * k] = __dsqrt_rn(d);
     }
     __syncthreads();
     if (*s_fail) return 1;
-    const double d = A[k + (int64_t)n * k];
-    for (int i = k + 1 + tid; i < n; i += nth) A[i + (int64_t)n * k] = __ddiv_rn(A[i + (int64_t)n * k], d);
+    const double d = A[k + n * k];
+    for (int i = k + 1 + tid; i < n; i += nth) A[i + n * k] = __ddiv_rn(A[i + n * k], d);
     __syncthreads();
-    const int m = n - k - 1;  // trailing size
-    for (int64_t e = tid; e < (int64_t)m * m; e += nth) {
-      int i = k + 1 + (int)(e % m), j = k + 1 + (int)(e / m);
-      if (i >= j) A[i + (int64_t)n * j] = __fma_rn(-A[i + (int64_t)n * k], A[j + (int64_t)n * k], A[i + (int64_t)n * j]);
+    for (int j = k + 1 + wy; j < n; j += nw) {  // trailing update, lower triangle: every entry gets its updates in pivot order
+      const double ljk = A[j + n * k];
+#pragma unroll 4
+      for (int i = j + lx; i < n; i += 32) A[i + n * j] = __fma_rn(-A[i + n * k], ljk, A[i + n * j]);
     }
   }
   __syncthreads();
-  for (int64_t e = tid; e < (int64_t)n * n; e += nth) {
-    int i = (int)(e % n), j = (int)(e / n);
-    if (i < j) A[e] = 0.0;
-  }
+  for (int j = 1 + wy; j < n; j += nw)
+    for (int i = lx; i < j; i += 32) A[i + n * j] = 0.0;
   __syncthreads();
   return 0;
 }
+// Index of L[i, j] (i >= j): full column-major n x n, or the lower triangle packed column by column (shared-memory path:
+// the n x n right-hand side block and the packed factor together fit 227 KB up to n = 135)
+struct LIdxFull {
+  int n;
+  __device__ __forceinline__ int64_t operator()(int i, int j) const { return i + (int64_t)n * j; }
+};
+struct LIdxPacked {
+  int n;
+  __device__ __forceinline__ int64_t operator()(int i, int j) const { return (int64_t)j * n - ((int64_t)j * (j - 1)) / 2 + (i - j); }
+};
 // Solve (L L') X = B for nrhs right-hand sides stored as columns of B (ld = n), in place.
 // Column sweeps keep every entry's update order identical to the oracle's substitutions.
-__device__ inline void cta_chol_solve(const double* L, int n, double* B, int nrhs) {
+template <class IDX>
+__device__ inline void cta_chol_solve(const double* L, IDX ix, int n, double* B, int nrhs) {
   const int tid = threadIdx.x, nth = blockDim.x;
+  const int lx = tid & 31, wy = tid >> 5, nw = nth >> 5;
   for (int e = 0; e < n; ++e) {  // forward: L y = b
     __syncthreads();
-    const double piv = L[e + (int64_t)n * e];
-    for (int r = tid; r < nrhs; r += nth) B[e + (int64_t)n * r] = __ddiv_rn(B[e + (int64_t)n * r], piv);
+    const double piv = L[ix(e, e)];
+    for (int r = tid; r < nrhs; r += nth) B[e + n * r] = __ddiv_rn(B[e + n * r], piv);
     __syncthreads();
-    const int m = n - e - 1;
-    for (int64_t w = tid; w < (int64_t)m * nrhs; w += nth) {
-      int d = e + 1 + (int)(w % m), r = (int)(w / m);
-      B[d + (int64_t)n * r] = __fma_rn(-L[d + (int64_t)n * e], B[e + (int64_t)n * r], B[d + (int64_t)n * r]);
+    for (int r = wy; r < nrhs; r += nw) {
+      const double ber = B[e + n * r];
+#pragma unroll 4
+      for (int d = e + 1 + lx; d < n; d += 32) B[d + n * r] = __fma_rn(-L[ix(d, e)], ber, B[d + n * r]);
     }
   }
   for (int e = n - 1; e >= 0; --e) {  // backward: L' x = y
     __syncthreads();
-    const double piv = L[e + (int64_t)n * e];
-    for (int r = tid; r < nrhs; r += nth) B[e + (int64_t)n * r] = __ddiv_rn(B[e + (int64_t)n * r], piv);
+    const double piv = L[ix(e, e)];
+    for (int r = tid; r < nrhs; r += nth) B[e + n * r] = __ddiv_rn(B[e + n * r], piv);
     __syncthreads();
-    for (int64_t w = tid; w < (int64_t)e * nrhs; w += nth) {
-      int d = (int)(w % e), r = (int)(w / e);
-      B[d + (int64_t)n * r] = __fma_rn(-L[e + (int64_t)n * d], B[e + (int64_t)n * r], B[d + (int64_t)n * r]);
+    for (int r = wy; r < nrhs; r += nw) {
+      const double ber = B[e + n * r];
+#pragma unroll 4
+      for (int d = lx; d < e; d += 32) B[d + n * r] = __fma_rn(-L[ix(e, d)], ber, B[d + n * r]);
     }
   }
   __syncthreads();
 }
 
+// bytes of dynamic shared memory the on-chip path of k_mniw needs (0: does not fit, the global-memory path runs)
+__host__ __device__ inline size_t mniw_smem_bytes(int np) {
+  const size_t b = ((size_t)np * np + (size_t)np * (np + 1) / 2) * 8;
+  return b <= (size_t)220 * 1024 ? b : 0;
+}
+
 // MNIW_sample + refresh of the chain parameters used by the next sweep.  One CTA per chain.
-static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md) {
+// n_phi <= 135 (both reference examples: 5 and 125): the n_phi x n_phi work matrix (Sigbar -> its factor -> the identity ->
+// left_cov -> its factor) and the packed factor of Sigbar live in SHARED memory for the whole kernel — the two
+// factorisations and the n_phi-right-hand-side solve are ~1 500 CTA barriers with a dependent memory round trip between
+// each pair, which cost 2 ms against global memory and ~0.2 ms on chip.  Same operations in the same
+// order on every entry, hence the same bits; larger bases take the global-memory path.
+static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md, int use_smem) {
+  extern __shared__ double mn_sm[];
   __shared__ int s_fail;
   __shared__ double s_small[8][16];  // covM, Lc, S, B, LB, Wm, Qn, Lq
   const int chain = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   const int nx = md.n_x, np = md.n_phi;
   const int64_t pp = (int64_t)np * np;
-  double* Ls = md.Ls + chain * pp;
-  double* Sinv = md.Sinv + chain * pp;
-  double* Lv = md.Lv + chain * pp;
+  double* Ls = use_smem ? mn_sm : md.Ls + chain * pp;       // on chip the three stages reuse one n_phi x n_phi block
+  double* Sinv = use_smem ? mn_sm : md.Sinv + chain * pp;
+  double* Lv = use_smem ? mn_sm : md.Lv + chain * pp;
+  double* Lp = mn_sm + pp;                                   // packed factor of Sigbar (on-chip path)
   double* Mp = md.Mpost + (int64_t)chain * nx * np;
   double* Xn = md.Xn + (int64_t)chain * nx * np;
   double* LX = md.LX + (int64_t)chain * nx * np;
@@ -293,7 +320,16 @@ static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md) {
     int i = (int)(e % np), d = (int)(e / np);
     LX[e] = Psi[d + nx * i];
   }
-  cta_chol_solve(Ls, np, LX, nx);
+  if (use_smem) {  // keep the factor, packed, before the block is reused for the inverse
+    for (int64_t e = tid; e < pp; e += nth) {
+      int i = (int)(e % np), j = (int)(e / np);
+      if (i >= j) Lp[LIdxPacked{np}(i, j)] = Ls[e];
+    }
+    __syncthreads();
+    cta_chol_solve(Lp, LIdxPacked{np}, np, LX, nx);
+  } else {
+    cta_chol_solve(Ls, LIdxFull{np}, np, LX, nx);
+  }
   for (int64_t e = tid; e < (int64_t)np * nx; e += nth) {
     int i = (int)(e % np), d = (int)(e / np);
     Mp[d + nx * i] = LX[e];
@@ -312,18 +348,22 @@ static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md) {
     s_small[1][a + nx * b] = __dmul_rn(0.5, __dadd_rn(s_small[0][a + nx * b], s_small[0][b + nx * a]));
   }
   // left_cov = I / Sigbar (:68): inverse via np right-hand sides, lower triangle mirrored
+  __syncthreads();
   for (int64_t e = tid; e < pp; e += nth) Sinv[e] = ((e % np) == (e / np)) ? 1.0 : 0.0;
-  cta_chol_solve(Ls, np, Sinv, np);
+  if (use_smem) cta_chol_solve(Lp, LIdxPacked{np}, np, Sinv, np);
+  else cta_chol_solve(Ls, LIdxFull{np}, np, Sinv, np);
   for (int64_t e = tid; e < pp; e += nth) {
     int i = (int)(e % np), j = (int)(e / np);
     if (i < j) Sinv[e] = Sinv[j + (int64_t)np * i];
   }
   __syncthreads();
   // symmetrise (:69) and factor: chol(left_cov_sym)
-  for (int64_t e = tid; e < pp; e += nth) {
-    int i = (int)(e % np), j = (int)(e / np);
-    Lv[e] = __dmul_rn(0.5, __dadd_rn(Sinv[i + (int64_t)np * j], Sinv[j + (int64_t)np * i]));
-  }
+  if (!use_smem) {
+    for (int64_t e = tid; e < pp; e += nth) {
+      int i = (int)(e % np), j = (int)(e / np);
+      Lv[e] = __dmul_rn(0.5, __dadd_rn(Sinv[i + (int64_t)np * j], Sinv[j + (int64_t)np * i]));
+    }
+  }  // on chip Lv aliases Sinv, which the mirroring above made exactly symmetric: 0.5 * (a + a) == a
   if (cta_cholesky(Lv, np, &s_fail)) {
     if (tid == 0) atomicOr(&md.status[chain], 16);
     return;

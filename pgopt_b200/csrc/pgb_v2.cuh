@@ -592,6 +592,7 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
 #else
 #define V2_TICK(idx) do { } while (0)
 #endif
+  // tile sums (replicating them over several L2 slices for the 148 simultaneous readers was tried: no change)
   double* pe = vd.pe + (int64_t)chain * nt;
   double* pw = vd.pw + (int64_t)chain * nt;
   double* pa = vd.pa + (int64_t)chain * nt;
@@ -1019,15 +1020,28 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
     V2_TICK(9);
     // ================================================================ rare, grid-uniform sections
     {
+      // Every word this section reads is requested up front (one L2 round trip instead of four or five dependent ones:
+      // the grid-uniform conditions, this chain's candidate, the lead thread's pending status bits).
+      const int tpar = (int)(t & 1);
+      int amb = 0, anyf0 = 0;
+      for (int ch = lane; ch < fd.nc; ch += 32) {
+        const int cz = anc ? __ldcg(&vd.cand[2 * ch]) : 1;
+        const int f1 = __ldcg(&fd.main.flag[ch + fd.nc * tpar]), f2 = __ldcg(&fd.side.flag[ch + fd.nc * tpar]);
+        amb |= (cz == 0) ? 1 : 0;
+        anyf0 |= (f1 | f2) & 1;
+      }
+      const int my_cnt = anc ? __ldcg(&vd.cand[2 * chain]) : 1;
+      const int my_idx = (anc && lead && tid == 0) ? __ldcg(&vd.cand[2 * chain + 1]) : 0;
+      int pend0 = 0;
+      if (lead && tid == 0) pend0 = __ldcg(&fd.main.pend[chain]) | __ldcg(&fd.side.pend[chain]);
+      bool rare_ran = false;  // a rare path ran: flags / pending bits may have changed since the prefetch
       // (a) ancestor draw undecided by the shortcut (about 1e-3 of the steps), or forced: exact scan of waN'
       if (anc) {
-        // every warp evaluates the (grid-uniform) condition itself: no CTA barrier on the common path
-        int amb = 0;
-        for (int ch = lane; ch < fd.nc; ch += 32) amb |= (__ldcg(&vd.cand[2 * ch]) == 0) ? 1 : 0;
         const bool amb_any = __any_sync(0xffffffffu, amb) || (vd.force_fallback != 0);
-        const bool amb_me = (__ldcg(&vd.cand[2 * chain]) == 0) || (vd.force_fallback != 0);
+        const bool amb_me = (my_cnt == 0) || (vd.force_fallback != 0);
         int32_t* aout = fd.ah + ((int64_t)chain * T + t) * N + (N - 1);
-        if (!amb_me && lead && tid == 0) *aout = __ldcg(&vd.cand[2 * chain + 1]);
+        if (!amb_me && lead && tid == 0) *aout = my_idx;
+        rare_ran = amb_any;
         if (amb_any) {
           // waN' = waN / S3 (:180) with its chunk / tile sums and chunk prefixes: only this exact scan needs them
           if (amb_me) {
@@ -1086,10 +1100,14 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
         }
       }
       // (b) a failed seam check / record overflow / forced fallback: serial exact walk, consumers redone
-      int anyf = 0;
-      for (int ch = lane; ch < fd.nc; ch += 32)
-        anyf |= (__ldcg(&fd.main.flag[ch + fd.nc * (int)(t & 1)]) | __ldcg(&fd.side.flag[ch + fd.nc * (int)(t & 1)])) & 1;
+      int anyf = anyf0;
+      if (rare_ran) {  // the exact side scan may have raised a flag since
+        anyf = 0;
+        for (int ch = lane; ch < fd.nc; ch += 32)
+          anyf |= (__ldcg(&fd.main.flag[ch + fd.nc * tpar]) | __ldcg(&fd.side.flag[ch + fd.nc * tpar])) & 1;
+      }
       if (__any_sync(0xffffffffu, anyf)) {
+        rare_ran = true;
         const int fm = __ldcg(fmain) & 1, fs = anc ? (__ldcg(fside) & 1) : 0;
         double* Wn = vd.Wn + (int64_t)chain * NP;
         double* qfb = vd.qin_fb + (int64_t)chain * nt * TPB;
@@ -1188,10 +1206,12 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
       }
       // merge the status bits raised by consumer passes that were not redone; re-arm the other parity's flags
       if (lead && tid == 0) {
-        const int p = fd.main.pend[chain] | fd.side.pend[chain];
+        const int p = rare_ran ? (__ldcg(&fd.main.pend[chain]) | __ldcg(&fd.side.pend[chain])) : pend0;
         if (p) atomicOr(&fd.status[chain], p);
-        fd.main.pend[chain] = 0;
-        fd.side.pend[chain] = 0;
+        if (p || rare_ran) {
+          fd.main.pend[chain] = 0;
+          fd.side.pend[chain] = 0;
+        }
         fd.main.flag[chain + fd.nc * (int)((t + 1) & 1)] = 0;
         fd.side.flag[chain + fd.nc * (int)((t + 1) & 1)] = 0;
       }

@@ -70,6 +70,35 @@ def test_no_cpu_fallback():
     assert ei.value.code == _lib.PGB_ERR_CUDA
 
 
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_new_entry_points():
+    """the device-resident, multi-GPU and supplied-scenario entry points also refuse to compute without a device, and
+    validate what they can on the host"""
+    basis = pgopt_b200.KnownBasisVB()
+    with pytest.raises(pgopt_b200.PgoptError) as ei:
+        pgopt_b200.DeviceSamples(basis, 1, 30, 4)
+    assert ei.value.code == _lib.PGB_ERR_CUDA and "no CPU fallback" in str(ei.value)
+    with pytest.raises(pgopt_b200.PgoptError) as ei:
+        pgopt_b200.MultiGPUEngine(basis, 1, 30, 100, 2, [0])
+    assert ei.value.code == _lib.PGB_ERR_CUDA
+    with pytest.raises(pgopt_b200.PgoptError) as ei:  # n_chains is the TOTAL and must cover the devices
+        pgopt_b200.MultiGPUEngine(basis, 1, 30, 100, 1, [0, 1])
+    assert ei.value.code == _lib.PGB_ERR_INVALID
+    rng = np.random.default_rng(0)
+    smp = [pgopt_b200.PG_sample(rng.normal(size=(2, 5)), np.eye(2), np.ones(3) / 3, rng.normal(size=(2, 3)), np.zeros(1))]
+    with pytest.raises(pgopt_b200.PgoptError) as ei:
+        pgopt_b200.scenario_rollout(smp, basis, pgopt_b200.LinearMeasurement([[1.0, 0.0]]), 0.1, 4, x_vec_0=np.zeros(2))
+    assert ei.value.code == _lib.PGB_ERR_CUDA
+    cfg = _lib.PgbConfig()
+    cfg.device, cfg.n_x, cfg.n_u, cfg.n_y, cfg.n_phi, cfg.basis = 0, 2, 1, 1, 5, _lib.BASIS_KNOWN_VB
+    cfg.N, cfg.T, cfg.n_chains, cfg.precision = 30, 100, 1, 7
+    h = C.c_void_p()
+    assert _lib.lib().pgb_create(C.byref(h), C.byref(cfg)) == _lib.PGB_ERR_INVALID
+    assert b"precision" in _lib.lib().pgb_last_error(None)
+    assert _lib.lib().pgb_packed_record_doubles(C.c_int32(2), C.c_int32(125), C.c_int32(1)) == 2 * 125 + 4 + 2 + 1
+    assert _lib.lib().pgb_samples_pack_bytes(None, C.c_int32(1)) == 0 and _lib.lib().pgb_checkpoint_bytes(None) == 0
+
+
 def test_sample_batch_packs_like_the_sample_list():
     """PGSampleBatch (stacked arrays) must hand the C ABI exactly the bytes the Vector{PG_sample} mirror does."""
     from pgopt_b200.api import _pack_samples

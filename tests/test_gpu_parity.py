@@ -463,6 +463,25 @@ def test_mniw_bit_exact(model):
     _assert_same("A philox", Ag, Ar)
 
 
+@pytest.mark.parametrize("n_x,n_phi", [(2, 135), (2, 136), (3, 200), (4, 625)])
+def test_mniw_bit_exact_sizes(n_x, n_phi):
+    """MNIW_sample at the edge of the shared-memory path (n_phi <= 135), just beyond it, and at the configs[4] basis size
+    (n_phi = 5^4 = 625: global-memory path) — bit-identical to the oracle either way."""
+    rng = np.random.default_rng(100 + n_phi)
+    Tm1 = n_phi + 50
+    zeta, z = rng.normal(size=(n_x, Tm1)), rng.normal(size=(n_phi, Tm1))
+    Phi, Psi, Sig = zeta @ zeta.T, zeta @ z.T, z @ z.T
+    Sig = 0.5 * (Sig + Sig.T)
+    V = rng.uniform(0.5, 20.0, n_phi)
+    Lam, ell = 100 * np.eye(n_x), 10.0
+    stp = O.make_streams(philox=True, seed=5, chain=2)
+    Ar, Qr, rc = O.mniw_sample(n_x, n_phi, Phi, Psi, Sig, V, Lam, ell, Tm1, stp, 3)
+    assert rc == 0
+    Ag, Qg = pg.MNIW_sample(Phi, Psi, Sig, V, Lam, ell, Tm1, seed=5, chain=2, sweep_index=3)
+    _assert_same("Q", Qg, Qr)
+    _assert_same("A", Ag, Ar)
+
+
 @pytest.mark.parametrize("model,N,T,K,K_b,k_d", [("known", 30, 150, 4, 6, 2), ("hilbert", 30, 60, 3, 3, 1),
                                                  ("known", 2500, 30, 3, 2, 1), ("hilbert", 300, 25, 2, 2, 1),
                                                  ("known", 1024, 20, 2, 1, 1)])
