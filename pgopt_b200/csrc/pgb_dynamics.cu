@@ -8,8 +8,8 @@
 // Kernel: one warp per scenario, persistent grid.  The products A_k * (.) use the order the rollout defines (128 runs of
 // c = ceil(n_phi/128) consecutive columns, fma in increasing i, balanced tree over the runs; oracle: blocked_dot), lane l
 // owning runs 4l .. 4l+3, so x_next equals the rollout's X[t+1] bit for bit.  The 1 + n_z contractions (phi and its n_z
-// partial derivatives) are separate passes over the lane's columns: A_k comes from HBM once (20 KB per scenario at
-// n_phi = 625) and from L1 afterwards.  HBM-bound: 8 (n_x n_phi + 2 n_x + n_x n_z) bytes per scenario.
+// partial derivatives) are accumulated in ONE pass over the lane's columns: A_k comes from HBM once (20 KB per scenario at
+// n_phi = 625).  HBM traffic: 8 (n_x n_phi + 2 n_x + n_x n_z) bytes per scenario.
 #include "pgb_internal.h"
 
 using namespace pgb;
@@ -28,6 +28,7 @@ struct DynDev {
 
 constexpr int DY_WPB = 4;
 constexpr int DY_MAXC = 8;  // columns per run up to which the digit decode is hoisted (n_phi <= 1024)
+constexpr int DY_MAXQ = 1 + PGB_MAX_Z_;  // phi and its partial derivatives
 
 template <int NX>
 __global__ void __launch_bounds__(DY_WPB * 32) k_dynamics(const __grid_constant__ FilterDev fd, const __grid_constant__ DynDev dd) {
@@ -131,57 +132,70 @@ __global__ void __launch_bounds__(DY_WPB * 32) k_dynamics(const __grid_constant_
       }
     }
     __syncwarp();
-    const int npass = 1 + ((dd.ju ? nu : 0) > 0 || dd.jx ? nz : 0);
-    for (int q = 0; q < npass; ++q) {  // q = 0: phi; q >= 1: d phi / d z_{q-1}
-      const int mm = q - 1;
-      if (q >= 1 && ((mm < nu && !dd.ju) || (mm >= nu && !dd.jx))) continue;  // warp-uniform
-      double part[4][NX];
+    // ONE pass over the lane's columns: A_k is read once (from HBM) and feeds phi and all n_z partial derivatives — the
+    // first version made 1 + n_z passes and re-read A_k through L2 each time (L1 cannot hold 32 warps x 20 KB): 5 % of the
+    // HBM roofline.  q = 0: phi; q >= 1: d phi / d z_{q-1}; every product left to right with the differentiated factor
+    // in its place (the oracle's order).
+    const bool want_j = (dd.ju != nullptr) || (dd.jx != nullptr);
+    const int nq = want_j ? 1 + nz : 1;
+    double part[4][DY_MAXQ * NX];
 #pragma unroll 1
-      for (int r = 0; r < 4; ++r) {
-        double acc[NX];
+    for (int r = 0; r < 4; ++r) {
+      double acc[DY_MAXQ][NX];
 #pragma unroll
-        for (int d = 0; d < NX; ++d) acc[d] = 0.0;
-        const int i0 = (4 * lane + r) * c;
+      for (int q = 0; q < DY_MAXQ; ++q)
+#pragma unroll
+        for (int d = 0; d < NX; ++d) acc[q][d] = 0.0;
+      const int i0 = (4 * lane + r) * c;
+#pragma unroll 1
+      for (int m = 0; m < c; ++m) {
+        const int i = i0 + m;
+        if (i >= n_phi) break;
+        unsigned pk;
         if (packed_ok) {
-#pragma unroll 1
-          for (int m = 0; m < c; ++m) {
-            const int i = i0 + m;
-            if (i < n_phi) {
-              const unsigned pk = dgs[warp][r * DY_MAXC + m][lane];
-              double p = 1.0;
-#pragma unroll
-              for (int kk = 0; kk < PGB_MAX_Z_; ++kk)
-                if (kk < nz) p = __dmul_rn(p, (kk == mm ? dk : tk)[kk * MAXC + ((pk >> (4 * kk)) & 15u)]);
-#pragma unroll
-              for (int d = 0; d < NX; ++d) acc[d] = __fma_rn(__ldg(Ak + (int64_t)NX * i + d), p, acc[d]);
-            }
-          }
+          pk = dgs[warp][r * DY_MAXC + m][lane];
         } else {
-          for (int m = 0; m < c; ++m) {
-            const int i = i0 + m;
-            if (i >= n_phi) break;
-            int rem = i;
-            int dg[PGB_MAX_Z_];
+          pk = 0;
+          int rem = i;
+          for (int kk = nz - 1; kk >= 0; --kk) {
+            pk |= (unsigned)(rem % fd.hg_count[kk]) << (4 * kk);
+            rem /= fd.hg_count[kk];
+          }
+        }
+        double a[NX];
 #pragma unroll
-            for (int kk = PGB_MAX_Z_ - 1; kk >= 0; --kk)
-              if (kk < nz) {
-                dg[kk] = rem % fd.hg_count[kk];
-                rem /= fd.hg_count[kk];
-              }
+        for (int d = 0; d < NX; ++d) a[d] = __ldg(Ak + (int64_t)NX * i + d);
+        double tv[PGB_MAX_Z_], dv[PGB_MAX_Z_];
+#pragma unroll
+        for (int kk = 0; kk < PGB_MAX_Z_; ++kk)
+          if (kk < nz) {
+            const int o = kk * MAXC + ((pk >> (4 * kk)) & 15u);
+            tv[kk] = tk[o];
+            dv[kk] = want_j ? dk[o] : 0.0;
+          }
+#pragma unroll
+        for (int q = 0; q < DY_MAXQ; ++q)
+          if (q < nq) {
             double p = 1.0;
 #pragma unroll
             for (int kk = 0; kk < PGB_MAX_Z_; ++kk)
-              if (kk < nz) p = __dmul_rn(p, (kk == mm ? dk : tk)[kk * MAXC + dg[kk]]);
+              if (kk < nz) p = __dmul_rn(p, (kk == q - 1) ? dv[kk] : tv[kk]);
 #pragma unroll
-            for (int d = 0; d < NX; ++d) acc[d] = __fma_rn(__ldg(Ak + (int64_t)NX * i + d), p, acc[d]);
+            for (int d = 0; d < NX; ++d) acc[q][d] = __fma_rn(a[d], p, acc[q][d]);
           }
-        }
-#pragma unroll
-        for (int d = 0; d < NX; ++d) part[r][d] = acc[d];
       }
 #pragma unroll
+      for (int q = 0; q < DY_MAXQ; ++q)
+#pragma unroll
+        for (int d = 0; d < NX; ++d) part[r][q * NX + d] = acc[q][d];
+    }
+#pragma unroll 1
+    for (int q = 0; q < nq; ++q) {
+      const int mm = q - 1;
+      if (q >= 1 && ((mm < nu && !dd.ju) || (mm >= nu && !dd.jx))) continue;  // warp-uniform
+#pragma unroll
       for (int d = 0; d < NX; ++d) {
-        double s = __dadd_rn(__dadd_rn(part[0][d], part[1][d]), __dadd_rn(part[2][d], part[3][d]));
+        double s = __dadd_rn(__dadd_rn(part[0][q * NX + d], part[1][q * NX + d]), __dadd_rn(part[2][q * NX + d], part[3][q * NX + d]));
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
         out[d] = s;
