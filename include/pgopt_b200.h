@@ -314,7 +314,7 @@ int pgb_multi_last_ms(pgb_multi* m, double* sample_gather_ms, double* rollout_ke
 /* ---- sample serialisation and checkpoint / resume ----------------------------------
  * The reference keeps PG_sample only in memory (PGopt.jl:23-29) and warm-starts through the x_prim keyword
  * (particle_Gibbs.jl:114,126-128).  Packed layout, little-endian, version 1:
- *   64-byte header {char magic[8] = "PGB200S\0"; u32 version; u32 flags (bit 0: particles follow); i32 n_x, n_u, n_phi,
+ *   64-byte header {char magic[8] = "PGB200S\0"; u32 version; u32 flags (bit 0: particles follow, bit 1: x_T valid); i32 n_x, n_u, n_phi,
  *   n_y; i64 N; i64 K; u64 reserved[2]} | K records [A | Q | x_T | u_m1] (pgb_packed_record_doubles) | if flags&1:
  *   K x [w_m1 N | x_m1 n_x*N column-major].  x_T is filled by pgb_samples_draw_xT (zeros before). */
 int64_t pgb_samples_pack_bytes(const pgb_samples* s, int32_t with_particles);

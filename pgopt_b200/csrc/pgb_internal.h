@@ -70,6 +70,7 @@ struct pgb_samples {
   double *A = nullptr, *Q = nullptr, *w = nullptr, *x = nullptr, *um = nullptr;  // [K][...] layouts of pgb_rollout
   double* xT = nullptr; // [K][n_x] x_m1[:, star] (pgb_samples_draw_xT) or null
   bool have_xT = false;
+  bool have_particles = false;  // w_m1 / x_m1 hold data (set, store or unpack with particle blocks): the star can be drawn
   // scenario buffers of the last rollout (allocated for horizon H_cap on first use)
   int64_t H = 0, H_cap = 0;
   double *x0 = nullptr, *v = nullptr, *e = nullptr, *X = nullptr, *Y = nullptr, *ui = nullptr, *hmax = nullptr;

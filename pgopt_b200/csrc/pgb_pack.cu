@@ -44,7 +44,7 @@ extern "C" int pgb_samples_pack(pgb_samples* s, int32_t with_particles, void* bu
   memset(&hd, 0, sizeof(hd));
   memcpy(hd.magic, MAGIC_S, 8);
   hd.version = 1;
-  hd.flags = with_particles ? 1u : 0u;
+  hd.flags = (with_particles ? 1u : 0u) | (s->have_xT ? 2u : 0u);  // bit 0: particle blocks follow, bit 1: x_T is valid
   hd.n_x = c.n_x; hd.n_u = c.n_u; hd.n_phi = c.n_phi; hd.n_y = c.n_y; hd.N = c.N; hd.K = s->K_active;
   memcpy(buf, &hd, sizeof(hd));
   double* out = reinterpret_cast<double*>(static_cast<char*>(buf) + sizeof(hd));
@@ -104,8 +104,10 @@ extern "C" int pgb_samples_unpack(pgb_samples* s, const void* buf, int64_t buf_b
   }
   CK(h, cudaStreamSynchronize(st));
   s->K_active = K;
-  // records without particle blocks can only be rolled out through their x_T (the star draw needs w_m1 / x_m1)
-  s->have_xT = !parts;
+  // records without particle blocks can only be rolled out through their x_T (the star draw needs w_m1 / x_m1); with
+  // particle blocks the star is re-drawn (same stream, same value) so that a stale x_T can never be used
+  s->have_particles = parts;
+  s->have_xT = !parts && (hd.flags & 2u) != 0;
   s->have_scen = false;
   return PGB_OK;
 }

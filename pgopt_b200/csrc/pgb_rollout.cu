@@ -414,6 +414,7 @@ extern "C" int pgb_samples_set(pgb_samples* s, int64_t k0, int64_t n, const doub
   if (u_m1) CK(h, cudaMemcpyAsync(s->um + (size_t)k0 * nu, u_m1, (size_t)n * nu * 8, cudaMemcpyHostToDevice, st));
   CK(h, cudaStreamSynchronize(st));
   if (w_m1 || x_m1) s->have_xT = false;
+  if (w_m1 && x_m1) s->have_particles = true;
   return PGB_OK;
 }
 
@@ -464,6 +465,7 @@ int pgb_samples_store_async(pgb_samples* s, int64_t k, pgb_handle* h, int chain)
     k_soa_to_aos<double><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(h->fd.xh + xoff, s->x + (size_t)k * nx * N, N, nx);
   CK(h, cudaGetLastError());
   s->have_xT = false;
+  s->have_particles = true;
   return PGB_OK;
 }
 
@@ -483,6 +485,7 @@ extern "C" int pgb_samples_draw_xT(pgb_samples* s, uint64_t seed, uint32_t k_off
   NEEDS(s);
   const int64_t K = s->K_active;
   if ((uint64_t)k_offset + (uint64_t)K > (1ull << 24)) return set_err(h, PGB_ERR_INVALID, "k_offset + K exceeds the 2^24 Philox stream ids");
+  if (!s->have_particles) return set_err(h, PGB_ERR_STATE, "the set holds no w_m1 / x_m1 to draw the star from");
   CK(h, cudaMemsetAsync(s->status, 0, 4, h->stream));
   k_draw_xT<<<(unsigned)((K + 3) / 4), 128, 0, h->stream>>>(K, h->cfg.N, h->cfg.n_x, s->w, s->x, seed, k_offset, s->xT, s->status);
   CK(h, cudaGetLastError());
@@ -522,6 +525,8 @@ extern "C" int pgb_rollout_dev(pgb_samples* s, int64_t H, const double* C, const
   if (!C || !Le || !u_init || H < 1) return set_err(h, PGB_ERR_INVALID, "bad arguments");
   if ((uint64_t)k_offset + (uint64_t)s->K_active > (1ull << 24)) return set_err(h, PGB_ERR_INVALID, "k_offset + K exceeds the 2^24 Philox stream ids");
   if (reuse && (!s->have_scen || H != s->H)) return set_err(h, PGB_ERR_STATE, "reuse needs a previous rollout of this set with the same horizon");
+  if (!x0_in && !(reuse & 1) && !s->have_xT && !s->have_particles)
+    return set_err(h, PGB_ERR_STATE, "the set holds neither particles (w_m1, x_m1) nor x_T: x_vec_0 cannot be drawn; supply x0_in");
   int rc = samples_scen_alloc(s, H);
   if (rc) return rc;
   const int nx = h->cfg.n_x, ny = h->cfg.n_y, nu = h->cfg.n_u;

@@ -225,6 +225,17 @@ def test_samples_pack_unpack_round_trip():
             d3.unpack(bad)
         with pytest.raises(pg.PgoptError):
             d3.unpack(slim[:100])
+    # records packed BEFORE x_T was drawn and without particle blocks cannot be rolled out: refused, not silently zero
+    with pg.DeviceSamples.from_samples(batch, p["basis"]) as d4:
+        bare = d4.pack(with_particles=False)
+    with pg.DeviceSamples(p["basis"], 1, 50, 9) as d5:
+        d5.unpack(bare)
+        with pytest.raises(pg.PgoptError):
+            d5.rollout(g, 0.1, p["H"], u_init=p["u_init"], seed=3)
+        with pytest.raises(pg.PgoptError):
+            d5.draw_xT(seed=3)
+        x0 = np.zeros(9 * 2)
+        d5.rollout(g, 0.1, p["H"], u_init=p["u_init"], seed=3, x_vec_0=x0)  # a supplied x_vec_0 needs neither
 
 
 def test_checkpoint_resume_is_bit_identical():
