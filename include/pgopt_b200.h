@@ -341,6 +341,9 @@ int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_
 int pgb_test_fp64_peak(int32_t device, double* tflops);
 /* rollout kernel choice for the tests: -1 automatic (default), 0 CTA per scenario, 1 warp per scenario */
 void pgb_test_rollout_kernel(int32_t which);
+/* dynamics kernel choice for the tests: -1 automatic (default), 0 k_dynamics (strided loads, every shape), 1 / 2
+ * k_dynamics_bulk with 4 / 5 warps per CTA (cp.async.bulk staging; Hilbert basis, even n_x, n_z = 3 | 5, else k_dynamics) */
+void pgb_test_dynamics_kernel(int32_t which);
 
 #ifdef __cplusplus
 }

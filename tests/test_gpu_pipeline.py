@@ -282,17 +282,37 @@ def test_checkpoint_resume_is_bit_identical():
 # ------------------------------------------------------------------------------------------------------------------
 # stacked-scenario dynamics + Jacobians (optimal_control_Altro.jl:79-107, @autodiff :51)
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("model,variant", [("known", 0), ("hilbert4", 0), ("hilbert4", 1), ("hilbert2", 0)])
-def test_stacked_dynamics_and_jacobians(model, variant):
+@pytest.fixture(params=["auto", "strided", "bulk4", "bulk2"])
+def dynamics_kernel(request):
+    """k_dynamics (strided loads) and k_dynamics_bulk (cp.async.bulk staging; as many warps per CTA as shared memory holds
+    rows of A, or capped at 4 / 2) on the same shapes"""
+    _lib.lib().pgb_test_dynamics_kernel({"auto": -1, "strided": 0, "bulk4": 1, "bulk2": 2}[request.param])
+    yield request.param
+    _lib.lib().pgb_test_dynamics_kernel(-1)
+
+
+@pytest.mark.parametrize("model,variant", [("known", 0), ("hilbert4", 0), ("hilbert4", 1), ("hilbert2", 0),
+                                           ("hilbert4_ragged", 0), ("hilbert2_5", 1), ("hilbert4_tail1", 1)])
+def test_stacked_dynamics_and_jacobians(model, variant, dynamics_kernel):
     rng = np.random.default_rng(91)
     if model == "known":
         basis, om, n_x = pg.KnownBasisVB(), O.known_model(), 2
     elif model == "hilbert4":
         basis = pg.HilbertGPBasis([1, 5, 5, 5, 5], [4.0, 5.0, 6.0, 7.0, 8.0])
         om, n_x = O.hilbert_model(4, 1, basis.count, basis.stride, basis.L), 4
+    elif model == "hilbert4_ragged":  # n_phi = 360: c = 3, the last lanes' chunks are partial / empty
+        basis = pg.HilbertGPBasis([2, 3, 5, 4, 3], [4.0, 5.0, 6.0, 7.0, 8.0])
+        om, n_x = O.hilbert_model(4, 1, basis.count, basis.stride, basis.L), 4
+    elif model == "hilbert4_tail1":   # n_phi = 625 with five functions in the fastest dimension (runs = its rows)
+        basis = pg.HilbertGPBasis([5, 5, 5, 5, 1], [4.0, 5.0, 6.0, 7.0, 8.0])
+        om, n_x = O.hilbert_model(4, 1, basis.count, basis.stride, basis.L), 4
+    elif model == "hilbert2_5":      # n_x = 2 with three inputs
+        basis = pg.HilbertGPBasis([2, 1, 3, 4, 5], [4.0, 5.0, 6.0, 7.0, 8.0], n_u=3)
+        om, n_x = O.hilbert_model(2, 3, basis.count, basis.stride, basis.L), 2
     else:
         basis = pg.HilbertGPBasis([3, 4, 2], [6.0, 9.0, 11.0])
         om, n_x = O.hilbert_model(2, 1, basis.count, basis.stride, basis.L), 2
+    n_u = len(basis.count) - n_x if model != "known" else 1
     K, H, N = 77, 7, 12
     A = rng.normal(0, 0.3, (K, n_x, basis.n_phi))
     Bq = rng.normal(0, 0.1, (K, n_x, n_x))
@@ -300,10 +320,10 @@ def test_stacked_dynamics_and_jacobians(model, variant):
     w = rng.uniform(size=(K, N))
     w /= w.sum(1, keepdims=True)
     x = rng.normal(0, 1, (K, N, n_x))
-    um = rng.normal(0, 1, (K, 1))
+    um = rng.normal(0, 1, (K, n_u))
     Cm = np.zeros((1, n_x))
     Cm[0, 0] = 1.0
-    u_init = rng.normal(0, 1, (1, H))
+    u_init = rng.normal(0, 1, (n_u, H))
     batch = pg.PGSampleBatch(A, Q, w, np.transpose(x, (0, 2, 1)), um)
     with pg.DeviceSamples.from_samples(batch, basis) as ds:
         sc = ds.rollout(pg.LinearMeasurement(Cm), 0.1, H, u_init=u_init, seed=4).scenarios()
@@ -327,6 +347,38 @@ def test_stacked_dynamics_and_jacobians(model, variant):
             fd = (ds.dynamics(xp.reshape(-1), u_init[:, t], t=None, phi_variant=variant, jacobians=False)[0]
                   - ds.dynamics(xm.reshape(-1), u_init[:, t], t=None, phi_variant=variant, jacobians=False)[0]) / (2 * eps)
             np.testing.assert_allclose(jx[:, :, c], fd.reshape(K, n_x), rtol=0, atol=2e-8)
-        fu = (ds.dynamics(x0.reshape(-1), u_init[:, t] + eps, t=None, phi_variant=variant, jacobians=False)[0]
-              - ds.dynamics(x0.reshape(-1), u_init[:, t] - eps, t=None, phi_variant=variant, jacobians=False)[0]) / (2 * eps)
-        np.testing.assert_allclose(ju[:, :, 0], fu.reshape(K, n_x), rtol=0, atol=2e-8)
+        for c in range(n_u):
+            du = np.zeros(n_u)
+            du[c] = eps
+            fu = (ds.dynamics(x0.reshape(-1), u_init[:, t] + du, t=None, phi_variant=variant, jacobians=False)[0]
+                  - ds.dynamics(x0.reshape(-1), u_init[:, t] - du, t=None, phi_variant=variant, jacobians=False)[0]) / (2 * eps)
+            np.testing.assert_allclose(ju[:, :, c], fu.reshape(K, n_x), rtol=0, atol=2e-8)
+
+
+@pytest.mark.parametrize("jac", [True, False])
+def test_stacked_dynamics_many_scenarios(dynamics_kernel, jac):
+    """K large enough that every warp of the persistent grid walks several scenarios (both copy stages, both mbarrier
+    phases of k_dynamics_bulk), the BASELINE.json configs[4] shape (n_x = 4, n_phi = 625), a ragged last shard."""
+    rng = np.random.default_rng(5)
+    basis = pg.HilbertGPBasis([1, 5, 5, 5, 5], [4.0, 5.0, 6.0, 7.0, 8.0])
+    om, n_x, N = O.hilbert_model(4, 1, basis.count, basis.stride, basis.L), 4, 3
+    K, H = 148 * 11 * 3 + 37, 2
+    A = rng.normal(0, 0.3, (K, n_x, basis.n_phi))
+    Q = np.broadcast_to(0.05 * np.eye(n_x), (K, n_x, n_x)).copy()
+    w = np.full((K, N), 1.0 / N)
+    x = rng.normal(0, 1, (K, N, n_x))
+    um = rng.normal(0, 1, (K, 1))
+    u_init = rng.normal(0, 1, (1, H))
+    Cm = np.zeros((1, n_x))
+    Cm[0, 0] = 1.0
+    batch = pg.PGSampleBatch(A, Q, w, np.transpose(x, (0, 2, 1)), um)
+    xv = rng.normal(0, 2, (K, n_x))
+    with pg.DeviceSamples.from_samples(batch, basis) as ds:
+        sc = ds.rollout(pg.LinearMeasurement(Cm), 0.1, H, u_init=u_init, seed=4).scenarios(want=("v",))
+        for variant in (0, 1):
+            xn, jx, ju = ds.dynamics(xv.reshape(-1), u_init[:, 1], t=1, phi_variant=variant, jacobians=jac)
+            rx, rjx, rju = O.dynamics(om, A, xv, u_init[:, 1], sc["v"], 1, variant)
+            _assert_same("x_next", xn.reshape(K, n_x), rx)
+            if jac:
+                _assert_same("df/dx", jx, rjx)
+                _assert_same("df/du", ju, rju)
