@@ -99,6 +99,10 @@ int pgb_set_measurement(pgb_handle* h, const double* C, const double* R);
 int pgb_set_init_dist(pgb_handle* h, const double* mean, const double* chol_lower);
 /* MNIW prior: V diagonal (n_phi), Lambda_Q n_x x n_x, ell_Q              :56, :226 */
 int pgb_set_prior(pgb_handle* h, const double* V_diag, const double* Lambda_Q, double ell_Q);
+/* the same with a dense V (n_phi x n_phi, column-major, symmetric positive definite): MNIW_sample takes any V (:56) and
+ * forms Sigbar = Sigma + I / V (:64).  I / V is a constant of the sampler: it is evaluated here, once, on the host
+ * (Cholesky + column solves) and added on the device in every draw.  PGB_ERR_NOT_POSDEF when V has no Cholesky factor. */
+int pgb_set_prior_dense(pgb_handle* h, const double* V, const double* Lambda_Q, double ell_Q);
 /* chain state: A n_x x n_phi, Q n_x x n_x, x_prim n_x x T (NULL = zeros, :126-128);
  * sweep_index = k of the next sweep (1 selects the plain bootstrap filter branch, :183-189). */
 int pgb_set_state(pgb_handle* h, int32_t chain, const double* A, const double* Q, const double* x_prim,
@@ -170,6 +174,11 @@ int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Ph
                     const double* Sigma, const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t T,
                     const double* bartlett, const double* Xmn, uint64_t seed, uint32_t chain, uint32_t sweep_index,
                     double* A_out, double* Q_out);
+/* MNIW_sample with a dense V (n_phi x n_phi, column-major); otherwise as pgb_mniw_sample */
+int pgb_mniw_sample_dense(int32_t device, int32_t n_x, int32_t n_phi, const double* Phi, const double* Psi,
+                          const double* Sigma, const double* V, const double* Lambda_Q, double ell_Q, int64_t T,
+                          const double* bartlett, const double* Xmn, uint64_t seed, uint32_t chain,
+                          uint32_t sweep_index, double* A_out, double* Q_out);
 
 /* Scenario sampling + forward rollout (optimal_control_Ipopt.jl:47-83,114-125) for K posterior
  * samples.  cfg supplies the model (N = particles per sample, T ignored).  Inputs (host):
@@ -280,6 +289,7 @@ int pgb_multi_set_data(pgb_multi* m, const double* u, const double* y);
 int pgb_multi_set_measurement(pgb_multi* m, const double* C, const double* R);
 int pgb_multi_set_init_dist(pgb_multi* m, const double* mean, const double* chol_lower);
 int pgb_multi_set_prior(pgb_multi* m, const double* V_diag, const double* Lambda_Q, double ell_Q);
+int pgb_multi_set_prior_dense(pgb_multi* m, const double* V, const double* Lambda_Q, double ell_Q);
 /* chain: global index, or -1 = every chain */
 int pgb_multi_set_state(pgb_multi* m, int32_t chain, const double* A, const double* Q, const double* x_prim,
                         int64_t sweep_index);
@@ -341,8 +351,9 @@ int pgb_test_math(int32_t device, int32_t fn, const double* x, double* y, int64_
 int pgb_test_fp64_peak(int32_t device, double* tflops);
 /* rollout kernel choice for the tests: -1 automatic (default), 0 CTA per scenario, 1 warp per scenario */
 void pgb_test_rollout_kernel(int32_t which);
-/* dynamics kernel choice for the tests: -1 automatic (default), 0 k_dynamics (strided loads, every shape), 1 / 2
- * k_dynamics_bulk with 4 / 5 warps per CTA (cp.async.bulk staging; Hilbert basis, even n_x, n_z = 3 | 5, else k_dynamics) */
+/* dynamics kernel choice for the tests: -1 automatic (default), 0 k_dynamics (strided loads, every shape), 1 / 2 / 3
+ * k_dynamics_bulk with at most 4 / 2 / 8 warps per CTA (cp.async.bulk staging of A_k; Hilbert basis, even n_x,
+ * n_z = 3 | 5, else k_dynamics) */
 void pgb_test_dynamics_kernel(int32_t which);
 
 #ifdef __cplusplus

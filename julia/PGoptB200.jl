@@ -90,17 +90,27 @@ function systematic_resampling(W, N; rnd=rand(), device=0)
     return idx
 end
 
+# V of the MN prior (particle_Gibbs.jl:56, :64): a Diagonal / diagonal matrix goes down the diagonal path (1 ./ V.diag, as
+# both examples), any other symmetric positive definite matrix down the dense one (pgb_*_dense: I / V by Cholesky, once)
+function prior_V(V)
+    V isa Diagonal && return false, Vector{Float64}(V.diag)
+    Vm = Matrix{Float64}(V)
+    isdiag(Vm) && return false, Vector{Float64}(diag(Vm))
+    return true, vec(Vm)
+end
+
 """
     MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T)      # Julia/src/particle_Gibbs.jl:56-81
 """
 function MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T; seed=rand(UInt64), chain=0, sweep_index=1, device=0)
     n_x, n_phi = size(Psi)
-    Vd = V isa Diagonal ? Vector{Float64}(V.diag) : Vector{Float64}(diag(V))
+    dense, Vd = prior_V(V)
     A = Matrix{Float64}(undef, n_x, n_phi); Q = Matrix{Float64}(undef, n_x, n_x)
-    check(ccall((:pgb_mniw_sample, LIB), Cint,
-                (Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Int64,
-                 Ptr{Float64}, Ptr{Float64}, UInt64, UInt32, UInt32, Ptr{Float64}, Ptr{Float64}),
-                device, n_x, n_phi, Matrix{Float64}(Phi), Matrix{Float64}(Psi), Matrix{Float64}(Sigma), Vd,
+    argt = (Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Int64,
+            Ptr{Float64}, Ptr{Float64}, UInt64, UInt32, UInt32, Ptr{Float64}, Ptr{Float64})
+    call(args...) = dense ? ccall((:pgb_mniw_sample_dense, LIB), Cint, argt, args...) :
+                            ccall((:pgb_mniw_sample, LIB), Cint, argt, args...)
+    check(call(device, n_x, n_phi, Matrix{Float64}(Phi), Matrix{Float64}(Psi), Matrix{Float64}(Sigma), Vd,
                 Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q), T, C_NULL, C_NULL, seed, chain, sweep_index, A, Q))
     return A, Q
 end
@@ -123,9 +133,14 @@ function particle_Gibbs(u_training, y_training, K, K_b, k_d, N, phi, Lambda_Q, e
         check(ccall((:pgb_set_measurement, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], g.C, Rm), h[])
         mu = Vector{Float64}(mean(x_init_dist)); Lc = Matrix{Float64}(cholesky(Matrix(cov(x_init_dist))).L)
         check(ccall((:pgb_set_init_dist, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], mu, Lc), h[])
-        Vd = V isa Diagonal ? Vector{Float64}(V.diag) : Vector{Float64}(diag(V))
-        check(ccall((:pgb_set_prior, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
-                    h[], Vd, Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q)), h[])
+        dense, Vd = prior_V(V)
+        if dense
+            check(ccall((:pgb_set_prior_dense, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
+                        h[], Vd, Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q)), h[])
+        else
+            check(ccall((:pgb_set_prior, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
+                        h[], Vd, Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q)), h[])
+        end
         xp = x_prim === nothing ? C_NULL : Matrix{Float64}(x_prim)
         check(ccall((:pgb_set_state, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
                     h[], 0, Matrix{Float64}(A_init), Matrix{Float64}(Q_init * I(n_x)), xp, 1), h[])

@@ -555,9 +555,10 @@ static double mt_chi2(const orc_streams* s, uint32_t sweep, uint32_t which, doub
   }
 }
 
-int orc_mniw_sample(int n_x, int n_phi, const double* Phi, const double* Psi, const double* Sigma,
-                    const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t Tm1,
-                    const orc_streams* s, uint32_t sweep_index, double* A_out, double* Q_out) {
+/* V_diag: the diagonal of V (the reference's examples); Vinv != NULL: I / V of a dense V (pgb_host_spd_inverse) */
+static int mniw_sample_impl(int n_x, int n_phi, const double* Phi, const double* Psi, const double* Sigma,
+                            const double* V_diag, const double* Vinv, const double* Lambda_Q, double ell_Q, int64_t Tm1,
+                            const orc_streams* s, uint32_t sweep_index, double* A_out, double* Q_out) {
   int status = 0;
   size_t pp = (size_t)n_phi * (size_t)n_phi;
   double* Ls = (double*)malloc(sizeof(double) * pp);      /* chol(Sigbar) */
@@ -572,7 +573,11 @@ int orc_mniw_sample(int n_x, int n_phi, const double* Phi, const double* Psi, co
 
   /* Sigbar = Sigma + I / V   (:64) */
   memcpy(Ls, Sigma, sizeof(double) * pp);
-  for (int i = 0; i < n_phi; ++i) Ls[i + n_phi * i] = Ls[i + n_phi * i] + 1.0 / V_diag[i];
+  if (Vinv) {
+    for (size_t e = 0; e < pp; ++e) Ls[e] = Ls[e] + Vinv[e];
+  } else {
+    for (int i = 0; i < n_phi; ++i) Ls[i + n_phi * i] = Ls[i + n_phi * i] + 1.0 / V_diag[i];
+  }
   if (orc_cholesky_lower(Ls, n_phi)) { status = 16; goto done; }
   /* post_mean = Psibar / Sigbar  (:67): row d solves Sigbar m = psi_d */
   for (int d = 0; d < n_x; ++d) {
@@ -661,13 +666,72 @@ done:
   return status;
 }
 
+int orc_mniw_sample(int n_x, int n_phi, const double* Phi, const double* Psi, const double* Sigma,
+                    const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t Tm1,
+                    const orc_streams* s, uint32_t sweep_index, double* A_out, double* Q_out) {
+  return mniw_sample_impl(n_x, n_phi, Phi, Psi, Sigma, V_diag, NULL, Lambda_Q, ell_Q, Tm1, s, sweep_index, A_out, Q_out);
+}
+
+/* I / V of a dense symmetric positive definite V (column-major n x n): 0 ok, 1 not positive definite */
+int orc_spd_inverse(const double* V, int n, double* inv) {
+  double* work = (double*)malloc(sizeof(double) * ((size_t)n * (size_t)n + (size_t)n));
+  int rc = pgb_host_spd_inverse(V, n, inv, work);
+  free(work);
+  return rc;
+}
+
+/* MNIW_sample with a dense V (particle_Gibbs.jl:56 takes any V; :64 Sigbar = Sigma + I / V) */
+int orc_mniw_sample_dense(int n_x, int n_phi, const double* Phi, const double* Psi, const double* Sigma,
+                          const double* V, const double* Lambda_Q, double ell_Q, int64_t Tm1,
+                          const orc_streams* s, uint32_t sweep_index, double* A_out, double* Q_out) {
+  double* Vinv = (double*)malloc(sizeof(double) * (size_t)n_phi * (size_t)n_phi);
+  int status = orc_spd_inverse(V, n_phi, Vinv) ? 16 : 0;
+  if (!status)
+    status = mniw_sample_impl(n_x, n_phi, Phi, Psi, Sigma, NULL, Vinv, Lambda_Q, ell_Q, Tm1, s, sweep_index, A_out, Q_out);
+  free(Vinv);
+  return status;
+}
+
 /* ------------------------------------------------------------------ full sampler */
+static int particle_gibbs_impl(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y,
+                               const double* C, const double* R, const double* x0_mean, const double* x0_chol,
+                               const double* A_init, const double* Q_init, const double* V_diag, const double* Vinv,
+                               const double* Lambda_Q, double ell_Q, int64_t K, int64_t K_b, int64_t k_d,
+                               uint64_t seed, uint32_t chain, double* x_prim, double* A_s, double* Q_s, double* w_s,
+                               double* x_s);
+
 int orc_particle_gibbs(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y,
                        const double* C, const double* R, const double* x0_mean, const double* x0_chol,
                        const double* A_init, const double* Q_init, const double* V_diag,
                        const double* Lambda_Q, double ell_Q, int64_t K, int64_t K_b, int64_t k_d,
                        uint64_t seed, uint32_t chain, double* x_prim, double* A_s, double* Q_s, double* w_s,
                        double* x_s) {
+  return particle_gibbs_impl(m, N, T, u, y, C, R, x0_mean, x0_chol, A_init, Q_init, V_diag, NULL, Lambda_Q, ell_Q, K, K_b,
+                             k_d, seed, chain, x_prim, A_s, Q_s, w_s, x_s);
+}
+
+/* particle_Gibbs with a dense prior covariance V (n_phi x n_phi, column-major) */
+int orc_particle_gibbs_dense(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y,
+                             const double* C, const double* R, const double* x0_mean, const double* x0_chol,
+                             const double* A_init, const double* Q_init, const double* V,
+                             const double* Lambda_Q, double ell_Q, int64_t K, int64_t K_b, int64_t k_d,
+                             uint64_t seed, uint32_t chain, double* x_prim, double* A_s, double* Q_s, double* w_s,
+                             double* x_s) {
+  double* Vinv = (double*)malloc(sizeof(double) * (size_t)m->n_phi * (size_t)m->n_phi);
+  int status = orc_spd_inverse(V, m->n_phi, Vinv) ? 16 : 0;
+  if (!status)
+    status = particle_gibbs_impl(m, N, T, u, y, C, R, x0_mean, x0_chol, A_init, Q_init, NULL, Vinv, Lambda_Q, ell_Q, K,
+                                 K_b, k_d, seed, chain, x_prim, A_s, Q_s, w_s, x_s);
+  free(Vinv);
+  return status;
+}
+
+static int particle_gibbs_impl(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y,
+                               const double* C, const double* R, const double* x0_mean, const double* x0_chol,
+                               const double* A_init, const double* Q_init, const double* V_diag, const double* Vinv,
+                               const double* Lambda_Q, double ell_Q, int64_t K, int64_t K_b, int64_t k_d,
+                               uint64_t seed, uint32_t chain, double* x_prim, double* A_s, double* Q_s, double* w_s,
+                               double* x_s) {
   const int n_x = m->n_x, n_phi = m->n_phi;
   int64_t K_total = K_b + 1 + (K - 1) * (k_d + 1); /* :116 */
   int status = 0;
@@ -696,7 +760,7 @@ int orc_particle_gibbs(const orc_model* m, int64_t N, int64_t T, const double* u
       if (x_s) memcpy(&x_s[cur * N * n_x], x_last, sizeof(double) * (size_t)(N * n_x));
       ++cur;
     }
-    status |= orc_mniw_sample(n_x, n_phi, Phi, Psi, Sigma, V_diag, Lambda_Q, ell_Q, T - 1, &s, (uint32_t)k, A, Q); /* :226 */
+    status |= mniw_sample_impl(n_x, n_phi, Phi, Psi, Sigma, V_diag, Vinv, Lambda_Q, ell_Q, T - 1, &s, (uint32_t)k, A, Q); /* :226 */
     if (status & 16) break;
   }
   free(A); free(Q); free(Phi); free(Psi); free(Sigma); free(w_last); free(x_last);

@@ -90,6 +90,19 @@ int orc_mniw_sample(int n_x, int n_phi, const double* Phi, const double* Psi, co
                     const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t Tm1,
                     const orc_streams* s, uint32_t sweep_index, double* A_out, double* Q_out);
 
+/* Dense prior covariance V (n_phi x n_phi, column-major, symmetric positive definite; particle_Gibbs.jl:56 takes any V):
+ * Sigbar = Sigma + I / V (:64) with I / V = orc_spd_inverse(V) (Cholesky + column solves, pgb_math.h). */
+int orc_spd_inverse(const double* V, int n, double* inv);
+int orc_mniw_sample_dense(int n_x, int n_phi, const double* Phi, const double* Psi, const double* Sigma,
+                          const double* V, const double* Lambda_Q, double ell_Q, int64_t Tm1,
+                          const orc_streams* s, uint32_t sweep_index, double* A_out, double* Q_out);
+int orc_particle_gibbs_dense(const orc_model* m, int64_t N, int64_t T, const double* u, const double* y,
+                             const double* C, const double* R, const double* x0_mean, const double* x0_chol,
+                             const double* A_init, const double* Q_init, const double* V,
+                             const double* Lambda_Q, double ell_Q, int64_t K, int64_t K_b, int64_t k_d,
+                             uint64_t seed, uint32_t chain, double* x_prim, double* A_s, double* Q_s, double* w_s,
+                             double* x_s);
+
 /* orc_sweep in the F32 precision mode (PGB_PRECISION_F32; see pg_oracle.c): FP32 particle states / basis functions /
  * noise / log-weights / exponentials with the bit-defined functions of pgb_mathf.h, FP64 normalisation and cumulative
  * sums.  Same arguments; the history arrays hold FP32 values widened to FP64. */

@@ -37,6 +37,21 @@ class PG_sample:
     u_m1: np.ndarray   # (n_u,)
 
 
+def _prior_V(V):
+    """(array for the C ABI, dense?): the diagonal of V when V is a vector or a diagonal matrix, else the column-major
+    dense matrix (symmetric: either triangle order gives the same bytes)."""
+    V = np.asarray(V, dtype=np.float64)
+    if V.ndim == 2:
+        if V.shape[0] != V.shape[1]:
+            raise ValueError("V must be square")
+        if np.count_nonzero(V - np.diag(np.diag(V))) == 0:
+            return np.diag(V).copy(), False
+        if not np.array_equal(V, V.T):
+            raise ValueError("V must be symmetric")
+        return np.ascontiguousarray(V), True
+    return V, False
+
+
 class PGSampleBatch:
     """K posterior samples as stacked arrays — the same content as a Vector{PG_sample} (PGopt.jl:23-29), without one
     Python object per sample: A (K, n_x, n_phi), Q (K, n_x, n_x), w_m1 (K, N), x_m1 (K, n_x, N), u_m1 (K, n_u).
@@ -250,13 +265,13 @@ class ParticleGibbsEngine:
         self._ck(lib().pgb_set_init_dist(self._h, _p(_f(dist.mean)), _p(_f(dist.chol))))
 
     def set_prior(self, V, Lambda_Q, ell_Q):
-        V = np.asarray(V, dtype=np.float64)
-        if V.ndim == 2:
-            if np.count_nonzero(V - np.diag(np.diag(V))):
-                raise ValueError("only a diagonal prior covariance V is supported (both reference examples)")
-            V = np.diag(V)
+        """V: the diagonal (n_phi,) or the matrix (n_phi, n_phi) of the MN prior's left covariance (particle_Gibbs.jl:56,
+        :64).  A diagonal matrix takes the diagonal path (1 / V[i], as both reference examples), any other symmetric
+        positive definite V the dense one (I / V by Cholesky, once)."""
+        V, dense = _prior_V(V)
         LQ = np.asarray(Lambda_Q, dtype=np.float64)
-        self._ck(lib().pgb_set_prior(self._h, _p(_f(V)), _p(_f(LQ)), C.c_double(float(ell_Q))))
+        fn = lib().pgb_set_prior_dense if dense else lib().pgb_set_prior
+        self._ck(fn(self._h, _p(_f(V)), _p(_f(LQ)), C.c_double(float(ell_Q))))
 
     def set_state(self, A, Q, x_prim=None, sweep_index=1, chain=0):
         xp = None if x_prim is None else _f(x_prim)
@@ -417,10 +432,9 @@ class MultiGPUEngine:
         self._ck(lib().pgb_multi_set_init_dist(self._m, _p(_f(dist.mean)), _p(_f(dist.chol))))
 
     def set_prior(self, V, Lambda_Q, ell_Q):
-        V = np.asarray(V, dtype=np.float64)
-        if V.ndim == 2:
-            V = np.diag(V)
-        self._ck(lib().pgb_multi_set_prior(self._m, _p(_f(V)), _p(_f(np.asarray(Lambda_Q, dtype=np.float64))), C.c_double(float(ell_Q))))
+        V, dense = _prior_V(V)
+        fn = lib().pgb_multi_set_prior_dense if dense else lib().pgb_multi_set_prior
+        self._ck(fn(self._m, _p(_f(V)), _p(_f(np.asarray(Lambda_Q, dtype=np.float64))), C.c_double(float(ell_Q))))
 
     def set_state(self, A, Q, x_prim=None, sweep_index=1, chain=-1):
         xp = None if x_prim is None else _f(x_prim)
@@ -504,18 +518,15 @@ def MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T, bartlett=None, Xmn=None,
     The Bartlett factor / matrix-normal normals may be injected (parity) or come from Philox."""
     Phi, Psi, Sigma = np.atleast_2d(Phi), np.atleast_2d(Psi), np.atleast_2d(Sigma)
     n_x, n_phi = Psi.shape
-    V = np.asarray(V, dtype=np.float64)
-    if V.ndim == 2:
-        if np.count_nonzero(V - np.diag(np.diag(V))):
-            raise ValueError("only a diagonal V is supported")
-        V = np.diag(V)
+    V, dense = _prior_V(V)
     A, Q = np.empty(n_x * n_phi), np.empty(n_x * n_x)
     b = None if bartlett is None else _f(bartlett)
     X = None if Xmn is None else _f(Xmn)
-    check(lib().pgb_mniw_sample(C.c_int32(device), C.c_int32(n_x), C.c_int32(n_phi), _p(_f(Phi)), _p(_f(Psi)),
-                                _p(_f(Sigma)), _p(_f(V)), _p(_f(np.asarray(Lambda_Q, dtype=np.float64))),
-                                C.c_double(float(ell_Q)), C.c_int64(int(T)), _p(b), _p(X), C.c_uint64(seed),
-                                C.c_uint32(chain), C.c_uint32(sweep_index), _p(A), _p(Q)))
+    fn = lib().pgb_mniw_sample_dense if dense else lib().pgb_mniw_sample
+    check(fn(C.c_int32(device), C.c_int32(n_x), C.c_int32(n_phi), _p(_f(Phi)), _p(_f(Psi)),
+             _p(_f(Sigma)), _p(_f(V)), _p(_f(np.asarray(Lambda_Q, dtype=np.float64))),
+             C.c_double(float(ell_Q)), C.c_int64(int(T)), _p(b), _p(X), C.c_uint64(seed),
+             C.c_uint32(chain), C.c_uint32(sweep_index), _p(A), _p(Q)))
     return A.reshape((n_x, n_phi), order="F"), Q.reshape((n_x, n_x), order="F")
 
 

@@ -292,6 +292,24 @@ extern "C" int pgb_set_prior(pgb_handle* h, const double* V_diag, const double* 
   CK(h, cudaMemcpyAsync(h->d_LambdaQ, Lambda_Q, (size_t)h->cfg.n_x * h->cfg.n_x * 8, cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   h->md.ell_Q = ell_Q;
+  h->md.Vinv = nullptr;
+  h->have_prior = true;
+  return PGB_OK;
+}
+
+extern "C" int pgb_set_prior_dense(pgb_handle* h, const double* V, const double* Lambda_Q, double ell_Q) {
+  NEED(h);
+  if (!V || !Lambda_Q) return set_err(h, PGB_ERR_INVALID, "V/Lambda_Q NULL");
+  const size_t np = (size_t)h->cfg.n_phi, pp = np * np;
+  std::vector<double> inv(pp), work(pp + np);
+  if (pgb_host_spd_inverse(V, (int)np, inv.data(), work.data()))
+    return set_err(h, PGB_ERR_NOT_POSDEF, "V is not positive definite");
+  if (!h->d_Vinv) CK(h, dalloc(h, &h->d_Vinv, pp, false));
+  CK(h, cudaMemcpyAsync(h->d_Vinv, inv.data(), pp * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_LambdaQ, Lambda_Q, (size_t)h->cfg.n_x * h->cfg.n_x * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  h->md.ell_Q = ell_Q;
+  h->md.Vinv = h->d_Vinv;
   h->have_prior = true;
   return PGB_OK;
 }
@@ -683,10 +701,10 @@ extern "C" int pgb_get_status(pgb_handle* h, int32_t chain, int32_t* status_bits
   return PGB_OK;
 }
 
-extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Phi, const double* Psi,
-                               const double* Sigma, const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t T,
-                               const double* bartlett, const double* Xmn, uint64_t seed, uint32_t chain,
-                               uint32_t sweep_index, double* A_out, double* Q_out) {
+static int mniw_sample_impl(int32_t device, int32_t n_x, int32_t n_phi, const double* Phi, const double* Psi,
+                            const double* Sigma, const double* V_diag, bool dense, const double* Lambda_Q, double ell_Q,
+                            int64_t T, const double* bartlett, const double* Xmn, uint64_t seed, uint32_t chain,
+                            uint32_t sweep_index, double* A_out, double* Q_out) {
   if (!Phi || !Psi || !Sigma || !V_diag || !Lambda_Q || !A_out || !Q_out || n_x < 1 || n_x > 4 || n_phi < 1)
     return set_err(nullptr, PGB_ERR_INVALID, "bad arguments");
   int ndev = 0;
@@ -706,15 +724,24 @@ extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const
   md.nc = 1; md.n_x = n_x; md.n_phi = n_phi; md.Tm1 = T; md.ell_Q = ell_Q;
   const size_t pp = (size_t)n_phi * n_phi, xp = (size_t)n_x * n_phi, xx = (size_t)n_x * n_x;
   double *dV, *dL, *dB = nullptr, *dX = nullptr, *dQ;
-  CK(h, dalloc(h, &dV, (size_t)n_phi));
+  CK(h, dalloc(h, &dV, dense ? pp : (size_t)n_phi));
   CK(h, dalloc(h, &dL, xx));
   CK(h, dalloc(h, &md.Phi, xx)); CK(h, dalloc(h, &md.Psi, xp)); CK(h, dalloc(h, &md.Sigma, pp));
   CK(h, dalloc(h, &md.Ls, pp)); CK(h, dalloc(h, &md.Sinv, pp)); CK(h, dalloc(h, &md.Lv, pp));
   CK(h, dalloc(h, &md.Mpost, xp)); CK(h, dalloc(h, &md.Xn, xp)); CK(h, dalloc(h, &md.LX, xp));
   CK(h, dalloc(h, &md.A, xp)); CK(h, dalloc(h, &dQ, xx)); CK(h, dalloc(h, &md.Lq, 16)); CK(h, dalloc(h, &md.c0, 1));
   CK(h, dalloc(h, &md.status, 1));
-  md.Q = dQ; md.V_diag = dV; md.Lambda_Q = dL;
-  CK(h, cudaMemcpy(dV, V_diag, (size_t)n_phi * 8, cudaMemcpyHostToDevice));
+  md.Q = dQ; md.Lambda_Q = dL;
+  if (dense) {  // V_diag points at the dense V: I / V on the host, as pgb_set_prior_dense
+    std::vector<double> inv(pp), work(pp + (size_t)n_phi);
+    if (pgb_host_spd_inverse(V_diag, n_phi, inv.data(), work.data()))
+      return set_err(nullptr, PGB_ERR_NOT_POSDEF, "V is not positive definite");
+    CK(h, cudaMemcpy(dV, inv.data(), pp * 8, cudaMemcpyHostToDevice));
+    md.Vinv = dV;
+  } else {
+    CK(h, cudaMemcpy(dV, V_diag, (size_t)n_phi * 8, cudaMemcpyHostToDevice));
+    md.V_diag = dV;
+  }
   CK(h, cudaMemcpy(dL, Lambda_Q, xx * 8, cudaMemcpyHostToDevice));
   CK(h, cudaMemcpy(md.Phi, Phi, xx * 8, cudaMemcpyHostToDevice));
   CK(h, cudaMemcpy(md.Psi, Psi, xp * 8, cudaMemcpyHostToDevice));
@@ -738,6 +765,22 @@ extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const
   CK(h, cudaMemcpy(A_out, md.A, xp * 8, cudaMemcpyDeviceToHost));
   CK(h, cudaMemcpy(Q_out, dQ, xx * 8, cudaMemcpyDeviceToHost));
   return PGB_OK;
+}
+
+extern "C" int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Phi, const double* Psi,
+                               const double* Sigma, const double* V_diag, const double* Lambda_Q, double ell_Q, int64_t T,
+                               const double* bartlett, const double* Xmn, uint64_t seed, uint32_t chain,
+                               uint32_t sweep_index, double* A_out, double* Q_out) {
+  return mniw_sample_impl(device, n_x, n_phi, Phi, Psi, Sigma, V_diag, false, Lambda_Q, ell_Q, T, bartlett, Xmn, seed,
+                          chain, sweep_index, A_out, Q_out);
+}
+
+extern "C" int pgb_mniw_sample_dense(int32_t device, int32_t n_x, int32_t n_phi, const double* Phi, const double* Psi,
+                                     const double* Sigma, const double* V, const double* Lambda_Q, double ell_Q, int64_t T,
+                                     const double* bartlett, const double* Xmn, uint64_t seed, uint32_t chain,
+                                     uint32_t sweep_index, double* A_out, double* Q_out) {
+  return mniw_sample_impl(device, n_x, n_phi, Phi, Psi, Sigma, V, true, Lambda_Q, ell_Q, T, bartlett, Xmn, seed, chain,
+                          sweep_index, A_out, Q_out);
 }
 
 extern "C" int pgb_set_mode(pgb_handle* h, int32_t persistent) {

@@ -317,4 +317,41 @@ PGB_HD int pgb_math_selftest(void) {
   return (unfused == 0.0 && fused == 0x1p-56) ? 0 : 1;
 }
 
+// Inverse of a symmetric positive definite matrix (column-major n x n), host side only: the dense-V form of
+// `I / V` (Julia/src/particle_Gibbs.jl:64) is a constant of the sampler, evaluated once when the prior is set.  Lower
+// Cholesky factor (right-looking, fma updates in increasing pivot order), then column j = L' \ (L \ e_j), upper triangle
+// copied from the lower one (LAPACK potri convention).  `work` holds n*n + n doubles.  Returns 1 when V is not positive
+// definite (Julia: PosDefException / SingularException).  Shared by the library (pgb_set_prior_dense) and the oracle.
+static inline int pgb_host_spd_inverse(const double* V, int n, double* inv, double* work) {
+  double* L = work;
+  double* col = work + (size_t)n * (size_t)n;
+  for (size_t e = 0; e < (size_t)n * (size_t)n; ++e) L[e] = V[e];
+  for (int k = 0; k < n; ++k) {
+    double d = L[k + (size_t)n * k];
+    if (!(d > 0.0)) return 1;
+    d = sqrt(d);
+    L[k + (size_t)n * k] = d;
+    for (int i = k + 1; i < n; ++i) L[i + (size_t)n * k] = L[i + (size_t)n * k] / d;
+    for (int j = k + 1; j < n; ++j)
+      for (int i = j; i < n; ++i) L[i + (size_t)n * j] = fma(-L[i + (size_t)n * k], L[j + (size_t)n * k], L[i + (size_t)n * j]);
+  }
+  for (int j = 0; j < n; ++j) {
+    for (int i = 0; i < n; ++i) col[i] = (i == j) ? 1.0 : 0.0;
+    for (int d = 0; d < n; ++d) {
+      double acc = col[d];
+      for (int e = 0; e < d; ++e) acc = fma(-L[d + (size_t)n * e], col[e], acc);
+      col[d] = acc / L[d + (size_t)n * d];
+    }
+    for (int d = n - 1; d >= 0; --d) {
+      double acc = col[d];
+      for (int e = n - 1; e > d; --e) acc = fma(-L[e + (size_t)n * d], col[e], acc);
+      col[d] = acc / L[d + (size_t)n * d];
+    }
+    for (int i = 0; i < n; ++i) inv[i + (size_t)n * j] = col[i];
+  }
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < j; ++i) inv[i + (size_t)n * j] = inv[j + (size_t)n * i];
+  return 0;
+}
+
 #endif  // PGB_MATH_H

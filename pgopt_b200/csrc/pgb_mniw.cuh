@@ -17,6 +17,7 @@ struct MniwDev {
   int64_t Tm1;
   double ell_Q;
   const double* V_diag;    // [n_phi]
+  const double* Vinv;      // [n_phi*n_phi] I / V of a dense V (pgb_set_prior_dense), or null: V is diag(V_diag)
   const double* Lambda_Q;  // [n_x*n_x]
   double* zeta;   // [nc][n_x][Tm1]
   double* zb;     // [nc][n_phi][Tm1]
@@ -307,7 +308,8 @@ static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md, int use_sm
   for (int64_t e = tid; e < pp; e += nth) {
     int i = (int)(e % np), j = (int)(e / np);
     double v = Sigma[e];
-    if (i == j) v = __dadd_rn(v, __ddiv_rn(1.0, md.V_diag[i]));
+    if (md.Vinv) v = __dadd_rn(v, md.Vinv[e]);
+    else if (i == j) v = __dadd_rn(v, __ddiv_rn(1.0, md.V_diag[i]));
     Ls[e] = v;
   }
   if (cta_cholesky(Ls, np, &s_fail)) {

@@ -229,6 +229,11 @@ extern "C" int pgb_multi_set_prior(pgb_multi* m, const double* V_diag, const dou
   NEEDM(m);
   return for_each_device(m, [=](pgb_multi_dev& D) { return pgb_set_prior(D.h, V_diag, Lambda_Q, ell_Q); });
 }
+
+extern "C" int pgb_multi_set_prior_dense(pgb_multi* m, const double* V, const double* Lambda_Q, double ell_Q) {
+  NEEDM(m);
+  return for_each_device(m, [=](pgb_multi_dev& D) { return pgb_set_prior_dense(D.h, V, Lambda_Q, ell_Q); });
+}
 // chain: global chain index, or -1 = the same state for every chain
 extern "C" int pgb_multi_set_state(pgb_multi* m, int32_t chain, const double* A, const double* Q, const double* x_prim,
                                    int64_t sweep_index) {

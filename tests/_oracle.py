@@ -142,11 +142,22 @@ def sweep(model, N, T, u, y, Cm, R, x0_mean, x0_chol, A, Q, x_prim, first, strea
 
 
 def mniw_sample(n_x, n_phi, Phi, Psi, Sigma, V_diag, Lambda_Q, ell_Q, Tm1, streams, sweep_index):
+    """V_diag: the diagonal (n_phi,) of V, or a dense symmetric positive definite V (n_phi, n_phi)"""
     A, Q = np.zeros(n_x * n_phi), np.zeros(n_x * n_x)
     args = [f64(np.asfortranarray(v).ravel(order="F")) for v in (Phi, Psi, Sigma, V_diag, Lambda_Q)]
-    st = lib().orc_mniw_sample(C.c_int(n_x), C.c_int(n_phi), *[_p(v) for v in args], C.c_double(ell_Q),
-                               C.c_int64(Tm1), C.byref(streams), C.c_uint32(sweep_index), _p(A), _p(Q))
+    fn = lib().orc_mniw_sample_dense if np.ndim(V_diag) == 2 else lib().orc_mniw_sample
+    st = fn(C.c_int(n_x), C.c_int(n_phi), *[_p(v) for v in args], C.c_double(ell_Q),
+            C.c_int64(Tm1), C.byref(streams), C.c_uint32(sweep_index), _p(A), _p(Q))
     return A.reshape((n_x, n_phi), order="F"), Q.reshape((n_x, n_x), order="F"), st
+
+
+def spd_inverse(V):
+    """orc_spd_inverse: I / V of a dense symmetric positive definite V (the oracle's and the library's definition)"""
+    V = np.asarray(V, dtype=np.float64)
+    n = V.shape[0]
+    out = np.zeros(n * n)
+    rc = lib().orc_spd_inverse(_p(f64(np.asfortranarray(V).ravel(order="F"))), C.c_int(n), _p(out))
+    return out.reshape((n, n), order="F"), rc
 
 
 def particle_gibbs(model, N, T, u, y, Cm, R, x0_mean, x0_chol, A_init, Q_init, V_diag, Lambda_Q, ell_Q,
@@ -157,11 +168,12 @@ def particle_gibbs(model, N, T, u, y, Cm, R, x0_mean, x0_chol, A_init, Q_init, V
     A_s, Q_s = np.zeros((K, n_x * n_phi)), np.zeros((K, n_x * n_x))
     w_s = np.zeros((K, N)) if keep_particles else None
     x_s = np.zeros((K, N, n_x)) if keep_particles else None
-    st = lib().orc_particle_gibbs(C.byref(model), C.c_int64(N), C.c_int64(T), _p(fl(u)), _p(fl(y)), _p(fl(Cm)),
-                                  _p(fl(np.atleast_2d(R))), _p(f64(x0_mean)), _p(fl(x0_chol)), _p(fl(A_init)),
-                                  _p(fl(Q_init)), _p(f64(V_diag)), _p(fl(Lambda_Q)), C.c_double(ell_Q),
-                                  C.c_int64(K), C.c_int64(K_b), C.c_int64(k_d), C.c_uint64(seed), C.c_uint32(chain),
-                                  _p(xp), _p(A_s), _p(Q_s), _p(w_s), _p(x_s))
+    fn = lib().orc_particle_gibbs_dense if np.ndim(V_diag) == 2 else lib().orc_particle_gibbs
+    st = fn(C.byref(model), C.c_int64(N), C.c_int64(T), _p(fl(u)), _p(fl(y)), _p(fl(Cm)),
+            _p(fl(np.atleast_2d(R))), _p(f64(x0_mean)), _p(fl(x0_chol)), _p(fl(A_init)),
+            _p(fl(Q_init)), _p(fl(V_diag)), _p(fl(Lambda_Q)), C.c_double(ell_Q),
+            C.c_int64(K), C.c_int64(K_b), C.c_int64(k_d), C.c_uint64(seed), C.c_uint32(chain),
+            _p(xp), _p(A_s), _p(Q_s), _p(w_s), _p(x_s))
     return dict(status=st, A=A_s.reshape((K, n_phi, n_x)).transpose(0, 2, 1), Q=Q_s.reshape((K, n_x, n_x)).transpose(0, 2, 1),
                 w=w_s, x=x_s, x_prim=xp.reshape((n_x, T), order="F"))
 

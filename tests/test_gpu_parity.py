@@ -482,6 +482,64 @@ def test_mniw_bit_exact_sizes(n_x, n_phi):
     _assert_same("A", Ag, Ar)
 
 
+def _dense_V(rng, n_phi, scale=1.0):
+    B = rng.normal(size=(n_phi, n_phi)) / np.sqrt(n_phi)
+    V = scale * (B @ B.T + 0.5 * np.eye(n_phi))
+    return 0.5 * (V + V.T)
+
+
+@pytest.mark.parametrize("n_x,n_phi", [(2, 5), (2, 125), (3, 200)])
+def test_mniw_dense_V_bit_exact(n_x, n_phi):
+    """MNIW_sample with a dense prior covariance V (particle_Gibbs.jl:56 takes any V; :64): pgb_mniw_sample_dense ==
+    orc_mniw_sample_dense with injected and with Philox draws, on the shared-memory and the global-memory path."""
+    rng = np.random.default_rng(200 + n_phi)
+    Tm1 = n_phi + 60
+    zeta, z = rng.normal(size=(n_x, Tm1)), rng.normal(size=(n_phi, Tm1))
+    Phi, Psi, Sig = zeta @ zeta.T, zeta @ z.T, z @ z.T
+    Sig = 0.5 * (Sig + Sig.T)
+    V = _dense_V(rng, n_phi, 4.0)
+    Lam, ell = 100 * np.eye(n_x), 10.0
+    s = P.injected_streams(4, 4, n_x, n_phi, 3, df=ell + Tm1 * n_x)
+    st = O.make_streams(philox=False, bartlett=s["bartlett"], Xmn=s["Xmn"])
+    Ar, Qr, rc = O.mniw_sample(n_x, n_phi, Phi, Psi, Sig, V, Lam, ell, Tm1, st, 1)
+    assert rc == 0
+    Ag, Qg = pg.MNIW_sample(Phi, Psi, Sig, V, Lam, ell, Tm1, bartlett=s["bartlett"], Xmn=s["Xmn"])
+    _assert_same("Q", Qg, Qr)
+    _assert_same("A", Ag, Ar)
+    stp = O.make_streams(philox=True, seed=6, chain=1)
+    Ar, Qr, rc = O.mniw_sample(n_x, n_phi, Phi, Psi, Sig, V, Lam, ell, Tm1, stp, 2)
+    Ag, Qg = pg.MNIW_sample(Phi, Psi, Sig, V, Lam, ell, Tm1, seed=6, chain=1, sweep_index=2)
+    _assert_same("Q philox", Qg, Qr)
+    _assert_same("A philox", Ag, Ar)
+    # a diagonal matrix takes the diagonal path: the same bits as passing the diagonal
+    Vd = rng.uniform(0.5, 20.0, n_phi)
+    A1, Q1 = pg.MNIW_sample(Phi, Psi, Sig, Vd, Lam, ell, Tm1, seed=6, chain=1, sweep_index=2)
+    A2, Q2 = pg.MNIW_sample(Phi, Psi, Sig, np.diag(Vd), Lam, ell, Tm1, seed=6, chain=1, sweep_index=2)
+    _assert_same("diag == vector", A2, A1)
+    with pytest.raises(pg.PgoptError):
+        pg.MNIW_sample(Phi, Psi, Sig, V - 10 * np.eye(n_phi), Lam, ell, Tm1, seed=6)
+
+
+@pytest.mark.parametrize("model,N", [("known", 30), ("hilbert", 300), ("known", 2500)])
+def test_particle_gibbs_dense_V_bit_exact(model, N):
+    """Whole sampler with a dense V (pgb_set_prior_dense) on the warp, CTA and sweep kernels: every kept sample identical
+    to the oracle's."""
+    basis, om, _ = _models()[model]
+    T, K, K_b, k_d = 30, 3, 2, 1
+    u, y, _ = P.make_data(T, 17)
+    n_phi = basis.n_phi
+    V = _dense_V(np.random.default_rng(3), n_phi, 10.0)
+    ref = O.particle_gibbs(om, N, T, u, y, [[1.0, 0.0]], 0.1, [2.0, 2.0], np.eye(2), np.zeros((2, n_phi)),
+                           100 * np.eye(2), V, 100 * np.eye(2), 10.0, K, K_b, k_d, seed=41, chain=1)
+    smp = pg.particle_Gibbs(u, y, K, K_b, k_d, N, basis, 100 * np.eye(2), 10.0, 100 * np.eye(2), V, np.zeros((2, n_phi)),
+                            pg.MvNormal([2.0, 2.0], 1.0), pg.LinearMeasurement([[1.0, 0.0]]), 0.1, seed=41, chain=1)
+    assert ref["status"] == 0 and len(smp) == K
+    for k in range(K):
+        _assert_same("A[%d]" % k, smp[k].A, ref["A"][k])
+        _assert_same("Q[%d]" % k, smp[k].Q, ref["Q"][k])
+        _assert_same("w_m1[%d]" % k, smp[k].w_m1, ref["w"][k])
+
+
 @pytest.mark.parametrize("model,N,T,K,K_b,k_d", [("known", 30, 150, 4, 6, 2), ("hilbert", 30, 60, 3, 3, 1),
                                                  ("known", 2500, 30, 3, 2, 1), ("hilbert", 300, 25, 2, 2, 1),
                                                  ("known", 1024, 20, 2, 1, 1)])

@@ -156,6 +156,44 @@ def test_mniw_matches_dense_linear_algebra():
     np.testing.assert_allclose(A, Ar, rtol=1e-9, atol=1e-12)
 
 
+def test_mniw_dense_V_matches_dense_linear_algebra():
+    """MNIW_sample takes any V (:56): Sigbar = Sigma + I / V (:64) with a dense symmetric positive definite V — the
+    oracle's I / V (Cholesky + column solves, pgb_math.h) against np.linalg.inv, and the draw against NumPy algebra."""
+    rng = np.random.default_rng(8)
+    n_x, n_phi, Tm1 = 2, 7, 150
+    zeta, z = rng.normal(size=(n_x, Tm1)), rng.normal(size=(n_phi, Tm1))
+    Phi, Psi, Sig = zeta @ zeta.T, zeta @ z.T, z @ z.T
+    B = rng.normal(size=(n_phi, n_phi))
+    V = B @ B.T + 0.5 * np.eye(n_phi)
+    V = 0.5 * (V + V.T)
+    Vinv, rc = O.spd_inverse(V)
+    assert rc == 0
+    np.testing.assert_allclose(Vinv, np.linalg.inv(V), rtol=1e-11, atol=1e-13)
+    np.testing.assert_array_equal(Vinv, Vinv.T)
+    assert O.spd_inverse(-V)[1] == 1                      # not positive definite: PosDefException in the reference
+    Lam, ell = 100 * np.eye(n_x), 10.0
+    s = P.injected_streams(4, 4, n_x, n_phi, 3, df=ell + Tm1 * n_x)
+    st = O.make_streams(philox=False, bartlett=s["bartlett"], Xmn=s["Xmn"])
+    A, Q, rc = O.mniw_sample(n_x, n_phi, Phi, Psi, Sig, V, Lam, ell, Tm1, st, 1)
+    assert rc == 0
+    Sigbar = Sig + np.linalg.inv(V)
+    M = Psi @ np.linalg.inv(Sigbar)
+    covM = Lam + Phi - M @ Psi.T
+    covM = 0.5 * (covM + covM.T)
+    LS = np.linalg.cholesky(np.linalg.inv(covM))
+    Wm = (LS @ s["bartlett"]) @ (LS @ s["bartlett"]).T
+    Qr = np.linalg.inv(Wm)
+    Ar = M + np.linalg.cholesky(Qr) @ s["Xmn"] @ np.linalg.cholesky(np.linalg.inv(Sigbar)).T
+    np.testing.assert_allclose(Q, Qr, rtol=1e-10)
+    np.testing.assert_allclose(A, Ar, rtol=1e-9, atol=1e-12)
+    # a diagonal V through the dense path agrees with the diagonal path to round-off (1/v vs the Cholesky route)
+    Vd = rng.uniform(0.5, 20.0, n_phi)
+    A1, Q1, _ = O.mniw_sample(n_x, n_phi, Phi, Psi, Sig, Vd, Lam, ell, Tm1, st, 1)
+    A2, Q2, _ = O.mniw_sample(n_x, n_phi, Phi, Psi, Sig, np.diag(Vd), Lam, ell, Tm1, st, 1)
+    np.testing.assert_allclose(A2, A1, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(Q2, Q1, rtol=1e-12)
+
+
 def test_mniw_philox_statistics():
     """Philox-driven Q ~ IW(df, Psi): E[Q] = Psi/(df - p - 1)."""
     n_x, n_phi = 2, 5
