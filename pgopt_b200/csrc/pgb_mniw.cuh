@@ -200,72 +200,142 @@ __device__ inline double mt_chi2_dev(uint64_t seed, uint32_t cid, uint32_t sweep
   }
 }
 
-// right-looking Cholesky of an n x n column-major matrix (global or shared memory) by one CTA.  Threads form a
-// 32 x (nth/32) grid: lane = row offset, warp = column offset — no integer division in the inner loops (the 64-bit
-// div / mod per element of the first version cost more than the arithmetic: 1.7 ms of a 2 ms kernel at n = 125).
+// Right-looking Cholesky of an n x n column-major matrix (global or shared memory) by one CTA, in panels of CHOL_PB
+// columns.  Every entry receives the same fma updates in the same (increasing pivot) order as the oracle's unblocked loops
+// — a blocked schedule only changes WHEN an update is applied, never the chain an entry goes through — so the bits are
+// the oracle's.  The first version synchronised the whole CTA three times per pivot (375 barriers per factorisation at
+// n = 125, ~1 100 cycles each with the dependent sqrt / division in between: most of a 1.0 ms kernel).  Now warp 0
+// factors a panel on its own (rows split over the lanes, __syncwarp between the dependent steps) and the CTA meets twice
+// per panel for the trailing update, in which every thread applies the panel's CHOL_PB updates to its entries in order.
+constexpr int CHOL_PB = 8;
 __device__ inline int cta_cholesky(double* A, int n, int* s_fail) {
   const int tid = threadIdx.x, nth = blockDim.x;
   const int lx = tid & 31, wy = tid >> 5, nw = nth >> 5;
-  for (int k = 0; k < n; ++k) {
-    __syncthreads();
-    if (tid == 0) {
-      double d = A[k + n * k];
-      if (!(d > 0.0)) *s_fail = 1;
-      else A[k + n * k] = __dsqrt_rn(d);
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += CHOL_PB) {
+    const int kb = min(CHOL_PB, n - k0);
+    if (wy == 0) {  // panel: columns k0 .. k0+kb-1, rows k0 .. n-1
+      for (int k = k0; k < k0 + kb; ++k) {
+        const double d = A[k + (int64_t)n * k];
+        if (!(d > 0.0)) {  // warp-uniform
+          if (lx == 0) *s_fail = 1;
+          break;
+        }
+        const double sd = __dsqrt_rn(d);
+        __syncwarp();
+        if (lx == 0) A[k + (int64_t)n * k] = sd;
+        for (int i = k + 1 + lx; i < n; i += 32) A[i + (int64_t)n * k] = __ddiv_rn(A[i + (int64_t)n * k], sd);
+        __syncwarp();
+        for (int j = k + 1; j < k0 + kb; ++j) {  // the panel's own trailing columns
+          const double ljk = A[j + (int64_t)n * k];
+          for (int i = j + lx; i < n; i += 32)
+            A[i + (int64_t)n * j] = __fma_rn(-A[i + (int64_t)n * k], ljk, A[i + (int64_t)n * j]);
+        }
+        __syncwarp();
+      }
     }
     __syncthreads();
     if (*s_fail) return 1;
-    const double d = A[k + n * k];
-    for (int i = k + 1 + tid; i < n; i += nth) A[i + n * k] = __ddiv_rn(A[i + n * k], d);
-    __syncthreads();
-    for (int j = k + 1 + wy; j < n; j += nw) {  // trailing update, lower triangle: every entry gets its updates in pivot order
-      const double ljk = A[j + n * k];
-#pragma unroll 4
-      for (int i = j + lx; i < n; i += 32) A[i + n * j] = __fma_rn(-A[i + n * k], ljk, A[i + n * j]);
+    // trailing update: entry (i, j), i >= j >= k0 + kb, gets the panel's kb updates in pivot order
+    for (int j = k0 + kb + wy; j < n; j += nw) {
+      double lj[CHOL_PB];
+#pragma unroll
+      for (int q = 0; q < CHOL_PB; ++q) lj[q] = q < kb ? A[j + (int64_t)n * (k0 + q)] : 0.0;
+      for (int i = j + lx; i < n; i += 32) {
+        double acc = A[i + (int64_t)n * j];
+#pragma unroll
+        for (int q = 0; q < CHOL_PB; ++q)
+          if (q < kb) acc = __fma_rn(-A[i + (int64_t)n * (k0 + q)], lj[q], acc);
+        A[i + (int64_t)n * j] = acc;
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
   for (int j = 1 + wy; j < n; j += nw)
-    for (int i = lx; i < j; i += 32) A[i + n * j] = 0.0;
+    for (int i = lx; i < j; i += 32) A[i + (int64_t)n * j] = 0.0;
   __syncthreads();
   return 0;
 }
 // Index of L[i, j] (i >= j): full column-major n x n, or the lower triangle packed column by column (shared-memory path:
-// the n x n right-hand side block and the packed factor together fit 227 KB up to n = 135)
+// the n x n right-hand side block and the packed factor together fit 227 KB up to n = 135).  row_step(j): the offset from
+// L[i, j] to L[i, j+1].
 struct LIdxFull {
   int n;
   __device__ __forceinline__ int64_t operator()(int i, int j) const { return i + (int64_t)n * j; }
+  __device__ __forceinline__ int row_step(int) const { return n; }
 };
 struct LIdxPacked {
   int n;
   __device__ __forceinline__ int64_t operator()(int i, int j) const { return (int64_t)j * n - ((int64_t)j * (j - 1)) / 2 + (i - j); }
+  __device__ __forceinline__ int row_step(int j) const { return n - j - 1; }
 };
-// Solve (L L') X = B for nrhs right-hand sides stored as columns of B (ld = n), in place.
-// Column sweeps keep every entry's update order identical to the oracle's substitutions.
+// Solve (L L') X = B in place for two blocks of right-hand sides at once: the n1 columns of B1 (post_mean, :67) and the
+// n2 columns of B2, which holds the IDENTITY on entry (left_cov = I / Sigbar, :68).  Right-hand sides are independent:
+// ONE THREAD PER COLUMN walks the oracle's two substitutions on its own (row e divides by L[e,e], then updates the rows
+// below / above in the oracle's order; L[., e] is a broadcast read), SOLVE_CPW columns per warp, no barrier inside.  The
+// first version met with the whole CTA twice per row (1 000 barriers for the two solves); a warp-per-column version was
+// instruction-bound on the one SM a chain's draw runs on (a 35-instruction exact division per row and column executed by
+// 32 lanes for one useful result: 40 % of the kernel's instructions).  Column j of the identity is zero above row j and
+// stays +0 through the forward sweep (0 / piv = +0, fma(-l, +0, +0) = +0), so its forward sweep starts at row j — the
+// same bits with half the work.
+constexpr int SOLVE_CPW = 16, SOLVE_UB = 8;
 template <class IDX>
-__device__ inline void cta_chol_solve(const double* L, IDX ix, int n, double* B, int nrhs) {
+__device__ inline void cta_chol_solve2(const double* L, IDX ix, int n, double* B1, int n1, double* B2, int n2) {
   const int tid = threadIdx.x, nth = blockDim.x;
   const int lx = tid & 31, wy = tid >> 5, nw = nth >> 5;
-  for (int e = 0; e < n; ++e) {  // forward: L y = b
-    __syncthreads();
-    const double piv = L[ix(e, e)];
-    for (int r = tid; r < nrhs; r += nth) B[e + n * r] = __ddiv_rn(B[e + n * r], piv);
-    __syncthreads();
-    for (int r = wy; r < nrhs; r += nw) {
-      const double ber = B[e + n * r];
-#pragma unroll 4
-      for (int d = e + 1 + lx; d < n; d += 32) B[d + n * r] = __fma_rn(-L[ix(d, e)], ber, B[d + n * r]);
+  __syncthreads();
+  const int ntot = n1 + n2;
+  for (int cb = wy * SOLVE_CPW; cb < ntot; cb += nw * SOLVE_CPW) {  // warp-uniform
+    const int c = cb + lx;
+    double* col = nullptr;
+    int start = n;
+    if (lx < SOLVE_CPW) {
+      if (c < n1) { col = B1 + (int64_t)n * c; start = 0; }
+      else if (c < ntot) { col = B2 + (int64_t)n * (c - n1); start = c - n1; }
     }
-  }
-  for (int e = n - 1; e >= 0; --e) {  // backward: L' x = y
-    __syncthreads();
-    const double piv = L[ix(e, e)];
-    for (int r = tid; r < nrhs; r += nth) B[e + n * r] = __ddiv_rn(B[e + n * r], piv);
-    __syncthreads();
-    for (int r = wy; r < nrhs; r += nw) {
-      const double ber = B[e + n * r];
-#pragma unroll 4
-      for (int d = lx; d < e; d += 32) B[d + n * r] = __fma_rn(-L[ix(e, d)], ber, B[d + n * r]);
+    int first = start;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    for (int e = first; e < n; ++e) {  // forward: L y = b
+      const double* Le = L + ix(e, e) - e;   // column e of the factor: Le[d] = L[d, e]
+      const double piv = Le[e];
+      if (e >= start) {
+        const double be = __ddiv_rn(col[e], piv);
+        col[e] = be;
+        int d = e + 1;
+        for (; d + SOLVE_UB <= n; d += SOLVE_UB) {  // loads first, then the stores: nothing waits on a possible alias
+          double l[SOLVE_UB], v[SOLVE_UB];
+#pragma unroll
+          for (int q = 0; q < SOLVE_UB; ++q) { l[q] = Le[d + q]; v[q] = col[d + q]; }
+#pragma unroll
+          for (int q = 0; q < SOLVE_UB; ++q) col[d + q] = __fma_rn(-l[q], be, v[q]);
+        }
+        for (; d < n; ++d) col[d] = __fma_rn(-Le[d], be, col[d]);
+      }
+    }
+    if (col) {
+      for (int e = n - 1; e >= 0; --e) {  // backward: L' x = y
+        const double* Lr = L + ix(e, 0);     // row e of the factor, walked along the columns
+        const double be = __ddiv_rn(col[e], L[ix(e, e)]);
+        col[e] = be;
+        int64_t off = 0;
+        int d = 0;
+        for (; d + SOLVE_UB <= e; d += SOLVE_UB) {
+          double l[SOLVE_UB], v[SOLVE_UB];
+#pragma unroll
+          for (int q = 0; q < SOLVE_UB; ++q) {
+            l[q] = Lr[off];
+            v[q] = col[d + q];
+            off += ix.row_step(d + q);
+          }
+#pragma unroll
+          for (int q = 0; q < SOLVE_UB; ++q) col[d + q] = __fma_rn(-l[q], be, v[q]);
+        }
+        for (; d < e; ++d) {
+          col[d] = __fma_rn(-Lr[off], be, col[d]);
+          off += ix.row_step(d);
+        }
+      }
     }
   }
   __syncthreads();
@@ -273,7 +343,7 @@ __device__ inline void cta_chol_solve(const double* L, IDX ix, int n, double* B,
 
 // bytes of dynamic shared memory the on-chip path of k_mniw needs (0: does not fit, the global-memory path runs)
 __host__ __device__ inline size_t mniw_smem_bytes(int np) {
-  const size_t b = ((size_t)np * np + (size_t)np * (np + 1) / 2) * 8;
+  const size_t b = ((size_t)np * np + (size_t)np * (np + 1) / 2 + (size_t)4 * np) * 8;  // work block, packed factor, n_x <= 4 right-hand sides
   return b <= (size_t)220 * 1024 ? b : 0;
 }
 
@@ -296,7 +366,7 @@ static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md, int use_sm
   double* Lp = mn_sm + pp;                                   // packed factor of Sigbar (on-chip path)
   double* Mp = md.Mpost + (int64_t)chain * nx * np;
   double* Xn = md.Xn + (int64_t)chain * nx * np;
-  double* LX = md.LX + (int64_t)chain * nx * np;
+  double* LX = use_smem ? Lp + (int64_t)np * (np + 1) / 2 : md.LX + (int64_t)chain * nx * np;  // [np x nx] / [nx x np] scratch
   const double* Phi = md.Phi + (int64_t)chain * nx * nx;
   const double* Psi = md.Psi + (int64_t)chain * nx * np;
   const double* Sigma = md.Sigma + chain * pp;
@@ -316,8 +386,9 @@ static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md, int use_sm
     if (tid == 0) atomicOr(&md.status[chain], 16);
     return;
   }
-  // post_mean = Psibar / Sigbar (:67): RHS r = row r of Psi, stored as column r of a np x nx buffer.
-  // Mp is used as that buffer (column-major np x nx), transposed afterwards into LX as scratch.
+  // post_mean = Psibar / Sigbar (:67): RHS r = row r of Psi, stored as column r of a np x nx buffer (LX as scratch,
+  // transposed into Mp afterwards); left_cov = I / Sigbar (:68): np right-hand sides holding the identity.  One joint
+  // solve: the right-hand sides are independent and the warps own whole columns.
   for (int64_t e = tid; e < (int64_t)np * nx; e += nth) {
     int i = (int)(e % np), d = (int)(e / np);
     LX[e] = Psi[d + nx * i];
@@ -328,10 +399,10 @@ static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md, int use_sm
       if (i >= j) Lp[LIdxPacked{np}(i, j)] = Ls[e];
     }
     __syncthreads();
-    cta_chol_solve(Lp, LIdxPacked{np}, np, LX, nx);
-  } else {
-    cta_chol_solve(Ls, LIdxFull{np}, np, LX, nx);
   }
+  for (int64_t e = tid; e < pp; e += nth) Sinv[e] = ((e % np) == (e / np)) ? 1.0 : 0.0;
+  if (use_smem) cta_chol_solve2(Lp, LIdxPacked{np}, np, LX, nx, Sinv, np);
+  else cta_chol_solve2(Ls, LIdxFull{np}, np, LX, nx, Sinv, np);
   for (int64_t e = tid; e < (int64_t)np * nx; e += nth) {
     int i = (int)(e % np), d = (int)(e / np);
     Mp[d + nx * i] = LX[e];
@@ -349,11 +420,7 @@ static __global__ void __launch_bounds__(MNIW_TPB) k_mniw(MniwDev md, int use_sm
     int a = tid % nx, b = tid / nx;
     s_small[1][a + nx * b] = __dmul_rn(0.5, __dadd_rn(s_small[0][a + nx * b], s_small[0][b + nx * a]));
   }
-  // left_cov = I / Sigbar (:68): inverse via np right-hand sides, lower triangle mirrored
-  __syncthreads();
-  for (int64_t e = tid; e < pp; e += nth) Sinv[e] = ((e % np) == (e / np)) ? 1.0 : 0.0;
-  if (use_smem) cta_chol_solve(Lp, LIdxPacked{np}, np, Sinv, np);
-  else cta_chol_solve(Ls, LIdxFull{np}, np, Sinv, np);
+  // the inverse: lower triangle mirrored (LAPACK potri convention, as the oracle)
   for (int64_t e = tid; e < pp; e += nth) {
     int i = (int)(e % np), j = (int)(e / np);
     if (i < j) Sinv[e] = Sinv[j + (int64_t)np * i];
