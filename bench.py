@@ -316,15 +316,31 @@ def run_gpu(args):
             out["cpu_baseline"] = cpu
     eng.close()
     eng = None
-    if rank == 0:
-        if world == 1 and not args.no_secondary:
-            try:
-                out["secondary"] = secondary_measurements(fp64_peak.value)
-            except Exception as e:  # never let the side measurements take the headline line down
-                out["secondary"] = {"error": repr(e)}
-        print(json.dumps(out))
-    if dist:
+    if dist:  # the side measurements below run after every rank has released its GPU: no collective is pending
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+    if rank == 0:
+        if not args.no_secondary:
+            if world == 1:
+                try:
+                    if args.model == "generic":
+                        out["roofline"]["known"] = known_basis_roofline(N, T, max(2, args.steps), f32)
+                    out["roofline"]["resampling_only"] = resampling_only()
+                except Exception as e:
+                    out["roofline"]["known"] = {"error": repr(e)}
+                try:
+                    out["secondary"] = secondary_measurements(fp64_peak.value)
+                except Exception as e:  # never let the side measurements take the headline line down
+                    out["secondary"] = {"error": repr(e)}
+            else:
+                time.sleep(2.0)  # the other ranks are exiting
+                out["secondary"] = {}
+            try:
+                out["secondary"].update(sharded_secondary(world))
+            except Exception as e:
+                out["secondary"]["sharded"] = {"error": repr(e)}
+        print(json.dumps(out))
 
 
 def secondary_measurements(fp64_peak_tflops=None):
@@ -354,11 +370,14 @@ def secondary_measurements(fp64_peak_tflops=None):
         ds.constraint_max(y_min, y_max)
         t_screen = time.perf_counter() - t0
         ms2 = ds.last_ms()
-        t0 = time.perf_counter()
-        ds.dynamics(out["X"][:, 5].reshape(-1), p["u_init"][:, 5], t=5, phi_variant=1)
-        t_dyn = time.perf_counter() - t0
-        kd = C.c_double(0)
-        lib().pgb_dynamics_last_ms(ds._s, C.byref(kd))
+        kd, kd0 = C.c_double(0), C.c_double(0)
+        for rep in range(2):  # the second call is the measured one (first: lazy allocation of the output buffers)
+            t0 = time.perf_counter()
+            ds.dynamics(out["X"][:, 5].reshape(-1), p["u_init"][:, 5], t=5, phi_variant=1)
+            t_dyn = time.perf_counter() - t0
+            lib().pgb_dynamics_last_ms(ds._s, C.byref(kd))
+            ds.dynamics(out["X"][:, 5].reshape(-1), p["u_init"][:, 5], t=5, phi_variant=1, jacobians=False)
+            lib().pgb_dynamics_last_ms(ds._s, C.byref(kd0))
     kms = ms["rollout_kernel_ms"]
     bytes_alg = K * 8 * (n_x * n_phi + n_x * n_x + Np + n_x + 1 + (2 * H + 2) * n_x + 2 * H)
     res["rollout"] = {"workload": "K=%d scenarios x H=%d, n_x=4, n_phi=625 (configs[4] shape, K scaled), device-resident samples" % (K, H),
@@ -367,7 +386,11 @@ def secondary_measurements(fp64_peak_tflops=None):
                       "host_call_ms_rollout_plus_d2h_pinned": 1e3 * min(calls[1:]),
                       "screening_kernel_ms": ms2["screening_kernel_ms"], "screening_host_call_ms": 1e3 * t_screen,
                       "dynamics_jacobians_kernel_ms": kd.value, "dynamics_host_call_ms": 1e3 * t_dyn,
-                      "dynamics_hbm_GBps": K * 8 * (n_x * n_phi + 2 * n_x + n_x * (n_x + 1)) / (kd.value * 1e-3) / 1e9 if kd.value else None}
+                      "dynamics_hbm_GBps": K * 8 * (n_x * n_phi + 2 * n_x + n_x * (n_x + 1)) / (kd.value * 1e-3) / 1e9 if kd.value else None,
+                      "dynamics_state_only_kernel_ms": kd0.value,
+                      "dynamics_state_only_hbm_GBps": K * 8 * (n_x * n_phi + 2 * n_x) / (kd0.value * 1e-3) / 1e9 if kd0.value else None,
+                      "dynamics_note": "k_dynamics_bulk: A_k staged by cp.async.bulk (HBM-bound kernel; K = 2*10^4 here is a short launch, "
+                                       "profiles/r02b_dynamics_bulk_K1e5.json has K = 10^5: 83 % / 99 % of the measured HBM peak)"}
     # FP64 side of the roofline (2 n_x n_phi + ~20 sines + ~780 multiplications ~ 6.6 kflop
     # per scenario-step; AI ~ 12 flop/B, so the FP64 pipe binds before HBM does)
     flops = 6600.0 * K * (H + 1)
@@ -405,6 +428,75 @@ def secondary_measurements(fp64_peak_tflops=None):
     for model in ("known", "generic"):
         ex[model] = {"one_chain": _small_config(model, 1, 10), "256_chains_batched": _small_config(model, 256, 5)}
     res["reference_examples_N30_T2000_pg_sweeps_per_s"] = ex
+    return res
+
+
+def resampling_only():
+    """K3 alone: systematic_resampling (particle_Gibbs.jl:17-34) of N weights into N indices —
+    tile sums, exact sequential-order scan, index search — device time from CUDA events inside the call.  Algorithmic
+    bytes: 8 read (W) + 4 written (Int32 index on the device) per particle."""
+    from pgopt_b200._lib import lib, check
+    peak, _ = measured_peaks()
+    res = {}
+    rng = np.random.default_rng(3)
+    for lg in (20, 22):
+        n = 1 << lg
+        W = rng.uniform(size=n) ** 2
+        idx = np.empty(n, dtype=np.int64)
+        st, ms, best = C.c_int32(0), C.c_double(0), None
+        for rep in range(4):
+            check(lib().pgb_systematic_resampling(C.c_int32(0), W.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int64(n),
+                                                  C.c_double(0.37), idx.ctypes.data_as(C.c_void_p), C.byref(st)))
+            check(lib().pgb_resampling_last_ms(C.byref(ms)))
+            if rep:
+                best = ms.value if best is None else min(best, ms.value)
+        gbs = 12.0 * n / (best * 1e-3) / 1e9
+        res["N=2^%d" % lg] = {"kernel_ms": best, "GBps_algorithmic_12B_per_particle": gbs, "hbm_frac": gbs / peak,
+                              "status": int(st.value), "sorted": bool(np.all(np.diff(idx) >= 0))}
+    return res
+
+
+def known_basis_roofline(N, T, steps, f32):
+    """the HBM-bound variant of the headline (known basis, n_phi = 5): same kernel, same N and T, device-timed"""
+    import pgopt_b200 as pg
+    prob = build_problem("known", T, seed=0)
+    eng = pg.ParticleGibbsEngine(prob["basis"], 1, N, T, n_chains=1, precision="f32" if f32 else "f64")
+    try:
+        eng.set_data(prob["u"], prob["y"])
+        eng.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
+        eng.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
+        eng.set_prior(prob["V"], 100 * np.eye(2), 10.0)
+        eng.set_rng_philox(1234, 0)
+        ms = time_filter(eng, prob, steps, 2)
+    finally:
+        eng.close()
+    peak, _ = measured_peaks()
+    bps = BYTES_PER_PARTICLE_STEP(2, f32)
+    t = float(np.mean(ms)) * 1e-3
+    return {"value": N * (T - 1) / t, "unit": "particle-steps/s", "ms_per_step": 1e3 * t, "achieved": bps * N * (T - 1) / t / 1e9,
+            "frac": bps * N * (T - 1) / t / 1e9 / peak, "algorithmic_bytes_per_particle_step": bps,
+            "workload": "known basis (n_phi = 5), N=%d, T=%d, %s" % (N, T, "f32" if f32 else "f64")}
+
+
+def sharded_secondary(n_gpus):
+    """BASELINE.json configs[3] / configs[4] through pgb_multi_* on the node's n_gpus devices, each as its own bounded
+    `bench.py --workload c4|c5` child process (one process, in-process NCCL; no torch.distributed), so that the driver's
+    scaling run carries the two sharded workloads.  Returns {"c4": line, "c5": line}; a failure or a time-out is
+    reported in place of the line and never touches the headline."""
+    import subprocess
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT",
+                                                             "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE",
+                                                             "TORCHELASTIC_RUN_ID", "TORCHELASTIC_RESTART_COUNT",
+                                                             "TORCHELASTIC_MAX_RESTARTS", "TORCHELASTIC_USE_AGENT_STORE")}
+    res = {}
+    for wl, extra in (("c5", ["--steps", "3", "--warmup", "1"]), ("c4", ["--kept", "4"])):
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", wl, "--gpus", str(n_gpus)] + extra
+        try:
+            r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            res[wl] = json.loads(lines[-1]) if lines else {"error": "rc=%d %s" % (r.returncode, r.stderr[-300:])}
+        except Exception as e:
+            res[wl] = {"error": repr(e)}
     return res
 
 

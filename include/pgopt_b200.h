@@ -168,6 +168,8 @@ int pgb_get_launch_count(pgb_handle* h, int64_t* n);
 /* systematic_resampling(W, N) with rnd = the rand() of :21; idx is 1-based.  *status gets PGB_STATUS_* bits. */
 int pgb_systematic_resampling(int32_t device, const double* W, int64_t n_w, int64_t n_draw, double rnd,
                               int64_t* idx, int32_t* status);
+/* device time of the kernels of the last pgb_systematic_resampling (tile sums + exact scan + index search), CUDA events */
+int pgb_resampling_last_ms(double* kernel_ms);
 /* MNIW_sample(Phi, Psi, Sigma, V, Lambda_Q, ell_Q, T) with the Bartlett factor and the matrix-normal
  * normals injected (bartlett/Xmn non-NULL) or drawn from Philox (seed, sweep_index). */
 int pgb_mniw_sample(int32_t device, int32_t n_x, int32_t n_phi, const double* Phi, const double* Psi,

@@ -34,7 +34,7 @@ EXPORTS = ["pgb_version", "pgb_last_error", "pgb_create", "pgb_destroy", "pgb_se
            "pgb_set_init_dist", "pgb_set_prior", "pgb_set_prior_dense", "pgb_set_state", "pgb_get_state", "pgb_set_rng_philox",
            "pgb_set_rng_injected", "pgb_sweep", "pgb_sweep_filter", "pgb_sweep_mniw", "pgb_particle_gibbs",
            "pgb_get_sample", "pgb_get_history", "pgb_get_stats", "pgb_get_status", "pgb_synchronize",
-           "pgb_systematic_resampling", "pgb_mniw_sample", "pgb_mniw_sample_dense", "pgb_rollout", "pgb_test_prediction", "pgb_scenario_constraint_max", "pgb_scenario_constraint_last_ms", "pgb_rollout_last_ms", "pgb_test_force_fallback", "pgb_test_math", "pgb_test_fp64_peak", "pgb_test_rollout_kernel", "pgb_test_dynamics_kernel",
+           "pgb_systematic_resampling", "pgb_resampling_last_ms", "pgb_mniw_sample", "pgb_mniw_sample_dense", "pgb_rollout", "pgb_test_prediction", "pgb_scenario_constraint_max", "pgb_scenario_constraint_last_ms", "pgb_rollout_last_ms", "pgb_test_force_fallback", "pgb_test_math", "pgb_test_fp64_peak", "pgb_test_rollout_kernel", "pgb_test_dynamics_kernel",
            "pgb_rollout_supplied", "pgb_samples_create", "pgb_samples_destroy", "pgb_samples_last_error", "pgb_samples_set",
            "pgb_samples_get", "pgb_samples_store", "pgb_particle_gibbs_dev", "pgb_samples_draw_xT", "pgb_rollout_dev",
            "pgb_scenarios_get", "pgb_scenario_constraint_max_dev", "pgb_samples_last_ms", "pgb_dynamics_dev", "pgb_dynamics_last_ms", "pgb_host_alloc", "pgb_host_free",

@@ -131,6 +131,7 @@ int pgb_run_filter_tile_persistent(pgb_handle* h) {
 // ------------------------------------------------------------------------------------------------
 // stand-alone helpers
 // ------------------------------------------------------------------------------------------------
+static float g_resampling_ms = 0.f;  // device time of the last pgb_systematic_resampling (sum + exact scan + search)
 __global__ void k_build_one_utab(pgb_utable* ut, int64_t M, double rnd) { pgb_utable_build(ut, M, rnd); }
 
 extern "C" int pgb_systematic_resampling(int32_t device, const double* W, int64_t n_w, int64_t n_draw, double rnd,
@@ -159,11 +160,19 @@ extern "C" int pgb_systematic_resampling(int32_t device, const double* W, int64_
   cudaStream_t s = 0;
   h->stream = s;
   h->fd = fd;
+  cudaEvent_t ev[2];
+  CK(h, cudaEventCreate(&ev[0]));
+  CK(h, cudaEventCreate(&ev[1]));
+  CK(h, cudaEventRecord(ev[0], s));
   k_build_one_utab<<<1, 1, 0, s>>>(d_ut, n_draw, rnd);
   k_tile_sums<<<dim3(ws.nt, 1), TPB, 0, s>>>(ws, d_W);
   launch_scan<1, MODE_INDEX>(h, ws, d_W, d_ut, 1, 0, d_idx, n_draw, 0, 0, nullptr);
   CK(h, cudaGetLastError());
+  CK(h, cudaEventRecord(ev[1], s));
   CK(h, cudaDeviceSynchronize());
+  cudaEventElapsedTime(&g_resampling_ms, ev[0], ev[1]);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
   std::vector<int32_t> t32((size_t)n_draw);
   int st = 0;
   CK(h, cudaMemcpy(t32.data(), d_idx, (size_t)n_draw * 4, cudaMemcpyDeviceToHost));
@@ -175,5 +184,10 @@ extern "C" int pgb_systematic_resampling(int32_t device, const double* W, int64_
     *status = st | (c[0] ? 0x100 : 0);  // bit 8: the serial exact fallback ran
   }
   h->stream = nullptr;
+  return PGB_OK;
+}
+
+extern "C" int pgb_resampling_last_ms(double* kernel_ms) {
+  if (kernel_ms) *kernel_ms = g_resampling_ms;
   return PGB_OK;
 }
