@@ -31,6 +31,8 @@ struct pgb_handle {
   int64_t sweep_index = 1;
   // device
   double *d_u = nullptr, *d_y = nullptr, *d_Q = nullptr, *d_Vdiag = nullptr, *d_LambdaQ = nullptr;
+  // warp-per-chain kernel, Philox mode: the normals / uniforms of a whole sweep drawn ahead of the time loop (pgb_smalln.cu)
+  double *d_Zpre = nullptr, *d_Upre = nullptr, *d_Apre = nullptr;
   double* d_Vinv = nullptr;  // I / V of a dense prior covariance (pgb_set_prior_dense), allocated on first use
   double *d_Z0 = nullptr, *d_Z = nullptr, *d_Ures = nullptr, *d_Uanc = nullptr, *d_Ustar = nullptr;
   double *d_bart = nullptr, *d_Xmn = nullptr;

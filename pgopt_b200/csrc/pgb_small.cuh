@@ -64,13 +64,115 @@ __device__ __forceinline__ SmallRes small_resample(double v, int N, int n_draw, 
   return r;
 }
 
+// The state-independent draws of a sweep — the process-noise normals z[t, n, :] (Philox + Box-Muller: a third of the
+// instructions of a step) and the two uniforms per step — taken off the dependent chain: k_predraw_small fills
+// Zp [nc][T][N][NX], Up / Ap [nc][T] with the very values k_sweep_small would generate in place (same counters, same
+// routines), thousands of threads wide, and the time loop reads them back like injected streams.
+// The two draws of a conditional step — a[t, 1:N-1] = systematic_resampling(w, N-1) (:172) and
+// a[t, N] = systematic_resampling(waN, 1)[1] (:181) — are independent of each other: their tree sums, divisions and
+// sequential prefix walks are interleaved in one pass (three dependent chains side by side instead of two walks one after
+// the other).  Same operations per draw as small_resample; inc_r = 1 / n_draw is loop-invariant and passed in.
+struct SmallPair {
+  int idx_r, status_r;  // resampling: lane i < n_draw receives idx[i]
+  int idx_a, status_a;  // ancestor of slot N (every lane holds the count; lane 0 is the draw)
+};
+__device__ __forceinline__ SmallPair small_resample_pair(double vr, double va, int N, int n_draw, double inc_r, double rnd_r,
+                                                         double rnd_a, double* Wr_s, double* Wa_s, int lane) {
+  SmallPair r;
+  r.status_r = r.status_a = 0;
+  double sr = vr, sa = va;                                 // :19, both draws
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    sr = __dadd_rn(sr, __shfl_xor_sync(0xffffffffu, sr, o));
+    sa = __dadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
+  }
+  const double Wr = (lane < N) ? __ddiv_rn(vr, sr) : 0.0;
+  const double Wa = (lane < N) ? __ddiv_rn(va, sa) : 0.0;
+  if (lane < N && !(Wr >= 0.0 && Wr <= 1.7976931348623157e308)) r.status_r |= 4;
+  if (lane < N && !(Wa >= 0.0 && Wa <= 1.7976931348623157e308)) r.status_a |= 4;
+  __syncwarp();
+  Wr_s[lane] = Wr;
+  Wa_s[lane] = Wa;
+  __syncwarp();
+  double ur = __dmul_rn(inc_r, rnd_r);                     // :21
+  const double ua = __dmul_rn(1.0, rnd_a);                 // n_draw = 1: 1 / 1 = 1
+  double qs[SMALL_MAXN];
+  double qr = 0.0, qa = 0.0;                               // :23
+  int cnt_a = 0;
+  const int nu = (lane < n_draw - 1) ? lane : n_draw - 1;
+#pragma unroll
+  for (int n = 0; n < SMALL_MAXN; ++n) {
+    qs[n] = qr;
+    cnt_a += (qa < ua) ? 1 : 0;                            // the single draw's u never moves: counted on the fly
+    qr = __dadd_rn(qr, Wr_s[n]);
+    qa = __dadd_rn(qa, Wa_s[n]);
+    if (n < nu) ur = __dadd_rn(ur, inc_r);
+  }
+  int cnt = 0;
+#pragma unroll
+  for (int n = 0; n < SMALL_MAXN; ++n) cnt += (qs[n] < ur) ? 1 : 0;
+  if (cnt > N) cnt = N;
+  if (lane < n_draw) {
+    if (cnt == N && qr < ur) r.status_r |= 1;
+    if (cnt == 0) r.status_r |= 2;
+  }
+  r.idx_r = cnt;
+  if (cnt_a > N) cnt_a = N;
+  if (lane < 1) {
+    if (cnt_a == N && qa < ua) r.status_a |= 1;
+    if (cnt_a == 0) r.status_a |= 2;
+  }
+  r.idx_a = cnt_a;
+  return r;
+}
+
+template <int NX>
+__global__ void __launch_bounds__(128) k_predraw_small(const __grid_constant__ FilterDev fd, double* __restrict__ Zp,
+                                                       double* __restrict__ Up, double* __restrict__ Ap, int first) {
+  const int chain = blockIdx.y, lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) + 1;
+  const int N = (int)fd.N;
+  if (t >= fd.T) return;
+  const uint32_t cid = fd.chain_base + chain;
+  if (lane < N) {
+    constexpr int NP = (NX + 1) / 2;
+    pgb_u32x4 ctr[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      ctr[p].v[0] = (uint32_t)(lane * NP + p);
+      ctr[p].v[1] = (uint32_t)t;
+      ctr[p].v[2] = fd.sweep;
+      ctr[p].v[3] = ((uint32_t)PGB_STREAM_Z << 24) | (cid & 0x00ffffffu);
+    }
+    vphilox_wide<NP>(ctr, (uint32_t)fd.seed, (uint32_t)(fd.seed >> 32));
+    double z0[NP], z1[NP];
+    vnormal_pairs_wide<NP>(ctr, z0, z1);
+    double* zo = Zp + (((int64_t)chain * fd.T + t) * N + lane) * NX;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      zo[2 * p] = z0[p];
+      if (2 * p + 1 < NX) zo[2 * p + 1] = z1[p];
+    }
+  }
+  if (lane == 0) {
+    pgb_u32x4 b = pgb_stream_block(fd.seed, PGB_STREAM_URES, cid, fd.sweep, (uint32_t)t, 0);
+    Up[(int64_t)chain * fd.T + t] = pgb_u53_halfopen(b.v[0], b.v[1]);
+    if (!first) {
+      b = pgb_stream_block(fd.seed, PGB_STREAM_UANC, cid, fd.sweep, (uint32_t)t, 0);
+      Ap[(int64_t)chain * fd.T + t] = pgb_u53_halfopen(b.v[0], b.v[1]);
+    }
+  }
+}
+
 template <int NX>
 __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ FilterDev fd, int32_t* __restrict__ star_idx,
-                                                    int first) {
+                                                    int first, const double* __restrict__ Zp,
+                                                    const double* __restrict__ Up, const double* __restrict__ Ap) {
   extern __shared__ __align__(16) double sm_small[];
   double* A_sm = sm_small;                                   // [NX * n_phi]
   double* Fs = A_sm + ((NX * fd.n_phi + 1) & ~1);             // [NX][32]  F of every particle (gather source)
   double* Ws = Fs + NX * 32;                                  // [32]      normalised weights of the running draw
+  double* Ws2 = Ws + 32;                                      // [32]      ... of the ancestor draw (conditional sweeps)
   const int chain = blockIdx.x, lane = threadIdx.x;
   const int N = (int)fd.N;
   const int64_t T = fd.T;
@@ -118,16 +220,31 @@ __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ F
     if (!(lw == lw)) stat |= 4;
   }
 
+  // the per-step scalars (u_{t-1}, y_t, x'_t, the uniforms) are read sequentially in t: lane l < 5 pulls the cache line
+  // of stream l 16 steps ahead into L1 so that no step of this latency-bound loop waits for L2 / HBM (base and stride
+  // per lane fixed here: the first version re-derived five addresses in every step, 14 % of the loop's stall samples)
+  const double* pf_base = nullptr;
+  int64_t pf_stride = 0;
+  {
+    const double* ures = Up ? Up : (fd.philox ? nullptr : fd.Ures);
+    const double* uanc = Ap ? Ap : (fd.philox ? nullptr : fd.Uanc);
+    if (lane == 0) { pf_base = fd.u + (int64_t)fd.n_u * 15; pf_stride = fd.n_u; }
+    else if (lane == 1) { pf_base = fd.y + (int64_t)fd.n_y * 16; pf_stride = fd.n_y; }
+    else if (lane == 2) { pf_base = xprim + NX * 16; pf_stride = NX; }
+    else if (lane == 3 && ures) { pf_base = ures + (int64_t)chain * T + 16; pf_stride = 1; }
+    else if (lane == 4 && uanc) { pf_base = uanc + (int64_t)chain * T + 16; pf_stride = 1; }
+  }
+  const double inc_draw = __ddiv_rn(1.0, (double)(first ? N : N - 1));   // 1 / n_draw of the resampling draw (:21, :31)
   for (int64_t t = 1; t <= T; ++t) {
-    // the per-step scalars (u_{t-1}, y_t, x'_t, injected uniforms) are read sequentially in t: pull the cache line
-    // of 16 steps ahead into L1 so that no step of this latency-bound loop waits for L2 / HBM
-    if (lane < 5 && t + 16 < T) {
-      const void* p = lane == 0 ? (const void*)(fd.u + (int64_t)fd.n_u * (t + 15))
-                    : lane == 1 ? (const void*)(fd.y + (int64_t)fd.n_y * (t + 16))
-                    : lane == 2 ? (const void*)(xprim + NX * (t + 16))
-                    : lane == 3 ? (const void*)(fd.philox ? (const double*)fd.u : fd.Ures + (int64_t)chain * T + t + 16)
-                                : (const void*)(fd.philox ? (const double*)fd.u : fd.Uanc + (int64_t)chain * T + t + 16);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    if (pf_base && t + 16 < T) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf_base + t * pf_stride));
+    // pre-drawn noise of this step: requested now, consumed after the resampling (the whole step hides the latency)
+    double zpre[NX];
+#pragma unroll
+    for (int d = 0; d < NX; ++d) zpre[d] = 0.0;
+    if (Zp && live && t < T) {
+      const double* zin = Zp + (((int64_t)chain * T + t) * N + lane) * NX;
+#pragma unroll
+      for (int d = 0; d < NX; ++d) zpre[d] = zin[d];
     }
     // ---- weights of step t-1 (:198-199): e = exp(lw - max), w = e / sum(e)
     double m = lw;
@@ -163,7 +280,10 @@ __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ F
     const bool anc = !first;
     const double* up = fd.u + (int64_t)fd.n_u * (t - 1);
     double ur, ua = 0.0;
-    if (fd.philox) {
+    if (Up) {
+      ur = Up[(int64_t)chain * T + t];
+      if (anc) ua = Ap[(int64_t)chain * T + t];
+    } else if (fd.philox) {
       pgb_u32x4 b = pgb_stream_block(fd.seed, PGB_STREAM_URES, cid, fd.sweep, (uint32_t)t, 0);
       ur = pgb_u53_halfopen(b.v[0], b.v[1]);
       if (anc) {
@@ -205,6 +325,7 @@ __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ F
     for (int d = 0; d < NX; ++d) Fs[d * 32 + lane] = F[d];
     // ---- ancestor of the conditioned trajectory (:178-181)
     int a_last = 0;
+    double wa_n = 0.0;  // normalised ancestor weight of this lane (:180)
     if (anc) {
       double r[NX], sq = 0.0;
 #pragma unroll
@@ -221,20 +342,31 @@ __global__ void __launch_bounds__(32, 1) k_sweep_small(const __grid_constant__ F
       double wa = live ? __dmul_rn(w, pv[0]) : 0.0;
       const double S3 = warp_tree_sum(wa);                 // :180
       wa = live ? __ddiv_rn(wa, S3) : 0.0;
-      const SmallRes ra = small_resample(wa, N, 1, ua, Ws, lane);   // :181
-      a_last = __shfl_sync(0xffffffffu, ra.idx, 0);
-      stat |= __shfl_sync(0xffffffffu, ra.status, 0) | (ra.status & 4);
+      wa_n = wa;
     }
-    // ---- a[t, 1:n_draw] = systematic_resampling(w[t-1, :], n_draw) (:172 | :185)
+    // ---- a[t, 1:n_draw] = systematic_resampling(w[t-1, :], n_draw) (:172 | :185) and, in a conditional sweep,
+    //      a[t, N] = systematic_resampling(waN, 1)[1] (:181): the two draws walk side by side
     const int n_draw = first ? N : N - 1;
-    const SmallRes rr = small_resample(w, N, n_draw, ur, Ws, lane);
+    SmallRes rr;
+    if (anc) {
+      const SmallPair pr = small_resample_pair(w, wa_n, N, n_draw, inc_draw, ur, ua, Ws, Ws2, lane);
+      rr.idx = pr.idx_r;
+      rr.status = pr.status_r;
+      a_last = __shfl_sync(0xffffffffu, pr.idx_a, 0);
+      stat |= __shfl_sync(0xffffffffu, pr.status_a, 0) | (pr.status_a & 4);
+    } else {
+      rr = small_resample(w, N, n_draw, ur, Ws, lane);
+    }
     stat |= rr.status;
     // ---- x_t = f(x_{t-1}[a]) + L z (:175 | :188); slot N stays the conditioned trajectory (:160)
     int32_t* at = fd.ah + ((int64_t)chain * T + t) * N;
     if (lane < n_draw) {
       const int aj = rr.idx < 1 ? 0 : rr.idx - 1;
       double z[NX];
-      if (fd.philox) {  // the branch-free Philox / Box-Muller routines (same bits as pgb_normal_pair)
+      if (Zp) {
+#pragma unroll
+        for (int d = 0; d < NX; ++d) z[d] = zpre[d];
+      } else if (fd.philox) {  // the branch-free Philox / Box-Muller routines (same bits as pgb_normal_pair)
         constexpr int NP = (NX + 1) / 2;
         pgb_u32x4 ctr[NP];
 #pragma unroll
