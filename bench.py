@@ -566,6 +566,18 @@ def run_c5(args):
             if i >= args.warmup:
                 calls.append(time.perf_counter() - t0)
         ms = m.last_ms()
+        # one stacked-dynamics step + Jacobians on the same sharded samples (pgb_multi_dynamics: no collective)
+        dyn = {}
+        try:
+            xs = np.ascontiguousarray(out["X"][:, 5].reshape(-1))
+            for rep in range(3):
+                t0 = time.perf_counter()
+                _, _, _, kms = m.dynamics(xs, p["u_init"][:, 5], t=5, phi_variant=1)
+                t_dyn = time.perf_counter() - t0
+            dyn = {"kernel_ms_max_over_devices": kms, "host_call_ms": 1e3 * t_dyn,
+                   "hbm_GBps_per_gpu": K / n_dev * 8 * (n_x * p["n_phi"] + 2 * n_x + n_x * (n_x + 1)) / (kms * 1e-3) / 1e9}
+        except Exception as e:
+            dyn = {"error": repr(e)}
     call = float(np.mean(calls))
     bytes_alg = K * 8 * (n_x * p["n_phi"] + n_x * n_x + n_x + 1 + (2 * H + 2) * n_x + 2 * H)
     peak, _ = measured_peaks()
@@ -580,6 +592,7 @@ def run_c5(args):
                      "hbm_GBps_per_gpu": bytes_alg / n_dev / (1e-3 * ms["rollout_kernel_ms_max"]) / 1e9, "hbm_peak_GBps": peak},
         "config": {"workload": "scenario rollout K=%d x H=%d, n_x=4, n_phi=625 (BASELINE.json configs[4]), sharded over %d GPU(s) "
                                "through pgb_multi_rollout" % (K, H, n_dev)},
+        "dynamics_jacobians": dyn,
         "finite": bool(np.isfinite(out["X"]).all())}))
 
 

@@ -319,6 +319,11 @@ int pgb_multi_rollout(pgb_multi* m, int64_t H, const double* C, const double* Le
 /* the gathered scenario arrays as device which_device of the list holds them after pgb_multi_rollout (every device holds
  * all of them: what a solver running on any GPU reads); host outputs may be NULL */
 int pgb_multi_get_scenarios(pgb_multi* m, int32_t which_device, double* x0, double* X, double* Y);
+/* discrete_dynamics[!] and its Jacobians (optimal_control_Altro.jl:79-107, :51; see pgb_dynamics_dev) on the sharded resident
+ * samples: every device evaluates its own scenarios from / into its block of the host arrays (layouts of pgb_dynamics_dev
+ * over all K scenarios); independent scenarios, no collective.  kernel_ms_max (optional): slowest device's kernel. */
+int pgb_multi_dynamics(pgb_multi* m, const double* x_vec, const double* u, int64_t t, int32_t phi_variant, double* x_next,
+                       double* dfdx, double* dfdu, double* kernel_ms_max);
 /* device-side times (CUDA events, ms): NCCL gather of the packed samples; slowest device's rollout kernel; NCCL gather
  * of the scenario arrays */
 int pgb_multi_last_ms(pgb_multi* m, double* sample_gather_ms, double* rollout_kernel_ms_max, double* scenario_gather_ms);

@@ -266,8 +266,12 @@ function particle_Gibbs_multi(u_training, y_training, K, K_b, k_d, N, phi, Lambd
     mcheck(ccall((:pgb_multi_set_measurement, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m[], g.C, Rm))
     mu = Vector{Float64}(mean(x_init_dist)); Lc = Matrix{Float64}(cholesky(Matrix(cov(x_init_dist))).L)
     mcheck(ccall((:pgb_multi_set_init_dist, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m[], mu, Lc))
-    Vd = V isa Diagonal ? Vector{Float64}(V.diag) : Vector{Float64}(diag(V))
-    mcheck(ccall((:pgb_multi_set_prior, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), m[], Vd, Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q)))
+    dense, Vd = prior_V(V)
+    if dense
+        mcheck(ccall((:pgb_multi_set_prior_dense, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), m[], Vd, Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q)))
+    else
+        mcheck(ccall((:pgb_multi_set_prior, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), m[], Vd, Matrix{Float64}(Lambda_Q * I(n_x)), Float64(ell_Q)))
+    end
     mcheck(ccall((:pgb_multi_set_state, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64),
                  m[], -1, Matrix{Float64}(A_init), Matrix{Float64}(Q_init * I(n_x)), C_NULL, 1))
     mcheck(ccall((:pgb_multi_set_rng_philox, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt32), m[], seed, 0))
@@ -308,6 +312,22 @@ function discrete_dynamics_jacobians(samples::Ptr{Cvoid}, x_vec::Vector{Float64}
     rc = ccall((:pgb_dynamics_dev, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                samples, x_vec, u, t, phi_variant, xn, jx, ju)
     rc == 0 || error("pgopt_b200 error $rc: " * unsafe_string(ccall((:pgb_samples_last_error, LIB), Cstring, (Ptr{Cvoid},), samples)))
+    return xn, jx, ju
+end
+
+"""
+    multi_dynamics(m, x_vec, u, t, n_x, n_u; phi_variant=1)  ->  (x_vec_n, dfdx, dfdu)
+
+The same step on the samples a `pgb_multi` handle keeps sharded over its GPUs (after `multi_rollout`): every device
+evaluates its own scenarios from / into its block of the host arrays (`pgb_multi_dynamics`); no collective.
+"""
+function multi_dynamics(m::Ptr{Cvoid}, x_vec::Vector{Float64}, u::Vector{Float64}, t::Integer, n_x, n_u; phi_variant=1)
+    K = div(length(x_vec), n_x)
+    xn = Vector{Float64}(undef, K * n_x); jx = Array{Float64}(undef, n_x, n_x, K); ju = Array{Float64}(undef, n_x, n_u, K)
+    rc = ccall((:pgb_multi_dynamics, LIB), Cint,
+               (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+               m, x_vec, u, t, phi_variant, xn, jx, ju, C_NULL)
+    rc == 0 || error("pgopt_b200 error $rc: " * unsafe_string(ccall((:pgb_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), m)))
     return xn, jx, ju
 end
 

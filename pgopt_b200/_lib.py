@@ -41,7 +41,7 @@ EXPORTS = ["pgb_version", "pgb_last_error", "pgb_create", "pgb_destroy", "pgb_se
            "pgb_multi_create", "pgb_multi_destroy", "pgb_multi_last_error", "pgb_multi_n_devices", "pgb_multi_set_data",
            "pgb_multi_set_measurement", "pgb_multi_set_init_dist", "pgb_multi_set_prior", "pgb_multi_set_prior_dense", "pgb_multi_set_state",
            "pgb_multi_set_rng_philox", "pgb_packed_record_doubles", "pgb_multi_particle_gibbs", "pgb_multi_get_packed",
-           "pgb_multi_get_sample", "pgb_multi_set_samples", "pgb_multi_rollout", "pgb_multi_get_scenarios", "pgb_multi_last_ms",
+           "pgb_multi_get_sample", "pgb_multi_set_samples", "pgb_multi_rollout", "pgb_multi_get_scenarios", "pgb_multi_dynamics", "pgb_multi_last_ms",
            "pgb_samples_pack_bytes", "pgb_samples_pack", "pgb_samples_unpack", "pgb_checkpoint_bytes",
            "pgb_checkpoint_save", "pgb_checkpoint_load",
            "pgb_set_mode", "pgb_timer_start", "pgb_timer_stop", "pgb_profile", "pgb_get_profile", "pgb_get_launch_count"]

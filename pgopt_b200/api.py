@@ -480,6 +480,23 @@ class MultiGPUEngine:
                                          _p(bufs.get("x0")), _p(bufs.get("X")), _p(bufs.get("Y"))))
         return bufs
 
+    def dynamics(self, x_vec, u, t=None, phi_variant=0, jacobians=True):
+        """discrete_dynamics + Jacobians of the stacked scenario model (optimal_control_Altro.jl:79-107, :51) on the sharded
+        resident samples: every device evaluates its own scenarios (see DeviceSamples.dynamics for the layouts).
+        Returns (x_next (K*n_x,), dfdx (K, n_x, n_x), dfdu (K, n_x, n_u), slowest device's kernel ms)."""
+        Kt, nx, nu = self._n_scen, self.n_x, self.n_u
+        xv = np.ascontiguousarray(np.asarray(x_vec, dtype=np.float64).reshape(-1))
+        assert xv.size == Kt * nx
+        xn = np.empty(Kt * nx)
+        jx = np.empty((Kt, nx, nx)) if jacobians else None
+        ju = np.empty((Kt, nu, nx)) if jacobians else None
+        ms = C.c_double(0)
+        self._ck(lib().pgb_multi_dynamics(self._m, _p(xv), _p(_f(np.atleast_1d(u))), C.c_int64(-1 if t is None else int(t)),
+                                          C.c_int32(int(phi_variant)), _p(xn), _p(jx), _p(ju), C.byref(ms)))
+        if not jacobians:
+            return xn, None, None, ms.value
+        return xn, np.transpose(jx, (0, 2, 1)), np.transpose(ju, (0, 2, 1)), ms.value
+
     def scenarios_on(self, which_device, H):
         """the all-gathered x_vec_0 / X / Y as device `which_device` holds them after rollout()"""
         Kt, nx, ny = self._n_scen, self.n_x, self.n_y

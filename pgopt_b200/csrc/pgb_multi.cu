@@ -445,6 +445,38 @@ extern "C" int pgb_multi_rollout(pgb_multi* m, int64_t H, const double* C, const
   return PGB_OK;
 }
 
+// discrete_dynamics[!] + Jacobians of the stacked scenario model (optimal_control_Altro.jl:79-107, :51) on the sharded
+// resident samples: device d evaluates its own scenarios [g0, g0 + gn) from / into its block of the host arrays
+// (x_vec, x_next: [K][n_x]; dfdx: [K][n_x*n_x]; dfdu: [K][n_x*n_u]) — independent scenarios, no collective.  t >= 0 adds
+// the process noise v_vec[:, t+1, k] of the last pgb_multi_rollout.  last_ms: the slowest device's kernel.
+extern "C" int pgb_multi_dynamics(pgb_multi* m, const double* x_vec, const double* u, int64_t t, int32_t phi_variant,
+                                  double* x_next, double* dfdx, double* dfdu, double* kernel_ms_max) {
+  NEEDM(m);
+  if (!m->have_samples) return merr(m, PGB_ERR_STATE, "no samples are resident (pgb_multi_particle_gibbs / pgb_multi_set_samples first)");
+  if (!x_vec || !u || !x_next) return merr(m, PGB_ERR_INVALID, "bad arguments");
+  const size_t nx = (size_t)m->cfg.n_x, nu = (size_t)m->cfg.n_u;
+  int rc = for_each_device(m, [=](pgb_multi_dev& D) -> int {
+    if (!D.S || D.gn == 0) return PGB_OK;
+    const size_t o = (size_t)D.g0;
+    int r = pgb_dynamics_dev(D.S, x_vec + o * nx, u, t, phi_variant, x_next + o * nx, dfdx ? dfdx + o * nx * nx : nullptr,
+                             dfdu ? dfdu + o * nx * nu : nullptr);
+    if (r) pgb_set_err(nullptr, r, "%s", pgb_samples_last_error(D.S));
+    return r;
+  });
+  if (rc) return rc;
+  if (kernel_ms_max) {
+    double mx = 0.0;
+    for (auto& D : m->dev)
+      if (D.S && D.gn) {
+        double v = 0.0;
+        pgb_dynamics_last_ms(D.S, &v);
+        mx = std::max(mx, v);
+      }
+    *kernel_ms_max = mx;
+  }
+  return PGB_OK;
+}
+
 // the gathered scenario arrays as device `which_device` of the list holds them (every device holds all) -> host
 extern "C" int pgb_multi_get_scenarios(pgb_multi* m, int32_t which_device, double* x0, double* X, double* Y) {
   NEEDM(m);

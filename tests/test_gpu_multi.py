@@ -100,3 +100,13 @@ def test_multi_scenario_sharded_rollout():
                 got = m.scenarios_on(d, H)
                 for name in ("x0", "X", "Y"):
                     _assert_same("%s gathered on device %d of %s" % (name, d, devs), got[name], ref[name])
+            # the stacked dynamics step + Jacobians on the sharded samples (optimal_control_Altro.jl:79-107): every device
+            # its own scenarios, with the process noise of the rollout above; == the oracle and == the rollout's next state
+            t = 4
+            xn, jx, ju, ms = m.dynamics(ref["X"][:, t].reshape(-1), u_init[:, t], t=t, phi_variant=0)
+            rx, rjx, rju = O.dynamics(om, A, ref["X"][:, t], u_init[:, t], ref["v"], t, 0)
+            _assert_same("x_next on %s" % devs, xn.reshape(K, n_x), rx)
+            _assert_same("df/dx on %s" % devs, jx, rjx)
+            _assert_same("df/du on %s" % devs, ju, rju)
+            _assert_same("x_next == X[t+1] on %s" % devs, xn.reshape(K, n_x), ref["X"][:, t + 1])
+            assert ms > 0
