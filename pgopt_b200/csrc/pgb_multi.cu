@@ -90,6 +90,7 @@ struct pgb_multi {
   bool have_samples = false, have_scen = false;
   std::string err;
   float gather_ms = 0.f, rollout_gather_ms = 0.f;
+  bool scen_gather_pending = false;  // the all-gather of the last rollout's x_vec_0 / X / Y may still be in flight
   double rollout_kernel_ms_max = 0.0;
 };
 
@@ -123,6 +124,19 @@ static int for_each_device(pgb_multi* m, F fn) {
   return PGB_OK;
 }
 
+// pgb_multi_rollout returns when the host arrays are complete; the NVLink all-gather of the scenario arrays finishes
+// behind it.  Everything that reads the gathered copies or overwrites the gather's sources waits here first.
+static void wait_scenario_gather(pgb_multi* m) {
+  if (!m->scen_gather_pending) return;
+  for (auto& D : m->dev) {
+    cudaSetDevice(D.device);
+    cudaStreamSynchronize(D.stream);
+  }
+  cudaSetDevice(m->dev[0].device);
+  cudaEventElapsedTime(&m->rollout_gather_ms, m->dev[0].ev0, m->dev[0].ev1);
+  m->scen_gather_pending = false;
+}
+
 extern "C" int64_t pgb_packed_record_doubles(int32_t n_x, int32_t n_phi, int32_t n_u) {
   return (int64_t)n_x * n_phi + (int64_t)n_x * n_x + n_x + n_u;
 }
@@ -131,6 +145,7 @@ extern "C" const char* pgb_multi_last_error(const pgb_multi* m) { return m ? m->
 
 extern "C" void pgb_multi_destroy(pgb_multi* m) {
   if (!m) return;
+  wait_scenario_gather(m);
   NcclApi* nc = nccl_api();
   for (auto& D : m->dev) {
     cudaSetDevice(D.device);
@@ -295,6 +310,7 @@ static int all_gather(pgb_multi* m, const std::vector<const double*>& send, cons
 // all-gather of the packed records.  packed (host, may be NULL): [n_chains*K][pgb_packed_record_doubles] in global order.
 extern "C" int pgb_multi_particle_gibbs(pgb_multi* m, int64_t K, int64_t K_b, int64_t k_d, uint64_t roll_seed, double* packed) {
   NEEDM(m);
+  wait_scenario_gather(m);
   if (K < 1) return merr(m, PGB_ERR_INVALID, "bad K");
   int maxnc = 0;
   for (auto& D : m->dev) maxnc = std::max(maxnc, D.nc);
@@ -391,6 +407,7 @@ extern "C" int pgb_multi_rollout(pgb_multi* m, int64_t H, const double* C, const
   NEEDM(m);
   if (!m->have_samples) return merr(m, PGB_ERR_STATE, "pgb_multi_particle_gibbs (or pgb_multi_set_samples) must run first");
   if (seed != m->roll_seed) return merr(m, PGB_ERR_INVALID, "seed differs from the roll_seed the x_T were drawn with");
+  wait_scenario_gather(m);  // the previous gather reads the buffers this rollout overwrites
   const int nx = m->cfg.n_x, ny = m->cfg.n_y;
   const int64_t cap = m->cap;
   int rc = for_each_device(m, [=](pgb_multi_dev& D) -> int {
@@ -405,21 +422,21 @@ extern "C" int pgb_multi_rollout(pgb_multi* m, int64_t H, const double* C, const
         return pgb_set_err(nullptr, PGB_ERR_CUDA, "cudaMalloc of the scenario gather buffers failed");
       D.gH = H;
     }
-    return pgb_rollout_dev(D.S, H, C, Le, u_init, seed, (uint32_t)D.g0, 0, nullptr, nullptr, nullptr);
-  });
-  if (rc) return rc;
-  m->rollout_kernel_ms_max = 0.0;
-  for (auto& D : m->dev) m->rollout_kernel_ms_max = std::max(m->rollout_kernel_ms_max, (double)D.S->last_ms[0]);
-  // host outputs: every device sends ITS OWN block over its own PCIe link (stream2), concurrently with the NVLink gather
-  for (auto& D : m->dev) {
-    cudaSetDevice(D.device);
+    int r = pgb_rollout_dev(D.S, H, C, Le, u_init, seed, (uint32_t)D.g0, 0, nullptr, nullptr, nullptr);
+    if (r) return r;
+    // host outputs: every device sends ITS OWN block over its own PCIe link (stream2) as soon as ITS kernel is done —
+    // not after the slowest device — and concurrently with the NVLink gather below
     const size_t n = (size_t)D.gn, o = (size_t)D.g0;
     cudaError_t e = cudaSuccess;
     if (x0 && e == cudaSuccess) e = cudaMemcpyAsync(x0 + o * nx, D.S->x0, n * nx * 8, cudaMemcpyDeviceToHost, D.stream2);
     if (X && e == cudaSuccess) e = cudaMemcpyAsync(X + o * (H + 1) * nx, D.S->X, n * (H + 1) * nx * 8, cudaMemcpyDeviceToHost, D.stream2);
     if (Y && e == cudaSuccess) e = cudaMemcpyAsync(Y + o * H * ny, D.S->Y, n * H * ny * 8, cudaMemcpyDeviceToHost, D.stream2);
-    if (e != cudaSuccess) return merr(m, PGB_ERR_CUDA, "D2H failed on device %d: %s", D.device, cudaGetErrorString(e));
-  }
+    if (e != cudaSuccess) return pgb_set_err(nullptr, PGB_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(e));
+    return PGB_OK;
+  });
+  if (rc) return rc;
+  m->rollout_kernel_ms_max = 0.0;
+  for (auto& D : m->dev) m->rollout_kernel_ms_max = std::max(m->rollout_kernel_ms_max, (double)D.S->last_ms[0]);
   cudaSetDevice(m->dev[0].device);
   cudaEventRecord(m->dev[0].ev0, m->dev[0].stream);
   struct Arr { double* pgb_multi_dev::*g; double* pgb_samples::*s; size_t per; };
@@ -434,13 +451,12 @@ extern "C" int pgb_multi_rollout(pgb_multi* m, int64_t H, const double* C, const
   }
   cudaSetDevice(m->dev[0].device);
   cudaEventRecord(m->dev[0].ev1, m->dev[0].stream);
+  m->scen_gather_pending = true;  // the gather completes behind the call (wait_scenario_gather)
   for (auto& D : m->dev) {
     cudaSetDevice(D.device);
-    if (cudaStreamSynchronize(D.stream) != cudaSuccess || cudaStreamSynchronize(D.stream2) != cudaSuccess)
-      return merr(m, PGB_ERR_CUDA, "scenario gather / D2H failed on device %d", D.device);
+    if (cudaStreamSynchronize(D.stream2) != cudaSuccess)
+      return merr(m, PGB_ERR_CUDA, "D2H of the scenario arrays failed on device %d", D.device);
   }
-  cudaSetDevice(m->dev[0].device);
-  cudaEventElapsedTime(&m->rollout_gather_ms, m->dev[0].ev0, m->dev[0].ev1);
   m->have_scen = true;
   return PGB_OK;
 }
@@ -481,6 +497,7 @@ extern "C" int pgb_multi_dynamics(pgb_multi* m, const double* x_vec, const doubl
 extern "C" int pgb_multi_get_scenarios(pgb_multi* m, int32_t which_device, double* x0, double* X, double* Y) {
   NEEDM(m);
   if (!m->have_scen) return merr(m, PGB_ERR_STATE, "no rollout has run");
+  wait_scenario_gather(m);
   if (which_device < 0 || which_device >= m->n_dev) return merr(m, PGB_ERR_INVALID, "bad device index %d", which_device);
   const int nx = m->cfg.n_x, ny = m->cfg.n_y;
   const int64_t cap = m->cap, H = m->dev[0].gH;
@@ -502,6 +519,7 @@ extern "C" int pgb_multi_get_scenarios(pgb_multi* m, int32_t which_device, doubl
 extern "C" int pgb_multi_set_samples(pgb_multi* m, int64_t K_total, const double* A, const double* Q, const double* w_m1,
                                      const double* x_m1, const double* u_m1, uint64_t roll_seed) {
   NEEDM(m);
+  wait_scenario_gather(m);
   if (K_total < m->n_dev || !A || !Q || !w_m1 || !x_m1 || !u_m1) return merr(m, PGB_ERR_INVALID, "bad arguments");
   if ((uint64_t)K_total > (1ull << 24)) return merr(m, PGB_ERR_INVALID, "K exceeds the 2^24 Philox stream ids");
   const int nx = m->cfg.n_x, np = m->cfg.n_phi, nu = m->cfg.n_u;
@@ -549,6 +567,7 @@ extern "C" int pgb_multi_set_samples(pgb_multi* m, int64_t K_total, const double
 // of the scenario arrays
 extern "C" int pgb_multi_last_ms(pgb_multi* m, double* sample_gather_ms, double* rollout_kernel_ms_max, double* scenario_gather_ms) {
   NEEDM(m);
+  wait_scenario_gather(m);
   if (sample_gather_ms) *sample_gather_ms = m->gather_ms;
   if (rollout_kernel_ms_max) *rollout_kernel_ms_max = m->rollout_kernel_ms_max;
   if (scenario_gather_ms) *scenario_gather_ms = m->rollout_gather_ms;
