@@ -182,7 +182,7 @@ def run_gpu(args):
     eng.set_measurement(pg.LinearMeasurement([[1.0, 0.0]]), 0.1)
     eng.set_init_dist(pg.MvNormal([2.0, 2.0], 1.0))
     eng.set_prior(prob["V"], 100 * np.eye(2), 10.0)
-    eng.set_rng_philox(1234, rank)
+    eng.set_rng_philox(1234, rank + args.chain_base)
 
     def barrier():
         eng.synchronize()
@@ -205,10 +205,19 @@ def run_gpu(args):
     n1 = C.c_int64(0)
     check(lib().pgb_get_launch_count(eng._h, C.byref(n1)), eng._h)
     t_total = sum(ms) / 1e3
+    per_rank = None
     if dist:
         tt = torch.tensor([t_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_total = float(tt.item())
+        # every rank's own step times and clocks (a single throttled GPU sets the max-over-ranks time: it must be visible)
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"rank": rank, "ms_per_step": [round(v, 2) for v in ms], "sm_mhz": clocks["sm_mhz"],
+                                          "reasons": clocks["reasons"]})
+        clocks = dict(clocks)
+        clocks["reasons"] = sorted({r for p_ in per_rank for r in p_["reasons"]})
+        mhz = [p_["sm_mhz"] for p_ in per_rank if p_["sm_mhz"]]
+        clocks["sm_mhz_min_over_ranks"] = min(mhz) if mhz else None
     psteps = N * (T - 1) * args.steps
     value = world * psteps / t_total
     st, nfb, nscan = eng.status(0, clear=True)
@@ -224,6 +233,11 @@ def run_gpu(args):
     prof = {PROF_NAMES[i]: {"launches": int(launches[i]), "ms": float(pms[i])} for i in range(len(PROF_NAMES))
             if launches[i]}
     tot_prof = sum(v["ms"] for v in prof.values()) or 1.0
+    if dist:  # which kernels every rank actually ran (a shape that does not fit the sweep kernel falls back silently)
+        kr = [None] * world
+        dist.all_gather_object(kr, {k: [v["launches"], round(v["ms"], 2)] for k, v in prof.items()})
+        for p_, k_ in zip(per_rank, kr):
+            p_["kernels"] = k_
     dom = max(prof, key=lambda k: prof[k]["ms"])
     fp64_peak = C.c_double(0)
     check(lib().pgb_test_fp64_peak(local, C.byref(fp64_peak)))
@@ -294,6 +308,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(d2h), "includes": "set_data+set_state H2D, filter+trace+stats+MNIW, get_sample D2H"},
             "gpu_launches": int(n1.value - n0.value),
             "clocks": clocks,
+            "per_rank": per_rank,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_PARTICLE_STEP[args.model] * N * (T - 1) / 1e9 if (N == 2 ** 20 and not f32) else None,
                          "traffic_unit": "GB per launch (ncu DRAM bytes per particle-step of the FP64 kernel at T=24, x this launch's "
@@ -721,6 +736,7 @@ def main():
                          "flat in N: README, profiles/r02_cpu_oracle_rate_vs_N.json)")
     ap.add_argument("--cpu-T", type=int, default=6, help="time steps of the CPU sample (reduced from T = 2000: stated in the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chain-base", type=int, default=0, help="Philox stream id of rank 0's chain (rank r uses chain_base + r)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the bounded rollout / chain-batch side measurements")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "c4", "c5"],
                     help="sweep: the headline CPF-AS sweep (default; the driver's contract).  c4 / c5: BASELINE.json configs[3] / [4] "

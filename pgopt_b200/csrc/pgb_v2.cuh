@@ -531,23 +531,42 @@ __device__ __forceinline__ void v2_counts(const pgb_utable* ut, const double (&q
   }
 }
 
-// serial exact walk by warp 0 of the chain's lead CTA over the dumped normalised weights (fix-up path)
+// serial exact walk by warp 0 of the chain's lead CTA over the dumped normalised weights (fix-up path): q_n = q_{n-1} + W[n]
+// strictly left to right (:28).  The 128 weights of a 32-thread group are staged in shared memory (double-buffered, the next
+// group's loads in flight meanwhile) and every lane walks them redundantly with broadcast reads — one dependent add per
+// element and nothing else on the chain (the first version broadcast each weight with two shuffles from its owner lane and
+// loaded a group only after the previous one was finished: 35 cycles per element, 19 ms per walk at N = 2^20; now ~5 ms).
+// Lane l keeps the value that enters thread t0 + l of the tile layout.
 __device__ __forceinline__ void v2_seq_exact(const double* __restrict__ Wn, double* __restrict__ qin_fb, int64_t N, int nt,
-                                             long long* counters) {
+                                             long long* counters, double* __restrict__ sbuf /* [2][128] shared */) {
   const int lane = threadIdx.x;
   if (lane >= 32) return;
   const int64_t nthr = (int64_t)nt * TPB;
   double q = 0.0;
+  double Wc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) Wc[i] = ((int64_t)lane * 4 + i < N) ? __ldcg(Wn + (int64_t)lane * 4 + i) : 0.0;
   for (int64_t t0 = 0; t0 < nthr; t0 += 32) {
-    const int64_t base = (t0 + lane) * 4;
-    double W[4];
+    double* buf = sbuf + ((t0 >> 5) & 1) * 128;
+    *reinterpret_cast<double2*>(buf + lane * 4) = make_double2(Wc[0], Wc[1]);
+    *reinterpret_cast<double2*>(buf + lane * 4 + 2) = make_double2(Wc[2], Wc[3]);
+    if (t0 + 32 < nthr) {
+      const int64_t base = (t0 + 32 + lane) * 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) W[i] = (base + i < N) ? __ldcg(Wn + base + i) : 0.0;
-    for (int l = 0; l < 32; ++l) {
-      if (lane == l) qin_fb[t0 + l] = q;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) q = __dadd_rn(q, __shfl_sync(0xffffffffu, W[i], l));
+      for (int i = 0; i < 4; ++i) Wc[i] = (base + i < N) ? __ldcg(Wn + base + i) : 0.0;
     }
+    __syncwarp();
+    double mine = 0.0;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) {
+      mine = (lane == l) ? q : mine;
+      const double2 a = *reinterpret_cast<const double2*>(buf + l * 4), b = *reinterpret_cast<const double2*>(buf + l * 4 + 2);
+      q = __dadd_rn(q, a.x);
+      q = __dadd_rn(q, a.y);
+      q = __dadd_rn(q, b.x);
+      q = __dadd_rn(q, b.y);
+    }
+    qin_fb[t0 + lane] = mine;
   }
   if (lane == 0) counters[0] += 1;
 }
@@ -883,6 +902,84 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
     V2_TICK(5);
     v2_grid_barrier(vd.bar, bar_target);  // B3
     V2_TICK(6);
+    // By-output expansion of the offspring counts the lanes left in their TE slots (rr[0..4], zero_upto): the chain's
+    // output slots [J0, J1) of this CTA in pieces of V2_CAP — ancestors scattered into the staging buffer, then every
+    // thread propagates output slots (:175 | :188, :194).  Used by the regular PD phase and by the serial-fallback re-walk
+    // (whose first version expanded by input, one lane walking all offspring of its particle: with the degenerate weights
+    // that cause a record overflow in the first place — one particle holding most of the mass — a single thread emitted
+    // ~N outputs, 450 ms per fallback at N = 2^20; chains whose streams hit two such steps ran 4 x slower).
+    auto expand_pieces = [&](const int J0, const int J1, int* pend, double& lmax) {
+      RT* xt = r_x_row<RT>(fd, chain, t);
+      int32_t* at = fd.ah + ((int64_t)chain * T + t) * N;
+      const RT* Fb = reinterpret_cast<const RT*>(fd.Fbuf) + (int64_t)chain * NX * N;
+      const double* yt = fd.y + (int64_t)fd.n_y * t;
+      const double* zin = fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr;
+      for (int ps = J0; ps < J1; ps += V2_CAP) {
+        const int pe_ = (J1 - ps < V2_CAP) ? J1 : ps + V2_CAP;
+        // (2) scatter: slot jj in [rr[k], rr[k+1]) belongs to particle n0 + k
+        for (int cc = warp; cc < nch; cc += V2_NW) {
+          const int* slot = reinterpret_cast<const int*>(&TE[cc * 32 + lane]);
+          const int n0 = p0 + cc * V2_CHUNK + lane * 4;
+          const int zu = slot[5];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int lo = slot[i], hi = slot[i + 1];
+            if (lo < ps) lo = ps;
+            if (hi > pe_) hi = pe_;
+            const int anc_id = n0 + i;
+            // short ranges by the lane itself, long ones by the whole warp
+            int len = hi - lo;
+            if (len < 0) len = 0;
+            const int mine = len < 8 ? len : 0;
+            for (int j = 0; j < mine; ++j) s_anc[lo + j - ps] = (lo + j < zu) ? -1 : anc_id;
+            unsigned big = __ballot_sync(0xffffffffu, len >= 8);
+            while (big) {
+              const int src = __ffs(big) - 1;
+              big &= big - 1;
+              const int blo = __shfl_sync(0xffffffffu, lo, src), bhi = __shfl_sync(0xffffffffu, hi, src);
+              const int bid = __shfl_sync(0xffffffffu, anc_id, src), bzu = __shfl_sync(0xffffffffu, zu, src);
+              for (int j = blo + lane; j < bhi; j += 32) s_anc[j - ps] = (j < bzu) ? -1 : bid;
+            }
+          }
+        }
+        __syncthreads();
+        V2_TICK(0);
+        // (3) propagate: every thread takes output slots (:175 | :188, :194)
+        const int cnt = pe_ - ps;
+        int a_n = (tid < cnt) ? s_anc[tid] : 0;
+        RT F_n[NX];
+#pragma unroll
+        for (int d = 0; d < NX; ++d) F_n[d] = (tid < cnt) ? __ldcg(Fb + (int64_t)d * N + (a_n < 0 ? 0 : a_n)) : (RT)0.0;
+#pragma unroll 1
+        for (int o = tid; o < cnt; o += V2_NT) {
+          const int jj = ps + o;
+          const int a0 = a_n;
+          RT F[NX], z[NX], x[NX];
+#pragma unroll
+          for (int d = 0; d < NX; ++d) F[d] = F_n[d];
+          if (o + V2_NT < cnt) {  // the gathered F of the next slot is in flight while this one is propagated
+            a_n = s_anc[o + V2_NT];
+#pragma unroll
+            for (int d = 0; d < NX; ++d) F_n[d] = __ldcg(Fb + (int64_t)d * N + (a_n < 0 ? 0 : a_n));
+          }
+          r_normals<NX>(fd, stream_z, (uint32_t)t, jj, zin, z);
+#pragma unroll
+          for (int d = 0; d < NX; ++d) {
+            RT acc = (RT)0.0;
+#pragma unroll
+            for (int e = 0; e <= d; ++e) acc = rfma(Lq[d + NX * e], z[e], acc);
+            x[d] = radd(F[d], acc);
+            xt[(int64_t)d * N + jj] = x[d];
+          }
+          at[jj] = a0;
+          const RT lw = r_log_weight<NX>(fd, x, yt, ivR);
+          lwg[jj] = lw;
+          lmax = fmax(lmax, (double)lw);
+          if (!(lw == lw)) atomicOr(pend, 4);
+        }
+        __syncthreads();
+      }
+    };
     // ================================================================ PD: resolve, exact prefixes, expansion; side shortcut
     {
       {  // the step's sampling grid -> shared memory; issued first so that its L2 latency hides behind the resolve
@@ -934,71 +1031,7 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
           const RT* Fb = reinterpret_cast<const RT*>(fd.Fbuf) + (int64_t)chain * NX * N;
           const double* yt = fd.y + (int64_t)fd.n_y * t;
           const double* zin = fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr;
-          for (int ps = J0; ps < J1; ps += V2_CAP) {
-            const int pe_ = (J1 - ps < V2_CAP) ? J1 : ps + V2_CAP;
-            // (2) scatter: slot jj in [rr[k], rr[k+1]) belongs to particle n0 + k
-            for (int cc = warp; cc < nch; cc += V2_NW) {
-              const int* slot = reinterpret_cast<const int*>(&TE[cc * 32 + lane]);
-              const int n0 = p0 + cc * V2_CHUNK + lane * 4;
-              const int zu = slot[5];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                int lo = slot[i], hi = slot[i + 1];
-                if (lo < ps) lo = ps;
-                if (hi > pe_) hi = pe_;
-                const int anc_id = n0 + i;
-                // short ranges by the lane itself, long ones by the whole warp
-                int len = hi - lo;
-                if (len < 0) len = 0;
-                const int mine = len < 8 ? len : 0;
-                for (int j = 0; j < mine; ++j) s_anc[lo + j - ps] = (lo + j < zu) ? -1 : anc_id;
-                unsigned big = __ballot_sync(0xffffffffu, len >= 8);
-                while (big) {
-                  const int src = __ffs(big) - 1;
-                  big &= big - 1;
-                  const int blo = __shfl_sync(0xffffffffu, lo, src), bhi = __shfl_sync(0xffffffffu, hi, src);
-                  const int bid = __shfl_sync(0xffffffffu, anc_id, src), bzu = __shfl_sync(0xffffffffu, zu, src);
-                  for (int j = blo + lane; j < bhi; j += 32) s_anc[j - ps] = (j < bzu) ? -1 : bid;
-                }
-              }
-            }
-            __syncthreads();
-            V2_TICK(0);
-            // (3) propagate: every thread takes output slots (:175 | :188, :194)
-            const int cnt = pe_ - ps;
-            int a_n = (tid < cnt) ? s_anc[tid] : 0;
-            RT F_n[NX];
-#pragma unroll
-            for (int d = 0; d < NX; ++d) F_n[d] = (tid < cnt) ? __ldcg(Fb + (int64_t)d * N + (a_n < 0 ? 0 : a_n)) : (RT)0.0;
-#pragma unroll 1
-            for (int o = tid; o < cnt; o += V2_NT) {
-              const int jj = ps + o;
-              const int a0 = a_n;
-              RT F[NX], z[NX], x[NX];
-#pragma unroll
-              for (int d = 0; d < NX; ++d) F[d] = F_n[d];
-              if (o + V2_NT < cnt) {  // the gathered F of the next slot is in flight while this one is propagated
-                a_n = s_anc[o + V2_NT];
-#pragma unroll
-                for (int d = 0; d < NX; ++d) F_n[d] = __ldcg(Fb + (int64_t)d * N + (a_n < 0 ? 0 : a_n));
-              }
-              r_normals<NX>(fd, stream_z, (uint32_t)t, jj, zin, z);
-#pragma unroll
-              for (int d = 0; d < NX; ++d) {
-                RT acc = (RT)0.0;
-#pragma unroll
-                for (int e = 0; e <= d; ++e) acc = rfma(Lq[d + NX * e], z[e], acc);
-                x[d] = radd(F[d], acc);
-                xt[(int64_t)d * N + jj] = x[d];
-              }
-              at[jj] = a0;
-              const RT lw = r_log_weight<NX>(fd, x, yt, ivR);
-              lwg[jj] = lw;
-              lmax = fmax(lmax, (double)lw);
-              if (!(lw == lw)) atomicOr(pend, 4);
-            }
-            __syncthreads();
-          }
+          expand_pieces(J0, J1, pend, lmax);
           if (ANC && lead && tid == 0) {  // the conditioned trajectory keeps slot N-1 (:160)
             RT x[NX];
 #pragma unroll
@@ -1124,7 +1157,8 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
               (pass == 0 ? fd.main.pend : fd.side.pend)[chain] = 0;
               if (pass == 0 && !last_only) fd.maxkey[chain] = 0ull;
             }
-            v2_seq_exact(Wn, qfb, N, nt, (pass == 0 ? fd.main.counters : fd.side.counters) + 2 * chain);
+            v2_seq_exact(Wn, qfb, N, nt, (pass == 0 ? fd.main.counters : fd.side.counters) + 2 * chain,
+                         reinterpret_cast<double*>(s_anc));  // the staging buffer is idle here
           }
           v2_grid_barrier(vd.bar, bar_target);
           if (mine) {
@@ -1151,38 +1185,18 @@ k_sweep_v2(const __grid_constant__ FilterDev fd, const __grid_constant__ V2Dev v
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                   if (n0 + i < N && rr[i + 1] > rr[i]) *iout = (rr[i] < zu) ? -1 : n0 + i;
-              } else {  // by-input expansion (rare path: simplicity over balance)
-                RT* xt = r_x_row<RT>(fd, chain, t);
-                int32_t* at = fd.ah + ((int64_t)chain * T + t) * N;
-                const RT* Fb = reinterpret_cast<const RT*>(fd.Fbuf) + (int64_t)chain * NX * N;
-                const double* yt = fd.y + (int64_t)fd.n_y * t;
-                const double* zin = fd.Z ? fd.Z + ((int64_t)chain * T + t) * NX * N : nullptr;
-#pragma unroll 1
-                for (int i = 0; i < 4; ++i) {
-                  const int n = n0 + i;
-                  if (n >= N || rr[i + 1] <= rr[i]) continue;
-                  RT F[NX];
+              } else {  // counts into the lane's TE slot, expanded by output below (balanced over the CTA)
+                int* slot = reinterpret_cast<int*>(&TE[cc * 32 + lane]);
 #pragma unroll
-                  for (int d = 0; d < NX; ++d) F[d] = __ldcg(Fb + (int64_t)d * N + n);
-                  for (int jj = rr[i]; jj < rr[i + 1]; ++jj) {
-                    RT z[NX], x[NX];
-                    r_normals<NX>(fd, stream_z, (uint32_t)t, jj, zin, z);
-#pragma unroll
-                    for (int d = 0; d < NX; ++d) {
-                      RT acc = (RT)0.0;
-#pragma unroll
-                      for (int e = 0; e <= d; ++e) acc = rfma(Lq[d + NX * e], z[e], acc);
-                      x[d] = radd(F[d], acc);
-                      xt[(int64_t)d * N + jj] = x[d];
-                    }
-                    at[jj] = (jj < zu) ? -1 : n;
-                    const RT lw = r_log_weight<NX>(fd, x, yt, ivR);
-                    lwg[jj] = lw;
-                    lmax = fmax(lmax, (double)lw);
-                    if (!(lw == lw)) atomicOr(&fd.status[chain], 4);
-                  }
-                }
+                for (int i = 0; i < 5; ++i) slot[i] = rr[i];
+                slot[5] = zu;
+                if (cc == 0 && lane == 0) sh.J0 = rr[0];
+                if (cc == nch - 1 && lane == 31) sh.J1 = rr[4];
               }
+            }
+            if (!index_only) {
+              __syncthreads();
+              expand_pieces((int)sh.J0, (int)sh.J1, &fd.status[chain], lmax);
             }
             if (pass == 0 && !last_only) {
               if (ANC && lead && tid == 0) {  // the conditioned trajectory keeps slot N-1 (:160)
