@@ -719,6 +719,11 @@ def run_reference(args):
                 "Julia/src/particle_Gibbs.jl (oracle/pg_oracle.c)"}))
 
 
+# single-GPU side benchmarks kept as scripts, reachable from the one entry point
+SIDE_WORKLOADS = {"small": "bench_small_configs.py", "mid": "bench_mid_n.py", "dynamics": "bench_dynamics.py",
+                  "mniw": "bench_mniw.py", "screening": "bench_screening.py"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -738,9 +743,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chain-base", type=int, default=0, help="Philox stream id of rank 0's chain (rank r uses chain_base + r)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the bounded rollout / chain-batch side measurements")
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "c4", "c5"],
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "c4", "c5"] + sorted(SIDE_WORKLOADS),
                     help="sweep: the headline CPF-AS sweep (default; the driver's contract).  c4 / c5: BASELINE.json configs[3] / [4] "
-                         "sharded over --gpus devices from ONE process through pgb_multi_* (run with plain python)")
+                         "sharded over --gpus devices from ONE process through pgb_multi_* (run with plain python).  "
+                         "small / mid / dynamics / mniw / screening: the single-GPU side benchmarks (scripts/bench_*.py)")
     ap.add_argument("--scenarios", type=int, default=100000)
     ap.add_argument("--chains", type=int, default=64)
     ap.add_argument("--chain-particles", type=int, default=2 ** 16)
@@ -748,7 +754,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.workload == "c5":
+    if args.workload in SIDE_WORKLOADS:
+        import runpy
+        sys.argv = [SIDE_WORKLOADS[args.workload]]
+        runpy.run_path(os.path.join(ROOT, "scripts", SIDE_WORKLOADS[args.workload]), run_name="__main__")
+    elif args.workload == "c5":
         run_c5(args)
     elif args.workload == "c4":
         run_c4(args)
