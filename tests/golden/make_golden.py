@@ -152,6 +152,35 @@ def prediction_case():
                 mean_rmse=np.array(ref["mean_rmse"]))
 
 
+def dynamics_case():
+    """One stacked dynamics step + Jacobians (optimal_control_Altro.jl:79-107, :51) on the rollout fixture's samples, with
+    the rollout's own process noise: state t -> t+1 for both phi roundings, and a dense-V MNIW draw."""
+    g = dict(np.load(os.path.join(HERE, "rollout.npz")))
+    from pgopt_b200.api import HilbertGPBasis
+    hb = HilbertGPBasis([int(c) for c in g["count"]], [float(v) for v in g["L"]])
+    om = O.hilbert_model(4, 1, hb.count, hb.stride, hb.L)
+    t = 4
+    out = {"t": np.array(t)}
+    for variant in (0, 1):
+        xn, jx, ju = O.dynamics(om, g["A"], g["X"][:, t], g["u_init"][:, t], g["v"], t, variant)
+        out["x_next_%d" % variant], out["dfdx_%d" % variant], out["dfdu_%d" % variant] = xn, jx, ju
+    assert np.array_equal(out["x_next_0"], g["X"][:, t + 1])  # the step the rollout iterates
+    # MNIW_sample with a dense prior covariance V (particle_Gibbs.jl:56, :64)
+    rng = np.random.default_rng(77)
+    n_x, n_phi, Tm1 = 2, 9, 120
+    zeta, z = rng.normal(size=(n_x, Tm1)), rng.normal(size=(n_phi, Tm1))
+    B = rng.normal(size=(n_phi, n_phi))
+    V = B @ B.T + 0.5 * np.eye(n_phi)
+    V = 0.5 * (V + V.T)
+    Sig = z @ z.T
+    Sig = 0.5 * (Sig + Sig.T)
+    st = O.make_streams(philox=True, seed=13, chain=2)
+    A, Q, rc = O.mniw_sample(n_x, n_phi, zeta @ zeta.T, zeta @ z.T, Sig, V, 100 * np.eye(n_x), 10.0, Tm1, st, 4)
+    assert rc == 0
+    out.update(mn_Phi=zeta @ zeta.T, mn_Psi=zeta @ z.T, mn_Sigma=Sig, mn_V=V, mn_Tm1=np.array(Tm1), mn_A=A, mn_Q=Q)
+    return out
+
+
 def main():
     save = lambda name, d: np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
     save("resampling", resampling_cases())
@@ -162,6 +191,7 @@ def main():
     save("mniw", mniw_case())
     save("rollout", rollout_case())
     save("prediction", prediction_case())
+    save("dynamics", dynamics_case())
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

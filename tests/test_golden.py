@@ -101,7 +101,87 @@ def test_oracle_reproduces_prediction_fixture():
     assert r["mean_rmse"] == float(gp["mean_rmse"])
 
 
+def _dynamics_inputs():
+    g, gd = load("rollout"), load("dynamics")
+    hb = pg.HilbertGPBasis([int(c) for c in g["count"]], [float(v) for v in g["L"]])
+    return g, gd, hb
+
+
+def test_oracle_reproduces_dynamics_fixture():
+    """stacked dynamics + Jacobians (optimal_control_Altro.jl:79-107, :51) and MNIW_sample with a dense V"""
+    g, gd, hb = _dynamics_inputs()
+    om = O.hilbert_model(4, 1, hb.count, hb.stride, hb.L)
+    t = int(gd["t"])
+    for variant in (0, 1):
+        xn, jx, ju = O.dynamics(om, g["A"], g["X"][:, t], g["u_init"][:, t], g["v"], t, variant)
+        same("x_next", xn, gd["x_next_%d" % variant]); same("dfdx", jx, gd["dfdx_%d" % variant])
+        same("dfdu", ju, gd["dfdu_%d" % variant])
+    same("x_next == X[t+1]", gd["x_next_0"], g["X"][:, t + 1])
+    st = O.make_streams(philox=True, seed=13, chain=2)
+    n_x, n_phi = gd["mn_Psi"].shape
+    A, Q, rc = O.mniw_sample(n_x, n_phi, gd["mn_Phi"], gd["mn_Psi"], gd["mn_Sigma"], gd["mn_V"], 100 * np.eye(n_x), 10.0,
+                             int(gd["mn_Tm1"]), st, 4)
+    assert rc == 0
+    same("A (dense V)", A, gd["mn_A"]); same("Q (dense V)", Q, gd["mn_Q"])
+
+
+def test_oracle_dynamics_matches_numpy():
+    """orc_dynamics against a NumPy statement of x_n[k] = A_k phi(x[k], u) + v[:, t+1, k] with
+    phi_j(z) = prod_k L_k^-1/2 sin(pi j_k (z_k + L_k) / (2 L_k)) (examples/PG_OCP_generic_basis_functions_Altro.jl:204-217) and
+    of its analytic Jacobians (what RobotDynamics.@autodiff derives, :51): values to 1e-12, and the Jacobians also against
+    central differences of the NumPy function."""
+    g, gd, hb = _dynamics_inputs()
+    t = int(gd["t"])
+    count, L, nz, n_x, n_u = hb.count, hb.L, len(hb.count), 4, 1
+    K = g["A"].shape[0]
+    digits = np.array(np.unravel_index(np.arange(hb.n_phi), count)).T      # last augmented dimension fastest
+
+    def phi_and_grad(z):
+        arg = [np.pi * np.arange(1, count[k] + 1) * (z[k] + L[k]) / (2 * L[k]) for k in range(nz)]
+        tk = [np.sin(arg[k]) / np.sqrt(L[k]) for k in range(nz)]
+        dk = [np.cos(arg[k]) * np.pi * np.arange(1, count[k] + 1) / (2 * L[k]) / np.sqrt(L[k]) for k in range(nz)]
+        fac = np.stack([tk[k][digits[:, k]] for k in range(nz)], axis=1)
+        phi = fac.prod(axis=1)
+        grad = np.stack([np.prod(np.delete(fac, k, axis=1), axis=1) * dk[k][digits[:, k]] for k in range(nz)], axis=1)
+        return phi, grad
+
+    for k in range(K):
+        x, u = g["X"][k, t], g["u_init"][:, t]
+        z = np.concatenate([u, x])
+        phi, grad = phi_and_grad(z)
+        np.testing.assert_allclose(gd["x_next_0"][k], g["A"][k] @ phi + g["v"][k, t], rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(gd["dfdu_0"][k], g["A"][k] @ grad[:, :n_u], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(gd["dfdx_0"][k], g["A"][k] @ grad[:, n_u:], rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(gd["x_next_1"][k], gd["x_next_0"][k], rtol=1e-12, atol=1e-13)   # phi_opt rounding only
+        eps = 1e-6
+        for c in range(nz):
+            zp, zm = z.copy(), z.copy()
+            zp[c] += eps
+            zm[c] -= eps
+            fd = g["A"][k] @ (phi_and_grad(zp)[0] - phi_and_grad(zm)[0]) / (2 * eps)
+            np.testing.assert_allclose((gd["dfdu_0"][k][:, c] if c < n_u else gd["dfdx_0"][k][:, c - n_u]), fd, rtol=0, atol=5e-8)
+
+
 # ------------------------------------------------------------------------------------------ GPU: CUDA path vs fixtures
+@pytest.mark.gpu
+def test_gpu_reproduces_dynamics_fixture():
+    g, gd, hb = _dynamics_inputs()
+    K, t = g["A"].shape[0], int(gd["t"])
+    batch = pg.PGSampleBatch(g["A"], g["Q"], g["w"], np.transpose(g["x"], (0, 2, 1)), g["um"])
+    with pg.DeviceSamples.from_samples(batch, hb) as ds:
+        sc = ds.rollout(pg.LinearMeasurement(g["Cm"]), 0.1, g["u_init"].shape[1], u_init=g["u_init"], seed=17).scenarios(want=("X", "v"))
+        same("rollout X", sc["X"], g["X"])
+        for variant in (0, 1):
+            xn, jx, ju = ds.dynamics(g["X"][:, t].reshape(-1), g["u_init"][:, t], t=t, phi_variant=variant)
+            same("x_next", xn.reshape(K, 4), gd["x_next_%d" % variant]); same("dfdx", jx, gd["dfdx_%d" % variant])
+            same("dfdu", ju, gd["dfdu_%d" % variant])
+    n_x, n_phi = gd["mn_Psi"].shape
+    A, Q = pg.MNIW_sample(gd["mn_Phi"], gd["mn_Psi"], gd["mn_Sigma"], gd["mn_V"], 100 * np.eye(n_x), 10.0, int(gd["mn_Tm1"]),
+                          seed=13, chain=2, sweep_index=4)
+    same("A (dense V)", A, gd["mn_A"]); same("Q (dense V)", Q, gd["mn_Q"])
+
+
+
 @pytest.mark.gpu
 def test_gpu_reproduces_prediction_fixture():
     g, gp, hb = _prediction_inputs()
